@@ -1,0 +1,206 @@
+/* lpl_b200.h — C ABI of the B200-native LiDAR perception hot path.
+ *
+ * Drop-in boundary for the reference's `lidar_processing_lib` (a C++ class API, see
+ * include/lidar_processing_lib/*.hpp in this repo for the header-only C++ adaptors that keep the
+ * reference's class / enum / struct names). Every entry point takes plain pointers and sizes;
+ * host pointers unless a name ends in `_device`. All functions return 0 on success or a negative
+ * lpl_status; lpl_last_error() gives the text. A context owns one CUDA stream, all device scratch
+ * and pinned staging; like the reference objects it is stateful and not thread-safe (one context
+ * per calling thread / GPU).
+ *
+ * Reference interfaces replaced (paths relative to the reference repository root):
+ *   lpl_ring_partition      Dataloader::addRingInfo            src/dataloader/src/dataloader.cpp:68-137
+ *   lpl_dror_config/filter  NoiseRemover::config / filter      lidar_processing_lib/include/lidar_processing_lib/noise_remover.hpp:56-80
+ *   lpl_segmenter_config    Segmenter::config                  lidar_processing_lib/include/lidar_processing_lib/segmenter.hpp:156
+ *   lpl_segment             Segmenter::segment / image         .../segmenter.hpp:163-169
+ *   lpl_cluster_config      Clusterer::config                  .../clusterer.hpp:79-86
+ *   lpl_cluster             Clusterer::cluster                 .../clusterer.hpp:93-94
+ *   lpl_convex_hull         Polygonizer::convexHull            .../polygonizer.hpp:105-106
+ *   lpl_cluster_hulls       per-label gather + convexHull      src/processor/src/processor.cpp:627-663
+ *   lpl_pipeline_*          Processor::run (segment -> split -> cluster -> hulls), batched
+ *                                                              src/processor/src/processor.cpp:552-663
+ */
+#ifndef LPL_B200_H
+#define LPL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lpl_ctx lpl_ctx;
+
+typedef enum lpl_status
+{
+    LPL_OK = 0,
+    LPL_ERR_INVALID_ARGUMENT = -1, /* std::invalid_argument in the C++ adaptors            */
+    LPL_ERR_CUDA = -2,             /* std::runtime_error                                   */
+    LPL_ERR_CAPACITY = -3,         /* std::overflow_error (more points / voxels than reserved) */
+    LPL_ERR_NO_DEVICE = -4         /* no CUDA device: there is no CPU fallback             */
+} lpl_status;
+
+/* POD mirror of lidar_processing_lib::SegmenterConfiguration (segmenter.hpp:87-112). */
+typedef struct lpl_segmenter_cfg
+{
+    float elevation_up_deg;
+    float elevation_down_deg;
+    int32_t image_width;
+    int32_t image_height;
+    int32_t assume_unorganized_cloud;
+    float grid_radial_spacing_m;
+    float grid_slice_resolution_deg;
+    float ground_height_threshold_m;
+    float road_maximum_slope_m_per_m;
+    float min_distance_m;
+    float max_distance_m;
+    float sensor_height_m;
+    float kernel_threshold_distance_m;
+    float amplification_factor;
+    float z_min_m;
+    float z_max_m;
+} lpl_segmenter_cfg;
+
+/* POD mirror of NoiseRemoverConfiguration (noise_remover.hpp:41-54). */
+typedef struct lpl_dror_cfg
+{
+    float radius_multiplier_m_per_m;
+    float min_search_radius_m;
+    uint32_t min_neighbours;
+} lpl_dror_cfg;
+
+/* POD mirror of ClustererConfiguration (clusterer.hpp:61-68). */
+typedef struct lpl_cluster_cfg
+{
+    float voxel_grid_range_resolution_m;
+    float voxel_grid_azimuth_resolution_deg;
+    float voxel_grid_elevation_resolution_deg;
+    uint32_t min_cluster_size;
+} lpl_cluster_cfg;
+
+/* JCP border behaviour (hazard H2). */
+enum
+{
+    LPL_JCP_AS_REFERENCE = 0, /* reproduce the reference's stale out-of-image kernel slots (default) */
+    LPL_JCP_CLEAN = 1         /* out-of-image slots contribute nothing */
+};
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+/* max_points: capacity per frame (rounded up to a multiple of 2048); max_frames: frames per batch.
+ * image_height/width fix the range-image size the scratch is allocated for (64 x 2048 when 0). */
+int lpl_create(lpl_ctx** out, int device, uint32_t max_points, uint32_t max_frames,
+               int32_t image_height, int32_t image_width);
+void lpl_destroy(lpl_ctx* ctx);
+const char* lpl_last_error(const lpl_ctx* ctx);
+const char* lpl_version(void);
+
+/* ---- configuration (defaults = the reference's struct defaults) ------------------------ */
+void lpl_segmenter_default_cfg(lpl_segmenter_cfg* cfg);
+void lpl_dror_default_cfg(lpl_dror_cfg* cfg);
+void lpl_cluster_default_cfg(lpl_cluster_cfg* cfg);
+int lpl_segmenter_config(lpl_ctx* ctx, const lpl_segmenter_cfg* cfg);
+int lpl_dror_config(lpl_ctx* ctx, const lpl_dror_cfg* cfg);
+int lpl_cluster_config(lpl_ctx* ctx, const lpl_cluster_cfg* cfg);
+int lpl_set_jcp_mode(lpl_ctx* ctx, int mode);
+
+/* ---- single-frame, host-pointer entry points (one per reference entry point) ------------ */
+/* points: n records `stride` bytes apart whose first 12 bytes are float x, y, z (every PCL point
+ * type and std::array<float,3>). */
+int lpl_ring_partition(lpl_ctx* ctx, const void* points, size_t stride, uint32_t n, uint16_t* ring_out);
+
+/* labels_out[n]: 0 = VALID, 1 = NOISE (NoiseRemoverLabel). */
+int lpl_dror_filter(lpl_ctx* ctx, const void* points, size_t stride, uint32_t n, uint8_t* labels_out);
+
+/* ring_offset: byte offset of the uint16 ring field inside a record, or -1 for ring-less point
+ * types (height index from the elevation angle). labels_out[n]: 0 UNKNOWN, 1 GROUND, 2 OBSTACLE
+ * (Label). bgr_image_out: nullable, image_height * image_width * 3 bytes (Segmenter::image()). */
+int lpl_segment(lpl_ctx* ctx, const void* points, size_t stride, int32_t ring_offset, uint32_t n,
+                uint32_t* labels_out, uint8_t* bgr_image_out);
+
+/* labels_out[n]: cluster id or -1 (ClusterLabel); num_clusters_out nullable. */
+int lpl_cluster(lpl_ctx* ctx, const void* points, size_t stride, uint32_t n, int32_t* labels_out,
+                uint32_t* num_clusters_out);
+
+/* Polygonizer::convexHull on n (x, y) doubles `stride` bytes apart; indices_out needs n entries. */
+int lpl_convex_hull(lpl_ctx* ctx, const void* xy, size_t stride, uint32_t n, int32_t* indices_out,
+                    uint32_t* count_out);
+
+/* Gather every cluster (labels 0..num_clusters-1, obstacle-cloud order) and build its hull.
+ * hull_offsets[num_clusters + 1]; hull_indices / hull_xy sized for n vertices (indices into the
+ * input cloud; xy as float pairs); zminmax[num_clusters][2] nullable. */
+int lpl_cluster_hulls(lpl_ctx* ctx, const void* points, size_t stride, const int32_t* labels, uint32_t n,
+                      uint32_t num_clusters, uint32_t* hull_offsets, int32_t* hull_indices,
+                      float* hull_xy, float* zminmax);
+
+/* ---- batched, chained pipeline ----------------------------------------------------------- */
+enum
+{
+    LPL_STAGE_RING = 1,     /* ring partition from point order (else: ring supplied or ring-less) */
+    LPL_STAGE_DROR = 2,     /* DROR filter; only VALID points enter segmentation */
+    LPL_STAGE_SEGMENT = 4,
+    LPL_STAGE_CLUSTER = 8,  /* on OBSTACLE points, cloud order */
+    LPL_STAGE_HULLS = 16,
+    LPL_STAGE_ALL = 31
+};
+
+/* One frame of input: n points of 4 floats (x, y, z, unused), contiguous. */
+typedef struct lpl_frame
+{
+    const float* xyzw;    /* host (or device for the *_device call) pointer, 16 B per point */
+    uint32_t n;
+    const uint16_t* ring; /* nullable; ignored when LPL_STAGE_RING is set */
+} lpl_frame;
+
+/* Upload a batch into the context's device buffers (async on the context stream). */
+int lpl_pipeline_upload(lpl_ctx* ctx, const lpl_frame* frames, uint32_t num_frames);
+/* Same, from device-resident frames (device-to-device copies). */
+int lpl_pipeline_upload_device(lpl_ctx* ctx, const lpl_frame* frames, uint32_t num_frames);
+/* Enqueue the selected stages for the uploaded batch (async). */
+int lpl_pipeline_run(lpl_ctx* ctx, uint32_t num_frames, uint32_t stages);
+/* Wait for the stream; fails if any kernel raised a capacity flag. */
+int lpl_pipeline_sync(lpl_ctx* ctx, uint32_t num_frames);
+
+/* Per-frame results of the last batch (host buffers, any pointer may be NULL to skip).
+ * Copies are synchronous with respect to the context stream. */
+typedef struct lpl_frame_result
+{
+    uint8_t* noise;           /* [n] DROR labels                                   */
+    uint16_t* ring;           /* [n]                                               */
+    uint32_t* labels;         /* [n] segmentation Label per input point            */
+    uint32_t* obstacle_index; /* [num_obstacles] input index of each obstacle point */
+    int32_t* cluster_labels;  /* [num_obstacles]                                   */
+    uint32_t* hull_offsets;   /* [num_clusters + 1]                                */
+    uint32_t* hull_indices;   /* [num_hull_vertices] index into the obstacle cloud */
+    float* hull_xy;           /* [num_hull_vertices][2]                            */
+    float* zminmax;           /* [num_clusters][2]                                 */
+    uint8_t* bgr;             /* [H*W*3] (only if the batch ran with lpl_pipeline_want_image) */
+    /* counts, filled by lpl_pipeline_counts / lpl_pipeline_download */
+    uint32_t n, num_valid, num_obstacles, num_clusters, num_hull_vertices;
+} lpl_frame_result;
+
+int lpl_pipeline_want_image(lpl_ctx* ctx, int enable);
+int lpl_pipeline_counts(lpl_ctx* ctx, uint32_t frame, lpl_frame_result* res);
+int lpl_pipeline_download(lpl_ctx* ctx, uint32_t frame, lpl_frame_result* res);
+
+/* ---- measurement / debugging ------------------------------------------------------------- */
+/* CUDA-event bracket on the context stream. */
+int lpl_timer_start(lpl_ctx* ctx);
+int lpl_timer_stop_ms(lpl_ctx* ctx, float* ms_out);
+/* Kernels launched by this context since the last call with reset != 0. */
+uint64_t lpl_launch_count(lpl_ctx* ctx, int reset);
+/* Intermediates of the last segmentation of `frame` (all nullable): elevation[slices*rings],
+ * plane[4] + best inlier count, counters[8] = {binned, candidates, queued, jcp_rounds,
+ * border_rows, slices, rings, status}. */
+int lpl_debug_segment(lpl_ctx* ctx, uint32_t frame, float* elevation, float* plane,
+                      uint32_t* best_inliers, uint32_t* counters);
+/* Intermediates of the last clustering: dims[3] = num_range, num_azimuth, num_elevation. */
+int lpl_debug_cluster(lpl_ctx* ctx, uint32_t frame, int32_t* dims);
+/* cudaStream_t of the context (as void*), for callers that order their own work after ours. */
+void* lpl_stream(lpl_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* LPL_B200_H */

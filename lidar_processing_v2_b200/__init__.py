@@ -1,0 +1,23 @@
+"""B200-native (sm_100a) implementation of LiDAR-Processing-V2's per-frame perception hot path.
+
+The product is the C-ABI shared library ``liblpl_b200.so`` (include/lpl_b200.h, csrc/*.cu) plus the
+header-only C++ adaptors in include/lidar_processing_lib/. This package holds the in-tree build
+and a thin ctypes binding used by the tests and bench.py.
+"""
+from .build import SO_PATH, build_native  # noqa: F401
+from .native import (  # noqa: F401
+    JCP_AS_REFERENCE,
+    JCP_CLEAN,
+    STAGE_ALL,
+    STAGE_CLUSTER,
+    STAGE_DROR,
+    STAGE_HULLS,
+    STAGE_RING,
+    STAGE_SEGMENT,
+    ClusterCfg,
+    Context,
+    DrorCfg,
+    LplError,
+    SegmenterCfg,
+    load_library,
+)

@@ -1,0 +1,1106 @@
+// C ABI (include/lpl_b200.h): context, configuration, staging and stage orchestration.
+// No torch types, no CPU fallback: every entry point fails with LPL_ERR_NO_DEVICE / LPL_ERR_CUDA
+// when the GPU is not usable.
+#include <cfloat>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <random>
+#include <vector>
+
+#include "../../include/lpl_b200.h"
+#include "common.cuh"
+
+using namespace lpl;
+
+struct lpl_ctx
+{
+    Ctx c;
+    lpl_segmenter_cfg seg_cfg;
+    lpl_dror_cfg dror_cfg;
+    lpl_cluster_cfg clu_cfg;
+    int ncell_cap = 0;
+    int want_image = 0;
+    int jcp_mode = LPL_JCP_AS_REFERENCE;
+    int have_ring = 0; // ring plane of the current batch is meaningful
+    std::vector<std::uint32_t> h_status;
+};
+
+namespace
+{
+constexpr std::size_t kAlign = 256;
+
+struct Carver
+{
+    std::size_t off = 0;
+    char* base = nullptr;
+    template <typename T>
+    void take(T*& p, std::size_t count)
+    {
+        off = (off + kAlign - 1) / kAlign * kAlign;
+        if (base != nullptr)
+        {
+            p = reinterpret_cast<T*>(base + off);
+        }
+        off += count * sizeof(T);
+    }
+};
+
+void carve(Dev& d, Carver& cv, int npx, int ncell_cap, std::uint32_t** mt_raw)
+{
+    const std::size_t B = d.B, cap = d.cap, q = d.qcap, h = d.hcap;
+    cv.take(d.pts_in, B * cap);
+    cv.take(d.n_in, B);
+    cv.take(d.ring, B * cap);
+    cv.take(d.noise, B * cap);
+    cv.take(d.grid_cnt, B * kDrorCells);
+    cv.take(d.grid_start, B * (kDrorCells + 1));
+    cv.take(d.grid_pts, B * cap);
+    cv.take(d.unres, B * cap);
+    cv.take(d.n_unres, B);
+    cv.take(d.pts_v, B * cap);
+    cv.take(d.idx_v, B * cap);
+    cv.take(d.n_v, B);
+    cv.take(d.cell, B * cap);
+    cv.take(d.px, B * cap);
+    cv.take(d.slot, B * cap);
+    cv.take(d.cell_cnt, B * ncell_cap);
+    cv.take(d.cell_start, B * (ncell_cap + 1));
+    cv.take(d.n_binned, B);
+    cv.take(d.order, B * cap);
+    cv.take(d.zsort, B * cap);
+    cv.take(d.cell_zmin, B * ncell_cap);
+    cv.take(d.elev, B * ncell_cap);
+    cv.take(d.lab, B * cap);
+    cv.take(d.cand, B * cap);
+    cv.take(d.n_cand, B);
+    cv.take(d.planes, B * kRansacIters);
+    cv.take(d.inliers, B * kRansacIters);
+    cv.take(d.best_plane, B);
+    cv.take(d.best_cnt, B);
+    cv.take(d.key, B * npx);
+    cv.take(d.pxpt, B * npx);
+    cv.take(d.code, B * npx);
+    cv.take(d.queue, B * q);
+    cv.take(d.n_queue, B);
+    cv.take(d.wn, B * 24 * q);
+    cv.take(d.mk, B * q);
+    cv.take(d.stale_ref, B * d.nborder_cap * 12);
+    cv.take(d.n_border, B);
+    cv.take(d.pend, B * 2 * q);
+    cv.take(d.jcp_rounds, B);
+    cv.take(d.seg_label, B * cap);
+    cv.take(d.labels_out, B * cap);
+    cv.take(d.bgr, B * npx * 3);
+    cv.take(d.pts_o, B * cap);
+    cv.take(d.idx_o, B * cap);
+    cv.take(d.n_o, B);
+    cv.take(d.sph, B * cap);
+    cv.take(d.sph_max, B * 4);
+    cv.take(d.hkey, B * h);
+    cv.take(d.hparent, B * h);
+    cv.take(d.hmin, B * h);
+    cv.take(d.hcount, B * h);
+    cv.take(d.hlabel, B * h);
+    cv.take(d.vslot, B * cap);
+    cv.take(d.clabel, B * cap);
+    cv.take(d.n_clusters, B);
+    cv.take(d.ccount, B * cap);
+    cv.take(d.cstart, B * (cap + 1));
+    cv.take(d.hsk, B * cap);
+    cv.take(d.hsi, B * cap);
+    cv.take(d.hstack, B * 2 * cap);
+    cv.take(d.hcnt, B * cap);
+    cv.take(d.hull_off, B * (cap + 1));
+    cv.take(d.hull_idx, B * cap);
+    cv.take(d.hull_xy, B * cap);
+    cv.take(d.zminmax, B * cap);
+    const std::size_t tl = std::max<std::size_t>(d.tiles, d.ptiles);
+    cv.take(d.tile_cnt, B * tl);
+    cv.take(d.status, B);
+    cv.take(*mt_raw, kMtRaws);
+}
+
+int fail(lpl_ctx* ctx, int code, const char* msg)
+{
+    if (ctx != nullptr)
+    {
+        std::snprintf(ctx->c.err, sizeof(ctx->c.err), "%s", msg);
+    }
+    return code;
+}
+
+#define LPL_TRY(call)                                                                              \
+    do                                                                                             \
+    {                                                                                              \
+        const cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess)                                                                     \
+        {                                                                                          \
+            std::snprintf(ctx->c.err, sizeof(ctx->c.err), "%s:%d %s: %s", __FILE__, __LINE__,      \
+                          #call, cudaGetErrorString(e_));                                          \
+            return LPL_ERR_CUDA;                                                                   \
+        }                                                                                          \
+    } while (0)
+
+int ensure_stage(lpl_ctx* ctx, std::size_t bytes)
+{
+    Ctx& c = ctx->c;
+    if (c.h_stage_bytes >= bytes)
+    {
+        return 0;
+    }
+    if (c.h_stage != nullptr)
+    {
+        LPL_TRY(cudaStreamSynchronize(c.stream));
+        cudaFreeHost(c.h_stage);
+        c.h_stage = nullptr;
+        c.h_stage_bytes = 0;
+    }
+    bytes = (bytes + (1u << 20)) & ~((std::size_t(1) << 20) - 1);
+    LPL_TRY(cudaMallocHost(&c.h_stage, bytes));
+    c.h_stage_bytes = bytes;
+    return 0;
+}
+
+// derived constants, in the reference's own float expressions (segmenter.cpp:42-46,106-109,
+// 121-122,209-211,220-221,359-360,532-533)
+int apply_seg_cfg(lpl_ctx* ctx)
+{
+    const lpl_segmenter_cfg& g = ctx->seg_cfg;
+    SegParams& s = ctx->c.seg;
+    const float kD2R = static_cast<float>(M_PI / 180.0);
+    const float kTwoPi = static_cast<float>(2.0 * M_PI);
+    if (g.image_height != s.H || g.image_width != s.W)
+    {
+        return fail(ctx, LPL_ERR_INVALID_ARGUMENT,
+                    "image_height/image_width differ from the size the context was created for");
+    }
+    if (!(g.grid_radial_spacing_m > 0.f) || !(g.grid_slice_resolution_deg > 0.f))
+    {
+        return fail(ctx, LPL_ERR_INVALID_ARGUMENT, "grid spacing / slice resolution must be positive");
+    }
+    const float slice_res = g.grid_slice_resolution_deg * kD2R;
+    const int rings = static_cast<std::int32_t>(g.max_distance_m / g.grid_radial_spacing_m);
+    const int slices = static_cast<std::int32_t>(kTwoPi / slice_res);
+    if (rings <= 0 || slices <= 0 || static_cast<long long>(rings) * slices > ctx->ncell_cap)
+    {
+        return fail(ctx, LPL_ERR_CAPACITY, "polar grid has no cells or more cells than reserved (262144)");
+    }
+    s.rings = rings;
+    s.slices = slices;
+    s.ncell = rings * slices;
+    s.radial_spacing = g.grid_radial_spacing_m;
+    s.min_dist = g.min_distance_m;
+    s.max_dist = g.max_distance_m;
+    s.slice_res = slice_res;
+    const float el_up = g.elevation_up_deg * kD2R;
+    const float el_down = g.elevation_down_deg * kD2R;
+    const float vfov = el_up - el_down;
+    s.el_down = el_down;
+    s.rad_per_px = vfov / g.image_height;
+    s.z_lo = -g.sensor_height_m + g.z_min_m;
+    s.z_hi = -g.sensor_height_m + g.z_max_m;
+    s.thr = g.ground_height_threshold_m;
+    s.thr2 = 2.0F * g.ground_height_threshold_m;
+    s.delta = std::min(g.grid_radial_spacing_m * std::tan(g.road_maximum_slope_m_per_m),
+                       g.ground_height_threshold_m - std::numeric_limits<float>::epsilon());
+    s.e0 = -g.sensor_height_m + g.ground_height_threshold_m;
+    s.cos_max = std::cos(std::tan(g.road_maximum_slope_m_per_m));
+    s.p1z = -g.sensor_height_m;
+    s.kthr_sqr = g.kernel_threshold_distance_m * g.kernel_threshold_distance_m;
+    s.amp = g.amplification_factor;
+    s.wscale = static_cast<float>(g.image_width - 1);
+    s.jcp_emulate_stale = (ctx->jcp_mode == LPL_JCP_AS_REFERENCE) ? 1 : 0;
+    return 0;
+}
+
+void apply_dror_cfg(lpl_ctx* ctx)
+{
+    // noise_remover.cpp:46-49
+    ctx->c.dror.scaling = std::pow(static_cast<double>(ctx->dror_cfg.radius_multiplier_m_per_m), 2.0);
+    ctx->c.dror.min_r_sqr = ctx->dror_cfg.min_search_radius_m * ctx->dror_cfg.min_search_radius_m;
+    ctx->c.dror.min_neighbours = ctx->dror_cfg.min_neighbours;
+}
+
+void apply_cluster_cfg(lpl_ctx* ctx)
+{
+    // clusterer.hpp:79-86
+    const float kD2R = static_cast<float>(M_PI / 180.0);
+    ctx->c.clu.range_res = ctx->clu_cfg.voxel_grid_range_resolution_m;
+    ctx->c.clu.az_res = ctx->clu_cfg.voxel_grid_azimuth_resolution_deg * kD2R;
+    ctx->c.clu.el_res = ctx->clu_cfg.voxel_grid_elevation_resolution_deg * kD2R;
+    ctx->c.clu.min_cluster_size = ctx->clu_cfg.min_cluster_size;
+}
+
+// pack n strided records (first `take` bytes of each) into pinned staging at `dst`
+void pack(void* dst, std::size_t dst_pitch, const void* src, std::size_t stride, std::size_t take, std::uint32_t n)
+{
+    auto* o = static_cast<char*>(dst);
+    const auto* s = static_cast<const char*>(src);
+    if (stride == take && dst_pitch == take)
+    {
+        std::memcpy(o, s, static_cast<std::size_t>(n) * take);
+        return;
+    }
+    for (std::uint32_t i = 0; i < n; ++i)
+    {
+        std::memcpy(o + i * dst_pitch, s + i * stride, take);
+    }
+}
+
+int check_status(lpl_ctx* ctx, std::uint32_t nf)
+{
+    Ctx& c = ctx->c;
+    ctx->h_status.resize(nf);
+    LPL_TRY(cudaMemcpyAsync(ctx->h_status.data(), c.d.status, sizeof(std::uint32_t) * nf, cudaMemcpyDeviceToHost,
+                            c.stream));
+    LPL_TRY(cudaStreamSynchronize(c.stream));
+    LPL_TRY(cudaGetLastError());
+    for (std::uint32_t f = 0; f < nf; ++f)
+    {
+        const std::uint32_t s = ctx->h_status[f];
+        if (s != 0)
+        {
+            std::snprintf(c.err, sizeof(c.err),
+                          "frame %u exceeded a reserved capacity:%s%s%s%s", f,
+                          (s & ST_QUEUE_OVERFLOW) ? " JCP queue" : "", (s & ST_RNG_EXHAUSTED) ? " RANSAC RNG table" : "",
+                          (s & ST_HASH_FULL) ? " voxel hash" : "", (s & ST_BORDER_OVERFLOW) ? " JCP border rows" : "");
+            return LPL_ERR_CAPACITY;
+        }
+    }
+    return 0;
+}
+
+__global__ void k_label_count(Dev d, std::uint32_t K)
+{
+    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t n = d.n_o[f];
+    const std::uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    if (i >= n)
+    {
+        return;
+    }
+    const std::size_t o = static_cast<std::size_t>(f) * d.cap;
+    const std::int32_t l = d.clabel[o + i];
+    if (l >= 0 && static_cast<std::uint32_t>(l) < K)
+    {
+        atomicAdd(&d.ccount[o + l], 1u);
+    }
+    else
+    {
+        d.clabel[o + i] = -1;
+    }
+}
+} // namespace
+
+extern "C"
+{
+const char* lpl_version(void) { return "lpl_b200 0.1 (sm_100a)"; }
+
+void lpl_segmenter_default_cfg(lpl_segmenter_cfg* g)
+{
+    // segmenter.hpp:87-112
+    g->elevation_up_deg = 2.0F;
+    g->elevation_down_deg = -24.8F;
+    g->image_width = 2048;
+    g->image_height = 64;
+    g->assume_unorganized_cloud = 0;
+    g->grid_radial_spacing_m = 2.0F;
+    g->grid_slice_resolution_deg = 1.0F;
+    g->ground_height_threshold_m = 0.2F;
+    g->road_maximum_slope_m_per_m = 0.2F;
+    g->min_distance_m = 2.0F;
+    g->max_distance_m = 100.0F;
+    g->sensor_height_m = 1.73F;
+    g->kernel_threshold_distance_m = 1.0F;
+    g->amplification_factor = 5.0F;
+    g->z_min_m = -3.0F;
+    g->z_max_m = 4.0F;
+}
+
+void lpl_dror_default_cfg(lpl_dror_cfg* g)
+{
+    // noise_remover.hpp:41-54
+    g->radius_multiplier_m_per_m = 0.02F;
+    g->min_search_radius_m = 0.1F;
+    g->min_neighbours = 4U;
+}
+
+void lpl_cluster_default_cfg(lpl_cluster_cfg* g)
+{
+    // clusterer.hpp:61-68
+    g->voxel_grid_range_resolution_m = 0.4F;
+    g->voxel_grid_azimuth_resolution_deg = 1.0F;
+    g->voxel_grid_elevation_resolution_deg = 1.5F;
+    g->min_cluster_size = 3;
+}
+
+int lpl_create(lpl_ctx** out, int device, std::uint32_t max_points, std::uint32_t max_frames,
+               std::int32_t image_height, std::int32_t image_width)
+{
+    if (out == nullptr || max_points == 0 || max_frames == 0)
+    {
+        return LPL_ERR_INVALID_ARGUMENT;
+    }
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev)
+    {
+        return LPL_ERR_NO_DEVICE;
+    }
+    lpl_ctx* ctx = new (std::nothrow) lpl_ctx();
+    if (ctx == nullptr)
+    {
+        return LPL_ERR_CUDA;
+    }
+    Ctx& c = ctx->c;
+    c.device = device;
+    const int H = image_height > 0 ? image_height : 64;
+    const int W = image_width > 0 ? image_width : 2048;
+    if ((static_cast<long long>(H) * W) % 16 != 0)
+    {
+        delete ctx;
+        return LPL_ERR_INVALID_ARGUMENT;
+    }
+    Dev& d = c.d;
+    d.cap = (max_points + kTile - 1) / kTile * kTile;
+    d.tiles = d.cap / kTile;
+    d.B = max_frames;
+    const int npx = H * W;
+    d.ptiles = (npx + kTile - 1) / kTile;
+    d.qcap = static_cast<std::uint32_t>(npx / 2);
+    std::uint32_t h = 1024;
+    while (h < 2u * d.cap)
+    {
+        h <<= 1;
+    }
+    d.hcap = h;
+    d.nborder_cap = static_cast<std::uint32_t>(4 * W + 4 * H);
+    ctx->ncell_cap = 262144;
+    c.seg.H = H;
+    c.seg.W = W;
+    c.seg.npx = npx;
+    auto bail = [&](int code) {
+        lpl_destroy(ctx);
+        return code;
+    };
+    if (cudaSetDevice(device) != cudaSuccess)
+    {
+        return bail(LPL_ERR_CUDA);
+    }
+    if (cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&c.ev0) != cudaSuccess || cudaEventCreate(&c.ev1) != cudaSuccess)
+    {
+        return bail(LPL_ERR_CUDA);
+    }
+    std::uint32_t* mt_raw = nullptr;
+    Carver measure;
+    carve(d, measure, npx, ctx->ncell_cap, &mt_raw);
+    c.slab_bytes = measure.off + kAlign;
+    if (cudaMalloc(&c.slab, c.slab_bytes) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return bail(LPL_ERR_CAPACITY);
+    }
+    if (cudaMemsetAsync(c.slab, 0, c.slab_bytes, c.stream) != cudaSuccess)
+    {
+        return bail(LPL_ERR_CUDA);
+    }
+    Carver real;
+    real.base = static_cast<char*>(c.slab);
+    carve(d, real, npx, ctx->ncell_cap, &mt_raw);
+    d.mt_raw = mt_raw;
+    // std::mt19937{42} raw stream (segmenter.cpp:369); frame independent
+    {
+        std::vector<std::uint32_t> raws(kMtRaws);
+        std::mt19937 gen{42};
+        for (auto& r : raws)
+        {
+            r = static_cast<std::uint32_t>(gen());
+        }
+        if (cudaMemcpyAsync(mt_raw, raws.data(), sizeof(std::uint32_t) * kMtRaws, cudaMemcpyHostToDevice,
+                            c.stream) != cudaSuccess ||
+            cudaStreamSynchronize(c.stream) != cudaSuccess)
+        {
+            return bail(LPL_ERR_CUDA);
+        }
+    }
+    lpl_segmenter_default_cfg(&ctx->seg_cfg);
+    ctx->seg_cfg.image_height = H;
+    ctx->seg_cfg.image_width = W;
+    lpl_dror_default_cfg(&ctx->dror_cfg);
+    lpl_cluster_default_cfg(&ctx->clu_cfg);
+    if (apply_seg_cfg(ctx) != 0)
+    {
+        return bail(LPL_ERR_INVALID_ARGUMENT);
+    }
+    apply_dror_cfg(ctx);
+    apply_cluster_cfg(ctx);
+    *out = ctx;
+    return LPL_OK;
+}
+
+void lpl_destroy(lpl_ctx* ctx)
+{
+    if (ctx == nullptr)
+    {
+        return;
+    }
+    Ctx& c = ctx->c;
+    cudaSetDevice(c.device);
+    if (c.stream != nullptr)
+    {
+        cudaStreamSynchronize(c.stream);
+    }
+    if (c.slab != nullptr)
+    {
+        cudaFree(c.slab);
+    }
+    if (c.h_stage != nullptr)
+    {
+        cudaFreeHost(c.h_stage);
+    }
+    if (c.ev0 != nullptr)
+    {
+        cudaEventDestroy(c.ev0);
+    }
+    if (c.ev1 != nullptr)
+    {
+        cudaEventDestroy(c.ev1);
+    }
+    if (c.stream != nullptr)
+    {
+        cudaStreamDestroy(c.stream);
+    }
+    delete ctx;
+}
+
+const char* lpl_last_error(const lpl_ctx* ctx) { return ctx != nullptr ? ctx->c.err : "null context"; }
+
+int lpl_segmenter_config(lpl_ctx* ctx, const lpl_segmenter_cfg* cfg)
+{
+    if (ctx == nullptr || cfg == nullptr)
+    {
+        return LPL_ERR_INVALID_ARGUMENT;
+    }
+    const lpl_segmenter_cfg old = ctx->seg_cfg;
+    ctx->seg_cfg = *cfg;
+    const int rc = apply_seg_cfg(ctx);
+    if (rc != 0)
+    {
+        ctx->seg_cfg = old;
+        apply_seg_cfg(ctx);
+    }
+    return rc;
+}
+
+int lpl_dror_config(lpl_ctx* ctx, const lpl_dror_cfg* cfg)
+{
+    if (ctx == nullptr || cfg == nullptr)
+    {
+        return LPL_ERR_INVALID_ARGUMENT;
+    }
+    ctx->dror_cfg = *cfg;
+    apply_dror_cfg(ctx);
+    return LPL_OK;
+}
+
+int lpl_cluster_config(lpl_ctx* ctx, const lpl_cluster_cfg* cfg)
+{
+    if (ctx == nullptr || cfg == nullptr)
+    {
+        return LPL_ERR_INVALID_ARGUMENT;
+    }
+    if (!(cfg->voxel_grid_range_resolution_m > 0.f) || !(cfg->voxel_grid_azimuth_resolution_deg > 0.f) ||
+        !(cfg->voxel_grid_elevation_resolution_deg > 0.f))
+    {
+        return fail(ctx, LPL_ERR_INVALID_ARGUMENT, "voxel resolutions must be positive");
+    }
+    ctx->clu_cfg = *cfg;
+    apply_cluster_cfg(ctx);
+    return LPL_OK;
+}
+
+int lpl_set_jcp_mode(lpl_ctx* ctx, int mode)
+{
+    if (ctx == nullptr || (mode != LPL_JCP_AS_REFERENCE && mode != LPL_JCP_CLEAN))
+    {
+        return LPL_ERR_INVALID_ARGUMENT;
+    }
+    ctx->jcp_mode = mode;
+    ctx->c.seg.jcp_emulate_stale = (mode == LPL_JCP_AS_REFERENCE) ? 1 : 0;
+    return LPL_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// batched pipeline
+// ------------------------------------------------------------------------------------------
+static int upload_impl(lpl_ctx* ctx, const lpl_frame* frames, std::uint32_t nf, bool from_device)
+{
+    if (ctx == nullptr || frames == nullptr || nf == 0 || nf > ctx->c.d.B)
+    {
+        return fail(ctx, LPL_ERR_INVALID_ARGUMENT, "bad frame batch (null, empty or larger than max_frames)");
+    }
+    Ctx& c = ctx->c;
+    Dev& d = c.d;
+    LPL_TRY(cudaSetDevice(c.device));
+    if (ensure_stage(ctx, sizeof(std::uint32_t) * d.B) != 0)
+    {
+        return LPL_ERR_CUDA;
+    }
+    // the counts staging may still be in flight from the previous batch
+    LPL_TRY(cudaStreamSynchronize(c.stream));
+    auto* h_n = static_cast<std::uint32_t*>(c.h_stage);
+    bool any_ring = false;
+    for (std::uint32_t f = 0; f < nf; ++f)
+    {
+        if (frames[f].n > d.cap)
+        {
+            return fail(ctx, LPL_ERR_CAPACITY, "frame has more points than the context was created for");
+        }
+        if (frames[f].n != 0 && frames[f].xyzw == nullptr)
+        {
+            return fail(ctx, LPL_ERR_INVALID_ARGUMENT, "frame without points pointer");
+        }
+        h_n[f] = frames[f].n;
+        any_ring = any_ring || frames[f].ring != nullptr;
+    }
+    const cudaMemcpyKind kind = from_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    LPL_TRY(cudaMemcpyAsync(d.n_in, h_n, sizeof(std::uint32_t) * nf, cudaMemcpyHostToDevice, c.stream));
+    for (std::uint32_t f = 0; f < nf; ++f)
+    {
+        if (frames[f].n == 0)
+        {
+            continue;
+        }
+        LPL_TRY(cudaMemcpyAsync(d.pts_in + static_cast<std::size_t>(f) * d.cap, frames[f].xyzw,
+                                sizeof(float4) * frames[f].n, kind, c.stream));
+        if (frames[f].ring != nullptr)
+        {
+            LPL_TRY(cudaMemcpyAsync(d.ring + static_cast<std::size_t>(f) * d.cap, frames[f].ring,
+                                    sizeof(std::uint16_t) * frames[f].n, kind, c.stream));
+        }
+        else if (any_ring)
+        {
+            LPL_TRY(cudaMemsetAsync(d.ring + static_cast<std::size_t>(f) * d.cap, 0,
+                                    sizeof(std::uint16_t) * frames[f].n, c.stream));
+        }
+    }
+    ctx->have_ring = any_ring ? 1 : 0;
+    return LPL_OK;
+}
+
+int lpl_pipeline_upload(lpl_ctx* ctx, const lpl_frame* frames, std::uint32_t nf)
+{
+    return upload_impl(ctx, frames, nf, false);
+}
+
+int lpl_pipeline_upload_device(lpl_ctx* ctx, const lpl_frame* frames, std::uint32_t nf)
+{
+    return upload_impl(ctx, frames, nf, true);
+}
+
+int lpl_pipeline_run(lpl_ctx* ctx, std::uint32_t nf, std::uint32_t stages)
+{
+    if (ctx == nullptr || nf == 0 || nf > ctx->c.d.B)
+    {
+        return fail(ctx, LPL_ERR_INVALID_ARGUMENT, "bad frame count");
+    }
+    Ctx& c = ctx->c;
+    Dev& d = c.d;
+    LPL_TRY(cudaSetDevice(c.device));
+    LPL_TRY(cudaMemsetAsync(d.status, 0, sizeof(std::uint32_t) * nf, c.stream));
+    const bool ring_stage = (stages & LPL_STAGE_RING) != 0;
+    if (ring_stage)
+    {
+        launch_ring(&c, nf);
+    }
+    else if (!ctx->have_ring)
+    {
+        LPL_TRY(cudaMemsetAsync(d.ring, 0, sizeof(std::uint16_t) * static_cast<std::size_t>(d.cap) * nf, c.stream));
+    }
+    c.seg.use_ring = ((ring_stage || ctx->have_ring) && ctx->seg_cfg.assume_unorganized_cloud == 0) ? 1 : 0;
+    if (stages & LPL_STAGE_DROR)
+    {
+        launch_dror(&c, nf);
+    }
+    if (stages & (LPL_STAGE_SEGMENT | LPL_STAGE_CLUSTER | LPL_STAGE_HULLS))
+    {
+        if (stages & LPL_STAGE_DROR)
+        {
+            launch_take_valid(&c, nf);
+        }
+        else
+        {
+            launch_take_all(&c, nf);
+        }
+    }
+    if (stages & LPL_STAGE_SEGMENT)
+    {
+        launch_segment(&c, nf, ctx->want_image != 0);
+    }
+    if (stages & LPL_STAGE_CLUSTER)
+    {
+        launch_take_obstacles(&c, nf);
+        launch_cluster(&c, nf);
+    }
+    if (stages & LPL_STAGE_HULLS)
+    {
+        launch_hulls(&c, nf);
+    }
+    LPL_TRY(cudaGetLastError());
+    return LPL_OK;
+}
+
+int lpl_pipeline_sync(lpl_ctx* ctx, std::uint32_t nf)
+{
+    if (ctx == nullptr || nf == 0 || nf > ctx->c.d.B)
+    {
+        return LPL_ERR_INVALID_ARGUMENT;
+    }
+    return check_status(ctx, nf);
+}
+
+int lpl_pipeline_want_image(lpl_ctx* ctx, int enable)
+{
+    if (ctx == nullptr)
+    {
+        return LPL_ERR_INVALID_ARGUMENT;
+    }
+    ctx->want_image = enable ? 1 : 0;
+    return LPL_OK;
+}
+
+int lpl_pipeline_counts(lpl_ctx* ctx, std::uint32_t f, lpl_frame_result* r)
+{
+    if (ctx == nullptr || r == nullptr || f >= ctx->c.d.B)
+    {
+        return LPL_ERR_INVALID_ARGUMENT;
+    }
+    Ctx& c = ctx->c;
+    Dev& d = c.d;
+    LPL_TRY(cudaSetDevice(c.device));
+    std::uint32_t v[5] = {0, 0, 0, 0, 0};
+    LPL_TRY(cudaMemcpyAsync(&v[0], d.n_in + f, 4, cudaMemcpyDeviceToHost, c.stream));
+    LPL_TRY(cudaMemcpyAsync(&v[1], d.n_v + f, 4, cudaMemcpyDeviceToHost, c.stream));
+    LPL_TRY(cudaMemcpyAsync(&v[2], d.n_o + f, 4, cudaMemcpyDeviceToHost, c.stream));
+    LPL_TRY(cudaMemcpyAsync(&v[3], d.n_clusters + f, 4, cudaMemcpyDeviceToHost, c.stream));
+    LPL_TRY(cudaStreamSynchronize(c.stream));
+    if (v[3] <= d.cap)
+    {
+        LPL_TRY(cudaMemcpyAsync(&v[4], d.hull_off + static_cast<std::size_t>(f) * (d.cap + 1) + v[3], 4,
+                                cudaMemcpyDeviceToHost, c.stream));
+        LPL_TRY(cudaStreamSynchronize(c.stream));
+    }
+    r->n = v[0];
+    r->num_valid = v[1];
+    r->num_obstacles = v[2];
+    r->num_clusters = v[3];
+    r->num_hull_vertices = v[4];
+    return LPL_OK;
+}
+
+int lpl_pipeline_download(lpl_ctx* ctx, std::uint32_t f, lpl_frame_result* r)
+{
+    const int rc = lpl_pipeline_counts(ctx, f, r);
+    if (rc != 0)
+    {
+        return rc;
+    }
+    Ctx& c = ctx->c;
+    Dev& d = c.d;
+    const std::size_t o = static_cast<std::size_t>(f) * d.cap;
+    const cudaMemcpyKind k = cudaMemcpyDeviceToHost;
+    if (r->noise != nullptr && r->n != 0)
+    {
+        LPL_TRY(cudaMemcpyAsync(r->noise, d.noise + o, r->n, k, c.stream));
+    }
+    if (r->ring != nullptr && r->n != 0)
+    {
+        LPL_TRY(cudaMemcpyAsync(r->ring, d.ring + o, sizeof(std::uint16_t) * r->n, k, c.stream));
+    }
+    if (r->labels != nullptr && r->n != 0)
+    {
+        LPL_TRY(cudaMemcpyAsync(r->labels, d.labels_out + o, sizeof(std::uint32_t) * r->n, k, c.stream));
+    }
+    if (r->obstacle_index != nullptr && r->num_obstacles != 0)
+    {
+        LPL_TRY(cudaMemcpyAsync(r->obstacle_index, d.idx_o + o, sizeof(std::uint32_t) * r->num_obstacles, k, c.stream));
+    }
+    if (r->cluster_labels != nullptr && r->num_obstacles != 0)
+    {
+        LPL_TRY(cudaMemcpyAsync(r->cluster_labels, d.clabel + o, sizeof(std::int32_t) * r->num_obstacles, k, c.stream));
+    }
+    if (r->hull_offsets != nullptr)
+    {
+        LPL_TRY(cudaMemcpyAsync(r->hull_offsets, d.hull_off + static_cast<std::size_t>(f) * (d.cap + 1),
+                                sizeof(std::uint32_t) * (r->num_clusters + 1), k, c.stream));
+    }
+    if (r->hull_indices != nullptr && r->num_hull_vertices != 0)
+    {
+        LPL_TRY(cudaMemcpyAsync(r->hull_indices, d.hull_idx + o, sizeof(std::uint32_t) * r->num_hull_vertices, k, c.stream));
+    }
+    if (r->hull_xy != nullptr && r->num_hull_vertices != 0)
+    {
+        LPL_TRY(cudaMemcpyAsync(r->hull_xy, d.hull_xy + o, sizeof(float2) * r->num_hull_vertices, k, c.stream));
+    }
+    if (r->zminmax != nullptr && r->num_clusters != 0)
+    {
+        LPL_TRY(cudaMemcpyAsync(r->zminmax, d.zminmax + o, sizeof(float2) * r->num_clusters, k, c.stream));
+    }
+    if (r->bgr != nullptr)
+    {
+        LPL_TRY(cudaMemcpyAsync(r->bgr, d.bgr + static_cast<std::size_t>(f) * c.seg.npx * 3,
+                                static_cast<std::size_t>(c.seg.npx) * 3, k, c.stream));
+    }
+    LPL_TRY(cudaStreamSynchronize(c.stream));
+    return LPL_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// single-frame entry points (the reference's per-object calls)
+// ------------------------------------------------------------------------------------------
+static int stage_points(lpl_ctx* ctx, const void* points, std::size_t stride, std::uint32_t n, float4* dst,
+                        std::uint32_t* n_dst, std::int32_t ring_offset)
+{
+    Ctx& c = ctx->c;
+    Dev& d = c.d;
+    if (n > d.cap)
+    {
+        return fail(ctx, LPL_ERR_CAPACITY, "more points than the context was created for");
+    }
+    if (n != 0 && (points == nullptr || stride < 12))
+    {
+        return fail(ctx, LPL_ERR_INVALID_ARGUMENT, "null points or stride < 12 bytes");
+    }
+    LPL_TRY(cudaSetDevice(c.device));
+    const std::size_t need = 64 + static_cast<std::size_t>(n) * 16 + static_cast<std::size_t>(n) * 2;
+    if (ensure_stage(ctx, need) != 0)
+    {
+        return LPL_ERR_CUDA;
+    }
+    LPL_TRY(cudaStreamSynchronize(c.stream));
+    auto* base = static_cast<char*>(c.h_stage);
+    *reinterpret_cast<std::uint32_t*>(base) = n;
+    LPL_TRY(cudaMemcpyAsync(n_dst, base, 4, cudaMemcpyHostToDevice, c.stream));
+    if (n == 0)
+    {
+        return LPL_OK;
+    }
+    char* hp = base + 64;
+    if (stride < 16)
+    {
+        std::memset(hp, 0, static_cast<std::size_t>(n) * 16);
+    }
+    pack(hp, 16, points, stride, stride < 16 ? 12 : 16, n);
+    LPL_TRY(cudaMemcpyAsync(dst, hp, static_cast<std::size_t>(n) * 16, cudaMemcpyHostToDevice, c.stream));
+    if (ring_offset >= 0)
+    {
+        char* hr = hp + static_cast<std::size_t>(n) * 16;
+        pack(hr, 2, static_cast<const char*>(points) + ring_offset, stride, 2, n);
+        LPL_TRY(cudaMemcpyAsync(d.ring, hr, static_cast<std::size_t>(n) * 2, cudaMemcpyHostToDevice, c.stream));
+    }
+    return LPL_OK;
+}
+
+int lpl_ring_partition(lpl_ctx* ctx, const void* points, std::size_t stride, std::uint32_t n, std::uint16_t* ring_out)
+{
+    if (ctx == nullptr || (n != 0 && ring_out == nullptr))
+    {
+        return LPL_ERR_INVALID_ARGUMENT;
+    }
+    Ctx& c = ctx->c;
+    int rc = stage_points(ctx, points, stride, n, c.d.pts_in, c.d.n_in, -1);
+    if (rc != 0 || n == 0)
+    {
+        return rc;
+    }
+    launch_ring(&c, 1);
+    LPL_TRY(cudaMemcpyAsync(ring_out, c.d.ring, sizeof(std::uint16_t) * n, cudaMemcpyDeviceToHost, c.stream));
+    LPL_TRY(cudaStreamSynchronize(c.stream));
+    LPL_TRY(cudaGetLastError());
+    return LPL_OK;
+}
+
+int lpl_dror_filter(lpl_ctx* ctx, const void* points, std::size_t stride, std::uint32_t n, std::uint8_t* labels_out)
+{
+    if (ctx == nullptr || (n != 0 && labels_out == nullptr))
+    {
+        return LPL_ERR_INVALID_ARGUMENT;
+    }
+    Ctx& c = ctx->c;
+    int rc = stage_points(ctx, points, stride, n, c.d.pts_in, c.d.n_in, -1);
+    if (rc != 0 || n == 0)
+    {
+        return rc; // empty cloud: valid no-op (kdtree.hpp:167-170)
+    }
+    launch_dror(&c, 1);
+    LPL_TRY(cudaMemcpyAsync(labels_out, c.d.noise, n, cudaMemcpyDeviceToHost, c.stream));
+    LPL_TRY(cudaStreamSynchronize(c.stream));
+    LPL_TRY(cudaGetLastError());
+    return LPL_OK;
+}
+
+int lpl_segment(lpl_ctx* ctx, const void* points, std::size_t stride, std::int32_t ring_offset, std::uint32_t n,
+                std::uint32_t* labels_out, std::uint8_t* bgr_image_out)
+{
+    if (ctx == nullptr || (n != 0 && labels_out == nullptr))
+    {
+        return LPL_ERR_INVALID_ARGUMENT;
+    }
+    if (ring_offset >= 0 && static_cast<std::size_t>(ring_offset) + 2 > stride)
+    {
+        return fail(ctx, LPL_ERR_INVALID_ARGUMENT, "ring_offset outside the point record");
+    }
+    Ctx& c = ctx->c;
+    Dev& d = c.d;
+    int rc = stage_points(ctx, points, stride, n, d.pts_in, d.n_in, ring_offset);
+    if (rc != 0)
+    {
+        return rc;
+    }
+    LPL_TRY(cudaMemsetAsync(d.status, 0, sizeof(std::uint32_t), c.stream));
+    if (ring_offset < 0)
+    {
+        LPL_TRY(cudaMemsetAsync(d.ring, 0, sizeof(std::uint16_t) * d.cap, c.stream));
+    }
+    c.seg.use_ring = (ring_offset >= 0 && ctx->seg_cfg.assume_unorganized_cloud == 0) ? 1 : 0;
+    launch_take_all(&c, 1);
+    launch_segment(&c, 1, bgr_image_out != nullptr);
+    if (n != 0)
+    {
+        LPL_TRY(cudaMemcpyAsync(labels_out, d.labels_out, sizeof(std::uint32_t) * n, cudaMemcpyDeviceToHost, c.stream));
+    }
+    if (bgr_image_out != nullptr)
+    {
+        LPL_TRY(cudaMemcpyAsync(bgr_image_out, d.bgr, static_cast<std::size_t>(c.seg.npx) * 3, cudaMemcpyDeviceToHost,
+                                c.stream));
+    }
+    return check_status(ctx, 1);
+}
+
+int lpl_cluster(lpl_ctx* ctx, const void* points, std::size_t stride, std::uint32_t n, std::int32_t* labels_out,
+                std::uint32_t* num_clusters_out)
+{
+    if (ctx == nullptr || (n != 0 && labels_out == nullptr))
+    {
+        return LPL_ERR_INVALID_ARGUMENT;
+    }
+    Ctx& c = ctx->c;
+    Dev& d = c.d;
+    int rc = stage_points(ctx, points, stride, n, d.pts_o, d.n_o, -1);
+    if (rc != 0)
+    {
+        return rc;
+    }
+    if (num_clusters_out != nullptr)
+    {
+        *num_clusters_out = 0;
+    }
+    if (n == 0)
+    {
+        return LPL_OK; // clusterer.cpp:62-65
+    }
+    LPL_TRY(cudaMemsetAsync(d.status, 0, sizeof(std::uint32_t), c.stream));
+    launch_cluster(&c, 1);
+    LPL_TRY(cudaMemcpyAsync(labels_out, d.clabel, sizeof(std::int32_t) * n, cudaMemcpyDeviceToHost, c.stream));
+    std::uint32_t k = 0;
+    LPL_TRY(cudaMemcpyAsync(&k, d.n_clusters, 4, cudaMemcpyDeviceToHost, c.stream));
+    rc = check_status(ctx, 1);
+    if (num_clusters_out != nullptr)
+    {
+        *num_clusters_out = k;
+    }
+    return rc;
+}
+
+int lpl_cluster_hulls(lpl_ctx* ctx, const void* points, std::size_t stride, const std::int32_t* labels, std::uint32_t n,
+                      std::uint32_t num_clusters, std::uint32_t* hull_offsets, std::int32_t* hull_indices, float* hull_xy,
+                      float* zminmax)
+{
+    if (ctx == nullptr || hull_offsets == nullptr || (n != 0 && labels == nullptr))
+    {
+        return LPL_ERR_INVALID_ARGUMENT;
+    }
+    Ctx& c = ctx->c;
+    Dev& d = c.d;
+    if (num_clusters > d.cap)
+    {
+        return fail(ctx, LPL_ERR_CAPACITY, "more clusters than point capacity");
+    }
+    int rc = stage_points(ctx, points, stride, n, d.pts_o, d.n_o, -1);
+    if (rc != 0)
+    {
+        return rc;
+    }
+    if (n == 0 || num_clusters == 0)
+    {
+        for (std::uint32_t k = 0; k <= num_clusters; ++k)
+        {
+            hull_offsets[k] = 0;
+        }
+        return LPL_OK;
+    }
+    LPL_TRY(cudaMemcpyAsync(d.clabel, labels, sizeof(std::int32_t) * n, cudaMemcpyHostToDevice, c.stream));
+    LPL_TRY(cudaMemcpyAsync(d.n_clusters, &num_clusters, 4, cudaMemcpyHostToDevice, c.stream));
+    LPL_TRY(cudaMemsetAsync(d.ccount, 0, sizeof(std::uint32_t) * num_clusters, c.stream));
+    k_label_count<<<dim3((d.cap + 255) / 256, 1), 256, 0, c.stream>>>(d, num_clusters);
+    c.launches += 1;
+    launch_hulls(&c, 1);
+    LPL_TRY(cudaMemcpyAsync(hull_offsets, d.hull_off, sizeof(std::uint32_t) * (num_clusters + 1), cudaMemcpyDeviceToHost,
+                            c.stream));
+    LPL_TRY(cudaStreamSynchronize(c.stream));
+    const std::uint32_t tot = hull_offsets[num_clusters];
+    if (tot > n)
+    {
+        return fail(ctx, LPL_ERR_CUDA, "internal error: more hull vertices than points");
+    }
+    if (hull_indices != nullptr && tot != 0)
+    {
+        LPL_TRY(cudaMemcpyAsync(hull_indices, d.hull_idx, sizeof(std::uint32_t) * tot, cudaMemcpyDeviceToHost, c.stream));
+    }
+    if (hull_xy != nullptr && tot != 0)
+    {
+        LPL_TRY(cudaMemcpyAsync(hull_xy, d.hull_xy, sizeof(float2) * tot, cudaMemcpyDeviceToHost, c.stream));
+    }
+    if (zminmax != nullptr)
+    {
+        LPL_TRY(cudaMemcpyAsync(zminmax, d.zminmax, sizeof(float2) * num_clusters, cudaMemcpyDeviceToHost, c.stream));
+    }
+    LPL_TRY(cudaStreamSynchronize(c.stream));
+    LPL_TRY(cudaGetLastError());
+    return LPL_OK;
+}
+
+int lpl_convex_hull(lpl_ctx* ctx, const void* xy, std::size_t stride, std::uint32_t n, std::int32_t* indices_out,
+                    std::uint32_t* count_out)
+{
+    if (ctx == nullptr || count_out == nullptr || (n != 0 && (xy == nullptr || indices_out == nullptr)) || stride < 16)
+    {
+        return LPL_ERR_INVALID_ARGUMENT;
+    }
+    *count_out = 0;
+    if (n == 0)
+    {
+        return LPL_OK;
+    }
+    // The device path sorts on float keys: every PCL-derived PointXY is float-representable
+    // (processor.cpp:645-646). Anything else is rejected rather than silently rounded.
+    std::vector<float> pts(static_cast<std::size_t>(n) * 4, 0.f);
+    std::vector<std::int32_t> lab(n, 0);
+    for (std::uint32_t i = 0; i < n; ++i)
+    {
+        double v[2];
+        std::memcpy(v, static_cast<const char*>(xy) + i * stride, 16);
+        const float fx = static_cast<float>(v[0]), fy = static_cast<float>(v[1]);
+        if (static_cast<double>(fx) != v[0] || static_cast<double>(fy) != v[1])
+        {
+            return fail(ctx, LPL_ERR_INVALID_ARGUMENT,
+                        "convexHull: coordinates are not float-representable (device path sorts float keys)");
+        }
+        pts[4 * i] = fx;
+        pts[4 * i + 1] = fy;
+    }
+    std::vector<std::uint32_t> off(2, 0);
+    const int rc = lpl_cluster_hulls(ctx, pts.data(), 16, lab.data(), n, 1, off.data(), indices_out, nullptr, nullptr);
+    if (rc == 0)
+    {
+        *count_out = off[1];
+    }
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------
+int lpl_timer_start(lpl_ctx* ctx)
+{
+    if (ctx == nullptr)
+    {
+        return LPL_ERR_INVALID_ARGUMENT;
+    }
+    LPL_TRY(cudaEventRecord(ctx->c.ev0, ctx->c.stream));
+    return LPL_OK;
+}
+
+int lpl_timer_stop_ms(lpl_ctx* ctx, float* ms_out)
+{
+    if (ctx == nullptr || ms_out == nullptr)
+    {
+        return LPL_ERR_INVALID_ARGUMENT;
+    }
+    LPL_TRY(cudaEventRecord(ctx->c.ev1, ctx->c.stream));
+    LPL_TRY(cudaEventSynchronize(ctx->c.ev1));
+    LPL_TRY(cudaEventElapsedTime(ms_out, ctx->c.ev0, ctx->c.ev1));
+    return LPL_OK;
+}
+
+std::uint64_t lpl_launch_count(lpl_ctx* ctx, int reset)
+{
+    if (ctx == nullptr)
+    {
+        return 0;
+    }
+    const std::uint64_t v = ctx->c.launches;
+    if (reset)
+    {
+        ctx->c.launches = 0;
+    }
+    return v;
+}
+
+int lpl_debug_segment(lpl_ctx* ctx, std::uint32_t f, float* elevation, float* plane, std::uint32_t* best_inliers,
+                      std::uint32_t* counters)
+{
+    if (ctx == nullptr || f >= ctx->c.d.B)
+    {
+        return LPL_ERR_INVALID_ARGUMENT;
+    }
+    Ctx& c = ctx->c;
+    Dev& d = c.d;
+    const SegParams& s = c.seg;
+    LPL_TRY(cudaStreamSynchronize(c.stream));
+    if (elevation != nullptr)
+    {
+        LPL_TRY(cudaMemcpy(elevation, d.elev + static_cast<std::size_t>(f) * s.ncell, sizeof(float) * s.ncell,
+                           cudaMemcpyDeviceToHost));
+    }
+    if (plane != nullptr)
+    {
+        LPL_TRY(cudaMemcpy(plane, d.best_plane + f, sizeof(float4), cudaMemcpyDeviceToHost));
+    }
+    if (best_inliers != nullptr)
+    {
+        LPL_TRY(cudaMemcpy(best_inliers, d.best_cnt + f, 4, cudaMemcpyDeviceToHost));
+    }
+    if (counters != nullptr)
+    {
+        LPL_TRY(cudaMemcpy(&counters[0], d.n_binned + f, 4, cudaMemcpyDeviceToHost));
+        LPL_TRY(cudaMemcpy(&counters[1], d.n_cand + f, 4, cudaMemcpyDeviceToHost));
+        LPL_TRY(cudaMemcpy(&counters[2], d.n_queue + f, 4, cudaMemcpyDeviceToHost));
+        LPL_TRY(cudaMemcpy(&counters[3], d.jcp_rounds + f, 4, cudaMemcpyDeviceToHost));
+        LPL_TRY(cudaMemcpy(&counters[4], d.n_border + f, 4, cudaMemcpyDeviceToHost));
+        counters[5] = static_cast<std::uint32_t>(s.slices);
+        counters[6] = static_cast<std::uint32_t>(s.rings);
+        LPL_TRY(cudaMemcpy(&counters[7], d.status + f, 4, cudaMemcpyDeviceToHost));
+    }
+    return LPL_OK;
+}
+
+int lpl_debug_cluster(lpl_ctx* ctx, std::uint32_t f, std::int32_t* dims)
+{
+    if (ctx == nullptr || dims == nullptr || f >= ctx->c.d.B)
+    {
+        return LPL_ERR_INVALID_ARGUMENT;
+    }
+    Ctx& c = ctx->c;
+    LPL_TRY(cudaStreamSynchronize(c.stream));
+    float mx[4];
+    LPL_TRY(cudaMemcpy(mx, c.d.sph_max + f * 4, 16, cudaMemcpyDeviceToHost));
+    dims[0] = static_cast<std::int32_t>(std::ceil(mx[0] / c.clu.range_res) + 1);
+    dims[1] = static_cast<std::int32_t>(std::ceil(mx[1] / c.clu.az_res) + 1);
+    dims[2] = static_cast<std::int32_t>(std::ceil(mx[2] / c.clu.el_res) + 1);
+    return LPL_OK;
+}
+
+void* lpl_stream(lpl_ctx* ctx) { return ctx != nullptr ? static_cast<void*>(ctx->c.stream) : nullptr; }
+} // extern "C"

@@ -1,0 +1,359 @@
+// Stage 3: curved-voxel clustering of the obstacle cloud, batched over frames.
+//
+// Reference: lidar_processing_lib/src/clusterer.cpp
+//   cartesianToSpherical :55-100   -> k_clu_sph (glibc-exact atan2f / atanf, frame-wide maxima)
+//   buildHashTable       :102-120  -> k_clu_insert (device open-addressing hash, key = flat index)
+//   clusterImpl          :122-193  -> k_clu_union / k_clu_flatten: the BFS over 26-connected
+//                                     occupied voxels computes connected components; here they
+//                                     come from a lock-free union-find over hash slots
+//   removeSmallClusters  :195-239  -> stable compaction of the component representatives
+//
+// Label order: the reference opens a new cluster at the first point (in cloud order) whose
+// voxel is unlabelled, so cluster ids are ranked by the component's minimum point index, and
+// the small-cluster pass renumbers the survivors in that same order. A stable compaction over
+// "point i is the minimum point of a surviving component" yields exactly those ids.
+//
+// The azimuth wrap is the reference's literal one (index -1 -> num_azimuth - 1, num_azimuth -> 0
+// with num_azimuth = ceil(max_az / res) + 1), see DESIGN.md hazard H3.
+#include "common.cuh"
+
+namespace lpl
+{
+__global__ void __launch_bounds__(256) k_clu_sph(Dev d)
+{
+    __shared__ std::uint32_t smax[3];
+    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t n = d.n_o[f];
+    if (blockIdx.x * 256u >= n)
+    {
+        return;
+    }
+    if (threadIdx.x < 3)
+    {
+        smax[threadIdx.x] = 0;
+    }
+    __syncthreads();
+    const std::uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    std::uint32_t br = 0, ba = 0, be = 0;
+    if (i < n)
+    {
+        const std::size_t o = static_cast<std::size_t>(f) * d.cap;
+        const float4 p = d.pts_o[o + i];
+        float az = atan2f_glibc(p.y, p.x);
+        az = (az < 0.f) ? (az + 6.28318530717958647692f) : az;
+        const float dxy2 = p.x * p.x + p.y * p.y;
+        const float dxy = sqrtf(dxy2);
+        const float range = sqrtf(dxy2 + p.z * p.z);
+        const float el = atanf_glibc(p.z / dxy) + 1.57079632679489661923f;
+        d.sph[o + i] = make_float4(range, az, el, 0.f);
+        // non-negative floats order like their bit patterns; "+ 0.0f" folds -0.0 into +0.0
+        br = __float_as_uint(range + 0.0f);
+        ba = __float_as_uint(az + 0.0f);
+        be = __float_as_uint(el + 0.0f);
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1)
+    {
+        br = max(br, __shfl_xor_sync(0xffffffffu, br, s));
+        ba = max(ba, __shfl_xor_sync(0xffffffffu, ba, s));
+        be = max(be, __shfl_xor_sync(0xffffffffu, be, s));
+    }
+    if (lane_id() == 0)
+    {
+        atomicMax(&smax[0], br);
+        atomicMax(&smax[1], ba);
+        atomicMax(&smax[2], be);
+    }
+    __syncthreads();
+    if (threadIdx.x < 3)
+    {
+        atomicMax(&d.sph_max[f * 4 + threadIdx.x], smax[threadIdx.x]);
+    }
+}
+
+struct VoxelDims
+{
+    std::int32_t nr, na, ne;
+};
+
+__device__ __forceinline__ VoxelDims voxel_dims(const Dev& d, const ClusterParams& cp, std::uint32_t f)
+{
+    // clusterer.cpp:92-99
+    const float mr = __uint_as_float(d.sph_max[f * 4 + 0]);
+    const float ma = __uint_as_float(d.sph_max[f * 4 + 1]);
+    const float me = __uint_as_float(d.sph_max[f * 4 + 2]);
+    VoxelDims v;
+    v.nr = static_cast<std::int32_t>(ceilf(mr / cp.range_res) + 1.f);
+    v.na = static_cast<std::int32_t>(ceilf(ma / cp.az_res) + 1.f);
+    v.ne = static_cast<std::int32_t>(ceilf(me / cp.el_res) + 1.f);
+    return v;
+}
+
+__device__ __forceinline__ std::uint32_t voxel_hash(std::int32_t key)
+{
+    std::uint32_t h = static_cast<std::uint32_t>(key) * 0x9E3779B1u;
+    return h ^ (h >> 15);
+}
+
+__global__ void __launch_bounds__(256) k_clu_insert(Dev d, ClusterParams cp)
+{
+    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t n = d.n_o[f];
+    const std::uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    if (i >= n)
+    {
+        return;
+    }
+    const VoxelDims vd = voxel_dims(d, cp, f);
+    const std::size_t o = static_cast<std::size_t>(f) * d.cap;
+    const float4 s = d.sph[o + i];
+    const std::int32_t ri = static_cast<std::int32_t>(s.x / cp.range_res);
+    const std::int32_t ai = static_cast<std::int32_t>(s.y / cp.az_res);
+    const std::int32_t ei = static_cast<std::int32_t>(s.z / cp.el_res);
+    const std::int32_t flat = vd.nr * (vd.na * ei + ai) + ri; // clusterer.hpp:136-142
+    const std::uint32_t mask = d.hcap - 1u;
+    std::int32_t* keys = d.hkey + static_cast<std::size_t>(f) * d.hcap;
+    std::uint32_t h = voxel_hash(flat) & mask;
+    std::uint32_t slot = 0xffffffffu;
+    for (std::uint32_t probe = 0; probe < d.hcap; ++probe)
+    {
+        const std::int32_t prev = atomicCAS(&keys[h], -1, flat);
+        if (prev == -1 || prev == flat)
+        {
+            slot = h;
+            break;
+        }
+        h = (h + 1u) & mask;
+    }
+    if (slot == 0xffffffffu)
+    {
+        atomicOr(&d.status[f], ST_HASH_FULL);
+        slot = 0;
+    }
+    d.vslot[o + i] = slot;
+    const std::size_t ho = static_cast<std::size_t>(f) * d.hcap;
+    d.hparent[ho + slot] = slot; // same value from every point of the voxel
+    d.hcount[ho + slot] = 0;
+    atomicMin(&d.hmin[ho + slot], i);
+}
+
+// parent[] is updated with L2 atomics while other threads walk it: read through L2 (ld.cg) so a
+// stale L1 line can never make a failed CAS retry forever.
+__device__ __forceinline__ std::uint32_t uf_find(const std::uint32_t* parent, std::uint32_t x)
+{
+    std::uint32_t p = __ldcg(parent + x);
+    while (p != x)
+    {
+        x = p;
+        p = __ldcg(parent + x);
+    }
+    return x;
+}
+
+// roots only ever move to smaller slot ids, so the structure stays a forest under races
+__device__ __forceinline__ void uf_union(std::uint32_t* parent, std::uint32_t a, std::uint32_t b)
+{
+    while (true)
+    {
+        a = uf_find(parent, a);
+        b = uf_find(parent, b);
+        if (a == b)
+        {
+            return;
+        }
+        if (a < b)
+        {
+            const std::uint32_t t = a;
+            a = b;
+            b = t;
+        }
+        if (atomicCAS(&parent[a], a, b) == a)
+        {
+            return;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_clu_union(Dev d, ClusterParams cp)
+{
+    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t n = d.n_o[f];
+    const std::uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    if (i >= n)
+    {
+        return;
+    }
+    const std::size_t o = static_cast<std::size_t>(f) * d.cap;
+    const std::size_t ho = static_cast<std::size_t>(f) * d.hcap;
+    const std::uint32_t slot = d.vslot[o + i];
+    if (d.hmin[ho + slot] != i)
+    {
+        return; // one representative point per voxel does the neighbour look-ups
+    }
+    const VoxelDims vd = voxel_dims(d, cp, f);
+    const std::int32_t* keys = d.hkey + ho;
+    std::uint32_t* parent = d.hparent + ho;
+    const std::uint32_t mask = d.hcap - 1u;
+    const std::int32_t flat = keys[slot];
+    const std::int32_t ri = flat % vd.nr;
+    const std::int32_t t = flat / vd.nr;
+    const std::int32_t ai = t % vd.na;
+    const std::int32_t ei = t / vd.na;
+    for (int de = -1; de <= 1; ++de)
+    {
+        const std::int32_t e2 = ei + de;
+        if (e2 < 0 || e2 >= vd.ne)
+        {
+            continue;
+        }
+        for (int da = -1; da <= 1; ++da)
+        {
+            std::int32_t a2 = ai + da;
+            if (a2 < 0)
+            {
+                a2 += vd.na;
+            }
+            else if (a2 >= vd.na)
+            {
+                a2 -= vd.na;
+            }
+            for (int dr = -1; dr <= 1; ++dr)
+            {
+                if (de == 0 && da == 0 && dr == 0)
+                {
+                    continue;
+                }
+                const std::int32_t r2 = ri + dr;
+                if (r2 < 0 || r2 >= vd.nr)
+                {
+                    continue;
+                }
+                const std::int32_t key2 = vd.nr * (vd.na * e2 + a2) + r2;
+                std::uint32_t h = voxel_hash(key2) & mask;
+                for (std::uint32_t probe = 0; probe < d.hcap; ++probe)
+                {
+                    const std::int32_t kk = keys[h];
+                    if (kk == key2)
+                    {
+                        uf_union(parent, slot, h);
+                        break;
+                    }
+                    if (kk == -1)
+                    {
+                        break;
+                    }
+                    h = (h + 1u) & mask;
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_clu_flatten(Dev d)
+{
+    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t n = d.n_o[f];
+    const std::uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    if (i >= n)
+    {
+        return;
+    }
+    const std::size_t o = static_cast<std::size_t>(f) * d.cap;
+    const std::size_t ho = static_cast<std::size_t>(f) * d.hcap;
+    const std::uint32_t root = uf_find(d.hparent + ho, d.vslot[o + i]);
+    d.vslot[o + i] = root;
+    atomicMin(&d.hmin[ho + root], i); // becomes the component's minimum point index
+    atomicAdd(&d.hcount[ho + root], 1u);
+    d.hlabel[ho + root] = -1;
+}
+
+struct ClusterRepPred
+{
+    Dev d;
+    std::uint32_t min_size;
+    __device__ bool operator()(std::uint32_t f, std::uint32_t i) const
+    {
+        const std::size_t ho = static_cast<std::size_t>(f) * d.hcap;
+        const std::uint32_t root = d.vslot[static_cast<std::size_t>(f) * d.cap + i];
+        return d.hmin[ho + root] == i && d.hcount[ho + root] >= min_size;
+    }
+};
+
+struct ClusterRepEmit
+{
+    Dev d;
+    __device__ void operator()(std::uint32_t f, std::uint32_t i, std::uint32_t pos) const
+    {
+        const std::size_t ho = static_cast<std::size_t>(f) * d.hcap;
+        const std::uint32_t root = d.vslot[static_cast<std::size_t>(f) * d.cap + i];
+        d.hlabel[ho + root] = static_cast<std::int32_t>(pos);
+        d.ccount[static_cast<std::size_t>(f) * d.cap + pos] = d.hcount[ho + root];
+    }
+};
+
+__global__ void __launch_bounds__(256) k_clu_labels(Dev d)
+{
+    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t n = d.n_o[f];
+    const std::uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    if (i >= n)
+    {
+        return;
+    }
+    const std::size_t o = static_cast<std::size_t>(f) * d.cap;
+    d.clabel[o + i] = d.hlabel[static_cast<std::size_t>(f) * d.hcap + d.vslot[o + i]];
+}
+
+// hand-over from segmentation: stable compaction of OBSTACLE points in cloud order
+// (src/processor/src/processor.cpp:562-579)
+struct ObstaclePred
+{
+    const std::uint8_t* seg_label;
+    std::uint32_t cap;
+    __device__ bool operator()(std::uint32_t f, std::uint32_t i) const
+    {
+        return seg_label[static_cast<std::size_t>(f) * cap + i] == PX_OBSTACLE;
+    }
+};
+
+struct ObstacleEmit
+{
+    const float4* pts_v;
+    const std::uint32_t* idx_v;
+    float4* pts_o;
+    std::uint32_t* idx_o;
+    std::uint32_t cap;
+    __device__ void operator()(std::uint32_t f, std::uint32_t i, std::uint32_t pos) const
+    {
+        const std::size_t o = static_cast<std::size_t>(f) * cap;
+        pts_o[o + pos] = pts_v[o + i];
+        idx_o[o + pos] = idx_v[o + i];
+    }
+};
+
+void launch_take_obstacles(Ctx* c, std::uint32_t nf)
+{
+    Dev& d = c->d;
+    launch_compact(c->stream, nf, d.tiles, d.n_v, 0u, d.tile_cnt, d.n_o, ObstaclePred{d.seg_label, d.cap},
+                   ObstacleEmit{d.pts_v, d.idx_v, d.pts_o, d.idx_o, d.cap});
+    c->launches += 2;
+}
+
+void launch_cluster(Ctx* c, std::uint32_t nf)
+{
+    Dev& d = c->d;
+    cudaStream_t s = c->stream;
+    cudaMemsetAsync(d.sph_max, 0, sizeof(std::uint32_t) * 4 * nf, s);
+    cudaMemsetAsync(d.hkey, 0xff, sizeof(std::int32_t) * static_cast<std::size_t>(d.hcap) * nf, s);
+    cudaMemsetAsync(d.hmin, 0xff, sizeof(std::uint32_t) * static_cast<std::size_t>(d.hcap) * nf, s);
+    const dim3 g((d.cap + 255) / 256, nf);
+    k_clu_sph<<<g, 256, 0, s>>>(d);
+    k_clu_insert<<<g, 256, 0, s>>>(d, c->clu);
+    k_clu_union<<<g, 256, 0, s>>>(d, c->clu);
+    k_clu_flatten<<<g, 256, 0, s>>>(d);
+    launch_compact(s, nf, d.tiles, d.n_o, 0u, d.tile_cnt, d.n_clusters,
+                   ClusterRepPred{d, c->clu.min_cluster_size}, ClusterRepEmit{d});
+    k_clu_labels<<<g, 256, 0, s>>>(d);
+    c->launches += 7;
+}
+} // namespace lpl

@@ -1,0 +1,433 @@
+// Shared declarations for the sm_100a kernels of the LiDAR hot path.
+//
+// Layout in HBM: every per-point array is frame-major with a fixed stride of `cap` elements
+// (ctx->cap, a multiple of kTile), so a batch of B frames is one launch with blockIdx.y = frame
+// and per-frame point counts living in device memory (no host sync between stages).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+
+#include "libm_exact.cuh"
+
+namespace lpl
+{
+constexpr int kTile = 2048;         // items per compaction / scan tile
+constexpr int kTileThreads = 256;   // threads per tile block (8 items per thread)
+constexpr int kItems = kTile / kTileThreads;
+constexpr int kDrorGrid = 256;      // DROR uniform grid: kDrorGrid x kDrorGrid cells of 1 m
+constexpr int kDrorCells = kDrorGrid * kDrorGrid;
+constexpr int kRansacIters = 60;    // segmenter.cpp:324
+constexpr int kRansacBins = 4;      // segmenter.cpp:323
+constexpr int kMtRaws = 8192;       // pre-generated std::mt19937{42} outputs
+
+// pixel codes of the range image
+enum : std::uint8_t
+{
+    PX_EMPTY = 0,
+    PX_GROUND = 1,
+    PX_OBSTACLE = 2,
+    PX_QUEUED = 3,    // CV_INTERSECTION: ground pixel under the dilated obstacle mask
+    PX_UNDECIDED = 4, // queued pixel whose neighbourhood carried no weight
+    PX_DILATED = 0x10 // flag: red channel set by the 5x5 dilation (only visible on empty pixels)
+};
+
+struct SegParams
+{
+    // image / grid geometry
+    int H, W, npx;
+    int rings, slices, ncell;
+    int use_ring; // 1: height index = ring field, 0: from elevation angle
+    // derived float constants (computed on the host with the reference's float expressions)
+    float radial_spacing, min_dist, max_dist;
+    float slice_res, el_down, rad_per_px;
+    float z_lo, z_hi;
+    float thr, thr2, delta, e0;
+    float cos_max, p1z;
+    float kthr_sqr, amp;
+    float wscale; // (W - 1) as float
+    int jcp_emulate_stale; // 1 = bit-compatible with the reference's stale out-of-image slots
+};
+
+struct DrorParams
+{
+    double scaling;   // pow((double)radius_multiplier, 2.0)
+    float min_r_sqr;  // min_search_radius^2
+    std::uint32_t min_neighbours;
+};
+
+struct ClusterParams
+{
+    float range_res, az_res, el_res;
+    std::uint32_t min_cluster_size;
+};
+
+// All device buffers of a context. Pointers are to the start of frame 0; frame f lives at
+// ptr + f * stride (stride noted per field).
+struct Dev
+{
+    std::uint32_t cap;    // points per frame (multiple of kTile)
+    std::uint32_t tiles;  // cap / kTile
+    std::uint32_t B;      // frames per batch
+    std::uint32_t qcap;   // JCP queue capacity per frame
+    std::uint32_t hcap;   // voxel hash slots per frame (power of two)
+    std::uint32_t ptiles; // pixel tiles per frame = ceil(npx / kTile)
+
+    // ---- input cloud
+    float4* pts_in;           // [B][cap]  x,y,z,(unused)
+    std::uint32_t* n_in;      // [B]
+    std::uint16_t* ring;      // [B][cap]
+    // ---- DROR
+    std::uint8_t* noise;      // [B][cap]  0 valid, 1 noise
+    std::uint32_t* grid_cnt;  // [B][kDrorCells]  (self-cleaning)
+    std::uint32_t* grid_start;// [B][kDrorCells+1]
+    float4* grid_pts;         // [B][cap]  points in cell order
+    std::uint32_t* unres;     // [B][cap]  unresolved point indices after the scan-line pass
+    std::uint32_t* n_unres;   // [B]
+    // ---- cloud entering segmentation (valid points, ring packed into .w)
+    float4* pts_v;            // [B][cap]
+    std::uint32_t* idx_v;     // [B][cap]  index in the input cloud
+    std::uint32_t* n_v;       // [B]
+    // ---- segmentation scratch
+    std::int32_t* cell;       // [B][cap]  polar cell or -1
+    std::uint32_t* px;        // [B][cap]  pixel index
+    std::uint32_t* slot;      // [B][cap]  arrival slot inside the cell
+    std::uint32_t* cell_cnt;  // [B][ncell]
+    std::uint32_t* cell_start;// [B][ncell+1]
+    std::uint32_t* n_binned;  // [B]       points that fell into the polar grid
+    std::uint32_t* order;     // [B][cap]  sorted position -> point index ((cell, cloud) order)
+    float* zsort;             // [B][cap]  scratch for oversized cells
+    float* cell_zmin;         // [B][ncell]
+    float* elev;              // [B][ncell]
+    std::uint8_t* lab;        // [B][cap]  label by sorted position
+    std::uint32_t* cand;      // [B][cap]  RANSAC candidates (sorted positions)
+    std::uint32_t* n_cand;    // [B]
+    float4* planes;           // [B][kRansacIters] (nx, ny, nz, d); nz = NaN marks a skipped draw
+    std::uint32_t* inliers;   // [B][kRansacIters]
+    float4* best_plane;       // [B]  (a, b, c, d); w component of [B + f] unused
+    std::uint32_t* best_cnt;  // [B]
+    unsigned long long* key;  // [B][npx]  (depth_sqr bits << 32) | sorted position
+    float4* pxpt;             // [B][npx]  x, y, z, point index (int bits; -1 = none)
+    std::uint8_t* code;       // [B][npx]  PX_* before / after JCP
+    std::uint32_t* queue;     // [B][qcap] queued pixels in raster order
+    std::uint32_t* n_queue;   // [B]
+    float* wn;                // [B][24][qcap] normalised weights, slot-major
+    unsigned long long* mk;   // [B][qcap] 2-bit mask source per slot + flags
+    std::uint32_t* stale_ref; // [B][nborder][12] explicit pixel refs for inherited slots
+    std::uint32_t* n_border;  // [B]
+    std::uint32_t nborder_cap;
+    std::uint32_t* pend;      // [B][2][qcap]
+    std::uint32_t* jcp_rounds;// [B]
+    std::uint8_t* seg_label;  // [B][cap]  label per point of the segmented cloud
+    std::uint32_t* labels_out;// [B][cap]  u32 Label per *input* point
+    std::uint8_t* bgr;        // [B][npx*3]
+    // ---- obstacle cloud / clustering
+    float4* pts_o;            // [B][cap]
+    std::uint32_t* idx_o;     // [B][cap]  index in the input cloud
+    std::uint32_t* n_o;       // [B]
+    float4* sph;              // [B][cap]  range, azimuth, elevation
+    std::uint32_t* sph_max;   // [B][4]    float bits of max range / azimuth / elevation
+    std::int32_t* hkey;       // [B][hcap] voxel flat index or -1
+    std::uint32_t* hparent;   // [B][hcap] union-find parent (slot ids)
+    std::uint32_t* hmin;      // [B][hcap] min point index (per voxel, then per root)
+    std::uint32_t* hcount;    // [B][hcap] points per root
+    std::int32_t* hlabel;     // [B][hcap] final label per root
+    std::uint32_t* vslot;     // [B][cap]  voxel slot per point
+    std::int32_t* clabel;     // [B][cap]  cluster label per obstacle point
+    std::uint32_t* n_clusters;// [B]
+    // ---- hulls
+    std::uint32_t* ccount;    // [B][cap]  points per cluster (indexed by label)
+    std::uint32_t* cstart;    // [B][cap+1]
+    unsigned long long* hsk;  // [B][cap]  sort keys (x, y) per cluster segment
+    std::uint32_t* hsi;       // [B][cap]  point index per cluster segment
+    std::uint32_t* hstack;    // [B][cap]  per-cluster hull vertices (at the segment offset)
+    std::uint32_t* hcnt;      // [B][cap]  hull vertex count per cluster
+    std::uint32_t* hull_off;  // [B][cap+1]
+    std::uint32_t* hull_idx;  // [B][cap]  obstacle-cloud index per hull vertex
+    float2* hull_xy;          // [B][cap]
+    float2* zminmax;          // [B][cap]  per cluster
+    // ---- generic
+    std::uint32_t* tile_cnt;  // [B][max(tiles, ptiles)]
+    std::uint32_t* status;    // [B]  error bits raised by kernels
+    const std::uint32_t* mt_raw; // [kMtRaws]
+};
+
+enum : std::uint32_t
+{
+    ST_QUEUE_OVERFLOW = 1u,  // more queued JCP pixels than qcap
+    ST_RNG_EXHAUSTED = 2u,   // RANSAC needed more than kMtRaws generator outputs
+    ST_HASH_FULL = 4u,       // voxel hash table full
+    ST_BORDER_OVERFLOW = 8u, // more queued border pixels than reserved
+};
+
+// ---------------------------------------------------------------- small device helpers
+__device__ __forceinline__ std::uint32_t lane_id() { return threadIdx.x & 31u; }
+
+__device__ __forceinline__ std::uint32_t warp_sum(std::uint32_t v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        v += __shfl_xor_sync(0xffffffffu, v, o);
+    }
+    return v;
+}
+
+__device__ __forceinline__ std::uint32_t warp_incl_scan(std::uint32_t v)
+{
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        const std::uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane_id() >= static_cast<std::uint32_t>(o))
+        {
+            v += t;
+        }
+    }
+    return v;
+}
+
+// Block-wide sum for blockDim.x <= 1024 (multiple of 32). `sh` needs 32 words.
+__device__ __forceinline__ std::uint32_t block_sum(std::uint32_t v, std::uint32_t* sh)
+{
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane_id() == 0)
+    {
+        sh[threadIdx.x >> 5] = v;
+    }
+    __syncthreads();
+    const std::uint32_t nw = (blockDim.x + 31) >> 5;
+    std::uint32_t r = (threadIdx.x < nw) ? sh[threadIdx.x] : 0;
+    if (threadIdx.x < 32)
+    {
+        r = warp_sum(r);
+        if (threadIdx.x == 0)
+        {
+            sh[0] = r;
+        }
+    }
+    __syncthreads();
+    return sh[0];
+}
+
+// Block-wide exclusive scan of one value per thread (blockDim.x <= 1024, multiple of 32).
+// Returns the exclusive prefix; *total receives the block sum. `sh` needs 33 words.
+__device__ __forceinline__ std::uint32_t block_excl_scan(std::uint32_t v, std::uint32_t* sh,
+                                                         std::uint32_t* total)
+{
+    const std::uint32_t incl = warp_incl_scan(v);
+    __syncthreads();
+    if (lane_id() == 31)
+    {
+        sh[threadIdx.x >> 5] = incl;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32)
+    {
+        const std::uint32_t nw = (blockDim.x + 31) >> 5;
+        const std::uint32_t w = (threadIdx.x < nw) ? sh[threadIdx.x] : 0;
+        const std::uint32_t ws = warp_incl_scan(w);
+        sh[threadIdx.x] = ws - w;
+        if (threadIdx.x == 31)
+        {
+            sh[32] = ws;
+        }
+    }
+    __syncthreads();
+    *total = sh[32];
+    return sh[threadIdx.x >> 5] + incl - v;
+}
+
+// Stable ranks for a tile processed as kItems striped rounds of kTileThreads threads:
+// item (j, t) = tile_base + j * kTileThreads + t. Returns per-item exclusive rank among the
+// flagged items of the tile, in item order. `sh` needs kItems * 8 + 1 words.
+__device__ __forceinline__ void tile_ranks(const bool (&flag)[kItems], std::uint32_t (&rank)[kItems],
+                                           std::uint32_t* total, std::uint32_t* sh)
+{
+    constexpr int kWarps = kTileThreads / 32;
+    const std::uint32_t w = threadIdx.x >> 5;
+    std::uint32_t below[kItems];
+#pragma unroll
+    for (int j = 0; j < kItems; ++j)
+    {
+        const std::uint32_t b = __ballot_sync(0xffffffffu, flag[j]);
+        below[j] = __popc(b & ((1u << lane_id()) - 1u));
+        if (lane_id() == 0)
+        {
+            sh[j * kWarps + w] = __popc(b);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32)
+    {
+        // kItems * kWarps = 64 counters -> two per lane
+        const std::uint32_t a = sh[2 * threadIdx.x];
+        const std::uint32_t b = sh[2 * threadIdx.x + 1];
+        const std::uint32_t s = warp_incl_scan(a + b);
+        sh[2 * threadIdx.x] = s - a - b;
+        sh[2 * threadIdx.x + 1] = s - b;
+        if (threadIdx.x == 31)
+        {
+            sh[kItems * kWarps] = s;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kItems; ++j)
+    {
+        rank[j] = sh[j * kWarps + w] + below[j];
+    }
+    *total = sh[kItems * kWarps];
+    __syncthreads();
+}
+
+static_assert(kItems * (kTileThreads / 32) == 64, "tile_ranks assumes 64 (round, warp) counters");
+
+// ---------------------------------------------------------------- generic tile compaction
+// Stable, order-preserving selection of the items i in [0, n_f) of every frame f for which
+// pred(f, i) holds. Pass 1 counts per tile, pass 2 adds the counts of the preceding tiles and
+// scatters: emit(f, i, pos). n_out[f] (nullable) receives the number selected.
+template <class Pred>
+__global__ void __launch_bounds__(kTileThreads)
+    k_compact_count(Pred pred, const std::uint32_t* __restrict__ n_arr, std::uint32_t n_const,
+                    std::uint32_t* __restrict__ tile_cnt, std::uint32_t tiles_per_frame)
+{
+    __shared__ std::uint32_t sh[33];
+    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t n = n_arr ? n_arr[f] : n_const;
+    const std::uint32_t base = blockIdx.x * kTile;
+    std::uint32_t c = 0;
+    if (base < n)
+    {
+#pragma unroll
+        for (int j = 0; j < kItems; ++j)
+        {
+            const std::uint32_t i = base + j * kTileThreads + threadIdx.x;
+            c += (i < n && pred(f, i)) ? 1u : 0u;
+        }
+    }
+    const std::uint32_t s = block_sum(c, sh);
+    if (threadIdx.x == 0)
+    {
+        tile_cnt[f * tiles_per_frame + blockIdx.x] = s;
+    }
+}
+
+template <class Pred, class Emit>
+__global__ void __launch_bounds__(kTileThreads)
+    k_compact_scatter(Pred pred, Emit emit, const std::uint32_t* __restrict__ n_arr,
+                      std::uint32_t n_const, const std::uint32_t* __restrict__ tile_cnt,
+                      std::uint32_t tiles_per_frame, std::uint32_t* __restrict__ n_out)
+{
+    __shared__ std::uint32_t sh[kItems * (kTileThreads / 32) + 1];
+    __shared__ std::uint32_t sh2[33];
+    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t n = n_arr ? n_arr[f] : n_const;
+    const std::uint32_t base = blockIdx.x * kTile;
+    const std::uint32_t* tc = tile_cnt + f * tiles_per_frame;
+    // sum of the preceding tiles (and, in tile 0, of all tiles for n_out)
+    std::uint32_t before = 0, all = 0;
+    for (std::uint32_t t = threadIdx.x; t < tiles_per_frame; t += kTileThreads)
+    {
+        const std::uint32_t v = tc[t];
+        all += v;
+        before += (t < blockIdx.x) ? v : 0u;
+    }
+    before = block_sum(before, sh2);
+    if (blockIdx.x == 0 && n_out != nullptr)
+    {
+        all = block_sum(all, sh2);
+        if (threadIdx.x == 0)
+        {
+            n_out[f] = all;
+        }
+    }
+    if (base >= n)
+    {
+        return;
+    }
+    bool flag[kItems];
+    std::uint32_t rank[kItems];
+#pragma unroll
+    for (int j = 0; j < kItems; ++j)
+    {
+        const std::uint32_t i = base + j * kTileThreads + threadIdx.x;
+        flag[j] = (i < n) && pred(f, i);
+    }
+    std::uint32_t total;
+    tile_ranks(flag, rank, &total, sh);
+#pragma unroll
+    for (int j = 0; j < kItems; ++j)
+    {
+        if (flag[j])
+        {
+            emit(f, base + j * kTileThreads + threadIdx.x, before + rank[j]);
+        }
+    }
+}
+
+template <class Pred, class Emit>
+inline void launch_compact(cudaStream_t s, std::uint32_t B, std::uint32_t tiles_per_frame,
+                           const std::uint32_t* n_arr, std::uint32_t n_const,
+                           std::uint32_t* tile_cnt, std::uint32_t* n_out, Pred pred, Emit emit)
+{
+    const dim3 grid(tiles_per_frame, B);
+    k_compact_count<<<grid, kTileThreads, 0, s>>>(pred, n_arr, n_const, tile_cnt, tiles_per_frame);
+    k_compact_scatter<<<grid, kTileThreads, 0, s>>>(pred, emit, n_arr, n_const, tile_cnt,
+                                                    tiles_per_frame, n_out);
+}
+
+// Exclusive scan of `len` counters per frame by one block of 1024 threads:
+// out[f][0..len] (len + 1 entries, out[len] = total).
+// `len_arr` (nullable) gives a per-frame length <= len; strides are in elements; total_out
+// (nullable) receives the per-frame total.
+__global__ void k_excl_scan(const std::uint32_t* __restrict__ in, std::uint32_t in_stride,
+                            std::uint32_t* __restrict__ out, std::uint32_t out_stride,
+                            std::uint32_t len, const std::uint32_t* __restrict__ len_arr,
+                            std::uint32_t* __restrict__ total_out);
+
+// host-side launchers implemented per stage
+struct Ctx;
+void launch_ring(Ctx* c, std::uint32_t nf);
+void launch_dror(Ctx* c, std::uint32_t nf);
+void launch_take_all(Ctx* c, std::uint32_t nf);   // pts_in (+ ring) -> pts_v without DROR
+void launch_take_valid(Ctx* c, std::uint32_t nf); // DROR-valid points -> pts_v
+void launch_segment(Ctx* c, std::uint32_t nf, bool want_image);
+void launch_take_obstacles(Ctx* c, std::uint32_t nf);
+void launch_cluster(Ctx* c, std::uint32_t nf);
+void launch_hulls(Ctx* c, std::uint32_t nf);
+
+struct Ctx
+{
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    Dev d{};
+    SegParams seg{};
+    DrorParams dror{};
+    ClusterParams clu{};
+    void* slab = nullptr;       // one device allocation backing every Dev pointer
+    std::size_t slab_bytes = 0;
+    char err[512] = {0};
+    // pinned host staging for the C-ABI calls that take host pointers
+    void* h_stage = nullptr;
+    std::size_t h_stage_bytes = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    unsigned long long launches = 0; // kernels launched since the last reset
+};
+
+#define LPL_CUDA_OK(call)                                                                          \
+    do                                                                                             \
+    {                                                                                              \
+        const cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess)                                                                     \
+        {                                                                                          \
+            std::snprintf(c->err, sizeof(c->err), "%s:%d %s: %s", __FILE__, __LINE__, #call,       \
+                          cudaGetErrorString(e_));                                                 \
+            return -2;                                                                             \
+        }                                                                                          \
+    } while (0)
+
+} // namespace lpl

@@ -1,0 +1,381 @@
+// Stage 0 (ring partition) and stage 1 (DROR outlier filter).
+//
+// Reference behaviour:
+//   ring partition  src/dataloader/src/dataloader.cpp:68-137 (Dataloader::addRingInfo)
+//   DROR            lidar_processing_lib/src/noise_remover.cpp:38-68 (NoiseRemover::filter) with
+//                   the neighbour predicate of kdtree.hpp:131-149,363-371; "exact" semantics
+//                   (count of points with dist_sqr <= r_sqr, self included, compared with
+//                   min_neighbours) — the reference's KD-tree early exit leaves a stale traversal
+//                   stack whose effect depends on nth_element's tree shape (hazard H1).
+//
+// Both stages are HBM-bound streaming kernels over float4 points (16 B/pt in, 2 B or 1 B out).
+#include "common.cuh"
+
+namespace lpl
+{
+// ------------------------------------------------------------------------------------------
+// Ring partition: ring(i) = max(0, 63 - #{j <= i : quadrant(j) == FIRST && quadrant(j-1) == FOURTH}).
+// The sequential counter of the reference becomes a two-pass tile scan.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int quadrant_of(float x, float y)
+{
+    // dataloader.cpp:96-114; M_PI_2f, M_PIf and 1.5F * M_PIf as float constants
+    float az = atan2f_glibc(y, x);
+    az = (az < 0.f) ? (az + 2.0f * 3.14159265358979323846f) : az;
+    if (az < 1.57079632679489661923f)
+    {
+        return 0;
+    }
+    if (az < 3.14159265358979323846f)
+    {
+        return 1;
+    }
+    if (az < 1.5f * 3.14159265358979323846f)
+    {
+        return 2;
+    }
+    return 3;
+}
+
+struct RingWrapPred
+{
+    const float4* pts;
+    std::uint32_t cap;
+    __device__ bool operator()(std::uint32_t f, std::uint32_t i) const
+    {
+        if (i == 0)
+        {
+            return false; // previous_quadrant starts as FIRST (dataloader.cpp:86)
+        }
+        const float4* p = pts + static_cast<std::size_t>(f) * cap;
+        const float4 a = p[i];
+        if (quadrant_of(a.x, a.y) != 0)
+        {
+            return false;
+        }
+        const float4 b = p[i - 1];
+        return quadrant_of(b.x, b.y) == 3;
+    }
+};
+
+__global__ void __launch_bounds__(kTileThreads)
+    k_ring_write(RingWrapPred pred, const std::uint32_t* __restrict__ n_arr,
+                 const std::uint32_t* __restrict__ tile_cnt, std::uint32_t tiles_per_frame,
+                 std::uint16_t* __restrict__ ring, std::uint32_t cap)
+{
+    __shared__ std::uint32_t sh[kItems * (kTileThreads / 32) + 1];
+    __shared__ std::uint32_t sh2[33];
+    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t n = n_arr[f];
+    const std::uint32_t base = blockIdx.x * kTile;
+    if (base >= n)
+    {
+        return;
+    }
+    std::uint32_t before = 0;
+    for (std::uint32_t t = threadIdx.x; t < blockIdx.x; t += kTileThreads)
+    {
+        before += tile_cnt[f * tiles_per_frame + t];
+    }
+    before = block_sum(before, sh2);
+    bool flag[kItems];
+    std::uint32_t rank[kItems];
+#pragma unroll
+    for (int j = 0; j < kItems; ++j)
+    {
+        const std::uint32_t i = base + j * kTileThreads + threadIdx.x;
+        flag[j] = (i < n) && pred(f, i);
+    }
+    std::uint32_t total;
+    tile_ranks(flag, rank, &total, sh);
+#pragma unroll
+    for (int j = 0; j < kItems; ++j)
+    {
+        const std::uint32_t i = base + j * kTileThreads + threadIdx.x;
+        if (i < n)
+        {
+            const std::uint32_t wraps = before + rank[j] + (flag[j] ? 1u : 0u); // inclusive
+            ring[static_cast<std::size_t>(f) * cap + i] =
+                static_cast<std::uint16_t>(wraps >= 63u ? 0u : 63u - wraps);
+        }
+    }
+}
+
+void launch_ring(Ctx* c, std::uint32_t nf)
+{
+    Dev& d = c->d;
+    const dim3 grid(d.tiles, nf);
+    RingWrapPred pred{d.pts_in, d.cap};
+    k_compact_count<<<grid, kTileThreads, 0, c->stream>>>(pred, d.n_in, 0u, d.tile_cnt, d.tiles);
+    k_ring_write<<<grid, kTileThreads, 0, c->stream>>>(pred, d.n_in, d.tile_cnt, d.tiles, d.ring,
+                                                      d.cap);
+    c->launches += 2;
+}
+
+// ------------------------------------------------------------------------------------------
+// DROR
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float dror_radius_sqr(float x, float y, const DrorParams& p)
+{
+    // noise_remover.cpp:57-59: float range^2 widened to double, scaled, narrowed, clamped
+    const float range_sqr_f = (x * x) + (y * y);
+    const float dyn = static_cast<float>(p.scaling * static_cast<double>(range_sqr_f));
+    return fmaxf(dyn, p.min_r_sqr);
+}
+
+__device__ __forceinline__ bool dror_within(const float4& target, const float4& node, float r_sqr)
+{
+    // kdtree.hpp:131-143: (a0-b0)^2 + ((a1-b1)^2 + ((a2-b2)^2 + 0)), a = target, b = node
+    const float d0 = target.x - node.x;
+    const float d1 = target.y - node.y;
+    const float d2 = target.z - node.z;
+    const float dist = d0 * d0 + (d1 * d1 + (d2 * d2 + 0.0f));
+    return dist <= r_sqr;
+}
+
+constexpr int kNearHalo = 8; // scan-line neighbours examined on each side
+
+// Pass A: LiDAR clouds arrive in firing order, so a point's nearest neighbours are almost always
+// its predecessors / successors on the same ring. Counting those first settles the vast majority
+// of points (VALID as soon as min_neighbours are found) with one coalesced tile load; the
+// remaining points go to the exhaustive grid search. Any input order gives the same result.
+__global__ void __launch_bounds__(256)
+    k_dror_near(Dev d, DrorParams prm)
+{
+    __shared__ float4 sh[256 + 2 * kNearHalo];
+    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t n = d.n_in[f];
+    const std::uint32_t base = blockIdx.x * 256u;
+    if (base >= n)
+    {
+        return;
+    }
+    const float4* pts = d.pts_in + static_cast<std::size_t>(f) * d.cap;
+    for (int t = threadIdx.x; t < 256 + 2 * kNearHalo; t += 256)
+    {
+        const long long gi = static_cast<long long>(base) + t - kNearHalo;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gi >= 0 && gi < static_cast<long long>(n))
+        {
+            v = pts[gi];
+        }
+        sh[t] = v;
+    }
+    __syncthreads();
+    const std::uint32_t i = base + threadIdx.x;
+    bool unresolved = false;
+    if (i < n)
+    {
+        const float4 p = sh[threadIdx.x + kNearHalo];
+        const float r_sqr = dror_radius_sqr(p.x, p.y, prm);
+        std::uint32_t cnt = dror_within(p, p, r_sqr) ? 1u : 0u; // self (dist 0 unless NaN)
+#pragma unroll
+        for (int o = 1; o <= kNearHalo; ++o)
+        {
+            if (i >= static_cast<std::uint32_t>(o))
+            {
+                cnt += dror_within(p, sh[threadIdx.x + kNearHalo - o], r_sqr) ? 1u : 0u;
+            }
+            if (i + o < n)
+            {
+                cnt += dror_within(p, sh[threadIdx.x + kNearHalo + o], r_sqr) ? 1u : 0u;
+            }
+        }
+        unresolved = cnt < prm.min_neighbours;
+        d.noise[static_cast<std::size_t>(f) * d.cap + i] = 0; // provisional: VALID
+    }
+    // warp-aggregated append
+    const std::uint32_t m = __ballot_sync(0xffffffffu, unresolved);
+    if (m != 0)
+    {
+        std::uint32_t pos = 0;
+        if (lane_id() == 0)
+        {
+            pos = atomicAdd(&d.n_unres[f], __popc(m));
+        }
+        pos = __shfl_sync(0xffffffffu, pos, 0);
+        if (unresolved)
+        {
+            d.unres[static_cast<std::size_t>(f) * d.cap + pos + __popc(m & ((1u << lane_id()) - 1u))] = i;
+        }
+    }
+}
+
+__device__ __forceinline__ int dror_cell_coord(float v)
+{
+    int c = static_cast<int>(floorf(v)) + kDrorGrid / 2;
+    return min(max(c, 0), kDrorGrid - 1);
+}
+
+__global__ void __launch_bounds__(256) k_dror_grid_count(Dev d)
+{
+    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t n = d.n_in[f];
+    const std::uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    if (i >= n || d.n_unres[f] == 0)
+    {
+        return;
+    }
+    const float4 p = d.pts_in[static_cast<std::size_t>(f) * d.cap + i];
+    const int cell = dror_cell_coord(p.y) * kDrorGrid + dror_cell_coord(p.x);
+    atomicAdd(&d.grid_cnt[static_cast<std::size_t>(f) * kDrorCells + cell], 1u);
+}
+
+__global__ void __launch_bounds__(256) k_dror_grid_scatter(Dev d)
+{
+    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t n = d.n_in[f];
+    const std::uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    if (i >= n || d.n_unres[f] == 0)
+    {
+        return;
+    }
+    const float4 p = d.pts_in[static_cast<std::size_t>(f) * d.cap + i];
+    const int cell = dror_cell_coord(p.y) * kDrorGrid + dror_cell_coord(p.x);
+    // counting down returns grid_cnt to zero for the next batch
+    const std::uint32_t k = atomicSub(&d.grid_cnt[static_cast<std::size_t>(f) * kDrorCells + cell], 1u) - 1u;
+    const std::uint32_t pos = d.grid_start[static_cast<std::size_t>(f) * (kDrorCells + 1) + cell] + k;
+    d.grid_pts[static_cast<std::size_t>(f) * d.cap + pos] = p;
+}
+
+// Pass B: exhaustive count for the unresolved points over every grid cell the search disc can
+// touch. Cells of one grid row are contiguous in grid_pts, so each row is one range.
+__global__ void __launch_bounds__(128) k_dror_query(Dev d, DrorParams prm)
+{
+    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t nu = d.n_unres[f];
+    const std::uint32_t u = blockIdx.x * 128u + threadIdx.x;
+    if (u >= nu)
+    {
+        return;
+    }
+    const std::uint32_t i = d.unres[static_cast<std::size_t>(f) * d.cap + u];
+    const float4 p = d.pts_in[static_cast<std::size_t>(f) * d.cap + i];
+    const float r_sqr = dror_radius_sqr(p.x, p.y, prm);
+    const float rc = sqrtf(r_sqr) * 1.001f + 1e-4f; // conservative cover of the float predicate
+    const int x0 = dror_cell_coord(p.x - rc), x1 = dror_cell_coord(p.x + rc);
+    const int y0 = dror_cell_coord(p.y - rc), y1 = dror_cell_coord(p.y + rc);
+    const std::uint32_t* start = d.grid_start + static_cast<std::size_t>(f) * (kDrorCells + 1);
+    const float4* gp = d.grid_pts + static_cast<std::size_t>(f) * d.cap;
+    std::uint32_t cnt = 0;
+    for (int cy = y0; cy <= y1 && cnt < prm.min_neighbours; ++cy)
+    {
+        const std::uint32_t a = start[cy * kDrorGrid + x0];
+        const std::uint32_t b = start[cy * kDrorGrid + x1 + 1];
+        for (std::uint32_t k = a; k < b; ++k)
+        {
+            if (dror_within(p, gp[k], r_sqr))
+            {
+                if (++cnt >= prm.min_neighbours)
+                {
+                    break;
+                }
+            }
+        }
+    }
+    if (cnt < prm.min_neighbours)
+    {
+        d.noise[static_cast<std::size_t>(f) * d.cap + i] = 1;
+    }
+}
+
+__global__ void k_excl_scan(const std::uint32_t* __restrict__ in, std::uint32_t in_stride,
+                            std::uint32_t* __restrict__ out, std::uint32_t out_stride,
+                            std::uint32_t len, const std::uint32_t* __restrict__ len_arr,
+                            std::uint32_t* __restrict__ total_out)
+{
+    __shared__ std::uint32_t sh[33];
+    const std::uint32_t f = blockIdx.x;
+    if (len_arr != nullptr)
+    {
+        len = min(len, len_arr[f]);
+    }
+    const std::uint32_t* src = in + static_cast<std::size_t>(f) * in_stride;
+    std::uint32_t* dst = out + static_cast<std::size_t>(f) * out_stride;
+    const std::uint32_t per = (len + blockDim.x - 1) / blockDim.x;
+    const std::uint32_t a = min(threadIdx.x * per, len);
+    const std::uint32_t b = min(a + per, len);
+    std::uint32_t s = 0;
+    for (std::uint32_t k = a; k < b; ++k)
+    {
+        s += src[k];
+    }
+    std::uint32_t total;
+    std::uint32_t run = block_excl_scan(s, sh, &total);
+    for (std::uint32_t k = a; k < b; ++k)
+    {
+        dst[k] = run;
+        run += src[k];
+    }
+    if (threadIdx.x == 0)
+    {
+        dst[len] = total;
+        if (total_out != nullptr)
+        {
+            total_out[f] = total;
+        }
+    }
+}
+
+void launch_dror(Ctx* c, std::uint32_t nf)
+{
+    Dev& d = c->d;
+    cudaMemsetAsync(d.n_unres, 0, sizeof(std::uint32_t) * nf, c->stream);
+    const dim3 grid((d.cap + 255) / 256, nf);
+    k_dror_near<<<grid, 256, 0, c->stream>>>(d, c->dror);
+    k_dror_grid_count<<<grid, 256, 0, c->stream>>>(d);
+    k_excl_scan<<<nf, 1024, 0, c->stream>>>(d.grid_cnt, kDrorCells, d.grid_start, kDrorCells + 1, kDrorCells,
+                                            nullptr, nullptr);
+    k_dror_grid_scatter<<<grid, 256, 0, c->stream>>>(d);
+    const dim3 qgrid((d.cap + 127) / 128, nf);
+    k_dror_query<<<qgrid, 128, 0, c->stream>>>(d, c->dror);
+    c->launches += 5;
+}
+
+// ------------------------------------------------------------------------------------------
+// Hand-over to segmentation: stable compaction of the DROR-valid points (or all points), with
+// the ring index carried in the .w lane and the original index kept for the label scatter.
+// ------------------------------------------------------------------------------------------
+struct ValidPred
+{
+    const std::uint8_t* noise; // nullptr = take all
+    std::uint32_t cap;
+    __device__ bool operator()(std::uint32_t f, std::uint32_t i) const
+    {
+        return noise == nullptr || noise[static_cast<std::size_t>(f) * cap + i] == 0;
+    }
+};
+
+struct ValidEmit
+{
+    const float4* pts_in;
+    const std::uint16_t* ring;
+    float4* pts_v;
+    std::uint32_t* idx_v;
+    std::uint32_t cap;
+    __device__ void operator()(std::uint32_t f, std::uint32_t i, std::uint32_t pos) const
+    {
+        const std::size_t o = static_cast<std::size_t>(f) * cap;
+        float4 p = pts_in[o + i];
+        p.w = __uint_as_float(static_cast<std::uint32_t>(ring[o + i]));
+        pts_v[o + pos] = p;
+        idx_v[o + pos] = i;
+    }
+};
+
+void launch_take_valid(Ctx* c, std::uint32_t nf)
+{
+    Dev& d = c->d;
+    launch_compact(c->stream, nf, d.tiles, d.n_in, 0u, d.tile_cnt, d.n_v, ValidPred{d.noise, d.cap},
+                   ValidEmit{d.pts_in, d.ring, d.pts_v, d.idx_v, d.cap});
+    c->launches += 2;
+}
+
+void launch_take_all(Ctx* c, std::uint32_t nf)
+{
+    Dev& d = c->d;
+    launch_compact(c->stream, nf, d.tiles, d.n_in, 0u, d.tile_cnt, d.n_v, ValidPred{nullptr, d.cap},
+                   ValidEmit{d.pts_in, d.ring, d.pts_v, d.idx_v, d.cap});
+    c->launches += 2;
+}
+} // namespace lpl

@@ -1,0 +1,1007 @@
+// Stage 2: JCP ground segmentation on the RECM (+ near-field RANSAC), batched over frames.
+//
+// Reference: lidar_processing_lib/src/segmenter.cpp
+//   constructPolarGrid :103-204   -> k_seg_bin, k_excl_scan, k_seg_scatter, k_seg_cell
+//   RECM               :206-283   -> k_seg_cell (robust per-cell minimum), k_seg_elev, k_seg_label
+//   RANSAC             :321-479   -> candidate compaction, k_ransac_setup, k_ransac_count
+//   image scatter      :291-318   -> k_seg_image (64-bit atomicMin keys), k_seg_px
+//   JCP                :481-638   -> k_seg_dilate (5x5 stencil on shared-memory tiles),
+//                                    queue compaction, k_jcp_pre, k_jcp_resolve
+//   populateLabels     :640-669   -> epilogue of k_jcp_resolve
+//
+// Ordered semantics on an unordered machine: the reference iterates polar cells in index order
+// and the points of a cell in cloud order. `order` holds exactly that sequence (cells are
+// filled with atomics, then each cell is sorted by point index by one warp), and a point's
+// position in it is (i) its RANSAC candidate rank after a stable compaction and (ii) the low
+// word of its range-image key, so strict-`<` / first-wins ties resolve as in the reference.
+//
+// JCP is a Gauss-Seidel sweep in raster order. A queued pixel only depends on queued pixels
+// that precede it in raster order and lie within the kernel distance, so the sweep is replayed
+// as a data-flow relaxation: weights and mask sources are computed for all queued pixels in
+// parallel (k_jcp_pre), then one CTA per frame fires every pixel whose predecessors are
+// resolved, round after round, on a 2-bit state plane in shared memory (k_jcp_resolve).
+// The reference leaves out-of-image kernel slots untouched, so border pixels inherit those
+// slots from the previously popped pixel (hazard H2); k_jcp_pre reproduces that by
+// locating the most recent earlier queued pixel for which the slot was inside the image.
+#include <cfloat>
+
+#include "common.cuh"
+
+namespace lpl
+{
+__constant__ int c_off_h[24] = {-2, -2, -2, -2, -2, -1, -1, -1, -1, -1, 0, 0,
+                                0,  0,  1,  1,  1,  1,  1,  2,  2,  2,  2, 2};
+__constant__ int c_off_w[24] = {-2, -1, 0, 1, 2, -2, -1, 0, 1, 2, -2, -1,
+                                1,  2,  -2, -1, 0, 1, 2, -2, -1, 0, 1, 2};
+
+// ------------------------------------------------------------------------------------------
+// polar binning (segmenter.cpp:124-203)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_seg_bin(Dev d, SegParams sp)
+{
+    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t n = d.n_v[f];
+    const std::uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    if (i >= n)
+    {
+        return;
+    }
+    const std::size_t o = static_cast<std::size_t>(f) * d.cap;
+    const float4 p = d.pts_v[o + i];
+    std::int32_t cell = -1;
+    std::uint32_t px = 0, slot = 0;
+    if (!(p.z < sp.z_lo || p.z > sp.z_hi))
+    {
+        const float dist = sqrtf(p.x * p.x + p.y * p.y);
+        const std::int32_t radial = static_cast<std::int32_t>(dist / sp.radial_spacing);
+        if (!(dist < sp.min_dist || dist > sp.max_dist || radial >= sp.rings))
+        {
+            float az = atan2_approx(p.y, p.x);
+            az = (az < 0.f) ? (az + 6.28318530717958647692f) : az;
+            const std::int32_t az_idx = min(static_cast<std::int32_t>(az / sp.slice_res), sp.slices - 1);
+            std::int32_t hgt;
+            bool ok = true;
+            if (sp.use_ring)
+            {
+                hgt = static_cast<std::int32_t>(__float_as_uint(p.w) & 0xffffu);
+                ok = hgt < sp.H;
+            }
+            else
+            {
+                const float el = atanf_glibc(p.z / dist);
+                hgt = static_cast<std::int32_t>((el - sp.el_down) / sp.rad_per_px);
+                ok = !(hgt < 0 || hgt >= sp.H);
+            }
+            if (ok)
+            {
+                // static_cast<uint16_t>((W - 1) * az / TWO_M_PIf): float -> int32 -> low 16 bits
+                const std::int32_t wi = static_cast<std::int32_t>(sp.wscale * az / 6.28318530717958647692f);
+                const std::uint32_t wid = static_cast<std::uint32_t>(wi) & 0xffffu;
+                cell = az_idx * sp.rings + radial;
+                px = static_cast<std::uint32_t>(hgt) * sp.W + wid;
+                slot = atomicAdd(&d.cell_cnt[static_cast<std::size_t>(f) * sp.ncell + cell], 1u);
+            }
+        }
+    }
+    d.cell[o + i] = cell;
+    d.px[o + i] = px;
+    d.slot[o + i] = slot;
+}
+
+__global__ void __launch_bounds__(256) k_seg_scatter(Dev d, SegParams sp)
+{
+    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t n = d.n_v[f];
+    const std::uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    if (i >= n)
+    {
+        return;
+    }
+    const std::size_t o = static_cast<std::size_t>(f) * d.cap;
+    const std::int32_t cell = d.cell[o + i];
+    if (cell >= 0)
+    {
+        const std::uint32_t s = d.cell_start[static_cast<std::size_t>(f) * (sp.ncell + 1) + cell];
+        d.order[o + s + d.slot[o + i]] = i;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// per-cell work: restore cloud order, robust minimum (segmenter.cpp:240-260)
+// ------------------------------------------------------------------------------------------
+constexpr int kCellSmem = 1024; // entries per warp
+
+// in-place ascending sort of buf[0..n) by one warp (bitonic network for arbitrary n: the first
+// step of every merge mirrors, so all exchanges move the larger value to the higher index and
+// the virtual +inf padding beyond n is never touched)
+template <typename T>
+__device__ __forceinline__ void warp_sort(T* buf, std::uint32_t n)
+{
+    for (std::uint32_t k = 2; (k >> 1) < n; k <<= 1)
+    {
+        for (std::uint32_t t = lane_id(); t < n; t += 32)
+        {
+            const std::uint32_t u = t ^ (k - 1);
+            if (u > t && u < n)
+            {
+                const T a = buf[t], b = buf[u];
+                if (b < a)
+                {
+                    buf[t] = b;
+                    buf[u] = a;
+                }
+            }
+        }
+        __syncwarp();
+        for (std::uint32_t j = k >> 2; j > 0; j >>= 1)
+        {
+            for (std::uint32_t t = lane_id(); t < n; t += 32)
+            {
+                const std::uint32_t u = t ^ j;
+                if (u > t && u < n)
+                {
+                    const T a = buf[t], b = buf[u];
+                    if (b < a)
+                    {
+                        buf[t] = b;
+                        buf[u] = a;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_seg_cell(Dev d, SegParams sp)
+{
+    __shared__ std::uint32_t sh[4][kCellSmem];
+    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t warp = threadIdx.x >> 5;
+    const std::uint32_t cell = blockIdx.x * 4u + warp;
+    if (cell >= static_cast<std::uint32_t>(sp.ncell))
+    {
+        return;
+    }
+    const std::uint32_t* cs = d.cell_start + static_cast<std::size_t>(f) * (sp.ncell + 1);
+    const std::uint32_t a = cs[cell], n = cs[cell + 1] - a;
+    if (n == 0)
+    {
+        return;
+    }
+    const std::size_t o = static_cast<std::size_t>(f) * d.cap;
+    std::uint32_t* ord = d.order + o + a;
+    const float4* pts = d.pts_v + o;
+    float zmin;
+    std::uint32_t best = 0; // largest i in [1, n/2] with z[i] - z[i-1] > 0.5, 0 = none
+    if (n <= kCellSmem)
+    {
+        std::uint32_t* buf = sh[warp];
+        for (std::uint32_t t = lane_id(); t < n; t += 32)
+        {
+            buf[t] = ord[t];
+        }
+        __syncwarp();
+        warp_sort(buf, n);
+        float* zb = reinterpret_cast<float*>(buf);
+        for (std::uint32_t t = lane_id(); t < n; t += 32)
+        {
+            const std::uint32_t idx = buf[t];
+            ord[t] = idx;
+            zb[t] = pts[idx].z; // same thread, same slot: no hazard
+        }
+        __syncwarp();
+        warp_sort(zb, n);
+        zmin = zb[0];
+        for (std::uint32_t hi = n / 2; hi >= 1 && best == 0;)
+        {
+            // lanes test i = hi - lane
+            const bool valid = hi > lane_id();
+            const std::uint32_t i = hi - lane_id();
+            const bool hit = valid && (zb[i] - zb[i - 1] > 0.5f);
+            const std::uint32_t m = __ballot_sync(0xffffffffu, hit);
+            if (m != 0)
+            {
+                best = hi - (__ffs(m) - 1);
+                zmin = zb[best];
+            }
+            if (hi <= 32)
+            {
+                break;
+            }
+            hi -= 32;
+        }
+    }
+    else
+    {
+        // oversized cell: rank sort through global scratch (slot[] and zsort[] are free here)
+        std::uint32_t* tmp = d.slot + o + a;
+        float* zs = d.zsort + o + a;
+        for (std::uint32_t t = lane_id(); t < n; t += 32)
+        {
+            const std::uint32_t v = ord[t];
+            std::uint32_t r = 0;
+            for (std::uint32_t u = 0; u < n; ++u)
+            {
+                r += (ord[u] < v) ? 1u : 0u;
+            }
+            tmp[r] = v;
+        }
+        __syncwarp();
+        for (std::uint32_t t = lane_id(); t < n; t += 32)
+        {
+            ord[t] = tmp[t];
+        }
+        __syncwarp();
+        float* zt = reinterpret_cast<float*>(tmp);
+        for (std::uint32_t t = lane_id(); t < n; t += 32)
+        {
+            zt[t] = pts[ord[t]].z;
+        }
+        __syncwarp();
+        for (std::uint32_t t = lane_id(); t < n; t += 32)
+        {
+            const float v = zt[t];
+            std::uint32_t r = 0;
+            for (std::uint32_t u = 0; u < n; ++u)
+            {
+                const float w = zt[u];
+                r += (w < v || (w == v && u < t)) ? 1u : 0u;
+            }
+            zs[r] = v;
+        }
+        __syncwarp();
+        zmin = zs[0];
+        for (std::uint32_t hi = n / 2; hi >= 1 && best == 0;)
+        {
+            const bool valid = hi > lane_id();
+            const std::uint32_t i = hi - lane_id();
+            const bool hit = valid && (zs[i] - zs[i - 1] > 0.5f);
+            const std::uint32_t m = __ballot_sync(0xffffffffu, hit);
+            if (m != 0)
+            {
+                best = hi - (__ffs(m) - 1);
+                zmin = zs[best];
+            }
+            if (hi <= 32)
+            {
+                break;
+            }
+            hi -= 32;
+        }
+    }
+    if (lane_id() == 0)
+    {
+        d.cell_zmin[static_cast<std::size_t>(f) * sp.ncell + cell] = zmin;
+    }
+}
+
+// radial recurrence, one thread per azimuth slice (segmenter.cpp:215-267). The repeated
+// `+ delta` is not re-associable bit-exactly, so it stays sequential (50 steps).
+__global__ void __launch_bounds__(128) k_seg_elev(Dev d, SegParams sp)
+{
+    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t s = blockIdx.x * 128u + threadIdx.x;
+    if (s >= static_cast<std::uint32_t>(sp.slices))
+    {
+        return;
+    }
+    const std::uint32_t* cnt = d.cell_cnt + static_cast<std::size_t>(f) * sp.ncell;
+    const float* zmin = d.cell_zmin + static_cast<std::size_t>(f) * sp.ncell;
+    float* elev = d.elev + static_cast<std::size_t>(f) * sp.ncell;
+    float prev = sp.e0;
+    elev[s * sp.rings] = prev;
+    for (int r = 1; r < sp.rings; ++r)
+    {
+        const int c = s * sp.rings + r;
+        float e = prev + sp.delta;
+        if (cnt[c] != 0)
+        {
+            e = fminf(zmin[c], e);
+        }
+        elev[c] = e;
+        prev = e;
+    }
+}
+
+// obstacle classification by sorted position (segmenter.cpp:271-283)
+__global__ void __launch_bounds__(256) k_seg_label(Dev d, SegParams sp, const std::uint32_t* n_binned)
+{
+    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t nb = n_binned[f];
+    const std::uint32_t k = blockIdx.x * 256u + threadIdx.x;
+    if (k >= nb)
+    {
+        return;
+    }
+    const std::size_t o = static_cast<std::size_t>(f) * d.cap;
+    const std::uint32_t i = d.order[o + k];
+    const float z = d.pts_v[o + i].z;
+    const float e = d.elev[static_cast<std::size_t>(f) * sp.ncell + d.cell[o + i]];
+    d.lab[o + k] = (z >= e + sp.thr) ? PX_OBSTACLE : PX_GROUND;
+}
+
+// ------------------------------------------------------------------------------------------
+// near-field RANSAC (segmenter.cpp:321-479)
+// ------------------------------------------------------------------------------------------
+struct CandPred
+{
+    Dev d;
+    SegParams sp;
+    __device__ bool operator()(std::uint32_t f, std::uint32_t k) const
+    {
+        const std::size_t o = static_cast<std::size_t>(f) * d.cap;
+        const std::uint32_t i = d.order[o + k];
+        const std::int32_t c = d.cell[o + i];
+        if ((c % sp.rings) >= kRansacBins)
+        {
+            return false;
+        }
+        const float e = d.elev[static_cast<std::size_t>(f) * sp.ncell + c];
+        return fabsf(e - d.pts_v[o + i].z) < sp.thr2;
+    }
+};
+
+struct CandEmit
+{
+    std::uint32_t* cand;
+    std::uint32_t cap;
+    __device__ void operator()(std::uint32_t f, std::uint32_t k, std::uint32_t pos) const
+    {
+        cand[static_cast<std::size_t>(f) * cap + pos] = k;
+    }
+};
+
+// std::mt19937{42} raw outputs are frame independent (pre-generated on the host); libstdc++'s
+// uniform_int_distribution<uint32_t>{0, n-1} maps them with Lemire's multiply-shift + rejection.
+__device__ __forceinline__ std::uint32_t mt_draw(const std::uint32_t* raw, std::uint32_t& pos,
+                                                 std::uint32_t n, bool& exhausted)
+{
+    auto next = [&]() -> std::uint32_t {
+        if (pos >= kMtRaws)
+        {
+            exhausted = true;
+            return 0u;
+        }
+        return raw[pos++];
+    };
+    unsigned long long product = static_cast<unsigned long long>(next()) * n;
+    std::uint32_t low = static_cast<std::uint32_t>(product);
+    if (low < n)
+    {
+        const std::uint32_t threshold = (0u - n) % n;
+        while (low < threshold && !exhausted)
+        {
+            product = static_cast<unsigned long long>(next()) * n;
+            low = static_cast<std::uint32_t>(product);
+        }
+    }
+    return static_cast<std::uint32_t>(product >> 32);
+}
+
+__global__ void __launch_bounds__(64) k_ransac_setup(Dev d, SegParams sp)
+{
+    __shared__ std::uint32_t pair[kRansacIters][2];
+    const std::uint32_t f = blockIdx.x;
+    const std::uint32_t nc = d.n_cand[f];
+    // a single candidate makes the reference spin forever (segmenter.cpp:382-386); RANSAC is
+    // skipped for nc < 2 here and in the oracle.
+    const bool run = nc >= 2;
+    if (threadIdx.x == 0 && run)
+    {
+        std::uint32_t pos = 0;
+        bool exhausted = false;
+        for (int it = 0; it < kRansacIters; ++it)
+        {
+            const std::uint32_t i2 = mt_draw(d.mt_raw, pos, nc, exhausted);
+            std::uint32_t i3 = mt_draw(d.mt_raw, pos, nc, exhausted);
+            while (i3 == i2 && !exhausted)
+            {
+                i3 = mt_draw(d.mt_raw, pos, nc, exhausted);
+            }
+            pair[it][0] = i2;
+            pair[it][1] = i3;
+        }
+        if (exhausted)
+        {
+            atomicOr(&d.status[f], ST_RNG_EXHAUSTED);
+        }
+    }
+    __syncthreads();
+    const int it = threadIdx.x;
+    if (it >= kRansacIters)
+    {
+        return;
+    }
+    float4 plane = make_float4(0.f, 0.f, __int_as_float(0x7fc00000), 0.f); // skipped
+    if (run)
+    {
+        const std::size_t o = static_cast<std::size_t>(f) * d.cap;
+        const float4 p2 = d.pts_v[o + d.order[o + d.cand[o + pair[it][0]]]];
+        const float4 p3 = d.pts_v[o + d.order[o + d.cand[o + pair[it][1]]]];
+        const float p1x = 0.0f, p1y = 0.0f, p1z = sp.p1z;
+        float nx = ((p2.y - p1y) * (p3.z - p1z)) - ((p2.z - p1z) * (p3.y - p1y));
+        float ny = ((p2.z - p1z) * (p3.x - p1x)) - ((p2.x - p1x) * (p3.z - p1z));
+        float nz = ((p2.x - p1x) * (p3.y - p1y)) - ((p2.y - p1y) * (p3.x - p1x));
+        const float den = (nx * nx) + (ny * ny) + (nz * nz);
+        if (!(den < 1.0e-5f))
+        {
+            const float norm = 1.0f / sqrtf(den);
+            nz *= norm;
+            if (!(fabsf(nz) < sp.cos_max))
+            {
+                nx *= norm;
+                ny *= norm;
+                const float pd = (nx * p1x) + (ny * p1y) + (nz * p1z);
+                plane = make_float4(nx, ny, nz, pd);
+            }
+        }
+    }
+    d.planes[f * kRansacIters + it] = plane;
+    d.inliers[f * kRansacIters + it] = 0;
+}
+
+__global__ void __launch_bounds__(256) k_ransac_count(Dev d, SegParams sp)
+{
+    __shared__ float4 pl[kRansacIters];
+    __shared__ std::uint32_t cnt[kRansacIters];
+    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t nc = d.n_cand[f];
+    if (nc < 2 || blockIdx.x * 256u >= nc)
+    {
+        return;
+    }
+    if (threadIdx.x < kRansacIters)
+    {
+        pl[threadIdx.x] = d.planes[f * kRansacIters + threadIdx.x];
+        cnt[threadIdx.x] = 0;
+    }
+    __syncthreads();
+    const std::uint32_t k = blockIdx.x * 256u + threadIdx.x;
+    const std::size_t o = static_cast<std::size_t>(f) * d.cap;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool live = k < nc;
+    if (live)
+    {
+        p = d.pts_v[o + d.order[o + d.cand[o + k]]];
+    }
+#pragma unroll 4
+    for (int it = 0; it < kRansacIters; ++it)
+    {
+        const float4 q = pl[it];
+        if (q.z != q.z)
+        {
+            continue; // skipped draw (uniform branch)
+        }
+        const float od = fabsf((q.x * p.x) + (q.y * p.y) + (q.z * p.z) - q.w);
+        const std::uint32_t m = __ballot_sync(0xffffffffu, live && od < sp.thr);
+        if (lane_id() == 0 && m != 0)
+        {
+            atomicAdd(&cnt[it], __popc(m));
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < kRansacIters && cnt[threadIdx.x] != 0)
+    {
+        atomicAdd(&d.inliers[f * kRansacIters + threadIdx.x], cnt[threadIdx.x]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// plane application + range-image scatter (segmenter.cpp:434-477, 291-318)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_seg_image(Dev d, SegParams sp, const std::uint32_t* n_binned)
+{
+    __shared__ float4 s_plane;
+    __shared__ int s_have;
+    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t nb = n_binned[f];
+    if (blockIdx.x * 256u >= nb)
+    {
+        return;
+    }
+    if (threadIdx.x == 0)
+    {
+        std::uint32_t best = 0;
+        int sel = -1;
+        if (d.n_cand[f] >= 2)
+        {
+            for (int it = 0; it < kRansacIters; ++it)
+            {
+                const std::uint32_t c = d.inliers[f * kRansacIters + it];
+                if (c > best) // strictly greater: first maximum wins
+                {
+                    best = c;
+                    sel = it;
+                }
+            }
+        }
+        float4 pl = make_float4(0.f, 0.f, 1.f, 0.f);
+        if (sel >= 0)
+        {
+            pl = d.planes[f * kRansacIters + sel];
+            if (pl.z < 0.f)
+            {
+                pl = make_float4(-pl.x, -pl.y, -pl.z, -pl.w);
+            }
+        }
+        s_plane = pl;
+        s_have = sel >= 0;
+        if (blockIdx.x == 0)
+        {
+            d.best_plane[f] = pl;
+            d.best_cnt[f] = best;
+        }
+    }
+    __syncthreads();
+    const std::uint32_t k = blockIdx.x * 256u + threadIdx.x;
+    if (k >= nb)
+    {
+        return;
+    }
+    const std::size_t o = static_cast<std::size_t>(f) * d.cap;
+    const std::uint32_t i = d.order[o + k];
+    const float4 p = d.pts_v[o + i];
+    std::uint8_t l = d.lab[o + k];
+    if (s_have && (d.cell[o + i] % sp.rings) < kRansacBins)
+    {
+        const float4 pl = s_plane;
+        const float sd = (pl.x * p.x) + (pl.y * p.y) + (pl.z * p.z) - pl.w;
+        if (sd < sp.thr)
+        {
+            l = PX_GROUND;
+            d.lab[o + k] = l;
+        }
+    }
+    const float d2 = (p.x * p.x) + (p.y * p.y);
+    const unsigned long long key =
+        (static_cast<unsigned long long>(__float_as_uint(d2)) << 32) | static_cast<unsigned long long>(k);
+    atomicMin(&d.key[static_cast<std::size_t>(f) * sp.npx + d.px[o + i]], key);
+}
+
+__global__ void __launch_bounds__(256) k_seg_px(Dev d, SegParams sp)
+{
+    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t p = blockIdx.x * 256u + threadIdx.x;
+    if (p >= static_cast<std::uint32_t>(sp.npx))
+    {
+        return;
+    }
+    const std::size_t po = static_cast<std::size_t>(f) * sp.npx;
+    const unsigned long long key = d.key[po + p];
+    float4 v = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+    std::uint8_t c = PX_EMPTY;
+    if (key != ~0ULL)
+    {
+        const std::size_t o = static_cast<std::size_t>(f) * d.cap;
+        const std::uint32_t k = static_cast<std::uint32_t>(key & 0xffffffffULL);
+        const std::uint32_t i = d.order[o + k];
+        const float4 q = d.pts_v[o + i];
+        v = make_float4(q.x, q.y, q.z, __int_as_float(static_cast<int>(i)));
+        c = d.lab[o + k];
+    }
+    d.pxpt[po + p] = v;
+    d.code[po + p] = c;
+}
+
+// ------------------------------------------------------------------------------------------
+// 5x5 in-image dilation of the obstacle mask + queue flags (segmenter.cpp:486-514).
+// One CTA per 16 x 128 pixel tile; the tile and its 2-pixel halo are staged in shared memory.
+// ------------------------------------------------------------------------------------------
+constexpr int kDilTh = 16, kDilTw = 128;
+
+__global__ void __launch_bounds__(256) k_seg_dilate(Dev d, SegParams sp)
+{
+    __shared__ std::uint8_t tile[kDilTh + 4][kDilTw + 4 + 4];
+    __shared__ std::uint8_t hmax[kDilTh + 4][kDilTw + 4];
+    const std::uint32_t f = blockIdx.z;
+    const int h0 = blockIdx.y * kDilTh, w0 = blockIdx.x * kDilTw;
+    std::uint8_t* code = d.code + static_cast<std::size_t>(f) * sp.npx;
+    for (int t = threadIdx.x; t < (kDilTh + 4) * (kDilTw + 4); t += 256)
+    {
+        const int r = t / (kDilTw + 4), c = t % (kDilTw + 4);
+        const int h = h0 + r - 2, w = w0 + c - 2;
+        std::uint8_t v = 0;
+        if (h >= 0 && h < sp.H && w >= 0 && w < sp.W)
+        {
+            v = ((code[h * sp.W + w] & 0xf) == PX_OBSTACLE) ? 1 : 0;
+        }
+        tile[r][c] = v;
+    }
+    __syncthreads();
+    // separable maximum: horizontal 5 taps on (kDilTh + 4) rows, then vertical 5 taps
+    for (int t = threadIdx.x; t < (kDilTh + 4) * kDilTw; t += 256)
+    {
+        const int r = t / kDilTw, c = t % kDilTw;
+        hmax[r][c] = tile[r][c] | tile[r][c + 1] | tile[r][c + 2] | tile[r][c + 3] | tile[r][c + 4];
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < kDilTh * kDilTw; t += 256)
+    {
+        const int r = t / kDilTw, c = t % kDilTw;
+        const int h = h0 + r, w = w0 + c;
+        if (h >= sp.H || w >= sp.W)
+        {
+            continue;
+        }
+        const std::uint8_t dil = hmax[r][c] | hmax[r + 1][c] | hmax[r + 2][c] | hmax[r + 3][c] | hmax[r + 4][c];
+        if (dil)
+        {
+            const std::uint8_t cur = code[h * sp.W + w];
+            if (cur == PX_GROUND)
+            {
+                code[h * sp.W + w] = PX_QUEUED;
+            }
+            else if (cur == PX_EMPTY)
+            {
+                code[h * sp.W + w] = PX_EMPTY | PX_DILATED;
+            }
+        }
+    }
+}
+
+struct QueuePred
+{
+    const std::uint8_t* code;
+    std::uint32_t npx;
+    __device__ bool operator()(std::uint32_t f, std::uint32_t p) const
+    {
+        return code[static_cast<std::size_t>(f) * npx + p] == PX_QUEUED;
+    }
+};
+
+struct QueueEmit
+{
+    std::uint32_t* queue;
+    std::uint32_t* status;
+    std::uint32_t qcap;
+    __device__ void operator()(std::uint32_t f, std::uint32_t p, std::uint32_t pos) const
+    {
+        if (pos < qcap)
+        {
+            queue[static_cast<std::size_t>(f) * qcap + pos] = p;
+        }
+        else
+        {
+            atomicOr(&status[f], ST_QUEUE_OVERFLOW);
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// JCP pre-pass: weights and mask sources for every queued pixel (segmenter.cpp:543-607)
+// mask source per slot (2 bits): 0 unknown, 1 ground, 2 obstacle, 3 = final state of a queued
+// pixel that precedes this one in raster order (slots 0..11 only).
+// mk bit 48: the pixel can be decided (|sum| > FLT_EPSILON); bits 49..63: 1 + row of stale_ref.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void jcp_slot(const Dev& d, const SegParams& sp, std::size_t po, const float4& core,
+                                         int hh, int ww, int i, float& wgt, std::uint32_t& msk)
+{
+    const std::uint32_t np = static_cast<std::uint32_t>(hh * sp.W + ww);
+    const float4 q = d.pxpt[po + np];
+    wgt = 0.f;
+    msk = 0;
+    if (__float_as_int(q.w) < 0)
+    {
+        return;
+    }
+    const float dx = core.x - q.x;
+    const float dy = core.y - q.y;
+    const float dz = core.z - q.z;
+    const float d2 = dx * dx + dy * dy + dz * dz;
+    if (d2 > sp.kthr_sqr)
+    {
+        return;
+    }
+    wgt = expf_glibc(-sp.amp * sqrtf(d2));
+    const std::uint8_t c = d.code[po + np] & 0xf;
+    if (c == PX_GROUND)
+    {
+        msk = 1;
+    }
+    else if (c == PX_OBSTACLE)
+    {
+        msk = 2;
+    }
+    else if (c == PX_QUEUED && i < 12)
+    {
+        msk = 3;
+    }
+}
+
+__global__ void __launch_bounds__(128) k_jcp_pre(Dev d, SegParams sp)
+{
+    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t nq = min(d.n_queue[f], d.qcap);
+    const std::uint32_t k = blockIdx.x * 128u + threadIdx.x;
+    if (k >= nq)
+    {
+        return;
+    }
+    const std::size_t po = static_cast<std::size_t>(f) * sp.npx;
+    const std::uint32_t* queue = d.queue + static_cast<std::size_t>(f) * d.qcap;
+    const std::uint32_t p = queue[k];
+    const int h = static_cast<int>(p / sp.W), w = static_cast<int>(p % sp.W);
+    const float4 core = d.pxpt[po + p];
+    float* wn = d.wn + static_cast<std::size_t>(f) * 24 * d.qcap;
+    unsigned long long mk = 0;
+    std::uint32_t brow = 0; // 1 + stale_ref row once allocated
+    float sum = 0.f;
+#pragma unroll 1
+    for (int i = 0; i < 24; ++i)
+    {
+        const int hh = h + c_off_h[i], ww = w + c_off_w[i];
+        float wgt = 0.f;
+        std::uint32_t msk = 0;
+        if (hh >= 0 && hh < sp.H && ww >= 0 && ww < sp.W)
+        {
+            jcp_slot(d, sp, po, core, hh, ww, i, wgt, msk);
+            if (wgt != 0.f)
+            {
+                sum += wgt;
+            }
+        }
+        else if (sp.jcp_emulate_stale)
+        {
+            // most recent earlier queued pixel for which slot i lies inside the image
+            for (std::uint32_t kk = k; kk-- > 0;)
+            {
+                const std::uint32_t pp = queue[kk];
+                const int h2 = static_cast<int>(pp / sp.W), w2 = static_cast<int>(pp % sp.W);
+                const int hh2 = h2 + c_off_h[i], ww2 = w2 + c_off_w[i];
+                if (hh2 >= 0 && hh2 < sp.H && ww2 >= 0 && ww2 < sp.W)
+                {
+                    jcp_slot(d, sp, po, d.pxpt[po + pp], hh2, ww2, i, wgt, msk);
+                    if (msk == 3)
+                    {
+                        if (brow == 0)
+                        {
+                            const std::uint32_t r = atomicAdd(&d.n_border[f], 1u);
+                            if (r < d.nborder_cap)
+                            {
+                                brow = r + 1;
+                            }
+                            else
+                            {
+                                atomicOr(&d.status[f], ST_BORDER_OVERFLOW);
+                            }
+                        }
+                        if (brow != 0)
+                        {
+                            d.stale_ref[(static_cast<std::size_t>(f) * d.nborder_cap + (brow - 1)) * 12 + i] =
+                                static_cast<std::uint32_t>(hh2 * sp.W + ww2);
+                        }
+                        else
+                        {
+                            msk = 0;
+                        }
+                    }
+                    break;
+                }
+                if (hh2 < 0)
+                {
+                    break; // every earlier queued pixel sits in the same or a lower row
+                }
+            }
+        }
+        wn[static_cast<std::size_t>(i) * d.qcap + k] = wgt; // raw weight, normalised below
+        mk |= static_cast<unsigned long long>(msk) << (2 * i);
+    }
+    const bool decidable = fabsf(sum) > FLT_EPSILON;
+#pragma unroll 4
+    for (int i = 0; i < 24; ++i)
+    {
+        float* slot = wn + static_cast<std::size_t>(i) * d.qcap + k;
+        *slot = decidable ? (*slot / sum) : 0.f; // weight_matrix = unnormalized / sum (segmenter.cpp:611)
+    }
+    mk |= static_cast<unsigned long long>(decidable ? 1 : 0) << 48;
+    mk |= static_cast<unsigned long long>(brow) << 49;
+    d.mk[static_cast<std::size_t>(f) * d.qcap + k] = mk;
+}
+
+// ------------------------------------------------------------------------------------------
+// JCP relaxation: one CTA per frame, 2-bit state plane in shared memory
+// (0 unknown / empty / undecided, 1 ground, 2 obstacle, 3 queued and not yet relaxed).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ std::uint32_t plane_get(const volatile std::uint32_t* plane, std::uint32_t p)
+{
+    return (plane[p >> 4] >> ((p & 15u) * 2u)) & 3u;
+}
+
+__global__ void __launch_bounds__(1024) k_jcp_resolve(Dev d, SegParams sp, int want_image)
+{
+    extern __shared__ std::uint32_t plane[]; // npx / 16 words
+    __shared__ std::uint32_t s_next;
+    const std::uint32_t f = blockIdx.x;
+    const std::size_t po = static_cast<std::size_t>(f) * sp.npx;
+    std::uint8_t* code = d.code + po;
+    const std::uint32_t nwords = (sp.npx + 15) / 16;
+    for (std::uint32_t wi = threadIdx.x; wi < nwords; wi += blockDim.x)
+    {
+        std::uint32_t v = 0;
+        // 16 pixels = 16 bytes of code
+        const uint4 raw = *reinterpret_cast<const uint4*>(code + static_cast<std::size_t>(wi) * 16);
+        const std::uint32_t r[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int b = 0; b < 16; ++b)
+        {
+            const std::uint32_t c = (r[b >> 2] >> ((b & 3) * 8)) & 0xfu;
+            v |= (c & 3u) << (2 * b); // EMPTY 0, GROUND 1, OBSTACLE 2, QUEUED 3
+        }
+        plane[wi] = v;
+    }
+    const std::uint32_t nq = min(d.n_queue[f], d.qcap);
+    const std::uint32_t* queue = d.queue + static_cast<std::size_t>(f) * d.qcap;
+    const unsigned long long* mkv = d.mk + static_cast<std::size_t>(f) * d.qcap;
+    const float* wn = d.wn + static_cast<std::size_t>(f) * 24 * d.qcap;
+    std::uint32_t* pend0 = d.pend + static_cast<std::size_t>(f) * 2 * d.qcap;
+    std::uint32_t* pend1 = pend0 + d.qcap;
+    const std::uint32_t* sref = d.stale_ref + static_cast<std::size_t>(f) * d.nborder_cap * 12;
+    std::uint32_t np = nq, rounds = 0;
+    bool first = true;
+    __syncthreads();
+    while (np != 0)
+    {
+        if (threadIdx.x == 0)
+        {
+            s_next = 0;
+        }
+        __syncthreads();
+        for (std::uint32_t j = threadIdx.x; j < np; j += blockDim.x)
+        {
+            const std::uint32_t k = first ? j : pend0[j];
+            const unsigned long long m = mkv[k];
+            const std::uint32_t p = queue[k];
+            const int h = static_cast<int>(p / sp.W), w = static_cast<int>(p % sp.W);
+            const std::uint32_t brow = static_cast<std::uint32_t>(m >> 49);
+            bool ready = true;
+            std::uint32_t dyn_state = 0; // 2 bits per slot 0..11 once resolved
+#pragma unroll
+            for (int i = 0; i < 12; ++i)
+            {
+                if (((m >> (2 * i)) & 3ULL) == 3ULL)
+                {
+                    const int hh = h + c_off_h[i], ww = w + c_off_w[i];
+                    std::uint32_t ref;
+                    if (hh >= 0 && hh < sp.H && ww >= 0 && ww < sp.W)
+                    {
+                        ref = static_cast<std::uint32_t>(hh * sp.W + ww);
+                    }
+                    else
+                    {
+                        ref = sref[static_cast<std::size_t>(brow - 1) * 12 + i];
+                    }
+                    const std::uint32_t s = plane_get(plane, ref);
+                    if (s == 3u)
+                    {
+                        ready = false;
+                    }
+                    dyn_state |= s << (2 * i);
+                }
+            }
+            if (!ready)
+            {
+                const std::uint32_t pos = atomicAdd(&s_next, 1u);
+                pend1[pos] = k;
+                continue;
+            }
+            std::uint32_t out = 0;
+            if ((m >> 48) & 1ULL)
+            {
+                float wo = 0.f, wg = 0.f;
+#pragma unroll
+                for (int i = 0; i < 24; ++i)
+                {
+                    std::uint32_t mi = static_cast<std::uint32_t>((m >> (2 * i)) & 3ULL);
+                    if (mi == 3u)
+                    {
+                        mi = (dyn_state >> (2 * i)) & 3u; // i < 12 by construction
+                    }
+                    if (mi == 1u)
+                    {
+                        wg += wn[static_cast<std::size_t>(i) * d.qcap + k];
+                    }
+                    else if (mi == 2u)
+                    {
+                        wo += wn[static_cast<std::size_t>(i) * d.qcap + k];
+                    }
+                }
+                out = (wo > wg) ? 2u : 1u;
+            }
+            // 3 -> out: clear the bits that differ
+            atomicAnd(&plane[p >> 4], ~((3u ^ out) << ((p & 15u) * 2u)));
+            code[p] = (out == 0u) ? PX_UNDECIDED : static_cast<std::uint8_t>(out);
+        }
+        __syncthreads();
+        np = s_next;
+        std::uint32_t* t = pend0;
+        pend0 = pend1;
+        pend1 = t;
+        first = false;
+        ++rounds;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+    {
+        d.jcp_rounds[f] = rounds;
+    }
+    // ---- populateLabels (segmenter.cpp:640-669): only pixel winners receive a label
+    const std::size_t o = static_cast<std::size_t>(f) * d.cap;
+    for (std::uint32_t p = threadIdx.x; p < static_cast<std::uint32_t>(sp.npx); p += blockDim.x)
+    {
+        const std::uint8_t cfull = code[p];
+        const std::uint8_t c = cfull & 0xf;
+        if (c == PX_GROUND || c == PX_OBSTACLE)
+        {
+            const int idx = __float_as_int(d.pxpt[po + p].w);
+            if (idx >= 0)
+            {
+                d.seg_label[o + idx] = c;
+                d.labels_out[o + d.idx_v[o + idx]] = c;
+            }
+        }
+        if (want_image)
+        {
+            std::uint8_t b = 0, g = 0, r = 0;
+            if (c == PX_GROUND)
+            {
+                g = 255;
+            }
+            else if (c == PX_OBSTACLE)
+            {
+                r = 255;
+            }
+            else if (c == PX_QUEUED || c == PX_UNDECIDED)
+            {
+                b = 255;
+            }
+            else if (cfull & PX_DILATED)
+            {
+                r = 255;
+            }
+            std::uint8_t* px = d.bgr + (po + p) * 3;
+            px[0] = b;
+            px[1] = g;
+            px[2] = r;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+void launch_segment(Ctx* c, std::uint32_t nf, bool want_image)
+{
+    Dev& d = c->d;
+    const SegParams& sp = c->seg;
+    cudaStream_t s = c->stream;
+    // per-batch resets
+    cudaMemsetAsync(d.cell_cnt, 0, sizeof(std::uint32_t) * sp.ncell * nf, s);
+    cudaMemsetAsync(d.key, 0xff, sizeof(unsigned long long) * sp.npx * nf, s);
+    cudaMemsetAsync(d.seg_label, 0, static_cast<std::size_t>(d.cap) * nf, s);
+    cudaMemsetAsync(d.labels_out, 0, sizeof(std::uint32_t) * static_cast<std::size_t>(d.cap) * nf, s);
+    cudaMemsetAsync(d.n_border, 0, sizeof(std::uint32_t) * nf, s);
+
+    const dim3 gpts((d.cap + 255) / 256, nf);
+    k_seg_bin<<<gpts, 256, 0, s>>>(d, sp);
+    k_excl_scan<<<nf, 1024, 0, s>>>(d.cell_cnt, sp.ncell, d.cell_start, sp.ncell + 1,
+                                    static_cast<std::uint32_t>(sp.ncell), nullptr, d.n_binned);
+    k_seg_scatter<<<gpts, 256, 0, s>>>(d, sp);
+    k_seg_cell<<<dim3((sp.ncell + 3) / 4, nf), 128, 0, s>>>(d, sp);
+    k_seg_elev<<<dim3((sp.slices + 127) / 128, nf), 128, 0, s>>>(d, sp);
+    const std::uint32_t* n_binned = d.n_binned;
+    k_seg_label<<<gpts, 256, 0, s>>>(d, sp, n_binned);
+    launch_compact(s, nf, d.tiles, n_binned, 0u, d.tile_cnt, d.n_cand, CandPred{d, sp},
+                   CandEmit{d.cand, d.cap});
+    k_ransac_setup<<<nf, 64, 0, s>>>(d, sp);
+    k_ransac_count<<<gpts, 256, 0, s>>>(d, sp);
+    k_seg_image<<<gpts, 256, 0, s>>>(d, sp, n_binned);
+    k_seg_px<<<dim3((sp.npx + 255) / 256, nf), 256, 0, s>>>(d, sp);
+    k_seg_dilate<<<dim3((sp.W + kDilTw - 1) / kDilTw, (sp.H + kDilTh - 1) / kDilTh, nf), 256, 0, s>>>(d, sp);
+    launch_compact(s, nf, d.ptiles, nullptr, static_cast<std::uint32_t>(sp.npx), d.tile_cnt, d.n_queue,
+                   QueuePred{d.code, static_cast<std::uint32_t>(sp.npx)},
+                   QueueEmit{d.queue, d.status, d.qcap});
+    k_jcp_pre<<<dim3((d.qcap + 127) / 128, nf), 128, 0, s>>>(d, sp);
+    const std::size_t plane_bytes = static_cast<std::size_t>((sp.npx + 15) / 16) * 4;
+    k_jcp_resolve<<<nf, 1024, plane_bytes, s>>>(d, sp, want_image ? 1 : 0);
+    c->launches += 17;
+}
+} // namespace lpl

@@ -1,0 +1,380 @@
+"""ctypes binding of include/lpl_b200.h (the C-ABI shared library liblpl_b200.so).
+
+This is the only way Python reaches the product path; it never imports oracle/ and has no CPU
+fallback: without the library or without a CUDA device every call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+LPL_OK = 0
+LPL_ERR_INVALID_ARGUMENT = -1
+LPL_ERR_CUDA = -2
+LPL_ERR_CAPACITY = -3
+LPL_ERR_NO_DEVICE = -4
+
+JCP_AS_REFERENCE = 0
+JCP_CLEAN = 1
+
+STAGE_RING, STAGE_DROR, STAGE_SEGMENT, STAGE_CLUSTER, STAGE_HULLS = 1, 2, 4, 8, 16
+STAGE_ALL = 31
+
+# every symbol include/lpl_b200.h declares (tests check that the library exports them all)
+EXPORTS = [
+    "lpl_create", "lpl_destroy", "lpl_last_error", "lpl_version",
+    "lpl_segmenter_default_cfg", "lpl_dror_default_cfg", "lpl_cluster_default_cfg",
+    "lpl_segmenter_config", "lpl_dror_config", "lpl_cluster_config", "lpl_set_jcp_mode",
+    "lpl_ring_partition", "lpl_dror_filter", "lpl_segment", "lpl_cluster", "lpl_convex_hull",
+    "lpl_cluster_hulls",
+    "lpl_pipeline_upload", "lpl_pipeline_upload_device", "lpl_pipeline_run", "lpl_pipeline_sync",
+    "lpl_pipeline_want_image", "lpl_pipeline_counts", "lpl_pipeline_download",
+    "lpl_timer_start", "lpl_timer_stop_ms", "lpl_launch_count", "lpl_debug_segment",
+    "lpl_debug_cluster", "lpl_stream",
+]
+
+
+class SegmenterCfg(C.Structure):
+    """lpl_segmenter_cfg == SegmenterConfiguration (segmenter.hpp:87-112)."""
+
+    _fields_ = [
+        ("elevation_up_deg", C.c_float),
+        ("elevation_down_deg", C.c_float),
+        ("image_width", C.c_int32),
+        ("image_height", C.c_int32),
+        ("assume_unorganized_cloud", C.c_int32),
+        ("grid_radial_spacing_m", C.c_float),
+        ("grid_slice_resolution_deg", C.c_float),
+        ("ground_height_threshold_m", C.c_float),
+        ("road_maximum_slope_m_per_m", C.c_float),
+        ("min_distance_m", C.c_float),
+        ("max_distance_m", C.c_float),
+        ("sensor_height_m", C.c_float),
+        ("kernel_threshold_distance_m", C.c_float),
+        ("amplification_factor", C.c_float),
+        ("z_min_m", C.c_float),
+        ("z_max_m", C.c_float),
+    ]
+
+
+class DrorCfg(C.Structure):
+    _fields_ = [
+        ("radius_multiplier_m_per_m", C.c_float),
+        ("min_search_radius_m", C.c_float),
+        ("min_neighbours", C.c_uint32),
+    ]
+
+
+class ClusterCfg(C.Structure):
+    _fields_ = [
+        ("voxel_grid_range_resolution_m", C.c_float),
+        ("voxel_grid_azimuth_resolution_deg", C.c_float),
+        ("voxel_grid_elevation_resolution_deg", C.c_float),
+        ("min_cluster_size", C.c_uint32),
+    ]
+
+
+class Frame(C.Structure):
+    _fields_ = [("xyzw", C.c_void_p), ("n", C.c_uint32), ("ring", C.c_void_p)]
+
+
+class FrameResult(C.Structure):
+    _fields_ = [
+        ("noise", C.c_void_p),
+        ("ring", C.c_void_p),
+        ("labels", C.c_void_p),
+        ("obstacle_index", C.c_void_p),
+        ("cluster_labels", C.c_void_p),
+        ("hull_offsets", C.c_void_p),
+        ("hull_indices", C.c_void_p),
+        ("hull_xy", C.c_void_p),
+        ("zminmax", C.c_void_p),
+        ("bgr", C.c_void_p),
+        ("n", C.c_uint32),
+        ("num_valid", C.c_uint32),
+        ("num_obstacles", C.c_uint32),
+        ("num_clusters", C.c_uint32),
+        ("num_hull_vertices", C.c_uint32),
+    ]
+
+
+class LplError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"lpl_b200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load_library(path: str | None = None) -> C.CDLL:
+    """dlopen liblpl_b200.so (building it first if the sources are newer). No GPU needed to load."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    so = path or _build.SO_PATH
+    if path is None and _build.needs_build():
+        _build.build_native()
+    if not os.path.exists(so):
+        raise LplError(LPL_ERR_NO_DEVICE, f"{so} is missing: the CUDA extension was not built "
+                       "(there is no CPU fallback)")
+    L = C.CDLL(so)
+    vp, u32, i32, sz = C.c_void_p, C.c_uint32, C.c_int32, C.c_size_t
+    L.lpl_create.argtypes = [C.POINTER(vp), C.c_int, u32, u32, i32, i32]
+    L.lpl_create.restype = C.c_int
+    L.lpl_destroy.argtypes = [vp]
+    L.lpl_destroy.restype = None
+    L.lpl_last_error.argtypes = [vp]
+    L.lpl_last_error.restype = C.c_char_p
+    L.lpl_version.restype = C.c_char_p
+    L.lpl_segmenter_default_cfg.argtypes = [C.POINTER(SegmenterCfg)]
+    L.lpl_dror_default_cfg.argtypes = [C.POINTER(DrorCfg)]
+    L.lpl_cluster_default_cfg.argtypes = [C.POINTER(ClusterCfg)]
+    L.lpl_segmenter_config.argtypes = [vp, C.POINTER(SegmenterCfg)]
+    L.lpl_dror_config.argtypes = [vp, C.POINTER(DrorCfg)]
+    L.lpl_cluster_config.argtypes = [vp, C.POINTER(ClusterCfg)]
+    L.lpl_set_jcp_mode.argtypes = [vp, C.c_int]
+    L.lpl_ring_partition.argtypes = [vp, vp, sz, u32, vp]
+    L.lpl_dror_filter.argtypes = [vp, vp, sz, u32, vp]
+    L.lpl_segment.argtypes = [vp, vp, sz, i32, u32, vp, vp]
+    L.lpl_cluster.argtypes = [vp, vp, sz, u32, vp, C.POINTER(u32)]
+    L.lpl_convex_hull.argtypes = [vp, vp, sz, u32, vp, C.POINTER(u32)]
+    L.lpl_cluster_hulls.argtypes = [vp, vp, sz, vp, u32, u32, vp, vp, vp, vp]
+    L.lpl_pipeline_upload.argtypes = [vp, C.POINTER(Frame), u32]
+    L.lpl_pipeline_upload_device.argtypes = [vp, C.POINTER(Frame), u32]
+    L.lpl_pipeline_run.argtypes = [vp, u32, u32]
+    L.lpl_pipeline_sync.argtypes = [vp, u32]
+    L.lpl_pipeline_want_image.argtypes = [vp, C.c_int]
+    L.lpl_pipeline_counts.argtypes = [vp, u32, C.POINTER(FrameResult)]
+    L.lpl_pipeline_download.argtypes = [vp, u32, C.POINTER(FrameResult)]
+    L.lpl_timer_start.argtypes = [vp]
+    L.lpl_timer_stop_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.lpl_launch_count.argtypes = [vp, C.c_int]
+    L.lpl_launch_count.restype = C.c_uint64
+    L.lpl_debug_segment.argtypes = [vp, u32, vp, vp, vp, vp]
+    L.lpl_debug_cluster.argtypes = [vp, u32, vp]
+    L.lpl_stream.argtypes = [vp]
+    L.lpl_stream.restype = vp
+    for name in ("lpl_segmenter_config", "lpl_dror_config", "lpl_cluster_config", "lpl_set_jcp_mode",
+                 "lpl_ring_partition", "lpl_dror_filter", "lpl_segment", "lpl_cluster",
+                 "lpl_convex_hull", "lpl_cluster_hulls", "lpl_pipeline_upload",
+                 "lpl_pipeline_upload_device", "lpl_pipeline_run", "lpl_pipeline_sync",
+                 "lpl_pipeline_want_image", "lpl_pipeline_counts", "lpl_pipeline_download",
+                 "lpl_timer_start", "lpl_timer_stop_ms", "lpl_debug_segment", "lpl_debug_cluster"):
+        getattr(L, name).restype = C.c_int
+    if path is None:
+        _lib = L
+    return L
+
+
+def _points_arg(pts):
+    """(pointer, stride_bytes, n, keepalive) for an (n, >=3) float32 array."""
+    a = np.ascontiguousarray(pts, dtype=np.float32)
+    if a.ndim != 2 or a.shape[1] < 3:
+        raise ValueError("points must be (n, >=3) float32")
+    return a.ctypes.data, a.shape[1] * 4, a.shape[0], a
+
+
+class Context:
+    """Owns one lpl_ctx (one CUDA stream + all device scratch)."""
+
+    def __init__(self, device: int = 0, max_points: int = 131072, max_frames: int = 1,
+                 image_height: int = 64, image_width: int = 2048):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.lpl_create(C.byref(h), device, max_points, max_frames, image_height, image_width)
+        if rc != 0:
+            msg = {LPL_ERR_NO_DEVICE: "no CUDA device (the hot path has no CPU fallback)",
+                   LPL_ERR_CAPACITY: "device allocation failed"}.get(rc, "lpl_create failed")
+            raise LplError(rc, msg)
+        self.h = h
+        self.max_points = max_points
+        self.max_frames = max_frames
+        self.H, self.W = image_height, image_width
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.lpl_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc: int):
+        if rc != 0:
+            raise LplError(rc, self.lib.lpl_last_error(self.h).decode(errors="replace"))
+
+    # ---- configuration
+    def segmenter_default_cfg(self) -> SegmenterCfg:
+        c = SegmenterCfg()
+        self.lib.lpl_segmenter_default_cfg(C.byref(c))
+        return c
+
+    def segmenter_config(self, cfg: SegmenterCfg):
+        self._chk(self.lib.lpl_segmenter_config(self.h, C.byref(cfg)))
+
+    def dror_config(self, mult=0.02, min_radius=0.1, min_neighbours=4):
+        self._chk(self.lib.lpl_dror_config(self.h, C.byref(DrorCfg(mult, min_radius, min_neighbours))))
+
+    def cluster_config(self, range_m=0.4, az_deg=1.0, el_deg=1.5, min_size=3):
+        self._chk(self.lib.lpl_cluster_config(self.h, C.byref(ClusterCfg(range_m, az_deg, el_deg, min_size))))
+
+    def set_jcp_mode(self, mode: int):
+        self._chk(self.lib.lpl_set_jcp_mode(self.h, mode))
+
+    # ---- single-frame entry points
+    def ring_partition(self, pts) -> np.ndarray:
+        p, stride, n, keep = _points_arg(pts)
+        out = np.zeros(n, np.uint16)
+        self._chk(self.lib.lpl_ring_partition(self.h, p, stride, n, out.ctypes.data))
+        return out
+
+    def dror_filter(self, pts) -> np.ndarray:
+        p, stride, n, keep = _points_arg(pts)
+        out = np.zeros(n, np.uint8)
+        self._chk(self.lib.lpl_dror_filter(self.h, p, stride, n, out.ctypes.data))
+        return out
+
+    def segment(self, pts, ring=None, want_image=False):
+        """pts (n, >=3) float32; ring (n,) uint16 or None (ring-less point type)."""
+        a = np.ascontiguousarray(pts, dtype=np.float32)
+        n = a.shape[0]
+        if ring is not None:
+            # build PointXYZIR-like records: x y z pad | intensity ring(u16) pad  (32 bytes)
+            rec = np.zeros((n, 8), np.float32)
+            rec[:, :3] = a[:, :3]
+            rec.view(np.uint16).reshape(n, 16)[:, 10] = np.asarray(ring, np.uint16)
+            p, stride, roff, keep = rec.ctypes.data, 32, 20, rec
+        else:
+            p, stride, roff, keep = a.ctypes.data, a.shape[1] * 4, -1, a
+        labels = np.zeros(n, np.uint32)
+        img = np.zeros((self.H, self.W, 3), np.uint8) if want_image else None
+        self._chk(self.lib.lpl_segment(self.h, p, stride, roff, n, labels.ctypes.data,
+                                       img.ctypes.data if want_image else None))
+        return (labels, img) if want_image else labels
+
+    def cluster(self, pts):
+        p, stride, n, keep = _points_arg(pts)
+        out = np.full(n, -1, np.int32)
+        k = C.c_uint32(0)
+        self._chk(self.lib.lpl_cluster(self.h, p, stride, n, out.ctypes.data, C.byref(k)))
+        return out, k.value
+
+    def convex_hull(self, xy) -> np.ndarray:
+        a = np.ascontiguousarray(xy, dtype=np.float64)
+        n = a.shape[0]
+        idx = np.zeros(max(n, 1), np.int32)
+        cnt = C.c_uint32(0)
+        self._chk(self.lib.lpl_convex_hull(self.h, a.ctypes.data, a.shape[1] * 8, n, idx.ctypes.data,
+                                           C.byref(cnt)))
+        return idx[: cnt.value].copy()
+
+    def cluster_hulls(self, pts, labels, num_clusters=None):
+        p, stride, n, keep = _points_arg(pts)
+        lab = np.ascontiguousarray(labels, np.int32)
+        K = int(lab.max()) + 1 if (num_clusters is None and n) else int(num_clusters or 0)
+        K = max(K, 0)
+        off = np.zeros(K + 1, np.uint32)
+        hidx = np.zeros(max(n, 1), np.int32)
+        hxy = np.zeros((max(n, 1), 2), np.float32)
+        zmm = np.zeros((max(K, 1), 2), np.float32)
+        self._chk(self.lib.lpl_cluster_hulls(self.h, p, stride, lab.ctypes.data, n, K, off.ctypes.data,
+                                             hidx.ctypes.data, hxy.ctypes.data, zmm.ctypes.data))
+        tot = int(off[K]) if K else 0
+        return off, hxy[:tot].copy(), hidx[:tot].copy(), zmm[:K].copy()
+
+    # ---- batched pipeline
+    def upload(self, frames, rings=None, device=False):
+        """frames: list of (n, 4) float32 arrays (host) or list of (device_ptr, n) when device."""
+        nf = len(frames)
+        arr = (Frame * nf)()
+        keep = []
+        for i, fr in enumerate(frames):
+            if device:
+                ptr, n = fr
+                arr[i].xyzw, arr[i].n = ptr, n
+                arr[i].ring = rings[i] if rings is not None else None
+            else:
+                a = np.ascontiguousarray(fr, dtype=np.float32)
+                assert a.ndim == 2 and a.shape[1] == 4, "pipeline frames are (n, 4) float32"
+                keep.append(a)
+                arr[i].xyzw, arr[i].n = a.ctypes.data, a.shape[0]
+                if rings is not None and rings[i] is not None:
+                    r = np.ascontiguousarray(rings[i], np.uint16)
+                    keep.append(r)
+                    arr[i].ring = r.ctypes.data
+        fn = self.lib.lpl_pipeline_upload_device if device else self.lib.lpl_pipeline_upload
+        self._chk(fn(self.h, arr, nf))
+        self._keep = keep
+        return nf
+
+    def run(self, nf: int, stages: int = STAGE_ALL):
+        self._chk(self.lib.lpl_pipeline_run(self.h, nf, stages))
+
+    def sync(self, nf: int):
+        self._chk(self.lib.lpl_pipeline_sync(self.h, nf))
+
+    def want_image(self, enable: bool):
+        self._chk(self.lib.lpl_pipeline_want_image(self.h, 1 if enable else 0))
+
+    def counts(self, f: int) -> FrameResult:
+        r = FrameResult()
+        self._chk(self.lib.lpl_pipeline_counts(self.h, f, C.byref(r)))
+        return r
+
+    def download(self, f: int, want_image=False) -> dict:
+        r = self.counts(f)
+        out = dict(
+            noise=np.zeros(r.n, np.uint8), ring=np.zeros(r.n, np.uint16), labels=np.zeros(r.n, np.uint32),
+            obstacle_index=np.zeros(r.num_obstacles, np.uint32),
+            cluster_labels=np.zeros(r.num_obstacles, np.int32),
+            hull_offsets=np.zeros(r.num_clusters + 1, np.uint32),
+            hull_indices=np.zeros(r.num_hull_vertices, np.uint32),
+            hull_xy=np.zeros((r.num_hull_vertices, 2), np.float32),
+            zminmax=np.zeros((r.num_clusters, 2), np.float32),
+        )
+        if want_image:
+            out["bgr"] = np.zeros((self.H, self.W, 3), np.uint8)
+        for k, v in out.items():
+            setattr(r, k, v.ctypes.data if v.size else None)
+        self._chk(self.lib.lpl_pipeline_download(self.h, f, C.byref(r)))
+        out.update(n=r.n, num_valid=r.num_valid, num_obstacles=r.num_obstacles,
+                   num_clusters=r.num_clusters, num_hull_vertices=r.num_hull_vertices)
+        return out
+
+    # ---- measurement / debugging
+    def timer_start(self):
+        self._chk(self.lib.lpl_timer_start(self.h))
+
+    def timer_stop_ms(self) -> float:
+        ms = C.c_float(0)
+        self._chk(self.lib.lpl_timer_stop_ms(self.h, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self, reset=False) -> int:
+        return int(self.lib.lpl_launch_count(self.h, 1 if reset else 0))
+
+    def debug_segment(self, f: int = 0) -> dict:
+        cnt = np.zeros(8, np.uint32)
+        self._chk(self.lib.lpl_debug_segment(self.h, f, None, None, None, cnt.ctypes.data))
+        slices, rings = int(cnt[5]), int(cnt[6])
+        elev = np.zeros(slices * rings, np.float32)
+        plane = np.zeros(4, np.float32)
+        best = C.c_uint32(0)
+        self._chk(self.lib.lpl_debug_segment(self.h, f, elev.ctypes.data, plane.ctypes.data, C.byref(best),
+                                             cnt.ctypes.data))
+        return dict(elevation=elev.reshape(slices, rings), plane=plane, best_inliers=best.value,
+                    n_binned=int(cnt[0]), n_candidates=int(cnt[1]), n_queued=int(cnt[2]),
+                    rounds=int(cnt[3]), border_rows=int(cnt[4]), status=int(cnt[7]))
+
+    def debug_cluster(self, f: int = 0) -> np.ndarray:
+        dims = np.zeros(3, np.int32)
+        self._chk(self.lib.lpl_debug_cluster(self.h, f, dims.ctypes.data))
+        return dims
