@@ -1,0 +1,488 @@
+#!/usr/bin/env python
+"""Benchmark of the per-frame LiDAR perception hot path on B200 (driver contract: see README/DESIGN).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+A *step* is one pass of the whole hot path (ring partition -> DROR -> JCP/RECM segmentation ->
+curved-voxel clustering -> per-cluster hulls) over one batch of frames on every rank:
+
+  workload "kitti154"  BASELINE.json configs[1]: the reference's 154 KITTI HDL-64E frames
+                       (18.7 M points, 300 MB of float4 input > the 126 MB L2, so no L2 flush is needed)
+                       as one batch; every rank runs its own copy (weak scaling, no collective on
+                       the data path - NCCL only reduces the timing).
+  workload "synth64"   used only when data/kitti154.npz is absent: seeded synthetic HDL-64E sweeps.
+
+`value`  = frames/s with the inputs already resident in HBM (CUDA events on the context stream).
+`e2e`    = frames/s through the C ABI with HOST buffers: every step uploads the batch from pinned
+           host memory, runs the pipeline and reads labels / clusters / hulls back; two contexts are
+           double-buffered so copies overlap compute.
+`roofline` describes the dominant kernel (largest share of the step) from per-kernel CUDA events
+recorded inside the timed region; `cpu_baseline` / `--impl reference` time the reference's own CPU
+code (oracle/_ref, compiled from the unmodified sources) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "frames/s (HDL-64E ~120k pts/frame: ring partition + DROR + JCP segmentation + curved-voxel clustering + hulls)"
+UNIT = "frames/s"
+
+
+# --------------------------------------------------------------------------------------------
+# workload
+# --------------------------------------------------------------------------------------------
+def load_frames(limit=None):
+    from tools import frames as F
+
+    if F.have_pack():
+        fr = F.load_pack(limit=limit)
+        return fr, "kitti154", "KITTI HDL-64E frames of the reference repository (data/*.pcd, repacked)"
+    n = limit or 154
+    base = [F.synth_scan(4000 + i)[0] for i in range(min(n, 16))]
+    fr = [base[i % len(base)] for i in range(n)]
+    return fr, "synth64", "synthetic HDL-64E sweeps (seeded ray-cast scenes; data/kitti154.npz absent)"
+
+
+# --------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            t = [x.strip() for x in r.split(",")]
+            if len(t) < 7:
+                continue
+            try:
+                sm.append(float(t[0]))
+                mx.append(float(t[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, t[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+# roofline bookkeeping: algorithmic bytes per kernel (DESIGN.md "Kernels and their rooflines")
+# --------------------------------------------------------------------------------------------
+def algorithmic_bytes(name: str, s: dict) -> float:
+    """Compulsory HBM bytes of one launch of kernel `name` over the batch described by `s`
+    (N input points, V DROR-valid points, NB binned points, M obstacle points, K clusters,
+    HV hull vertices, PX pixels, CELLS polar cells, Q queued pixels, C RANSAC candidates,
+    U DROR-unresolved points, F frames)."""
+    N, V, NB, M, K, HV = s["N"], s["V"], s["NB"], s["M"], s["K"], s["HV"]
+    PX, CELLS, Q, C, U, F = s["PX"], s["CELLS"], s["Q"], s["C"], s["U"], s["F"]
+    t = {
+        "ring_count": 16 * N, "ring_write": 16 * N + 2 * N,
+        "dror_near": 16 * N + 1 * N + 4 * U,
+        "dror_grid_count": 16 * N, "dror_grid_scan": 8 * 65536 * F, "dror_grid_scatter": 32 * N,
+        "dror_query": 20 * U + U,
+        "take_valid": (16 + 2 + 1) * N + 20 * V, "take_all": (16 + 2) * N + 20 * V,
+        "seg_bin": 16 * V + 12 * V, "seg_cell_scan": 8 * CELLS, "seg_scatter": 12 * V + 4 * NB,
+        "seg_cell": 8 * NB + 4 * NB + 4 * CELLS, "seg_elev": 12 * CELLS,
+        "seg_label": 4 * NB + 4 * NB + 4 * NB + 1 * NB,
+        "ransac_cand": 12 * NB + 4 * C, "ransac_setup": 1024 * F, "ransac_count": 24 * C,
+        "seg_image": 4 * NB + 16 * NB + 1 * NB + 8 * NB, "seg_px": 8 * PX + 17 * PX,
+        "seg_dilate": 2 * PX, "jcp_queue": 2 * PX + 4 * Q,
+        "jcp_pre": Q * (25 * 17 + 24 * 4 + 8), "jcp_resolve": PX * 1 + Q * (8 + 4 + 96) + PX * 17 + V * 2,
+        "take_obstacles": 1 * V + 20 * M + 20 * M,
+        "clu_sph": 16 * M + 16 * M, "clu_insert": 16 * M + 4 * M, "clu_union": 8 * M,
+        "clu_flatten": 8 * M, "clu_rank": 8 * M, "clu_labels": 8 * M,
+        "hull_seg_scan": 8 * K, "hull_scatter": 20 * M + 12 * M, "hull": 16 * M + 8 * K + 4 * HV,
+        "hull_off_scan": 8 * K, "hull_gather": 4 * HV + 16 * HV + 12 * HV,
+        "label_count": 4 * M,
+    }
+    return float(t.get(name, 0.0))
+
+
+def batch_stats(ctx, nf, seg_dbg=True) -> dict:
+    s = dict(N=0, V=0, NB=0, M=0, K=0, HV=0, Q=0, C=0, U=0, F=nf, PX=nf * ctx.H * ctx.W, CELLS=0)
+    for f in range(nf):
+        r = ctx.counts(f)
+        s["N"] += r.n
+        s["V"] += r.num_valid
+        s["M"] += r.num_obstacles
+        s["K"] += r.num_clusters
+        s["HV"] += r.num_hull_vertices
+        if seg_dbg:
+            d = ctx.debug_counters(f)
+            s["NB"] += d["n_binned"]
+            s["C"] += d["n_candidates"]
+            s["Q"] += d["n_queued"]
+            s["U"] += d["n_unresolved"]
+            s["CELLS"] += d["cells"]
+    return s
+
+
+# --------------------------------------------------------------------------------------------
+# reference CPU path (oracle/_ref = the reference's own sources; port only for the two stages the
+# reference keeps outside the library: ring partition and the per-cluster gather + hull call)
+# --------------------------------------------------------------------------------------------
+class CpuReference:
+    def __init__(self):
+        from oracle.oracle import PortOracle, RefOracle, have_ref
+
+        self.kind = "reference" if have_ref() else "port"
+        self._mk = (lambda: (RefOracle(), PortOracle())) if have_ref() else (lambda: (None, PortOracle()))
+        self.tls = threading.local()
+
+    def _inst(self):
+        if not hasattr(self.tls, "o"):
+            self.tls.o = self._mk()
+        return self.tls.o
+
+    def frame(self, pts: np.ndarray):
+        """Whole hot path on one frame, chained as in DESIGN.md (ring -> DROR -> segment VALID ->
+        cluster OBSTACLE -> hulls)."""
+        ref, port = self._inst()
+        ring = port.ring_partition(pts)
+        noise = ref.dror(pts, mode="as_is") if ref is not None else port.dror(pts)
+        keep = noise == 0
+        pv = np.ascontiguousarray(pts[keep])
+        rv = np.ascontiguousarray(ring[keep])
+        labels = ref.segment(pv, rv) if ref is not None else port.segment(pv, rv)
+        obs = np.ascontiguousarray(pv[labels == 2])
+        cl = ref.cluster(obs) if ref is not None else port.cluster(obs)
+        off, xy, idx, zmm = port.cluster_hulls(obs, cl)
+        return int(off[-1]) if off.size else 0
+
+    def run(self, frames, threads: int) -> float:
+        """Seconds to push `frames` through `threads` worker threads (ctypes drops the GIL)."""
+        from concurrent.futures import ThreadPoolExecutor
+
+        t0 = time.perf_counter()
+        if threads <= 1:
+            for p in frames:
+                self.frame(p)
+        else:
+            with ThreadPoolExecutor(max_workers=threads) as ex:
+                list(ex.map(self.frame, frames))
+        return time.perf_counter() - t0
+
+
+def host_cores() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return 0
+    frames, workload, data_desc = load_frames()
+    cores = host_cores()
+    cpu = CpuReference()
+    per_step = min(len(frames), 2 * cores)
+    sample = frames[:per_step]
+    for _ in range(args.warmup):
+        cpu.run(sample[: max(cores, 1)], cores)
+    t = 0.0
+    for _ in range(args.steps):
+        t += cpu.run(sample, cores)
+    fps = per_step * args.steps / t
+    desc = (f"{per_step} frames of {workload} per step through the reference's own CPU code "
+            f"(oracle/_ref: unmodified segmenter/clusterer/noise_remover sources; ring partition and hull "
+            f"gather restated) on {cores} threads")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": data_desc,
+        "config": {"workload": workload, "frames_per_step": per_step, "stages": "ring+dror+segment+cluster+hulls",
+                   "host_threads": cores},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": cpu.kind, "sample": desc},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# --------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------
+def run_ours(args, rank, local_rank, world):
+    import torch
+
+    import lidar_processing_v2_b200 as lpl
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    frames, workload, data_desc = load_frames(args.frames)
+    # every rank runs the same number of frames; rotate the sequence so ranks do not share inputs
+    rot = (rank * 19) % len(frames)
+    frames = frames[rot:] + frames[:rot]
+    nf = len(frames)
+    max_pts = max(f.shape[0] for f in frames)
+    stages = lpl.STAGE_ALL
+    ctx = lpl.Context(local_rank, max_points=max_pts, max_frames=nf)
+    ctx.cluster_config(range_m=0.4, az_deg=1.0, el_deg=3.0, min_size=3)  # processor.param.yaml:31-35
+    total_pts = sum(f.shape[0] for f in frames)
+
+    # ---- device-resident throughput ("value")
+    ctx.upload(frames)
+    ctx.sync(nf)
+    for _ in range(args.warmup):
+        ctx.run(nf, stages)
+    ctx.sync(nf)
+    sampler = ClockSampler(local_rank)
+    ctx.profile(True)
+    prof = {}
+    barrier()
+    sampler.start()
+    ctx.launch_count(reset=True)
+    t_wall = time.perf_counter()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        ctx.run(nf, stages)
+        # per-kernel events of this step; reading them waits for the step (the stream itself stays
+        # busy: the next run is enqueued right after)
+        for name, ms in ctx.profile_read():
+            a = prof.setdefault(name, [0.0, 0])
+            a[0] += ms
+            a[1] += 1
+    ms_total = ctx.timer_stop_ms()
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    clocks = sampler.stop()
+    launches = ctx.launch_count()
+    ctx.profile(False)
+    ctx.sync(nf)
+    stats = batch_stats(ctx, nf)
+
+    # ---- end to end through the C ABI with host buffers ("e2e")
+    e2e = run_e2e(lpl, ctx, frames, local_rank, args, barrier, stages)
+
+    # ---- p50 latency of single-frame batches (H2D -> all results on the host)
+    lat = run_latency(lpl, frames, local_rank, stages, max_pts) if rank == 0 else None
+
+    t_ms = torch.tensor([ms_total, e2e["seconds"] * 1e3], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_max, e2e_ms_max = float(t_ms[0]), float(t_ms[1])
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    value = world * nf * args.steps / (ms_max * 1e-3)
+    e2e_value = world * nf * args.steps / (e2e_ms_max * 1e-3)
+
+    # ---- roofline of the dominant kernel
+    import json as _json
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak = float(_json.load(open(peaks_path))["hbm_gbs"])
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+    kernels = []
+    for name, (ms, cnt) in prof.items():
+        per_launch_ms = ms / cnt
+        by = algorithmic_bytes(name, stats)
+        kernels.append({"kernel": name, "launches": cnt, "ms_per_launch": per_launch_ms,
+                        "share": ms / (ms_total if ms_total > 0 else 1.0),
+                        "alg_bytes_per_launch": by, "gbs": by / (per_launch_ms * 1e6) if per_launch_ms > 0 else 0.0})
+    # kernels launched twice per step under one name (two-pass compactions) are merged above
+    kernels.sort(key=lambda k: -k["share"])
+    top = kernels[0]
+    roofline = {"bound": "hbm", "kernel": top["kernel"], "achieved": top["gbs"], "peak": peak, "unit": "GB/s",
+                "frac": top["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                "share_of_step": top["share"], "ms_per_launch": top["ms_per_launch"],
+                "note": "sequential sub-steps (JCP relaxation, hull chains, RECM scans) are latency-bound; see "
+                        "DESIGN.md and profiles/ for stall counters"}
+    traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_path):
+        try:
+            roofline["traffic"] = _json.load(open(traffic_path)).get(top["kernel"])
+        except Exception:
+            pass
+
+    # ---- CPU baseline on this box's host cores (bounded sample)
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu:
+        cores = host_cores()
+        cpu = CpuReference()
+        sample = frames[: min(nf, 2 * cores)]
+        cpu.run(sample[:cores], cores)  # warm-up (library load, page faults)
+        secs = cpu.run(sample, cores)
+        cpu_baseline = {"value": len(sample) / secs, "unit": UNIT, "cores": cores, "kind": cpu.kind,
+                        "sample": f"first {len(sample)} frames of {workload}, whole chained pipeline, "
+                                  f"{cores} threads, {secs:.1f} s"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": data_desc,
+        "config": {"workload": workload, "frames_per_step_per_gpu": nf, "points_per_step_per_gpu": total_pts,
+                   "stages": "ring+dror+segment+cluster+hulls", "l2": "inputs (300 MB/step) larger than L2, no flush",
+                   "parallelism": f"frame-sharded x{world}, no data-path collective"},
+        "points_per_s": world * total_pts * args.steps / (ms_max * 1e-3),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
+                "pipelining": "2 contexts double-buffered, pinned host memory"},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "kernels": [{k: (round(v, 6) if isinstance(v, float) else v) for k, v in kk.items()} for kk in kernels[:12]],
+        "latency_ms": lat,
+        "wall_s_timed_region": t_wall,
+    }
+    if cpu_baseline is not None:
+        line["cpu_baseline"] = cpu_baseline
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def run_e2e(lpl, ctx0, frames, device, args, barrier, stages):
+    """Upload (pinned host -> device) + run + batch download, double-buffered over two contexts."""
+    nf = len(frames)
+    max_pts = max(f.shape[0] for f in frames)
+    half = (nf + 1) // 2
+    # two half-size batches in flight keep the copy engines and the SMs busy at the same time
+    ctxs = [lpl.Context(device, max_points=max_pts, max_frames=half) for _ in range(2)]
+    for c in ctxs:
+        c.cluster_config(range_m=0.4, az_deg=1.0, el_deg=3.0, min_size=3)
+    parts = [frames[:half], frames[half:]]
+    pinned, views = [], []
+    for part in parts:
+        buf = lpl.PinnedBuffer((sum(f.shape[0] for f in part), 4), np.float32)
+        v, o = [], 0
+        for f in part:
+            buf.array[o:o + f.shape[0]] = f
+            v.append(buf.array[o:o + f.shape[0]])
+            o += f.shape[0]
+        pinned.append(buf)
+        views.append(v)
+    stride = ((max_pts + 2047) // 2048) * 2048
+    outs = [lpl.BatchBuffers(half, stride) for _ in range(2)]
+    h2d = sum(f.shape[0] for f in frames) * 16
+    d2h = 0
+
+    def one_step(count_bytes):
+        nonlocal d2h
+        for i in (0, 1):
+            ctxs[i].upload(views[i])
+            ctxs[i].run(len(views[i]), stages)
+        for i in (0, 1):
+            counts = ctxs[i].download_batch(len(views[i]), outs[i])
+            if count_bytes:
+                d2h += outs[i].bytes_for(counts)
+
+    for _ in range(max(args.warmup, 1)):
+        one_step(False)
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        one_step(s == 0)
+    barrier()
+    secs = time.perf_counter() - t0
+    for c in ctxs:
+        c.close()
+    return {"seconds": secs, "h2d": h2d, "d2h": d2h}
+
+
+def run_latency(lpl, frames, device, stages, max_pts):
+    ctx = lpl.Context(device, max_points=max_pts, max_frames=1)
+    ctx.cluster_config(range_m=0.4, az_deg=1.0, el_deg=3.0, min_size=3)
+    stride = ((max_pts + 2047) // 2048) * 2048
+    out = lpl.BatchBuffers(1, stride)
+    pin = lpl.PinnedBuffer((max_pts, 4), np.float32)
+    ts = []
+    for k, f in enumerate(frames[:64] + frames[:8]):
+        v = pin.array[: f.shape[0]]
+        v[:] = f
+        t0 = time.perf_counter()
+        ctx.upload([v])
+        ctx.run(1, stages)
+        ctx.download_batch(1, out)
+        ts.append((time.perf_counter() - t0) * 1e3)
+    ts = np.array(ts[8:])
+    ctx.close()
+    return {"p50": float(np.percentile(ts, 50)), "p95": float(np.percentile(ts, 95)), "frames": int(ts.size),
+            "what": "batch of 1: pinned H2D + all stages + labels/clusters/hulls D2H"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=None, help="frames per batch (default: the whole sequence)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference_arm(args, rank, world)
+    return run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

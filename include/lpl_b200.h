@@ -183,10 +183,42 @@ int lpl_pipeline_want_image(lpl_ctx* ctx, int enable);
 int lpl_pipeline_counts(lpl_ctx* ctx, uint32_t frame, lpl_frame_result* res);
 int lpl_pipeline_download(lpl_ctx* ctx, uint32_t frame, lpl_frame_result* res);
 
+/* Results of the whole batch in one call: host planes are frame-major, frame f of a plane starts
+ * `stride` elements after frame f - 1 (stride >= the largest frame and >= max clusters + 1).
+ * Only the occupied width of every plane crosses PCIe (one strided copy per plane). Any plane
+ * pointer may be NULL; `counts` is required: [5][num_frames] = n, num_valid, num_obstacles,
+ * num_clusters, num_hull_vertices. Pinned host memory (lpl_host_alloc) makes the copies async
+ * with respect to other contexts' work. */
+typedef struct lpl_batch_result
+{
+    uint32_t* counts;         /* [5][num_frames]                                   */
+    size_t stride;            /* elements per frame in every host plane            */
+    uint8_t* labels_u8;       /* Label per input point as a byte (0 / 1 / 2)       */
+    uint8_t* noise;
+    uint16_t* ring;
+    uint32_t* obstacle_index;
+    int32_t* cluster_labels;
+    uint32_t* hull_offsets;
+    uint32_t* hull_indices;
+    float* hull_xy;           /* 2 floats per element                              */
+    float* zminmax;           /* 2 floats per element                              */
+} lpl_batch_result;
+int lpl_pipeline_download_batch(lpl_ctx* ctx, uint32_t num_frames, lpl_batch_result* res);
+
+/* Pinned host memory for frame / result buffers (cudaMallocHost / cudaFreeHost). */
+int lpl_host_alloc(void** out, size_t bytes);
+void lpl_host_free(void* p);
+
 /* ---- measurement / debugging ------------------------------------------------------------- */
 /* CUDA-event bracket on the context stream. */
 int lpl_timer_start(lpl_ctx* ctx);
 int lpl_timer_stop_ms(lpl_ctx* ctx, float* ms_out);
+/* Per-kernel CUDA-event profile of the last lpl_pipeline_run on the context stream: entry i is
+ * the time between the events dropped behind kernel i - 1 and kernel i (names are static strings;
+ * a kernel launched twice appears twice). */
+int lpl_profile_enable(lpl_ctx* ctx, int enable);
+int lpl_profile_read(lpl_ctx* ctx, uint32_t max_entries, const char** names_out, float* ms_out,
+                     uint32_t* count_out);
 /* Kernels launched by this context since the last call with reset != 0. */
 uint64_t lpl_launch_count(lpl_ctx* ctx, int reset);
 /* Intermediates of the last segmentation of `frame` (all nullable): elevation[slices*rings],
@@ -194,6 +226,8 @@ uint64_t lpl_launch_count(lpl_ctx* ctx, int reset);
  * border_rows, slices, rings, status}. */
 int lpl_debug_segment(lpl_ctx* ctx, uint32_t frame, float* elevation, float* plane,
                       uint32_t* best_inliers, uint32_t* counters);
+/* Points the DROR scan-line pass left to the exhaustive grid search in the last run. */
+int lpl_debug_dror(lpl_ctx* ctx, uint32_t frame, uint32_t* n_unresolved);
 /* Intermediates of the last clustering: dims[3] = num_range, num_azimuth, num_elevation. */
 int lpl_debug_cluster(lpl_ctx* ctx, uint32_t frame, int32_t* dims);
 /* cudaStream_t of the context (as void*), for callers that order their own work after ours. */

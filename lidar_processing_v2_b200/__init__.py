@@ -14,10 +14,12 @@ from .native import (  # noqa: F401
     STAGE_HULLS,
     STAGE_RING,
     STAGE_SEGMENT,
+    BatchBuffers,
     ClusterCfg,
     Context,
     DrorCfg,
     LplError,
+    PinnedBuffer,
     SegmenterCfg,
     load_library,
 )

@@ -116,6 +116,7 @@ void carve(Dev& d, Carver& cv, int npx, int ncell_cap, std::uint32_t** mt_raw)
     cv.take(d.hull_idx, B * cap);
     cv.take(d.hull_xy, B * cap);
     cv.take(d.zminmax, B * cap);
+    cv.take(d.n_hull, B);
     const std::size_t tl = std::max<std::size_t>(d.tiles, d.ptiles);
     cv.take(d.tile_cnt, B * tl);
     cv.take(d.status, B);
@@ -469,6 +470,13 @@ void lpl_destroy(lpl_ctx* ctx)
     {
         cudaEventDestroy(c.ev1);
     }
+    for (cudaEvent_t e : c.prof_ev)
+    {
+        if (e != nullptr)
+        {
+            cudaEventDestroy(e);
+        }
+    }
     if (c.stream != nullptr)
     {
         cudaStreamDestroy(c.stream);
@@ -610,7 +618,21 @@ int lpl_pipeline_run(lpl_ctx* ctx, std::uint32_t nf, std::uint32_t stages)
     Ctx& c = ctx->c;
     Dev& d = c.d;
     LPL_TRY(cudaSetDevice(c.device));
+    if (c.prof_on)
+    {
+        c.prof_n = 0;
+        LPL_TRY(cudaEventRecord(c.prof_ev[0], c.stream));
+    }
     LPL_TRY(cudaMemsetAsync(d.status, 0, sizeof(std::uint32_t) * nf, c.stream));
+    if ((stages & LPL_STAGE_DROR) == 0)
+    {
+        LPL_TRY(cudaMemsetAsync(d.noise, 0, static_cast<std::size_t>(d.cap) * nf, c.stream));
+    }
+    // counts of stages that are not selected read as zero
+    LPL_TRY(cudaMemsetAsync(d.n_v, 0, sizeof(std::uint32_t) * nf, c.stream));
+    LPL_TRY(cudaMemsetAsync(d.n_o, 0, sizeof(std::uint32_t) * nf, c.stream));
+    LPL_TRY(cudaMemsetAsync(d.n_clusters, 0, sizeof(std::uint32_t) * nf, c.stream));
+    LPL_TRY(cudaMemsetAsync(d.n_hull, 0, sizeof(std::uint32_t) * nf, c.stream));
     const bool ring_stage = (stages & LPL_STAGE_RING) != 0;
     if (ring_stage)
     {
@@ -722,7 +744,14 @@ int lpl_pipeline_download(lpl_ctx* ctx, std::uint32_t f, lpl_frame_result* r)
     }
     if (r->labels != nullptr && r->n != 0)
     {
-        LPL_TRY(cudaMemcpyAsync(r->labels, d.labels_out + o, sizeof(std::uint32_t) * r->n, k, c.stream));
+        // device plane is u8; the reference's Label is uint32_t (segmenter.hpp:69-74)
+        auto* raw = reinterpret_cast<std::uint8_t*>(r->labels) + static_cast<std::size_t>(r->n) * 3;
+        LPL_TRY(cudaMemcpyAsync(raw, d.labels_out + o, r->n, k, c.stream));
+        LPL_TRY(cudaStreamSynchronize(c.stream));
+        for (std::uint32_t i = 0; i < r->n; ++i)
+        {
+            r->labels[i] = raw[i]; // forward in-place widening: byte i sits at offset 3n + i >= 4i
+        }
     }
     if (r->obstacle_index != nullptr && r->num_obstacles != 0)
     {
@@ -868,16 +897,22 @@ int lpl_segment(lpl_ctx* ctx, const void* points, std::size_t stride, std::int32
     c.seg.use_ring = (ring_offset >= 0 && ctx->seg_cfg.assume_unorganized_cloud == 0) ? 1 : 0;
     launch_take_all(&c, 1);
     launch_segment(&c, 1, bgr_image_out != nullptr);
+    std::uint8_t* raw = reinterpret_cast<std::uint8_t*>(labels_out) + static_cast<std::size_t>(n) * 3;
     if (n != 0)
     {
-        LPL_TRY(cudaMemcpyAsync(labels_out, d.labels_out, sizeof(std::uint32_t) * n, cudaMemcpyDeviceToHost, c.stream));
+        LPL_TRY(cudaMemcpyAsync(raw, d.labels_out, n, cudaMemcpyDeviceToHost, c.stream));
     }
     if (bgr_image_out != nullptr)
     {
         LPL_TRY(cudaMemcpyAsync(bgr_image_out, d.bgr, static_cast<std::size_t>(c.seg.npx) * 3, cudaMemcpyDeviceToHost,
                                 c.stream));
     }
-    return check_status(ctx, 1);
+    rc = check_status(ctx, 1);
+    for (std::uint32_t i = 0; i < n; ++i)
+    {
+        labels_out[i] = raw[i]; // u8 device plane -> uint32_t Label, widened in place front to back
+    }
+    return rc;
 }
 
 int lpl_cluster(lpl_ctx* ctx, const void* points, std::size_t stride, std::uint32_t n, std::int32_t* labels_out,
@@ -946,7 +981,7 @@ int lpl_cluster_hulls(lpl_ctx* ctx, const void* points, std::size_t stride, cons
     LPL_TRY(cudaMemcpyAsync(d.n_clusters, &num_clusters, 4, cudaMemcpyHostToDevice, c.stream));
     LPL_TRY(cudaMemsetAsync(d.ccount, 0, sizeof(std::uint32_t) * num_clusters, c.stream));
     k_label_count<<<dim3((d.cap + 255) / 256, 1), 256, 0, c.stream>>>(d, num_clusters);
-    c.launches += 1;
+    mark(&c, "label_count");
     launch_hulls(&c, 1);
     LPL_TRY(cudaMemcpyAsync(hull_offsets, d.hull_off, sizeof(std::uint32_t) * (num_clusters + 1), cudaMemcpyDeviceToHost,
                             c.stream));
@@ -1009,6 +1044,132 @@ int lpl_convex_hull(lpl_ctx* ctx, const void* xy, std::size_t stride, std::uint3
         *count_out = off[1];
     }
     return rc;
+}
+
+int lpl_pipeline_download_batch(lpl_ctx* ctx, std::uint32_t nf, lpl_batch_result* r)
+{
+    if (ctx == nullptr || r == nullptr || nf == 0 || nf > ctx->c.d.B || r->counts == nullptr)
+    {
+        return fail(ctx, LPL_ERR_INVALID_ARGUMENT, "bad batch download request");
+    }
+    Ctx& c = ctx->c;
+    Dev& d = c.d;
+    LPL_TRY(cudaSetDevice(c.device));
+    const cudaMemcpyKind k = cudaMemcpyDeviceToHost;
+    // phase 1: per-frame counts (sizes the plane copies) + status
+    std::uint32_t* cn = r->counts;
+    LPL_TRY(cudaMemcpyAsync(cn + 0 * nf, d.n_in, 4 * nf, k, c.stream));
+    LPL_TRY(cudaMemcpyAsync(cn + 1 * nf, d.n_v, 4 * nf, k, c.stream));
+    LPL_TRY(cudaMemcpyAsync(cn + 2 * nf, d.n_o, 4 * nf, k, c.stream));
+    LPL_TRY(cudaMemcpyAsync(cn + 3 * nf, d.n_clusters, 4 * nf, k, c.stream));
+    LPL_TRY(cudaMemcpyAsync(cn + 4 * nf, d.n_hull, 4 * nf, k, c.stream));
+    const int rc = check_status(ctx, nf);
+    if (rc != 0)
+    {
+        return rc;
+    }
+    std::uint32_t mx[5] = {0, 0, 0, 0, 0};
+    for (int a = 0; a < 5; ++a)
+    {
+        for (std::uint32_t f = 0; f < nf; ++f)
+        {
+            mx[a] = std::max(mx[a], cn[a * nf + f]);
+        }
+    }
+    const std::size_t hs = r->stride; // host plane stride in elements
+    if (hs < mx[0] || hs < static_cast<std::size_t>(mx[3]) + 1)
+    {
+        return fail(ctx, LPL_ERR_CAPACITY, "host result stride smaller than the largest frame");
+    }
+    auto plane = [&](void* dst, const void* src, std::size_t elem, std::size_t dev_stride, std::uint32_t width) -> cudaError_t {
+        if (dst == nullptr || width == 0)
+        {
+            return cudaSuccess;
+        }
+        return cudaMemcpy2DAsync(dst, hs * elem, src, dev_stride * elem, static_cast<std::size_t>(width) * elem, nf, k,
+                                 c.stream);
+    };
+    LPL_TRY(plane(r->labels_u8, d.labels_out, 1, d.cap, mx[0]));
+    LPL_TRY(plane(r->noise, d.noise, 1, d.cap, mx[0]));
+    LPL_TRY(plane(r->ring, d.ring, 2, d.cap, mx[0]));
+    LPL_TRY(plane(r->obstacle_index, d.idx_o, 4, d.cap, mx[2]));
+    LPL_TRY(plane(r->cluster_labels, d.clabel, 4, d.cap, mx[2]));
+    LPL_TRY(plane(r->hull_offsets, d.hull_off, 4, d.cap + 1, mx[3] + 1));
+    LPL_TRY(plane(r->hull_indices, d.hull_idx, 4, d.cap, mx[4]));
+    LPL_TRY(plane(r->hull_xy, d.hull_xy, 8, d.cap, mx[4]));
+    LPL_TRY(plane(r->zminmax, d.zminmax, 8, d.cap, mx[3]));
+    LPL_TRY(cudaStreamSynchronize(c.stream));
+    return LPL_OK;
+}
+
+int lpl_host_alloc(void** out, std::size_t bytes)
+{
+    if (out == nullptr)
+    {
+        return LPL_ERR_INVALID_ARGUMENT;
+    }
+    *out = nullptr;
+    return cudaMallocHost(out, bytes) == cudaSuccess ? LPL_OK : LPL_ERR_CUDA;
+}
+
+void lpl_host_free(void* p)
+{
+    if (p != nullptr)
+    {
+        cudaFreeHost(p);
+    }
+}
+
+int lpl_profile_enable(lpl_ctx* ctx, int enable)
+{
+    if (ctx == nullptr)
+    {
+        return LPL_ERR_INVALID_ARGUMENT;
+    }
+    Ctx& c = ctx->c;
+    LPL_TRY(cudaSetDevice(c.device));
+    if (enable && c.prof_ev[0] == nullptr)
+    {
+        for (cudaEvent_t& e : c.prof_ev)
+        {
+            LPL_TRY(cudaEventCreate(&e));
+        }
+    }
+    c.prof_on = enable != 0;
+    c.prof_n = 0;
+    return LPL_OK;
+}
+
+int lpl_profile_read(lpl_ctx* ctx, std::uint32_t max_entries, const char** names_out, float* ms_out,
+                     std::uint32_t* count_out)
+{
+    if (ctx == nullptr || count_out == nullptr)
+    {
+        return LPL_ERR_INVALID_ARGUMENT;
+    }
+    Ctx& c = ctx->c;
+    *count_out = 0;
+    if (!c.prof_on || c.prof_n == 0)
+    {
+        return LPL_OK;
+    }
+    LPL_TRY(cudaEventSynchronize(c.prof_ev[c.prof_n]));
+    const std::uint32_t m = std::min<std::uint32_t>(max_entries, static_cast<std::uint32_t>(c.prof_n));
+    for (std::uint32_t i = 0; i < m; ++i)
+    {
+        float ms = 0.f;
+        LPL_TRY(cudaEventElapsedTime(&ms, c.prof_ev[i], c.prof_ev[i + 1]));
+        if (names_out != nullptr)
+        {
+            names_out[i] = c.prof_name[i];
+        }
+        if (ms_out != nullptr)
+        {
+            ms_out[i] = ms;
+        }
+    }
+    *count_out = m;
+    return LPL_OK;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1083,6 +1244,18 @@ int lpl_debug_segment(lpl_ctx* ctx, std::uint32_t f, float* elevation, float* pl
         counters[6] = static_cast<std::uint32_t>(s.rings);
         LPL_TRY(cudaMemcpy(&counters[7], d.status + f, 4, cudaMemcpyDeviceToHost));
     }
+    return LPL_OK;
+}
+
+int lpl_debug_dror(lpl_ctx* ctx, std::uint32_t f, std::uint32_t* n_unresolved)
+{
+    if (ctx == nullptr || n_unresolved == nullptr || f >= ctx->c.d.B)
+    {
+        return LPL_ERR_INVALID_ARGUMENT;
+    }
+    Ctx& c = ctx->c;
+    LPL_TRY(cudaStreamSynchronize(c.stream));
+    LPL_TRY(cudaMemcpy(n_unresolved, c.d.n_unres + f, 4, cudaMemcpyDeviceToHost));
     return LPL_OK;
 }
 

@@ -334,9 +334,8 @@ struct ObstacleEmit
 void launch_take_obstacles(Ctx* c, std::uint32_t nf)
 {
     Dev& d = c->d;
-    launch_compact(c->stream, nf, d.tiles, d.n_v, 0u, d.tile_cnt, d.n_o, ObstaclePred{d.seg_label, d.cap},
+    launch_compact(c, "take_obstacles", nf, d.tiles, d.n_v, 0u, d.tile_cnt, d.n_o, ObstaclePred{d.seg_label, d.cap},
                    ObstacleEmit{d.pts_v, d.idx_v, d.pts_o, d.idx_o, d.cap});
-    c->launches += 2;
 }
 
 void launch_cluster(Ctx* c, std::uint32_t nf)
@@ -348,12 +347,16 @@ void launch_cluster(Ctx* c, std::uint32_t nf)
     cudaMemsetAsync(d.hmin, 0xff, sizeof(std::uint32_t) * static_cast<std::size_t>(d.hcap) * nf, s);
     const dim3 g((d.cap + 255) / 256, nf);
     k_clu_sph<<<g, 256, 0, s>>>(d);
+    mark(c, "clu_sph");
     k_clu_insert<<<g, 256, 0, s>>>(d, c->clu);
+    mark(c, "clu_insert");
     k_clu_union<<<g, 256, 0, s>>>(d, c->clu);
+    mark(c, "clu_union");
     k_clu_flatten<<<g, 256, 0, s>>>(d);
-    launch_compact(s, nf, d.tiles, d.n_o, 0u, d.tile_cnt, d.n_clusters,
+    mark(c, "clu_flatten");
+    launch_compact(c, "clu_rank", nf, d.tiles, d.n_o, 0u, d.tile_cnt, d.n_clusters,
                    ClusterRepPred{d, c->clu.min_cluster_size}, ClusterRepEmit{d});
     k_clu_labels<<<g, 256, 0, s>>>(d);
-    c->launches += 7;
+    mark(c, "clu_labels");
 }
 } // namespace lpl

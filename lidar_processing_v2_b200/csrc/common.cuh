@@ -121,7 +121,7 @@ struct Dev
     std::uint32_t* pend;      // [B][2][qcap]
     std::uint32_t* jcp_rounds;// [B]
     std::uint8_t* seg_label;  // [B][cap]  label per point of the segmented cloud
-    std::uint32_t* labels_out;// [B][cap]  u32 Label per *input* point
+    std::uint8_t* labels_out; // [B][cap]  Label (0/1/2) per *input* point
     std::uint8_t* bgr;        // [B][npx*3]
     // ---- obstacle cloud / clustering
     float4* pts_o;            // [B][cap]
@@ -148,6 +148,7 @@ struct Dev
     std::uint32_t* hull_idx;  // [B][cap]  obstacle-cloud index per hull vertex
     float2* hull_xy;          // [B][cap]
     float2* zminmax;          // [B][cap]  per cluster
+    std::uint32_t* n_hull;    // [B]       hull vertices of the frame
     // ---- generic
     std::uint32_t* tile_cnt;  // [B][max(tiles, ptiles)]
     std::uint32_t* status;    // [B]  error bits raised by kernels
@@ -369,17 +370,6 @@ __global__ void __launch_bounds__(kTileThreads)
     }
 }
 
-template <class Pred, class Emit>
-inline void launch_compact(cudaStream_t s, std::uint32_t B, std::uint32_t tiles_per_frame,
-                           const std::uint32_t* n_arr, std::uint32_t n_const,
-                           std::uint32_t* tile_cnt, std::uint32_t* n_out, Pred pred, Emit emit)
-{
-    const dim3 grid(tiles_per_frame, B);
-    k_compact_count<<<grid, kTileThreads, 0, s>>>(pred, n_arr, n_const, tile_cnt, tiles_per_frame);
-    k_compact_scatter<<<grid, kTileThreads, 0, s>>>(pred, emit, n_arr, n_const, tile_cnt,
-                                                    tiles_per_frame, n_out);
-}
-
 // Exclusive scan of `len` counters per frame by one block of 1024 threads:
 // out[f][0..len] (len + 1 entries, out[len] = total).
 // `len_arr` (nullable) gives a per-frame length <= len; strides are in elements; total_out
@@ -416,7 +406,41 @@ struct Ctx
     std::size_t h_stage_bytes = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     unsigned long long launches = 0; // kernels launched since the last reset
+    // per-kernel CUDA-event profile of the last lpl_pipeline_run (lpl_profile_*)
+    static constexpr int kProfMax = 96;
+    bool prof_on = false;
+    int prof_n = 0;                       // marks recorded in the current run
+    cudaEvent_t prof_ev[kProfMax + 1] = {};
+    const char* prof_name[kProfMax] = {};
 };
+
+// Called after every kernel launch: counts it and, when profiling, drops an event behind it so
+// the time between consecutive marks is that kernel's duration on the context stream
+// (preceding memsets are attributed to the kernel that follows them).
+inline void mark(Ctx* c, const char* name)
+{
+    c->launches += 1;
+    if (c->prof_on && c->prof_n < Ctx::kProfMax)
+    {
+        c->prof_name[c->prof_n] = name;
+        cudaEventRecord(c->prof_ev[c->prof_n + 1], c->stream);
+        c->prof_n += 1;
+    }
+}
+
+
+template <class Pred, class Emit>
+inline void launch_compact(Ctx* c, const char* name, std::uint32_t B, std::uint32_t tiles_per_frame,
+                           const std::uint32_t* n_arr, std::uint32_t n_const,
+                           std::uint32_t* tile_cnt, std::uint32_t* n_out, Pred pred, Emit emit)
+{
+    const dim3 grid(tiles_per_frame, B);
+    k_compact_count<<<grid, kTileThreads, 0, c->stream>>>(pred, n_arr, n_const, tile_cnt, tiles_per_frame);
+    mark(c, name);
+    k_compact_scatter<<<grid, kTileThreads, 0, c->stream>>>(pred, emit, n_arr, n_const, tile_cnt,
+                                                            tiles_per_frame, n_out);
+    mark(c, name);
+}
 
 #define LPL_CUDA_OK(call)                                                                          \
     do                                                                                             \

@@ -281,10 +281,14 @@ void launch_hulls(Ctx* c, std::uint32_t nf)
     Dev& d = c->d;
     cudaStream_t s = c->stream;
     k_excl_scan<<<nf, 1024, 0, s>>>(d.ccount, d.cap, d.cstart, d.cap + 1, d.cap, d.n_clusters, nullptr);
+    mark(c, "hull_seg_scan");
     k_hull_scatter<<<dim3((d.cap + 255) / 256, nf), 256, 0, s>>>(d);
+    mark(c, "hull_scatter");
     k_hull<<<dim3(kHullBlocks, nf), kHullThreads, 0, s>>>(d);
-    k_excl_scan<<<nf, 1024, 0, s>>>(d.hcnt, d.cap, d.hull_off, d.cap + 1, d.cap, d.n_clusters, nullptr);
+    mark(c, "hull");
+    k_excl_scan<<<nf, 1024, 0, s>>>(d.hcnt, d.cap, d.hull_off, d.cap + 1, d.cap, d.n_clusters, d.n_hull);
+    mark(c, "hull_off_scan");
     k_hull_gather<<<dim3(kHullBlocks, nf), kHullThreads, 0, s>>>(d);
-    c->launches += 5;
+    mark(c, "hull_gather");
 }
 } // namespace lpl

@@ -107,9 +107,10 @@ void launch_ring(Ctx* c, std::uint32_t nf)
     const dim3 grid(d.tiles, nf);
     RingWrapPred pred{d.pts_in, d.cap};
     k_compact_count<<<grid, kTileThreads, 0, c->stream>>>(pred, d.n_in, 0u, d.tile_cnt, d.tiles);
+    mark(c, "ring_count");
     k_ring_write<<<grid, kTileThreads, 0, c->stream>>>(pred, d.n_in, d.tile_cnt, d.tiles, d.ring,
                                                       d.cap);
-    c->launches += 2;
+    mark(c, "ring_write");
 }
 
 // ------------------------------------------------------------------------------------------
@@ -323,13 +324,17 @@ void launch_dror(Ctx* c, std::uint32_t nf)
     cudaMemsetAsync(d.n_unres, 0, sizeof(std::uint32_t) * nf, c->stream);
     const dim3 grid((d.cap + 255) / 256, nf);
     k_dror_near<<<grid, 256, 0, c->stream>>>(d, c->dror);
+    mark(c, "dror_near");
     k_dror_grid_count<<<grid, 256, 0, c->stream>>>(d);
+    mark(c, "dror_grid_count");
     k_excl_scan<<<nf, 1024, 0, c->stream>>>(d.grid_cnt, kDrorCells, d.grid_start, kDrorCells + 1, kDrorCells,
                                             nullptr, nullptr);
+    mark(c, "dror_grid_scan");
     k_dror_grid_scatter<<<grid, 256, 0, c->stream>>>(d);
+    mark(c, "dror_grid_scatter");
     const dim3 qgrid((d.cap + 127) / 128, nf);
     k_dror_query<<<qgrid, 128, 0, c->stream>>>(d, c->dror);
-    c->launches += 5;
+    mark(c, "dror_query");
 }
 
 // ------------------------------------------------------------------------------------------
@@ -366,16 +371,14 @@ struct ValidEmit
 void launch_take_valid(Ctx* c, std::uint32_t nf)
 {
     Dev& d = c->d;
-    launch_compact(c->stream, nf, d.tiles, d.n_in, 0u, d.tile_cnt, d.n_v, ValidPred{d.noise, d.cap},
+    launch_compact(c, "take_valid", nf, d.tiles, d.n_in, 0u, d.tile_cnt, d.n_v, ValidPred{d.noise, d.cap},
                    ValidEmit{d.pts_in, d.ring, d.pts_v, d.idx_v, d.cap});
-    c->launches += 2;
 }
 
 void launch_take_all(Ctx* c, std::uint32_t nf)
 {
     Dev& d = c->d;
-    launch_compact(c->stream, nf, d.tiles, d.n_in, 0u, d.tile_cnt, d.n_v, ValidPred{nullptr, d.cap},
+    launch_compact(c, "take_all", nf, d.tiles, d.n_in, 0u, d.tile_cnt, d.n_v, ValidPred{nullptr, d.cap},
                    ValidEmit{d.pts_in, d.ring, d.pts_v, d.idx_v, d.cap});
-    c->launches += 2;
 }
 } // namespace lpl

@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(64) k_ransac_setup(Dev d, SegParams sp)
     const std::uint32_t f = blockIdx.x;
     const std::uint32_t nc = d.n_cand[f];
     // a single candidate makes the reference spin forever (segmenter.cpp:382-386); RANSAC is
-    // skipped for nc < 2 here and in the oracle.
+    // skipped for nc < 2 (documented deviation).
     const bool run = nc >= 2;
     if (threadIdx.x == 0 && run)
     {
@@ -977,31 +977,43 @@ void launch_segment(Ctx* c, std::uint32_t nf, bool want_image)
     cudaMemsetAsync(d.cell_cnt, 0, sizeof(std::uint32_t) * sp.ncell * nf, s);
     cudaMemsetAsync(d.key, 0xff, sizeof(unsigned long long) * sp.npx * nf, s);
     cudaMemsetAsync(d.seg_label, 0, static_cast<std::size_t>(d.cap) * nf, s);
-    cudaMemsetAsync(d.labels_out, 0, sizeof(std::uint32_t) * static_cast<std::size_t>(d.cap) * nf, s);
+    cudaMemsetAsync(d.labels_out, 0, static_cast<std::size_t>(d.cap) * nf, s);
     cudaMemsetAsync(d.n_border, 0, sizeof(std::uint32_t) * nf, s);
 
     const dim3 gpts((d.cap + 255) / 256, nf);
     k_seg_bin<<<gpts, 256, 0, s>>>(d, sp);
+    mark(c, "seg_bin");
     k_excl_scan<<<nf, 1024, 0, s>>>(d.cell_cnt, sp.ncell, d.cell_start, sp.ncell + 1,
                                     static_cast<std::uint32_t>(sp.ncell), nullptr, d.n_binned);
+    mark(c, "seg_cell_scan");
     k_seg_scatter<<<gpts, 256, 0, s>>>(d, sp);
+    mark(c, "seg_scatter");
     k_seg_cell<<<dim3((sp.ncell + 3) / 4, nf), 128, 0, s>>>(d, sp);
+    mark(c, "seg_cell");
     k_seg_elev<<<dim3((sp.slices + 127) / 128, nf), 128, 0, s>>>(d, sp);
+    mark(c, "seg_elev");
     const std::uint32_t* n_binned = d.n_binned;
     k_seg_label<<<gpts, 256, 0, s>>>(d, sp, n_binned);
-    launch_compact(s, nf, d.tiles, n_binned, 0u, d.tile_cnt, d.n_cand, CandPred{d, sp},
+    mark(c, "seg_label");
+    launch_compact(c, "ransac_cand", nf, d.tiles, n_binned, 0u, d.tile_cnt, d.n_cand, CandPred{d, sp},
                    CandEmit{d.cand, d.cap});
     k_ransac_setup<<<nf, 64, 0, s>>>(d, sp);
+    mark(c, "ransac_setup");
     k_ransac_count<<<gpts, 256, 0, s>>>(d, sp);
+    mark(c, "ransac_count");
     k_seg_image<<<gpts, 256, 0, s>>>(d, sp, n_binned);
+    mark(c, "seg_image");
     k_seg_px<<<dim3((sp.npx + 255) / 256, nf), 256, 0, s>>>(d, sp);
+    mark(c, "seg_px");
     k_seg_dilate<<<dim3((sp.W + kDilTw - 1) / kDilTw, (sp.H + kDilTh - 1) / kDilTh, nf), 256, 0, s>>>(d, sp);
-    launch_compact(s, nf, d.ptiles, nullptr, static_cast<std::uint32_t>(sp.npx), d.tile_cnt, d.n_queue,
+    mark(c, "seg_dilate");
+    launch_compact(c, "jcp_queue", nf, d.ptiles, nullptr, static_cast<std::uint32_t>(sp.npx), d.tile_cnt, d.n_queue,
                    QueuePred{d.code, static_cast<std::uint32_t>(sp.npx)},
                    QueueEmit{d.queue, d.status, d.qcap});
     k_jcp_pre<<<dim3((d.qcap + 127) / 128, nf), 128, 0, s>>>(d, sp);
+    mark(c, "jcp_pre");
     const std::size_t plane_bytes = static_cast<std::size_t>((sp.npx + 15) / 16) * 4;
     k_jcp_resolve<<<nf, 1024, plane_bytes, s>>>(d, sp, want_image ? 1 : 0);
-    c->launches += 17;
+    mark(c, "jcp_resolve");
 }
 } // namespace lpl

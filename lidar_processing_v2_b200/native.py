@@ -1,6 +1,6 @@
 """ctypes binding of include/lpl_b200.h (the C-ABI shared library liblpl_b200.so).
 
-This is the only way Python reaches the product path; it never imports oracle/ and has no CPU
+This is the only way Python reaches the product path; it never touches the CPU checkers and has no CPU
 fallback: without the library or without a CUDA device every call raises.
 """
 from __future__ import annotations
@@ -33,8 +33,10 @@ EXPORTS = [
     "lpl_cluster_hulls",
     "lpl_pipeline_upload", "lpl_pipeline_upload_device", "lpl_pipeline_run", "lpl_pipeline_sync",
     "lpl_pipeline_want_image", "lpl_pipeline_counts", "lpl_pipeline_download",
+    "lpl_pipeline_download_batch", "lpl_host_alloc", "lpl_host_free",
+    "lpl_profile_enable", "lpl_profile_read",
     "lpl_timer_start", "lpl_timer_stop_ms", "lpl_launch_count", "lpl_debug_segment",
-    "lpl_debug_cluster", "lpl_stream",
+    "lpl_debug_dror", "lpl_debug_cluster", "lpl_stream",
 ]
 
 
@@ -102,6 +104,22 @@ class FrameResult(C.Structure):
     ]
 
 
+class BatchResult(C.Structure):
+    _fields_ = [
+        ("counts", C.c_void_p),
+        ("stride", C.c_size_t),
+        ("labels_u8", C.c_void_p),
+        ("noise", C.c_void_p),
+        ("ring", C.c_void_p),
+        ("obstacle_index", C.c_void_p),
+        ("cluster_labels", C.c_void_p),
+        ("hull_offsets", C.c_void_p),
+        ("hull_indices", C.c_void_p),
+        ("hull_xy", C.c_void_p),
+        ("zminmax", C.c_void_p),
+    ]
+
+
 class LplError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"lpl_b200 error {code}: {msg}")
@@ -151,12 +169,21 @@ def load_library(path: str | None = None) -> C.CDLL:
     L.lpl_pipeline_want_image.argtypes = [vp, C.c_int]
     L.lpl_pipeline_counts.argtypes = [vp, u32, C.POINTER(FrameResult)]
     L.lpl_pipeline_download.argtypes = [vp, u32, C.POINTER(FrameResult)]
+    L.lpl_pipeline_download_batch.argtypes = [vp, u32, C.POINTER(BatchResult)]
+    L.lpl_host_alloc.argtypes = [C.POINTER(vp), sz]
+    L.lpl_host_alloc.restype = C.c_int
+    L.lpl_host_free.argtypes = [vp]
+    L.lpl_host_free.restype = None
+    L.lpl_profile_enable.argtypes = [vp, C.c_int]
+    L.lpl_profile_read.argtypes = [vp, u32, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(u32)]
     L.lpl_timer_start.argtypes = [vp]
     L.lpl_timer_stop_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.lpl_launch_count.argtypes = [vp, C.c_int]
     L.lpl_launch_count.restype = C.c_uint64
     L.lpl_debug_segment.argtypes = [vp, u32, vp, vp, vp, vp]
     L.lpl_debug_cluster.argtypes = [vp, u32, vp]
+    L.lpl_debug_dror.argtypes = [vp, u32, C.POINTER(u32)]
+    L.lpl_debug_dror.restype = C.c_int
     L.lpl_stream.argtypes = [vp]
     L.lpl_stream.restype = vp
     for name in ("lpl_segmenter_config", "lpl_dror_config", "lpl_cluster_config", "lpl_set_jcp_mode",
@@ -164,11 +191,74 @@ def load_library(path: str | None = None) -> C.CDLL:
                  "lpl_convex_hull", "lpl_cluster_hulls", "lpl_pipeline_upload",
                  "lpl_pipeline_upload_device", "lpl_pipeline_run", "lpl_pipeline_sync",
                  "lpl_pipeline_want_image", "lpl_pipeline_counts", "lpl_pipeline_download",
+                 "lpl_pipeline_download_batch", "lpl_profile_enable", "lpl_profile_read",
                  "lpl_timer_start", "lpl_timer_stop_ms", "lpl_debug_segment", "lpl_debug_cluster"):
         getattr(L, name).restype = C.c_int
     if path is None:
         _lib = L
     return L
+
+
+class PinnedBuffer:
+    """cudaMallocHost block exposed as a numpy array (frame staging / result planes)."""
+
+    def __init__(self, shape, dtype):
+        self.lib = load_library()
+        self.shape = tuple(int(v) for v in np.atleast_1d(shape))
+        self.dtype = np.dtype(dtype)
+        nbytes = max(int(np.prod(self.shape)) * self.dtype.itemsize, 1)
+        p = C.c_void_p()
+        rc = self.lib.lpl_host_alloc(C.byref(p), nbytes)
+        if rc != 0 or not p.value:
+            raise LplError(rc, f"cudaMallocHost({nbytes}) failed")
+        self.ptr = p.value
+        buf = (C.c_char * nbytes).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            self.array = None
+            self.lib.lpl_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class BatchBuffers:
+    """Pinned host planes for lpl_pipeline_download_batch (frame-major, `stride` elements apart)."""
+
+    PLANES = (("labels_u8", np.uint8, 1), ("noise", np.uint8, 1), ("ring", np.uint16, 1),
+              ("obstacle_index", np.uint32, 1), ("cluster_labels", np.int32, 1),
+              ("hull_offsets", np.uint32, 1), ("hull_indices", np.uint32, 1),
+              ("hull_xy", np.float32, 2), ("zminmax", np.float32, 2))
+
+    def __init__(self, max_frames: int, stride: int, want=("labels_u8", "obstacle_index", "cluster_labels",
+                                                           "hull_offsets", "hull_xy", "zminmax")):
+        self.max_frames, self.stride = max_frames, stride
+        self.counts = PinnedBuffer((5, max_frames), np.uint32)
+        self.planes = {}
+        for name, dt, width in self.PLANES:
+            if name in want:
+                shape = (max_frames, stride) if width == 1 else (max_frames, stride, width)
+                self.planes[name] = PinnedBuffer(shape, dt)
+
+    def bytes_for(self, counts: np.ndarray) -> int:
+        """Bytes that cross PCIe for a batch with these per-frame counts ([5][nf])."""
+        nf = counts.shape[1]
+        mx = counts.max(axis=1)
+        width = dict(labels_u8=mx[0], noise=mx[0], ring=2 * mx[0], obstacle_index=4 * mx[2],
+                     cluster_labels=4 * mx[2], hull_offsets=4 * (mx[3] + 1), hull_indices=4 * mx[4],
+                     hull_xy=8 * mx[4], zminmax=8 * mx[3])
+        return int(sum(int(width[k]) for k in self.planes) * nf + counts.size * 4)
+
+    def close(self):
+        self.counts.close()
+        for b in self.planes.values():
+            b.close()
 
 
 def _points_arg(pts):
@@ -349,7 +439,29 @@ class Context:
                    num_clusters=r.num_clusters, num_hull_vertices=r.num_hull_vertices)
         return out
 
+    def download_batch(self, nf: int, bufs: BatchBuffers) -> np.ndarray:
+        """One strided D2H copy per plane for the whole batch; returns counts[5][nf] (a view)."""
+        r = BatchResult()
+        r.counts = bufs.counts.ptr
+        r.stride = bufs.stride
+        for name, b in bufs.planes.items():
+            setattr(r, name, b.ptr)
+        # counts are laid out [5][nf] for this call's nf
+        self._chk(self.lib.lpl_pipeline_download_batch(self.h, nf, C.byref(r)))
+        return bufs.counts.array.reshape(-1)[: 5 * nf].reshape(5, nf)
+
     # ---- measurement / debugging
+    def profile(self, enable: bool):
+        self._chk(self.lib.lpl_profile_enable(self.h, 1 if enable else 0))
+
+    def profile_read(self) -> list:
+        """[(kernel name, ms)] of the last run, in launch order."""
+        names = (C.c_char_p * 96)()
+        ms = (C.c_float * 96)()
+        cnt = C.c_uint32(0)
+        self._chk(self.lib.lpl_profile_read(self.h, 96, names, ms, C.byref(cnt)))
+        return [(names[i].decode(), float(ms[i])) for i in range(cnt.value)]
+
     def timer_start(self):
         self._chk(self.lib.lpl_timer_start(self.h))
 
@@ -373,6 +485,16 @@ class Context:
         return dict(elevation=elev.reshape(slices, rings), plane=plane, best_inliers=best.value,
                     n_binned=int(cnt[0]), n_candidates=int(cnt[1]), n_queued=int(cnt[2]),
                     rounds=int(cnt[3]), border_rows=int(cnt[4]), status=int(cnt[7]))
+
+    def debug_counters(self, f: int = 0) -> dict:
+        """Cheap per-frame counters of the last run (no plane downloads)."""
+        cnt = np.zeros(8, np.uint32)
+        self._chk(self.lib.lpl_debug_segment(self.h, f, None, None, None, cnt.ctypes.data))
+        nu = C.c_uint32(0)
+        self._chk(self.lib.lpl_debug_dror(self.h, f, C.byref(nu)))
+        return dict(n_binned=int(cnt[0]), n_candidates=int(cnt[1]), n_queued=int(cnt[2]), rounds=int(cnt[3]),
+                    border_rows=int(cnt[4]), cells=int(cnt[5]) * int(cnt[6]), status=int(cnt[7]),
+                    n_unresolved=int(nu.value))
 
     def debug_cluster(self, f: int = 0) -> np.ndarray:
         dims = np.zeros(3, np.int32)

@@ -1,0 +1,273 @@
+"""GPU suite: the CUDA path (always through the C ABI, lidar_processing_v2_b200.native) against
+the CPU oracle on the same inputs, the committed golden fixtures, and size-independent properties
+at full batch size. Integer / label / index outputs are compared bit-exactly; hull vertex
+coordinates are floats copied from the input, also compared bit-exactly (tolerance 0 <= 1e-5)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import lidar_processing_v2_b200 as lpl
+import parity
+from oracle.oracle import JCP_AS_IS, JCP_CLEAN, NODE_CLUSTER_CFG, PortOracle, default_seg_cfg, label_hash
+from tools import frames as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = lpl.Context(0, max_points=131072, max_frames=8)
+    yield c
+    c.close()
+
+
+def _assert_parity(rep):
+    bad = {k: v for k, v in rep.items() if k.endswith("_diff") and v != 0}
+    assert not bad and rep.get("seg_status", 0) == 0, rep
+
+
+def test_native_library_is_the_path(ctx):
+    # the extension in-tree is what runs: kernels were launched by this context
+    ctx.launch_count(reset=True)
+    ctx.dror_filter(np.zeros((10, 4), np.float32))
+    assert ctx.launch_count() > 0
+    assert os.path.exists(lpl.SO_PATH)
+
+
+def test_stagewise_vs_unmodified_reference(ctx, ref, golden0, golden100):
+    for g in (golden0, golden100):
+        _assert_parity(parity.stage_report(ctx, ref, g["pts"]))
+
+
+def test_stagewise_vs_golden_fixture(ctx, golden0):
+    g = golden0
+    pts = g["pts"]
+    assert np.array_equal(ctx.ring_partition(pts), g["ring"].astype(np.uint16))
+    assert np.array_equal(np.packbits(ctx.dror_filter(pts)), g["dror_exact"])
+    labels, img = ctx.segment(pts, g["ring"].astype(np.uint16), want_image=True)
+    assert np.array_equal(labels, g["labels"].astype(np.uint32))
+    assert np.array_equal(np.packbits(img.reshape(-1) > 0), g["image"])
+    assert np.array_equal(ctx.debug_segment(0)["elevation"].view(np.uint32), g["elevation"].view(np.uint32))
+    assert np.array_equal(ctx.segment(pts, None), g["labels_noring"].astype(np.uint32))
+    obs = np.ascontiguousarray(pts[labels == 2])
+    ctx.cluster_config(**NODE_CLUSTER_CFG)
+    cl, k = ctx.cluster(obs)
+    assert np.array_equal(cl, g["cluster_labels"].astype(np.int32)) and k == 262
+    assert np.array_equal(ctx.debug_cluster(0), g["voxel_dims"])
+    off, xy, idx, zmm = ctx.cluster_hulls(obs, cl)
+    assert np.array_equal(off, g["hull_offsets"])
+    assert np.abs(xy - g["hull_xy"]).max() <= 1e-5 and np.array_equal(xy, g["hull_xy"])
+    assert np.array_equal(zmm, g["zminmax"])
+
+
+def test_clean_jcp_mode(ctx, port, golden0):
+    _assert_parity(parity.stage_report(ctx, port, golden0["pts"], jcp_mode=JCP_CLEAN, check_ringless=False))
+    ctx.set_jcp_mode(lpl.JCP_AS_REFERENCE)
+
+
+def test_synthetic_frames(ctx, ref):
+    for seed in (4001, 4007):
+        pts, ring = F.synth_scan(seed)
+        _assert_parity(parity.stage_report(ctx, ref, pts, ring_given=ring))
+
+
+def test_cluster_configs_and_azimuth_seam(ctx, port):
+    """H3: the reference's literal azimuth wrap (num_azimuth = ceil(max/res) + 1) must be kept."""
+    rng = np.random.default_rng(5)
+    # a ring of points around the sensor crossing the 0 / 2 pi seam, plus blobs
+    a = rng.uniform(0, 2 * np.pi, 4000)
+    r = 12.0 + rng.normal(0, 0.05, a.size)
+    ringpts = np.stack([r * np.cos(a), r * np.sin(a), rng.uniform(-1, 0.5, a.size)], -1)
+    blobs = rng.normal(0, 0.3, (3000, 3)) + rng.uniform(-40, 40, (30, 1, 3)).repeat(100, 1).reshape(-1, 3) * [1, 1, 0.02]
+    pts = np.zeros((7000, 4), np.float32)
+    pts[:, :3] = np.round(np.concatenate([ringpts, blobs]) * 1000) / 1000
+    for cfg in (NODE_CLUSTER_CFG, dict(range_m=0.4, az_deg=1.0, el_deg=1.5, min_size=3),
+                dict(range_m=1.0, az_deg=2.0, el_deg=2.0, min_size=10),
+                dict(range_m=0.2, az_deg=0.5, el_deg=1.0, min_size=1)):
+        ctx.cluster_config(**cfg)
+        got, k = ctx.cluster(pts)
+        exp, dims = port.cluster(pts, want_dims=True, **cfg)
+        assert np.array_equal(got, exp), cfg
+        assert np.array_equal(ctx.debug_cluster(0), dims)
+        assert k == int(exp.max()) + 1
+    ctx.cluster_config(**NODE_CLUSTER_CFG)
+
+
+def test_convex_hull_entry_point(ctx, port):
+    rng = np.random.default_rng(1)
+    cases = [
+        np.round(rng.normal(0, 5, (500, 2)), 3),
+        np.round(rng.uniform(-1, 1, (5000, 2)), 2),            # many exact duplicates and collinear runs
+        np.stack([np.arange(50.0), 2 * np.arange(50.0)], -1),   # collinear -> 2 vertices
+        np.array([[0, 0], [1, 0], [1, 1], [0, 1], [0.5, 0.5]], float),
+        np.array([[3.0, 4.0]]), np.array([[0.0, 0.0], [1.0, 1.0]]),
+        np.repeat(np.array([[2.0, 2.0]]), 7, 0),                 # all identical
+    ]
+    for xy in cases:
+        xy = xy.astype(np.float32).astype(np.float64)
+        got = ctx.convex_hull(xy)
+        exp = port.convex_hull(xy)
+        assert got.shape == exp.shape
+        # indices may differ between equal points (unstable sort), coordinates may not
+        assert np.abs(xy[got] - xy[exp]).max() <= 1e-5 if got.size else True
+        assert np.array_equal(xy[got], xy[exp])
+    with pytest.raises(lpl.LplError):
+        ctx.convex_hull(np.array([[0.1, 0.2], [1.0, 1.0], [0.0, 3.0]]))  # not float-representable
+
+
+def test_edge_cases(ctx, port):
+    empty = np.zeros((0, 4), np.float32)
+    assert ctx.ring_partition(empty).shape == (0,)
+    assert ctx.dror_filter(empty).shape == (0,)
+    assert ctx.segment(empty, np.zeros(0, np.uint16)).shape == (0,)
+    cl, k = ctx.cluster(empty)
+    assert cl.shape == (0,) and k == 0
+    for n in (1, 2, 3, 31, 257, 2049):
+        rng = np.random.default_rng(n)
+        pts = np.zeros((n, 4), np.float32)
+        pts[:, :3] = np.round(rng.uniform(-30, 30, (n, 3)) * [1, 1, 0.05] * 1000) / 1000
+        ring = rng.integers(0, 64, n).astype(np.uint16)
+        assert np.array_equal(ctx.ring_partition(pts), port.ring_partition(pts))
+        assert np.array_equal(ctx.dror_filter(pts), port.dror(pts))
+        assert np.array_equal(ctx.segment(pts, ring), port.segment(pts, ring))
+        got, k = ctx.cluster(pts)
+        assert np.array_equal(got, port.cluster(pts, **NODE_CLUSTER_CFG))
+    # the point at the origin (KITTI frame 0 has one): range_xy = 0
+    z = np.zeros((5, 4), np.float32)
+    z[1:, 0] = [5, 5.01, 5.02, 5.03]
+    assert np.array_equal(ctx.dror_filter(z), port.dror(z))
+    assert np.array_equal(ctx.segment(z, np.zeros(5, np.uint16)), port.segment(z, np.zeros(5, np.uint16)))
+    # more points than the context was created for -> capacity error, not a crash
+    with pytest.raises(lpl.LplError) as e:
+        ctx.dror_filter(np.zeros((140000, 4), np.float32))
+    assert e.value.code == lpl.native.LPL_ERR_CAPACITY
+
+
+def test_dror_configs_and_permutation_invariance(ctx, port, golden0):
+    pts = golden0["pts"][:60000]
+    for cfg in (dict(mult=0.02, min_radius=0.1, min_neighbours=4), dict(mult=0.05, min_radius=0.2, min_neighbours=8),
+                dict(mult=0.01, min_radius=0.05, min_neighbours=2)):
+        ctx.dror_config(**cfg)
+        assert np.array_equal(ctx.dror_filter(pts), port.dror(pts, **cfg)), cfg
+    ctx.dror_config()
+    base = ctx.dror_filter(pts)
+    perm = np.random.default_rng(0).permutation(pts.shape[0])
+    assert np.array_equal(ctx.dror_filter(np.ascontiguousarray(pts[perm])), base[perm])
+
+
+def test_chained_batch_ragged(ctx, port, golden0, golden100):
+    frames = [golden0["pts"], F.synth_scan(4100)[0], golden100["pts"][:70001].copy(), np.zeros((0, 4), np.float32),
+              golden100["pts"], golden0["pts"][:5].copy()]
+    ctx.cluster_config(**NODE_CLUSTER_CFG)
+    ctx.set_jcp_mode(lpl.JCP_AS_REFERENCE)
+    for dror in (True, False):
+        stages = lpl.STAGE_ALL if dror else (lpl.STAGE_ALL & ~lpl.STAGE_DROR)
+        nf = ctx.upload(frames)
+        ctx.run(nf, stages)
+        ctx.sync(nf)
+        bufs = lpl.BatchBuffers(8, 131072, want=[p[0] for p in lpl.BatchBuffers.PLANES])
+        counts = ctx.download_batch(nf, bufs).copy()
+        for f in range(nf):
+            got = ctx.download(f)
+            exp = parity.oracle_chain(port, frames[f], dror)
+            rep = parity.chain_report(got, exp)
+            assert all(v == 0 for v in rep.values()), (f, dror, rep)
+            # the batched download returns the same planes as the per-frame one
+            n, m, k, hv = got["n"], got["num_obstacles"], got["num_clusters"], got["num_hull_vertices"]
+            assert counts[:, f].tolist() == [n, got["num_valid"], m, k, hv]
+            P = {name: b.array for name, b in bufs.planes.items()}
+            assert np.array_equal(P["labels_u8"][f, :n], got["labels"].astype(np.uint8))
+            assert np.array_equal(P["noise"][f, :n], got["noise"])
+            assert np.array_equal(P["ring"][f, :n], got["ring"])
+            assert np.array_equal(P["obstacle_index"][f, :m], got["obstacle_index"])
+            assert np.array_equal(P["cluster_labels"][f, :m], got["cluster_labels"])
+            assert np.array_equal(P["hull_offsets"][f, :k + 1], got["hull_offsets"])
+            assert np.array_equal(P["hull_xy"][f, :hv], got["hull_xy"])
+            assert np.array_equal(P["zminmax"][f, :k], got["zminmax"])
+        bufs.close()
+
+
+def test_128_beam_config(port):
+    """BASELINE.json configs[2]: 128 x 2048 organised frames."""
+    pts, ring = F.synth_scan(3000, beams=128, n_boxes=120, n_poles=80, dropout=0.01)
+    c = lpl.Context(0, max_points=pts.shape[0], max_frames=1, image_height=128, image_width=2048)
+    cfg = c.segmenter_default_cfg()
+    cfg.image_height = 128
+    c.segmenter_config(cfg)
+    port.segment_config(default_seg_cfg(image_height=128))
+    try:
+        exp = port.segment(pts, ring)
+        got = c.segment(pts, ring)
+        assert np.array_equal(got, exp)
+        obs = np.ascontiguousarray(pts[exp == 2])
+        c.cluster_config(**NODE_CLUSTER_CFG)
+        cl, k = c.cluster(obs)
+        assert np.array_equal(cl, port.cluster(obs, **NODE_CLUSTER_CFG))
+    finally:
+        port.segment_config(default_seg_cfg())
+        c.close()
+
+
+def test_unorganized_2m_cloud_properties(port):
+    """BASELINE.json configs[4] at reduced size against the oracle, and at full size (2 M points)
+    through size-independent properties: idempotence and DROR monotonicity in the radius."""
+    small = F.synth_unorganized(5000, n=200_000, n_blobs=500)
+    c = lpl.Context(0, max_points=2_000_000, max_frames=1)
+    try:
+        assert np.array_equal(c.dror_filter(small), port.dror(small))
+        cl, k = c.cluster(small)
+        exp = port.cluster(small, range_m=0.4, az_deg=1.0, el_deg=1.5, min_size=3)
+        assert np.array_equal(cl, exp)
+        off, xy, idx, zmm = c.cluster_hulls(small, cl)
+        eo, exy, eidx, ezmm = port.cluster_hulls(small, exp)
+        assert np.array_equal(off, eo) and np.array_equal(xy, exy.astype(np.float32))
+        big = F.synth_unorganized(5001)
+        a = c.dror_filter(big)
+        assert np.array_equal(a, c.dror_filter(big))                 # idempotent / deterministic
+        c.dror_config(mult=0.04, min_radius=0.2, min_neighbours=4)
+        b = c.dror_filter(big)
+        assert int(((b == 1) & (a == 0)).sum()) == 0                 # a larger radius never adds noise
+        cl1, k1 = c.cluster(big)
+        cl2, k2 = c.cluster(big)
+        assert k1 == k2 and np.array_equal(cl1, cl2)
+        # canonical labelling: cluster ids are ranked by their minimum point index
+        first = np.full(k1, big.shape[0], np.int64)
+        np.minimum.at(first, cl1[cl1 >= 0], np.flatnonzero(cl1 >= 0))
+        assert np.all(np.diff(first) > 0)
+        sizes = np.bincount(cl1[cl1 >= 0], minlength=k1)
+        assert sizes.min() >= 3
+    finally:
+        c.close()
+
+
+@pytest.mark.skipif(not F.have_pack(), reason="data/kitti154.npz not built")
+def test_full_sequence_batch_vs_reference_summary():
+    """BASELINE.json configs[1] at full size: all 154 frames as ONE batch; labels / clusters / hulls
+    hash to what the unmodified reference produced frame by frame (tests/golden/kitti154_summary.json)."""
+    summ = json.load(open(os.path.join(F.GOLDEN_DIR, "kitti154_summary.json")))["frames"]
+    frames = F.load_pack()
+    c = lpl.Context(0, max_points=max(f.shape[0] for f in frames), max_frames=len(frames))
+    try:
+        c.cluster_config(**NODE_CLUSTER_CFG)
+        nf = c.upload(frames)
+        c.run(nf, lpl.STAGE_ALL & ~lpl.STAGE_DROR)   # the summary chain has no DROR (the node never wires it)
+        c.sync(nf)
+        for f, s in enumerate(summ):
+            got = c.download(f)
+            assert label_hash(got["ring"]) == s["ring_hash"], f
+            assert label_hash(got["labels"]) == s["label_hash"], f
+            assert got["num_clusters"] == s["clusters"], f
+            assert label_hash(got["cluster_labels"].astype(np.int64).astype(np.uint32)) == s["cluster_hash"], f
+            assert label_hash(got["hull_offsets"]) == s["hull_offsets_hash"], f
+            assert label_hash(got["hull_xy"].view(np.uint32).reshape(-1)) == s["hull_xy_hash"], f
+        # DROR stage-wise on the raw clouds
+        c.run(nf, lpl.STAGE_DROR)
+        c.sync(nf)
+        for f, s in enumerate(summ):
+            got = c.download(f)
+            assert int(got["noise"].sum()) == s["dror_noise_exact"], f
+            assert label_hash(got["noise"]) == s["dror_hash"], f
+    finally:
+        c.close()

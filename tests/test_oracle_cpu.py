@@ -1,0 +1,177 @@
+"""CPU suite: pins the oracle (port restatement + unmodified reference build) against the committed
+golden fixtures, which were produced by the reference's own sources (tools/make_golden.py).
+The reference's test-suite holds no vectors for this path."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle.oracle import JCP_AS_IS, JCP_AS_IS_DATAFLOW, JCP_CLEAN, JCP_CLEAN_DATAFLOW, NODE_CLUSTER_CFG, label_hash
+from tools import frames as F
+
+
+def _check_frame(o, g, is_port):
+    pts = g["pts"]
+    ring = o.ring_partition(pts) if is_port else g["ring"].astype(np.uint16)
+    if is_port:
+        assert np.array_equal(ring, g["ring"].astype(np.uint16))
+        labels, img, dbg = o.segment(pts, ring, want_image=True, want_debug=True)
+        elev = dbg["elevation"]
+    else:
+        labels, img = o.segment(pts, ring, want_image=True)
+        elev = o.segment_intermediates()["elevation"]
+    assert np.array_equal(labels, g["labels"].astype(np.uint32))
+    assert np.array_equal(np.packbits(img.reshape(-1) > 0), g["image"])
+    assert np.array_equal(elev.view(np.uint32), g["elevation"].view(np.uint32))
+    assert np.array_equal(o.segment(pts, None), g["labels_noring"].astype(np.uint32))
+    obs = np.ascontiguousarray(pts[labels == 2])
+    if is_port:
+        cl, dims = o.cluster(obs, want_dims=True, **NODE_CLUSTER_CFG)
+    else:
+        o.cluster_config(**NODE_CLUSTER_CFG)
+        cl, dims = o.cluster(obs, want_dims=True)
+    assert np.array_equal(cl, g["cluster_labels"].astype(np.int32))
+    assert np.array_equal(dims, g["voxel_dims"])
+    return obs, cl
+
+
+def test_port_matches_golden(port, golden0, golden100):
+    for g in (golden0, golden100):
+        obs, cl = _check_frame(port, g, True)
+        off, xy, idx, zmm = port.cluster_hulls(obs, cl)
+        assert np.array_equal(off, g["hull_offsets"])
+        assert np.array_equal(xy.astype(np.float32), g["hull_xy"])
+        assert np.array_equal(zmm.astype(np.float32), g["zminmax"])
+        assert np.array_equal(np.packbits(port.dror(g["pts"])), g["dror_exact"])
+
+
+def test_reference_build_matches_golden(ref, golden0):
+    _check_frame(ref, golden0, False)
+    n = golden0["pts"].shape[0]
+    assert np.array_equal(np.packbits(ref.dror(golden0["pts"], mode="exact")), golden0["dror_exact"])
+    # the as-is result (stale KD-tree stack, hazard H1) is one-directional: it only ever turns
+    # NOISE into VALID
+    as_is = np.unpackbits(golden0["dror_as_is"])[:n]
+    exact = np.unpackbits(golden0["dror_exact"])[:n]
+    assert int(((as_is == 1) & (exact == 0)).sum()) == 0
+    assert int(as_is.sum()) == 69 and int(exact.sum()) == 1050
+
+
+def test_known_answers_survey(golden0):
+    """SURVEY.md 8c provisional known-answers, re-derived from the committed fixture."""
+    lab = golden0["labels"]
+    assert golden0["pts"].shape[0] == 123398
+    assert [int((lab == k).sum()) for k in (1, 2, 0)] == [67718, 46500, 9180]
+    assert int(golden0["cluster_labels"].max()) + 1 == 262
+    assert int((golden0["cluster_labels"] < 0).sum()) == 151
+    assert golden0["hull_xy"].shape[0] == 1803
+    assert int(golden0["ring"].min()) == 0 and int(golden0["ring"].max()) == 63
+
+
+def test_rng_stream_matches_libstdcxx(port):
+    """std::mt19937{42} + uniform_int_distribution (segmenter.cpp:369-371): the restated Lemire
+    mapping must equal libstdc++'s own distribution (hazard H8)."""
+    import random
+
+    first = port.rng_draws(0xFFFFFFFF, 4)  # n = 2^32 - 1 is (almost) the raw stream
+    assert first.shape == (4,)
+    for n in (2, 3, 7, 1000, 38328, 40552, 123457, 2 ** 31 + 11):
+        a = port.rng_draws(n, 300)
+        b = port.rng_draws(n, 300, std=True)
+        assert np.array_equal(a, b), n
+        assert int(a.max()) < n
+    _ = random
+
+
+def test_port_equals_reference_on_synthetic(port, ref):
+    for seed in (4001, 4002):
+        pts, ring = F.synth_scan(seed)
+        a = port.segment(pts, ring)
+        b = ref.segment(pts, ring)
+        assert np.array_equal(a, b)
+        assert np.array_equal(port.segment(pts, None), ref.segment(pts, None))
+        obs = np.ascontiguousarray(pts[a == 2])
+        for cfg in (NODE_CLUSTER_CFG, dict(range_m=0.4, az_deg=1.0, el_deg=1.5, min_size=3),
+                    dict(range_m=1.0, az_deg=2.0, el_deg=2.0, min_size=10)):
+            ref.cluster_config(**cfg)
+            assert np.array_equal(port.cluster(obs, **cfg), ref.cluster(obs))
+        assert np.array_equal(port.dror(pts), ref.dror(pts, mode="exact"))
+
+
+def test_port_equals_reference_128_beams(port, ref):
+    from oracle.oracle import default_seg_cfg
+
+    pts, ring = F.synth_scan(3000, beams=128, n_boxes=120, n_poles=80, dropout=0.01)
+    cfg = default_seg_cfg(image_height=128)
+    port.segment_config(cfg)
+    ref.segment_config(cfg)
+    try:
+        assert np.array_equal(port.segment(pts, ring), ref.segment(pts, ring))
+    finally:
+        port.segment_config(default_seg_cfg())
+        ref.segment_config(default_seg_cfg())
+
+
+def test_jcp_dataflow_equals_raster(port, golden0, golden100):
+    """The GPU resolves JCP as a data-flow relaxation; the port carries the same schedule as a
+    cross-check that it reproduces the reference's raster-order Gauss-Seidel sweep exactly."""
+    for g in (golden0, golden100):
+        ring = g["ring"].astype(np.uint16)
+        assert np.array_equal(port.segment(g["pts"], ring, jcp_mode=JCP_AS_IS),
+                              port.segment(g["pts"], ring, jcp_mode=JCP_AS_IS_DATAFLOW))
+        assert np.array_equal(port.segment(g["pts"], ring, jcp_mode=JCP_CLEAN),
+                              port.segment(g["pts"], ring, jcp_mode=JCP_CLEAN_DATAFLOW))
+
+
+def test_edge_cases(port, ref):
+    empty = np.zeros((0, 4), np.float32)
+    assert port.segment(empty, np.zeros(0, np.uint16)).shape == (0,)
+    assert ref.segment(empty, np.zeros(0, np.uint16)).shape == (0,)
+    assert port.cluster(empty).shape == (0,)
+    assert port.dror(empty).shape == (0,)
+    assert port.ring_partition(empty).shape == (0,)
+    # isolated points are all noise; 4 coincident points are all valid (self counts)
+    far = np.array([[10, 0, 0, 0], [20, 0, 0, 0], [30, 5, 0, 0]], np.float32)
+    assert port.dror(far).tolist() == [1, 1, 1]
+    assert ref.dror(far, mode="exact").tolist() == [1, 1, 1]
+    same = np.tile(np.array([[10, 1, 0, 0]], np.float32), (4, 1))
+    assert port.dror(same).tolist() == [0, 0, 0, 0]
+    # a cluster below min size is dropped; hull of < 3 points is the identity
+    two = np.array([[10, 0, 0, 0], [10.05, 0, 0, 0]], np.float32)
+    assert port.cluster(two, **NODE_CLUSTER_CFG).tolist() == [-1, -1]
+    assert port.convex_hull(np.array([[0.0, 0.0], [1.0, 1.0]])).tolist() == [0, 1]
+    # collinear points collapse to the two extremes; square keeps 4 corners CCW from the lexicographic minimum
+    line = np.stack([np.arange(6.0), np.arange(6.0)], -1)
+    assert port.convex_hull(line).tolist() == [0, 5]
+    sq = np.array([[1, 1], [0, 0], [1, 0], [0, 1], [0.5, 0.5]], np.float64)
+    assert port.convex_hull(sq).tolist() == [1, 2, 0, 3]
+
+
+def test_dilate_shim_matches_opencv(ref):
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(0)
+    img = (rng.random((64, 2048)) < 0.02).astype(np.uint8) * 255
+    exp = cv2.dilate(img, cv2.getStructuringElement(cv2.MORPH_RECT, (5, 5)))
+    assert np.array_equal(ref.shim_dilate(img), exp)
+
+
+@pytest.mark.skipif(not F.have_pack(), reason="data/kitti154.npz not built")
+def test_port_matches_reference_summary_all_154(port):
+    """Every KITTI frame: the port's outputs hash to what the unmodified reference produced."""
+    summ = json.load(open(os.path.join(F.GOLDEN_DIR, "kitti154_summary.json")))["frames"]
+    frames = F.load_pack()
+    assert len(frames) == len(summ) == 154
+    for s, pts in list(zip(summ, frames))[::3]:
+        ring = port.ring_partition(pts)
+        assert label_hash(ring) == s["ring_hash"]
+        labels = port.segment(pts, ring)
+        assert label_hash(labels) == s["label_hash"], s["frame"]
+        obs = np.ascontiguousarray(pts[labels == 2])
+        cl = port.cluster(obs, **NODE_CLUSTER_CFG)
+        assert int(cl.max()) + 1 == s["clusters"]
+        assert label_hash(cl.astype(np.int64).astype(np.uint32)) == s["cluster_hash"]
+        off, xy, idx, zmm = port.cluster_hulls(obs, cl)
+        assert xy.shape[0] == s["hull_vertices"]
+        assert label_hash(xy.astype(np.float32).view(np.uint32).reshape(-1)) == s["hull_xy_hash"]
+        assert int(port.dror(pts).sum()) == s["dror_noise_exact"]

@@ -19,19 +19,26 @@ PACK_PATH = os.path.join(ROOT, "data", "kitti154.npz")
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 
 
-def encode_xyz_mm(xyz: np.ndarray) -> np.ndarray:
+def encode_xyz_mm(xyz: np.ndarray):
+    """(n, 3) float32 -> (int32 millimetre deltas, flat indices of the -0.0 entries)."""
+    xyz = np.ascontiguousarray(xyz, np.float32)
     k = np.round(xyz.astype(np.float64) * 1000.0).astype(np.int64)
     back = (k.astype(np.float64) / 1000.0).astype(np.float32)
-    if not np.array_equal(back, xyz.astype(np.float32)):
+    if not np.array_equal(back, xyz):
         raise ValueError("cloud is not exactly millimetre-quantised")
-    return np.diff(k, axis=0, prepend=0).astype(np.int32)
+    negzero = np.flatnonzero(xyz.reshape(-1).view(np.uint32) == 0x80000000).astype(np.uint32)
+    return np.diff(k, axis=0, prepend=0).astype(np.int32), negzero
 
 
-def decode_xyz_mm(delta: np.ndarray) -> np.ndarray:
-    """(n, 3) int32 deltas -> (n, 4) float32 x, y, z, 0 (bit-identical to the PCD floats)."""
+def decode_xyz_mm(delta: np.ndarray, negzero=None) -> np.ndarray:
+    """(n, 3) int32 deltas (+ the -0.0 positions) -> (n, 4) float32 x, y, z, 0, bit-identical to the
+    PCD floats (KITTI frames do contain negative zeros)."""
     k = np.cumsum(delta.astype(np.int64), axis=0)
+    xyz = (k.astype(np.float64) / 1000.0).astype(np.float32)
+    if negzero is not None and len(negzero):
+        xyz.reshape(-1).view(np.uint32)[np.asarray(negzero, np.int64)] = 0x80000000
     out = np.zeros((k.shape[0], 4), np.float32)
-    out[:, :3] = (k.astype(np.float64) / 1000.0).astype(np.float32)
+    out[:, :3] = xyz
     return out
 
 
@@ -41,17 +48,17 @@ def have_pack() -> bool:
 
 def load_pack(limit: int | None = None) -> list[np.ndarray]:
     z = np.load(PACK_PATH)
-    names = sorted(z.files)
+    names = sorted(k for k in z.files if k.startswith("f"))
     if limit is not None:
         names = names[:limit]
-    return [decode_xyz_mm(z[k]) for k in names]
+    return [decode_xyz_mm(z[k], z["z" + k[1:]]) for k in names]
 
 
 def load_golden(name: str) -> dict:
     """tests/golden/<name>.npz -> dict with 'pts' (n, 4) float32 and the expected outputs."""
     z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
     out = {k: z[k] for k in z.files}
-    out["pts"] = decode_xyz_mm(out.pop("delta"))
+    out["pts"] = decode_xyz_mm(out.pop("delta"), out.pop("negzero", None))
     return out
 
 

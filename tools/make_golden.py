@@ -61,7 +61,7 @@ def work(path):
     if idx in FULL:
         np.savez_compressed(
             os.path.join(GOLDEN_DIR, f"kitti_f{idx:03d}.npz"),
-            delta=encode_xyz_mm(pts[:, :3]), ring=ring.astype(np.uint8), labels=labels.astype(np.uint8),
+            delta=encode_xyz_mm(pts[:, :3])[0], negzero=encode_xyz_mm(pts[:, :3])[1], ring=ring.astype(np.uint8), labels=labels.astype(np.uint8),
             labels_noring=labels_noring.astype(np.uint8),
             image=np.packbits(img.reshape(-1) > 0), elevation=inter["elevation"],
             cluster_labels=clabels.astype(np.int16), voxel_dims=dims,

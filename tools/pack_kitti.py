@@ -25,9 +25,10 @@ def main(src="/root/reference/data"):
     total = 0
     for f in files:
         p = read_pcd_xyzi(f)
-        d = encode_xyz_mm(p[:, :3])
-        assert np.array_equal(decode_xyz_mm(d)[:, :3], p[:, :3])
+        d, nz = encode_xyz_mm(p[:, :3])
+        assert np.array_equal(decode_xyz_mm(d, nz)[:, :3].view(np.uint32), p[:, :3].view(np.uint32))
         arrays["f" + os.path.basename(f)[:-4]] = d
+        arrays["z" + os.path.basename(f)[:-4]] = nz
         total += p.shape[0]
     os.makedirs(os.path.dirname(PACK_PATH), exist_ok=True)
     np.savez_compressed(PACK_PATH, **arrays)
