@@ -164,46 +164,56 @@ def batch_stats(ctx, nf, seg_dbg=True) -> dict:
 # reference CPU path (oracle/_ref = the reference's own sources; port only for the two stages the
 # reference keeps outside the library: ring partition and the per-cluster gather + hull call)
 # --------------------------------------------------------------------------------------------
+_W = {}
+
+
+def _cpu_worker_init(limit):
+    from oracle.oracle import PortOracle, RefOracle, have_ref
+
+    _W["frames"] = load_frames(limit)[0]
+    _W["ref"] = RefOracle() if have_ref() else None
+    _W["port"] = PortOracle()
+
+
+def _cpu_worker_frame(i):
+    """Whole hot path on frame i, chained as in DESIGN.md (ring -> DROR -> segment VALID ->
+    cluster OBSTACLE -> hulls), through the reference's own code where it is a library function."""
+    ref, port, pts = _W["ref"], _W["port"], _W["frames"][i]
+    ring = port.ring_partition(pts)
+    noise = ref.dror(pts, mode="as_is") if ref is not None else port.dror(pts)
+    keep = noise == 0
+    pv = np.ascontiguousarray(pts[keep])
+    rv = np.ascontiguousarray(ring[keep])
+    labels = ref.segment(pv, rv) if ref is not None else port.segment(pv, rv)
+    obs = np.ascontiguousarray(pv[labels == 2])
+    cl = ref.cluster(obs) if ref is not None else port.cluster(obs)
+    off, xy, idx, zmm = port.cluster_hulls(obs, cl)
+    return int(off[-1]) if off.size else 0
+
+
 class CpuReference:
-    def __init__(self):
-        from oracle.oracle import PortOracle, RefOracle, have_ref
+    """The reference's CPU path on `procs` worker processes (the library is single-threaded and
+    its objects are not thread-safe, so one process per core with its own instances)."""
 
+    def __init__(self, procs: int, limit: int):
+        import multiprocessing as mp
+
+        from oracle.oracle import build, have_ref
+
+        build()
         self.kind = "reference" if have_ref() else "port"
-        self._mk = (lambda: (RefOracle(), PortOracle())) if have_ref() else (lambda: (None, PortOracle()))
-        self.tls = threading.local()
+        self.procs = procs
+        self.pool = mp.get_context("spawn").Pool(procs, initializer=_cpu_worker_init, initargs=(limit,))
+        self.pool.map(_cpu_worker_frame, list(range(min(limit, procs))))  # warm-up: imports, page faults
 
-    def _inst(self):
-        if not hasattr(self.tls, "o"):
-            self.tls.o = self._mk()
-        return self.tls.o
-
-    def frame(self, pts: np.ndarray):
-        """Whole hot path on one frame, chained as in DESIGN.md (ring -> DROR -> segment VALID ->
-        cluster OBSTACLE -> hulls)."""
-        ref, port = self._inst()
-        ring = port.ring_partition(pts)
-        noise = ref.dror(pts, mode="as_is") if ref is not None else port.dror(pts)
-        keep = noise == 0
-        pv = np.ascontiguousarray(pts[keep])
-        rv = np.ascontiguousarray(ring[keep])
-        labels = ref.segment(pv, rv) if ref is not None else port.segment(pv, rv)
-        obs = np.ascontiguousarray(pv[labels == 2])
-        cl = ref.cluster(obs) if ref is not None else port.cluster(obs)
-        off, xy, idx, zmm = port.cluster_hulls(obs, cl)
-        return int(off[-1]) if off.size else 0
-
-    def run(self, frames, threads: int) -> float:
-        """Seconds to push `frames` through `threads` worker threads (ctypes drops the GIL)."""
-        from concurrent.futures import ThreadPoolExecutor
-
+    def run(self, idx) -> float:
         t0 = time.perf_counter()
-        if threads <= 1:
-            for p in frames:
-                self.frame(p)
-        else:
-            with ThreadPoolExecutor(max_workers=threads) as ex:
-                list(ex.map(self.frame, frames))
+        self.pool.map(_cpu_worker_frame, list(idx), chunksize=1)
         return time.perf_counter() - t0
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
 
 
 def host_cores() -> int:
@@ -218,18 +228,18 @@ def run_reference_arm(args, rank, world):
         return 0
     frames, workload, data_desc = load_frames()
     cores = host_cores()
-    cpu = CpuReference()
     per_step = min(len(frames), 2 * cores)
-    sample = frames[:per_step]
-    for _ in range(args.warmup):
-        cpu.run(sample[: max(cores, 1)], cores)
+    cpu = CpuReference(cores, per_step)
+    for _ in range(min(args.warmup, 1)):
+        cpu.run(range(per_step))
     t = 0.0
     for _ in range(args.steps):
-        t += cpu.run(sample, cores)
+        t += cpu.run(range(per_step))
+    cpu.close()
     fps = per_step * args.steps / t
     desc = (f"{per_step} frames of {workload} per step through the reference's own CPU code "
             f"(oracle/_ref: unmodified segmenter/clusterer/noise_remover sources; ring partition and hull "
-            f"gather restated) on {cores} threads")
+            f"gather restated) on {cores} worker processes")
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
@@ -363,13 +373,13 @@ def run_ours(args, rank, local_rank, world):
     cpu_baseline = None
     if world == 1 and not args.no_cpu:
         cores = host_cores()
-        cpu = CpuReference()
-        sample = frames[: min(nf, 2 * cores)]
-        cpu.run(sample[:cores], cores)  # warm-up (library load, page faults)
-        secs = cpu.run(sample, cores)
-        cpu_baseline = {"value": len(sample) / secs, "unit": UNIT, "cores": cores, "kind": cpu.kind,
-                        "sample": f"first {len(sample)} frames of {workload}, whole chained pipeline, "
-                                  f"{cores} threads, {secs:.1f} s"}
+        ns = min(nf, 4 * cores)
+        cpu = CpuReference(cores, ns)
+        secs = cpu.run(range(ns))
+        cpu.close()
+        cpu_baseline = {"value": ns / secs, "unit": UNIT, "cores": cores, "kind": cpu.kind,
+                        "sample": f"first {ns} frames of {workload} (unrotated), whole chained pipeline, "
+                                  f"{cores} worker processes, {secs:.1f} s"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -1013,6 +1013,11 @@ void launch_segment(Ctx* c, std::uint32_t nf, bool want_image)
     k_jcp_pre<<<dim3((d.qcap + 127) / 128, nf), 128, 0, s>>>(d, sp);
     mark(c, "jcp_pre");
     const std::size_t plane_bytes = static_cast<std::size_t>((sp.npx + 15) / 16) * 4;
+    if (plane_bytes > 48 * 1024)
+    {
+        // 128-beam images: 64 KB state plane (opt-in above 48 KB; up to 227 KB per CTA on sm_100a)
+        cudaFuncSetAttribute(k_jcp_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(plane_bytes));
+    }
     k_jcp_resolve<<<nf, 1024, plane_bytes, s>>>(d, sp, want_image ? 1 : 0);
     mark(c, "jcp_resolve");
 }
