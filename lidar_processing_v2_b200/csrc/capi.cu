@@ -88,7 +88,8 @@ void carve(Dev& d, Carver& cv, int npx, int ncell_cap, std::uint32_t** mt_raw)
     cv.take(d.mk, B * q);
     cv.take(d.stale_ref, B * d.nborder_cap * 12);
     cv.take(d.n_border, B);
-    cv.take(d.pend, B * 2 * q);
+    cv.take(d.runs, B * q);
+    cv.take(d.n_runs, B);
     cv.take(d.jcp_rounds, B);
     cv.take(d.seg_label, B * cap);
     cv.take(d.labels_out, B * cap);
@@ -108,8 +109,10 @@ void carve(Dev& d, Carver& cv, int npx, int ncell_cap, std::uint32_t** mt_raw)
     cv.take(d.n_clusters, B);
     cv.take(d.ccount, B * cap);
     cv.take(d.cstart, B * (cap + 1));
-    cv.take(d.hsk, B * cap);
-    cv.take(d.hsi, B * cap);
+    cv.take(d.hsA, B * cap);
+    cv.take(d.hsB, B * cap);
+    cv.take(d.hstL, B * cap);
+    cv.take(d.hstU, B * cap);
     cv.take(d.hstack, B * 2 * cap);
     cv.take(d.hcnt, B * cap);
     cv.take(d.hull_off, B * (cap + 1));
@@ -117,6 +120,8 @@ void carve(Dev& d, Carver& cv, int npx, int ncell_cap, std::uint32_t** mt_raw)
     cv.take(d.hull_xy, B * cap);
     cv.take(d.zminmax, B * cap);
     cv.take(d.n_hull, B);
+    cv.take(d.zmin_u, B * cap);
+    cv.take(d.zmax_u, B * cap);
     const std::size_t tl = std::max<std::size_t>(d.tiles, d.ptiles);
     cv.take(d.tile_cnt, B * tl);
     cv.take(d.status, B);
@@ -266,7 +271,8 @@ int check_status(lpl_ctx* ctx, std::uint32_t nf)
             std::snprintf(c.err, sizeof(c.err),
                           "frame %u exceeded a reserved capacity:%s%s%s%s", f,
                           (s & ST_QUEUE_OVERFLOW) ? " JCP queue" : "", (s & ST_RNG_EXHAUSTED) ? " RANSAC RNG table" : "",
-                          (s & ST_HASH_FULL) ? " voxel hash" : "", (s & ST_BORDER_OVERFLOW) ? " JCP border rows" : "");
+                          (s & ST_HASH_FULL) ? " voxel hash" : "",
+                          (s & (ST_BORDER_OVERFLOW | ST_JCP_STALL)) ? " JCP border rows / sweep stall" : "");
             return LPL_ERR_CAPACITY;
         }
     }
@@ -278,20 +284,28 @@ __global__ void k_label_count(Dev d, std::uint32_t K)
     const std::uint32_t f = blockIdx.y;
     const std::uint32_t n = d.n_o[f];
     const std::uint32_t i = blockIdx.x * 256u + threadIdx.x;
-    if (i >= n)
+    if (blockIdx.x * 256u >= n)
     {
         return;
     }
     const std::size_t o = static_cast<std::size_t>(f) * d.cap;
-    const std::int32_t l = d.clabel[o + i];
-    if (l >= 0 && static_cast<std::uint32_t>(l) < K)
+    std::int32_t l = -1;
+    float z = 0.f;
+    if (i < n)
     {
-        atomicAdd(&d.ccount[o + l], 1u);
+        l = d.clabel[o + i];
+        if (l >= 0 && static_cast<std::uint32_t>(l) < K)
+        {
+            atomicAdd(&d.ccount[o + l], 1u);
+            z = d.pts_o[o + i].z;
+        }
+        else
+        {
+            l = -1;
+            d.clabel[o + i] = -1;
+        }
     }
-    else
-    {
-        d.clabel[o + i] = -1;
-    }
+    accumulate_zext(d.zmin_u + o, d.zmax_u + o, l, z);
 }
 } // namespace
 
@@ -980,6 +994,8 @@ int lpl_cluster_hulls(lpl_ctx* ctx, const void* points, std::size_t stride, cons
     LPL_TRY(cudaMemcpyAsync(d.clabel, labels, sizeof(std::int32_t) * n, cudaMemcpyHostToDevice, c.stream));
     LPL_TRY(cudaMemcpyAsync(d.n_clusters, &num_clusters, 4, cudaMemcpyHostToDevice, c.stream));
     LPL_TRY(cudaMemsetAsync(d.ccount, 0, sizeof(std::uint32_t) * num_clusters, c.stream));
+    LPL_TRY(cudaMemsetAsync(d.zmin_u, 0xff, sizeof(std::uint32_t) * num_clusters, c.stream));
+    LPL_TRY(cudaMemsetAsync(d.zmax_u, 0, sizeof(std::uint32_t) * num_clusters, c.stream));
     k_label_count<<<dim3((d.cap + 255) / 256, 1), 256, 0, c.stream>>>(d, num_clusters);
     mark(&c, "label_count");
     launch_hulls(&c, 1);

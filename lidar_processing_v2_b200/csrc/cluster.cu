@@ -89,10 +89,36 @@ __device__ __forceinline__ VoxelDims voxel_dims(const Dev& d, const ClusterParam
     return v;
 }
 
-__device__ __forceinline__ std::uint32_t voxel_hash(std::int32_t key)
+// Block-coherent open addressing: the table is split into buckets of 8 slots (one 32-byte
+// sector); a voxel's bucket comes from hashing (flat >> 3) and its place inside the bucket is
+// (flat & 7), so the range neighbours r - 1, r, r + 1 of a voxel (consecutive flat indices)
+// almost always share a sector. A taken slot sends the probe to the same place of the next bucket.
+// Only the first pow2 >= 2 * n_o slots of the frame's table are used (min 1024), which keeps the
+// random look-ups of a frame inside a few hundred KB of L2.
+__device__ __forceinline__ std::uint32_t voxel_slots(const Dev& d, std::uint32_t f)
 {
-    std::uint32_t h = static_cast<std::uint32_t>(key) * 0x9E3779B1u;
-    return h ^ (h >> 15);
+    const std::uint32_t n = d.n_o[f];
+    std::uint32_t s = 1024u;
+    if (n > 512u)
+    {
+        s = 1u << (32 - __clz(2u * n - 1u));
+    }
+    return min(s, d.hcap);
+}
+
+// probe t of the sequence that starts at `home`: first the same place of every bucket, then (only
+// when all of those are taken, e.g. every key congruent modulo 8) plain linear probing
+__device__ __forceinline__ std::uint32_t voxel_probe(std::uint32_t home, std::uint32_t t, std::uint32_t slots)
+{
+    const std::uint32_t nb = slots / 8u;
+    return (t < nb ? home + 8u * t : home + (t - nb) + 1u) & (slots - 1u);
+}
+
+__device__ __forceinline__ std::uint32_t voxel_home(std::int32_t key, std::uint32_t slots)
+{
+    std::uint32_t h = (static_cast<std::uint32_t>(key) >> 3) * 0x9E3779B1u;
+    h ^= h >> 15;
+    return ((h & (slots / 8u - 1u)) << 3) | (static_cast<std::uint32_t>(key) & 7u);
 }
 
 __global__ void __launch_bounds__(256) k_clu_insert(Dev d, ClusterParams cp)
@@ -111,19 +137,19 @@ __global__ void __launch_bounds__(256) k_clu_insert(Dev d, ClusterParams cp)
     const std::int32_t ai = static_cast<std::int32_t>(s.y / cp.az_res);
     const std::int32_t ei = static_cast<std::int32_t>(s.z / cp.el_res);
     const std::int32_t flat = vd.nr * (vd.na * ei + ai) + ri; // clusterer.hpp:136-142
-    const std::uint32_t mask = d.hcap - 1u;
+    const std::uint32_t slots = voxel_slots(d, f);
     std::int32_t* keys = d.hkey + static_cast<std::size_t>(f) * d.hcap;
-    std::uint32_t h = voxel_hash(flat) & mask;
+    const std::uint32_t home = voxel_home(flat, slots);
     std::uint32_t slot = 0xffffffffu;
-    for (std::uint32_t probe = 0; probe < d.hcap; ++probe)
+    for (std::uint32_t t = 0; t < slots / 8u + slots; ++t)
     {
+        const std::uint32_t h = voxel_probe(home, t, slots);
         const std::int32_t prev = atomicCAS(&keys[h], -1, flat);
         if (prev == -1 || prev == flat)
         {
             slot = h;
             break;
         }
-        h = (h + 1u) & mask;
     }
     if (slot == 0xffffffffu)
     {
@@ -193,58 +219,70 @@ __global__ void __launch_bounds__(256) k_clu_union(Dev d, ClusterParams cp)
     const VoxelDims vd = voxel_dims(d, cp, f);
     const std::int32_t* keys = d.hkey + ho;
     std::uint32_t* parent = d.hparent + ho;
-    const std::uint32_t mask = d.hcap - 1u;
+    const std::uint32_t slots = voxel_slots(d, f);
     const std::int32_t flat = keys[slot];
     const std::int32_t ri = flat % vd.nr;
     const std::int32_t t = flat / vd.nr;
     const std::int32_t ai = t % vd.na;
     const std::int32_t ei = t / vd.na;
-    for (int de = -1; de <= 1; ++de)
+    // The 26-neighbourhood is symmetric (also across the literal azimuth wrap and the clipped
+    // range / elevation borders), so each voxel only looks at the 13 "forward" offsets
+    // (de, da, dr) > (0, 0, 0); all first probes are issued before any is consumed.
+    std::int32_t key2[13];
+    std::uint32_t slot2[13];
+    std::int32_t found[13];
+    int j = 0;
+#pragma unroll
+    for (int de = 0; de <= 1; ++de)
     {
-        const std::int32_t e2 = ei + de;
-        if (e2 < 0 || e2 >= vd.ne)
+#pragma unroll
+        for (int da = -1; da <= 1; ++da)
+        {
+#pragma unroll
+            for (int dr = -1; dr <= 1; ++dr)
+            {
+                if (de == 0 && (da < 0 || (da == 0 && dr <= 0)))
+                {
+                    continue;
+                }
+                const std::int32_t e2 = ei + de;
+                std::int32_t a2 = ai + da;
+                a2 = a2 < 0 ? a2 + vd.na : (a2 >= vd.na ? a2 - vd.na : a2);
+                const std::int32_t r2 = ri + dr;
+                const bool ok = e2 < vd.ne && r2 >= 0 && r2 < vd.nr;
+                key2[j] = ok ? vd.nr * (vd.na * e2 + a2) + r2 : -1;
+                slot2[j] = voxel_home(key2[j], slots);
+                ++j;
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 13; ++q)
+    {
+        found[q] = key2[q] >= 0 ? keys[slot2[q]] : -1;
+    }
+#pragma unroll
+    for (int q = 0; q < 13; ++q)
+    {
+        if (key2[q] < 0)
         {
             continue;
         }
-        for (int da = -1; da <= 1; ++da)
+        std::uint32_t h = slot2[q];
+        std::int32_t kk = found[q];
+        for (std::uint32_t t = 1; t <= slots / 8u + slots; ++t)
         {
-            std::int32_t a2 = ai + da;
-            if (a2 < 0)
+            if (kk == key2[q])
             {
-                a2 += vd.na;
+                uf_union(parent, slot, h);
+                break;
             }
-            else if (a2 >= vd.na)
+            if (kk == -1)
             {
-                a2 -= vd.na;
+                break;
             }
-            for (int dr = -1; dr <= 1; ++dr)
-            {
-                if (de == 0 && da == 0 && dr == 0)
-                {
-                    continue;
-                }
-                const std::int32_t r2 = ri + dr;
-                if (r2 < 0 || r2 >= vd.nr)
-                {
-                    continue;
-                }
-                const std::int32_t key2 = vd.nr * (vd.na * e2 + a2) + r2;
-                std::uint32_t h = voxel_hash(key2) & mask;
-                for (std::uint32_t probe = 0; probe < d.hcap; ++probe)
-                {
-                    const std::int32_t kk = keys[h];
-                    if (kk == key2)
-                    {
-                        uf_union(parent, slot, h);
-                        break;
-                    }
-                    if (kk == -1)
-                    {
-                        break;
-                    }
-                    h = (h + 1u) & mask;
-                }
-            }
+            h = voxel_probe(slot2[q], t, slots);
+            kk = keys[h];
         }
     }
 }
@@ -287,7 +325,10 @@ struct ClusterRepEmit
         const std::size_t ho = static_cast<std::size_t>(f) * d.hcap;
         const std::uint32_t root = d.vslot[static_cast<std::size_t>(f) * d.cap + i];
         d.hlabel[ho + root] = static_cast<std::int32_t>(pos);
-        d.ccount[static_cast<std::size_t>(f) * d.cap + pos] = d.hcount[ho + root];
+        const std::size_t o = static_cast<std::size_t>(f) * d.cap;
+        d.ccount[o + pos] = d.hcount[ho + root];
+        d.zmin_u[o + pos] = 0xffffffffu; // z extent accumulators of the new label
+        d.zmax_u[o + pos] = 0u;
     }
 };
 
@@ -296,12 +337,20 @@ __global__ void __launch_bounds__(256) k_clu_labels(Dev d)
     const std::uint32_t f = blockIdx.y;
     const std::uint32_t n = d.n_o[f];
     const std::uint32_t i = blockIdx.x * 256u + threadIdx.x;
-    if (i >= n)
+    if (blockIdx.x * 256u >= n)
     {
         return;
     }
     const std::size_t o = static_cast<std::size_t>(f) * d.cap;
-    d.clabel[o + i] = d.hlabel[static_cast<std::size_t>(f) * d.hcap + d.vslot[o + i]];
+    std::int32_t l = -1;
+    float z = 0.f;
+    if (i < n)
+    {
+        l = d.hlabel[static_cast<std::size_t>(f) * d.hcap + d.vslot[o + i]];
+        d.clabel[o + i] = l;
+        z = d.pts_o[o + i].z;
+    }
+    accumulate_zext(d.zmin_u + o, d.zmax_u + o, l, z);
 }
 
 // hand-over from segmentation: stable compaction of OBSTACLE points in cloud order

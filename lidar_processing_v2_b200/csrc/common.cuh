@@ -113,12 +113,13 @@ struct Dev
     std::uint8_t* code;       // [B][npx]  PX_* before / after JCP
     std::uint32_t* queue;     // [B][qcap] queued pixels in raster order
     std::uint32_t* n_queue;   // [B]
-    float* wn;                // [B][24][qcap] normalised weights, slot-major
+    float* wn;                // [B][qcap][24] normalised weights, entry-major (96 B per queued pixel)
     unsigned long long* mk;   // [B][qcap] 2-bit mask source per slot + flags
     std::uint32_t* stale_ref; // [B][nborder][12] explicit pixel refs for inherited slots
     std::uint32_t* n_border;  // [B]
     std::uint32_t nborder_cap;
-    std::uint32_t* pend;      // [B][2][qcap]
+    std::uint32_t* runs;      // [B][qcap] first queue entry of every run of horizontally adjacent queued pixels
+    std::uint32_t* n_runs;    // [B]
     std::uint32_t* jcp_rounds;// [B]
     std::uint8_t* seg_label;  // [B][cap]  label per point of the segmented cloud
     std::uint8_t* labels_out; // [B][cap]  Label (0/1/2) per *input* point
@@ -140,15 +141,19 @@ struct Dev
     // ---- hulls
     std::uint32_t* ccount;    // [B][cap]  points per cluster (indexed by label)
     std::uint32_t* cstart;    // [B][cap+1]
-    unsigned long long* hsk;  // [B][cap]  sort keys (x, y) per cluster segment
-    std::uint32_t* hsi;       // [B][cap]  point index per cluster segment
-    std::uint32_t* hstack;    // [B][cap]  per-cluster hull vertices (at the segment offset)
+    uint4* hsA;               // [B][cap]  sort elements (label, ord x, ord y, index), ping
+    uint4* hsB;               // [B][cap]  pong
+    std::uint32_t* hstL;      // [B][cap]  per-lane lower-chain stacks of the thinning passes
+    std::uint32_t* hstU;      // [B][cap]  per-lane upper-chain stacks
+    std::uint32_t* hstack;    // [B][2*cap] per-cluster hull vertices (at segment offset + cluster id)
     std::uint32_t* hcnt;      // [B][cap]  hull vertex count per cluster
     std::uint32_t* hull_off;  // [B][cap+1]
     std::uint32_t* hull_idx;  // [B][cap]  obstacle-cloud index per hull vertex
     float2* hull_xy;          // [B][cap]
     float2* zminmax;          // [B][cap]  per cluster
     std::uint32_t* n_hull;    // [B]       hull vertices of the frame
+    std::uint32_t* zmin_u;    // [B][cap]  per cluster: order-preserving bits of min z
+    std::uint32_t* zmax_u;    // [B][cap]  per cluster: order-preserving bits of max z
     // ---- generic
     std::uint32_t* tile_cnt;  // [B][max(tiles, ptiles)]
     std::uint32_t* status;    // [B]  error bits raised by kernels
@@ -161,6 +166,7 @@ enum : std::uint32_t
     ST_RNG_EXHAUSTED = 2u,   // RANSAC needed more than kMtRaws generator outputs
     ST_HASH_FULL = 4u,       // voxel hash table full
     ST_BORDER_OVERFLOW = 8u, // more queued border pixels than reserved
+    ST_JCP_STALL = 16u,      // JCP sweep waited beyond its spin limit (internal error)
 };
 
 // ---------------------------------------------------------------- small device helpers
@@ -286,6 +292,48 @@ __device__ __forceinline__ void tile_ranks(const bool (&flag)[kItems], std::uint
 }
 
 static_assert(kItems * (kTileThreads / 32) == 64, "tile_ranks assumes 64 (round, warp) counters");
+
+// order-preserving float <-> uint32 map (-0.0 folded into +0.0)
+__device__ __forceinline__ std::uint32_t ord_f32(float v)
+{
+    v = v + 0.0f;
+    const std::uint32_t b = __float_as_uint(v);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+__device__ __forceinline__ float unord_f32(std::uint32_t k)
+{
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// z extent per cluster label (src/processor/src/processor.cpp:648-655): lanes of a warp that
+// carry the same label are reduced first, then one atomicMin / atomicMax pair per label and warp.
+// Must be called by all 32 lanes; label < 0 = no contribution.
+__device__ __forceinline__ void accumulate_zext(std::uint32_t* zmin_u, std::uint32_t* zmax_u, std::int32_t label, float z)
+{
+    std::uint32_t todo = __ballot_sync(0xffffffffu, label >= 0);
+    const std::uint32_t zk = ord_f32(z);
+    while (todo != 0)
+    {
+        const int leader = __ffs(todo) - 1;
+        const std::int32_t l = __shfl_sync(0xffffffffu, label, leader);
+        const bool mine = label == l;
+        const std::uint32_t grp = __ballot_sync(0xffffffffu, mine);
+        std::uint32_t lo = mine ? zk : 0xffffffffu, hi = mine ? zk : 0u;
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1)
+        {
+            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, s));
+            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, s));
+        }
+        if (static_cast<int>(lane_id()) == leader)
+        {
+            atomicMin(&zmin_u[l], lo);
+            atomicMax(&zmax_u[l], hi);
+        }
+        todo &= ~grp;
+    }
+}
 
 // ---------------------------------------------------------------- generic tile compaction
 // Stable, order-preserving selection of the items i in [0, n_f) of every frame f for which

@@ -1,196 +1,440 @@
 // Stage 4: per-cluster gather and Andrew monotone-chain convex hulls, batched over frames.
 //
 // Reference:
-//   cluster gather  src/processor/src/processor.cpp:627-658 (O(K*M) rescan per label; here one
-//                   counting-sort pass over the obstacle cloud) incl. z_min / z_max
+//   cluster gather  src/processor/src/processor.cpp:627-658 (O(K*M) rescan per label) incl.
+//                   z_min / z_max
 //   convexHull      lidar_processing_lib/src/polygonizer.cpp:33-91 on PointXY{double x, y}
 //
-// Every cluster is sorted by (x, y) on order-preserving 64-bit keys and then swept by the same
-// sequential lower/upper chain as the reference, with the same fp64 orientation predicate
-// evaluated without FMA contraction, so the vertex list (coordinates) is identical; only the
-// *index* reported for exactly duplicated (x, y) points may differ, as it does between
-// std::sort implementations. Clusters of up to kHullSmem points are sorted and swept in shared
-// memory by one CTA; larger ones use the same network on their global-memory segment.
+// One frame-wide merge sort on the key (cluster label, x, y, point index) replaces both the
+// per-label gather and the per-cluster std::sort: after it every cluster is a contiguous,
+// (x, y)-sorted segment (k_hull_tilesort: 2048-element bitonic tiles in shared memory;
+// k_hull_merge: merge-path passes, each output tile merged in shared memory).
+// One warp then builds each hull (k_hull_chain): clusters above 128 points are first thinned
+// by per-lane monotone chains over contiguous chunks (a point that is not on the lower or upper
+// hull of its chunk cannot be on the cluster's hull), repeatedly, and the survivors are swept by
+// the reference's own lower/upper chain with the same fp64 orientation predicate evaluated
+// without FMA contraction. The vertex list (coordinates) equals the reference's; only the *index*
+// reported for exactly duplicated (x, y) points may differ, as it does between std::sort
+// implementations.
 #include "common.cuh"
 
 namespace lpl
 {
-constexpr int kHullSmem = 2048;
 constexpr int kHullThreads = 128;
-constexpr int kHullBlocks = 592; // 4 CTAs per SM x 148 SMs, grid-stride over clusters
+constexpr int kHullWarps = kHullThreads / 32;
+constexpr int kHullCtasPerFrame = 64;  // 256 warps per frame, warp-stride over clusters
+constexpr std::uint32_t kChainSmem = 512; // survivors swept from shared memory
+constexpr std::uint32_t kFilterAbove = 48;  // clusters above this are thinned by all lanes first
+constexpr std::uint32_t kLaneStack = 16;  // per-lane chain stack entries kept in shared memory
 
-__device__ __forceinline__ std::uint32_t ord_f32(float v)
+// per-lane stack of positions: the first kLaneStack entries live in shared memory (pops are on the
+// critical path of the sweep), deeper ones spill to the lane's slice of a global scratch array
+struct LaneStack
 {
-    v = v + 0.0f; // -0.0 -> +0.0 (the reference comparator treats them as equal)
-    const std::uint32_t b = __float_as_uint(v);
-    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    std::uint32_t* sm;  // this lane's kLaneStack shared-memory entries
+    std::uint32_t* gl;  // this lane's global slice
+    __device__ __forceinline__ std::uint32_t get(std::uint32_t k) const { return k < kLaneStack ? sm[k] : gl[k]; }
+    __device__ __forceinline__ void set(std::uint32_t k, std::uint32_t v) const
+    {
+        if (k < kLaneStack)
+        {
+            sm[k] = v;
+        }
+        else
+        {
+            gl[k] = v;
+        }
+    }
+};
+
+// plain (coherent) load: the thinning passes re-read what earlier passes of the same kernel wrote
+__device__ __forceinline__ uint4 ldg4(const uint4* p) { return *p; }
+
+// element = (label, x bits, y bits, obstacle-cloud index) with -0.0 folded into +0.0 (the
+// reference comparator treats them as equal); the index makes the order total
+__device__ __forceinline__ bool elem_less(const uint4& a, const uint4& b)
+{
+    if (a.x != b.x)
+    {
+        return a.x < b.x;
+    }
+    const float ax = __uint_as_float(a.y), bx = __uint_as_float(b.y);
+    if (ax != bx)
+    {
+        return ax < bx;
+    }
+    const float ay = __uint_as_float(a.z), by = __uint_as_float(b.z);
+    if (ay != by)
+    {
+        return ay < by;
+    }
+    return a.w < b.w;
 }
 
-__device__ __forceinline__ float unord_f32(std::uint32_t k)
+__device__ __forceinline__ std::uint32_t sort_passes(std::uint32_t n)
 {
-    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+    const std::uint32_t nt = (n + kTile - 1) / kTile;
+    return nt <= 1 ? 0u : 32u - __clz(nt - 1u); // ceil(log2(nt))
 }
 
-__global__ void __launch_bounds__(256) k_hull_scatter(Dev d)
+// ------------------------------------------------------------------------------------------
+// tile sort: 2048 elements per CTA, mirror-first bitonic network for arbitrary n (every exchange
+// moves the larger key to the higher index, so the virtual +inf padding beyond n never moves)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTileThreads) k_hull_tilesort(Dev d)
 {
+    __shared__ uint4 s[kTile];
     const std::uint32_t f = blockIdx.y;
     const std::uint32_t n = d.n_o[f];
-    const std::uint32_t i = blockIdx.x * 256u + threadIdx.x;
-    if (i >= n)
+    const std::uint32_t base = blockIdx.x * kTile;
+    if (base >= n)
     {
         return;
     }
     const std::size_t o = static_cast<std::size_t>(f) * d.cap;
-    const std::int32_t l = d.clabel[o + i];
-    if (l < 0)
+    const std::uint32_t m = min(static_cast<std::uint32_t>(kTile), n - base);
+    for (std::uint32_t t = threadIdx.x; t < m; t += kTileThreads)
     {
-        return;
+        const std::uint32_t i = base + t;
+        const float4 p = d.pts_o[o + i];
+        const std::int32_t l = d.clabel[o + i];
+        s[t] = make_uint4(l < 0 ? 0xffffffffu : static_cast<std::uint32_t>(l), __float_as_uint(p.x + 0.0f),
+                          __float_as_uint(p.y + 0.0f), i);
     }
-    // counting down returns ccount to zero; the segment size stays available from cstart
-    const std::uint32_t k = atomicSub(&d.ccount[o + l], 1u) - 1u;
-    const std::uint32_t pos = d.cstart[static_cast<std::size_t>(f) * (d.cap + 1) + l] + k;
-    const float4 p = d.pts_o[o + i];
-    d.hsk[o + pos] = (static_cast<unsigned long long>(ord_f32(p.x)) << 32) | ord_f32(p.y);
-    d.hsi[o + pos] = i;
-}
-
-// CTA-wide ascending sort of (key, value) pairs for arbitrary n. Mirror-first bitonic network:
-// every exchange moves the larger key to the higher index, so the virtual +inf padding beyond
-// n never moves and no physical padding is needed.
-__device__ __forceinline__ void block_sort_pairs(unsigned long long* keys, std::uint32_t* vals, std::uint32_t n)
-{
-    for (std::uint32_t k = 2; (k >> 1) < n; k <<= 1)
+    __syncthreads();
+    for (std::uint32_t k = 2; (k >> 1) < m; k <<= 1)
     {
-        for (std::uint32_t t = threadIdx.x; t < n; t += blockDim.x)
+        for (std::uint32_t t = threadIdx.x; t < m; t += kTileThreads)
         {
             const std::uint32_t u = t ^ (k - 1);
-            if (u > t && u < n)
+            if (u > t && u < m)
             {
-                const unsigned long long a = keys[t], b = keys[u];
-                if (b < a)
+                const uint4 a = s[t], b = s[u];
+                if (elem_less(b, a))
                 {
-                    keys[t] = b;
-                    keys[u] = a;
-                    const std::uint32_t va = vals[t];
-                    vals[t] = vals[u];
-                    vals[u] = va;
+                    s[t] = b;
+                    s[u] = a;
                 }
             }
         }
         __syncthreads();
         for (std::uint32_t j = k >> 2; j > 0; j >>= 1)
         {
-            for (std::uint32_t t = threadIdx.x; t < n; t += blockDim.x)
+            for (std::uint32_t t = threadIdx.x; t < m; t += kTileThreads)
             {
                 const std::uint32_t u = t ^ j;
-                if (u > t && u < n)
+                if (u > t && u < m)
                 {
-                    const unsigned long long a = keys[t], b = keys[u];
-                    if (b < a)
+                    const uint4 a = s[t], b = s[u];
+                    if (elem_less(b, a))
                     {
-                        keys[t] = b;
-                        keys[u] = a;
-                        const std::uint32_t va = vals[t];
-                        vals[t] = vals[u];
-                        vals[u] = va;
+                        s[t] = b;
+                        s[u] = a;
                     }
                 }
             }
             __syncthreads();
         }
     }
+    for (std::uint32_t t = threadIdx.x; t < m; t += kTileThreads)
+    {
+        d.hsA[o + base + t] = s[t];
+    }
+}
+
+// number of elements taken from A among the first `diag` outputs of merge(A, B)
+template <class GetA, class GetB>
+__device__ __forceinline__ std::uint32_t merge_path(GetA A, std::uint32_t la, GetB B, std::uint32_t lb, std::uint32_t diag)
+{
+    std::uint32_t lo = diag > lb ? diag - lb : 0u;
+    std::uint32_t hi = min(diag, la);
+    while (lo < hi)
+    {
+        const std::uint32_t mid = (lo + hi) >> 1;
+        if (elem_less(A(mid), B(diag - 1u - mid)))
+        {
+            lo = mid + 1u;
+        }
+        else
+        {
+            hi = mid;
+        }
+    }
+    return lo;
+}
+
+// merge pass p: runs of (kTile << p) elements, pairwise, one output tile per CTA
+__global__ void __launch_bounds__(kTileThreads) k_hull_merge(Dev d, std::uint32_t pass)
+{
+    __shared__ uint4 s[kTile];
+    __shared__ std::uint32_t s_split[2];
+    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t n = d.n_o[f];
+    const std::uint32_t out0 = blockIdx.x * kTile;
+    if (out0 >= n || sort_passes(n) <= pass)
+    {
+        return; // this frame was fully sorted by an earlier pass
+    }
+    const std::size_t o = static_cast<std::size_t>(f) * d.cap;
+    const uint4* src = ((pass & 1u) ? d.hsB : d.hsA) + o;
+    uint4* dst = ((pass & 1u) ? d.hsA : d.hsB) + o;
+    const std::uint32_t run = static_cast<std::uint32_t>(kTile) << pass;
+    const std::uint32_t pair0 = (out0 / (2u * run)) * (2u * run);
+    const std::uint32_t a0 = pair0, a1 = min(n, a0 + run);
+    const std::uint32_t b0 = a1, b1 = min(n, b0 + run);
+    const std::uint32_t la = a1 - a0, lb = b1 - b0;
+    const std::uint32_t d0 = out0 - pair0;
+    const std::uint32_t d1 = min(d0 + static_cast<std::uint32_t>(kTile), la + lb);
+    const std::uint32_t cnt = d1 - d0;
+    if (lb == 0)
+    {
+        for (std::uint32_t t = threadIdx.x; t < cnt; t += kTileThreads)
+        {
+            dst[out0 + t] = src[out0 + t];
+        }
+        return;
+    }
+    if (threadIdx.x == 0 || threadIdx.x == 32)
+    {
+        const std::uint32_t dg = threadIdx.x == 0 ? d0 : d1;
+        s_split[threadIdx.x >> 5] = merge_path([&](std::uint32_t i) { return src[a0 + i]; }, la,
+                                               [&](std::uint32_t i) { return src[b0 + i]; }, lb, dg);
+    }
+    __syncthreads();
+    const std::uint32_t ai0 = s_split[0], ai1 = s_split[1];
+    const std::uint32_t bi0 = d0 - ai0, bi1 = d1 - ai1;
+    const std::uint32_t na = ai1 - ai0, nb = bi1 - bi0; // na + nb == cnt <= kTile
+    for (std::uint32_t t = threadIdx.x; t < na; t += kTileThreads)
+    {
+        s[t] = src[a0 + ai0 + t];
+    }
+    for (std::uint32_t t = threadIdx.x; t < nb; t += kTileThreads)
+    {
+        s[na + t] = src[b0 + bi0 + t];
+    }
+    __syncthreads();
+    // each thread merges kItems consecutive outputs
+    const std::uint32_t dg = min(threadIdx.x * static_cast<std::uint32_t>(kItems), cnt);
+    std::uint32_t ia = merge_path([&](std::uint32_t i) { return s[i]; }, na,
+                                  [&](std::uint32_t i) { return s[na + i]; }, nb, dg);
+    std::uint32_t ib = dg - ia;
+    uint4 out[kItems];
+#pragma unroll
+    for (int k = 0; k < kItems; ++k)
+    {
+        const bool has_a = ia < na, has_b = ib < nb;
+        uint4 va = make_uint4(0, 0, 0, 0), vb = va;
+        if (has_a)
+        {
+            va = s[ia];
+        }
+        if (has_b)
+        {
+            vb = s[na + ib];
+        }
+        const bool take_a = has_a && (!has_b || elem_less(va, vb));
+        out[k] = take_a ? va : vb;
+        ia += take_a ? 1u : 0u;
+        ib += take_a ? 0u : 1u;
+    }
+#pragma unroll
+    for (int k = 0; k < kItems; ++k)
+    {
+        if (dg + k < cnt)
+        {
+            dst[out0 + dg + k] = out[k];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// hull chains
+// ------------------------------------------------------------------------------------------
+struct P2
+{
+    double x, y;
+};
+
+__device__ __forceinline__ P2 elem_pt(const uint4& e)
+{
+    P2 p;
+    p.x = static_cast<double>(__uint_as_float(e.y));
+    p.y = static_cast<double>(__uint_as_float(e.z));
+    return p;
 }
 
 // polygonizer.cpp:45-48: true when p3 is not strictly left of p1 -> p2 (pop p2)
-__device__ __forceinline__ bool not_left(unsigned long long k1, unsigned long long k2, unsigned long long k3)
+__device__ __forceinline__ bool not_left(const P2& p1, const P2& p2, const P2& p3)
 {
-    const double x1 = static_cast<double>(unord_f32(static_cast<std::uint32_t>(k1 >> 32)));
-    const double y1 = static_cast<double>(unord_f32(static_cast<std::uint32_t>(k1)));
-    const double x2 = static_cast<double>(unord_f32(static_cast<std::uint32_t>(k2 >> 32)));
-    const double y2 = static_cast<double>(unord_f32(static_cast<std::uint32_t>(k2)));
-    const double x3 = static_cast<double>(unord_f32(static_cast<std::uint32_t>(k3 >> 32)));
-    const double y3 = static_cast<double>(unord_f32(static_cast<std::uint32_t>(k3)));
-    return (x2 - x1) * (y3 - y1) - (y2 - y1) * (x3 - x1) <= 0.0;
+    return (p2.x - p1.x) * (p3.y - p1.y) - (p2.y - p1.y) * (p3.x - p1.x) <= 0.0;
 }
 
-// sequential monotone chain over sorted keys; st needs n + 1 entries; returns the vertex count
-__device__ std::uint32_t monotone_chain(const unsigned long long* keys, std::uint32_t n, std::uint32_t* st)
+// Warp-wide thinning pass: lane l sweeps its contiguous chunk of src[0..m) with the lower chain
+// (left to right) and the upper chain (right to left, as the reference walks it); the union of
+// both survivor lists, in sorted order, is compacted into dst. stL / stU: global spill space for
+// the per-lane stacks (m entries each); smL / smU: 32 * kLaneStack shared-memory words each.
+// Returns the survivor count.
+__device__ std::uint32_t hull_filter(const uint4* __restrict__ src, std::uint32_t m, uint4* __restrict__ dst,
+                                     std::uint32_t* __restrict__ stL, std::uint32_t* __restrict__ stU,
+                                     std::uint32_t* smL, std::uint32_t* smU)
+{
+    const std::uint32_t lane = lane_id();
+    const std::uint32_t lanes = min(32u, (m + 7u) / 8u);
+    const std::uint32_t chunk = (m + lanes - 1u) / lanes;
+    const std::uint32_t a = min(m, lane * chunk), b = min(m, a + chunk);
+    const LaneStack L{smL + lane * kLaneStack, stL + a};
+    const LaneStack U{smU + lane * kLaneStack, stU + a};
+    std::uint32_t kl = 0, ku = 0;
+    if (b > a)
+    {
+        P2 s2 = {0.0, 0.0}, s1 = {0.0, 0.0};
+        uint4 nx = ldg4(src + a);
+        for (std::uint32_t i = a; i < b; ++i)
+        {
+            const P2 p = elem_pt(nx);
+            if (i + 1 < b)
+            {
+                nx = ldg4(src + i + 1); // in flight during the pops below
+            }
+            while (kl >= 2 && not_left(s2, s1, p))
+            {
+                --kl;
+                s1 = s2;
+                if (kl >= 2)
+                {
+                    s2 = elem_pt(ldg4(src + L.get(kl - 2)));
+                }
+            }
+            L.set(kl, i);
+            ++kl;
+            s2 = s1;
+            s1 = p;
+        }
+        nx = ldg4(src + b - 1);
+        for (std::uint32_t i = b; i-- > a;)
+        {
+            const P2 p = elem_pt(nx);
+            if (i > a)
+            {
+                nx = ldg4(src + i - 1);
+            }
+            while (ku >= 2 && not_left(s2, s1, p))
+            {
+                --ku;
+                s1 = s2;
+                if (ku >= 2)
+                {
+                    s2 = elem_pt(ldg4(src + U.get(ku - 2)));
+                }
+            }
+            U.set(ku, i);
+            ++ku;
+            s2 = s1;
+            s1 = p;
+        }
+    }
+    // union of the ascending lower list and the descending upper list
+    std::uint32_t cnt = 0;
+    {
+        std::uint32_t i = 0, j = ku;
+        while (i < kl || j > 0)
+        {
+            const std::uint32_t pl = i < kl ? L.get(i) : 0xffffffffu;
+            const std::uint32_t pu = j > 0 ? U.get(j - 1) : 0xffffffffu;
+            i += (pl <= pu) ? 1u : 0u;
+            j -= (pu <= pl) ? 1u : 0u;
+            ++cnt;
+        }
+    }
+    const std::uint32_t incl = warp_incl_scan(cnt);
+    const std::uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    {
+        std::uint32_t w = incl - cnt;
+        std::uint32_t i = 0, j = ku;
+        while (i < kl || j > 0)
+        {
+            const std::uint32_t pl = i < kl ? L.get(i) : 0xffffffffu;
+            const std::uint32_t pu = j > 0 ? U.get(j - 1) : 0xffffffffu;
+            i += (pl <= pu) ? 1u : 0u;
+            j -= (pu <= pl) ? 1u : 0u;
+            dst[w++] = ldg4(src + min(pl, pu));
+        }
+    }
+    __syncwarp();
+    return total;
+}
+
+// the reference's sweep (polygonizer.cpp:67-90) over m >= 1 sorted points; st needs m + 1 entries.
+// The two topmost stack points stay in registers; only a pop reads the stack and a point again.
+template <class Get, class Stack>
+__device__ __forceinline__ std::uint32_t monotone_chain(Get P, std::uint32_t m, Stack* st)
 {
     std::int32_t k = 0;
-    for (std::int32_t i = 0; i < static_cast<std::int32_t>(n); ++i)
+    P2 s2 = {0.0, 0.0}, s1 = {0.0, 0.0};
+    for (std::int32_t i = 0; i < static_cast<std::int32_t>(m); ++i)
     {
-        const unsigned long long ki = keys[i];
-        while (k > 1 && not_left(keys[st[k - 2]], keys[st[k - 1]], ki))
+        const P2 pi = P(i);
+        while (k > 1 && not_left(s2, s1, pi))
         {
             --k;
+            s1 = s2;
+            if (k > 1)
+            {
+                s2 = P(st[k - 2]);
+            }
         }
-        st[k++] = static_cast<std::uint32_t>(i);
+        st[k++] = static_cast<Stack>(i);
+        s2 = s1;
+        s1 = pi;
     }
-    for (std::int32_t i = static_cast<std::int32_t>(n) - 2, t = k + 1; i >= 0; --i)
+    for (std::int32_t i = static_cast<std::int32_t>(m) - 2, t = k + 1; i >= 0; --i)
     {
-        const unsigned long long ki = keys[i];
-        while (k >= t && not_left(keys[st[k - 2]], keys[st[k - 1]], ki))
+        const P2 pi = P(i);
+        while (k >= t && not_left(s2, s1, pi))
         {
             --k;
+            s1 = s2;
+            if (k > 1)
+            {
+                s2 = P(st[k - 2]);
+            }
         }
-        st[k++] = static_cast<std::uint32_t>(i);
+        st[k++] = static_cast<Stack>(i);
+        s2 = s1;
+        s1 = pi;
     }
     return static_cast<std::uint32_t>(k - 1);
 }
 
-__global__ void __launch_bounds__(kHullThreads) k_hull(Dev d)
+__global__ void __launch_bounds__(kHullThreads) k_hull_chain(Dev d)
 {
-    __shared__ unsigned long long s_keys[kHullSmem];
-    __shared__ std::uint32_t s_vals[kHullSmem];
-    __shared__ std::uint32_t s_stack[kHullSmem + 1];
-    __shared__ float s_red[2][kHullThreads / 32];
-    __shared__ std::uint32_t s_cnt;
+    __shared__ float2 s_key[kHullWarps][kChainSmem];
+    __shared__ std::uint16_t s_st[kHullWarps][kChainSmem + 2];
+    __shared__ std::uint32_t s_lane[kHullWarps][2][32 * kLaneStack];
     const std::uint32_t f = blockIdx.y;
     const std::uint32_t K = d.n_clusters[f];
+    const std::uint32_t warp = threadIdx.x >> 5, lane = lane_id();
     const std::size_t o = static_cast<std::size_t>(f) * d.cap;
     const std::uint32_t* cstart = d.cstart + static_cast<std::size_t>(f) * (d.cap + 1);
-    for (std::uint32_t c = blockIdx.x; c < K; c += gridDim.x)
+    const bool in_b = (sort_passes(d.n_o[f]) & 1u) != 0u;
+    uint4* sorted = (in_b ? d.hsB : d.hsA) + o;
+    uint4* other = (in_b ? d.hsA : d.hsB) + o;
+    for (std::uint32_t c = blockIdx.x * kHullWarps + warp; c < K; c += gridDim.x * kHullWarps)
     {
         const std::uint32_t seg = cstart[c];
         const std::uint32_t n = cstart[c + 1] - seg;
-        unsigned long long* gk = d.hsk + o + seg;
-        std::uint32_t* gv = d.hsi + o + seg;
         std::uint32_t* gst = d.hstack + static_cast<std::size_t>(f) * 2 * d.cap + seg + c; // n + 1 entries
-        // z extent of the cluster
-        float zmn = 3.402823466e+38f, zmx = -3.402823466e+38f;
-        for (std::uint32_t t = threadIdx.x; t < n; t += blockDim.x)
+        if (lane == 0)
         {
-            const float z = d.pts_o[o + gv[t]].z;
-            zmn = fminf(zmn, z);
-            zmx = fmaxf(zmx, z);
-        }
-#pragma unroll
-        for (int s = 16; s > 0; s >>= 1)
-        {
-            zmn = fminf(zmn, __shfl_xor_sync(0xffffffffu, zmn, s));
-            zmx = fmaxf(zmx, __shfl_xor_sync(0xffffffffu, zmx, s));
-        }
-        if (lane_id() == 0)
-        {
-            s_red[0][threadIdx.x >> 5] = zmn;
-            s_red[1][threadIdx.x >> 5] = zmx;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0)
-        {
-            for (int w = 1; w < kHullThreads / 32; ++w)
-            {
-                zmn = fminf(zmn, s_red[0][w]);
-                zmx = fmaxf(zmx, s_red[1][w]);
-            }
-            d.zminmax[o + c] = make_float2(zmn, zmx);
+            // z extent of the cluster (processor.cpp:648-655), reduced while labelling (cluster.cu)
+            d.zminmax[o + c] = make_float2(unord_f32(d.zmin_u[o + c]), unord_f32(d.zmax_u[o + c]));
         }
         if (n < 3)
         {
             // identity order = obstacle-cloud order (polygonizer.cpp:36-41)
-            if (threadIdx.x == 0)
+            if (lane == 0)
             {
-                std::uint32_t a = (n > 0) ? gv[0] : 0u, b = (n > 1) ? gv[1] : 0u;
+                std::uint32_t a = (n > 0) ? sorted[seg].w : 0u, b = (n > 1) ? sorted[seg + 1].w : 0u;
                 if (n == 2 && b < a)
                 {
                     const std::uint32_t t = a;
@@ -207,66 +451,102 @@ __global__ void __launch_bounds__(kHullThreads) k_hull(Dev d)
                 }
                 d.hcnt[o + c] = n;
             }
-            __syncthreads();
             continue;
         }
-        if (n <= kHullSmem)
+        // thinning passes ping-pong between the two sort buffers (the segment is private to this warp)
+        uint4* cur = sorted + seg;
+        uint4* nxt = other + seg;
+        std::uint32_t m = n;
+        while (m > kFilterAbove)
         {
-            for (std::uint32_t t = threadIdx.x; t < n; t += blockDim.x)
+            const std::uint32_t m2 = hull_filter(cur, m, nxt, d.hstL + o + seg, d.hstU + o + seg, s_lane[warp][0], s_lane[warp][1]);
+            uint4* t = cur;
+            cur = nxt;
+            nxt = t;
+            const bool stalled = m2 * 4u > m * 3u; // convex-position input: thinning does not pay
+            m = m2;
+            if (stalled)
             {
-                s_keys[t] = gk[t];
-                s_vals[t] = gv[t];
+                break;
             }
-            __syncthreads();
-            block_sort_pairs(s_keys, s_vals, n);
-            if (threadIdx.x == 0)
+        }
+        std::uint32_t hc = 0;
+        if (m <= kChainSmem)
+        {
+            for (std::uint32_t t = lane; t < m; t += 32)
             {
-                s_cnt = monotone_chain(s_keys, n, s_stack);
+                const uint4 e = cur[t];
+                s_key[warp][t] = make_float2(__uint_as_float(e.y), __uint_as_float(e.z));
             }
-            __syncthreads();
-            const std::uint32_t hc = s_cnt;
-            for (std::uint32_t t = threadIdx.x; t < hc; t += blockDim.x)
+            __syncwarp();
+            if (lane == 0)
             {
-                gst[t] = s_vals[s_stack[t]];
+                const float2* key = s_key[warp];
+                hc = monotone_chain(
+                    [&](std::uint32_t i) {
+                        const float2 v = key[i];
+                        P2 p;
+                        p.x = static_cast<double>(v.x);
+                        p.y = static_cast<double>(v.y);
+                        return p;
+                    },
+                    m, s_st[warp]);
             }
-            if (threadIdx.x == 0)
+            hc = __shfl_sync(0xffffffffu, hc, 0);
+            __syncwarp();
+            for (std::uint32_t t = lane; t < hc; t += 32)
             {
-                d.hcnt[o + c] = hc;
+                gst[t] = cur[s_st[warp][t]].w;
             }
+            __syncwarp();
         }
         else
         {
-            __syncthreads();
-            block_sort_pairs(gk, gv, n);
-            if (threadIdx.x == 0)
+            // rare: more than kChainSmem points in (near) convex position; sweep in global memory
+            std::uint32_t* st = (m == n) ? gst : (d.hstL + o + seg); // m + 1 entries
+            if (lane == 0)
             {
-                const std::uint32_t hc = monotone_chain(gk, n, gst);
-                s_cnt = hc;
-                d.hcnt[o + c] = hc;
+                hc = monotone_chain([&](std::uint32_t i) { return elem_pt(cur[i]); }, m, st);
             }
-            __syncthreads();
-            const std::uint32_t hc = s_cnt;
-            for (std::uint32_t t = threadIdx.x; t < hc; t += blockDim.x)
+            hc = __shfl_sync(0xffffffffu, hc, 0);
+            __syncwarp();
+            // positions -> obstacle-cloud indices (in place when st == gst)
+            for (std::uint32_t t0 = 0; t0 < hc; t0 += 32)
             {
-                gst[t] = gv[gst[t]]; // sorted position -> obstacle-cloud index
+                const std::uint32_t t = t0 + lane;
+                std::uint32_t v = 0;
+                if (t < hc)
+                {
+                    v = cur[st[t]].w;
+                }
+                __syncwarp();
+                if (t < hc)
+                {
+                    gst[t] = v;
+                }
             }
+            __syncwarp();
         }
-        __syncthreads();
+        if (lane == 0)
+        {
+            d.hcnt[o + c] = hc;
+        }
     }
 }
 
-__global__ void __launch_bounds__(kHullThreads) k_hull_gather(Dev d)
+__global__ void __launch_bounds__(128) k_hull_gather(Dev d)
 {
     const std::uint32_t f = blockIdx.y;
     const std::uint32_t K = d.n_clusters[f];
     const std::size_t o = static_cast<std::size_t>(f) * d.cap;
     const std::uint32_t* cstart = d.cstart + static_cast<std::size_t>(f) * (d.cap + 1);
     const std::uint32_t* hoff = d.hull_off + static_cast<std::size_t>(f) * (d.cap + 1);
-    for (std::uint32_t c = blockIdx.x; c < K; c += gridDim.x)
+    const std::uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    for (std::uint32_t c = blockIdx.x * 4u + warp; c < K; c += gridDim.x * 4u)
     {
         const std::uint32_t* gst = d.hstack + static_cast<std::size_t>(f) * 2 * d.cap + cstart[c] + c;
         const std::uint32_t off = hoff[c], hc = hoff[c + 1] - off;
-        for (std::uint32_t t = threadIdx.x; t < hc; t += blockDim.x)
+        for (std::uint32_t t = lane; t < hc; t += 32)
         {
             const std::uint32_t idx = gst[t];
             const float4 p = d.pts_o[o + idx];
@@ -282,13 +562,24 @@ void launch_hulls(Ctx* c, std::uint32_t nf)
     cudaStream_t s = c->stream;
     k_excl_scan<<<nf, 1024, 0, s>>>(d.ccount, d.cap, d.cstart, d.cap + 1, d.cap, d.n_clusters, nullptr);
     mark(c, "hull_seg_scan");
-    k_hull_scatter<<<dim3((d.cap + 255) / 256, nf), 256, 0, s>>>(d);
-    mark(c, "hull_scatter");
-    k_hull<<<dim3(kHullBlocks, nf), kHullThreads, 0, s>>>(d);
-    mark(c, "hull");
+    k_hull_tilesort<<<dim3(d.tiles, nf), kTileThreads, 0, s>>>(d);
+    mark(c, "hull_tilesort");
+    std::uint32_t passes = 0;
+    while ((1u << passes) < d.tiles)
+    {
+        ++passes;
+    }
+    for (std::uint32_t p = 0; p < passes; ++p)
+    {
+        // frames whose obstacle cloud is already one sorted run leave at once
+        k_hull_merge<<<dim3(d.tiles, nf), kTileThreads, 0, s>>>(d, p);
+        mark(c, "hull_merge");
+    }
+    k_hull_chain<<<dim3(kHullCtasPerFrame, nf), kHullThreads, 0, s>>>(d);
+    mark(c, "hull_chain");
     k_excl_scan<<<nf, 1024, 0, s>>>(d.hcnt, d.cap, d.hull_off, d.cap + 1, d.cap, d.n_clusters, d.n_hull);
     mark(c, "hull_off_scan");
-    k_hull_gather<<<dim3(kHullBlocks, nf), kHullThreads, 0, s>>>(d);
+    k_hull_gather<<<dim3(kHullCtasPerFrame, nf), 128, 0, s>>>(d);
     mark(c, "hull_gather");
 }
 } // namespace lpl

@@ -240,43 +240,43 @@ __global__ void __launch_bounds__(256) k_dror_grid_scatter(Dev d)
 }
 
 // Pass B: exhaustive count for the unresolved points over every grid cell the search disc can
-// touch. Cells of one grid row are contiguous in grid_pts, so each row is one range.
-__global__ void __launch_bounds__(128) k_dror_query(Dev d, DrorParams prm)
+// touch. Cells of one grid row are contiguous in grid_pts, so each row is one range that the 32
+// lanes of a warp scan together (coalesced float4 loads, ballot count, early exit at
+// min_neighbours).
+constexpr int kDrorQueryWarps = 8;
+constexpr int kDrorQueryCtas = 96; // per frame; warps stride over the unresolved list
+
+__global__ void __launch_bounds__(kDrorQueryWarps * 32) k_dror_query(Dev d, DrorParams prm)
 {
     const std::uint32_t f = blockIdx.y;
     const std::uint32_t nu = d.n_unres[f];
-    const std::uint32_t u = blockIdx.x * 128u + threadIdx.x;
-    if (u >= nu)
-    {
-        return;
-    }
-    const std::uint32_t i = d.unres[static_cast<std::size_t>(f) * d.cap + u];
-    const float4 p = d.pts_in[static_cast<std::size_t>(f) * d.cap + i];
-    const float r_sqr = dror_radius_sqr(p.x, p.y, prm);
-    const float rc = sqrtf(r_sqr) * 1.001f + 1e-4f; // conservative cover of the float predicate
-    const int x0 = dror_cell_coord(p.x - rc), x1 = dror_cell_coord(p.x + rc);
-    const int y0 = dror_cell_coord(p.y - rc), y1 = dror_cell_coord(p.y + rc);
+    const std::uint32_t lane = lane_id();
     const std::uint32_t* start = d.grid_start + static_cast<std::size_t>(f) * (kDrorCells + 1);
     const float4* gp = d.grid_pts + static_cast<std::size_t>(f) * d.cap;
-    std::uint32_t cnt = 0;
-    for (int cy = y0; cy <= y1 && cnt < prm.min_neighbours; ++cy)
+    for (std::uint32_t u = blockIdx.x * kDrorQueryWarps + (threadIdx.x >> 5); u < nu; u += gridDim.x * kDrorQueryWarps)
     {
-        const std::uint32_t a = start[cy * kDrorGrid + x0];
-        const std::uint32_t b = start[cy * kDrorGrid + x1 + 1];
-        for (std::uint32_t k = a; k < b; ++k)
+        const std::uint32_t i = d.unres[static_cast<std::size_t>(f) * d.cap + u];
+        const float4 p = d.pts_in[static_cast<std::size_t>(f) * d.cap + i];
+        const float r_sqr = dror_radius_sqr(p.x, p.y, prm);
+        const float rc = sqrtf(r_sqr) * 1.001f + 1e-4f; // conservative cover of the float predicate
+        const int x0 = dror_cell_coord(p.x - rc), x1 = dror_cell_coord(p.x + rc);
+        const int y0 = dror_cell_coord(p.y - rc), y1 = dror_cell_coord(p.y + rc);
+        std::uint32_t cnt = 0;
+        for (int cy = y0; cy <= y1 && cnt < prm.min_neighbours; ++cy)
         {
-            if (dror_within(p, gp[k], r_sqr))
+            const std::uint32_t a = start[cy * kDrorGrid + x0];
+            const std::uint32_t b = start[cy * kDrorGrid + x1 + 1];
+            for (std::uint32_t k0 = a; k0 < b && cnt < prm.min_neighbours; k0 += 32)
             {
-                if (++cnt >= prm.min_neighbours)
-                {
-                    break;
-                }
+                const std::uint32_t k = k0 + lane;
+                const bool hit = k < b && dror_within(p, gp[k], r_sqr);
+                cnt += __popc(__ballot_sync(0xffffffffu, hit));
             }
         }
-    }
-    if (cnt < prm.min_neighbours)
-    {
-        d.noise[static_cast<std::size_t>(f) * d.cap + i] = 1;
+        if (lane == 0 && cnt < prm.min_neighbours)
+        {
+            d.noise[static_cast<std::size_t>(f) * d.cap + i] = 1;
+        }
     }
 }
 
@@ -332,8 +332,7 @@ void launch_dror(Ctx* c, std::uint32_t nf)
     mark(c, "dror_grid_scan");
     k_dror_grid_scatter<<<grid, 256, 0, c->stream>>>(d);
     mark(c, "dror_grid_scatter");
-    const dim3 qgrid((d.cap + 127) / 128, nf);
-    k_dror_query<<<qgrid, 128, 0, c->stream>>>(d, c->dror);
+    k_dror_query<<<dim3(kDrorQueryCtas, nf), kDrorQueryWarps * 32, 0, c->stream>>>(d, c->dror);
     mark(c, "dror_query");
 }
 

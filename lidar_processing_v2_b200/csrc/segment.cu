@@ -7,7 +7,7 @@
 //   image scatter      :291-318   -> k_seg_image (64-bit atomicMin keys), k_seg_px
 //   JCP                :481-638   -> k_seg_dilate (5x5 stencil on shared-memory tiles),
 //                                    queue compaction, k_jcp_pre, k_jcp_resolve
-//   populateLabels     :640-669   -> epilogue of k_jcp_resolve
+//   populateLabels     :640-669   -> k_seg_labels_out
 //
 // Ordered semantics on an unordered machine: the reference iterates polar cells in index order
 // and the points of a cell in cloud order. `order` holds exactly that sequence (cells are
@@ -18,8 +18,9 @@
 // JCP is a Gauss-Seidel sweep in raster order. A queued pixel only depends on queued pixels
 // that precede it in raster order and lie within the kernel distance, so the sweep is replayed
 // as a data-flow relaxation: weights and mask sources are computed for all queued pixels in
-// parallel (k_jcp_pre), then one CTA per frame fires every pixel whose predecessors are
-// resolved, round after round, on a 2-bit state plane in shared memory (k_jcp_resolve).
+// parallel (k_jcp_pre); then one CTA per frame walks the queue as *runs* of horizontally adjacent
+// queued pixels, one thread per run, left to right, waiting on a 2-bit state plane in shared
+// memory only for the earlier queued pixels of the rows above (k_jcp_resolve).
 // The reference leaves out-of-image kernel slots untouched, so border pixels inherit those
 // slots from the previously popped pixel (hazard H2); k_jcp_pre reproduces that by
 // locating the most recent earlier queued pixel for which the slot was inside the image.
@@ -153,16 +154,34 @@ __device__ __forceinline__ void warp_sort(T* buf, std::uint32_t n)
     }
 }
 
-__global__ void __launch_bounds__(128) k_seg_cell(Dev d, SegParams sp)
+constexpr int kCellWarps = 4;     // warps per CTA
+constexpr int kCellsPerWarp = 8;  // cells per warp, interleaved across the CTA's warps (most cells are empty)
+
+__device__ __forceinline__ void seg_cell_one(const Dev& d, const SegParams& sp, std::uint32_t f, std::uint32_t cell,
+                                             std::uint32_t* buf);
+
+__global__ void __launch_bounds__(kCellWarps * 32) k_seg_cell(Dev d, SegParams sp)
 {
-    __shared__ std::uint32_t sh[4][kCellSmem];
+    __shared__ std::uint32_t sh[kCellWarps][kCellSmem];
     const std::uint32_t f = blockIdx.y;
     const std::uint32_t warp = threadIdx.x >> 5;
-    const std::uint32_t cell = blockIdx.x * 4u + warp;
-    if (cell >= static_cast<std::uint32_t>(sp.ncell))
+    // consecutive cells are radial neighbours of one slice (dense near the sensor, empty far out):
+    // interleaving them over the warps keeps the warps of a CTA equally loaded
+    const std::uint32_t first = blockIdx.x * (kCellWarps * kCellsPerWarp) + warp;
+    for (std::uint32_t j = 0; j < kCellsPerWarp; ++j)
     {
-        return;
+        const std::uint32_t cell = first + j * kCellWarps;
+        if (cell < static_cast<std::uint32_t>(sp.ncell))
+        {
+            seg_cell_one(d, sp, f, cell, sh[warp]);
+        }
+        __syncwarp();
     }
+}
+
+__device__ __forceinline__ void seg_cell_one(const Dev& d, const SegParams& sp, std::uint32_t f, std::uint32_t cell,
+                                             std::uint32_t* buf)
+{
     const std::uint32_t* cs = d.cell_start + static_cast<std::size_t>(f) * (sp.ncell + 1);
     const std::uint32_t a = cs[cell], n = cs[cell + 1] - a;
     if (n == 0)
@@ -176,7 +195,6 @@ __global__ void __launch_bounds__(128) k_seg_cell(Dev d, SegParams sp)
     std::uint32_t best = 0; // largest i in [1, n/2] with z[i] - z[i-1] > 0.5, 0 = none
     if (n <= kCellSmem)
     {
-        std::uint32_t* buf = sh[warp];
         for (std::uint32_t t = lane_id(); t < n; t += 32)
         {
             buf[t] = ord[t];
@@ -711,13 +729,16 @@ __device__ __forceinline__ void jcp_slot(const Dev& d, const SegParams& sp, std:
 
 __global__ void __launch_bounds__(128) k_jcp_pre(Dev d, SegParams sp)
 {
+    __shared__ float s_w[128][25]; // raw weights of the CTA's 128 queued pixels (+1 pad: no bank conflicts)
+    __shared__ float s_inv[128];   // the divisor (sum) or 0 when the pixel cannot be decided
     const std::uint32_t f = blockIdx.y;
     const std::uint32_t nq = min(d.n_queue[f], d.qcap);
-    const std::uint32_t k = blockIdx.x * 128u + threadIdx.x;
-    if (k >= nq)
+    if (blockIdx.x * 128u >= nq)
     {
         return;
     }
+    const std::uint32_t k = min(blockIdx.x * 128u + threadIdx.x, nq - 1u); // tail threads redo the last pixel
+    const bool live = blockIdx.x * 128u + threadIdx.x < nq;
     const std::size_t po = static_cast<std::size_t>(f) * sp.npx;
     const std::uint32_t* queue = d.queue + static_cast<std::size_t>(f) * d.qcap;
     const std::uint32_t p = queue[k];
@@ -754,7 +775,7 @@ __global__ void __launch_bounds__(128) k_jcp_pre(Dev d, SegParams sp)
                     jcp_slot(d, sp, po, d.pxpt[po + pp], hh2, ww2, i, wgt, msk);
                     if (msk == 3)
                     {
-                        if (brow == 0)
+                        if (brow == 0 && live)
                         {
                             const std::uint32_t r = atomicAdd(&d.n_border[f], 1u);
                             if (r < d.nborder_cap)
@@ -784,34 +805,95 @@ __global__ void __launch_bounds__(128) k_jcp_pre(Dev d, SegParams sp)
                 }
             }
         }
-        wn[static_cast<std::size_t>(i) * d.qcap + k] = wgt; // raw weight, normalised below
+        s_w[threadIdx.x][i] = wgt; // raw weight, normalised below
         mk |= static_cast<unsigned long long>(msk) << (2 * i);
     }
     const bool decidable = fabsf(sum) > FLT_EPSILON;
-#pragma unroll 4
-    for (int i = 0; i < 24; ++i)
-    {
-        float* slot = wn + static_cast<std::size_t>(i) * d.qcap + k;
-        *slot = decidable ? (*slot / sum) : 0.f; // weight_matrix = unnormalized / sum (segmenter.cpp:611)
-    }
+    s_inv[threadIdx.x] = decidable ? sum : 0.f;
     mk |= static_cast<unsigned long long>(decidable ? 1 : 0) << 48;
     mk |= static_cast<unsigned long long>(brow) << 49;
-    d.mk[static_cast<std::size_t>(f) * d.qcap + k] = mk;
+    if (live)
+    {
+        d.mk[static_cast<std::size_t>(f) * d.qcap + k] = mk;
+    }
+    __syncthreads();
+    // weight_matrix = unnormalized / sum (segmenter.cpp:611); the CTA's rows are one contiguous
+    // block of the entry-major array -> coalesced stores
+    const std::uint32_t rows = min(128u, nq - blockIdx.x * 128u);
+    float* out = wn + static_cast<std::size_t>(blockIdx.x) * 128u * 24u;
+    for (std::uint32_t t = threadIdx.x; t < rows * 24u; t += 128u)
+    {
+        const std::uint32_t e = t / 24u, i = t % 24u;
+        const float dv = s_inv[e];
+        out[t] = dv != 0.f ? s_w[e][i] / dv : 0.f;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
 // JCP relaxation: one CTA per frame, 2-bit state plane in shared memory
 // (0 unknown / empty / undecided, 1 ground, 2 obstacle, 3 queued and not yet relaxed).
+//
+// The raster-order sweep of the reference only couples a queued pixel to *earlier* queued pixels
+// of its 5x5 neighbourhood. Queued pixels that touch horizontally form runs; one thread walks a
+// run left to right (the in-row predecessors are its own results) and spin-waits on the state
+// plane for the queued pixels of the two rows above, so a row follows the row above it with a lag
+// of two pixels instead of a barrier per pixel. Runs are handed out in raster order
+// (thread t takes runs t, t + T, ...): the raster-first unfinished run never waits on anything
+// unfinished and its owner is working on it, so the sweep cannot deadlock.
+// Weights are entry-major (96 B per pixel) and loaded one pixel ahead of the vote.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ std::uint32_t plane_get(const volatile std::uint32_t* plane, std::uint32_t p)
 {
     return (plane[p >> 4] >> ((p & 15u) * 2u)) & 3u;
 }
 
-__global__ void __launch_bounds__(1024) k_jcp_resolve(Dev d, SegParams sp, int want_image)
+constexpr int kJcpThreads = 256;
+constexpr std::uint32_t kJcpSpinLimit = 1u << 24;
+
+struct RunHeadPred
+{
+    const std::uint32_t* queue;
+    std::uint32_t qcap, W;
+    __device__ bool operator()(std::uint32_t f, std::uint32_t k) const
+    {
+        const std::uint32_t* q = queue + static_cast<std::size_t>(f) * qcap;
+        const std::uint32_t p = q[k];
+        return k == 0 || (p % W) == 0 || q[k - 1] + 1u != p;
+    }
+};
+
+struct RunHeadEmit
+{
+    std::uint32_t* runs;
+    std::uint32_t qcap;
+    __device__ void operator()(std::uint32_t f, std::uint32_t k, std::uint32_t pos) const
+    {
+        runs[static_cast<std::size_t>(f) * qcap + pos] = k;
+    }
+};
+
+struct JcpEntry
+{
+    unsigned long long m;
+    float4 w[6];
+};
+
+__device__ __forceinline__ JcpEntry jcp_load(const unsigned long long* mkv, const float* wn, std::uint32_t k)
+{
+    JcpEntry e;
+    e.m = mkv[k];
+    const float4* row = reinterpret_cast<const float4*>(wn + static_cast<std::size_t>(k) * 24);
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+    {
+        e.w[i] = row[i];
+    }
+    return e;
+}
+
+__global__ void __launch_bounds__(kJcpThreads) k_jcp_resolve(Dev d, SegParams sp)
 {
     extern __shared__ std::uint32_t plane[]; // npx / 16 words
-    __shared__ std::uint32_t s_next;
     const std::uint32_t f = blockIdx.x;
     const std::size_t po = static_cast<std::size_t>(f) * sp.npx;
     std::uint8_t* code = d.code + po;
@@ -831,60 +913,38 @@ __global__ void __launch_bounds__(1024) k_jcp_resolve(Dev d, SegParams sp, int w
         plane[wi] = v;
     }
     const std::uint32_t nq = min(d.n_queue[f], d.qcap);
+    const std::uint32_t nruns = min(d.n_runs[f], d.qcap);
     const std::uint32_t* queue = d.queue + static_cast<std::size_t>(f) * d.qcap;
+    const std::uint32_t* runs = d.runs + static_cast<std::size_t>(f) * d.qcap;
     const unsigned long long* mkv = d.mk + static_cast<std::size_t>(f) * d.qcap;
     const float* wn = d.wn + static_cast<std::size_t>(f) * 24 * d.qcap;
-    std::uint32_t* pend0 = d.pend + static_cast<std::size_t>(f) * 2 * d.qcap;
-    std::uint32_t* pend1 = pend0 + d.qcap;
     const std::uint32_t* sref = d.stale_ref + static_cast<std::size_t>(f) * d.nborder_cap * 12;
-    std::uint32_t np = nq, rounds = 0;
-    bool first = true;
+    const std::uint32_t W = static_cast<std::uint32_t>(sp.W);
+    std::uint32_t spins = 0;
     __syncthreads();
-    while (np != 0)
+    // raster-adjacent runs wait on each other: spread them over different warps (lane l of warp w
+    // takes runs w + 8 * l, + 256, ...), each thread still walking its runs in raster order
+    const std::uint32_t first_run = (threadIdx.x >> 5) + (kJcpThreads / 32) * (threadIdx.x & 31u);
+    for (std::uint32_t r = first_run; r < nruns; r += kJcpThreads)
     {
-        if (threadIdx.x == 0)
+        std::uint32_t k = runs[r];
+        const std::uint32_t kend = (r + 1 < nruns) ? runs[r + 1] : nq; // first entry of the next run
+        std::uint32_t p = queue[k];
+        const int h = static_cast<int>(p / W);
+        int wv = static_cast<int>(p % W);
+        JcpEntry cur = jcp_load(mkv, wn, k);
+        for (; k < kend; ++k, ++p, ++wv)
         {
-            s_next = 0;
-        }
-        __syncthreads();
-        for (std::uint32_t j = threadIdx.x; j < np; j += blockDim.x)
-        {
-            const std::uint32_t k = first ? j : pend0[j];
-            const unsigned long long m = mkv[k];
-            const std::uint32_t p = queue[k];
-            const int h = static_cast<int>(p / sp.W), w = static_cast<int>(p % sp.W);
-            const std::uint32_t brow = static_cast<std::uint32_t>(m >> 49);
-            bool ready = true;
-            std::uint32_t dyn_state = 0; // 2 bits per slot 0..11 once resolved
-#pragma unroll
-            for (int i = 0; i < 12; ++i)
+            JcpEntry nxt = cur;
+            if (k + 1 < kend)
             {
-                if (((m >> (2 * i)) & 3ULL) == 3ULL)
-                {
-                    const int hh = h + c_off_h[i], ww = w + c_off_w[i];
-                    std::uint32_t ref;
-                    if (hh >= 0 && hh < sp.H && ww >= 0 && ww < sp.W)
-                    {
-                        ref = static_cast<std::uint32_t>(hh * sp.W + ww);
-                    }
-                    else
-                    {
-                        ref = sref[static_cast<std::size_t>(brow - 1) * 12 + i];
-                    }
-                    const std::uint32_t s = plane_get(plane, ref);
-                    if (s == 3u)
-                    {
-                        ready = false;
-                    }
-                    dyn_state |= s << (2 * i);
-                }
+                nxt = jcp_load(mkv, wn, k + 1); // in flight while this pixel waits and votes
             }
-            if (!ready)
-            {
-                const std::uint32_t pos = atomicAdd(&s_next, 1u);
-                pend1[pos] = k;
-                continue;
-            }
+            const unsigned long long m = cur.m;
+            const float wts[24] = {cur.w[0].x, cur.w[0].y, cur.w[0].z, cur.w[0].w, cur.w[1].x, cur.w[1].y,
+                                   cur.w[1].z, cur.w[1].w, cur.w[2].x, cur.w[2].y, cur.w[2].z, cur.w[2].w,
+                                   cur.w[3].x, cur.w[3].y, cur.w[3].z, cur.w[3].w, cur.w[4].x, cur.w[4].y,
+                                   cur.w[4].z, cur.w[4].w, cur.w[5].x, cur.w[5].y, cur.w[5].z, cur.w[5].w};
             std::uint32_t out = 0;
             if ((m >> 48) & 1ULL)
             {
@@ -893,17 +953,41 @@ __global__ void __launch_bounds__(1024) k_jcp_resolve(Dev d, SegParams sp, int w
                 for (int i = 0; i < 24; ++i)
                 {
                     std::uint32_t mi = static_cast<std::uint32_t>((m >> (2 * i)) & 3ULL);
-                    if (mi == 3u)
+                    if (i < 12 && mi == 3u)
                     {
-                        mi = (dyn_state >> (2 * i)) & 3u; // i < 12 by construction
+                        // final state of an earlier queued pixel (kernel offsets of segmenter.cpp:527-530)
+                        const int dh = i < 5 ? -2 : (i < 10 ? -1 : 0);
+                        const int dw = i < 5 ? i - 2 : (i < 10 ? i - 7 : i - 12);
+                        const int hh = h + dh, ww = wv + dw;
+                        std::uint32_t ref;
+                        if (hh >= 0 && ww >= 0 && ww < sp.W)
+                        {
+                            ref = static_cast<std::uint32_t>(hh * sp.W + ww);
+                        }
+                        else
+                        {
+                            // inherited (stale) slot of a border pixel: explicit pixel reference
+                            const std::uint32_t brow = static_cast<std::uint32_t>(m >> 49);
+                            ref = sref[static_cast<std::size_t>(brow - 1) * 12 + i];
+                        }
+                        while ((mi = plane_get(plane, ref)) == 3u)
+                        {
+                            if (++spins > kJcpSpinLimit)
+                            {
+                                atomicOr(&d.status[f], ST_JCP_STALL);
+                                mi = 0u;
+                                break;
+                            }
+                            __nanosleep(20);
+                        }
                     }
                     if (mi == 1u)
                     {
-                        wg += wn[static_cast<std::size_t>(i) * d.qcap + k];
+                        wg += wts[i];
                     }
                     else if (mi == 2u)
                     {
-                        wo += wn[static_cast<std::size_t>(i) * d.qcap + k];
+                        wo += wts[i];
                     }
                 }
                 out = (wo > wg) ? 2u : 1u;
@@ -911,59 +995,60 @@ __global__ void __launch_bounds__(1024) k_jcp_resolve(Dev d, SegParams sp, int w
             // 3 -> out: clear the bits that differ
             atomicAnd(&plane[p >> 4], ~((3u ^ out) << ((p & 15u) * 2u)));
             code[p] = (out == 0u) ? PX_UNDECIDED : static_cast<std::uint8_t>(out);
+            cur = nxt;
         }
-        __syncthreads();
-        np = s_next;
-        std::uint32_t* t = pend0;
-        pend0 = pend1;
-        pend1 = t;
-        first = false;
-        ++rounds;
-        __syncthreads();
     }
     if (threadIdx.x == 0)
     {
-        d.jcp_rounds[f] = rounds;
+        d.jcp_rounds[f] = nruns;
     }
-    // ---- populateLabels (segmenter.cpp:640-669): only pixel winners receive a label
-    const std::size_t o = static_cast<std::size_t>(f) * d.cap;
-    for (std::uint32_t p = threadIdx.x; p < static_cast<std::uint32_t>(sp.npx); p += blockDim.x)
+}
+
+// populateLabels (segmenter.cpp:640-669): only pixel winners receive a label; optional BGR image
+__global__ void __launch_bounds__(256) k_seg_labels_out(Dev d, SegParams sp, int want_image)
+{
+    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t p = blockIdx.x * 256u + threadIdx.x;
+    if (p >= static_cast<std::uint32_t>(sp.npx))
     {
-        const std::uint8_t cfull = code[p];
-        const std::uint8_t c = cfull & 0xf;
-        if (c == PX_GROUND || c == PX_OBSTACLE)
+        return;
+    }
+    const std::size_t po = static_cast<std::size_t>(f) * sp.npx;
+    const std::size_t o = static_cast<std::size_t>(f) * d.cap;
+    const std::uint8_t cfull = d.code[po + p];
+    const std::uint8_t c = cfull & 0xf;
+    if (c == PX_GROUND || c == PX_OBSTACLE)
+    {
+        const int idx = __float_as_int(d.pxpt[po + p].w);
+        if (idx >= 0)
         {
-            const int idx = __float_as_int(d.pxpt[po + p].w);
-            if (idx >= 0)
-            {
-                d.seg_label[o + idx] = c;
-                d.labels_out[o + d.idx_v[o + idx]] = c;
-            }
+            d.seg_label[o + idx] = c;
+            d.labels_out[o + d.idx_v[o + idx]] = c;
         }
-        if (want_image)
+    }
+    if (want_image)
+    {
+        std::uint8_t b = 0, g = 0, r = 0;
+        if (c == PX_GROUND)
         {
-            std::uint8_t b = 0, g = 0, r = 0;
-            if (c == PX_GROUND)
-            {
-                g = 255;
-            }
-            else if (c == PX_OBSTACLE)
-            {
-                r = 255;
-            }
-            else if (c == PX_QUEUED || c == PX_UNDECIDED)
-            {
-                b = 255;
-            }
-            else if (cfull & PX_DILATED)
-            {
-                r = 255;
-            }
-            std::uint8_t* px = d.bgr + (po + p) * 3;
-            px[0] = b;
-            px[1] = g;
-            px[2] = r;
+            g = 255;
         }
+        else if (c == PX_OBSTACLE)
+        {
+            r = 255;
+        }
+        else if (c == PX_QUEUED || c == PX_UNDECIDED)
+        {
+            b = 255;
+        }
+        else if (cfull & PX_DILATED)
+        {
+            r = 255;
+        }
+        std::uint8_t* px = d.bgr + (po + p) * 3;
+        px[0] = b;
+        px[1] = g;
+        px[2] = r;
     }
 }
 
@@ -988,7 +1073,7 @@ void launch_segment(Ctx* c, std::uint32_t nf, bool want_image)
     mark(c, "seg_cell_scan");
     k_seg_scatter<<<gpts, 256, 0, s>>>(d, sp);
     mark(c, "seg_scatter");
-    k_seg_cell<<<dim3((sp.ncell + 3) / 4, nf), 128, 0, s>>>(d, sp);
+    k_seg_cell<<<dim3((sp.ncell + kCellWarps * kCellsPerWarp - 1) / (kCellWarps * kCellsPerWarp), nf), kCellWarps * 32, 0, s>>>(d, sp);
     mark(c, "seg_cell");
     k_seg_elev<<<dim3((sp.slices + 127) / 128, nf), 128, 0, s>>>(d, sp);
     mark(c, "seg_elev");
@@ -1010,6 +1095,8 @@ void launch_segment(Ctx* c, std::uint32_t nf, bool want_image)
     launch_compact(c, "jcp_queue", nf, d.ptiles, nullptr, static_cast<std::uint32_t>(sp.npx), d.tile_cnt, d.n_queue,
                    QueuePred{d.code, static_cast<std::uint32_t>(sp.npx)},
                    QueueEmit{d.queue, d.status, d.qcap});
+    launch_compact(c, "jcp_runs", nf, (d.qcap + kTile - 1) / kTile, d.n_queue, 0u, d.tile_cnt, d.n_runs,
+                   RunHeadPred{d.queue, d.qcap, static_cast<std::uint32_t>(sp.W)}, RunHeadEmit{d.runs, d.qcap});
     k_jcp_pre<<<dim3((d.qcap + 127) / 128, nf), 128, 0, s>>>(d, sp);
     mark(c, "jcp_pre");
     const std::size_t plane_bytes = static_cast<std::size_t>((sp.npx + 15) / 16) * 4;
@@ -1018,7 +1105,9 @@ void launch_segment(Ctx* c, std::uint32_t nf, bool want_image)
         // 128-beam images: 64 KB state plane (opt-in above 48 KB; up to 227 KB per CTA on sm_100a)
         cudaFuncSetAttribute(k_jcp_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(plane_bytes));
     }
-    k_jcp_resolve<<<nf, 1024, plane_bytes, s>>>(d, sp, want_image ? 1 : 0);
+    k_jcp_resolve<<<nf, kJcpThreads, plane_bytes, s>>>(d, sp);
     mark(c, "jcp_resolve");
+    k_seg_labels_out<<<dim3((sp.npx + 255) / 256, nf), 256, 0, s>>>(d, sp, want_image ? 1 : 0);
+    mark(c, "seg_labels_out");
 }
 } // namespace lpl

@@ -51,7 +51,8 @@ def load_pack(limit: int | None = None) -> list[np.ndarray]:
     names = sorted(k for k in z.files if k.startswith("f"))
     if limit is not None:
         names = names[:limit]
-    return [decode_xyz_mm(z[k], z["z" + k[1:]]) for k in names]
+    # pack members are stored column-major (3, n) for compression
+    return [decode_xyz_mm(np.ascontiguousarray(z[k].T), z["z" + k[1:]]) for k in names]
 
 
 def load_golden(name: str) -> dict:

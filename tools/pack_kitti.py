@@ -31,7 +31,16 @@ def main(src="/root/reference/data"):
         arrays["z" + os.path.basename(f)[:-4]] = nz
         total += p.shape[0]
     os.makedirs(os.path.dirname(PACK_PATH), exist_ok=True)
-    np.savez_compressed(PACK_PATH, **arrays)
+    # LZMA members (np.load reads them transparently): ~30 % smaller than deflate, and the pack is
+    # re-sent to the GPU box with every gpurun call
+    import io
+    import zipfile
+
+    with zipfile.ZipFile(PACK_PATH, "w", compression=zipfile.ZIP_LZMA) as zf:
+        for k, v in arrays.items():
+            buf = io.BytesIO()
+            np.save(buf, np.ascontiguousarray(v.T) if v.ndim == 2 else v)
+            zf.writestr(k + ".npy", buf.getvalue())
     print(f"{len(files)} frames, {total} points -> {PACK_PATH} ({os.path.getsize(PACK_PATH) / 1e6:.1f} MB)")
     return 0
 
