@@ -105,6 +105,8 @@ void carve(Dev& d, Carver& cv, int npx, int ncell_cap, std::uint32_t** mt_raw)
     cv.take(d.hcount, B * h);
     cv.take(d.hlabel, B * h);
     cv.take(d.vslot, B * cap);
+    cv.take(d.vlist, B * cap);
+    cv.take(d.n_vox, B);
     cv.take(d.clabel, B * cap);
     cv.take(d.n_clusters, B);
     cv.take(d.ccount, B * cap);

@@ -148,6 +148,11 @@ __global__ void __launch_bounds__(256) k_clu_insert(Dev d, ClusterParams cp)
         if (prev == -1 || prev == flat)
         {
             slot = h;
+            if (prev == -1)
+            {
+                // this thread created the voxel: list it for the neighbour pass
+                d.vlist[o + atomicAdd(&d.n_vox[f], 1u)] = h;
+            }
             break;
         }
     }
@@ -203,19 +208,14 @@ __device__ __forceinline__ void uf_union(std::uint32_t* parent, std::uint32_t a,
 __global__ void __launch_bounds__(256) k_clu_union(Dev d, ClusterParams cp)
 {
     const std::uint32_t f = blockIdx.y;
-    const std::uint32_t n = d.n_o[f];
     const std::uint32_t i = blockIdx.x * 256u + threadIdx.x;
-    if (i >= n)
+    if (i >= d.n_vox[f])
     {
-        return;
+        return; // one thread per occupied voxel (dense list built while inserting)
     }
     const std::size_t o = static_cast<std::size_t>(f) * d.cap;
     const std::size_t ho = static_cast<std::size_t>(f) * d.hcap;
-    const std::uint32_t slot = d.vslot[o + i];
-    if (d.hmin[ho + slot] != i)
-    {
-        return; // one representative point per voxel does the neighbour look-ups
-    }
+    const std::uint32_t slot = d.vlist[o + i];
     const VoxelDims vd = voxel_dims(d, cp, f);
     const std::int32_t* keys = d.hkey + ho;
     std::uint32_t* parent = d.hparent + ho;
@@ -392,6 +392,7 @@ void launch_cluster(Ctx* c, std::uint32_t nf)
     Dev& d = c->d;
     cudaStream_t s = c->stream;
     cudaMemsetAsync(d.sph_max, 0, sizeof(std::uint32_t) * 4 * nf, s);
+    cudaMemsetAsync(d.n_vox, 0, sizeof(std::uint32_t) * nf, s);
     cudaMemsetAsync(d.hkey, 0xff, sizeof(std::int32_t) * static_cast<std::size_t>(d.hcap) * nf, s);
     cudaMemsetAsync(d.hmin, 0xff, sizeof(std::uint32_t) * static_cast<std::size_t>(d.hcap) * nf, s);
     const dim3 g((d.cap + 255) / 256, nf);

@@ -136,6 +136,8 @@ struct Dev
     std::uint32_t* hcount;    // [B][hcap] points per root
     std::int32_t* hlabel;     // [B][hcap] final label per root
     std::uint32_t* vslot;     // [B][cap]  voxel slot per point
+    std::uint32_t* vlist;     // [B][cap]  slots of the occupied voxels (unordered)
+    std::uint32_t* n_vox;     // [B]
     std::int32_t* clabel;     // [B][cap]  cluster label per obstacle point
     std::uint32_t* n_clusters;// [B]
     // ---- hulls

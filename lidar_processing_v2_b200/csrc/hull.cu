@@ -20,9 +20,9 @@
 
 namespace lpl
 {
-constexpr int kHullThreads = 128;
+constexpr int kHullThreads = 32;   // one warp per CTA: the hardware balances clusters of very different size
 constexpr int kHullWarps = kHullThreads / 32;
-constexpr int kHullCtasPerFrame = 64;  // 256 warps per frame, warp-stride over clusters
+constexpr int kHullCtasPerFrame = 512; // warp-stride over clusters; CTAs beyond the cluster count leave at once
 constexpr std::uint32_t kChainSmem = 512; // survivors swept from shared memory
 constexpr std::uint32_t kFilterAbove = 48;  // clusters above this are thinned by all lanes first
 constexpr std::uint32_t kLaneStack = 16;  // per-lane chain stack entries kept in shared memory
@@ -288,49 +288,81 @@ __device__ std::uint32_t hull_filter(const uint4* __restrict__ src, std::uint32_
     if (b > a)
     {
         P2 s2 = {0.0, 0.0}, s1 = {0.0, 0.0};
-        uint4 nx = ldg4(src + a);
-        for (std::uint32_t i = a; i < b; ++i)
+        // the next block of four elements is in flight while the current one is swept
+        uint4 nx[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
         {
-            const P2 p = elem_pt(nx);
-            if (i + 1 < b)
-            {
-                nx = ldg4(src + i + 1); // in flight during the pops below
-            }
-            while (kl >= 2 && not_left(s2, s1, p))
-            {
-                --kl;
-                s1 = s2;
-                if (kl >= 2)
-                {
-                    s2 = elem_pt(ldg4(src + L.get(kl - 2)));
-                }
-            }
-            L.set(kl, i);
-            ++kl;
-            s2 = s1;
-            s1 = p;
+            nx[u] = ldg4(src + min(a + u, b - 1u));
         }
-        nx = ldg4(src + b - 1);
-        for (std::uint32_t i = b; i-- > a;)
+        for (std::uint32_t i0 = a; i0 < b; i0 += 4)
         {
-            const P2 p = elem_pt(nx);
-            if (i > a)
+            uint4 cu[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
             {
-                nx = ldg4(src + i - 1);
+                cu[u] = nx[u];
+                nx[u] = ldg4(src + min(i0 + 4u + u, b - 1u));
             }
-            while (ku >= 2 && not_left(s2, s1, p))
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
             {
-                --ku;
-                s1 = s2;
-                if (ku >= 2)
+                const std::uint32_t i = i0 + u;
+                if (i < b)
                 {
-                    s2 = elem_pt(ldg4(src + U.get(ku - 2)));
+                    const P2 p = elem_pt(cu[u]);
+                    while (kl >= 2 && not_left(s2, s1, p))
+                    {
+                        --kl;
+                        s1 = s2;
+                        if (kl >= 2)
+                        {
+                            s2 = elem_pt(ldg4(src + L.get(kl - 2)));
+                        }
+                    }
+                    L.set(kl, i);
+                    ++kl;
+                    s2 = s1;
+                    s1 = p;
                 }
             }
-            U.set(ku, i);
-            ++ku;
-            s2 = s1;
-            s1 = p;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+        {
+            nx[u] = ldg4(src + (b - 1u - min(static_cast<std::uint32_t>(u), b - 1u - a)));
+        }
+        for (std::uint32_t done = 0; done < b - a; done += 4)
+        {
+            uint4 cu[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+            {
+                cu[u] = nx[u];
+                nx[u] = ldg4(src + (b - 1u - min(done + 4u + u, b - 1u - a)));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+            {
+                if (done + u < b - a)
+                {
+                    const std::uint32_t i = b - 1u - (done + u);
+                    const P2 p = elem_pt(cu[u]);
+                    while (ku >= 2 && not_left(s2, s1, p))
+                    {
+                        --ku;
+                        s1 = s2;
+                        if (ku >= 2)
+                        {
+                            s2 = elem_pt(ldg4(src + U.get(ku - 2)));
+                        }
+                    }
+                    U.set(ku, i);
+                    ++ku;
+                    s2 = s1;
+                    s1 = p;
+                }
+            }
         }
     }
     // union of the ascending lower list and the descending upper list
@@ -579,7 +611,7 @@ void launch_hulls(Ctx* c, std::uint32_t nf)
     mark(c, "hull_chain");
     k_excl_scan<<<nf, 1024, 0, s>>>(d.hcnt, d.cap, d.hull_off, d.cap + 1, d.cap, d.n_clusters, d.n_hull);
     mark(c, "hull_off_scan");
-    k_hull_gather<<<dim3(kHullCtasPerFrame, nf), 128, 0, s>>>(d);
+    k_hull_gather<<<dim3(64, nf), 128, 0, s>>>(d);
     mark(c, "hull_gather");
 }
 } // namespace lpl

@@ -193,7 +193,46 @@ __device__ __forceinline__ void seg_cell_one(const Dev& d, const SegParams& sp, 
     const float4* pts = d.pts_v + o;
     float zmin;
     std::uint32_t best = 0; // largest i in [1, n/2] with z[i] - z[i-1] > 0.5, 0 = none
-    if (n <= kCellSmem)
+    if (n <= 32)
+    {
+        // the common case: one point per lane, both sorts are shuffle-only bitonic networks
+        const std::uint32_t lane = lane_id();
+        std::uint32_t v = lane < n ? ord[lane] : 0xffffffffu;
+#pragma unroll
+        for (std::uint32_t k = 2; k <= 32; k <<= 1)
+        {
+#pragma unroll
+            for (std::uint32_t j = k >> 1; j > 0; j >>= 1)
+            {
+                const std::uint32_t other = __shfl_xor_sync(0xffffffffu, v, j);
+                const bool take_min = ((lane & j) == 0) == ((lane & k) == 0);
+                v = take_min ? min(v, other) : max(v, other);
+            }
+        }
+        float z = 3.402823466e+38f;
+        if (lane < n)
+        {
+            ord[lane] = v;
+            z = pts[v].z;
+        }
+#pragma unroll
+        for (std::uint32_t k = 2; k <= 32; k <<= 1)
+        {
+#pragma unroll
+            for (std::uint32_t j = k >> 1; j > 0; j >>= 1)
+            {
+                const float other = __shfl_xor_sync(0xffffffffu, z, j);
+                const bool take_min = ((lane & j) == 0) == ((lane & k) == 0);
+                z = take_min ? fminf(z, other) : fmaxf(z, other);
+            }
+        }
+        const float prev = __shfl_up_sync(0xffffffffu, z, 1);
+        const bool hit = lane >= 1 && lane <= n / 2 && (z - prev > 0.5f);
+        const std::uint32_t m = __ballot_sync(0xffffffffu, hit);
+        const int src_lane = m != 0 ? 31 - __clz(m) : 0;
+        zmin = __shfl_sync(0xffffffffu, z, src_lane);
+    }
+    else if (n <= kCellSmem)
     {
         for (std::uint32_t t = lane_id(); t < n; t += 32)
         {
@@ -847,8 +886,8 @@ __device__ __forceinline__ std::uint32_t plane_get(const volatile std::uint32_t*
     return (plane[p >> 4] >> ((p & 15u) * 2u)) & 3u;
 }
 
-constexpr int kJcpThreads = 256;
-constexpr std::uint32_t kJcpSpinLimit = 1u << 24;
+constexpr int kJcpThreads = 512;
+constexpr std::uint32_t kJcpSpinLimit = 1u << 22;
 
 struct RunHeadPred
 {
@@ -871,25 +910,6 @@ struct RunHeadEmit
         runs[static_cast<std::size_t>(f) * qcap + pos] = k;
     }
 };
-
-struct JcpEntry
-{
-    unsigned long long m;
-    float4 w[6];
-};
-
-__device__ __forceinline__ JcpEntry jcp_load(const unsigned long long* mkv, const float* wn, std::uint32_t k)
-{
-    JcpEntry e;
-    e.m = mkv[k];
-    const float4* row = reinterpret_cast<const float4*>(wn + static_cast<std::size_t>(k) * 24);
-#pragma unroll
-    for (int i = 0; i < 6; ++i)
-    {
-        e.w[i] = row[i];
-    }
-    return e;
-}
 
 __global__ void __launch_bounds__(kJcpThreads) k_jcp_resolve(Dev d, SegParams sp)
 {
@@ -920,82 +940,111 @@ __global__ void __launch_bounds__(kJcpThreads) k_jcp_resolve(Dev d, SegParams sp
     const float* wn = d.wn + static_cast<std::size_t>(f) * 24 * d.qcap;
     const std::uint32_t* sref = d.stale_ref + static_cast<std::size_t>(f) * d.nborder_cap * 12;
     const std::uint32_t W = static_cast<std::uint32_t>(sp.W);
+    const std::uint32_t lane = lane_id();
+    const int slot = static_cast<int>(min(lane, 23u)); // lanes 24..31 shadow slot 23 and contribute nothing
+    // kernel offsets of slots 0..11 (segmenter.cpp:527-530); slots >= 12 are never dynamic
+    const int dh = slot < 5 ? -2 : (slot < 10 ? -1 : 0);
+    const int dw = slot < 5 ? slot - 2 : (slot < 10 ? slot - 7 : slot - 12);
     std::uint32_t spins = 0;
-    __syncthreads();
-    // raster-adjacent runs wait on each other: spread them over different warps (lane l of warp w
-    // takes runs w + 8 * l, + 256, ...), each thread still walking its runs in raster order
-    const std::uint32_t first_run = (threadIdx.x >> 5) + (kJcpThreads / 32) * (threadIdx.x & 31u);
-    for (std::uint32_t r = first_run; r < nruns; r += kJcpThreads)
+    __shared__ std::uint32_t s_next_run;
+    if (threadIdx.x == 0)
     {
-        std::uint32_t k = runs[r];
-        const std::uint32_t kend = (r + 1 < nruns) ? runs[r + 1] : nq; // first entry of the next run
+        s_next_run = 0;
+    }
+    __syncthreads();
+    // One warp per run, lane i = kernel slot i: the 96-byte weight row of a pixel is one coalesced
+    // load, every lane resolves its own slot (spinning on the plane only for a queued pixel of the
+    // rows above that another warp has not fired yet), and the vote is the reference's ordered sum
+    // over the 24 slots, accumulated by shuffles so that the float additions happen in slot order.
+    // Runs are handed out in raster order to whichever warp is free: the raster-first unfinished
+    // run is always being worked on and waits on nothing unfinished, so the sweep cannot deadlock.
+    while (true)
+    {
+        std::uint32_t r = 0;
+        if (lane == 0)
+        {
+            r = atomicAdd(&s_next_run, 1u);
+        }
+        r = __shfl_sync(0xffffffffu, r, 0);
+        if (r >= nruns)
+        {
+            break;
+        }
+        // lanes 0 / 1 fetch this run's and the next run's first entry together
+        std::uint32_t kk = nq;
+        if (lane < 2u && r + lane < nruns)
+        {
+            kk = runs[r + lane];
+        }
+        std::uint32_t k = __shfl_sync(0xffffffffu, kk, 0);
+        const std::uint32_t kend = __shfl_sync(0xffffffffu, kk, 1); // first entry of the next run
         std::uint32_t p = queue[k];
         const int h = static_cast<int>(p / W);
         int wv = static_cast<int>(p % W);
-        JcpEntry cur = jcp_load(mkv, wn, k);
+        unsigned long long m = mkv[k];
+        float wt = lane < 24u ? wn[static_cast<std::size_t>(k) * 24 + lane] : 0.f;
         for (; k < kend; ++k, ++p, ++wv)
         {
-            JcpEntry nxt = cur;
+            unsigned long long m_next = 0;
+            float wt_next = 0.f;
             if (k + 1 < kend)
             {
-                nxt = jcp_load(mkv, wn, k + 1); // in flight while this pixel waits and votes
+                m_next = mkv[k + 1]; // in flight while this pixel waits and votes
+                wt_next = lane < 24u ? wn[static_cast<std::size_t>(k + 1) * 24 + lane] : 0.f;
             }
-            const unsigned long long m = cur.m;
-            const float wts[24] = {cur.w[0].x, cur.w[0].y, cur.w[0].z, cur.w[0].w, cur.w[1].x, cur.w[1].y,
-                                   cur.w[1].z, cur.w[1].w, cur.w[2].x, cur.w[2].y, cur.w[2].z, cur.w[2].w,
-                                   cur.w[3].x, cur.w[3].y, cur.w[3].z, cur.w[3].w, cur.w[4].x, cur.w[4].y,
-                                   cur.w[4].z, cur.w[4].w, cur.w[5].x, cur.w[5].y, cur.w[5].z, cur.w[5].w};
             std::uint32_t out = 0;
             if ((m >> 48) & 1ULL)
             {
-                float wo = 0.f, wg = 0.f;
+                std::uint32_t mi = lane < 24u ? static_cast<std::uint32_t>((m >> (2 * slot)) & 3ULL) : 0u;
+                if (mi == 3u)
+                {
+                    // final state of an earlier queued pixel
+                    const int hh = h + dh, ww = wv + dw;
+                    std::uint32_t ref;
+                    if (hh >= 0 && ww >= 0 && ww < sp.W)
+                    {
+                        ref = static_cast<std::uint32_t>(hh * sp.W + ww);
+                    }
+                    else
+                    {
+                        // inherited (stale) slot of a border pixel: explicit pixel reference
+                        const std::uint32_t brow = static_cast<std::uint32_t>(m >> 49);
+                        ref = sref[static_cast<std::size_t>(brow - 1) * 12 + slot];
+                    }
+                    while ((mi = plane_get(plane, ref)) == 3u)
+                    {
+                        if (++spins > kJcpSpinLimit)
+                        {
+                            atomicOr(&d.status[f], ST_JCP_STALL);
+                            mi = 0u;
+                            break;
+                        }
+                        __nanosleep(64); // back off: a spinning warp must not starve the warp it waits for
+                    }
+                }
+                __syncwarp();
+                // x + 0.0f == x: adding a zero for the slots of the other classes keeps the sums
+                // bit-identical to the reference's conditional accumulation in slot order
+                const float g = mi == 1u ? wt : 0.f;
+                const float o = mi == 2u ? wt : 0.f;
+                float wg = 0.f, wo = 0.f;
 #pragma unroll
                 for (int i = 0; i < 24; ++i)
                 {
-                    std::uint32_t mi = static_cast<std::uint32_t>((m >> (2 * i)) & 3ULL);
-                    if (i < 12 && mi == 3u)
-                    {
-                        // final state of an earlier queued pixel (kernel offsets of segmenter.cpp:527-530)
-                        const int dh = i < 5 ? -2 : (i < 10 ? -1 : 0);
-                        const int dw = i < 5 ? i - 2 : (i < 10 ? i - 7 : i - 12);
-                        const int hh = h + dh, ww = wv + dw;
-                        std::uint32_t ref;
-                        if (hh >= 0 && ww >= 0 && ww < sp.W)
-                        {
-                            ref = static_cast<std::uint32_t>(hh * sp.W + ww);
-                        }
-                        else
-                        {
-                            // inherited (stale) slot of a border pixel: explicit pixel reference
-                            const std::uint32_t brow = static_cast<std::uint32_t>(m >> 49);
-                            ref = sref[static_cast<std::size_t>(brow - 1) * 12 + i];
-                        }
-                        while ((mi = plane_get(plane, ref)) == 3u)
-                        {
-                            if (++spins > kJcpSpinLimit)
-                            {
-                                atomicOr(&d.status[f], ST_JCP_STALL);
-                                mi = 0u;
-                                break;
-                            }
-                            __nanosleep(20);
-                        }
-                    }
-                    if (mi == 1u)
-                    {
-                        wg += wts[i];
-                    }
-                    else if (mi == 2u)
-                    {
-                        wo += wts[i];
-                    }
+                    wg += __shfl_sync(0xffffffffu, g, i);
+                    wo += __shfl_sync(0xffffffffu, o, i);
                 }
                 out = (wo > wg) ? 2u : 1u;
             }
-            // 3 -> out: clear the bits that differ
-            atomicAnd(&plane[p >> 4], ~((3u ^ out) << ((p & 15u) * 2u)));
-            code[p] = (out == 0u) ? PX_UNDECIDED : static_cast<std::uint8_t>(out);
-            cur = nxt;
+            if (lane == 0)
+            {
+                // 3 -> out: clear the bits that differ
+                atomicAnd(&plane[p >> 4], ~((3u ^ out) << ((p & 15u) * 2u)));
+                code[p] = (out == 0u) ? PX_UNDECIDED : static_cast<std::uint8_t>(out);
+            }
+            __syncwarp(); // orders lane 0's plane update before the next pixel's look-ups
+            m = m_next;
+            wt = wt_next;
         }
     }
     if (threadIdx.x == 0)
