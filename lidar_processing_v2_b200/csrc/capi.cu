@@ -116,6 +116,7 @@ void carve(Dev& d, Carver& cv, int npx, int ncell_cap, std::uint32_t** mt_raw)
     cv.take(d.hstL, B * cap);
     cv.take(d.hstU, B * cap);
     cv.take(d.hstack, B * 2 * cap);
+    cv.take(d.hfin, B * cap);
     cv.take(d.hcnt, B * cap);
     cv.take(d.hull_off, B * (cap + 1));
     cv.take(d.hull_idx, B * cap);

@@ -169,14 +169,22 @@ __global__ void __launch_bounds__(256) k_clu_insert(Dev d, ClusterParams cp)
 }
 
 // parent[] is updated with L2 atomics while other threads walk it: read through L2 (ld.cg) so a
-// stale L1 line can never make a failed CAS retry forever.
-__device__ __forceinline__ std::uint32_t uf_find(const std::uint32_t* parent, std::uint32_t x)
+// stale L1 line can never make a failed CAS retry forever. The walk halves the path as it goes
+// (every visited node is re-pointed to its grandparent): parents only ever move to ancestors, so
+// racing walkers and hooks stay correct, and the chains that index-ordered hooking builds in
+// large components stay short.
+__device__ __forceinline__ std::uint32_t uf_find(std::uint32_t* parent, std::uint32_t x)
 {
     std::uint32_t p = __ldcg(parent + x);
     while (p != x)
     {
+        const std::uint32_t g = __ldcg(parent + p);
+        if (g != p)
+        {
+            parent[x] = g;
+        }
         x = p;
-        p = __ldcg(parent + x);
+        p = g;
     }
     return x;
 }

@@ -148,6 +148,7 @@ struct Dev
     std::uint32_t* hstL;      // [B][cap]  per-lane lower-chain stacks of the thinning passes
     std::uint32_t* hstU;      // [B][cap]  per-lane upper-chain stacks
     std::uint32_t* hstack;    // [B][2*cap] per-cluster hull vertices (at segment offset + cluster id)
+    std::uint32_t* hfin;      // [B][cap]  per cluster: survivor count | buffer flag | done flag after thinning
     std::uint32_t* hcnt;      // [B][cap]  hull vertex count per cluster
     std::uint32_t* hull_off;  // [B][cap+1]
     std::uint32_t* hull_idx;  // [B][cap]  obstacle-cloud index per hull vertex

@@ -21,8 +21,7 @@
 namespace lpl
 {
 constexpr int kHullThreads = 32;   // one warp per CTA: the hardware balances clusters of very different size
-constexpr int kHullWarps = kHullThreads / 32;
-constexpr int kHullCtasPerFrame = 512; // warp-stride over clusters; CTAs beyond the cluster count leave at once
+constexpr int kHullCtasPerFrame = 256; // warp-stride over clusters; CTAs beyond the cluster count leave at once
 constexpr std::uint32_t kChainSmem = 512; // survivors swept from shared memory
 constexpr std::uint32_t kFilterAbove = 48;  // clusters above this are thinned by all lanes first
 constexpr std::uint32_t kLaneStack = 16;  // per-lane chain stack entries kept in shared memory
@@ -279,7 +278,13 @@ __device__ std::uint32_t hull_filter(const uint4* __restrict__ src, std::uint32_
                                      std::uint32_t* smL, std::uint32_t* smU)
 {
     const std::uint32_t lane = lane_id();
-    const std::uint32_t lanes = min(32u, (m + 7u) / 8u);
+    // balance the two sequential phases: a lane sweeps m / lanes points now and every lane leaves
+    // roughly eight survivors for the next (sequential or thinner) sweep -> lanes ~ sqrt(m / 8)
+    std::uint32_t lanes = 2u;
+    while (lanes < 32u && lanes * lanes * 8u < m)
+    {
+        ++lanes;
+    }
     const std::uint32_t chunk = (m + lanes - 1u) / lanes;
     const std::uint32_t a = min(m, lane * chunk), b = min(m, a + chunk);
     const LaneStack L{smL + lane * kLaneStack, stL + a};
@@ -438,63 +443,52 @@ __device__ __forceinline__ std::uint32_t monotone_chain(Get P, std::uint32_t m, 
     return static_cast<std::uint32_t>(k - 1);
 }
 
-__global__ void __launch_bounds__(kHullThreads) k_hull_chain(Dev d)
+// hfin[c]: what k_hull_thin leaves for k_hull_final
+constexpr std::uint32_t kFinDone = 0x80000000u;   // hull already written by k_hull_thin
+constexpr std::uint32_t kFinOther = 0x40000000u;  // survivors live in the second sort buffer
+constexpr std::uint32_t kFinalMax = 256;          // survivors swept by one thread (local-memory stack)
+
+// Pass 1, one warp per cluster above kFilterAbove points: thinning passes ping-pong between the two
+// sort buffers (the segment is private to the warp) until few enough points survive for a single
+// thread, or thinning stops paying (points in convex position), in which case the warp sweeps the
+// survivors itself.
+__global__ void __launch_bounds__(kHullThreads) k_hull_thin(Dev d)
 {
-    __shared__ float2 s_key[kHullWarps][kChainSmem];
-    __shared__ std::uint16_t s_st[kHullWarps][kChainSmem + 2];
-    __shared__ std::uint32_t s_lane[kHullWarps][2][32 * kLaneStack];
+    __shared__ float2 s_key[kChainSmem];
+    __shared__ std::uint16_t s_st[kChainSmem + 2];
+    __shared__ std::uint32_t s_lane[2][32 * kLaneStack];
     const std::uint32_t f = blockIdx.y;
     const std::uint32_t K = d.n_clusters[f];
-    const std::uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    const std::uint32_t lane = lane_id();
     const std::size_t o = static_cast<std::size_t>(f) * d.cap;
     const std::uint32_t* cstart = d.cstart + static_cast<std::size_t>(f) * (d.cap + 1);
     const bool in_b = (sort_passes(d.n_o[f]) & 1u) != 0u;
     uint4* sorted = (in_b ? d.hsB : d.hsA) + o;
     uint4* other = (in_b ? d.hsA : d.hsB) + o;
-    for (std::uint32_t c = blockIdx.x * kHullWarps + warp; c < K; c += gridDim.x * kHullWarps)
+    for (std::uint32_t c = blockIdx.x; c < K; c += gridDim.x)
     {
         const std::uint32_t seg = cstart[c];
         const std::uint32_t n = cstart[c + 1] - seg;
-        std::uint32_t* gst = d.hstack + static_cast<std::size_t>(f) * 2 * d.cap + seg + c; // n + 1 entries
-        if (lane == 0)
+        if (n <= kFilterAbove)
         {
-            // z extent of the cluster (processor.cpp:648-655), reduced while labelling (cluster.cu)
-            d.zminmax[o + c] = make_float2(unord_f32(d.zmin_u[o + c]), unord_f32(d.zmax_u[o + c]));
-        }
-        if (n < 3)
-        {
-            // identity order = obstacle-cloud order (polygonizer.cpp:36-41)
             if (lane == 0)
             {
-                std::uint32_t a = (n > 0) ? sorted[seg].w : 0u, b = (n > 1) ? sorted[seg + 1].w : 0u;
-                if (n == 2 && b < a)
-                {
-                    const std::uint32_t t = a;
-                    a = b;
-                    b = t;
-                }
-                if (n > 0)
-                {
-                    gst[0] = a;
-                }
-                if (n > 1)
-                {
-                    gst[1] = b;
-                }
-                d.hcnt[o + c] = n;
+                d.hfin[o + c] = n;
             }
             continue;
         }
-        // thinning passes ping-pong between the two sort buffers (the segment is private to this warp)
+        std::uint32_t* gst = d.hstack + static_cast<std::size_t>(f) * 2 * d.cap + seg + c; // n + 1 entries
         uint4* cur = sorted + seg;
         uint4* nxt = other + seg;
         std::uint32_t m = n;
+        bool in_other = false;
         while (m > kFilterAbove)
         {
-            const std::uint32_t m2 = hull_filter(cur, m, nxt, d.hstL + o + seg, d.hstU + o + seg, s_lane[warp][0], s_lane[warp][1]);
+            const std::uint32_t m2 = hull_filter(cur, m, nxt, d.hstL + o + seg, d.hstU + o + seg, s_lane[0], s_lane[1]);
             uint4* t = cur;
             cur = nxt;
             nxt = t;
+            in_other = !in_other;
             const bool stalled = m2 * 4u > m * 3u; // convex-position input: thinning does not pay
             m = m2;
             if (stalled)
@@ -502,18 +496,26 @@ __global__ void __launch_bounds__(kHullThreads) k_hull_chain(Dev d)
                 break;
             }
         }
+        if (m <= kFinalMax)
+        {
+            if (lane == 0)
+            {
+                d.hfin[o + c] = m | (in_other ? kFinOther : 0u);
+            }
+            continue;
+        }
         std::uint32_t hc = 0;
         if (m <= kChainSmem)
         {
             for (std::uint32_t t = lane; t < m; t += 32)
             {
                 const uint4 e = cur[t];
-                s_key[warp][t] = make_float2(__uint_as_float(e.y), __uint_as_float(e.z));
+                s_key[t] = make_float2(__uint_as_float(e.y), __uint_as_float(e.z));
             }
             __syncwarp();
             if (lane == 0)
             {
-                const float2* key = s_key[warp];
+                const float2* key = s_key;
                 hc = monotone_chain(
                     [&](std::uint32_t i) {
                         const float2 v = key[i];
@@ -522,13 +524,13 @@ __global__ void __launch_bounds__(kHullThreads) k_hull_chain(Dev d)
                         p.y = static_cast<double>(v.y);
                         return p;
                     },
-                    m, s_st[warp]);
+                    m, s_st);
             }
             hc = __shfl_sync(0xffffffffu, hc, 0);
             __syncwarp();
             for (std::uint32_t t = lane; t < hc; t += 32)
             {
-                gst[t] = cur[s_st[warp][t]].w;
+                gst[t] = cur[s_st[t]].w;
             }
             __syncwarp();
         }
@@ -562,7 +564,64 @@ __global__ void __launch_bounds__(kHullThreads) k_hull_chain(Dev d)
         if (lane == 0)
         {
             d.hcnt[o + c] = hc;
+            d.hfin[o + c] = kFinDone;
         }
+    }
+}
+
+// Pass 2, one thread per cluster: z extent, the trivial cases, and the reference's sweep over the
+// (at most kFinalMax) surviving points with the stack in local memory. 32 clusters per warp keep
+// the sequential sweeps from wasting 31 of 32 lanes.
+__global__ void __launch_bounds__(64) k_hull_final(Dev d)
+{
+    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t K = d.n_clusters[f];
+    const std::size_t o = static_cast<std::size_t>(f) * d.cap;
+    const std::uint32_t* cstart = d.cstart + static_cast<std::size_t>(f) * (d.cap + 1);
+    const bool in_b = (sort_passes(d.n_o[f]) & 1u) != 0u;
+    for (std::uint32_t c = blockIdx.x * 64u + threadIdx.x; c < K; c += gridDim.x * 64u)
+    {
+    const std::uint32_t seg = cstart[c];
+    const std::uint32_t n = cstart[c + 1] - seg;
+    // z extent of the cluster (processor.cpp:648-655), reduced while labelling (cluster.cu)
+    d.zminmax[o + c] = make_float2(unord_f32(d.zmin_u[o + c]), unord_f32(d.zmax_u[o + c]));
+    const std::uint32_t fin = d.hfin[o + c];
+    if (fin & kFinDone)
+    {
+        continue;
+    }
+    const bool use_b = in_b != ((fin & kFinOther) != 0u);
+    const uint4* cur = (use_b ? d.hsB : d.hsA) + o + seg;
+    std::uint32_t* gst = d.hstack + static_cast<std::size_t>(f) * 2 * d.cap + seg + c; // n + 1 entries
+    if (n < 3)
+    {
+        // identity order = obstacle-cloud order (polygonizer.cpp:36-41)
+        std::uint32_t a = (n > 0) ? cur[0].w : 0u, b = (n > 1) ? cur[1].w : 0u;
+        if (n == 2 && b < a)
+        {
+            const std::uint32_t t = a;
+            a = b;
+            b = t;
+        }
+        if (n > 0)
+        {
+            gst[0] = a;
+        }
+        if (n > 1)
+        {
+            gst[1] = b;
+        }
+        d.hcnt[o + c] = n;
+        continue;
+    }
+    const std::uint32_t m = fin & 0x3fffffffu;
+    std::uint16_t st[kFinalMax + 2];
+    const std::uint32_t hc = monotone_chain([&](std::uint32_t i) { return elem_pt(cur[i]); }, m, st);
+    for (std::uint32_t t = 0; t < hc; ++t)
+    {
+        gst[t] = cur[st[t]].w;
+    }
+    d.hcnt[o + c] = hc;
     }
 }
 
@@ -607,8 +666,10 @@ void launch_hulls(Ctx* c, std::uint32_t nf)
         k_hull_merge<<<dim3(d.tiles, nf), kTileThreads, 0, s>>>(d, p);
         mark(c, "hull_merge");
     }
-    k_hull_chain<<<dim3(kHullCtasPerFrame, nf), kHullThreads, 0, s>>>(d);
-    mark(c, "hull_chain");
+    k_hull_thin<<<dim3(kHullCtasPerFrame, nf), kHullThreads, 0, s>>>(d);
+    mark(c, "hull_thin");
+    k_hull_final<<<dim3(16, nf), 64, 0, s>>>(d);
+    mark(c, "hull_final");
     k_excl_scan<<<nf, 1024, 0, s>>>(d.hcnt, d.cap, d.hull_off, d.cap + 1, d.cap, d.n_clusters, d.n_hull);
     mark(c, "hull_off_scan");
     k_hull_gather<<<dim3(64, nf), 128, 0, s>>>(d);

@@ -154,6 +154,51 @@ __device__ __forceinline__ void warp_sort(T* buf, std::uint32_t n)
     }
 }
 
+// Bitonic sort of 32 * E values held E per lane (value index = e * 32 + lane): exchanges across
+// lanes are shuffles, exchanges across the registers of a lane are plain moves; no shared memory.
+template <int E, typename T>
+__device__ __forceinline__ void warp_sort_regs(T (&v)[E])
+{
+    const std::uint32_t lane = lane_id();
+#pragma unroll
+    for (std::uint32_t k = 2; k <= 32u * E; k <<= 1)
+    {
+#pragma unroll
+        for (std::uint32_t j = k >> 1; j > 0; j >>= 1)
+        {
+            if (j >= 32u)
+            {
+                const std::uint32_t je = j >> 5;
+#pragma unroll
+                for (std::uint32_t e = 0; e < static_cast<std::uint32_t>(E); ++e)
+                {
+                    const std::uint32_t pe = e ^ je;
+                    if (pe > e)
+                    {
+                        const bool asc = (((e << 5) | lane) & k) == 0;
+                        const T a = v[e], b = v[pe];
+                        const bool swap = asc ? (b < a) : (a < b);
+                        v[e] = swap ? b : a;
+                        v[pe] = swap ? a : b;
+                    }
+                }
+            }
+            else
+            {
+#pragma unroll
+                for (std::uint32_t e = 0; e < static_cast<std::uint32_t>(E); ++e)
+                {
+                    const T other = __shfl_xor_sync(0xffffffffu, v[e], j);
+                    const bool asc = (((e << 5) | lane) & k) == 0;
+                    const bool lower = (lane & j) == 0;
+                    const bool take_min = lower == asc;
+                    v[e] = take_min ? (other < v[e] ? other : v[e]) : (v[e] < other ? other : v[e]);
+                }
+            }
+        }
+    }
+}
+
 constexpr int kCellWarps = 4;     // warps per CTA
 constexpr int kCellsPerWarp = 8;  // cells per warp, interleaved across the CTA's warps (most cells are empty)
 
@@ -231,6 +276,59 @@ __device__ __forceinline__ void seg_cell_one(const Dev& d, const SegParams& sp, 
         const std::uint32_t m = __ballot_sync(0xffffffffu, hit);
         const int src_lane = m != 0 ? 31 - __clz(m) : 0;
         zmin = __shfl_sync(0xffffffffu, z, src_lane);
+    }
+    else if (n <= 128)
+    {
+        // four values per lane in registers; the sorted heights go through shared memory only for
+        // the gap scan
+        const std::uint32_t lane = lane_id();
+        std::uint32_t v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+        {
+            const std::uint32_t t = e * 32 + lane;
+            v[e] = t < n ? ord[t] : 0xffffffffu;
+        }
+        warp_sort_regs<4>(v);
+        float z[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+        {
+            const std::uint32_t t = e * 32 + lane;
+            z[e] = 3.402823466e+38f;
+            if (t < n)
+            {
+                ord[t] = v[e];
+                z[e] = pts[v[e]].z;
+            }
+        }
+        warp_sort_regs<4>(z);
+        float* zb = reinterpret_cast<float*>(buf);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+        {
+            zb[e * 32 + lane] = z[e];
+        }
+        __syncwarp();
+        zmin = zb[0];
+        for (std::uint32_t hi = n / 2; hi >= 1 && best == 0;)
+        {
+            const bool valid = hi > lane;
+            const std::uint32_t i = hi - lane;
+            const bool hit = valid && (zb[i] - zb[i - 1] > 0.5f);
+            const std::uint32_t m = __ballot_sync(0xffffffffu, hit);
+            if (m != 0)
+            {
+                best = hi - (__ffs(m) - 1);
+                zmin = zb[best];
+            }
+            if (hi <= 32)
+            {
+                break;
+            }
+            hi -= 32;
+        }
+        __syncwarp();
     }
     else if (n <= kCellSmem)
     {
@@ -947,6 +1045,7 @@ __global__ void __launch_bounds__(kJcpThreads) k_jcp_resolve(Dev d, SegParams sp
     const int dw = slot < 5 ? slot - 2 : (slot < 10 ? slot - 7 : slot - 12);
     std::uint32_t spins = 0;
     __shared__ std::uint32_t s_next_run;
+    __shared__ __align__(16) float s_vote[kJcpThreads / 32][48];
     if (threadIdx.x == 0)
     {
         s_next_run = 0;
@@ -1022,19 +1121,38 @@ __global__ void __launch_bounds__(kJcpThreads) k_jcp_resolve(Dev d, SegParams sp
                         __nanosleep(64); // back off: a spinning warp must not starve the warp it waits for
                     }
                 }
-                __syncwarp();
                 // x + 0.0f == x: adding a zero for the slots of the other classes keeps the sums
-                // bit-identical to the reference's conditional accumulation in slot order
-                const float g = mi == 1u ? wt : 0.f;
-                const float o = mi == 2u ? wt : 0.f;
-                float wg = 0.f, wo = 0.f;
-#pragma unroll
-                for (int i = 0; i < 24; ++i)
+                // bit-identical to the reference's conditional accumulation in slot order. The 24
+                // (ground, obstacle) contributions go through shared memory (one store per lane, six
+                // 128-bit loads per class by lane 0): 48 shuffles per pixel would saturate the SM's
+                // shuffle throughput with 16 warps per frame in flight.
+                float* vg = s_vote[threadIdx.x >> 5];
+                float* vo = vg + 24;
+                if (lane < 24u)
                 {
-                    wg += __shfl_sync(0xffffffffu, g, i);
-                    wo += __shfl_sync(0xffffffffu, o, i);
+                    vg[lane] = mi == 1u ? wt : 0.f;
+                    vo[lane] = mi == 2u ? wt : 0.f;
                 }
-                out = (wo > wg) ? 2u : 1u;
+                __syncwarp();
+                if (lane == 0)
+                {
+                    float wg = 0.f, wo = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 6; ++i)
+                    {
+                        const float4 a = reinterpret_cast<const float4*>(vg)[i];
+                        const float4 b = reinterpret_cast<const float4*>(vo)[i];
+                        wg += a.x;
+                        wg += a.y;
+                        wg += a.z;
+                        wg += a.w;
+                        wo += b.x;
+                        wo += b.y;
+                        wo += b.z;
+                        wo += b.w;
+                    }
+                    out = (wo > wg) ? 2u : 1u;
+                }
             }
             if (lane == 0)
             {
