@@ -431,22 +431,31 @@ def run_e2e(lpl, ctx0, frames, device, args, barrier, stages):
     h2d = sum(f.shape[0] for f in frames) * 16
     d2h = 0
 
-    def one_step(count_bytes):
-        nonlocal d2h
-        for i in (0, 1):
-            ctxs[i].upload(views[i])
-            ctxs[i].run(len(views[i]), stages)
-        for i in (0, 1):
-            counts = ctxs[i].download_batch(len(views[i]), outs[i])
-            if count_bytes:
-                d2h += outs[i].bytes_for(counts)
+    def enqueue(i):
+        ctxs[i].upload(views[i])
+        ctxs[i].run(len(views[i]), stages)
 
-    for _ in range(max(args.warmup, 1)):
-        one_step(False)
+    def collect(i, count_bytes):
+        nonlocal d2h
+        counts = ctxs[i].download_batch(len(views[i]), outs[i])
+        if count_bytes:
+            d2h += outs[i].bytes_for(counts)
+
+    def run_steps(k, count_first):
+        # software pipeline: while one context's results cross PCIe and its next batch is uploaded,
+        # the other context's kernels keep the SMs busy
+        enqueue(0)
+        enqueue(1)
+        for s in range(k):
+            for i in (0, 1):
+                collect(i, count_first and s == 0)
+                if s + 1 < k:
+                    enqueue(i)
+
+    run_steps(max(args.warmup, 1), False)
     barrier()
     t0 = time.perf_counter()
-    for s in range(args.steps):
-        one_step(s == 0)
+    run_steps(args.steps, True)
     barrier()
     secs = time.perf_counter() - t0
     for c in ctxs:

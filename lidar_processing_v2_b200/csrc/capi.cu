@@ -125,6 +125,10 @@ void carve(Dev& d, Carver& cv, int npx, int ncell_cap, std::uint32_t** mt_raw)
     cv.take(d.n_hull, B);
     cv.take(d.zmin_u, B * cap);
     cv.take(d.zmax_u, B * cap);
+    cv.take(d.ext, B * cap * 8);
+    cv.take(d.octa, B * cap * 8);
+    cv.take(d.hseg_cnt, B * cap);
+    cv.take(d.n_h, B);
     const std::size_t tl = std::max<std::size_t>(d.tiles, d.ptiles);
     cv.take(d.tile_cnt, B * tl);
     cv.take(d.status, B);
@@ -309,6 +313,20 @@ __global__ void k_label_count(Dev d, std::uint32_t K)
         }
     }
     accumulate_zext(d.zmin_u + o, d.zmax_u + o, l, z);
+    if (i < n && l >= 0)
+    {
+        const float4 p = d.pts_o[o + i];
+        accumulate_extremes(d.ext + o * 8, l, p.x, p.y, i);
+    }
+}
+
+__global__ void k_ext_init(Dev d, std::uint32_t K)
+{
+    const std::uint32_t c = blockIdx.x * 256u + threadIdx.x;
+    if (c < K)
+    {
+        ext_init(d.ext + static_cast<std::size_t>(c) * 8);
+    }
 }
 } // namespace
 
@@ -999,6 +1017,8 @@ int lpl_cluster_hulls(lpl_ctx* ctx, const void* points, std::size_t stride, cons
     LPL_TRY(cudaMemsetAsync(d.ccount, 0, sizeof(std::uint32_t) * num_clusters, c.stream));
     LPL_TRY(cudaMemsetAsync(d.zmin_u, 0xff, sizeof(std::uint32_t) * num_clusters, c.stream));
     LPL_TRY(cudaMemsetAsync(d.zmax_u, 0, sizeof(std::uint32_t) * num_clusters, c.stream));
+    k_ext_init<<<(num_clusters + 255) / 256, 256, 0, c.stream>>>(d, num_clusters);
+    mark(&c, "ext_init");
     k_label_count<<<dim3((d.cap + 255) / 256, 1), 256, 0, c.stream>>>(d, num_clusters);
     mark(&c, "label_count");
     launch_hulls(&c, 1);

@@ -337,6 +337,7 @@ struct ClusterRepEmit
         d.ccount[o + pos] = d.hcount[ho + root];
         d.zmin_u[o + pos] = 0xffffffffu; // z extent accumulators of the new label
         d.zmax_u[o + pos] = 0u;
+        ext_init(d.ext + (o + pos) * 8);
     }
 };
 
@@ -356,7 +357,9 @@ __global__ void __launch_bounds__(256) k_clu_labels(Dev d)
     {
         l = d.hlabel[static_cast<std::size_t>(f) * d.hcap + d.vslot[o + i]];
         d.clabel[o + i] = l;
-        z = d.pts_o[o + i].z;
+        const float4 p = d.pts_o[o + i];
+        z = p.z;
+        accumulate_extremes(d.ext + o * 8, l, p.x, p.y, i);
     }
     accumulate_zext(d.zmin_u + o, d.zmax_u + o, l, z);
 }

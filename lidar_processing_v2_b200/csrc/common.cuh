@@ -157,6 +157,11 @@ struct Dev
     std::uint32_t* n_hull;    // [B]       hull vertices of the frame
     std::uint32_t* zmin_u;    // [B][cap]  per cluster: order-preserving bits of min z
     std::uint32_t* zmax_u;    // [B][cap]  per cluster: order-preserving bits of max z
+    unsigned long long* ext;  // [B][cap][8] per cluster: extreme points (ordered value bits << 32 | point index) for
+                              //             min x, min x+y, min y, max x-y, max x, max x+y, max y, min x-y (CCW order)
+    float2* octa;             // [B][cap][8] per cluster: the octagon of those points, or NaN when unusable
+    std::uint32_t* hseg_cnt;  // [B][cap]  per cluster: points that survive the octagon filter
+    std::uint32_t* n_h;       // [B]       survivors per frame (input size of the hull sort)
     // ---- generic
     std::uint32_t* tile_cnt;  // [B][max(tiles, ptiles)]
     std::uint32_t* status;    // [B]  error bits raised by kernels
@@ -335,6 +340,49 @@ __device__ __forceinline__ void accumulate_zext(std::uint32_t* zmin_u, std::uint
             atomicMax(&zmax_u[l], hi);
         }
         todo &= ~grp;
+    }
+}
+
+// Extreme points of a cluster in eight directions (hull.cu builds an inscribed octagon from them
+// and drops every point strictly inside it before the hull sort). Slots in counter-clockwise
+// order: 0 min x, 1 min x+y, 2 min y, 3 max x-y, 4 max x, 5 max x+y, 6 max y, 7 min x-y.
+// A cheap L2 read filters out the (vast majority of) points that cannot improve a slot.
+__device__ __forceinline__ void ext_init(unsigned long long* e)
+{
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+    {
+        const bool is_min = (k == 0 || k == 1 || k == 2 || k == 7);
+        e[k] = is_min ? ~0ULL : 0ULL;
+    }
+}
+
+__device__ __forceinline__ void accumulate_extremes(unsigned long long* ext, std::int32_t label, float x, float y,
+                                                    std::uint32_t idx)
+{
+    if (label < 0)
+    {
+        return;
+    }
+    unsigned long long* e = ext + static_cast<std::size_t>(label) * 8;
+    const float v[8] = {x, x + y, y, x - y, x, x + y, y, x - y};
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+    {
+        const bool is_min = (k == 0 || k == 1 || k == 2 || k == 7);
+        const unsigned long long key = (static_cast<unsigned long long>(ord_f32(v[k])) << 32) | idx;
+        const unsigned long long cur = __ldcg(e + k);
+        if (is_min ? key < cur : key > cur)
+        {
+            if (is_min)
+            {
+                atomicMin(e + k, key);
+            }
+            else
+            {
+                atomicMax(e + k, key);
+            }
+        }
     }
 }
 

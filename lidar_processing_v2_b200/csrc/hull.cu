@@ -77,6 +77,119 @@ __device__ __forceinline__ std::uint32_t sort_passes(std::uint32_t n)
 }
 
 // ------------------------------------------------------------------------------------------
+// octagon filter (Akl-Toussaint): a point strictly inside the polygon spanned by up to eight
+// extreme points of its cluster cannot be a hull vertex, so it never enters the sort. The
+// extreme points are actual points of the cluster (found while labelling, cluster.cu), the test
+// is the reference's own fp64 orientation predicate, and a polygon that is not convex in
+// counter-clockwise order (possible only through float rounding of x + y / x - y) disables the
+// filter for that cluster.
+// ------------------------------------------------------------------------------------------
+struct P2
+{
+    double x, y;
+};
+
+// polygonizer.cpp:45-48: true when p3 is not strictly left of p1 -> p2 (pop p2)
+__device__ __forceinline__ bool not_left(const P2& p1, const P2& p2, const P2& p3)
+{
+    return (p2.x - p1.x) * (p3.y - p1.y) - (p2.y - p1.y) * (p3.x - p1.x) <= 0.0;
+}
+
+constexpr std::uint32_t kOctaMinPoints = 16; // smaller clusters skip the filter
+
+__global__ void __launch_bounds__(128) k_hull_octagon(Dev d)
+{
+    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t K = d.n_clusters[f];
+    const std::size_t o = static_cast<std::size_t>(f) * d.cap;
+    for (std::uint32_t c = blockIdx.x * 128u + threadIdx.x; c < K; c += gridDim.x * 128u)
+    {
+        float2 v[8];
+        bool ok = d.ccount[o + c] >= kOctaMinPoints;
+        if (ok)
+        {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+            {
+                const std::uint32_t idx = static_cast<std::uint32_t>(d.ext[(o + c) * 8 + k]);
+                const float4 p = d.pts_o[o + idx];
+                v[k] = make_float2(p.x + 0.0f, p.y + 0.0f);
+            }
+            // convex and counter-clockwise (repeated vertices allowed), and not degenerate
+            bool any_turn = false;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+            {
+                const P2 a = {static_cast<double>(v[k].x), static_cast<double>(v[k].y)};
+                const P2 b = {static_cast<double>(v[(k + 1) & 7].x), static_cast<double>(v[(k + 1) & 7].y)};
+#pragma unroll
+                for (int j = 2; j < 8; ++j)
+                {
+                    const P2 q = {static_cast<double>(v[(k + j) & 7].x), static_cast<double>(v[(k + j) & 7].y)};
+                    const double cr = (b.x - a.x) * (q.y - a.y) - (b.y - a.y) * (q.x - a.x);
+                    ok = ok && !(cr < 0.0); // every other vertex on or left of every edge
+                    any_turn = any_turn || cr > 0.0;
+                }
+            }
+            ok = ok && any_turn;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+        {
+            d.octa[(o + c) * 8 + k] = ok ? v[k] : make_float2(__int_as_float(0x7fc00000), 0.f);
+        }
+        d.hseg_cnt[o + c] = 0;
+    }
+}
+
+struct HullKeepPred
+{
+    Dev d;
+    __device__ bool operator()(std::uint32_t f, std::uint32_t i) const
+    {
+        const std::size_t o = static_cast<std::size_t>(f) * d.cap;
+        const std::int32_t l = d.clabel[o + i];
+        if (l < 0)
+        {
+            return false;
+        }
+        const float2* v = d.octa + (o + l) * 8;
+        const float2 v0 = v[0];
+        if (v0.x != v0.x)
+        {
+            return true; // no usable octagon for this cluster
+        }
+        const float4 pt = d.pts_o[o + i];
+        const P2 q = {static_cast<double>(pt.x), static_cast<double>(pt.y)};
+        P2 a = {static_cast<double>(v0.x), static_cast<double>(v0.y)};
+        bool inside = true;
+#pragma unroll
+        for (int k = 1; k <= 8; ++k)
+        {
+            const float2 vk = v[k & 7];
+            const P2 b = {static_cast<double>(vk.x), static_cast<double>(vk.y)};
+            const bool degenerate = (a.x == b.x) && (a.y == b.y);
+            inside = inside && (degenerate || !not_left(a, b, q)); // strictly left of every proper edge
+            a = b;
+        }
+        return !inside;
+    }
+};
+
+struct HullKeepEmit
+{
+    Dev d;
+    __device__ void operator()(std::uint32_t f, std::uint32_t i, std::uint32_t pos) const
+    {
+        const std::size_t o = static_cast<std::size_t>(f) * d.cap;
+        const float4 p = d.pts_o[o + i];
+        const std::uint32_t l = static_cast<std::uint32_t>(d.clabel[o + i]);
+        d.hsB[o + pos] = make_uint4(l, __float_as_uint(p.x + 0.0f), __float_as_uint(p.y + 0.0f), i);
+        atomicAdd(&d.hseg_cnt[o + l], 1u);
+    }
+};
+
+// ------------------------------------------------------------------------------------------
 // tile sort: 2048 elements per CTA, mirror-first bitonic network for arbitrary n (every exchange
 // moves the larger key to the higher index, so the virtual +inf padding beyond n never moves)
 // ------------------------------------------------------------------------------------------
@@ -84,7 +197,7 @@ __global__ void __launch_bounds__(kTileThreads) k_hull_tilesort(Dev d)
 {
     __shared__ uint4 s[kTile];
     const std::uint32_t f = blockIdx.y;
-    const std::uint32_t n = d.n_o[f];
+    const std::uint32_t n = d.n_h[f];
     const std::uint32_t base = blockIdx.x * kTile;
     if (base >= n)
     {
@@ -94,11 +207,7 @@ __global__ void __launch_bounds__(kTileThreads) k_hull_tilesort(Dev d)
     const std::uint32_t m = min(static_cast<std::uint32_t>(kTile), n - base);
     for (std::uint32_t t = threadIdx.x; t < m; t += kTileThreads)
     {
-        const std::uint32_t i = base + t;
-        const float4 p = d.pts_o[o + i];
-        const std::int32_t l = d.clabel[o + i];
-        s[t] = make_uint4(l < 0 ? 0xffffffffu : static_cast<std::uint32_t>(l), __float_as_uint(p.x + 0.0f),
-                          __float_as_uint(p.y + 0.0f), i);
+        s[t] = d.hsB[o + base + t]; // (label, x, y, index) of the points that survived the octagon filter
     }
     __syncthreads();
     for (std::uint32_t k = 2; (k >> 1) < m; k <<= 1)
@@ -168,7 +277,7 @@ __global__ void __launch_bounds__(kTileThreads) k_hull_merge(Dev d, std::uint32_
     __shared__ uint4 s[kTile];
     __shared__ std::uint32_t s_split[2];
     const std::uint32_t f = blockIdx.y;
-    const std::uint32_t n = d.n_o[f];
+    const std::uint32_t n = d.n_h[f];
     const std::uint32_t out0 = blockIdx.x * kTile;
     if (out0 >= n || sort_passes(n) <= pass)
     {
@@ -249,23 +358,12 @@ __global__ void __launch_bounds__(kTileThreads) k_hull_merge(Dev d, std::uint32_
 // ------------------------------------------------------------------------------------------
 // hull chains
 // ------------------------------------------------------------------------------------------
-struct P2
-{
-    double x, y;
-};
-
 __device__ __forceinline__ P2 elem_pt(const uint4& e)
 {
     P2 p;
     p.x = static_cast<double>(__uint_as_float(e.y));
     p.y = static_cast<double>(__uint_as_float(e.z));
     return p;
-}
-
-// polygonizer.cpp:45-48: true when p3 is not strictly left of p1 -> p2 (pop p2)
-__device__ __forceinline__ bool not_left(const P2& p1, const P2& p2, const P2& p3)
-{
-    return (p2.x - p1.x) * (p3.y - p1.y) - (p2.y - p1.y) * (p3.x - p1.x) <= 0.0;
 }
 
 // Warp-wide thinning pass: lane l sweeps its contiguous chunk of src[0..m) with the lower chain
@@ -462,7 +560,7 @@ __global__ void __launch_bounds__(kHullThreads) k_hull_thin(Dev d)
     const std::uint32_t lane = lane_id();
     const std::size_t o = static_cast<std::size_t>(f) * d.cap;
     const std::uint32_t* cstart = d.cstart + static_cast<std::size_t>(f) * (d.cap + 1);
-    const bool in_b = (sort_passes(d.n_o[f]) & 1u) != 0u;
+    const bool in_b = (sort_passes(d.n_h[f]) & 1u) != 0u;
     uint4* sorted = (in_b ? d.hsB : d.hsA) + o;
     uint4* other = (in_b ? d.hsA : d.hsB) + o;
     for (std::uint32_t c = blockIdx.x; c < K; c += gridDim.x)
@@ -578,7 +676,7 @@ __global__ void __launch_bounds__(64) k_hull_final(Dev d)
     const std::uint32_t K = d.n_clusters[f];
     const std::size_t o = static_cast<std::size_t>(f) * d.cap;
     const std::uint32_t* cstart = d.cstart + static_cast<std::size_t>(f) * (d.cap + 1);
-    const bool in_b = (sort_passes(d.n_o[f]) & 1u) != 0u;
+    const bool in_b = (sort_passes(d.n_h[f]) & 1u) != 0u;
     for (std::uint32_t c = blockIdx.x * 64u + threadIdx.x; c < K; c += gridDim.x * 64u)
     {
     const std::uint32_t seg = cstart[c];
@@ -651,7 +749,10 @@ void launch_hulls(Ctx* c, std::uint32_t nf)
 {
     Dev& d = c->d;
     cudaStream_t s = c->stream;
-    k_excl_scan<<<nf, 1024, 0, s>>>(d.ccount, d.cap, d.cstart, d.cap + 1, d.cap, d.n_clusters, nullptr);
+    k_hull_octagon<<<dim3(4, nf), 128, 0, s>>>(d);
+    mark(c, "hull_octagon");
+    launch_compact(c, "hull_keep", nf, d.tiles, d.n_o, 0u, d.tile_cnt, d.n_h, HullKeepPred{d}, HullKeepEmit{d});
+    k_excl_scan<<<nf, 1024, 0, s>>>(d.hseg_cnt, d.cap, d.cstart, d.cap + 1, d.cap, d.n_clusters, nullptr);
     mark(c, "hull_seg_scan");
     k_hull_tilesort<<<dim3(d.tiles, nf), kTileThreads, 0, s>>>(d);
     mark(c, "hull_tilesort");
