@@ -407,14 +407,14 @@ def run_ours(args, rank, local_rank, world):
 
 
 def run_e2e(lpl, ctx0, frames, device, args, barrier, stages):
-    """Upload (pinned host -> device) + run + batch download, double-buffered over two contexts."""
+    """Upload (pinned host -> device) + run + batch download through the package's FramePipeline
+    (two contexts / CUDA streams working on alternating half batches)."""
+    from lidar_processing_v2_b200.stream import FramePipeline
+
     nf = len(frames)
     max_pts = max(f.shape[0] for f in frames)
     half = (nf + 1) // 2
-    # two half-size batches in flight keep the copy engines and the SMs busy at the same time
-    ctxs = [lpl.Context(device, max_points=max_pts, max_frames=half) for _ in range(2)]
-    for c in ctxs:
-        c.cluster_config(range_m=0.4, az_deg=1.0, el_deg=3.0, min_size=3)
+    pipe = FramePipeline(device, max_pts, half, stages=stages)
     parts = [frames[:half], frames[half:]]
     pinned, views = [], []
     for part in parts:
@@ -426,40 +426,22 @@ def run_e2e(lpl, ctx0, frames, device, args, barrier, stages):
             o += f.shape[0]
         pinned.append(buf)
         views.append(v)
-    stride = ((max_pts + 2047) // 2048) * 2048
-    outs = [lpl.BatchBuffers(half, stride) for _ in range(2)]
-    h2d = sum(f.shape[0] for f in frames) * 16
-    d2h = 0
 
-    def enqueue(i):
-        ctxs[i].upload(views[i])
-        ctxs[i].run(len(views[i]), stages)
-
-    def collect(i, count_bytes):
-        nonlocal d2h
-        counts = ctxs[i].download_batch(len(views[i]), outs[i])
-        if count_bytes:
-            d2h += outs[i].bytes_for(counts)
-
-    def run_steps(k, count_first):
-        # software pipeline: while one context's results cross PCIe and its next batch is uploaded,
-        # the other context's kernels keep the SMs busy
-        enqueue(0)
-        enqueue(1)
-        for s in range(k):
+    def run_steps(k):
+        for _ in range(k):
             for i in (0, 1):
-                collect(i, count_first and s == 0)
-                if s + 1 < k:
-                    enqueue(i)
+                pipe.submit(views[i])  # returns (and thereby downloads) the batch this slot held before
+        pipe.drain()
 
-    run_steps(max(args.warmup, 1), False)
+    run_steps(max(args.warmup, 1))
     barrier()
+    pipe.h2d_bytes = pipe.d2h_bytes = 0
     t0 = time.perf_counter()
-    run_steps(args.steps, True)
+    run_steps(args.steps)
     barrier()
     secs = time.perf_counter() - t0
-    for c in ctxs:
-        c.close()
+    h2d, d2h = pipe.h2d_bytes // args.steps, pipe.d2h_bytes // args.steps
+    pipe.close()
     return {"seconds": secs, "h2d": h2d, "d2h": d2h}
 
 

@@ -105,6 +105,17 @@ class Mat
 
     std::uint8_t* data() { return buf_.data(); }
     const std::uint8_t* data() const { return buf_.data(); }
+    // cv::Mat::ptr<T>(row): the accessor the drop-in adaptors use (same spelling as real OpenCV)
+    template <typename T = std::uint8_t>
+    T* ptr(int r = 0)
+    {
+        return reinterpret_cast<T*>(buf_.data() + static_cast<std::size_t>(r) * cols * channels_);
+    }
+    template <typename T = std::uint8_t>
+    const T* ptr(int r = 0) const
+    {
+        return reinterpret_cast<const T*>(buf_.data() + static_cast<std::size_t>(r) * cols * channels_);
+    }
 
   private:
     int channels_ = 1;

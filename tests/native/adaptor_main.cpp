@@ -1,0 +1,162 @@
+// Exercises the drop-in C++ surface (include/lidar_processing_lib/*.hpp) the way the reference's
+// processor node does (src/processor/src/processor.cpp:552-663): Segmenter::segment on a
+// PointXYZIR cloud, label split, Clusterer::cluster on the obstacle cloud, per-label gather and
+// Polygonizer::convexHull, plus NoiseRemover::filter on the raw points.
+// Built by tests/test_adaptors.py against the PCL / OpenCV shims under oracle/shim (test
+// infrastructure) and linked with liblpl_b200.so.
+//
+// usage: adaptor_main <in.bin> <out.bin>
+//   in : u32 n, n x (float x, y, z, w), n x u16 ring
+//   out: u32 n, n x u8 noise, n x u32 label, u32 m, m x i32 cluster label, u32 K, K x u32 hull size,
+//        sum(hull size) x (double x, y)
+// exit code 3: no CUDA device (std::runtime_error from the adaptors), 4: any other exception
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <iostream>
+#include <vector>
+
+#include <lidar_processing_lib/clusterer.hpp>
+#include <lidar_processing_lib/noise_remover.hpp>
+#include <lidar_processing_lib/polygonizer.hpp>
+#include <lidar_processing_lib/segmenter.hpp>
+
+namespace lpl = lidar_processing_lib;
+
+int main(int argc, char** argv)
+{
+    if (argc < 3)
+    {
+        return 2;
+    }
+    try
+    {
+        std::FILE* fi = std::fopen(argv[1], "rb");
+        if (fi == nullptr)
+        {
+            return 2;
+        }
+        std::uint32_t n = 0;
+        if (std::fread(&n, 4, 1, fi) != 1)
+        {
+            return 2;
+        }
+        std::vector<float> xyzw(static_cast<std::size_t>(n) * 4);
+        std::vector<std::uint16_t> ring(n);
+        if (n != 0 && (std::fread(xyzw.data(), 16, n, fi) != n || std::fread(ring.data(), 2, n, fi) != n))
+        {
+            return 2;
+        }
+        std::fclose(fi);
+
+        // ---- NoiseRemover (noise_remover.hpp:56-80)
+        std::vector<lpl::NoiseRemover::PointT> raw(n);
+        pcl::PointCloud<pcl::PointXYZIR> cloud;
+        cloud.points.resize(n);
+        for (std::uint32_t i = 0; i < n; ++i)
+        {
+            raw[i] = {xyzw[4 * i], xyzw[4 * i + 1], xyzw[4 * i + 2]};
+            auto& p = cloud.points[i];
+            p.x = xyzw[4 * i];
+            p.y = xyzw[4 * i + 1];
+            p.z = xyzw[4 * i + 2];
+            p.intensity = 0.5F;
+            p.ring = ring[i];
+        }
+        lpl::NoiseRemover noise_remover;
+        noise_remover.reserve(200'000U);
+        std::vector<lpl::NoiseRemoverLabel> noise;
+        noise_remover.filter(raw, noise);
+
+        // ---- Segmenter (processor.cpp:552-556)
+        lpl::Segmenter segmenter;
+        lpl::SegmenterConfiguration scfg; // node values == struct defaults (processor.param.yaml:10-30)
+        segmenter.config(scfg);
+        std::vector<lpl::Label> labels;
+        segmenter.segment(cloud, labels);
+        const cv::Mat& image = segmenter.image();
+        if (image.rows != scfg.image_height || image.cols != scfg.image_width)
+        {
+            return 5;
+        }
+
+        // ---- label split (processor.cpp:562-579), cluster (:599)
+        pcl::PointCloud<pcl::PointXYZRGB> obstacles;
+        for (std::uint32_t i = 0; i < n; ++i)
+        {
+            if (labels[i] == lpl::Label::OBSTACLE)
+            {
+                pcl::PointXYZRGB q;
+                q.x = cloud.points[i].x;
+                q.y = cloud.points[i].y;
+                q.z = cloud.points[i].z;
+                obstacles.points.push_back(q);
+            }
+        }
+        lpl::Clusterer clusterer;
+        lpl::ClustererConfiguration ccfg;
+        ccfg.voxel_grid_elevation_resolution_deg = 3.0F; // processor.param.yaml:31-35
+        clusterer.config(ccfg);
+        std::vector<lpl::ClusterLabel> clabels;
+        clusterer.cluster(obstacles, clabels);
+
+        // ---- per-label gather + convexHull (processor.cpp:627-663)
+        std::int32_t max_label = -1;
+        for (const auto l : clabels)
+        {
+            max_label = l > max_label ? l : max_label;
+        }
+        lpl::Polygonizer polygonizer;
+        std::vector<std::uint32_t> hull_sizes;
+        std::vector<double> hull_xy;
+        std::vector<lpl::PointXY> pts;
+        std::vector<std::int32_t> idx;
+        for (std::int32_t l = 0; l <= max_label; ++l)
+        {
+            pts.clear();
+            for (std::size_t i = 0; i < clabels.size(); ++i)
+            {
+                if (clabels[i] == l)
+                {
+                    pts.push_back({static_cast<double>(obstacles.points[i].x), static_cast<double>(obstacles.points[i].y)});
+                }
+            }
+            polygonizer.convexHull(pts, idx);
+            hull_sizes.push_back(static_cast<std::uint32_t>(idx.size()));
+            for (const auto j : idx)
+            {
+                hull_xy.push_back(pts[j].x);
+                hull_xy.push_back(pts[j].y);
+            }
+        }
+
+        std::FILE* fo = std::fopen(argv[2], "wb");
+        if (fo == nullptr)
+        {
+            return 2;
+        }
+        const std::uint32_t m = static_cast<std::uint32_t>(clabels.size());
+        const std::uint32_t K = static_cast<std::uint32_t>(hull_sizes.size());
+        std::fwrite(&n, 4, 1, fo);
+        std::fwrite(noise.data(), 1, n, fo);
+        std::fwrite(labels.data(), 4, n, fo);
+        std::fwrite(&m, 4, 1, fo);
+        std::fwrite(clabels.data(), 4, m, fo);
+        std::fwrite(&K, 4, 1, fo);
+        std::fwrite(hull_sizes.data(), 4, K, fo);
+        std::fwrite(hull_xy.data(), 8, hull_xy.size(), fo);
+        std::fclose(fo);
+        std::printf("ok n=%u obstacles=%u clusters=%u hull_vertices=%zu\n", n, m, K, hull_xy.size() / 2);
+        return 0;
+    }
+    catch (const std::runtime_error& e)
+    {
+        std::cerr << "runtime_error: " << e.what() << "\n";
+        return std::strstr(e.what(), "no CUDA device") != nullptr ? 3 : 4;
+    }
+    catch (const std::exception& e)
+    {
+        std::cerr << "exception: " << e.what() << "\n";
+        return 4;
+    }
+}

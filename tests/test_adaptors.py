@@ -1,0 +1,75 @@
+"""The drop-in C++ surface (include/lidar_processing_lib/*.hpp): compiles against PCL / OpenCV
+headers (here: the shims under oracle/shim), links the C-ABI library, translates status codes into
+the reference's exceptions, and - on a GPU - reproduces the oracle through the node's call sequence."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+import lidar_processing_v2_b200 as lpl
+from conftest import HAVE_GPU, ROOT
+from oracle.oracle import NODE_CLUSTER_CFG
+
+EXE = os.path.join(ROOT, "tests", "native", "adaptor_main")
+SRC = os.path.join(ROOT, "tests", "native", "adaptor_main.cpp")
+
+
+@pytest.fixture(scope="module")
+def exe():
+    lpl.load_library()  # builds liblpl_b200.so if needed
+    pkg = os.path.dirname(lpl.SO_PATH)
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    deps = [SRC] + [os.path.join(ROOT, "include", "lidar_processing_lib", f)
+                    for f in os.listdir(os.path.join(ROOT, "include", "lidar_processing_lib")) if f.endswith(".hpp")]
+    if not os.path.exists(EXE) or any(os.path.getmtime(d) > os.path.getmtime(EXE) for d in deps + [lpl.SO_PATH]):
+        cmd = [cxx, "-std=c++17", "-O2", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "include"),
+               "-I", os.path.join(ROOT, "oracle", "shim"), SRC, "-o", EXE, "-L", pkg, "-llpl_b200",
+               "-Wl,-rpath," + pkg]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        assert res.returncode == 0, res.stderr
+    return EXE
+
+
+def _write_frame(path, pts, ring):
+    with open(path, "wb") as f:
+        f.write(struct.pack("<I", pts.shape[0]))
+        f.write(np.ascontiguousarray(pts, np.float32).tobytes())
+        f.write(np.ascontiguousarray(ring, np.uint16).tobytes())
+
+
+@pytest.mark.skipif(HAVE_GPU, reason="checks the no-device error translation")
+def test_adaptors_compile_link_and_fail_loudly_without_gpu(exe, tmp_path, golden0):
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    _write_frame(fin, golden0["pts"][:1000], golden0["ring"][:1000])
+    res = subprocess.run([exe, fin, fout], capture_output=True, text=True)
+    assert res.returncode == 3, (res.returncode, res.stderr)
+    assert "no CUDA device" in res.stderr and not os.path.exists(fout)
+
+
+@pytest.mark.gpu
+def test_adaptors_reproduce_the_reference_call_sequence(exe, tmp_path, golden0, port):
+    pts, ring = golden0["pts"], golden0["ring"].astype(np.uint16)
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    _write_frame(fin, pts, ring)
+    res = subprocess.run([exe, fin, fout], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    raw = open(fout, "rb").read()
+    o = 0
+    (n,) = struct.unpack_from("<I", raw, o); o += 4
+    noise = np.frombuffer(raw, np.uint8, n, o); o += n
+    labels = np.frombuffer(raw, np.uint32, n, o); o += 4 * n
+    (m,) = struct.unpack_from("<I", raw, o); o += 4
+    clabels = np.frombuffer(raw, np.int32, m, o); o += 4 * m
+    (K,) = struct.unpack_from("<I", raw, o); o += 4
+    sizes = np.frombuffer(raw, np.uint32, K, o); o += 4 * K
+    hxy = np.frombuffer(raw, np.float64, 2 * int(sizes.sum()), o).reshape(-1, 2)
+    assert n == pts.shape[0]
+    assert np.array_equal(noise, np.unpackbits(golden0["dror_exact"])[:n])
+    assert np.array_equal(labels, golden0["labels"].astype(np.uint32))
+    assert np.array_equal(clabels, golden0["cluster_labels"].astype(np.int32))
+    off = golden0["hull_offsets"]
+    assert np.array_equal(np.diff(off), sizes)
+    assert np.abs(hxy - golden0["hull_xy"].astype(np.float64)).max() <= 1e-5
+    _ = (port, NODE_CLUSTER_CFG)

@@ -271,3 +271,18 @@ def test_full_sequence_batch_vs_reference_summary():
             assert label_hash(got["noise"]) == s["dror_hash"], f
     finally:
         c.close()
+
+
+def test_frame_pipeline_stream(port, golden0, golden100):
+    """The double-buffered two-stream pipeline returns the same per-frame results as a single context."""
+    from lidar_processing_v2_b200.stream import run_stream
+
+    frames = [golden0["pts"], golden100["pts"], golden0["pts"][:60000].copy(), golden100["pts"][:90000].copy(),
+              golden0["pts"]]
+    stats = run_stream(frames, device=0, batch=2)
+    exp = [parity.oracle_chain(port, f, dror=True) for f in frames]
+    assert stats["frames"] == len(frames) and stats["world"] == 1
+    assert stats["points"] == sum(f.shape[0] for f in frames)
+    assert stats["obstacles"] == sum(int(e["obstacle_index"].shape[0]) for e in exp)
+    assert stats["clusters"] == sum(e["num_clusters"] for e in exp)
+    assert stats["hull_vertices"] == sum(int(e["hull_xy"].shape[0]) for e in exp)
