@@ -124,11 +124,11 @@ def algorithmic_bytes(name: str, s: dict) -> float:
         "dror_grid_count": 16 * N, "dror_grid_scan": 8 * 65536 * F, "dror_grid_scatter": 32 * N,
         "dror_query": 20 * U + U,
         "take_valid": (16 + 2 + 1) * N + 20 * V, "take_all": (16 + 2) * N + 20 * V,
-        "seg_bin": 16 * V + 12 * V, "seg_cell_scan": 8 * CELLS, "seg_scatter": 12 * V + 4 * NB,
-        "seg_cell": 8 * NB + 4 * NB + 4 * CELLS, "seg_elev": 12 * CELLS,
-        "seg_label": 4 * NB + 4 * NB + 4 * NB + 1 * NB,
-        "ransac_cand": 12 * NB + 4 * C, "ransac_setup": 1024 * F, "ransac_count": 24 * C,
-        "seg_image": 4 * NB + 16 * NB + 1 * NB + 8 * NB, "seg_px": 8 * PX + 17 * PX,
+        "seg_bin": 16 * V + 12 * V, "seg_cell_scan": 8 * CELLS, "seg_scatter": (16 + 8) * V + 8 * NB,
+        "seg_cell": 8 * NB + 8 * CELLS, "seg_elev": 12 * CELLS,
+        "seg_label": (16 + 4) * V + 4 * NB + 1 * V,
+        "ransac_setup": 1024 * F + 8 * CELLS, "ransac_count": 1 * V + 16 * C,
+        "seg_image": (16 + 4 + 4 + 1) * V + 1 * NB + 8 * NB, "seg_px": 8 * PX + 17 * PX + 17 * PX,
         "seg_dilate": 2 * PX, "jcp_queue": 2 * PX + 4 * Q,
         "jcp_pre": Q * (25 * 17 + 24 * 4 + 8), "jcp_resolve": PX * 1 + Q * (8 + 4 + 96) + PX * 17 + V * 2,
         "take_obstacles": 1 * V + 20 * M + 20 * M,
@@ -381,6 +381,9 @@ def run_ours(args, rank, local_rank, world):
                         "sample": f"first {ns} frames of {workload} (unrotated), whole chained pipeline, "
                                   f"{cores} worker processes, {secs:.1f} s"}
 
+    if os.environ.get("LPL_BENCH_KERNELS"):
+        with open(os.environ["LPL_BENCH_KERNELS"], "w") as fh:
+            _json.dump(kernels, fh, indent=1)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,

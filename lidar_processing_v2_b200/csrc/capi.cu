@@ -68,12 +68,13 @@ void carve(Dev& d, Carver& cv, int npx, int ncell_cap, std::uint32_t** mt_raw)
     cv.take(d.cell_cnt, B * ncell_cap);
     cv.take(d.cell_start, B * (ncell_cap + 1));
     cv.take(d.n_binned, B);
-    cv.take(d.order, B * cap);
+    cv.take(d.zo, B * cap);
     cv.take(d.zsort, B * cap);
+    cv.take(d.zsort2, B * cap);
+    cv.take(d.ccnt, B * ncell_cap);
     cv.take(d.cell_zmin, B * ncell_cap);
     cv.take(d.elev, B * ncell_cap);
     cv.take(d.lab, B * cap);
-    cv.take(d.cand, B * cap);
     cv.take(d.n_cand, B);
     cv.take(d.planes, B * kRansacIters);
     cv.take(d.inliers, B * kRansacIters);
@@ -200,6 +201,22 @@ int apply_seg_cfg(lpl_ctx* ctx)
     {
         return fail(ctx, LPL_ERR_CAPACITY, "polar grid has no cells or more cells than reserved (262144)");
     }
+    // range-image keys carry (depth^2 bits : 31, azimuth slice, point index) in 64 bits
+    int idx_bits = 11, slice_bits = 0;
+    while ((1u << idx_bits) < ctx->c.d.cap)
+    {
+        ++idx_bits;
+    }
+    while ((1 << slice_bits) < slices)
+    {
+        ++slice_bits;
+    }
+    if (idx_bits + slice_bits > 33)
+    {
+        return fail(ctx, LPL_ERR_CAPACITY, "azimuth slices x points per frame exceed the 33-bit tie-break field of the range image");
+    }
+    s.idx_bits = idx_bits;
+    s.nb = std::min(rings, kRansacBins);
     s.rings = rings;
     s.slices = slices;
     s.ncell = rings * slices;

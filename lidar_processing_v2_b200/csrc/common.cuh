@@ -49,6 +49,8 @@ struct SegParams
     float kthr_sqr, amp;
     float wscale; // (W - 1) as float
     int jcp_emulate_stale; // 1 = bit-compatible with the reference's stale out-of-image slots
+    int idx_bits;          // range-image key: bits of the point index (ceil log2 of the frame capacity)
+    int nb;                // radial bins that feed RANSAC: min(rings, kRansacBins)
 };
 
 struct DrorParams
@@ -97,18 +99,19 @@ struct Dev
     std::uint32_t* cell_cnt;  // [B][ncell]
     std::uint32_t* cell_start;// [B][ncell+1]
     std::uint32_t* n_binned;  // [B]       points that fell into the polar grid
-    std::uint32_t* order;     // [B][cap]  sorted position -> point index ((cell, cloud) order)
+    uint2* zo;                // [B][cap]  cell-major (unordered inside a cell): (point index, z bits)
     float* zsort;             // [B][cap]  scratch for oversized cells
+    float* zsort2;            // [B][cap]  scratch for oversized cells
+    std::uint32_t* ccnt;      // [B][ncell] RANSAC candidates per cell, then their exclusive prefix in (slice, bin) order
     float* cell_zmin;         // [B][ncell]
     float* elev;              // [B][ncell]
-    std::uint8_t* lab;        // [B][cap]  label by sorted position
-    std::uint32_t* cand;      // [B][cap]  RANSAC candidates (sorted positions)
+    std::uint8_t* lab;        // [B][cap]  label per point of the segmented cloud; bit 7 = RANSAC candidate
     std::uint32_t* n_cand;    // [B]
     float4* planes;           // [B][kRansacIters] (nx, ny, nz, d); nz = NaN marks a skipped draw
     std::uint32_t* inliers;   // [B][kRansacIters]
     float4* best_plane;       // [B]  (a, b, c, d); w component of [B + f] unused
     std::uint32_t* best_cnt;  // [B]
-    unsigned long long* key;  // [B][npx]  (depth_sqr bits << 32) | sorted position
+    unsigned long long* key;  // [B][npx]  (depth_sqr bits << 33) | (azimuth slice << idx_bits) | point index
     float4* pxpt;             // [B][npx]  x, y, z, point index (int bits; -1 = none)
     std::uint8_t* code;       // [B][npx]  PX_* before / after JCP
     std::uint32_t* queue;     // [B][qcap] queued pixels in raster order

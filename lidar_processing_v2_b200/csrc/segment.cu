@@ -3,17 +3,20 @@
 // Reference: lidar_processing_lib/src/segmenter.cpp
 //   constructPolarGrid :103-204   -> k_seg_bin, k_excl_scan, k_seg_scatter, k_seg_cell
 //   RECM               :206-283   -> k_seg_cell (robust per-cell minimum), k_seg_elev, k_seg_label
-//   RANSAC             :321-479   -> candidate compaction, k_ransac_setup, k_ransac_count
+//   RANSAC             :321-479   -> candidate flags (k_seg_label), k_ransac_setup, k_ransac_count
 //   image scatter      :291-318   -> k_seg_image (64-bit atomicMin keys), k_seg_px
 //   JCP                :481-638   -> k_seg_dilate (5x5 stencil on shared-memory tiles),
 //                                    queue compaction, k_jcp_pre, k_jcp_resolve
 //   populateLabels     :640-669   -> k_seg_labels_out
 //
 // Ordered semantics on an unordered machine: the reference iterates polar cells in index order
-// and the points of a cell in cloud order. `order` holds exactly that sequence (cells are
-// filled with atomics, then each cell is sorted by point index by one warp), and a point's
-// position in it is (i) its RANSAC candidate rank after a stable compaction and (ii) the low
-// word of its range-image key, so strict-`<` / first-wins ties resolve as in the reference.
+// and the points of a cell in cloud order. Only two results depend on that order and both are
+// recovered without sorting the cells: (i) the <= 120 RANSAC draws address candidates by their
+// rank in (cell, cloud) order - a prefix over per-cell candidate counts plus a radix select over
+// the point indices of one cell resolves a rank (k_ransac_setup); (ii) the range image keeps the
+// first point among equal depths - equal depth^2 implies the same radial bin, so the 64-bit key
+// (depth^2, azimuth slice, point index) under atomicMin picks the reference's winner (k_seg_image).
+// Everything else (heights per cell, inlier counts, labels) is order independent.
 //
 // JCP is a Gauss-Seidel sweep in raster order. A queued pixel only depends on queued pixels
 // that precede it in raster order and lie within the kernel distance, so the sweep is replayed
@@ -42,53 +45,74 @@ __global__ void __launch_bounds__(256) k_seg_bin(Dev d, SegParams sp)
 {
     const std::uint32_t f = blockIdx.y;
     const std::uint32_t n = d.n_v[f];
-    const std::uint32_t i = blockIdx.x * 256u + threadIdx.x;
-    if (i >= n)
+    if (blockIdx.x * 256u >= n)
     {
         return;
     }
+    const std::uint32_t i = blockIdx.x * 256u + threadIdx.x;
     const std::size_t o = static_cast<std::size_t>(f) * d.cap;
-    const float4 p = d.pts_v[o + i];
     std::int32_t cell = -1;
-    std::uint32_t px = 0, slot = 0;
-    if (!(p.z < sp.z_lo || p.z > sp.z_hi))
+    std::uint32_t px = 0;
+    if (i < n)
     {
-        const float dist = sqrtf(p.x * p.x + p.y * p.y);
-        const std::int32_t radial = static_cast<std::int32_t>(dist / sp.radial_spacing);
-        if (!(dist < sp.min_dist || dist > sp.max_dist || radial >= sp.rings))
+        const float4 p = d.pts_v[o + i];
+        if (!(p.z < sp.z_lo || p.z > sp.z_hi))
         {
-            float az = atan2_approx(p.y, p.x);
-            az = (az < 0.f) ? (az + 6.28318530717958647692f) : az;
-            const std::int32_t az_idx = min(static_cast<std::int32_t>(az / sp.slice_res), sp.slices - 1);
-            std::int32_t hgt;
-            bool ok = true;
-            if (sp.use_ring)
+            const float dist = sqrtf(p.x * p.x + p.y * p.y);
+            const std::int32_t radial = static_cast<std::int32_t>(dist / sp.radial_spacing);
+            if (!(dist < sp.min_dist || dist > sp.max_dist || radial >= sp.rings))
             {
-                hgt = static_cast<std::int32_t>(__float_as_uint(p.w) & 0xffffu);
-                ok = hgt < sp.H;
-            }
-            else
-            {
-                const float el = atanf_glibc(p.z / dist);
-                hgt = static_cast<std::int32_t>((el - sp.el_down) / sp.rad_per_px);
-                ok = !(hgt < 0 || hgt >= sp.H);
-            }
-            if (ok)
-            {
-                // static_cast<uint16_t>((W - 1) * az / TWO_M_PIf): float -> int32 -> low 16 bits
-                const std::int32_t wi = static_cast<std::int32_t>(sp.wscale * az / 6.28318530717958647692f);
-                const std::uint32_t wid = static_cast<std::uint32_t>(wi) & 0xffffu;
-                cell = az_idx * sp.rings + radial;
-                px = static_cast<std::uint32_t>(hgt) * sp.W + wid;
-                slot = atomicAdd(&d.cell_cnt[static_cast<std::size_t>(f) * sp.ncell + cell], 1u);
+                float az = atan2_approx(p.y, p.x);
+                az = (az < 0.f) ? (az + 6.28318530717958647692f) : az;
+                const std::int32_t az_idx = min(static_cast<std::int32_t>(az / sp.slice_res), sp.slices - 1);
+                std::int32_t hgt;
+                bool ok = true;
+                if (sp.use_ring)
+                {
+                    hgt = static_cast<std::int32_t>(__float_as_uint(p.w) & 0xffffu);
+                    ok = hgt < sp.H;
+                }
+                else
+                {
+                    const float el = atanf_glibc(p.z / dist);
+                    hgt = static_cast<std::int32_t>((el - sp.el_down) / sp.rad_per_px);
+                    ok = !(hgt < 0 || hgt >= sp.H);
+                }
+                if (ok)
+                {
+                    // static_cast<uint16_t>((W - 1) * az / TWO_M_PIf): float -> int32 -> low 16 bits
+                    const std::int32_t wi = static_cast<std::int32_t>(sp.wscale * az / 6.28318530717958647692f);
+                    const std::uint32_t wid = static_cast<std::uint32_t>(wi) & 0xffffu;
+                    cell = az_idx * sp.rings + radial;
+                    px = static_cast<std::uint32_t>(hgt) * sp.W + wid;
+                }
             }
         }
     }
-    d.cell[o + i] = cell;
-    d.px[o + i] = px;
-    d.slot[o + i] = slot;
+    // consecutive points of a scan line mostly share a cell: one atomic per (warp, cell)
+    const std::uint32_t peers = __match_any_sync(0xffffffffu, cell);
+    std::uint32_t slot = 0;
+    if (cell >= 0)
+    {
+        const int leader = __ffs(peers) - 1;
+        std::uint32_t base = 0;
+        if (static_cast<int>(lane_id()) == leader)
+        {
+            base = atomicAdd(&d.cell_cnt[static_cast<std::size_t>(f) * sp.ncell + cell], __popc(peers));
+        }
+        base = __shfl_sync(peers, base, leader);
+        slot = base + __popc(peers & ((1u << lane_id()) - 1u));
+    }
+    if (i < n)
+    {
+        d.cell[o + i] = cell;
+        d.px[o + i] = px;
+        d.slot[o + i] = slot;
+    }
 }
 
+// cell-major copy of (point index, z): the only per-cell consumers are the height statistics of
+// k_seg_cell and the rank selection of the RANSAC draws, neither of which needs cloud order
 __global__ void __launch_bounds__(256) k_seg_scatter(Dev d, SegParams sp)
 {
     const std::uint32_t f = blockIdx.y;
@@ -103,7 +127,7 @@ __global__ void __launch_bounds__(256) k_seg_scatter(Dev d, SegParams sp)
     if (cell >= 0)
     {
         const std::uint32_t s = d.cell_start[static_cast<std::size_t>(f) * (sp.ncell + 1) + cell];
-        d.order[o + s + d.slot[o + i]] = i;
+        d.zo[o + s + d.slot[o + i]] = make_uint2(i, __float_as_uint(d.pts_v[o + i].z));
     }
 }
 
@@ -202,64 +226,68 @@ __device__ __forceinline__ void warp_sort_regs(T (&v)[E])
 constexpr int kCellWarps = 4;     // warps per CTA
 constexpr int kCellsPerWarp = 8;  // cells per warp, interleaved across the CTA's warps (most cells are empty)
 
-__device__ __forceinline__ void seg_cell_one(const Dev& d, const SegParams& sp, std::uint32_t f, std::uint32_t cell,
-                                             std::uint32_t* buf);
-
-__global__ void __launch_bounds__(kCellWarps * 32) k_seg_cell(Dev d, SegParams sp)
+// largest i in [1, n/2] with zs[i] - zs[i-1] > 0.5 on the ascending heights zs[0..n), scanned from
+// the top by whole warps (segmenter.cpp:249-259); returns zs[i] or zs[0] when there is no such gap
+template <class Load>
+__device__ __forceinline__ float gap_scan(Load zs, std::uint32_t n)
 {
-    __shared__ std::uint32_t sh[kCellWarps][kCellSmem];
-    const std::uint32_t f = blockIdx.y;
-    const std::uint32_t warp = threadIdx.x >> 5;
-    // consecutive cells are radial neighbours of one slice (dense near the sensor, empty far out):
-    // interleaving them over the warps keeps the warps of a CTA equally loaded
-    const std::uint32_t first = blockIdx.x * (kCellWarps * kCellsPerWarp) + warp;
-    for (std::uint32_t j = 0; j < kCellsPerWarp; ++j)
+    const std::uint32_t lane = lane_id();
+    float zmin = zs(0);
+    for (std::uint32_t hi = n / 2; hi >= 1;)
     {
-        const std::uint32_t cell = first + j * kCellWarps;
-        if (cell < static_cast<std::uint32_t>(sp.ncell))
+        const bool valid = hi > lane;
+        const std::uint32_t i = hi - lane;
+        const bool hit = valid && (zs(i) - zs(i - 1) > 0.5f);
+        const std::uint32_t m = __ballot_sync(0xffffffffu, hit);
+        if (m != 0)
         {
-            seg_cell_one(d, sp, f, cell, sh[warp]);
+            zmin = zs(hi - (__ffs(m) - 1));
+            break;
         }
-        __syncwarp();
+        if (hi <= 32)
+        {
+            break;
+        }
+        hi -= 32;
     }
+    return zmin;
+}
+
+// E values per lane sorted in registers, then the gap scan over shared memory
+template <int E>
+__device__ __forceinline__ float cell_zmin_regs(const uint2* zo, std::uint32_t n, float* zb)
+{
+    const std::uint32_t lane = lane_id();
+    float z[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+    {
+        const std::uint32_t t = e * 32 + lane;
+        z[e] = t < n ? __uint_as_float(zo[t].y) : 3.402823466e+38f;
+    }
+    warp_sort_regs<E>(z);
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+    {
+        zb[e * 32 + lane] = z[e];
+    }
+    __syncwarp();
+    const float r = gap_scan([&](std::uint32_t i) { return zb[i]; }, n);
+    __syncwarp();
+    return r;
 }
 
 __device__ __forceinline__ void seg_cell_one(const Dev& d, const SegParams& sp, std::uint32_t f, std::uint32_t cell,
-                                             std::uint32_t* buf)
+                                             std::uint32_t a, std::uint32_t n, float* zb)
 {
-    const std::uint32_t* cs = d.cell_start + static_cast<std::size_t>(f) * (sp.ncell + 1);
-    const std::uint32_t a = cs[cell], n = cs[cell + 1] - a;
-    if (n == 0)
-    {
-        return;
-    }
     const std::size_t o = static_cast<std::size_t>(f) * d.cap;
-    std::uint32_t* ord = d.order + o + a;
-    const float4* pts = d.pts_v + o;
+    const uint2* zo = d.zo + o + a;
     float zmin;
-    std::uint32_t best = 0; // largest i in [1, n/2] with z[i] - z[i-1] > 0.5, 0 = none
     if (n <= 32)
     {
-        // the common case: one point per lane, both sorts are shuffle-only bitonic networks
+        // the common case: one height per lane, shuffle-only bitonic network
         const std::uint32_t lane = lane_id();
-        std::uint32_t v = lane < n ? ord[lane] : 0xffffffffu;
-#pragma unroll
-        for (std::uint32_t k = 2; k <= 32; k <<= 1)
-        {
-#pragma unroll
-            for (std::uint32_t j = k >> 1; j > 0; j >>= 1)
-            {
-                const std::uint32_t other = __shfl_xor_sync(0xffffffffu, v, j);
-                const bool take_min = ((lane & j) == 0) == ((lane & k) == 0);
-                v = take_min ? min(v, other) : max(v, other);
-            }
-        }
-        float z = 3.402823466e+38f;
-        if (lane < n)
-        {
-            ord[lane] = v;
-            z = pts[v].z;
-        }
+        float z = lane < n ? __uint_as_float(zo[lane].y) : 3.402823466e+38f;
 #pragma unroll
         for (std::uint32_t k = 2; k <= 32; k <<= 1)
         {
@@ -277,121 +305,37 @@ __device__ __forceinline__ void seg_cell_one(const Dev& d, const SegParams& sp, 
         const int src_lane = m != 0 ? 31 - __clz(m) : 0;
         zmin = __shfl_sync(0xffffffffu, z, src_lane);
     }
+    else if (n <= 64)
+    {
+        zmin = cell_zmin_regs<2>(zo, n, zb);
+    }
     else if (n <= 128)
     {
-        // four values per lane in registers; the sorted heights go through shared memory only for
-        // the gap scan
-        const std::uint32_t lane = lane_id();
-        std::uint32_t v[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-        {
-            const std::uint32_t t = e * 32 + lane;
-            v[e] = t < n ? ord[t] : 0xffffffffu;
-        }
-        warp_sort_regs<4>(v);
-        float z[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-        {
-            const std::uint32_t t = e * 32 + lane;
-            z[e] = 3.402823466e+38f;
-            if (t < n)
-            {
-                ord[t] = v[e];
-                z[e] = pts[v[e]].z;
-            }
-        }
-        warp_sort_regs<4>(z);
-        float* zb = reinterpret_cast<float*>(buf);
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-        {
-            zb[e * 32 + lane] = z[e];
-        }
-        __syncwarp();
-        zmin = zb[0];
-        for (std::uint32_t hi = n / 2; hi >= 1 && best == 0;)
-        {
-            const bool valid = hi > lane;
-            const std::uint32_t i = hi - lane;
-            const bool hit = valid && (zb[i] - zb[i - 1] > 0.5f);
-            const std::uint32_t m = __ballot_sync(0xffffffffu, hit);
-            if (m != 0)
-            {
-                best = hi - (__ffs(m) - 1);
-                zmin = zb[best];
-            }
-            if (hi <= 32)
-            {
-                break;
-            }
-            hi -= 32;
-        }
-        __syncwarp();
+        zmin = cell_zmin_regs<4>(zo, n, zb);
+    }
+    else if (n <= 256)
+    {
+        zmin = cell_zmin_regs<8>(zo, n, zb);
     }
     else if (n <= kCellSmem)
     {
         for (std::uint32_t t = lane_id(); t < n; t += 32)
         {
-            buf[t] = ord[t];
-        }
-        __syncwarp();
-        warp_sort(buf, n);
-        float* zb = reinterpret_cast<float*>(buf);
-        for (std::uint32_t t = lane_id(); t < n; t += 32)
-        {
-            const std::uint32_t idx = buf[t];
-            ord[t] = idx;
-            zb[t] = pts[idx].z; // same thread, same slot: no hazard
+            zb[t] = __uint_as_float(zo[t].y);
         }
         __syncwarp();
         warp_sort(zb, n);
-        zmin = zb[0];
-        for (std::uint32_t hi = n / 2; hi >= 1 && best == 0;)
-        {
-            // lanes test i = hi - lane
-            const bool valid = hi > lane_id();
-            const std::uint32_t i = hi - lane_id();
-            const bool hit = valid && (zb[i] - zb[i - 1] > 0.5f);
-            const std::uint32_t m = __ballot_sync(0xffffffffu, hit);
-            if (m != 0)
-            {
-                best = hi - (__ffs(m) - 1);
-                zmin = zb[best];
-            }
-            if (hi <= 32)
-            {
-                break;
-            }
-            hi -= 32;
-        }
+        zmin = gap_scan([&](std::uint32_t i) { return zb[i]; }, n);
+        __syncwarp();
     }
     else
     {
-        // oversized cell: rank sort through global scratch (slot[] and zsort[] are free here)
-        std::uint32_t* tmp = d.slot + o + a;
-        float* zs = d.zsort + o + a;
+        // oversized cell: rank sort through global scratch
+        float* zt = d.zsort + o + a;
+        float* zs = d.zsort2 + o + a;
         for (std::uint32_t t = lane_id(); t < n; t += 32)
         {
-            const std::uint32_t v = ord[t];
-            std::uint32_t r = 0;
-            for (std::uint32_t u = 0; u < n; ++u)
-            {
-                r += (ord[u] < v) ? 1u : 0u;
-            }
-            tmp[r] = v;
-        }
-        __syncwarp();
-        for (std::uint32_t t = lane_id(); t < n; t += 32)
-        {
-            ord[t] = tmp[t];
-        }
-        __syncwarp();
-        float* zt = reinterpret_cast<float*>(tmp);
-        for (std::uint32_t t = lane_id(); t < n; t += 32)
-        {
-            zt[t] = pts[ord[t]].z;
+            zt[t] = __uint_as_float(zo[t].y);
         }
         __syncwarp();
         for (std::uint32_t t = lane_id(); t < n; t += 32)
@@ -406,28 +350,42 @@ __device__ __forceinline__ void seg_cell_one(const Dev& d, const SegParams& sp, 
             zs[r] = v;
         }
         __syncwarp();
-        zmin = zs[0];
-        for (std::uint32_t hi = n / 2; hi >= 1 && best == 0;)
-        {
-            const bool valid = hi > lane_id();
-            const std::uint32_t i = hi - lane_id();
-            const bool hit = valid && (zs[i] - zs[i - 1] > 0.5f);
-            const std::uint32_t m = __ballot_sync(0xffffffffu, hit);
-            if (m != 0)
-            {
-                best = hi - (__ffs(m) - 1);
-                zmin = zs[best];
-            }
-            if (hi <= 32)
-            {
-                break;
-            }
-            hi -= 32;
-        }
+        zmin = gap_scan([&](std::uint32_t i) { return zs[i]; }, n);
     }
     if (lane_id() == 0)
     {
         d.cell_zmin[static_cast<std::size_t>(f) * sp.ncell + cell] = zmin;
+    }
+}
+
+__global__ void __launch_bounds__(kCellWarps * 32) k_seg_cell(Dev d, SegParams sp)
+{
+    __shared__ float sh[kCellWarps][kCellSmem];
+    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t warp = threadIdx.x >> 5;
+    // consecutive cells are radial neighbours of one slice (dense near the sensor, empty far out):
+    // interleaving them over the warps keeps the warps of a CTA equally loaded. Lane j fetches the
+    // bounds of the warp's j-th cell up front, so empty cells cost no dependent load.
+    const std::uint32_t first = blockIdx.x * (kCellWarps * kCellsPerWarp) + warp;
+    const std::uint32_t* cs = d.cell_start + static_cast<std::size_t>(f) * (sp.ncell + 1);
+    std::uint32_t my_a = 0, my_n = 0;
+    {
+        const std::uint32_t cell = first + lane_id() * kCellWarps;
+        if (lane_id() < kCellsPerWarp && cell < static_cast<std::uint32_t>(sp.ncell))
+        {
+            my_a = cs[cell];
+            my_n = cs[cell + 1] - my_a;
+        }
+    }
+#pragma unroll 1
+    for (std::uint32_t j = 0; j < kCellsPerWarp; ++j)
+    {
+        const std::uint32_t a = __shfl_sync(0xffffffffu, my_a, j);
+        const std::uint32_t n = __shfl_sync(0xffffffffu, my_n, j);
+        if (n != 0)
+        {
+            seg_cell_one(d, sp, f, first + j * kCellWarps, a, n, sh[warp]);
+        }
     }
 }
 
@@ -459,54 +417,46 @@ __global__ void __launch_bounds__(128) k_seg_elev(Dev d, SegParams sp)
     }
 }
 
-// obstacle classification by sorted position (segmenter.cpp:271-283)
-__global__ void __launch_bounds__(256) k_seg_label(Dev d, SegParams sp, const std::uint32_t* n_binned)
+// obstacle classification (segmenter.cpp:271-283) and RANSAC candidate flags (:328-351), per point
+// of the segmented cloud. lab bit 7 marks a candidate; candidates are counted per cell.
+__global__ void __launch_bounds__(256) k_seg_label(Dev d, SegParams sp)
 {
     const std::uint32_t f = blockIdx.y;
-    const std::uint32_t nb = n_binned[f];
-    const std::uint32_t k = blockIdx.x * 256u + threadIdx.x;
-    if (k >= nb)
+    const std::uint32_t n = d.n_v[f];
+    if (blockIdx.x * 256u >= n)
     {
         return;
     }
+    const std::uint32_t i = blockIdx.x * 256u + threadIdx.x;
     const std::size_t o = static_cast<std::size_t>(f) * d.cap;
-    const std::uint32_t i = d.order[o + k];
-    const float z = d.pts_v[o + i].z;
-    const float e = d.elev[static_cast<std::size_t>(f) * sp.ncell + d.cell[o + i]];
-    d.lab[o + k] = (z >= e + sp.thr) ? PX_OBSTACLE : PX_GROUND;
+    std::int32_t ccell = -1; // cell of a candidate, -1 otherwise
+    if (i < n)
+    {
+        const std::int32_t c = d.cell[o + i];
+        std::uint8_t l = 0;
+        if (c >= 0)
+        {
+            const float z = d.pts_v[o + i].z;
+            const float e = d.elev[static_cast<std::size_t>(f) * sp.ncell + c];
+            l = (z >= e + sp.thr) ? PX_OBSTACLE : PX_GROUND;
+            if ((c % sp.rings) < kRansacBins && fabsf(e - z) < sp.thr2)
+            {
+                l |= 0x80;
+                ccell = c;
+            }
+        }
+        d.lab[o + i] = l;
+    }
+    const std::uint32_t peers = __match_any_sync(0xffffffffu, ccell);
+    if (ccell >= 0 && static_cast<int>(lane_id()) == __ffs(peers) - 1)
+    {
+        atomicAdd(&d.ccnt[static_cast<std::size_t>(f) * sp.ncell + ccell], __popc(peers));
+    }
 }
 
 // ------------------------------------------------------------------------------------------
 // near-field RANSAC (segmenter.cpp:321-479)
 // ------------------------------------------------------------------------------------------
-struct CandPred
-{
-    Dev d;
-    SegParams sp;
-    __device__ bool operator()(std::uint32_t f, std::uint32_t k) const
-    {
-        const std::size_t o = static_cast<std::size_t>(f) * d.cap;
-        const std::uint32_t i = d.order[o + k];
-        const std::int32_t c = d.cell[o + i];
-        if ((c % sp.rings) >= kRansacBins)
-        {
-            return false;
-        }
-        const float e = d.elev[static_cast<std::size_t>(f) * sp.ncell + c];
-        return fabsf(e - d.pts_v[o + i].z) < sp.thr2;
-    }
-};
-
-struct CandEmit
-{
-    std::uint32_t* cand;
-    std::uint32_t cap;
-    __device__ void operator()(std::uint32_t f, std::uint32_t k, std::uint32_t pos) const
-    {
-        cand[static_cast<std::size_t>(f) * cap + pos] = k;
-    }
-};
-
 // std::mt19937{42} raw outputs are frame independent (pre-generated on the host); libstdc++'s
 // uniform_int_distribution<uint32_t>{0, n-1} maps them with Lemire's multiply-shift + rejection.
 __device__ __forceinline__ std::uint32_t mt_draw(const std::uint32_t* raw, std::uint32_t& pos,
@@ -534,15 +484,51 @@ __device__ __forceinline__ std::uint32_t mt_draw(const std::uint32_t* raw, std::
     return static_cast<std::uint32_t>(product >> 32);
 }
 
-__global__ void __launch_bounds__(64) k_ransac_setup(Dev d, SegParams sp)
+constexpr int kSetupThreads = 256;
+constexpr int kSetupWarps = kSetupThreads / 32;
+constexpr int kSelCap = 1024; // candidate indices of one cell staged per warp
+
+// The reference numbers its candidates in (slice, bin, cloud) order and draws 60 index pairs.
+// Only those <= 120 candidates are ever looked at by position, so instead of materialising the
+// ordered list the draws are resolved by rank: an exclusive prefix of the per-cell candidate
+// counts (cells in index order, bins 0..3 only) locates the cell of rank t, and a radix select
+// over the point indices of that cell's candidates finds the (t - prefix)-th in cloud order.
+__global__ void __launch_bounds__(kSetupThreads) k_ransac_setup(Dev d, SegParams sp)
 {
     __shared__ std::uint32_t pair[kRansacIters][2];
+    __shared__ std::uint32_t pidx[kRansacIters][2]; // drawn point indices
+    __shared__ std::uint32_t sel[kSetupWarps][kSelCap];
+    __shared__ std::uint32_t sh[33];
     const std::uint32_t f = blockIdx.x;
-    const std::uint32_t nc = d.n_cand[f];
+    const std::uint32_t J = static_cast<std::uint32_t>(sp.slices) * sp.nb; // candidate cells in rank order
+    std::uint32_t* ccnt = d.ccnt + static_cast<std::size_t>(f) * sp.ncell;
+    auto cell_of = [&](std::uint32_t j) -> std::uint32_t { return (j / sp.nb) * sp.rings + (j % sp.nb); };
+    // in-place exclusive prefix over the J candidate cells, a contiguous chunk per thread
+    const std::uint32_t chunk = (J + kSetupThreads - 1) / kSetupThreads;
+    const std::uint32_t j0 = min(threadIdx.x * chunk, J), j1 = min(j0 + chunk, J);
+    std::uint32_t part = 0;
+    for (std::uint32_t j = j0; j < j1; ++j)
+    {
+        part += ccnt[cell_of(j)];
+    }
+    std::uint32_t total;
+    std::uint32_t run = block_excl_scan(part, sh, &total);
+    for (std::uint32_t j = j0; j < j1; ++j)
+    {
+        const std::uint32_t c = cell_of(j);
+        const std::uint32_t v = ccnt[c];
+        ccnt[c] = run;
+        run += v;
+    }
+    const std::uint32_t nc = total;
+    if (threadIdx.x == 0)
+    {
+        d.n_cand[f] = nc;
+    }
     // a single candidate makes the reference spin forever (segmenter.cpp:382-386); RANSAC is
     // skipped for nc < 2 (documented deviation).
-    const bool run = nc >= 2;
-    if (threadIdx.x == 0 && run)
+    const bool runit = nc >= 2;
+    if (threadIdx.x == 0 && runit)
     {
         std::uint32_t pos = 0;
         bool exhausted = false;
@@ -562,6 +548,104 @@ __global__ void __launch_bounds__(64) k_ransac_setup(Dev d, SegParams sp)
             atomicOr(&d.status[f], ST_RNG_EXHAUSTED);
         }
     }
+    __syncthreads(); // prefix (global, this CTA only) and draws visible
+    const std::size_t o = static_cast<std::size_t>(f) * d.cap;
+    const std::uint32_t* cs = d.cell_start + static_cast<std::size_t>(f) * (sp.ncell + 1);
+    if (runit)
+    {
+        const std::uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+        std::uint32_t* mine = sel[warp];
+        for (std::uint32_t q = warp; q < 2u * kRansacIters; q += kSetupWarps)
+        {
+            const std::uint32_t t = pair[q >> 1][q & 1u];
+            // last candidate cell j with prefix[j] <= t (cells without candidates repeat the prefix)
+            std::uint32_t lo = 0, hi = J;
+            while (hi - lo > 1)
+            {
+                const std::uint32_t mid = (lo + hi) >> 1;
+                if (ccnt[cell_of(mid)] <= t)
+                {
+                    lo = mid;
+                }
+                else
+                {
+                    hi = mid;
+                }
+            }
+            const std::uint32_t c = cell_of(lo);
+            std::uint32_t r = t - ccnt[c]; // rank inside the cell, cloud order
+            const std::uint32_t a = cs[c], n = cs[c + 1] - a;
+            const uint2* zo = d.zo + o + a;
+            // stage the candidates' point indices
+            std::uint32_t m = 0;
+            for (std::uint32_t base = 0; base < n; base += 32)
+            {
+                const std::uint32_t u = base + lane;
+                std::uint32_t idx = 0;
+                bool is = false;
+                if (u < n)
+                {
+                    idx = zo[u].x;
+                    is = (d.lab[o + idx] & 0x80) != 0;
+                }
+                const std::uint32_t b = __ballot_sync(0xffffffffu, is);
+                const std::uint32_t w = m + __popc(b & ((1u << lane) - 1u));
+                if (is && w < kSelCap)
+                {
+                    mine[w] = idx;
+                }
+                m += __popc(b);
+            }
+            __syncwarp();
+            std::uint32_t prefix = 0;
+            if (m <= kSelCap)
+            {
+                for (int bit = sp.idx_bits - 1; bit >= 0; --bit)
+                {
+                    std::uint32_t cnt0 = 0;
+                    for (std::uint32_t u = lane; u < m; u += 32)
+                    {
+                        const std::uint32_t v = mine[u];
+                        cnt0 += ((v >> (bit + 1)) == (prefix >> (bit + 1)) && ((v >> bit) & 1u) == 0u) ? 1u : 0u;
+                    }
+                    cnt0 = warp_sum(cnt0);
+                    if (r >= cnt0)
+                    {
+                        r -= cnt0;
+                        prefix |= 1u << bit;
+                    }
+                }
+            }
+            else
+            {
+                // more candidates in one cell than the staging holds: select straight from memory
+                for (int bit = sp.idx_bits - 1; bit >= 0; --bit)
+                {
+                    std::uint32_t cnt0 = 0;
+                    for (std::uint32_t u = lane; u < n; u += 32)
+                    {
+                        const std::uint32_t v = zo[u].x;
+                        if ((d.lab[o + v] & 0x80) != 0 && (v >> (bit + 1)) == (prefix >> (bit + 1)) &&
+                            ((v >> bit) & 1u) == 0u)
+                        {
+                            cnt0 += 1;
+                        }
+                    }
+                    cnt0 = warp_sum(cnt0);
+                    if (r >= cnt0)
+                    {
+                        r -= cnt0;
+                        prefix |= 1u << bit;
+                    }
+                }
+            }
+            if (lane == 0)
+            {
+                pidx[q >> 1][q & 1u] = prefix;
+            }
+            __syncwarp();
+        }
+    }
     __syncthreads();
     const int it = threadIdx.x;
     if (it >= kRansacIters)
@@ -569,11 +653,10 @@ __global__ void __launch_bounds__(64) k_ransac_setup(Dev d, SegParams sp)
         return;
     }
     float4 plane = make_float4(0.f, 0.f, __int_as_float(0x7fc00000), 0.f); // skipped
-    if (run)
+    if (runit)
     {
-        const std::size_t o = static_cast<std::size_t>(f) * d.cap;
-        const float4 p2 = d.pts_v[o + d.order[o + d.cand[o + pair[it][0]]]];
-        const float4 p3 = d.pts_v[o + d.order[o + d.cand[o + pair[it][1]]]];
+        const float4 p2 = d.pts_v[o + pidx[it][0]];
+        const float4 p3 = d.pts_v[o + pidx[it][1]];
         const float p1x = 0.0f, p1y = 0.0f, p1z = sp.p1z;
         float nx = ((p2.y - p1y) * (p3.z - p1z)) - ((p2.z - p1z) * (p3.y - p1y));
         float ny = ((p2.z - p1z) * (p3.x - p1x)) - ((p2.x - p1x) * (p3.z - p1z));
@@ -601,10 +684,17 @@ __global__ void __launch_bounds__(256) k_ransac_count(Dev d, SegParams sp)
     __shared__ float4 pl[kRansacIters];
     __shared__ std::uint32_t cnt[kRansacIters];
     const std::uint32_t f = blockIdx.y;
-    const std::uint32_t nc = d.n_cand[f];
-    if (nc < 2 || blockIdx.x * 256u >= nc)
+    const std::uint32_t n = d.n_v[f];
+    if (d.n_cand[f] < 2 || blockIdx.x * 256u >= n)
     {
         return;
+    }
+    const std::uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    const std::size_t o = static_cast<std::size_t>(f) * d.cap;
+    const bool live = i < n && (d.lab[o + i] & 0x80) != 0;
+    if (__syncthreads_or(live) == 0)
+    {
+        return; // no candidate among this CTA's points
     }
     if (threadIdx.x < kRansacIters)
     {
@@ -612,27 +702,27 @@ __global__ void __launch_bounds__(256) k_ransac_count(Dev d, SegParams sp)
         cnt[threadIdx.x] = 0;
     }
     __syncthreads();
-    const std::uint32_t k = blockIdx.x * 256u + threadIdx.x;
-    const std::size_t o = static_cast<std::size_t>(f) * d.cap;
     float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-    const bool live = k < nc;
     if (live)
     {
-        p = d.pts_v[o + d.order[o + d.cand[o + k]]];
+        p = d.pts_v[o + i];
     }
-#pragma unroll 4
-    for (int it = 0; it < kRansacIters; ++it)
+    if (__any_sync(0xffffffffu, live))
     {
-        const float4 q = pl[it];
-        if (q.z != q.z)
+#pragma unroll 4
+        for (int it = 0; it < kRansacIters; ++it)
         {
-            continue; // skipped draw (uniform branch)
-        }
-        const float od = fabsf((q.x * p.x) + (q.y * p.y) + (q.z * p.z) - q.w);
-        const std::uint32_t m = __ballot_sync(0xffffffffu, live && od < sp.thr);
-        if (lane_id() == 0 && m != 0)
-        {
-            atomicAdd(&cnt[it], __popc(m));
+            const float4 q = pl[it];
+            if (q.z != q.z)
+            {
+                continue; // skipped draw (uniform branch)
+            }
+            const float od = fabsf((q.x * p.x) + (q.y * p.y) + (q.z * p.z) - q.w);
+            const std::uint32_t m = __ballot_sync(0xffffffffu, live && od < sp.thr);
+            if (lane_id() == 0 && m != 0)
+            {
+                atomicAdd(&cnt[it], __popc(m));
+            }
         }
     }
     __syncthreads();
@@ -644,14 +734,18 @@ __global__ void __launch_bounds__(256) k_ransac_count(Dev d, SegParams sp)
 
 // ------------------------------------------------------------------------------------------
 // plane application + range-image scatter (segmenter.cpp:434-477, 291-318)
+// The reference walks cells in index order and the points of a cell in cloud order and replaces a
+// pixel only on a strictly smaller depth^2, so among equal depths the first in (cell, cloud) order
+// wins. Equal depth^2 means equal radial bin, hence cell order = azimuth-slice order: the key
+// (depth^2 bits, slice, point index) under atomicMin reproduces the winner without any sorted list.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_seg_image(Dev d, SegParams sp, const std::uint32_t* n_binned)
+__global__ void __launch_bounds__(256) k_seg_image(Dev d, SegParams sp)
 {
     __shared__ float4 s_plane;
     __shared__ int s_have;
     const std::uint32_t f = blockIdx.y;
-    const std::uint32_t nb = n_binned[f];
-    if (blockIdx.x * 256u >= nb)
+    const std::uint32_t n = d.n_v[f];
+    if (blockIdx.x * 256u >= n)
     {
         return;
     }
@@ -689,28 +783,33 @@ __global__ void __launch_bounds__(256) k_seg_image(Dev d, SegParams sp, const st
         }
     }
     __syncthreads();
-    const std::uint32_t k = blockIdx.x * 256u + threadIdx.x;
-    if (k >= nb)
+    const std::uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    if (i >= n)
     {
         return;
     }
     const std::size_t o = static_cast<std::size_t>(f) * d.cap;
-    const std::uint32_t i = d.order[o + k];
+    const std::int32_t c = d.cell[o + i];
+    if (c < 0)
+    {
+        return;
+    }
     const float4 p = d.pts_v[o + i];
-    std::uint8_t l = d.lab[o + k];
-    if (s_have && (d.cell[o + i] % sp.rings) < kRansacBins)
+    std::uint8_t l = d.lab[o + i] & 0x7f;
+    if (s_have && (c % sp.rings) < kRansacBins)
     {
         const float4 pl = s_plane;
         const float sd = (pl.x * p.x) + (pl.y * p.y) + (pl.z * p.z) - pl.w;
         if (sd < sp.thr)
         {
             l = PX_GROUND;
-            d.lab[o + k] = l;
         }
     }
+    d.lab[o + i] = l;
     const float d2 = (p.x * p.x) + (p.y * p.y);
-    const unsigned long long key =
-        (static_cast<unsigned long long>(__float_as_uint(d2)) << 32) | static_cast<unsigned long long>(k);
+    const unsigned long long key = (static_cast<unsigned long long>(__float_as_uint(d2)) << 33) |
+                                   (static_cast<unsigned long long>(c / sp.rings) << sp.idx_bits) |
+                                   static_cast<unsigned long long>(i);
     atomicMin(&d.key[static_cast<std::size_t>(f) * sp.npx + d.px[o + i]], key);
 }
 
@@ -729,11 +828,10 @@ __global__ void __launch_bounds__(256) k_seg_px(Dev d, SegParams sp)
     if (key != ~0ULL)
     {
         const std::size_t o = static_cast<std::size_t>(f) * d.cap;
-        const std::uint32_t k = static_cast<std::uint32_t>(key & 0xffffffffULL);
-        const std::uint32_t i = d.order[o + k];
+        const std::uint32_t i = static_cast<std::uint32_t>(key & ((1ULL << sp.idx_bits) - 1ULL));
         const float4 q = d.pts_v[o + i];
         v = make_float4(q.x, q.y, q.z, __int_as_float(static_cast<int>(i)));
-        c = d.lab[o + k];
+        c = d.lab[o + i];
     }
     d.pxpt[po + p] = v;
     d.code[po + p] = c;
@@ -1227,6 +1325,7 @@ void launch_segment(Ctx* c, std::uint32_t nf, bool want_image)
     cudaStream_t s = c->stream;
     // per-batch resets
     cudaMemsetAsync(d.cell_cnt, 0, sizeof(std::uint32_t) * sp.ncell * nf, s);
+    cudaMemsetAsync(d.ccnt, 0, sizeof(std::uint32_t) * sp.ncell * nf, s);
     cudaMemsetAsync(d.key, 0xff, sizeof(unsigned long long) * sp.npx * nf, s);
     cudaMemsetAsync(d.seg_label, 0, static_cast<std::size_t>(d.cap) * nf, s);
     cudaMemsetAsync(d.labels_out, 0, static_cast<std::size_t>(d.cap) * nf, s);
@@ -1244,16 +1343,13 @@ void launch_segment(Ctx* c, std::uint32_t nf, bool want_image)
     mark(c, "seg_cell");
     k_seg_elev<<<dim3((sp.slices + 127) / 128, nf), 128, 0, s>>>(d, sp);
     mark(c, "seg_elev");
-    const std::uint32_t* n_binned = d.n_binned;
-    k_seg_label<<<gpts, 256, 0, s>>>(d, sp, n_binned);
+    k_seg_label<<<gpts, 256, 0, s>>>(d, sp);
     mark(c, "seg_label");
-    launch_compact(c, "ransac_cand", nf, d.tiles, n_binned, 0u, d.tile_cnt, d.n_cand, CandPred{d, sp},
-                   CandEmit{d.cand, d.cap});
-    k_ransac_setup<<<nf, 64, 0, s>>>(d, sp);
+    k_ransac_setup<<<nf, kSetupThreads, 0, s>>>(d, sp);
     mark(c, "ransac_setup");
     k_ransac_count<<<gpts, 256, 0, s>>>(d, sp);
     mark(c, "ransac_count");
-    k_seg_image<<<gpts, 256, 0, s>>>(d, sp, n_binned);
+    k_seg_image<<<gpts, 256, 0, s>>>(d, sp);
     mark(c, "seg_image");
     k_seg_px<<<dim3((sp.npx + 255) / 256, nf), 256, 0, s>>>(d, sp);
     mark(c, "seg_px");
