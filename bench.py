@@ -394,7 +394,7 @@ def run_ours(args, rank, local_rank, world):
         "points_per_s": world * total_pts * args.steps / (ms_max * 1e-3),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
-                "pipelining": "2 contexts double-buffered, pinned host memory"},
+                "pipelining": f"{args.e2e_parts} part-batches per step over {args.e2e_ctx} contexts (streams) in rotation, pinned host memory"},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "kernels": [{k: (round(v, 6) if isinstance(v, float) else v) for k, v in kk.items()} for kk in kernels[:12]],
@@ -411,14 +411,15 @@ def run_ours(args, rank, local_rank, world):
 
 def run_e2e(lpl, ctx0, frames, device, args, barrier, stages):
     """Upload (pinned host -> device) + run + batch download through the package's FramePipeline
-    (two contexts / CUDA streams working on alternating half batches)."""
+    (args.e2e_ctx contexts / CUDA streams rotating over args.e2e_parts part-batches of the step)."""
     from lidar_processing_v2_b200.stream import FramePipeline
 
     nf = len(frames)
     max_pts = max(f.shape[0] for f in frames)
-    half = (nf + 1) // 2
-    pipe = FramePipeline(device, max_pts, half, stages=stages)
-    parts = [frames[:half], frames[half:]]
+    n_parts, n_ctx = args.e2e_parts, args.e2e_ctx
+    per = (nf + n_parts - 1) // n_parts
+    pipe = FramePipeline(device, max_pts, per, stages=stages, n_ctx=n_ctx)
+    parts = [frames[a:a + per] for a in range(0, nf, per)]
     pinned, views = [], []
     for part in parts:
         buf = lpl.PinnedBuffer((sum(f.shape[0] for f in part), 4), np.float32)
@@ -432,7 +433,7 @@ def run_e2e(lpl, ctx0, frames, device, args, barrier, stages):
 
     def run_steps(k):
         for _ in range(k):
-            for i in (0, 1):
+            for i in range(len(views)):
                 pipe.submit(views[i])  # returns (and thereby downloads) the batch this slot held before
         pipe.drain()
 
@@ -477,6 +478,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=None, help="frames per batch (default: the whole sequence)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--e2e-parts", type=int, default=1, help="part-batches one step is split into on the e2e path")
+    ap.add_argument("--e2e-ctx", type=int, default=4, help="contexts (CUDA streams) the e2e path rotates over")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

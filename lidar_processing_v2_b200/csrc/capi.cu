@@ -56,6 +56,7 @@ void carve(Dev& d, Carver& cv, int npx, int ncell_cap, std::uint32_t** mt_raw)
     cv.take(d.noise, B * cap);
     cv.take(d.grid_cnt, B * kDrorCells);
     cv.take(d.grid_start, B * (kDrorCells + 1));
+    cv.take(d.grid_mask, B * (kDrorCells / 32));
     cv.take(d.grid_pts, B * cap);
     cv.take(d.unres, B * cap);
     cv.take(d.n_unres, B);
@@ -70,12 +71,14 @@ void carve(Dev& d, Carver& cv, int npx, int ncell_cap, std::uint32_t** mt_raw)
     cv.take(d.n_binned, B);
     cv.take(d.zo, B * cap);
     cv.take(d.zsort, B * cap);
-    cv.take(d.zsort2, B * cap);
     cv.take(d.ccnt, B * ncell_cap);
     cv.take(d.cell_zmin, B * ncell_cap);
     cv.take(d.elev, B * ncell_cap);
     cv.take(d.lab, B * cap);
     cv.take(d.n_cand, B);
+    cv.take(d.cpts, B * cap);
+    cv.take(d.n_cpts, B);
+    cv.take(d.pairs, B * kRansacIters * 2);
     cv.take(d.planes, B * kRansacIters);
     cv.take(d.inliers, B * kRansacIters);
     cv.take(d.best_plane, B);
@@ -105,6 +108,7 @@ void carve(Dev& d, Carver& cv, int npx, int ncell_cap, std::uint32_t** mt_raw)
     cv.take(d.hmin, B * h);
     cv.take(d.hcount, B * h);
     cv.take(d.hlabel, B * h);
+    cv.take(d.hroot, B * h);
     cv.take(d.vslot, B * cap);
     cv.take(d.vlist, B * cap);
     cv.take(d.n_vox, B);
@@ -314,14 +318,17 @@ __global__ void k_label_count(Dev d, std::uint32_t K)
     }
     const std::size_t o = static_cast<std::size_t>(f) * d.cap;
     std::int32_t l = -1;
-    float z = 0.f;
+    float x = 0.f, y = 0.f, z = 0.f;
     if (i < n)
     {
         l = d.clabel[o + i];
         if (l >= 0 && static_cast<std::uint32_t>(l) < K)
         {
             atomicAdd(&d.ccount[o + l], 1u);
-            z = d.pts_o[o + i].z;
+            const float4 p = d.pts_o[o + i];
+            x = p.x;
+            y = p.y;
+            z = p.z;
         }
         else
         {
@@ -329,12 +336,7 @@ __global__ void k_label_count(Dev d, std::uint32_t K)
             d.clabel[o + i] = -1;
         }
     }
-    accumulate_zext(d.zmin_u + o, d.zmax_u + o, l, z);
-    if (i < n && l >= 0)
-    {
-        const float4 p = d.pts_o[o + i];
-        accumulate_extremes(d.ext + o * 8, l, p.x, p.y, i);
-    }
+    accumulate_cluster_stats(d.ext + o * 8, d.zmin_u + o, d.zmax_u + o, l, x, y, z, i);
 }
 
 __global__ void k_ext_init(Dev d, std::uint32_t K)

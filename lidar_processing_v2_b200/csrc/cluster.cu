@@ -125,47 +125,88 @@ __global__ void __launch_bounds__(256) k_clu_insert(Dev d, ClusterParams cp)
 {
     const std::uint32_t f = blockIdx.y;
     const std::uint32_t n = d.n_o[f];
-    const std::uint32_t i = blockIdx.x * 256u + threadIdx.x;
-    if (i >= n)
+    if (blockIdx.x * 256u >= n)
     {
         return;
     }
-    const VoxelDims vd = voxel_dims(d, cp, f);
+    const std::uint32_t i = blockIdx.x * 256u + threadIdx.x;
     const std::size_t o = static_cast<std::size_t>(f) * d.cap;
-    const float4 s = d.sph[o + i];
-    const std::int32_t ri = static_cast<std::int32_t>(s.x / cp.range_res);
-    const std::int32_t ai = static_cast<std::int32_t>(s.y / cp.az_res);
-    const std::int32_t ei = static_cast<std::int32_t>(s.z / cp.el_res);
-    const std::int32_t flat = vd.nr * (vd.na * ei + ai) + ri; // clusterer.hpp:136-142
-    const std::uint32_t slots = voxel_slots(d, f);
-    std::int32_t* keys = d.hkey + static_cast<std::size_t>(f) * d.hcap;
-    const std::uint32_t home = voxel_home(flat, slots);
-    std::uint32_t slot = 0xffffffffu;
-    for (std::uint32_t t = 0; t < slots / 8u + slots; ++t)
+    std::int32_t flat = -1;
+    if (i < n)
     {
-        const std::uint32_t h = voxel_probe(home, t, slots);
-        const std::int32_t prev = atomicCAS(&keys[h], -1, flat);
-        if (prev == -1 || prev == flat)
-        {
-            slot = h;
-            if (prev == -1)
-            {
-                // this thread created the voxel: list it for the neighbour pass
-                d.vlist[o + atomicAdd(&d.n_vox[f], 1u)] = h;
-            }
-            break;
-        }
+        const VoxelDims vd = voxel_dims(d, cp, f);
+        const float4 s = d.sph[o + i];
+        const std::int32_t ri = static_cast<std::int32_t>(s.x / cp.range_res);
+        const std::int32_t ai = static_cast<std::int32_t>(s.y / cp.az_res);
+        const std::int32_t ei = static_cast<std::int32_t>(s.z / cp.el_res);
+        flat = vd.nr * (vd.na * ei + ai) + ri; // clusterer.hpp:136-142
     }
-    if (slot == 0xffffffffu)
+    // neighbours along a scan line mostly share a voxel: the lowest lane of every group of equal
+    // keys inserts for the group (it also carries the group's smallest point index)
+    const std::uint32_t peers = __match_any_sync(0xffffffffu, flat);
+    const int leader = __ffs(peers) - 1;
+    __shared__ std::uint32_t s_new, s_base;
+    if (threadIdx.x == 0)
     {
-        atomicOr(&d.status[f], ST_HASH_FULL);
-        slot = 0;
+        s_new = 0;
     }
-    d.vslot[o + i] = slot;
+    __syncthreads();
+    std::uint32_t slot = 0;
+    bool created = false;
     const std::size_t ho = static_cast<std::size_t>(f) * d.hcap;
-    d.hparent[ho + slot] = slot; // same value from every point of the voxel
-    d.hcount[ho + slot] = 0;
-    atomicMin(&d.hmin[ho + slot], i);
+    if (i < n && static_cast<int>(lane_id()) == leader)
+    {
+        const std::uint32_t slots = voxel_slots(d, f);
+        std::int32_t* keys = d.hkey + ho;
+        const std::uint32_t home = voxel_home(flat, slots);
+        slot = 0xffffffffu;
+        for (std::uint32_t t = 0; t < slots / 8u + slots; ++t)
+        {
+            const std::uint32_t h = voxel_probe(home, t, slots);
+            const std::int32_t prev = atomicCAS(&keys[h], -1, flat);
+            if (prev == -1 || prev == flat)
+            {
+                slot = h;
+                created = prev == -1;
+                break;
+            }
+        }
+        if (slot == 0xffffffffu)
+        {
+            atomicOr(&d.status[f], ST_HASH_FULL);
+            slot = 0;
+        }
+        if (created)
+        {
+            d.hparent[ho + slot] = slot;
+        }
+        atomicMin(&d.hmin[ho + slot], i);
+        atomicAdd(&d.hcount[ho + slot], static_cast<std::uint32_t>(__popc(peers)));
+    }
+    // the voxels this CTA created are appended to the frame's voxel list with one atomic per CTA
+    // (a per-voxel atomic on the frame's counter serialises ~17k updates on one address)
+    const std::uint32_t cm = __ballot_sync(0xffffffffu, created);
+    std::uint32_t woff = 0;
+    if (lane_id() == 0 && cm != 0)
+    {
+        woff = atomicAdd(&s_new, static_cast<std::uint32_t>(__popc(cm)));
+    }
+    woff = __shfl_sync(0xffffffffu, woff, 0);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_new != 0)
+    {
+        s_base = atomicAdd(&d.n_vox[f], s_new);
+    }
+    __syncthreads();
+    if (created)
+    {
+        d.vlist[o + s_base + woff + __popc(cm & ((1u << lane_id()) - 1u))] = slot;
+    }
+    slot = __shfl_sync(0xffffffffu, slot, leader);
+    if (i < n)
+    {
+        d.vslot[o + i] = slot;
+    }
 }
 
 // parent[] is updated with L2 atomics while other threads walk it: read through L2 (ld.cg) so a
@@ -295,22 +336,27 @@ __global__ void __launch_bounds__(256) k_clu_union(Dev d, ClusterParams cp)
     }
 }
 
+// one thread per occupied voxel: root of its component, component size and minimum point index
+// accumulated at the root (a non-root voxel's own count / minimum are final after k_clu_insert)
 __global__ void __launch_bounds__(256) k_clu_flatten(Dev d)
 {
     const std::uint32_t f = blockIdx.y;
-    const std::uint32_t n = d.n_o[f];
     const std::uint32_t i = blockIdx.x * 256u + threadIdx.x;
-    if (i >= n)
+    if (i >= d.n_vox[f])
     {
         return;
     }
     const std::size_t o = static_cast<std::size_t>(f) * d.cap;
     const std::size_t ho = static_cast<std::size_t>(f) * d.hcap;
-    const std::uint32_t root = uf_find(d.hparent + ho, d.vslot[o + i]);
-    d.vslot[o + i] = root;
-    atomicMin(&d.hmin[ho + root], i); // becomes the component's minimum point index
-    atomicAdd(&d.hcount[ho + root], 1u);
-    d.hlabel[ho + root] = -1;
+    const std::uint32_t slot = d.vlist[o + i];
+    const std::uint32_t root = uf_find(d.hparent + ho, slot);
+    d.hroot[ho + slot] = root;
+    d.hlabel[ho + slot] = -1;
+    if (root != slot)
+    {
+        atomicMin(&d.hmin[ho + root], d.hmin[ho + slot]);
+        atomicAdd(&d.hcount[ho + root], d.hcount[ho + slot]);
+    }
 }
 
 struct ClusterRepPred
@@ -319,8 +365,15 @@ struct ClusterRepPred
     std::uint32_t min_size;
     __device__ bool operator()(std::uint32_t f, std::uint32_t i) const
     {
+        // the minimum point of a component is also the minimum point of its own voxel (for a root
+        // voxel hmin already holds the component's minimum): one look-up rejects most points
         const std::size_t ho = static_cast<std::size_t>(f) * d.hcap;
-        const std::uint32_t root = d.vslot[static_cast<std::size_t>(f) * d.cap + i];
+        const std::uint32_t slot = d.vslot[static_cast<std::size_t>(f) * d.cap + i];
+        if (d.hmin[ho + slot] != i)
+        {
+            return false;
+        }
+        const std::uint32_t root = d.hroot[ho + slot];
         return d.hmin[ho + root] == i && d.hcount[ho + root] >= min_size;
     }
 };
@@ -331,7 +384,7 @@ struct ClusterRepEmit
     __device__ void operator()(std::uint32_t f, std::uint32_t i, std::uint32_t pos) const
     {
         const std::size_t ho = static_cast<std::size_t>(f) * d.hcap;
-        const std::uint32_t root = d.vslot[static_cast<std::size_t>(f) * d.cap + i];
+        const std::uint32_t root = d.hroot[ho + d.vslot[static_cast<std::size_t>(f) * d.cap + i]];
         d.hlabel[ho + root] = static_cast<std::int32_t>(pos);
         const std::size_t o = static_cast<std::size_t>(f) * d.cap;
         d.ccount[o + pos] = d.hcount[ho + root];
@@ -352,16 +405,18 @@ __global__ void __launch_bounds__(256) k_clu_labels(Dev d)
     }
     const std::size_t o = static_cast<std::size_t>(f) * d.cap;
     std::int32_t l = -1;
-    float z = 0.f;
+    float x = 0.f, y = 0.f, z = 0.f;
     if (i < n)
     {
-        l = d.hlabel[static_cast<std::size_t>(f) * d.hcap + d.vslot[o + i]];
+        const std::size_t ho = static_cast<std::size_t>(f) * d.hcap;
+        l = d.hlabel[ho + d.hroot[ho + d.vslot[o + i]]];
         d.clabel[o + i] = l;
         const float4 p = d.pts_o[o + i];
+        x = p.x;
+        y = p.y;
         z = p.z;
-        accumulate_extremes(d.ext + o * 8, l, p.x, p.y, i);
     }
-    accumulate_zext(d.zmin_u + o, d.zmax_u + o, l, z);
+    accumulate_cluster_stats(d.ext + o * 8, d.zmin_u + o, d.zmax_u + o, l, x, y, z, i);
 }
 
 // hand-over from segmentation: stable compaction of OBSTACLE points in cloud order
@@ -406,6 +461,7 @@ void launch_cluster(Ctx* c, std::uint32_t nf)
     cudaMemsetAsync(d.n_vox, 0, sizeof(std::uint32_t) * nf, s);
     cudaMemsetAsync(d.hkey, 0xff, sizeof(std::int32_t) * static_cast<std::size_t>(d.hcap) * nf, s);
     cudaMemsetAsync(d.hmin, 0xff, sizeof(std::uint32_t) * static_cast<std::size_t>(d.hcap) * nf, s);
+    cudaMemsetAsync(d.hcount, 0, sizeof(std::uint32_t) * static_cast<std::size_t>(d.hcap) * nf, s);
     const dim3 g((d.cap + 255) / 256, nf);
     k_clu_sph<<<g, 256, 0, s>>>(d);
     mark(c, "clu_sph");

@@ -85,6 +85,7 @@ struct Dev
     std::uint8_t* noise;      // [B][cap]  0 valid, 1 noise
     std::uint32_t* grid_cnt;  // [B][kDrorCells]  (self-cleaning)
     std::uint32_t* grid_start;// [B][kDrorCells+1]
+    std::uint32_t* grid_mask; // [B][kDrorCells/32] cells inside the search box of an unresolved query
     float4* grid_pts;         // [B][cap]  points in cell order
     std::uint32_t* unres;     // [B][cap]  unresolved point indices after the scan-line pass
     std::uint32_t* n_unres;   // [B]
@@ -101,12 +102,14 @@ struct Dev
     std::uint32_t* n_binned;  // [B]       points that fell into the polar grid
     uint2* zo;                // [B][cap]  cell-major (unordered inside a cell): (point index, z bits)
     float* zsort;             // [B][cap]  scratch for oversized cells
-    float* zsort2;            // [B][cap]  scratch for oversized cells
     std::uint32_t* ccnt;      // [B][ncell] RANSAC candidates per cell, then their exclusive prefix in (slice, bin) order
     float* cell_zmin;         // [B][ncell]
     float* elev;              // [B][ncell]
     std::uint8_t* lab;        // [B][cap]  label per point of the segmented cloud; bit 7 = RANSAC candidate
     std::uint32_t* n_cand;    // [B]
+    float4* cpts;             // [B][cap]  dense unordered copy of the candidate points (inlier count)
+    std::uint32_t* n_cpts;    // [B]
+    std::uint32_t* pairs;     // [B][kRansacIters][2] drawn candidate ranks
     float4* planes;           // [B][kRansacIters] (nx, ny, nz, d); nz = NaN marks a skipped draw
     std::uint32_t* inliers;   // [B][kRansacIters]
     float4* best_plane;       // [B]  (a, b, c, d); w component of [B + f] unused
@@ -138,6 +141,7 @@ struct Dev
     std::uint32_t* hmin;      // [B][hcap] min point index (per voxel, then per root)
     std::uint32_t* hcount;    // [B][hcap] points per root
     std::int32_t* hlabel;     // [B][hcap] final label per root
+    std::uint32_t* hroot;     // [B][hcap] root slot per occupied voxel
     std::uint32_t* vslot;     // [B][cap]  voxel slot per point
     std::uint32_t* vlist;     // [B][cap]  slots of the occupied voxels (unordered)
     std::uint32_t* n_vox;     // [B]
@@ -317,39 +321,15 @@ __device__ __forceinline__ float unord_f32(std::uint32_t k)
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
-// z extent per cluster label (src/processor/src/processor.cpp:648-655): lanes of a warp that
-// carry the same label are reduced first, then one atomicMin / atomicMax pair per label and warp.
+// Per-cluster statistics gathered while labels are written: the z extent
+// (src/processor/src/processor.cpp:648-655) and the extreme points in eight directions (hull.cu
+// builds an inscribed octagon from them and drops every point strictly inside it before the hull
+// sort). Extreme slots in counter-clockwise order: 0 min x, 1 min x+y, 2 min y, 3 max x-y, 4 max x,
+// 5 max x+y, 6 max y, 7 min x-y; a slot holds (ordered value bits << 32 | point index).
+// Scan-ordered clouds are monotone along a ring, so per-point atomics would hammer one address
+// per cluster: the lanes of a warp that share a label are reduced first (redux.sync over the
+// match group), and the group leader only issues an atomic when an L2 read says it improves.
 // Must be called by all 32 lanes; label < 0 = no contribution.
-__device__ __forceinline__ void accumulate_zext(std::uint32_t* zmin_u, std::uint32_t* zmax_u, std::int32_t label, float z)
-{
-    std::uint32_t todo = __ballot_sync(0xffffffffu, label >= 0);
-    const std::uint32_t zk = ord_f32(z);
-    while (todo != 0)
-    {
-        const int leader = __ffs(todo) - 1;
-        const std::int32_t l = __shfl_sync(0xffffffffu, label, leader);
-        const bool mine = label == l;
-        const std::uint32_t grp = __ballot_sync(0xffffffffu, mine);
-        std::uint32_t lo = mine ? zk : 0xffffffffu, hi = mine ? zk : 0u;
-#pragma unroll
-        for (int s = 16; s > 0; s >>= 1)
-        {
-            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, s));
-            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, s));
-        }
-        if (static_cast<int>(lane_id()) == leader)
-        {
-            atomicMin(&zmin_u[l], lo);
-            atomicMax(&zmax_u[l], hi);
-        }
-        todo &= ~grp;
-    }
-}
-
-// Extreme points of a cluster in eight directions (hull.cu builds an inscribed octagon from them
-// and drops every point strictly inside it before the hull sort). Slots in counter-clockwise
-// order: 0 min x, 1 min x+y, 2 min y, 3 max x-y, 4 max x, 5 max x+y, 6 max y, 7 min x-y.
-// A cheap L2 read filters out the (vast majority of) points that cannot improve a slot.
 __device__ __forceinline__ void ext_init(unsigned long long* e)
 {
 #pragma unroll
@@ -360,12 +340,29 @@ __device__ __forceinline__ void ext_init(unsigned long long* e)
     }
 }
 
-__device__ __forceinline__ void accumulate_extremes(unsigned long long* ext, std::int32_t label, float x, float y,
-                                                    std::uint32_t idx)
+__device__ __forceinline__ void accumulate_cluster_stats(unsigned long long* ext, std::uint32_t* zmin_u,
+                                                         std::uint32_t* zmax_u, std::int32_t label, float x, float y,
+                                                         float z, std::uint32_t idx)
 {
+    const std::uint32_t peers = __match_any_sync(0xffffffffu, label);
     if (label < 0)
     {
         return;
+    }
+    const bool lead = static_cast<int>(lane_id()) == __ffs(peers) - 1;
+    const std::uint32_t zk = ord_f32(z);
+    const std::uint32_t zlo = __reduce_min_sync(peers, zk);
+    const std::uint32_t zhi = __reduce_max_sync(peers, zk);
+    if (lead)
+    {
+        if (zlo < __ldcg(zmin_u + label))
+        {
+            atomicMin(&zmin_u[label], zlo);
+        }
+        if (zhi > __ldcg(zmax_u + label))
+        {
+            atomicMax(&zmax_u[label], zhi);
+        }
     }
     unsigned long long* e = ext + static_cast<std::size_t>(label) * 8;
     const float v[8] = {x, x + y, y, x - y, x, x + y, y, x - y};
@@ -373,17 +370,32 @@ __device__ __forceinline__ void accumulate_extremes(unsigned long long* ext, std
     for (int k = 0; k < 8; ++k)
     {
         const bool is_min = (k == 0 || k == 1 || k == 2 || k == 7);
-        const unsigned long long key = (static_cast<unsigned long long>(ord_f32(v[k])) << 32) | idx;
-        const unsigned long long cur = __ldcg(e + k);
-        if (is_min ? key < cur : key > cur)
+        const std::uint32_t vk = ord_f32(v[k]);
+        std::uint32_t b, bi;
+        if (is_min)
         {
-            if (is_min)
+            b = __reduce_min_sync(peers, vk);
+            bi = __reduce_min_sync(peers, vk == b ? idx : 0xffffffffu);
+        }
+        else
+        {
+            b = __reduce_max_sync(peers, vk);
+            bi = __reduce_max_sync(peers, vk == b ? idx : 0u);
+        }
+        if (lead)
+        {
+            const unsigned long long key = (static_cast<unsigned long long>(b) << 32) | bi;
+            const unsigned long long cur = __ldcg(e + k);
+            if (is_min ? key < cur : key > cur)
             {
-                atomicMin(e + k, key);
-            }
-            else
-            {
-                atomicMax(e + k, key);
+                if (is_min)
+                {
+                    atomicMin(e + k, key);
+                }
+                else
+                {
+                    atomicMax(e + k, key);
+                }
             }
         }
     }

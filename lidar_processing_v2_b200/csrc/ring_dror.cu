@@ -208,72 +208,189 @@ __device__ __forceinline__ int dror_cell_coord(float v)
     return min(max(c, 0), kDrorGrid - 1);
 }
 
+// cells a query's search disc can touch (conservative cover of the float predicate)
+struct DrorBox
+{
+    int x0, x1, y0, y1;
+};
+
+__device__ __forceinline__ DrorBox dror_box(const float4& p, float r_sqr)
+{
+    const float rc = sqrtf(r_sqr) * 1.001f + 1e-4f;
+    DrorBox b;
+    b.x0 = dror_cell_coord(p.x - rc);
+    b.x1 = dror_cell_coord(p.x + rc);
+    b.y0 = dror_cell_coord(p.y - rc);
+    b.y1 = dror_cell_coord(p.y + rc);
+    return b;
+}
+
+// Only ~4 % of the points reach the exhaustive search, and only the points near them can be
+// their neighbours: every unresolved query marks the cells of its search box in a per-frame
+// bitmap (8 KB), and the grid is then built from the points of marked cells alone.
+__global__ void __launch_bounds__(256) k_dror_mark(Dev d, DrorParams prm)
+{
+    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t nu = d.n_unres[f];
+    std::uint32_t* mask = d.grid_mask + static_cast<std::size_t>(f) * (kDrorCells / 32);
+    for (std::uint32_t u = blockIdx.x * 256u + threadIdx.x; u < nu; u += gridDim.x * 256u)
+    {
+        const std::uint32_t i = d.unres[static_cast<std::size_t>(f) * d.cap + u];
+        const float4 p = d.pts_in[static_cast<std::size_t>(f) * d.cap + i];
+        const DrorBox b = dror_box(p, dror_radius_sqr(p.x, p.y, prm));
+        for (int cy = b.y0; cy <= b.y1; ++cy)
+        {
+            for (int cx = b.x0; cx <= b.x1; ++cx)
+            {
+                const std::uint32_t cell = static_cast<std::uint32_t>(cy * kDrorGrid + cx);
+                const std::uint32_t bit = 1u << (cell & 31u);
+                if ((__ldcg(mask + (cell >> 5)) & bit) == 0u)
+                {
+                    atomicOr(mask + (cell >> 5), bit);
+                }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ bool dror_marked(const std::uint32_t* mask, int cell)
+{
+    return (mask[static_cast<std::uint32_t>(cell) >> 5] >> (static_cast<std::uint32_t>(cell) & 31u)) & 1u;
+}
+
 __global__ void __launch_bounds__(256) k_dror_grid_count(Dev d)
 {
     const std::uint32_t f = blockIdx.y;
     const std::uint32_t n = d.n_in[f];
-    const std::uint32_t i = blockIdx.x * 256u + threadIdx.x;
-    if (i >= n || d.n_unres[f] == 0)
+    if (blockIdx.x * 256u >= n || d.n_unres[f] == 0)
     {
         return;
     }
-    const float4 p = d.pts_in[static_cast<std::size_t>(f) * d.cap + i];
-    const int cell = dror_cell_coord(p.y) * kDrorGrid + dror_cell_coord(p.x);
-    atomicAdd(&d.grid_cnt[static_cast<std::size_t>(f) * kDrorCells + cell], 1u);
+    const std::uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    int cell = -1;
+    if (i < n)
+    {
+        const float4 p = d.pts_in[static_cast<std::size_t>(f) * d.cap + i];
+        const int c = dror_cell_coord(p.y) * kDrorGrid + dror_cell_coord(p.x);
+        if (dror_marked(d.grid_mask + static_cast<std::size_t>(f) * (kDrorCells / 32), c))
+        {
+            cell = c;
+        }
+    }
+    const std::uint32_t peers = __match_any_sync(0xffffffffu, cell);
+    if (cell >= 0 && static_cast<int>(lane_id()) == __ffs(peers) - 1)
+    {
+        atomicAdd(&d.grid_cnt[static_cast<std::size_t>(f) * kDrorCells + cell], static_cast<std::uint32_t>(__popc(peers)));
+    }
 }
 
 __global__ void __launch_bounds__(256) k_dror_grid_scatter(Dev d)
 {
     const std::uint32_t f = blockIdx.y;
     const std::uint32_t n = d.n_in[f];
-    const std::uint32_t i = blockIdx.x * 256u + threadIdx.x;
-    if (i >= n || d.n_unres[f] == 0)
+    if (blockIdx.x * 256u >= n || d.n_unres[f] == 0)
     {
         return;
     }
-    const float4 p = d.pts_in[static_cast<std::size_t>(f) * d.cap + i];
-    const int cell = dror_cell_coord(p.y) * kDrorGrid + dror_cell_coord(p.x);
-    // counting down returns grid_cnt to zero for the next batch
-    const std::uint32_t k = atomicSub(&d.grid_cnt[static_cast<std::size_t>(f) * kDrorCells + cell], 1u) - 1u;
-    const std::uint32_t pos = d.grid_start[static_cast<std::size_t>(f) * (kDrorCells + 1) + cell] + k;
-    d.grid_pts[static_cast<std::size_t>(f) * d.cap + pos] = p;
+    const std::uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    int cell = -1;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < n)
+    {
+        p = d.pts_in[static_cast<std::size_t>(f) * d.cap + i];
+        const int c = dror_cell_coord(p.y) * kDrorGrid + dror_cell_coord(p.x);
+        if (dror_marked(d.grid_mask + static_cast<std::size_t>(f) * (kDrorCells / 32), c))
+        {
+            cell = c;
+        }
+    }
+    const std::uint32_t peers = __match_any_sync(0xffffffffu, cell);
+    if (cell >= 0)
+    {
+        const int leader = __ffs(peers) - 1;
+        std::uint32_t k = 0;
+        if (static_cast<int>(lane_id()) == leader)
+        {
+            // counting down returns grid_cnt to zero for the next batch
+            k = atomicSub(&d.grid_cnt[static_cast<std::size_t>(f) * kDrorCells + cell],
+                          static_cast<std::uint32_t>(__popc(peers)));
+        }
+        k = __shfl_sync(peers, k, leader) - 1u - __popc(peers & ((1u << lane_id()) - 1u));
+        const std::uint32_t pos = d.grid_start[static_cast<std::size_t>(f) * (kDrorCells + 1) + cell] + k;
+        d.grid_pts[static_cast<std::size_t>(f) * d.cap + pos] = p;
+    }
 }
 
 // Pass B: exhaustive count for the unresolved points over every grid cell the search disc can
-// touch. Cells of one grid row are contiguous in grid_pts, so each row is one range that the 32
-// lanes of a warp scan together (coalesced float4 loads, ballot count, early exit at
-// min_neighbours).
+// touch. Cells of one grid row are contiguous in grid_pts, so each row is one range. Rows are
+// short far from the sensor (where most unresolved points live), so a query is served by a group
+// of 8 lanes: four queries per warp in flight, 32 points per step, early exit at min_neighbours.
 constexpr int kDrorQueryWarps = 8;
-constexpr int kDrorQueryCtas = 96; // per frame; warps stride over the unresolved list
+constexpr int kDrorGroup = 8;      // lanes per query
+constexpr int kDrorQueryCtas = 48; // per frame; groups stride over the unresolved list
+constexpr int kDrorUnroll = 4;     // points per lane and step
 
 __global__ void __launch_bounds__(kDrorQueryWarps * 32) k_dror_query(Dev d, DrorParams prm)
 {
     const std::uint32_t f = blockIdx.y;
     const std::uint32_t nu = d.n_unres[f];
     const std::uint32_t lane = lane_id();
+    const std::uint32_t gl = lane & (kDrorGroup - 1);                 // lane inside the group
+    const std::uint32_t gmask = ((1u << kDrorGroup) - 1u) << (lane & ~(kDrorGroup - 1u));
     const std::uint32_t* start = d.grid_start + static_cast<std::size_t>(f) * (kDrorCells + 1);
     const float4* gp = d.grid_pts + static_cast<std::size_t>(f) * d.cap;
-    for (std::uint32_t u = blockIdx.x * kDrorQueryWarps + (threadIdx.x >> 5); u < nu; u += gridDim.x * kDrorQueryWarps)
+    const std::uint32_t groups_per_cta = kDrorQueryWarps * 32 / kDrorGroup;
+    for (std::uint32_t u = blockIdx.x * groups_per_cta + threadIdx.x / kDrorGroup; u < nu;
+         u += gridDim.x * groups_per_cta)
     {
         const std::uint32_t i = d.unres[static_cast<std::size_t>(f) * d.cap + u];
         const float4 p = d.pts_in[static_cast<std::size_t>(f) * d.cap + i];
         const float r_sqr = dror_radius_sqr(p.x, p.y, prm);
-        const float rc = sqrtf(r_sqr) * 1.001f + 1e-4f; // conservative cover of the float predicate
-        const int x0 = dror_cell_coord(p.x - rc), x1 = dror_cell_coord(p.x + rc);
-        const int y0 = dror_cell_coord(p.y - rc), y1 = dror_cell_coord(p.y + rc);
+        const DrorBox bx = dror_box(p, r_sqr);
         std::uint32_t cnt = 0;
-        for (int cy = y0; cy <= y1 && cnt < prm.min_neighbours; ++cy)
+        for (int cy0 = bx.y0; cy0 <= bx.y1 && cnt < prm.min_neighbours; cy0 += kDrorGroup)
         {
-            const std::uint32_t a = start[cy * kDrorGrid + x0];
-            const std::uint32_t b = start[cy * kDrorGrid + x1 + 1];
-            for (std::uint32_t k0 = a; k0 < b && cnt < prm.min_neighbours; k0 += 32)
+            // lane gl fetches the bounds of row cy0 + gl
+            const int cy = cy0 + static_cast<int>(gl);
+            std::uint32_t ra = 0, rb = 0;
+            if (cy <= bx.y1)
             {
-                const std::uint32_t k = k0 + lane;
-                const bool hit = k < b && dror_within(p, gp[k], r_sqr);
-                cnt += __popc(__ballot_sync(0xffffffffu, hit));
+                ra = start[cy * kDrorGrid + bx.x0];
+                rb = start[cy * kDrorGrid + bx.x1 + 1];
+            }
+            const int rows = min(kDrorGroup, bx.y1 - cy0 + 1);
+            for (int r = 0; r < rows && cnt < prm.min_neighbours; ++r)
+            {
+                const std::uint32_t a = __shfl_sync(gmask, ra, r, kDrorGroup);
+                const std::uint32_t b = __shfl_sync(gmask, rb, r, kDrorGroup);
+                // kDrorUnroll independent loads per lane and step: a dense row (hundreds of points in
+                // a near-range cell) is latency bound, a sparse one only ever issues the first load
+                for (std::uint32_t k0 = a; k0 < b && cnt < prm.min_neighbours; k0 += kDrorGroup * kDrorUnroll)
+                {
+                    float4 q[kDrorUnroll];
+#pragma unroll
+                    for (int j = 0; j < kDrorUnroll; ++j)
+                    {
+                        const std::uint32_t k = k0 + j * kDrorGroup + gl;
+                        q[j] = k < b ? gp[k] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    std::uint32_t hits = 0;
+#pragma unroll
+                    for (int j = 0; j < kDrorUnroll; ++j)
+                    {
+                        const std::uint32_t k = k0 + j * kDrorGroup + gl;
+                        hits += (k < b && dror_within(p, q[j], r_sqr)) ? 1u : 0u;
+                    }
+#pragma unroll
+                    for (int sft = kDrorGroup / 2; sft > 0; sft >>= 1)
+                    {
+                        hits += __shfl_xor_sync(gmask, hits, sft, kDrorGroup);
+                    }
+                    cnt += hits;
+                }
             }
         }
-        if (lane == 0 && cnt < prm.min_neighbours)
+        if (gl == 0 && cnt < prm.min_neighbours)
         {
             d.noise[static_cast<std::size_t>(f) * d.cap + i] = 1;
         }
@@ -293,20 +410,42 @@ __global__ void k_excl_scan(const std::uint32_t* __restrict__ in, std::uint32_t 
     }
     const std::uint32_t* src = in + static_cast<std::size_t>(f) * in_stride;
     std::uint32_t* dst = out + static_cast<std::size_t>(f) * out_stride;
-    const std::uint32_t per = (len + blockDim.x - 1) / blockDim.x;
-    const std::uint32_t a = min(threadIdx.x * per, len);
-    const std::uint32_t b = min(a + per, len);
-    std::uint32_t s = 0;
-    for (std::uint32_t k = a; k < b; ++k)
+    // tiles of 4 * blockDim.x counters, four consecutive counters per thread (one 16-byte load when
+    // the row is aligned), block scan per tile, running carry across tiles
+    std::uint32_t total = 0;
+    const bool vec = (reinterpret_cast<std::uintptr_t>(src) & 15u) == 0;
+    for (std::uint32_t base = 0; base < len; base += 4u * blockDim.x)
     {
-        s += src[k];
-    }
-    std::uint32_t total;
-    std::uint32_t run = block_excl_scan(s, sh, &total);
-    for (std::uint32_t k = a; k < b; ++k)
-    {
-        dst[k] = run;
-        run += src[k];
+        const std::uint32_t k = base + 4u * threadIdx.x;
+        std::uint32_t v[4] = {0u, 0u, 0u, 0u};
+        if (vec && k + 3u < len)
+        {
+            const uint4 q = *reinterpret_cast<const uint4*>(src + k);
+            v[0] = q.x;
+            v[1] = q.y;
+            v[2] = q.z;
+            v[3] = q.w;
+        }
+        else
+        {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+            {
+                v[j] = (k + j < len) ? src[k + j] : 0u;
+            }
+        }
+        std::uint32_t tile_total;
+        std::uint32_t run = total + block_excl_scan(v[0] + v[1] + v[2] + v[3], sh, &tile_total);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+        {
+            if (k + j < len)
+            {
+                dst[k + j] = run;
+            }
+            run += v[j];
+        }
+        total += tile_total;
     }
     if (threadIdx.x == 0)
     {
@@ -325,6 +464,9 @@ void launch_dror(Ctx* c, std::uint32_t nf)
     const dim3 grid((d.cap + 255) / 256, nf);
     k_dror_near<<<grid, 256, 0, c->stream>>>(d, c->dror);
     mark(c, "dror_near");
+    cudaMemsetAsync(d.grid_mask, 0, sizeof(std::uint32_t) * (kDrorCells / 32) * nf, c->stream);
+    k_dror_mark<<<dim3(8, nf), 256, 0, c->stream>>>(d, c->dror);
+    mark(c, "dror_mark");
     k_dror_grid_count<<<grid, 256, 0, c->stream>>>(d);
     mark(c, "dror_grid_count");
     k_excl_scan<<<nf, 1024, 0, c->stream>>>(d.grid_cnt, kDrorCells, d.grid_start, kDrorCells + 1, kDrorCells,

@@ -3,7 +3,8 @@
 // Reference: lidar_processing_lib/src/segmenter.cpp
 //   constructPolarGrid :103-204   -> k_seg_bin, k_excl_scan, k_seg_scatter, k_seg_cell
 //   RECM               :206-283   -> k_seg_cell (robust per-cell minimum), k_seg_elev, k_seg_label
-//   RANSAC             :321-479   -> candidate flags (k_seg_label), k_ransac_setup, k_ransac_count
+//   RANSAC             :321-479   -> candidate flags (k_seg_label), k_ransac_draw, k_ransac_plane,
+//                                    k_ransac_count
 //   image scatter      :291-318   -> k_seg_image (64-bit atomicMin keys), k_seg_px
 //   JCP                :481-638   -> k_seg_dilate (5x5 stencil on shared-memory tiles),
 //                                    queue compaction, k_jcp_pre, k_jcp_resolve
@@ -13,7 +14,7 @@
 // and the points of a cell in cloud order. Only two results depend on that order and both are
 // recovered without sorting the cells: (i) the <= 120 RANSAC draws address candidates by their
 // rank in (cell, cloud) order - a prefix over per-cell candidate counts plus a radix select over
-// the point indices of one cell resolves a rank (k_ransac_setup); (ii) the range image keeps the
+// the point indices of one cell resolves a rank (k_ransac_draw / k_ransac_plane); (ii) the range image keeps the
 // first point among equal depths - equal depth^2 implies the same radial bin, so the 64-bit key
 // (depth^2, azimuth slice, point index) under atomicMin picks the reference's winner (k_seg_image).
 // Everything else (heights per cell, inlier counts, labels) is order independent.
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(256) k_seg_scatter(Dev d, SegParams sp)
 // ------------------------------------------------------------------------------------------
 // per-cell work: restore cloud order, robust minimum (segmenter.cpp:240-260)
 // ------------------------------------------------------------------------------------------
-constexpr int kCellSmem = 1024; // entries per warp
+constexpr int kCellSmem = 256; // heights per warp staged in shared memory for the gap scan
 
 // in-place ascending sort of buf[0..n) by one warp (bitonic network for arbitrary n: the first
 // step of every merge mirrors, so all exchanges move the larger value to the higher index and
@@ -223,7 +224,7 @@ __device__ __forceinline__ void warp_sort_regs(T (&v)[E])
     }
 }
 
-constexpr int kCellWarps = 4;     // warps per CTA
+constexpr int kCellWarps = 8;     // warps per CTA
 constexpr int kCellsPerWarp = 8;  // cells per warp, interleaved across the CTA's warps (most cells are empty)
 
 // largest i in [1, n/2] with zs[i] - zs[i-1] > 0.5 on the ascending heights zs[0..n), scanned from
@@ -313,44 +314,22 @@ __device__ __forceinline__ void seg_cell_one(const Dev& d, const SegParams& sp, 
     {
         zmin = cell_zmin_regs<4>(zo, n, zb);
     }
-    else if (n <= 256)
+    else if (n <= kCellSmem)
     {
         zmin = cell_zmin_regs<8>(zo, n, zb);
     }
-    else if (n <= kCellSmem)
-    {
-        for (std::uint32_t t = lane_id(); t < n; t += 32)
-        {
-            zb[t] = __uint_as_float(zo[t].y);
-        }
-        __syncwarp();
-        warp_sort(zb, n);
-        zmin = gap_scan([&](std::uint32_t i) { return zb[i]; }, n);
-        __syncwarp();
-    }
     else
     {
-        // oversized cell: rank sort through global scratch
+        // oversized cell (rare): the same bitonic network over global scratch; a warp's own
+        // stores are visible to its lanes after __syncwarp
         float* zt = d.zsort + o + a;
-        float* zs = d.zsort2 + o + a;
         for (std::uint32_t t = lane_id(); t < n; t += 32)
         {
             zt[t] = __uint_as_float(zo[t].y);
         }
         __syncwarp();
-        for (std::uint32_t t = lane_id(); t < n; t += 32)
-        {
-            const float v = zt[t];
-            std::uint32_t r = 0;
-            for (std::uint32_t u = 0; u < n; ++u)
-            {
-                const float w = zt[u];
-                r += (w < v || (w == v && u < t)) ? 1u : 0u;
-            }
-            zs[r] = v;
-        }
-        __syncwarp();
-        zmin = gap_scan([&](std::uint32_t i) { return zs[i]; }, n);
+        warp_sort(zt, n);
+        zmin = gap_scan([&](std::uint32_t i) { return zt[i]; }, n);
     }
     if (lane_id() == 0)
     {
@@ -430,13 +409,15 @@ __global__ void __launch_bounds__(256) k_seg_label(Dev d, SegParams sp)
     const std::uint32_t i = blockIdx.x * 256u + threadIdx.x;
     const std::size_t o = static_cast<std::size_t>(f) * d.cap;
     std::int32_t ccell = -1; // cell of a candidate, -1 otherwise
+    float4 pt = make_float4(0.f, 0.f, 0.f, 0.f);
     if (i < n)
     {
         const std::int32_t c = d.cell[o + i];
         std::uint8_t l = 0;
         if (c >= 0)
         {
-            const float z = d.pts_v[o + i].z;
+            pt = d.pts_v[o + i];
+            const float z = pt.z;
             const float e = d.elev[static_cast<std::size_t>(f) * sp.ncell + c];
             l = (z >= e + sp.thr) ? PX_OBSTACLE : PX_GROUND;
             if ((c % sp.rings) < kRansacBins && fabsf(e - z) < sp.thr2)
@@ -452,6 +433,30 @@ __global__ void __launch_bounds__(256) k_seg_label(Dev d, SegParams sp)
     {
         atomicAdd(&d.ccnt[static_cast<std::size_t>(f) * sp.ncell + ccell], __popc(peers));
     }
+    // dense (unordered) copy of the candidates for the inlier count, one atomic per CTA
+    __shared__ std::uint32_t s_cnt, s_base;
+    if (threadIdx.x == 0)
+    {
+        s_cnt = 0;
+    }
+    __syncthreads();
+    const std::uint32_t cm = __ballot_sync(0xffffffffu, ccell >= 0);
+    std::uint32_t woff = 0;
+    if (lane_id() == 0 && cm != 0)
+    {
+        woff = atomicAdd(&s_cnt, static_cast<std::uint32_t>(__popc(cm)));
+    }
+    woff = __shfl_sync(0xffffffffu, woff, 0);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_cnt != 0)
+    {
+        s_base = atomicAdd(&d.n_cpts[f], s_cnt);
+    }
+    __syncthreads();
+    if (ccell >= 0)
+    {
+        d.cpts[o + s_base + woff + __popc(cm & ((1u << lane_id()) - 1u))] = pt;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -459,8 +464,8 @@ __global__ void __launch_bounds__(256) k_seg_label(Dev d, SegParams sp)
 // ------------------------------------------------------------------------------------------
 // std::mt19937{42} raw outputs are frame independent (pre-generated on the host); libstdc++'s
 // uniform_int_distribution<uint32_t>{0, n-1} maps them with Lemire's multiply-shift + rejection.
-__device__ __forceinline__ std::uint32_t mt_draw(const std::uint32_t* raw, std::uint32_t& pos,
-                                                 std::uint32_t n, bool& exhausted)
+template <class RawAt>
+__device__ __forceinline__ std::uint32_t mt_draw(RawAt raw_at, std::uint32_t& pos, std::uint32_t n, bool& exhausted)
 {
     auto next = [&]() -> std::uint32_t {
         if (pos >= kMtRaws)
@@ -468,7 +473,7 @@ __device__ __forceinline__ std::uint32_t mt_draw(const std::uint32_t* raw, std::
             exhausted = true;
             return 0u;
         }
-        return raw[pos++];
+        return raw_at(pos++);
     };
     unsigned long long product = static_cast<unsigned long long>(next()) * n;
     std::uint32_t low = static_cast<std::uint32_t>(product);
@@ -484,179 +489,197 @@ __device__ __forceinline__ std::uint32_t mt_draw(const std::uint32_t* raw, std::
     return static_cast<std::uint32_t>(product >> 32);
 }
 
-constexpr int kSetupThreads = 256;
-constexpr int kSetupWarps = kSetupThreads / 32;
-constexpr int kSelCap = 1024; // candidate indices of one cell staged per warp
+constexpr int kDrawThreads = 256;
+constexpr int kSelCap = 1024;    // candidate indices of one cell staged per warp
+constexpr int kRawStage = 1024;  // generator outputs staged in shared memory
 
 // The reference numbers its candidates in (slice, bin, cloud) order and draws 60 index pairs.
 // Only those <= 120 candidates are ever looked at by position, so instead of materialising the
 // ordered list the draws are resolved by rank: an exclusive prefix of the per-cell candidate
-// counts (cells in index order, bins 0..3 only) locates the cell of rank t, and a radix select
-// over the point indices of that cell's candidates finds the (t - prefix)-th in cloud order.
-__global__ void __launch_bounds__(kSetupThreads) k_ransac_setup(Dev d, SegParams sp)
+// counts (cells in index order, bins 0..3 only) locates the cell of rank t (k_ransac_draw), and a
+// radix select over the point indices of that cell's candidates finds the (t - prefix)-th in
+// cloud order (k_ransac_plane, one warp per draw).
+__device__ __forceinline__ std::uint32_t ransac_cell_of(const SegParams& sp, std::uint32_t j)
 {
-    __shared__ std::uint32_t pair[kRansacIters][2];
-    __shared__ std::uint32_t pidx[kRansacIters][2]; // drawn point indices
-    __shared__ std::uint32_t sel[kSetupWarps][kSelCap];
+    return (j / sp.nb) * sp.rings + (j % sp.nb);
+}
+
+__global__ void __launch_bounds__(kDrawThreads) k_ransac_draw(Dev d, SegParams sp)
+{
     __shared__ std::uint32_t sh[33];
+    __shared__ std::uint32_t raws[kRawStage];
     const std::uint32_t f = blockIdx.x;
     const std::uint32_t J = static_cast<std::uint32_t>(sp.slices) * sp.nb; // candidate cells in rank order
     std::uint32_t* ccnt = d.ccnt + static_cast<std::size_t>(f) * sp.ncell;
-    auto cell_of = [&](std::uint32_t j) -> std::uint32_t { return (j / sp.nb) * sp.rings + (j % sp.nb); };
+    for (std::uint32_t t = threadIdx.x; t < kRawStage; t += kDrawThreads)
+    {
+        raws[t] = d.mt_raw[t];
+    }
     // in-place exclusive prefix over the J candidate cells, a contiguous chunk per thread
-    const std::uint32_t chunk = (J + kSetupThreads - 1) / kSetupThreads;
+    const std::uint32_t chunk = (J + kDrawThreads - 1) / kDrawThreads;
     const std::uint32_t j0 = min(threadIdx.x * chunk, J), j1 = min(j0 + chunk, J);
     std::uint32_t part = 0;
     for (std::uint32_t j = j0; j < j1; ++j)
     {
-        part += ccnt[cell_of(j)];
+        part += ccnt[ransac_cell_of(sp, j)];
     }
     std::uint32_t total;
     std::uint32_t run = block_excl_scan(part, sh, &total);
     for (std::uint32_t j = j0; j < j1; ++j)
     {
-        const std::uint32_t c = cell_of(j);
+        const std::uint32_t c = ransac_cell_of(sp, j);
         const std::uint32_t v = ccnt[c];
         ccnt[c] = run;
         run += v;
     }
     const std::uint32_t nc = total;
-    if (threadIdx.x == 0)
+    if (threadIdx.x < kRansacIters)
     {
-        d.n_cand[f] = nc;
+        d.inliers[f * kRansacIters + threadIdx.x] = 0;
     }
     // a single candidate makes the reference spin forever (segmenter.cpp:382-386); RANSAC is
     // skipped for nc < 2 (documented deviation).
-    const bool runit = nc >= 2;
-    if (threadIdx.x == 0 && runit)
+    if (threadIdx.x == 0)
     {
-        std::uint32_t pos = 0;
-        bool exhausted = false;
-        for (int it = 0; it < kRansacIters; ++it)
+        d.n_cand[f] = nc;
+        if (nc >= 2)
         {
-            const std::uint32_t i2 = mt_draw(d.mt_raw, pos, nc, exhausted);
-            std::uint32_t i3 = mt_draw(d.mt_raw, pos, nc, exhausted);
-            while (i3 == i2 && !exhausted)
+            std::uint32_t pos = 0;
+            bool exhausted = false;
+            auto raw_at = [&](std::uint32_t k) -> std::uint32_t { return k < kRawStage ? raws[k] : d.mt_raw[k]; };
+            std::uint32_t* pairs = d.pairs + static_cast<std::size_t>(f) * kRansacIters * 2;
+            for (int it = 0; it < kRansacIters; ++it)
             {
-                i3 = mt_draw(d.mt_raw, pos, nc, exhausted);
+                const std::uint32_t i2 = mt_draw(raw_at, pos, nc, exhausted);
+                std::uint32_t i3 = mt_draw(raw_at, pos, nc, exhausted);
+                while (i3 == i2 && !exhausted)
+                {
+                    i3 = mt_draw(raw_at, pos, nc, exhausted);
+                }
+                pairs[2 * it] = i2;
+                pairs[2 * it + 1] = i3;
             }
-            pair[it][0] = i2;
-            pair[it][1] = i3;
-        }
-        if (exhausted)
-        {
-            atomicOr(&d.status[f], ST_RNG_EXHAUSTED);
+            if (exhausted)
+            {
+                atomicOr(&d.status[f], ST_RNG_EXHAUSTED);
+            }
         }
     }
-    __syncthreads(); // prefix (global, this CTA only) and draws visible
+}
+
+// one CTA per (draw pair, frame): warp w resolves draw w of the pair, then the plane is formed
+__global__ void __launch_bounds__(64) k_ransac_plane(Dev d, SegParams sp)
+{
+    __shared__ std::uint32_t sel[2][kSelCap];
+    __shared__ std::uint32_t pidx[2];
+    const std::uint32_t it = blockIdx.x, f = blockIdx.y;
+    const std::uint32_t nc = d.n_cand[f];
+    const bool runit = nc >= 2;
     const std::size_t o = static_cast<std::size_t>(f) * d.cap;
-    const std::uint32_t* cs = d.cell_start + static_cast<std::size_t>(f) * (sp.ncell + 1);
     if (runit)
     {
+        const std::uint32_t J = static_cast<std::uint32_t>(sp.slices) * sp.nb;
+        const std::uint32_t* ccnt = d.ccnt + static_cast<std::size_t>(f) * sp.ncell;
+        const std::uint32_t* cs = d.cell_start + static_cast<std::size_t>(f) * (sp.ncell + 1);
         const std::uint32_t warp = threadIdx.x >> 5, lane = lane_id();
         std::uint32_t* mine = sel[warp];
-        for (std::uint32_t q = warp; q < 2u * kRansacIters; q += kSetupWarps)
+        const std::uint32_t t = d.pairs[(static_cast<std::size_t>(f) * kRansacIters + it) * 2 + warp];
+        // last candidate cell j with prefix[j] <= t (cells without candidates repeat the prefix)
+        std::uint32_t lo = 0, hi = J;
+        while (hi - lo > 1)
         {
-            const std::uint32_t t = pair[q >> 1][q & 1u];
-            // last candidate cell j with prefix[j] <= t (cells without candidates repeat the prefix)
-            std::uint32_t lo = 0, hi = J;
-            while (hi - lo > 1)
+            const std::uint32_t mid = (lo + hi) >> 1;
+            if (ccnt[ransac_cell_of(sp, mid)] <= t)
             {
-                const std::uint32_t mid = (lo + hi) >> 1;
-                if (ccnt[cell_of(mid)] <= t)
-                {
-                    lo = mid;
-                }
-                else
-                {
-                    hi = mid;
-                }
-            }
-            const std::uint32_t c = cell_of(lo);
-            std::uint32_t r = t - ccnt[c]; // rank inside the cell, cloud order
-            const std::uint32_t a = cs[c], n = cs[c + 1] - a;
-            const uint2* zo = d.zo + o + a;
-            // stage the candidates' point indices
-            std::uint32_t m = 0;
-            for (std::uint32_t base = 0; base < n; base += 32)
-            {
-                const std::uint32_t u = base + lane;
-                std::uint32_t idx = 0;
-                bool is = false;
-                if (u < n)
-                {
-                    idx = zo[u].x;
-                    is = (d.lab[o + idx] & 0x80) != 0;
-                }
-                const std::uint32_t b = __ballot_sync(0xffffffffu, is);
-                const std::uint32_t w = m + __popc(b & ((1u << lane) - 1u));
-                if (is && w < kSelCap)
-                {
-                    mine[w] = idx;
-                }
-                m += __popc(b);
-            }
-            __syncwarp();
-            std::uint32_t prefix = 0;
-            if (m <= kSelCap)
-            {
-                for (int bit = sp.idx_bits - 1; bit >= 0; --bit)
-                {
-                    std::uint32_t cnt0 = 0;
-                    for (std::uint32_t u = lane; u < m; u += 32)
-                    {
-                        const std::uint32_t v = mine[u];
-                        cnt0 += ((v >> (bit + 1)) == (prefix >> (bit + 1)) && ((v >> bit) & 1u) == 0u) ? 1u : 0u;
-                    }
-                    cnt0 = warp_sum(cnt0);
-                    if (r >= cnt0)
-                    {
-                        r -= cnt0;
-                        prefix |= 1u << bit;
-                    }
-                }
+                lo = mid;
             }
             else
             {
-                // more candidates in one cell than the staging holds: select straight from memory
-                for (int bit = sp.idx_bits - 1; bit >= 0; --bit)
+                hi = mid;
+            }
+        }
+        const std::uint32_t c = ransac_cell_of(sp, lo);
+        std::uint32_t r = t - ccnt[c]; // rank inside the cell, cloud order
+        const std::uint32_t a = cs[c], n = cs[c + 1] - a;
+        const uint2* zo = d.zo + o + a;
+        // stage the candidates' point indices
+        std::uint32_t m = 0;
+        for (std::uint32_t base = 0; base < n; base += 32)
+        {
+            const std::uint32_t u = base + lane;
+            std::uint32_t idx = 0;
+            bool is = false;
+            if (u < n)
+            {
+                idx = zo[u].x;
+                is = (d.lab[o + idx] & 0x80) != 0;
+            }
+            const std::uint32_t b = __ballot_sync(0xffffffffu, is);
+            const std::uint32_t w = m + __popc(b & ((1u << lane) - 1u));
+            if (is && w < kSelCap)
+            {
+                mine[w] = idx;
+            }
+            m += __popc(b);
+        }
+        __syncwarp();
+        std::uint32_t prefix = 0;
+        if (m <= kSelCap)
+        {
+            for (int bit = sp.idx_bits - 1; bit >= 0; --bit)
+            {
+                std::uint32_t cnt0 = 0;
+                for (std::uint32_t u = lane; u < m; u += 32)
                 {
-                    std::uint32_t cnt0 = 0;
-                    for (std::uint32_t u = lane; u < n; u += 32)
-                    {
-                        const std::uint32_t v = zo[u].x;
-                        if ((d.lab[o + v] & 0x80) != 0 && (v >> (bit + 1)) == (prefix >> (bit + 1)) &&
-                            ((v >> bit) & 1u) == 0u)
-                        {
-                            cnt0 += 1;
-                        }
-                    }
-                    cnt0 = warp_sum(cnt0);
-                    if (r >= cnt0)
-                    {
-                        r -= cnt0;
-                        prefix |= 1u << bit;
-                    }
+                    const std::uint32_t v = mine[u];
+                    cnt0 += ((v >> (bit + 1)) == (prefix >> (bit + 1)) && ((v >> bit) & 1u) == 0u) ? 1u : 0u;
+                }
+                cnt0 = warp_sum(cnt0);
+                if (r >= cnt0)
+                {
+                    r -= cnt0;
+                    prefix |= 1u << bit;
                 }
             }
-            if (lane == 0)
+        }
+        else
+        {
+            // more candidates in one cell than the staging holds: select straight from memory
+            for (int bit = sp.idx_bits - 1; bit >= 0; --bit)
             {
-                pidx[q >> 1][q & 1u] = prefix;
+                std::uint32_t cnt0 = 0;
+                for (std::uint32_t u = lane; u < n; u += 32)
+                {
+                    const std::uint32_t v = zo[u].x;
+                    if ((d.lab[o + v] & 0x80) != 0 && (v >> (bit + 1)) == (prefix >> (bit + 1)) &&
+                        ((v >> bit) & 1u) == 0u)
+                    {
+                        cnt0 += 1;
+                    }
+                }
+                cnt0 = warp_sum(cnt0);
+                if (r >= cnt0)
+                {
+                    r -= cnt0;
+                    prefix |= 1u << bit;
+                }
             }
-            __syncwarp();
+        }
+        if (lane == 0)
+        {
+            pidx[warp] = prefix;
         }
     }
     __syncthreads();
-    const int it = threadIdx.x;
-    if (it >= kRansacIters)
+    if (threadIdx.x != 0)
     {
         return;
     }
     float4 plane = make_float4(0.f, 0.f, __int_as_float(0x7fc00000), 0.f); // skipped
     if (runit)
     {
-        const float4 p2 = d.pts_v[o + pidx[it][0]];
-        const float4 p3 = d.pts_v[o + pidx[it][1]];
+        const float4 p2 = d.pts_v[o + pidx[0]];
+        const float4 p3 = d.pts_v[o + pidx[1]];
         const float p1x = 0.0f, p1y = 0.0f, p1z = sp.p1z;
         float nx = ((p2.y - p1y) * (p3.z - p1z)) - ((p2.z - p1z) * (p3.y - p1y));
         float ny = ((p2.z - p1z) * (p3.x - p1x)) - ((p2.x - p1x) * (p3.z - p1z));
@@ -676,7 +699,6 @@ __global__ void __launch_bounds__(kSetupThreads) k_ransac_setup(Dev d, SegParams
         }
     }
     d.planes[f * kRansacIters + it] = plane;
-    d.inliers[f * kRansacIters + it] = 0;
 }
 
 __global__ void __launch_bounds__(256) k_ransac_count(Dev d, SegParams sp)
@@ -684,17 +706,10 @@ __global__ void __launch_bounds__(256) k_ransac_count(Dev d, SegParams sp)
     __shared__ float4 pl[kRansacIters];
     __shared__ std::uint32_t cnt[kRansacIters];
     const std::uint32_t f = blockIdx.y;
-    const std::uint32_t n = d.n_v[f];
-    if (d.n_cand[f] < 2 || blockIdx.x * 256u >= n)
+    const std::uint32_t nc = d.n_cpts[f]; // = n_cand, the dense copy is unordered
+    if (nc < 2 || blockIdx.x * 256u >= nc)
     {
         return;
-    }
-    const std::uint32_t i = blockIdx.x * 256u + threadIdx.x;
-    const std::size_t o = static_cast<std::size_t>(f) * d.cap;
-    const bool live = i < n && (d.lab[o + i] & 0x80) != 0;
-    if (__syncthreads_or(live) == 0)
-    {
-        return; // no candidate among this CTA's points
     }
     if (threadIdx.x < kRansacIters)
     {
@@ -702,28 +717,45 @@ __global__ void __launch_bounds__(256) k_ransac_count(Dev d, SegParams sp)
         cnt[threadIdx.x] = 0;
     }
     __syncthreads();
+    const std::uint32_t k = blockIdx.x * 256u + threadIdx.x;
+    const bool live = k < nc;
     float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
     if (live)
     {
-        p = d.pts_v[o + i];
+        p = d.cpts[static_cast<std::size_t>(f) * d.cap + k];
     }
-    if (__any_sync(0xffffffffu, live))
-    {
+    // lane j keeps the counts of planes j and j + 32 of its warp in registers
+    std::uint32_t c0 = 0, c1 = 0;
+    const std::uint32_t lane = lane_id();
 #pragma unroll 4
-        for (int it = 0; it < kRansacIters; ++it)
+    for (int it = 0; it < kRansacIters; ++it)
+    {
+        const float4 q = pl[it];
+        if (q.z != q.z)
         {
-            const float4 q = pl[it];
-            if (q.z != q.z)
+            continue; // skipped draw (uniform branch)
+        }
+        const float od = fabsf((q.x * p.x) + (q.y * p.y) + (q.z * p.z) - q.w);
+        const std::uint32_t hits = __popc(__ballot_sync(0xffffffffu, live && od < sp.thr));
+        if (static_cast<int>(lane) == (it & 31))
+        {
+            if (it < 32)
             {
-                continue; // skipped draw (uniform branch)
+                c0 += hits;
             }
-            const float od = fabsf((q.x * p.x) + (q.y * p.y) + (q.z * p.z) - q.w);
-            const std::uint32_t m = __ballot_sync(0xffffffffu, live && od < sp.thr);
-            if (lane_id() == 0 && m != 0)
+            else
             {
-                atomicAdd(&cnt[it], __popc(m));
+                c1 += hits;
             }
         }
+    }
+    if (c0 != 0)
+    {
+        atomicAdd(&cnt[lane], c0);
+    }
+    if (c1 != 0 && lane + 32 < kRansacIters)
+    {
+        atomicAdd(&cnt[lane + 32], c1);
     }
     __syncthreads();
     if (threadIdx.x < kRansacIters && cnt[threadIdx.x] != 0)
@@ -1326,6 +1358,7 @@ void launch_segment(Ctx* c, std::uint32_t nf, bool want_image)
     // per-batch resets
     cudaMemsetAsync(d.cell_cnt, 0, sizeof(std::uint32_t) * sp.ncell * nf, s);
     cudaMemsetAsync(d.ccnt, 0, sizeof(std::uint32_t) * sp.ncell * nf, s);
+    cudaMemsetAsync(d.n_cpts, 0, sizeof(std::uint32_t) * nf, s);
     cudaMemsetAsync(d.key, 0xff, sizeof(unsigned long long) * sp.npx * nf, s);
     cudaMemsetAsync(d.seg_label, 0, static_cast<std::size_t>(d.cap) * nf, s);
     cudaMemsetAsync(d.labels_out, 0, static_cast<std::size_t>(d.cap) * nf, s);
@@ -1345,8 +1378,10 @@ void launch_segment(Ctx* c, std::uint32_t nf, bool want_image)
     mark(c, "seg_elev");
     k_seg_label<<<gpts, 256, 0, s>>>(d, sp);
     mark(c, "seg_label");
-    k_ransac_setup<<<nf, kSetupThreads, 0, s>>>(d, sp);
-    mark(c, "ransac_setup");
+    k_ransac_draw<<<nf, kDrawThreads, 0, s>>>(d, sp);
+    mark(c, "ransac_draw");
+    k_ransac_plane<<<dim3(kRansacIters, nf), 64, 0, s>>>(d, sp);
+    mark(c, "ransac_plane");
     k_ransac_count<<<gpts, 256, 0, s>>>(d, sp);
     mark(c, "ransac_count");
     k_seg_image<<<gpts, 256, 0, s>>>(d, sp);

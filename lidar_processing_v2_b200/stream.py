@@ -44,21 +44,25 @@ def reduce_stats(counters: dict, elapsed_s: float, dist=None, device=None) -> di
 
 
 class FramePipeline:
-    """Two contexts (two CUDA streams) working on alternating batches: while one batch's results
-    cross PCIe and the next batch is uploaded from pinned host memory, the other batch's kernels
-    keep the SMs busy. `submit` returns the results of the batch submitted two calls earlier."""
+    """`n_ctx` contexts (one CUDA stream each) working on batches in rotation: while one batch's
+    results cross PCIe and the next batch is uploaded from pinned host memory, the other batches'
+    kernels keep the SMs busy. `submit` returns the results of the batch submitted `n_ctx` calls
+    earlier."""
 
     def __init__(self, device: int, max_points: int, batch: int, stages: int = _n.STAGE_ALL,
                  cluster_cfg: dict | None = None, want=("labels_u8", "obstacle_index", "cluster_labels",
-                                                         "hull_offsets", "hull_xy", "zminmax")):
+                                                         "hull_offsets", "hull_xy", "zminmax"), n_ctx: int = 2):
+        if n_ctx < 1:
+            raise ValueError("n_ctx must be >= 1")
         self.stages = stages
         self.batch = batch
-        self.ctx = [_n.Context(device, max_points=max_points, max_frames=batch) for _ in range(2)]
+        self.n_ctx = n_ctx
+        self.ctx = [_n.Context(device, max_points=max_points, max_frames=batch) for _ in range(n_ctx)]
         for c in self.ctx:
             c.cluster_config(**(cluster_cfg or dict(range_m=0.4, az_deg=1.0, el_deg=3.0, min_size=3)))
         stride = ((max_points + 2047) // 2048) * 2048
-        self.out = [_n.BatchBuffers(batch, stride, want=want) for _ in range(2)]
-        self.inflight = [0, 0]
+        self.out = [_n.BatchBuffers(batch, stride, want=want) for _ in range(n_ctx)]
+        self.inflight = [0] * n_ctx
         self.turn = 0
         self.h2d_bytes = 0
         self.d2h_bytes = 0
@@ -72,7 +76,7 @@ class FramePipeline:
         self.ctx[i].run(nf, self.stages)
         self.inflight[i] = nf
         self.h2d_bytes += sum(int(f.shape[0]) for f in frames) * 16
-        self.turn ^= 1
+        self.turn = (self.turn + 1) % self.n_ctx
         return done
 
     def collect(self, i: int):
@@ -87,8 +91,8 @@ class FramePipeline:
     def drain(self):
         """Results of everything still in flight, oldest first."""
         res = []
-        for i in (self.turn, self.turn ^ 1):
-            r = self.collect(i)
+        for k in range(self.n_ctx):
+            r = self.collect((self.turn + k) % self.n_ctx)
             if r is not None:
                 res.append(r)
         return res
