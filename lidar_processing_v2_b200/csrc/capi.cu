@@ -109,6 +109,8 @@ void carve(Dev& d, Carver& cv, int npx, int ncell_cap, std::uint32_t** mt_raw)
     cv.take(d.hcount, B * h);
     cv.take(d.hlabel, B * h);
     cv.take(d.hroot, B * h);
+    cv.take(d.hvid, B * h);
+    cv.take(d.edges, B * cap * 13);
     cv.take(d.vslot, B * cap);
     cv.take(d.vlist, B * cap);
     cv.take(d.n_vox, B);

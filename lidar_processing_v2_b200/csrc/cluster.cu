@@ -3,9 +3,11 @@
 // Reference: lidar_processing_lib/src/clusterer.cpp
 //   cartesianToSpherical :55-100   -> k_clu_sph (glibc-exact atan2f / atanf, frame-wide maxima)
 //   buildHashTable       :102-120  -> k_clu_insert (device open-addressing hash, key = flat index)
-//   clusterImpl          :122-193  -> k_clu_union / k_clu_flatten: the BFS over 26-connected
-//                                     occupied voxels computes connected components; here they
-//                                     come from a lock-free union-find over hash slots
+//   clusterImpl          :122-193  -> k_clu_edges + k_clu_union_sm (k_clu_union / k_clu_flatten for
+//                                     oversized frames): the BFS over 26-connected occupied voxels
+//                                     computes connected components; here they come from a
+//                                     lock-free union-find over the voxel list, held in shared
+//                                     memory per frame
 //   removeSmallClusters  :195-239  -> stable compaction of the component representatives
 //
 // Label order: the reference opens a new cluster at the first point (in cloud order) whose
@@ -15,6 +17,8 @@
 //
 // The azimuth wrap is the reference's literal one (index -1 -> num_azimuth - 1, num_azimuth -> 0
 // with num_azimuth = ceil(max_az / res) + 1), see DESIGN.md hazard H3.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace lpl
@@ -176,10 +180,6 @@ __global__ void __launch_bounds__(256) k_clu_insert(Dev d, ClusterParams cp)
             atomicOr(&d.status[f], ST_HASH_FULL);
             slot = 0;
         }
-        if (created)
-        {
-            d.hparent[ho + slot] = slot;
-        }
         atomicMin(&d.hmin[ho + slot], i);
         atomicAdd(&d.hcount[ho + slot], static_cast<std::uint32_t>(__popc(peers)));
     }
@@ -200,7 +200,9 @@ __global__ void __launch_bounds__(256) k_clu_insert(Dev d, ClusterParams cp)
     __syncthreads();
     if (created)
     {
-        d.vlist[o + s_base + woff + __popc(cm & ((1u << lane_id()) - 1u))] = slot;
+        const std::uint32_t vid = s_base + woff + __popc(cm & ((1u << lane_id()) - 1u));
+        d.vlist[o + vid] = slot;
+        d.hvid[ho + slot] = vid;
     }
     slot = __shfl_sync(0xffffffffu, slot, leader);
     if (i < n)
@@ -209,77 +211,37 @@ __global__ void __launch_bounds__(256) k_clu_insert(Dev d, ClusterParams cp)
     }
 }
 
-// parent[] is updated with L2 atomics while other threads walk it: read through L2 (ld.cg) so a
-// stale L1 line can never make a failed CAS retry forever. The walk halves the path as it goes
-// (every visited node is re-pointed to its grandparent): parents only ever move to ancestors, so
-// racing walkers and hooks stay correct, and the chains that index-ordered hooking builds in
-// large components stay short.
-__device__ __forceinline__ std::uint32_t uf_find(std::uint32_t* parent, std::uint32_t x)
-{
-    std::uint32_t p = __ldcg(parent + x);
-    while (p != x)
-    {
-        const std::uint32_t g = __ldcg(parent + p);
-        if (g != p)
-        {
-            parent[x] = g;
-        }
-        x = p;
-        p = g;
-    }
-    return x;
-}
+constexpr std::uint32_t kUfSmemVoxels = 24576; // occupied voxels per frame the shared-memory union-find holds (96 KB)
+constexpr int kUfThreads = 1024;
+constexpr int kFwd = 13; // forward half of the 26-neighbourhood
 
-// roots only ever move to smaller slot ids, so the structure stays a forest under races
-__device__ __forceinline__ void uf_union(std::uint32_t* parent, std::uint32_t a, std::uint32_t b)
-{
-    while (true)
-    {
-        a = uf_find(parent, a);
-        b = uf_find(parent, b);
-        if (a == b)
-        {
-            return;
-        }
-        if (a < b)
-        {
-            const std::uint32_t t = a;
-            a = b;
-            b = t;
-        }
-        if (atomicCAS(&parent[a], a, b) == a)
-        {
-            return;
-        }
-    }
-}
-
-__global__ void __launch_bounds__(256) k_clu_union(Dev d, ClusterParams cp)
+// Occupied voxels are numbered by their position in the frame's voxel list ("voxel id").
+// k_clu_edges (one thread per voxel, whole GPU): the 26-neighbourhood is symmetric (also across
+// the literal azimuth wrap and the clipped range / elevation borders), so each voxel only looks
+// at the 13 "forward" offsets (de, da, dr) > (0, 0, 0); all first probes are issued before any is
+// consumed, and the ids of the neighbours found go to a fixed 13-entry row per voxel.
+__global__ void __launch_bounds__(256) k_clu_edges(Dev d, ClusterParams cp)
 {
     const std::uint32_t f = blockIdx.y;
-    const std::uint32_t i = blockIdx.x * 256u + threadIdx.x;
-    if (i >= d.n_vox[f])
+    const std::uint32_t v = blockIdx.x * 256u + threadIdx.x;
+    if (v >= d.n_vox[f])
     {
-        return; // one thread per occupied voxel (dense list built while inserting)
+        return;
     }
     const std::size_t o = static_cast<std::size_t>(f) * d.cap;
     const std::size_t ho = static_cast<std::size_t>(f) * d.hcap;
-    const std::uint32_t slot = d.vlist[o + i];
+    const std::uint32_t slot = d.vlist[o + v];
     const VoxelDims vd = voxel_dims(d, cp, f);
     const std::int32_t* keys = d.hkey + ho;
-    std::uint32_t* parent = d.hparent + ho;
     const std::uint32_t slots = voxel_slots(d, f);
     const std::int32_t flat = keys[slot];
     const std::int32_t ri = flat % vd.nr;
     const std::int32_t t = flat / vd.nr;
     const std::int32_t ai = t % vd.na;
     const std::int32_t ei = t / vd.na;
-    // The 26-neighbourhood is symmetric (also across the literal azimuth wrap and the clipped
-    // range / elevation borders), so each voxel only looks at the 13 "forward" offsets
-    // (de, da, dr) > (0, 0, 0); all first probes are issued before any is consumed.
-    std::int32_t key2[13];
-    std::uint32_t slot2[13];
-    std::int32_t found[13];
+    std::int32_t key2[kFwd];
+    std::uint32_t slot2[kFwd];
+    std::int32_t found[kFwd];
     int j = 0;
 #pragma unroll
     for (int de = 0; de <= 1; ++de)
@@ -306,56 +268,211 @@ __global__ void __launch_bounds__(256) k_clu_union(Dev d, ClusterParams cp)
         }
     }
 #pragma unroll
-    for (int q = 0; q < 13; ++q)
+    for (int q = 0; q < kFwd; ++q)
     {
         found[q] = key2[q] >= 0 ? keys[slot2[q]] : -1;
     }
+    std::uint32_t* row = d.edges + (o + v) * kFwd;
 #pragma unroll
-    for (int q = 0; q < 13; ++q)
+    for (int q = 0; q < kFwd; ++q)
     {
-        if (key2[q] < 0)
+        std::uint32_t nb = 0xffffffffu;
+        if (key2[q] >= 0)
         {
-            continue;
+            std::uint32_t h = slot2[q];
+            std::int32_t kk = found[q];
+            for (std::uint32_t tt = 1; tt <= slots / 8u + slots; ++tt)
+            {
+                if (kk == key2[q])
+                {
+                    nb = d.hvid[ho + h];
+                    break;
+                }
+                if (kk == -1)
+                {
+                    break;
+                }
+                h = voxel_probe(slot2[q], tt, slots);
+                kk = keys[h];
+            }
         }
-        std::uint32_t h = slot2[q];
-        std::int32_t kk = found[q];
-        for (std::uint32_t t = 1; t <= slots / 8u + slots; ++t)
+        row[q] = nb;
+    }
+    d.hparent[ho + v] = v; // forest of the global path, indexed by voxel id
+}
+
+// parent[] is updated with atomics while other threads walk it. The walk halves the path as it
+// goes (every visited node is re-pointed to its grandparent): parents only ever move to
+// ancestors, so racing walkers and hooks stay correct. Voxel ids follow the scan order, so
+// hooking by id would build path-like trees; a multiplicative hash of the id gives a scattered
+// (but fixed) priority instead. The global variant reads through L2 (ld.cg) so that a stale L1
+// line can never make a failed CAS retry forever.
+__device__ __forceinline__ bool uf_before(std::uint32_t a, std::uint32_t b)
+{
+    return a * 0x9E3779B1u < b * 0x9E3779B1u;
+}
+
+__device__ __forceinline__ std::uint32_t uf_find(std::uint32_t* parent, std::uint32_t x)
+{
+    std::uint32_t p = __ldcg(parent + x);
+    while (p != x)
+    {
+        const std::uint32_t g = __ldcg(parent + p);
+        if (g != p)
         {
-            if (kk == key2[q])
-            {
-                uf_union(parent, slot, h);
-                break;
-            }
-            if (kk == -1)
-            {
-                break;
-            }
-            h = voxel_probe(slot2[q], t, slots);
-            kk = keys[h];
+            parent[x] = g;
         }
+        x = p;
+        p = g;
+    }
+    return x;
+}
+
+__device__ __forceinline__ std::uint32_t uf_find_sm(volatile std::uint32_t* parent, std::uint32_t x)
+{
+    std::uint32_t p = parent[x];
+    while (p != x)
+    {
+        const std::uint32_t g = parent[p];
+        if (g != p)
+        {
+            parent[x] = g;
+        }
+        x = p;
+        p = g;
+    }
+    return x;
+}
+
+// component statistics at the root slot (a non-root voxel's own count / minimum are final after
+// k_clu_insert)
+__device__ __forceinline__ void uf_publish(const Dev& d, std::size_t o, std::size_t ho, std::uint32_t v, std::uint32_t r)
+{
+    const std::uint32_t slot = d.vlist[o + v];
+    const std::uint32_t root = d.vlist[o + r];
+    d.hroot[ho + slot] = root;
+    d.hlabel[ho + slot] = -1;
+    if (r != v)
+    {
+        atomicMin(&d.hmin[ho + root], d.hmin[ho + slot]);
+        atomicAdd(&d.hcount[ho + root], d.hcount[ho + slot]);
     }
 }
 
-// one thread per occupied voxel: root of its component, component size and minimum point index
-// accumulated at the root (a non-root voxel's own count / minimum are final after k_clu_insert)
-__global__ void __launch_bounds__(256) k_clu_flatten(Dev d)
+// Shared-memory union-find: a frame's forest (typically 10-17k voxels) lives in one CTA's shared
+// memory, so the pointer chasing of find() costs shared-memory instead of L2 latency; the CTA
+// streams the frame's edge rows (coalesced) and hooks lock-free with shared-memory CAS.
+__global__ void __launch_bounds__(kUfThreads) k_clu_union_sm(Dev d)
 {
-    const std::uint32_t f = blockIdx.y;
-    const std::uint32_t i = blockIdx.x * 256u + threadIdx.x;
-    if (i >= d.n_vox[f])
+    extern __shared__ std::uint32_t par[];
+    const std::uint32_t f = blockIdx.x;
+    const std::uint32_t nv = d.n_vox[f];
+    if (nv == 0 || nv > kUfSmemVoxels)
     {
         return;
     }
     const std::size_t o = static_cast<std::size_t>(f) * d.cap;
     const std::size_t ho = static_cast<std::size_t>(f) * d.hcap;
-    const std::uint32_t slot = d.vlist[o + i];
-    const std::uint32_t root = uf_find(d.hparent + ho, slot);
-    d.hroot[ho + slot] = root;
-    d.hlabel[ho + slot] = -1;
-    if (root != slot)
+    for (std::uint32_t v = threadIdx.x; v < nv; v += kUfThreads)
     {
-        atomicMin(&d.hmin[ho + root], d.hmin[ho + slot]);
-        atomicAdd(&d.hcount[ho + root], d.hcount[ho + slot]);
+        par[v] = v;
+    }
+    __syncthreads();
+    const std::uint32_t* edges = d.edges + o * kFwd;
+    for (std::uint32_t e = threadIdx.x; e < nv * kFwd; e += kUfThreads)
+    {
+        const std::uint32_t u = edges[e];
+        if (u == 0xffffffffu)
+        {
+            continue;
+        }
+        std::uint32_t a = e / kFwd, b = u;
+        while (true)
+        {
+            a = uf_find_sm(par, a);
+            b = uf_find_sm(par, b);
+            if (a == b)
+            {
+                break;
+            }
+            if (uf_before(a, b))
+            {
+                const std::uint32_t sw = a;
+                a = b;
+                b = sw;
+            }
+            if (atomicCAS(&par[a], a, b) == a)
+            {
+                break;
+            }
+        }
+    }
+    __syncthreads();
+    for (std::uint32_t v = threadIdx.x; v < nv; v += kUfThreads)
+    {
+        uf_publish(d, o, ho, v, uf_find_sm(par, v));
+    }
+}
+
+// Global-memory path for frames with more occupied voxels than the shared-memory forest holds
+// (e.g. the 2M-point clouds): one thread per voxel walks its edge row.
+__global__ void __launch_bounds__(256) k_clu_union(Dev d)
+{
+    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t nvox = d.n_vox[f];
+    if (nvox <= kUfSmemVoxels)
+    {
+        return;
+    }
+    const std::size_t o = static_cast<std::size_t>(f) * d.cap;
+    std::uint32_t* parent = d.hparent + static_cast<std::size_t>(f) * d.hcap;
+    for (std::uint32_t v = blockIdx.x * 256u + threadIdx.x; v < nvox; v += gridDim.x * 256u)
+    {
+    const std::uint32_t* row = d.edges + (o + v) * kFwd;
+    for (int q = 0; q < kFwd; ++q)
+    {
+        const std::uint32_t u = row[q];
+        if (u == 0xffffffffu)
+        {
+            continue;
+        }
+        std::uint32_t a = v, b = u;
+        while (true)
+        {
+            a = uf_find(parent, a);
+            b = uf_find(parent, b);
+            if (a == b)
+            {
+                break;
+            }
+            if (uf_before(a, b))
+            {
+                const std::uint32_t sw = a;
+                a = b;
+                b = sw;
+            }
+            if (atomicCAS(&parent[a], a, b) == a)
+            {
+                break;
+            }
+        }
+    }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_clu_flatten(Dev d)
+{
+    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t nvox = d.n_vox[f];
+    if (nvox <= kUfSmemVoxels)
+    {
+        return;
+    }
+    const std::size_t o = static_cast<std::size_t>(f) * d.cap;
+    const std::size_t ho = static_cast<std::size_t>(f) * d.hcap;
+    for (std::uint32_t v = blockIdx.x * 256u + threadIdx.x; v < nvox; v += gridDim.x * 256u)
+    {
+        uf_publish(d, o, ho, v, uf_find(d.hparent + ho, v));
     }
 }
 
@@ -467,9 +584,17 @@ void launch_cluster(Ctx* c, std::uint32_t nf)
     mark(c, "clu_sph");
     k_clu_insert<<<g, 256, 0, s>>>(d, c->clu);
     mark(c, "clu_insert");
-    k_clu_union<<<g, 256, 0, s>>>(d, c->clu);
+    k_clu_edges<<<g, 256, 0, s>>>(d, c->clu);
+    mark(c, "clu_edges");
+    cudaFuncSetAttribute(k_clu_union_sm, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         static_cast<int>(kUfSmemVoxels * sizeof(std::uint32_t)));
+    k_clu_union_sm<<<nf, kUfThreads, kUfSmemVoxels * sizeof(std::uint32_t), s>>>(d);
+    mark(c, "clu_union_sm");
+    // frames with more occupied voxels than the shared-memory forest holds take the global path
+    const dim3 gbig(std::min<std::uint32_t>((d.cap + 255) / 256, 592u), nf);
+    k_clu_union<<<gbig, 256, 0, s>>>(d);
     mark(c, "clu_union");
-    k_clu_flatten<<<g, 256, 0, s>>>(d);
+    k_clu_flatten<<<gbig, 256, 0, s>>>(d);
     mark(c, "clu_flatten");
     launch_compact(c, "clu_rank", nf, d.tiles, d.n_o, 0u, d.tile_cnt, d.n_clusters,
                    ClusterRepPred{d, c->clu.min_cluster_size}, ClusterRepEmit{d});

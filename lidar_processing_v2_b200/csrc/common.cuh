@@ -137,11 +137,13 @@ struct Dev
     float4* sph;              // [B][cap]  range, azimuth, elevation
     std::uint32_t* sph_max;   // [B][4]    float bits of max range / azimuth / elevation
     std::int32_t* hkey;       // [B][hcap] voxel flat index or -1
-    std::uint32_t* hparent;   // [B][hcap] union-find parent (slot ids)
+    std::uint32_t* hparent;   // [B][hcap] union-find parent by voxel id (global path only)
     std::uint32_t* hmin;      // [B][hcap] min point index (per voxel, then per root)
     std::uint32_t* hcount;    // [B][hcap] points per root
     std::int32_t* hlabel;     // [B][hcap] final label per root
     std::uint32_t* hroot;     // [B][hcap] root slot per occupied voxel
+    std::uint32_t* hvid;      // [B][hcap] position of the slot in the frame's voxel list
+    std::uint32_t* edges;     // [B][cap][13] voxel ids of the occupied forward neighbours (or ~0)
     std::uint32_t* vslot;     // [B][cap]  voxel slot per point
     std::uint32_t* vlist;     // [B][cap]  slots of the occupied voxels (unordered)
     std::uint32_t* n_vox;     // [B]

@@ -29,6 +29,7 @@
 // slots from the previously popped pixel (hazard H2); k_jcp_pre reproduces that by
 // locating the most recent earlier queued pixel for which the slot was inside the image.
 #include <cfloat>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -1114,7 +1115,9 @@ __device__ __forceinline__ std::uint32_t plane_get(const volatile std::uint32_t*
     return (plane[p >> 4] >> ((p & 15u) * 2u)) & 3u;
 }
 
-constexpr int kJcpThreads = 512;
+constexpr int kJcpThreads = 1024;
+constexpr int kJcpAhead = 4; // queue entries whose weights / masks are in flight ahead of the vote
+constexpr int kJcpRunTable = 4096; // runs whose (first queue entry, first pixel) are staged in shared memory
 constexpr std::uint32_t kJcpSpinLimit = 1u << 22;
 
 struct RunHeadPred
@@ -1139,7 +1142,7 @@ struct RunHeadEmit
     }
 };
 
-__global__ void __launch_bounds__(kJcpThreads) k_jcp_resolve(Dev d, SegParams sp)
+__global__ void __launch_bounds__(1024) k_jcp_resolve(Dev d, SegParams sp)
 {
     extern __shared__ std::uint32_t plane[]; // npx / 16 words
     const std::uint32_t f = blockIdx.x;
@@ -1175,18 +1178,29 @@ __global__ void __launch_bounds__(kJcpThreads) k_jcp_resolve(Dev d, SegParams sp
     const int dw = slot < 5 ? slot - 2 : (slot < 10 ? slot - 7 : slot - 12);
     std::uint32_t spins = 0;
     __shared__ std::uint32_t s_next_run;
-    __shared__ __align__(16) float s_vote[kJcpThreads / 32][48];
+    __shared__ __align__(16) float s_vote[32][48];
+    __shared__ std::uint32_t s_runk[kJcpRunTable], s_runp[kJcpRunTable];
+    const std::uint32_t nrt = min(nruns, static_cast<std::uint32_t>(kJcpRunTable));
+    for (std::uint32_t t = threadIdx.x; t < nrt; t += blockDim.x)
+    {
+        const std::uint32_t kk = runs[t];
+        s_runk[t] = kk;
+        s_runp[t] = queue[kk];
+    }
     if (threadIdx.x == 0)
     {
         s_next_run = 0;
     }
     __syncthreads();
     // One warp per run, lane i = kernel slot i: the 96-byte weight row of a pixel is one coalesced
-    // load, every lane resolves its own slot (spinning on the plane only for a queued pixel of the
-    // rows above that another warp has not fired yet), and the vote is the reference's ordered sum
-    // over the 24 slots, accumulated by shuffles so that the float additions happen in slot order.
-    // Runs are handed out in raster order to whichever warp is free: the raster-first unfinished
-    // run is always being worked on and waits on nothing unfinished, so the sweep cannot deadlock.
+    // load, every lane resolves its own slot (waiting on the plane only for a queued pixel that
+    // another warp has not fired yet), and the vote is the reference's ordered sum over the 24
+    // slots. Runs are handed out in raster order to whichever warp is free: the raster-first
+    // unfinished run is always being worked on and waits on nothing unfinished, so the sweep
+    // cannot deadlock. Handing out one run at a time keeps the raster front wide (claiming several
+    // runs per warp serialises rows that could advance together); what a run start costs in
+    // memory latency is cut by keeping the run table (first queue entry, first pixel) of the frame
+    // in shared memory and the per-pixel loads kJcpAhead pixels ahead of the vote.
     while (true)
     {
         std::uint32_t r = 0;
@@ -1199,37 +1213,66 @@ __global__ void __launch_bounds__(kJcpThreads) k_jcp_resolve(Dev d, SegParams sp
         {
             break;
         }
-        // lanes 0 / 1 fetch this run's and the next run's first entry together
-        std::uint32_t kk = nq;
-        if (lane < 2u && r + lane < nruns)
+        std::uint32_t k, kend, p;
+        if (r + 1u < nrt)
         {
-            kk = runs[r + lane];
+            k = s_runk[r];
+            kend = s_runk[r + 1u];
+            p = s_runp[r];
         }
-        std::uint32_t k = __shfl_sync(0xffffffffu, kk, 0);
-        const std::uint32_t kend = __shfl_sync(0xffffffffu, kk, 1); // first entry of the next run
-        std::uint32_t p = queue[k];
+        else
+        {
+            // beyond the staged table (or its last entry): lanes 0 / 1 fetch the bounds together
+            std::uint32_t kk = nq;
+            if (lane < 2u && r + lane < nruns)
+            {
+                kk = runs[r + lane];
+            }
+            k = __shfl_sync(0xffffffffu, kk, 0);
+            kend = __shfl_sync(0xffffffffu, kk, 1); // first entry of the next run
+            p = queue[k];
+        }
         const int h = static_cast<int>(p / W);
         int wv = static_cast<int>(p % W);
-        unsigned long long m = mkv[k];
-        float wt = lane < 24u ? wn[static_cast<std::size_t>(k) * 24 + lane] : 0.f;
+        // register ring: the weight rows / masks of the next kJcpAhead pixels of the run are in
+        // flight while the current pixel waits on its neighbours and votes
+        unsigned long long mq[kJcpAhead];
+        float wq[kJcpAhead];
+#pragma unroll
+        for (int j = 0; j < kJcpAhead; ++j)
+        {
+            mq[j] = 0;
+            wq[j] = 0.f;
+            if (k + j < kend)
+            {
+                mq[j] = mkv[k + j];
+                wq[j] = lane < 24u ? wn[static_cast<std::size_t>(k + j) * 24 + lane] : 0.f;
+            }
+        }
         for (; k < kend; ++k, ++p, ++wv)
         {
-            unsigned long long m_next = 0;
-            float wt_next = 0.f;
-            if (k + 1 < kend)
+            const unsigned long long m = mq[0];
+            const float wt = wq[0];
+#pragma unroll
+            for (int j = 0; j + 1 < kJcpAhead; ++j)
             {
-                m_next = mkv[k + 1]; // in flight while this pixel waits and votes
-                wt_next = lane < 24u ? wn[static_cast<std::size_t>(k + 1) * 24 + lane] : 0.f;
+                mq[j] = mq[j + 1];
+                wq[j] = wq[j + 1];
+            }
+            if (k + kJcpAhead < kend)
+            {
+                mq[kJcpAhead - 1] = mkv[k + kJcpAhead];
+                wq[kJcpAhead - 1] = lane < 24u ? wn[static_cast<std::size_t>(k + kJcpAhead) * 24 + lane] : 0.f;
             }
             std::uint32_t out = 0;
             if ((m >> 48) & 1ULL)
             {
                 std::uint32_t mi = lane < 24u ? static_cast<std::uint32_t>((m >> (2 * slot)) & 3ULL) : 0u;
+                std::uint32_t ref = 0;
                 if (mi == 3u)
                 {
                     // final state of an earlier queued pixel
                     const int hh = h + dh, ww = wv + dw;
-                    std::uint32_t ref;
                     if (hh >= 0 && ww >= 0 && ww < sp.W)
                     {
                         ref = static_cast<std::uint32_t>(hh * sp.W + ww);
@@ -1240,22 +1283,36 @@ __global__ void __launch_bounds__(kJcpThreads) k_jcp_resolve(Dev d, SegParams sp
                         const std::uint32_t brow = static_cast<std::uint32_t>(m >> 49);
                         ref = sref[static_cast<std::size_t>(brow - 1) * 12 + slot];
                     }
-                    while ((mi = plane_get(plane, ref)) == 3u)
+                    mi = plane_get(plane, ref);
+                }
+                // warp-uniform wait: lanes still looking at an unfinished pixel poll again after a
+                // back-off that grows with the wait (a spinning warp must not take issue slots
+                // from the warp it waits for)
+                std::uint32_t pending = __ballot_sync(0xffffffffu, mi == 3u);
+                std::uint32_t backoff = 32;
+                while (pending != 0u)
+                {
+                    if (++spins > kJcpSpinLimit)
                     {
-                        if (++spins > kJcpSpinLimit)
+                        if (lane == 0)
                         {
                             atomicOr(&d.status[f], ST_JCP_STALL);
-                            mi = 0u;
-                            break;
                         }
-                        __nanosleep(64); // back off: a spinning warp must not starve the warp it waits for
+                        mi = mi == 3u ? 0u : mi;
+                        break;
                     }
+                    __nanosleep(backoff);
+                    backoff = min(backoff * 2u, 512u);
+                    if (mi == 3u)
+                    {
+                        mi = plane_get(plane, ref);
+                    }
+                    pending = __ballot_sync(0xffffffffu, mi == 3u);
                 }
                 // x + 0.0f == x: adding a zero for the slots of the other classes keeps the sums
                 // bit-identical to the reference's conditional accumulation in slot order. The 24
-                // (ground, obstacle) contributions go through shared memory (one store per lane, six
-                // 128-bit loads per class by lane 0): 48 shuffles per pixel would saturate the SM's
-                // shuffle throughput with 16 warps per frame in flight.
+                // (ground, obstacle) contributions go through shared memory (one store per lane);
+                // lane 0 sums the ground row and lane 1 the obstacle row, in slot order.
                 float* vg = s_vote[threadIdx.x >> 5];
                 float* vo = vg + 24;
                 if (lane < 24u)
@@ -1264,25 +1321,22 @@ __global__ void __launch_bounds__(kJcpThreads) k_jcp_resolve(Dev d, SegParams sp
                     vo[lane] = mi == 2u ? wt : 0.f;
                 }
                 __syncwarp();
-                if (lane == 0)
+                float acc = 0.f;
+                if (lane < 2u)
                 {
-                    float wg = 0.f, wo = 0.f;
+                    const float4* row = reinterpret_cast<const float4*>(vg + 24u * lane);
 #pragma unroll
                     for (int i = 0; i < 6; ++i)
                     {
-                        const float4 a = reinterpret_cast<const float4*>(vg)[i];
-                        const float4 b = reinterpret_cast<const float4*>(vo)[i];
-                        wg += a.x;
-                        wg += a.y;
-                        wg += a.z;
-                        wg += a.w;
-                        wo += b.x;
-                        wo += b.y;
-                        wo += b.z;
-                        wo += b.w;
+                        const float4 a = row[i];
+                        acc += a.x;
+                        acc += a.y;
+                        acc += a.z;
+                        acc += a.w;
                     }
-                    out = (wo > wg) ? 2u : 1u;
                 }
+                const float wo = __shfl_sync(0xffffffffu, acc, 1);
+                out = (wo > acc) ? 2u : 1u; // meaningful on lane 0 (acc = ground sum)
             }
             if (lane == 0)
             {
@@ -1291,8 +1345,6 @@ __global__ void __launch_bounds__(kJcpThreads) k_jcp_resolve(Dev d, SegParams sp
                 code[p] = (out == 0u) ? PX_UNDECIDED : static_cast<std::uint8_t>(out);
             }
             __syncwarp(); // orders lane 0's plane update before the next pixel's look-ups
-            m = m_next;
-            wt = wt_next;
         }
     }
     if (threadIdx.x == 0)
@@ -1398,12 +1450,11 @@ void launch_segment(Ctx* c, std::uint32_t nf, bool want_image)
     k_jcp_pre<<<dim3((d.qcap + 127) / 128, nf), 128, 0, s>>>(d, sp);
     mark(c, "jcp_pre");
     const std::size_t plane_bytes = static_cast<std::size_t>((sp.npx + 15) / 16) * 4;
-    if (plane_bytes > 48 * 1024)
-    {
-        // 128-beam images: 64 KB state plane (opt-in above 48 KB; up to 227 KB per CTA on sm_100a)
-        cudaFuncSetAttribute(k_jcp_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(plane_bytes));
-    }
-    k_jcp_resolve<<<nf, kJcpThreads, plane_bytes, s>>>(d, sp);
+    // state plane (32 KB for 64 x 2048, 64 KB for 128-beam images) on top of ~39 KB of static shared
+    // memory: above the 48 KB default, opt in (up to 227 KB per CTA on sm_100a)
+    cudaFuncSetAttribute(k_jcp_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(plane_bytes));
+    static const int jcp_threads = std::getenv("LPL_JCP_THREADS") ? std::atoi(std::getenv("LPL_JCP_THREADS")) : kJcpThreads;
+    k_jcp_resolve<<<nf, jcp_threads, plane_bytes, s>>>(d, sp);
     mark(c, "jcp_resolve");
     k_seg_labels_out<<<dim3((sp.npx + 255) / 256, nf), 256, 0, s>>>(d, sp, want_image ? 1 : 0);
     mark(c, "seg_labels_out");
