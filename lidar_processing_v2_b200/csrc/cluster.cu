@@ -591,7 +591,8 @@ void launch_cluster(Ctx* c, std::uint32_t nf)
     k_clu_union_sm<<<nf, kUfThreads, kUfSmemVoxels * sizeof(std::uint32_t), s>>>(d);
     mark(c, "clu_union_sm");
     // frames with more occupied voxels than the shared-memory forest holds take the global path
-    const dim3 gbig(std::min<std::uint32_t>((d.cap + 255) / 256, 592u), nf);
+    // about one resident wave of CTAs in total: the kernels stride over a frame's voxels
+    const dim3 gbig(std::max(1u, std::min<std::uint32_t>((d.cap + 255) / 256, (148u * 8u + nf - 1u) / nf)), nf);
     k_clu_union<<<gbig, 256, 0, s>>>(d);
     mark(c, "clu_union");
     k_clu_flatten<<<gbig, 256, 0, s>>>(d);

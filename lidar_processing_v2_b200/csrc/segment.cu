@@ -203,9 +203,8 @@ __device__ __forceinline__ void warp_sort_regs(T (&v)[E])
                     {
                         const bool asc = (((e << 5) | lane) & k) == 0;
                         const T a = v[e], b = v[pe];
-                        const bool swap = asc ? (b < a) : (a < b);
-                        v[e] = swap ? b : a;
-                        v[pe] = swap ? a : b;
+                        v[e] = asc ? min(a, b) : max(a, b);
+                        v[pe] = asc ? max(a, b) : min(a, b);
                     }
                 }
             }
@@ -218,7 +217,7 @@ __device__ __forceinline__ void warp_sort_regs(T (&v)[E])
                     const bool asc = (((e << 5) | lane) & k) == 0;
                     const bool lower = (lane & j) == 0;
                     const bool take_min = lower == asc;
-                    v[e] = take_min ? (other < v[e] ? other : v[e]) : (v[e] < other ? other : v[e]);
+                    v[e] = take_min ? min(v[e], other) : max(v[e], other);
                 }
             }
         }
@@ -255,23 +254,35 @@ __device__ __forceinline__ float gap_scan(Load zs, std::uint32_t n)
     return zmin;
 }
 
+// heights are sorted as order-preserving integer keys (a total order: -0.0 before +0.0), one
+// integer min / max per compare-exchange
+__device__ __forceinline__ std::uint32_t zkey(std::uint32_t bits)
+{
+    return (bits & 0x80000000u) ? ~bits : (bits | 0x80000000u);
+}
+
+__device__ __forceinline__ float zval(std::uint32_t key)
+{
+    return __uint_as_float((key & 0x80000000u) ? (key & 0x7fffffffu) : ~key);
+}
+
 // E values per lane sorted in registers, then the gap scan over shared memory
 template <int E>
 __device__ __forceinline__ float cell_zmin_regs(const uint2* zo, std::uint32_t n, float* zb)
 {
     const std::uint32_t lane = lane_id();
-    float z[E];
+    std::uint32_t z[E];
 #pragma unroll
     for (int e = 0; e < E; ++e)
     {
         const std::uint32_t t = e * 32 + lane;
-        z[e] = t < n ? __uint_as_float(zo[t].y) : 3.402823466e+38f;
+        z[e] = t < n ? zkey(zo[t].y) : 0xffffffffu;
     }
     warp_sort_regs<E>(z);
 #pragma unroll
     for (int e = 0; e < E; ++e)
     {
-        zb[e * 32 + lane] = z[e];
+        zb[e * 32 + lane] = zval(z[e]);
     }
     __syncwarp();
     const float r = gap_scan([&](std::uint32_t i) { return zb[i]; }, n);
@@ -289,18 +300,19 @@ __device__ __forceinline__ void seg_cell_one(const Dev& d, const SegParams& sp, 
     {
         // the common case: one height per lane, shuffle-only bitonic network
         const std::uint32_t lane = lane_id();
-        float z = lane < n ? __uint_as_float(zo[lane].y) : 3.402823466e+38f;
+        std::uint32_t zk = lane < n ? zkey(zo[lane].y) : 0xffffffffu;
 #pragma unroll
         for (std::uint32_t k = 2; k <= 32; k <<= 1)
         {
 #pragma unroll
             for (std::uint32_t j = k >> 1; j > 0; j >>= 1)
             {
-                const float other = __shfl_xor_sync(0xffffffffu, z, j);
+                const std::uint32_t other = __shfl_xor_sync(0xffffffffu, zk, j);
                 const bool take_min = ((lane & j) == 0) == ((lane & k) == 0);
-                z = take_min ? fminf(z, other) : fmaxf(z, other);
+                zk = take_min ? min(zk, other) : max(zk, other);
             }
         }
+        const float z = zval(zk);
         const float prev = __shfl_up_sync(0xffffffffu, z, 1);
         const bool hit = lane >= 1 && lane <= n / 2 && (z - prev > 0.5f);
         const std::uint32_t m = __ballot_sync(0xffffffffu, hit);
