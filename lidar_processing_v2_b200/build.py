@@ -40,7 +40,8 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/*.cu into lidar_processing_v2_b200/liblpl_b200.so (cross-compiles without a GPU)."""
     if not force and not needs_build():
         return SO_PATH
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", SO_PATH, *[os.path.join(CSRC, s) for s in SOURCES]]
+    extra = os.environ.get("LPL_NVCC_EXTRA", "").split()  # e.g. -DLPL_HULL_TRACE (diagnostics only)
+    cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-o", SO_PATH, *[os.path.join(CSRC, s) for s in SOURCES]]
     if verbose:
         print(" ".join(cmd))
     res = subprocess.run(cmd, capture_output=True, text=True)

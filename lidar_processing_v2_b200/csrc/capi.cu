@@ -136,6 +136,7 @@ void carve(Dev& d, Carver& cv, int npx, int ncell_cap, std::uint32_t** mt_raw)
     cv.take(d.octa, B * cap * 8);
     cv.take(d.hseg_cnt, B * cap);
     cv.take(d.n_h, B);
+    cv.take(d.hull_next, B);
     const std::size_t tl = std::max<std::size_t>(d.tiles, d.ptiles);
     cv.take(d.tile_cnt, B * tl);
     cv.take(d.status, B);

@@ -17,8 +17,9 @@ namespace lpl
 constexpr int kTile = 2048;         // items per compaction / scan tile
 constexpr int kTileThreads = 256;   // threads per tile block (8 items per thread)
 constexpr int kItems = kTile / kTileThreads;
-constexpr int kDrorGrid = 256;      // DROR uniform grid: kDrorGrid x kDrorGrid cells of 1 m
-constexpr int kDrorCells = kDrorGrid * kDrorGrid;
+constexpr int kDrorGrid = 256;      // DROR grids: kDrorGrid x kDrorGrid cells, two levels (1 m over +-128 m, 0.25 m over +-32 m)
+constexpr int kDrorLevelCells = kDrorGrid * kDrorGrid;
+constexpr int kDrorCells = 2 * kDrorLevelCells;
 constexpr int kRansacIters = 60;    // segmenter.cpp:324
 constexpr int kRansacBins = 4;      // segmenter.cpp:323
 constexpr int kMtRaws = 8192;       // pre-generated std::mt19937{42} outputs
@@ -171,6 +172,7 @@ struct Dev
     float2* octa;             // [B][cap][8] per cluster: the octagon of those points, or NaN when unusable
     std::uint32_t* hseg_cnt;  // [B][cap]  per cluster: points that survive the octagon filter
     std::uint32_t* n_h;       // [B]       survivors per frame (input size of the hull sort)
+    std::uint32_t* hull_next; // [B]       next cluster to hand out in k_hull_thin
     // ---- generic
     std::uint32_t* tile_cnt;  // [B][max(tiles, ptiles)]
     std::uint32_t* status;    // [B]  error bits raised by kernels

@@ -21,23 +21,30 @@
 namespace lpl
 {
 constexpr int kHullThreads = 32;   // one warp per CTA: the hardware balances clusters of very different size
-constexpr int kHullCtasPerFrame = 256; // warp-stride over clusters; CTAs beyond the cluster count leave at once
+constexpr int kHullCtasPerFrame = 24;  // single-warp CTAs per frame (about one resident wave for a 154-frame batch);
+                                       // clusters are handed out dynamically, their sizes differ by orders of magnitude
 constexpr std::uint32_t kChainSmem = 512; // survivors swept from shared memory
 constexpr std::uint32_t kFilterAbove = 48;  // clusters above this are thinned by all lanes first
 constexpr std::uint32_t kLaneStack = 16;  // per-lane chain stack entries kept in shared memory
 
-// per-lane stack of positions: the first kLaneStack entries live in shared memory (pops are on the
-// critical path of the sweep), deeper ones spill to the lane's slice of a global scratch array
+// per-lane stack of (position, x, y): the first kLaneStack entries live in shared memory - a pop
+// is on the critical path of the sweep and must not cost a trip to L2 for the popped point's
+// coordinates - deeper ones spill to the lane's slice of a global scratch array (positions only).
+// Entries of the lanes are interleaved (entry k of lane l at k * stride + l): no bank conflicts
+// when the lanes work at the same depth.
 struct LaneStack
 {
-    std::uint32_t* sm;  // this lane's kLaneStack shared-memory entries
-    std::uint32_t* gl;  // this lane's global slice
-    __device__ __forceinline__ std::uint32_t get(std::uint32_t k) const { return k < kLaneStack ? sm[k] : gl[k]; }
-    __device__ __forceinline__ void set(std::uint32_t k, std::uint32_t v) const
+    std::uint32_t* sm;    // shared-memory positions, already offset by the lane
+    float2* smp;          // shared-memory coordinates, same layout
+    std::uint32_t stride; // lanes in the group
+    std::uint32_t* gl;    // this lane's global slice
+    __device__ __forceinline__ std::uint32_t get(std::uint32_t k) const { return k < kLaneStack ? sm[k * stride] : gl[k]; }
+    __device__ __forceinline__ void set(std::uint32_t k, std::uint32_t v, float2 xy) const
     {
         if (k < kLaneStack)
         {
-            sm[k] = v;
+            sm[k * stride] = v;
+            smp[k * stride] = xy;
         }
         else
         {
@@ -358,6 +365,29 @@ __global__ void __launch_bounds__(kTileThreads) k_hull_merge(Dev d, std::uint32_
 // ------------------------------------------------------------------------------------------
 // hull chains
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 elem_xy(const uint4& e)
+{
+    return make_float2(__uint_as_float(e.y), __uint_as_float(e.z));
+}
+
+__device__ __forceinline__ P2 stack_pt(const LaneStack& S, std::uint32_t k, const uint4* __restrict__ src)
+{
+    P2 p;
+    if (k < kLaneStack)
+    {
+        const float2 v = S.smp[k * S.stride];
+        p.x = static_cast<double>(v.x);
+        p.y = static_cast<double>(v.y);
+    }
+    else
+    {
+        const uint4 e = src[S.gl[k]];
+        p.x = static_cast<double>(__uint_as_float(e.y));
+        p.y = static_cast<double>(__uint_as_float(e.z));
+    }
+    return p;
+}
+
 __device__ __forceinline__ P2 elem_pt(const uint4& e)
 {
     P2 p;
@@ -366,14 +396,136 @@ __device__ __forceinline__ P2 elem_pt(const uint4& e)
     return p;
 }
 
-// Warp-wide thinning pass: lane l sweeps its contiguous chunk of src[0..m) with the lower chain
-// (left to right) and the upper chain (right to left, as the reference walks it); the union of
-// both survivor lists, in sorted order, is compacted into dst. stL / stU: global spill space for
-// the per-lane stacks (m entries each); smL / smU: 32 * kLaneStack shared-memory words each.
-// Returns the survivor count.
+// One lane's share of a thinning pass: the lower chain (left to right) and the upper chain (right to
+// left, as the reference walks it) over the contiguous chunk src[a..b). A point that is on neither
+// chain of its chunk cannot be on the cluster's hull. The next block of four elements is in flight
+// while the current one is swept.
+__device__ __forceinline__ void lane_chains(const uint4* __restrict__ src, std::uint32_t a, std::uint32_t b,
+                                            const LaneStack& L, const LaneStack& U, std::uint32_t& kl,
+                                            std::uint32_t& ku)
+{
+    kl = 0;
+    ku = 0;
+    if (b <= a)
+    {
+        return;
+    }
+    P2 s2 = {0.0, 0.0}, s1 = {0.0, 0.0};
+    uint4 nx[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+    {
+        nx[u] = ldg4(src + min(a + u, b - 1u));
+    }
+    for (std::uint32_t i0 = a; i0 < b; i0 += 4)
+    {
+        uint4 cu[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+        {
+            cu[u] = nx[u];
+            nx[u] = ldg4(src + min(i0 + 4u + u, b - 1u));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+        {
+            const std::uint32_t i = i0 + u;
+            if (i < b)
+            {
+                const P2 p = elem_pt(cu[u]);
+                while (kl >= 2 && not_left(s2, s1, p))
+                {
+                    --kl;
+                    s1 = s2;
+                    if (kl >= 2)
+                    {
+                        s2 = stack_pt(L, kl - 2, src);
+                    }
+                }
+                L.set(kl, i, elem_xy(cu[u]));
+                ++kl;
+                s2 = s1;
+                s1 = p;
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+    {
+        nx[u] = ldg4(src + (b - 1u - min(static_cast<std::uint32_t>(u), b - 1u - a)));
+    }
+    for (std::uint32_t done = 0; done < b - a; done += 4)
+    {
+        uint4 cu[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+        {
+            cu[u] = nx[u];
+            nx[u] = ldg4(src + (b - 1u - min(done + 4u + u, b - 1u - a)));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+        {
+            if (done + u < b - a)
+            {
+                const std::uint32_t i = b - 1u - (done + u);
+                const P2 p = elem_pt(cu[u]);
+                while (ku >= 2 && not_left(s2, s1, p))
+                {
+                    --ku;
+                    s1 = s2;
+                    if (ku >= 2)
+                    {
+                        s2 = stack_pt(U, ku - 2, src);
+                    }
+                }
+                U.set(ku, i, elem_xy(cu[u]));
+                ++ku;
+                s2 = s1;
+                s1 = p;
+            }
+        }
+    }
+}
+
+// survivors of one lane = union of its ascending lower list and its descending upper list
+__device__ __forceinline__ std::uint32_t lane_survivors(const LaneStack& L, const LaneStack& U, std::uint32_t kl,
+                                                        std::uint32_t ku)
+{
+    std::uint32_t cnt = 0;
+    std::uint32_t i = 0, j = ku;
+    while (i < kl || j > 0)
+    {
+        const std::uint32_t pl = i < kl ? L.get(i) : 0xffffffffu;
+        const std::uint32_t pu = j > 0 ? U.get(j - 1) : 0xffffffffu;
+        i += (pl <= pu) ? 1u : 0u;
+        j -= (pu <= pl) ? 1u : 0u;
+        ++cnt;
+    }
+    return cnt;
+}
+
+__device__ __forceinline__ void lane_emit(const uint4* __restrict__ src, uint4* __restrict__ dst, std::uint32_t w,
+                                          const LaneStack& L, const LaneStack& U, std::uint32_t kl, std::uint32_t ku)
+{
+    std::uint32_t i = 0, j = ku;
+    while (i < kl || j > 0)
+    {
+        const std::uint32_t pl = i < kl ? L.get(i) : 0xffffffffu;
+        const std::uint32_t pu = j > 0 ? U.get(j - 1) : 0xffffffffu;
+        i += (pl <= pu) ? 1u : 0u;
+        j -= (pu <= pl) ? 1u : 0u;
+        dst[w++] = ldg4(src + min(pl, pu));
+    }
+}
+
+// Warp-wide thinning pass: lane l sweeps its contiguous chunk of src[0..m); the survivor lists, in
+// sorted order, are compacted into dst. stL / stU: global spill space for the per-lane stacks
+// (m entries each); smL / smU / spL / spU: 32 * kLaneStack shared-memory entries each. Returns the
+// survivor count.
 __device__ std::uint32_t hull_filter(const uint4* __restrict__ src, std::uint32_t m, uint4* __restrict__ dst,
                                      std::uint32_t* __restrict__ stL, std::uint32_t* __restrict__ stU,
-                                     std::uint32_t* smL, std::uint32_t* smU)
+                                     std::uint32_t* smL, std::uint32_t* smU, float2* spL, float2* spU)
 {
     const std::uint32_t lane = lane_id();
     // balance the two sequential phases: a lane sweeps m / lanes points now and every lane leaves
@@ -385,116 +537,14 @@ __device__ std::uint32_t hull_filter(const uint4* __restrict__ src, std::uint32_
     }
     const std::uint32_t chunk = (m + lanes - 1u) / lanes;
     const std::uint32_t a = min(m, lane * chunk), b = min(m, a + chunk);
-    const LaneStack L{smL + lane * kLaneStack, stL + a};
-    const LaneStack U{smU + lane * kLaneStack, stU + a};
-    std::uint32_t kl = 0, ku = 0;
-    if (b > a)
-    {
-        P2 s2 = {0.0, 0.0}, s1 = {0.0, 0.0};
-        // the next block of four elements is in flight while the current one is swept
-        uint4 nx[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-        {
-            nx[u] = ldg4(src + min(a + u, b - 1u));
-        }
-        for (std::uint32_t i0 = a; i0 < b; i0 += 4)
-        {
-            uint4 cu[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-            {
-                cu[u] = nx[u];
-                nx[u] = ldg4(src + min(i0 + 4u + u, b - 1u));
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-            {
-                const std::uint32_t i = i0 + u;
-                if (i < b)
-                {
-                    const P2 p = elem_pt(cu[u]);
-                    while (kl >= 2 && not_left(s2, s1, p))
-                    {
-                        --kl;
-                        s1 = s2;
-                        if (kl >= 2)
-                        {
-                            s2 = elem_pt(ldg4(src + L.get(kl - 2)));
-                        }
-                    }
-                    L.set(kl, i);
-                    ++kl;
-                    s2 = s1;
-                    s1 = p;
-                }
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-        {
-            nx[u] = ldg4(src + (b - 1u - min(static_cast<std::uint32_t>(u), b - 1u - a)));
-        }
-        for (std::uint32_t done = 0; done < b - a; done += 4)
-        {
-            uint4 cu[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-            {
-                cu[u] = nx[u];
-                nx[u] = ldg4(src + (b - 1u - min(done + 4u + u, b - 1u - a)));
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-            {
-                if (done + u < b - a)
-                {
-                    const std::uint32_t i = b - 1u - (done + u);
-                    const P2 p = elem_pt(cu[u]);
-                    while (ku >= 2 && not_left(s2, s1, p))
-                    {
-                        --ku;
-                        s1 = s2;
-                        if (ku >= 2)
-                        {
-                            s2 = elem_pt(ldg4(src + U.get(ku - 2)));
-                        }
-                    }
-                    U.set(ku, i);
-                    ++ku;
-                    s2 = s1;
-                    s1 = p;
-                }
-            }
-        }
-    }
-    // union of the ascending lower list and the descending upper list
-    std::uint32_t cnt = 0;
-    {
-        std::uint32_t i = 0, j = ku;
-        while (i < kl || j > 0)
-        {
-            const std::uint32_t pl = i < kl ? L.get(i) : 0xffffffffu;
-            const std::uint32_t pu = j > 0 ? U.get(j - 1) : 0xffffffffu;
-            i += (pl <= pu) ? 1u : 0u;
-            j -= (pu <= pl) ? 1u : 0u;
-            ++cnt;
-        }
-    }
+    const LaneStack L{smL + lane, spL + lane, 32u, stL + a};
+    const LaneStack U{smU + lane, spU + lane, 32u, stU + a};
+    std::uint32_t kl, ku;
+    lane_chains(src, a, b, L, U, kl, ku);
+    const std::uint32_t cnt = lane_survivors(L, U, kl, ku);
     const std::uint32_t incl = warp_incl_scan(cnt);
     const std::uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-    {
-        std::uint32_t w = incl - cnt;
-        std::uint32_t i = 0, j = ku;
-        while (i < kl || j > 0)
-        {
-            const std::uint32_t pl = i < kl ? L.get(i) : 0xffffffffu;
-            const std::uint32_t pu = j > 0 ? U.get(j - 1) : 0xffffffffu;
-            i += (pl <= pu) ? 1u : 0u;
-            j -= (pu <= pl) ? 1u : 0u;
-            dst[w++] = ldg4(src + min(pl, pu));
-        }
-    }
+    lane_emit(src, dst, incl - cnt, L, U, kl, ku);
     __syncwarp();
     return total;
 }
@@ -546,6 +596,65 @@ constexpr std::uint32_t kFinDone = 0x80000000u;   // hull already written by k_h
 constexpr std::uint32_t kFinOther = 0x40000000u;  // survivors live in the second sort buffer
 constexpr std::uint32_t kFinalMax = 256;          // survivors swept by one thread (local-memory stack)
 
+constexpr std::uint32_t kFinPre = 0x20000000u;    // k_hull_thin_big already thinned the cluster once (into the other buffer)
+constexpr std::uint32_t kBigAbove = 1024;         // clusters above this get a CTA-wide first thinning pass
+constexpr int kBigThreads = 256;
+constexpr int kBigCtasPerFrame = 8;
+
+// Pass 0: the handful of very large clusters of a frame (walls, vegetation: up to ~20k points) would
+// leave one warp sweeping 600-point chunks per lane while everything else has finished; a whole
+// CTA thins them once first (256 chunks), the warp passes of k_hull_thin take over from there.
+// Also resets hfin for every cluster of the frame.
+__global__ void __launch_bounds__(kBigThreads) k_hull_thin_big(Dev d)
+{
+    extern __shared__ __align__(16) unsigned char s_big[]; // 2 x (positions + coordinates) x kBigThreads x kLaneStack
+    float2* s_xy = reinterpret_cast<float2*>(s_big);
+    std::uint32_t* s_pos = reinterpret_cast<std::uint32_t*>(s_xy + 2 * kBigThreads * kLaneStack);
+    __shared__ std::uint32_t s_scan[33];
+    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t K = d.n_clusters[f];
+    const std::size_t o = static_cast<std::size_t>(f) * d.cap;
+    const std::uint32_t* cstart = d.cstart + static_cast<std::size_t>(f) * (d.cap + 1);
+    const bool in_b = (sort_passes(d.n_h[f]) & 1u) != 0u;
+    const uint4* sorted = (in_b ? d.hsB : d.hsA) + o;
+    uint4* other = (in_b ? d.hsA : d.hsB) + o;
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+    {
+        d.hull_next[f] = 0; // hand-out counter of k_hull_thin
+    }
+    for (std::uint32_t c = blockIdx.x; c < K; c += gridDim.x)
+    {
+        const std::uint32_t seg = cstart[c];
+        const std::uint32_t m = cstart[c + 1] - seg;
+        if (m <= kBigAbove)
+        {
+            if (threadIdx.x == 0)
+            {
+                d.hfin[o + c] = 0;
+            }
+            continue;
+        }
+        const uint4* src = sorted + seg;
+        uint4* dst = other + seg;
+        const std::uint32_t chunk = (m + kBigThreads - 1u) / kBigThreads;
+        const std::uint32_t a = min(m, threadIdx.x * chunk), b = min(m, a + chunk);
+        const LaneStack L{s_pos + threadIdx.x, s_xy + threadIdx.x, kBigThreads, d.hstL + o + seg + a};
+        const LaneStack U{s_pos + kBigThreads * kLaneStack + threadIdx.x, s_xy + kBigThreads * kLaneStack + threadIdx.x,
+                          kBigThreads, d.hstU + o + seg + a};
+        std::uint32_t kl, ku;
+        lane_chains(src, a, b, L, U, kl, ku);
+        const std::uint32_t cnt = lane_survivors(L, U, kl, ku);
+        std::uint32_t total;
+        const std::uint32_t w = block_excl_scan(cnt, s_scan, &total);
+        lane_emit(src, dst, w, L, U, kl, ku);
+        if (threadIdx.x == 0)
+        {
+            d.hfin[o + c] = total | kFinPre;
+        }
+        __syncthreads(); // the stacks / s_scan are reused by the next cluster
+    }
+}
+
 // Pass 1, one warp per cluster above kFilterAbove points: thinning passes ping-pong between the two
 // sort buffers (the segment is private to the warp) until few enough points survive for a single
 // thread, or thinning stops paying (points in convex position), in which case the warp sweeps the
@@ -555,6 +664,7 @@ __global__ void __launch_bounds__(kHullThreads) k_hull_thin(Dev d)
     __shared__ float2 s_key[kChainSmem];
     __shared__ std::uint16_t s_st[kChainSmem + 2];
     __shared__ std::uint32_t s_lane[2][32 * kLaneStack];
+    __shared__ float2 s_lxy[2][32 * kLaneStack];
     const std::uint32_t f = blockIdx.y;
     const std::uint32_t K = d.n_clusters[f];
     const std::uint32_t lane = lane_id();
@@ -563,10 +673,36 @@ __global__ void __launch_bounds__(kHullThreads) k_hull_thin(Dev d)
     const bool in_b = (sort_passes(d.n_h[f]) & 1u) != 0u;
     uint4* sorted = (in_b ? d.hsB : d.hsA) + o;
     uint4* other = (in_b ? d.hsA : d.hsB) + o;
-    for (std::uint32_t c = blockIdx.x; c < K; c += gridDim.x)
+    while (true)
     {
+        std::uint32_t c = 0;
+        if (lane == 0)
+        {
+            c = atomicAdd(&d.hull_next[f], 1u);
+        }
+        c = __shfl_sync(0xffffffffu, c, 0);
+        if (c >= K)
+        {
+            break;
+        }
         const std::uint32_t seg = cstart[c];
         const std::uint32_t n = cstart[c + 1] - seg;
+#ifdef LPL_HULL_TRACE
+        const long long t_begin = clock64();
+        struct Trace
+        {
+            long long t0;
+            std::uint32_t f, c, n;
+            __device__ ~Trace()
+            {
+                const long long dt = clock64() - t0;
+                if (dt > 100000 && (threadIdx.x & 31u) == 0)
+                {
+                    printf("hull_thin frame %u cluster %u n %u cycles %lld\n", f, c, n, dt);
+                }
+            }
+        } trace{t_begin, f, c, n};
+#endif
         if (n <= kFilterAbove)
         {
             if (lane == 0)
@@ -580,19 +716,25 @@ __global__ void __launch_bounds__(kHullThreads) k_hull_thin(Dev d)
         uint4* nxt = other + seg;
         std::uint32_t m = n;
         bool in_other = false;
-        while (m > kFilterAbove)
+        const std::uint32_t pre = d.hfin[o + c];
+        if (pre & kFinPre)
         {
-            const std::uint32_t m2 = hull_filter(cur, m, nxt, d.hstL + o + seg, d.hstU + o + seg, s_lane[0], s_lane[1]);
+            // k_hull_thin_big left its survivors in the other buffer
+            m = pre & 0x1fffffffu;
+            cur = other + seg;
+            nxt = sorted + seg;
+            in_other = true;
+        }
+        bool stalled = (pre & kFinPre) != 0u && m * 4u > n * 3u;
+        while (m > kFilterAbove && !stalled)
+        {
+            const std::uint32_t m2 = hull_filter(cur, m, nxt, d.hstL + o + seg, d.hstU + o + seg, s_lane[0], s_lane[1], s_lxy[0], s_lxy[1]);
             uint4* t = cur;
             cur = nxt;
             nxt = t;
             in_other = !in_other;
-            const bool stalled = m2 * 4u > m * 3u; // convex-position input: thinning does not pay
+            stalled = m2 * 4u > m * 3u; // convex-position input: thinning does not pay
             m = m2;
-            if (stalled)
-            {
-                break;
-            }
         }
         if (m <= kFinalMax)
         {
@@ -767,6 +909,10 @@ void launch_hulls(Ctx* c, std::uint32_t nf)
         k_hull_merge<<<dim3(d.tiles, nf), kTileThreads, 0, s>>>(d, p);
         mark(c, "hull_merge");
     }
+    constexpr std::size_t big_smem = static_cast<std::size_t>(2) * kBigThreads * kLaneStack * (sizeof(float2) + sizeof(std::uint32_t));
+    cudaFuncSetAttribute(k_hull_thin_big, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(big_smem));
+    k_hull_thin_big<<<dim3(kBigCtasPerFrame, nf), kBigThreads, big_smem, s>>>(d);
+    mark(c, "hull_thin_big");
     k_hull_thin<<<dim3(kHullCtasPerFrame, nf), kHullThreads, 0, s>>>(d);
     mark(c, "hull_thin");
     k_hull_final<<<dim3(16, nf), 64, 0, s>>>(d);

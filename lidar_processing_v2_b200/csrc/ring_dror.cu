@@ -202,32 +202,77 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// Two grid levels share one cell index space: level 0 = 1 m cells over +-128 m (cells
+// [0, kDrorLevelCells)), level 1 = 0.25 m cells over the inner +-32 m (cells [kDrorLevelCells,
+// 2 * kDrorLevelCells)). A point lives in exactly one level (the fine one iff it lies inside the
+// inner square), a query scans its search box in both. The search radius grows with range
+// (0.1 m below 5 m, 0.02 * range beyond), so near the sensor - where a 1 m cell holds hundreds of
+// points - the fine level cuts the candidates per query several times.
+constexpr float kDrorInner = 32.0f;
+constexpr float kDrorFineScale = 4.0f;
+
 __device__ __forceinline__ int dror_cell_coord(float v)
 {
     int c = static_cast<int>(floorf(v)) + kDrorGrid / 2;
     return min(max(c, 0), kDrorGrid - 1);
 }
 
-// cells a query's search disc can touch (conservative cover of the float predicate)
+__device__ __forceinline__ bool dror_is_inner(float x, float y)
+{
+    return x >= -kDrorInner && x < kDrorInner && y >= -kDrorInner && y < kDrorInner;
+}
+
+__device__ __forceinline__ int dror_point_cell(const float4& p)
+{
+    if (dror_is_inner(p.x, p.y))
+    {
+        return kDrorLevelCells + dror_cell_coord(p.y * kDrorFineScale) * kDrorGrid + dror_cell_coord(p.x * kDrorFineScale);
+    }
+    return dror_cell_coord(p.y) * kDrorGrid + dror_cell_coord(p.x);
+}
+
+// cells a query's search disc can touch on one level (conservative cover of the float predicate)
 struct DrorBox
 {
-    int x0, x1, y0, y1;
+    int x0, x1, y0, y1; // inclusive cell coordinates; empty when y1 < y0
+    int base;           // first cell index of the level
 };
 
-__device__ __forceinline__ DrorBox dror_box(const float4& p, float r_sqr)
+__device__ __forceinline__ DrorBox dror_box(const float4& p, float r_sqr, int level)
 {
     const float rc = sqrtf(r_sqr) * 1.001f + 1e-4f;
+    const float xl = p.x - rc, xh = p.x + rc, yl = p.y - rc, yh = p.y + rc;
     DrorBox b;
-    b.x0 = dror_cell_coord(p.x - rc);
-    b.x1 = dror_cell_coord(p.x + rc);
-    b.y0 = dror_cell_coord(p.y - rc);
-    b.y1 = dror_cell_coord(p.y + rc);
+    if (level == 0)
+    {
+        b.base = 0;
+        b.x0 = dror_cell_coord(xl);
+        b.x1 = dror_cell_coord(xh);
+        b.y0 = dror_cell_coord(yl);
+        b.y1 = dror_cell_coord(yh);
+        if (xl >= -kDrorInner && xh < kDrorInner && yl >= -kDrorInner && yh < kDrorInner)
+        {
+            b.y1 = b.y0 - 1; // box inside the inner square: every candidate lives on the fine level
+        }
+    }
+    else
+    {
+        b.base = kDrorLevelCells;
+        b.x0 = dror_cell_coord(xl * kDrorFineScale);
+        b.x1 = dror_cell_coord(xh * kDrorFineScale);
+        b.y0 = dror_cell_coord(yl * kDrorFineScale);
+        b.y1 = dror_cell_coord(yh * kDrorFineScale);
+        if (!(xh >= -kDrorInner && xl < kDrorInner && yh >= -kDrorInner && yl < kDrorInner))
+        {
+            b.y1 = b.y0 - 1; // box misses the inner square
+        }
+    }
     return b;
 }
 
 // Only ~4 % of the points reach the exhaustive search, and only the points near them can be
-// their neighbours: every unresolved query marks the cells of its search box in a per-frame
-// bitmap (8 KB), and the grid is then built from the points of marked cells alone.
+// their neighbours: every unresolved query marks the cells of its search boxes in a per-frame
+// bitmap (16 KB), and the grid is then built from the points of marked cells alone.
 __global__ void __launch_bounds__(256) k_dror_mark(Dev d, DrorParams prm)
 {
     const std::uint32_t f = blockIdx.y;
@@ -237,16 +282,24 @@ __global__ void __launch_bounds__(256) k_dror_mark(Dev d, DrorParams prm)
     {
         const std::uint32_t i = d.unres[static_cast<std::size_t>(f) * d.cap + u];
         const float4 p = d.pts_in[static_cast<std::size_t>(f) * d.cap + i];
-        const DrorBox b = dror_box(p, dror_radius_sqr(p.x, p.y, prm));
-        for (int cy = b.y0; cy <= b.y1; ++cy)
+        const float r_sqr = dror_radius_sqr(p.x, p.y, prm);
+        for (int level = 0; level < 2; ++level)
         {
-            for (int cx = b.x0; cx <= b.x1; ++cx)
+            const DrorBox b = dror_box(p, r_sqr, level);
+            for (int cy = b.y0; cy <= b.y1; ++cy)
             {
-                const std::uint32_t cell = static_cast<std::uint32_t>(cy * kDrorGrid + cx);
-                const std::uint32_t bit = 1u << (cell & 31u);
-                if ((__ldcg(mask + (cell >> 5)) & bit) == 0u)
+                // the cells x0..x1 of a row are consecutive bits: one OR per touched word
+                const std::uint32_t first = static_cast<std::uint32_t>(b.base + cy * kDrorGrid + b.x0);
+                const std::uint32_t last = static_cast<std::uint32_t>(b.base + cy * kDrorGrid + b.x1);
+                for (std::uint32_t w = first >> 5; w <= (last >> 5); ++w)
                 {
-                    atomicOr(mask + (cell >> 5), bit);
+                    const std::uint32_t lo = (w == (first >> 5)) ? (first & 31u) : 0u;
+                    const std::uint32_t hi = (w == (last >> 5)) ? (last & 31u) : 31u;
+                    const std::uint32_t bits = (0xffffffffu >> (31u - hi)) & (0xffffffffu << lo);
+                    if ((__ldcg(mask + w) & bits) != bits)
+                    {
+                        atomicOr(mask + w, bits);
+                    }
                 }
             }
         }
@@ -271,7 +324,7 @@ __global__ void __launch_bounds__(256) k_dror_grid_count(Dev d)
     if (i < n)
     {
         const float4 p = d.pts_in[static_cast<std::size_t>(f) * d.cap + i];
-        const int c = dror_cell_coord(p.y) * kDrorGrid + dror_cell_coord(p.x);
+        const int c = dror_point_cell(p);
         if (dror_marked(d.grid_mask + static_cast<std::size_t>(f) * (kDrorCells / 32), c))
         {
             cell = c;
@@ -298,7 +351,7 @@ __global__ void __launch_bounds__(256) k_dror_grid_scatter(Dev d)
     if (i < n)
     {
         p = d.pts_in[static_cast<std::size_t>(f) * d.cap + i];
-        const int c = dror_cell_coord(p.y) * kDrorGrid + dror_cell_coord(p.x);
+        const int c = dror_point_cell(p);
         if (dror_marked(d.grid_mask + static_cast<std::size_t>(f) * (kDrorCells / 32), c))
         {
             cell = c;
@@ -346,8 +399,10 @@ __global__ void __launch_bounds__(kDrorQueryWarps * 32) k_dror_query(Dev d, Dror
         const std::uint32_t i = d.unres[static_cast<std::size_t>(f) * d.cap + u];
         const float4 p = d.pts_in[static_cast<std::size_t>(f) * d.cap + i];
         const float r_sqr = dror_radius_sqr(p.x, p.y, prm);
-        const DrorBox bx = dror_box(p, r_sqr);
         std::uint32_t cnt = 0;
+        for (int level = 1; level >= 0 && cnt < prm.min_neighbours; --level)
+        {
+        const DrorBox bx = dror_box(p, r_sqr, level);
         for (int cy0 = bx.y0; cy0 <= bx.y1 && cnt < prm.min_neighbours; cy0 += kDrorGroup)
         {
             // lane gl fetches the bounds of row cy0 + gl
@@ -355,8 +410,8 @@ __global__ void __launch_bounds__(kDrorQueryWarps * 32) k_dror_query(Dev d, Dror
             std::uint32_t ra = 0, rb = 0;
             if (cy <= bx.y1)
             {
-                ra = start[cy * kDrorGrid + bx.x0];
-                rb = start[cy * kDrorGrid + bx.x1 + 1];
+                ra = start[bx.base + cy * kDrorGrid + bx.x0];
+                rb = start[bx.base + cy * kDrorGrid + bx.x1 + 1];
             }
             const int rows = min(kDrorGroup, bx.y1 - cy0 + 1);
             for (int r = 0; r < rows && cnt < prm.min_neighbours; ++r)
@@ -389,6 +444,7 @@ __global__ void __launch_bounds__(kDrorQueryWarps * 32) k_dror_query(Dev d, Dror
                     cnt += hits;
                 }
             }
+        }
         }
         if (gl == 0 && cnt < prm.min_neighbours)
         {
