@@ -1,15 +1,16 @@
-// Drop-in Polygonizer::convexHull over the B200 C ABI.
+// Drop-in Polygonizer over the B200 C ABI.
 // Replaces lidar_processing_lib/include/lidar_processing_lib/polygonizer.hpp:41-243 /
-// src/polygonizer.cpp:33-91 for the caller in src/processor/src/processor.cpp:663. The batched
-// entry point the GPU is built for is lpl_cluster_hulls (all clusters of a frame in one call, see
-// hulls()); convexHull() keeps the reference's one-polygon-per-call signature.
-// The oriented-bounding-box members are declared so that the node still compiles, but they are
-// outside the hot path (dead code in the node: processor.cpp:676 `perform_polygon_simplification =
-// false`) and throw.
+// src/polygonizer.cpp:33-362 for the callers in src/processor/src/processor.cpp:663,704. The batched
+// entry points the GPU is built for are lpl_cluster_hulls (all clusters of a frame in one call) and
+// lpl_bounding_boxes (all hulls in one call, see boundingBoxes()); convexHull() and the
+// boundingBox*() members keep the reference's one-polygon-per-call signatures.
+// findAntipodalPairsOfConvexHull is a few dozen sequential steps on a hull of ~7 vertices: it runs
+// inside the box kernel on the device and, as a public member, here on the host (same arithmetic).
 #ifndef LIDAR_PROCESSING_LIB__POLYGONIZER_HPP
 #define LIDAR_PROCESSING_LIB__POLYGONIZER_HPP
 
 #include <array>
+#include <cmath>
 #include <cstdint>
 #include <stdexcept>
 #include <vector>
@@ -93,18 +94,80 @@ class Polygonizer final
         indices.resize(count);
     }
 
-    void findAntipodalPairsOfConvexHull(const std::vector<PointXY>&, std::vector<AntipodalPair>&)
+    /// Shamos' antipodal pairs of a convex polygon (src/polygonizer.cpp:93-163), host-side.
+    void findAntipodalPairsOfConvexHull(const std::vector<PointXY>& h, std::vector<AntipodalPair>& pairs)
     {
-        throw std::logic_error("Polygonizer::findAntipodalPairsOfConvexHull is outside the lpl_b200 hot path");
+        pairs.clear();
+        const auto n = static_cast<std::int32_t>(h.size());
+        if (n < 2)
+        {
+            return;
+        }
+        const auto area = [](const PointXY& p1, const PointXY& p2, const PointXY& p3) {
+            return std::fabs((p1.x * (p2.y - p3.y) + p2.x * (p3.y - p1.y) + p3.x * (p1.y - p2.y)) * 0.5);
+        };
+        const auto nx = [n](std::int32_t k) { return (k + 1 == n) ? 0 : (k + 1); };
+        const std::int32_t i0 = n - 1;
+        std::int32_t i = 0, j = 1;
+        while (area(h[i], h[nx(i)], h[nx(j)]) > area(h[i], h[nx(i)], h[j]))
+        {
+            j = nx(j);
+        }
+        const std::int32_t j0 = j;
+        while (i != j0)
+        {
+            i = nx(i);
+            pairs.push_back({i, j});
+            while (area(h[i], h[nx(i)], h[nx(j)]) > area(h[i], h[nx(i)], h[j]))
+            {
+                j = nx(j);
+                if (i == j0 && j == i0)
+                {
+                    return;
+                }
+                pairs.push_back({i, j});
+            }
+            if (area(h[j], h[nx(i)], h[nx(j)]) == area(h[i], h[nx(i)], h[j]))
+            {
+                pairs.push_back((i == j0 && j == i0) ? AntipodalPair{nx(i), j} : AntipodalPair{i, nx(j)});
+            }
+        }
     }
-    BoundingBox boundingBoxRotatingCalipers(const std::vector<PointXY>&)
+
+    /// Minimum-area oriented box by rotating calipers (src/polygonizer.cpp:165-278).
+    BoundingBox boundingBoxRotatingCalipers(const std::vector<PointXY>& convex_hull_points)
     {
-        throw std::logic_error("Polygonizer::boundingBoxRotatingCalipers is outside the lpl_b200 hot path");
+        return box(convex_hull_points, LPL_BOX_ROTATING_CALIPERS, "Polygonizer::boundingBoxRotatingCalipers");
     }
-    BoundingBox boundingBoxPrincipalComponentAnalysis(const std::vector<PointXY>&)
+
+    /// Principal-axes box (src/polygonizer.cpp:280-362).
+    BoundingBox boundingBoxPrincipalComponentAnalysis(const std::vector<PointXY>& convex_hull_points)
     {
-        throw std::logic_error("Polygonizer::boundingBoxPrincipalComponentAnalysis is outside the lpl_b200 hot path");
+        return box(convex_hull_points, LPL_BOX_PCA, "Polygonizer::boundingBoxPrincipalComponentAnalysis");
     }
+
+    /// Batched form: hull k is hull_points[offsets[k] .. offsets[k + 1]).
+    void boundingBoxes(const std::vector<PointXY>& hull_points, const std::vector<std::uint32_t>& offsets,
+                       std::vector<BoundingBox>& boxes, int method = LPL_BOX_ROTATING_CALIPERS)
+    {
+        boxes.clear();
+        if (offsets.size() < 2)
+        {
+            return;
+        }
+        const auto k = static_cast<std::uint32_t>(offsets.size() - 1);
+        const auto n = static_cast<std::uint32_t>(hull_points.size());
+        lpl_ctx* ctx = handle_.ensure(n > config_.max_points ? n : config_.max_points);
+        std::vector<lpl_bbox> raw(k);
+        detail::check(lpl_bounding_boxes(ctx, hull_points.data(), sizeof(PointXY), offsets.data(), k, method, raw.data()),
+                      ctx, "Polygonizer::boundingBoxes");
+        boxes.resize(k);
+        for (std::uint32_t b = 0; b < k; ++b)
+        {
+            boxes[b] = convert(raw[b]);
+        }
+    }
+
     template <typename PointT>
     void concaveHull(const std::vector<PointT>&, std::vector<std::int32_t>&)
     {
@@ -115,6 +178,35 @@ class Polygonizer final
     const PolygonizerConfiguration& config() const noexcept { return config_; }
 
   private:
+    static BoundingBox convert(const lpl_bbox& r)
+    {
+        BoundingBox b{};
+        for (int k = 0; k < 4; ++k)
+        {
+            b.corners[k] = {r.corners[k][0], r.corners[k][1]};
+        }
+        b.area = r.area;
+        b.angle_rad = r.angle_rad;
+        b.is_valid = r.is_valid != 0;
+        return b;
+    }
+
+    BoundingBox box(const std::vector<PointXY>& hull, int method, const char* what)
+    {
+        BoundingBox invalid{};
+        invalid.is_valid = false;
+        if (hull.size() < 3)
+        {
+            return invalid; // src/polygonizer.cpp:172-175, 285-289
+        }
+        const auto n = static_cast<std::uint32_t>(hull.size());
+        lpl_ctx* ctx = handle_.ensure(n > config_.max_points ? n : config_.max_points);
+        const std::uint32_t offsets[2] = {0u, n};
+        lpl_bbox raw{};
+        detail::check(lpl_bounding_boxes(ctx, hull.data(), sizeof(PointXY), offsets, 1, method, &raw), ctx, what);
+        return convert(raw);
+    }
+
     PolygonizerConfiguration config_{};
     detail::Handle handle_;
 };

@@ -17,6 +17,8 @@
  *   lpl_cluster             Clusterer::cluster                 .../clusterer.hpp:93-94
  *   lpl_convex_hull         Polygonizer::convexHull            .../polygonizer.hpp:105-106
  *   lpl_cluster_hulls       per-label gather + convexHull      src/processor/src/processor.cpp:627-663
+ *   lpl_bounding_boxes      Polygonizer::boundingBoxRotatingCalipers / boundingBoxPrincipalComponentAnalysis
+ *                           (+ findAntipodalPairsOfConvexHull)  .../polygonizer.hpp:108-123, src/polygonizer.cpp:93-362
  *   lpl_pipeline_*          Processor::run (segment -> split -> cluster -> hulls), batched
  *                                                              src/processor/src/processor.cpp:552-663
  */
@@ -133,6 +135,28 @@ int lpl_cluster_hulls(lpl_ctx* ctx, const void* points, size_t stride, const int
                       uint32_t num_clusters, uint32_t* hull_offsets, int32_t* hull_indices,
                       float* hull_xy, float* zminmax);
 
+/* BoundingBox (polygonizer.hpp:75-81) with the same field meaning; is_valid = 0 leaves the rest zero. */
+typedef struct lpl_bbox
+{
+    double corners[4][2];
+    float area;
+    float angle_rad;
+    int32_t is_valid;
+    int32_t reserved;
+} lpl_bbox;
+
+enum
+{
+    LPL_BOX_ROTATING_CALIPERS = 0, /* Polygonizer::boundingBoxRotatingCalipers (polygonizer.cpp:165-278)           */
+    LPL_BOX_PCA = 1                /* Polygonizer::boundingBoxPrincipalComponentAnalysis (polygonizer.cpp:280-362) */
+};
+
+/* Oriented bounding boxes of num_hulls convex polygons in one call. xy: (x, y) doubles `stride`
+ * bytes apart, all hulls back to back, vertices in the order convexHull returns them;
+ * offsets[num_hulls + 1] delimits the hulls; boxes_out[num_hulls]. */
+int lpl_bounding_boxes(lpl_ctx* ctx, const void* xy, size_t stride, const uint32_t* offsets, uint32_t num_hulls,
+                       int method, lpl_bbox* boxes_out);
+
 /* ---- batched, chained pipeline ----------------------------------------------------------- */
 enum
 {
@@ -141,7 +165,8 @@ enum
     LPL_STAGE_SEGMENT = 4,
     LPL_STAGE_CLUSTER = 8,  /* on OBSTACLE points, cloud order */
     LPL_STAGE_HULLS = 16,
-    LPL_STAGE_ALL = 31
+    LPL_STAGE_ALL = 31,     /* the reference node's chain (processor.cpp:552-663) */
+    LPL_STAGE_BOXES = 32    /* rotating-calipers box per cluster hull (disabled in the node: processor.cpp:676) */
 };
 
 /* One frame of input: n points of 4 floats (x, y, z, unused), contiguous. */
@@ -174,6 +199,7 @@ typedef struct lpl_frame_result
     uint32_t* hull_indices;   /* [num_hull_vertices] index into the obstacle cloud */
     float* hull_xy;           /* [num_hull_vertices][2]                            */
     float* zminmax;           /* [num_clusters][2]                                 */
+    lpl_bbox* boxes;          /* [num_clusters] (only if the batch ran LPL_STAGE_BOXES) */
     uint8_t* bgr;             /* [H*W*3] (only if the batch ran with lpl_pipeline_want_image) */
     /* counts, filled by lpl_pipeline_counts / lpl_pipeline_download */
     uint32_t n, num_valid, num_obstacles, num_clusters, num_hull_vertices;
@@ -202,6 +228,7 @@ typedef struct lpl_batch_result
     uint32_t* hull_indices;
     float* hull_xy;           /* 2 floats per element                              */
     float* zminmax;           /* 2 floats per element                              */
+    lpl_bbox* boxes;          /* one box per element (LPL_STAGE_BOXES)             */
 } lpl_batch_result;
 int lpl_pipeline_download_batch(lpl_ctx* ctx, uint32_t num_frames, lpl_batch_result* res);
 

@@ -7,8 +7,12 @@ and a thin ctypes binding used by the tests and bench.py.
 from .build import SO_PATH, build_native  # noqa: F401
 from .native import (  # noqa: F401
     JCP_AS_REFERENCE,
+    BBOX_DTYPE,
+    BOX_PCA,
+    BOX_ROTATING_CALIPERS,
     JCP_CLEAN,
     STAGE_ALL,
+    STAGE_BOXES,
     STAGE_CLUSTER,
     STAGE_DROR,
     STAGE_HULLS,

@@ -137,6 +137,7 @@ void carve(Dev& d, Carver& cv, int npx, int ncell_cap, std::uint32_t** mt_raw)
     cv.take(d.hseg_cnt, B * cap);
     cv.take(d.n_h, B);
     cv.take(d.hull_next, B);
+    cv.take(d.boxes, B * cap);
     const std::size_t tl = std::max<std::size_t>(d.tiles, d.ptiles);
     cv.take(d.tile_cnt, B * tl);
     cv.take(d.status, B);
@@ -728,6 +729,10 @@ int lpl_pipeline_run(lpl_ctx* ctx, std::uint32_t nf, std::uint32_t stages)
     {
         launch_hulls(&c, nf);
     }
+    if ((stages & LPL_STAGE_BOXES) && (stages & LPL_STAGE_HULLS))
+    {
+        launch_boxes(&c, nf, LPL_BOX_ROTATING_CALIPERS);
+    }
     LPL_TRY(cudaGetLastError());
     return LPL_OK;
 }
@@ -834,6 +839,10 @@ int lpl_pipeline_download(lpl_ctx* ctx, std::uint32_t f, lpl_frame_result* r)
     if (r->zminmax != nullptr && r->num_clusters != 0)
     {
         LPL_TRY(cudaMemcpyAsync(r->zminmax, d.zminmax + o, sizeof(float2) * r->num_clusters, k, c.stream));
+    }
+    if (r->boxes != nullptr && r->num_clusters != 0)
+    {
+        LPL_TRY(cudaMemcpyAsync(r->boxes, d.boxes + o, sizeof(ObbBox) * r->num_clusters, k, c.stream));
     }
     if (r->bgr != nullptr)
     {
@@ -1069,6 +1078,65 @@ int lpl_cluster_hulls(lpl_ctx* ctx, const void* points, std::size_t stride, cons
     return LPL_OK;
 }
 
+static_assert(sizeof(lpl_bbox) == sizeof(ObbBox), "lpl_bbox and the device box record share one layout");
+
+int lpl_bounding_boxes(lpl_ctx* ctx, const void* xy, std::size_t stride, const std::uint32_t* offsets,
+                       std::uint32_t num_hulls, int method, lpl_bbox* boxes_out)
+{
+    if (ctx == nullptr || (num_hulls != 0 && (offsets == nullptr || boxes_out == nullptr)) || stride < 16 ||
+        (method != LPL_BOX_ROTATING_CALIPERS && method != LPL_BOX_PCA))
+    {
+        return fail(ctx, LPL_ERR_INVALID_ARGUMENT, "bad bounding-box request");
+    }
+    if (num_hulls == 0)
+    {
+        return LPL_OK;
+    }
+    Ctx& c = ctx->c;
+    Dev& d = c.d;
+    const std::size_t total = offsets[num_hulls];
+    for (std::uint32_t k = 0; k < num_hulls; ++k)
+    {
+        if (offsets[k] > offsets[k + 1])
+        {
+            return fail(ctx, LPL_ERR_INVALID_ARGUMENT, "hull offsets must be non-decreasing");
+        }
+    }
+    const std::size_t room = static_cast<std::size_t>(d.B) * d.cap;
+    if (total > room || num_hulls >= room)
+    {
+        return fail(ctx, LPL_ERR_CAPACITY, "more hull vertices / hulls than the context was created for");
+    }
+    if (total != 0 && xy == nullptr)
+    {
+        return fail(ctx, LPL_ERR_INVALID_ARGUMENT, "null hull points");
+    }
+    LPL_TRY(cudaSetDevice(c.device));
+    const std::size_t need = total * 16 + (static_cast<std::size_t>(num_hulls) + 1) * 4;
+    if (ensure_stage(ctx, need) != 0)
+    {
+        return LPL_ERR_CUDA;
+    }
+    LPL_TRY(cudaStreamSynchronize(c.stream));
+    auto* base = static_cast<char*>(c.h_stage);
+    pack(base, 16, xy, stride, 16, static_cast<std::uint32_t>(total));
+    std::memcpy(base + total * 16, offsets, (static_cast<std::size_t>(num_hulls) + 1) * 4);
+    // device scratch that is idle outside a pipeline run: the hull sort buffer and the segment starts
+    auto* dxy = reinterpret_cast<double2*>(d.hsA);
+    std::uint32_t* doff = d.cstart;
+    if (total != 0)
+    {
+        LPL_TRY(cudaMemcpyAsync(dxy, base, total * 16, cudaMemcpyHostToDevice, c.stream));
+    }
+    LPL_TRY(cudaMemcpyAsync(doff, base + total * 16, (static_cast<std::size_t>(num_hulls) + 1) * 4, cudaMemcpyHostToDevice,
+                            c.stream));
+    launch_boxes_hulls(&c, dxy, doff, num_hulls, method, d.boxes);
+    LPL_TRY(cudaMemcpyAsync(boxes_out, d.boxes, sizeof(ObbBox) * num_hulls, cudaMemcpyDeviceToHost, c.stream));
+    LPL_TRY(cudaStreamSynchronize(c.stream));
+    LPL_TRY(cudaGetLastError());
+    return LPL_OK;
+}
+
 int lpl_convex_hull(lpl_ctx* ctx, const void* xy, std::size_t stride, std::uint32_t n, std::int32_t* indices_out,
                     std::uint32_t* count_out)
 {
@@ -1159,6 +1227,7 @@ int lpl_pipeline_download_batch(lpl_ctx* ctx, std::uint32_t nf, lpl_batch_result
     LPL_TRY(plane(r->hull_indices, d.hull_idx, 4, d.cap, mx[4]));
     LPL_TRY(plane(r->hull_xy, d.hull_xy, 8, d.cap, mx[4]));
     LPL_TRY(plane(r->zminmax, d.zminmax, 8, d.cap, mx[3]));
+    LPL_TRY(plane(r->boxes, d.boxes, sizeof(ObbBox), d.cap, mx[3]));
     LPL_TRY(cudaStreamSynchronize(c.stream));
     return LPL_OK;
 }

@@ -67,6 +67,16 @@ struct ClusterParams
     std::uint32_t min_cluster_size;
 };
 
+// oriented bounding box of one hull (binary layout = lpl_bbox of the C ABI)
+struct ObbBox
+{
+    double c[8]; // four corners (x, y)
+    float area;
+    float angle;
+    std::int32_t valid;
+    std::int32_t pad;
+};
+
 // All device buffers of a context. Pointers are to the start of frame 0; frame f lives at
 // ptr + f * stride (stride noted per field).
 struct Dev
@@ -173,6 +183,7 @@ struct Dev
     std::uint32_t* hseg_cnt;  // [B][cap]  per cluster: points that survive the octagon filter
     std::uint32_t* n_h;       // [B]       survivors per frame (input size of the hull sort)
     std::uint32_t* hull_next; // [B]       next cluster to hand out in k_hull_thin
+    ObbBox* boxes;            // [B][cap]  oriented bounding box per cluster (LPL_STAGE_BOXES)
     // ---- generic
     std::uint32_t* tile_cnt;  // [B][max(tiles, ptiles)]
     std::uint32_t* status;    // [B]  error bits raised by kernels
@@ -507,6 +518,8 @@ void launch_segment(Ctx* c, std::uint32_t nf, bool want_image);
 void launch_take_obstacles(Ctx* c, std::uint32_t nf);
 void launch_cluster(Ctx* c, std::uint32_t nf);
 void launch_hulls(Ctx* c, std::uint32_t nf);
+void launch_boxes(Ctx* c, std::uint32_t nf, int method);
+void launch_boxes_hulls(Ctx* c, const double2* xy, const std::uint32_t* off, std::uint32_t K, int method, ObbBox* out);
 
 struct Ctx
 {

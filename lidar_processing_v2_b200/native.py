@@ -23,6 +23,11 @@ JCP_CLEAN = 1
 
 STAGE_RING, STAGE_DROR, STAGE_SEGMENT, STAGE_CLUSTER, STAGE_HULLS = 1, 2, 4, 8, 16
 STAGE_ALL = 31
+STAGE_BOXES = 32
+BOX_ROTATING_CALIPERS, BOX_PCA = 0, 1
+# numpy view of lpl_bbox (80 bytes)
+BBOX_DTYPE = np.dtype([("corners", np.float64, (4, 2)), ("area", np.float32), ("angle_rad", np.float32),
+                       ("is_valid", np.int32), ("reserved", np.int32)])
 
 # every symbol include/lpl_b200.h declares (tests check that the library exports them all)
 EXPORTS = [
@@ -30,7 +35,7 @@ EXPORTS = [
     "lpl_segmenter_default_cfg", "lpl_dror_default_cfg", "lpl_cluster_default_cfg",
     "lpl_segmenter_config", "lpl_dror_config", "lpl_cluster_config", "lpl_set_jcp_mode",
     "lpl_ring_partition", "lpl_dror_filter", "lpl_segment", "lpl_cluster", "lpl_convex_hull",
-    "lpl_cluster_hulls",
+    "lpl_cluster_hulls", "lpl_bounding_boxes",
     "lpl_pipeline_upload", "lpl_pipeline_upload_device", "lpl_pipeline_run", "lpl_pipeline_sync",
     "lpl_pipeline_want_image", "lpl_pipeline_counts", "lpl_pipeline_download",
     "lpl_pipeline_download_batch", "lpl_host_alloc", "lpl_host_free",
@@ -95,6 +100,7 @@ class FrameResult(C.Structure):
         ("hull_indices", C.c_void_p),
         ("hull_xy", C.c_void_p),
         ("zminmax", C.c_void_p),
+        ("boxes", C.c_void_p),
         ("bgr", C.c_void_p),
         ("n", C.c_uint32),
         ("num_valid", C.c_uint32),
@@ -117,6 +123,7 @@ class BatchResult(C.Structure):
         ("hull_indices", C.c_void_p),
         ("hull_xy", C.c_void_p),
         ("zminmax", C.c_void_p),
+        ("boxes", C.c_void_p),
     ]
 
 
@@ -162,6 +169,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     L.lpl_cluster.argtypes = [vp, vp, sz, u32, vp, C.POINTER(u32)]
     L.lpl_convex_hull.argtypes = [vp, vp, sz, u32, vp, C.POINTER(u32)]
     L.lpl_cluster_hulls.argtypes = [vp, vp, sz, vp, u32, u32, vp, vp, vp, vp]
+    L.lpl_bounding_boxes.argtypes = [vp, vp, sz, vp, u32, C.c_int, vp]
     L.lpl_pipeline_upload.argtypes = [vp, C.POINTER(Frame), u32]
     L.lpl_pipeline_upload_device.argtypes = [vp, C.POINTER(Frame), u32]
     L.lpl_pipeline_run.argtypes = [vp, u32, u32]
@@ -234,7 +242,7 @@ class BatchBuffers:
     PLANES = (("labels_u8", np.uint8, 1), ("noise", np.uint8, 1), ("ring", np.uint16, 1),
               ("obstacle_index", np.uint32, 1), ("cluster_labels", np.int32, 1),
               ("hull_offsets", np.uint32, 1), ("hull_indices", np.uint32, 1),
-              ("hull_xy", np.float32, 2), ("zminmax", np.float32, 2))
+              ("hull_xy", np.float32, 2), ("zminmax", np.float32, 2), ("boxes", BBOX_DTYPE, 1))
 
     def __init__(self, max_frames: int, stride: int, want=("labels_u8", "obstacle_index", "cluster_labels",
                                                            "hull_offsets", "hull_xy", "zminmax")):
@@ -252,7 +260,7 @@ class BatchBuffers:
         mx = counts.max(axis=1)
         width = dict(labels_u8=mx[0], noise=mx[0], ring=2 * mx[0], obstacle_index=4 * mx[2],
                      cluster_labels=4 * mx[2], hull_offsets=4 * (mx[3] + 1), hull_indices=4 * mx[4],
-                     hull_xy=8 * mx[4], zminmax=8 * mx[3])
+                     hull_xy=8 * mx[4], zminmax=8 * mx[3], boxes=80 * mx[3])
         return int(sum(int(width[k]) for k in self.planes) * nf + counts.size * 4)
 
     def close(self):
@@ -366,6 +374,16 @@ class Context:
                                            C.byref(cnt)))
         return idx[: cnt.value].copy()
 
+    def bounding_boxes(self, hull_xy, offsets, method: int = BOX_ROTATING_CALIPERS) -> np.ndarray:
+        """Oriented boxes of len(offsets) - 1 convex hulls given back to back in hull_xy ((m, 2) doubles)."""
+        a = np.ascontiguousarray(hull_xy, dtype=np.float64).reshape(-1, 2)
+        off = np.ascontiguousarray(offsets, dtype=np.uint32)
+        K = max(len(off) - 1, 0)
+        out = np.zeros(max(K, 1), BBOX_DTYPE)
+        self._chk(self.lib.lpl_bounding_boxes(self.h, a.ctypes.data if a.size else None, 16, off.ctypes.data, K,
+                                              method, out.ctypes.data))
+        return out[:K].copy()
+
     def cluster_hulls(self, pts, labels, num_clusters=None):
         p, stride, n, keep = _points_arg(pts)
         lab = np.ascontiguousarray(labels, np.int32)
@@ -419,7 +437,7 @@ class Context:
         self._chk(self.lib.lpl_pipeline_counts(self.h, f, C.byref(r)))
         return r
 
-    def download(self, f: int, want_image=False) -> dict:
+    def download(self, f: int, want_image=False, want_boxes=False) -> dict:
         r = self.counts(f)
         out = dict(
             noise=np.zeros(r.n, np.uint8), ring=np.zeros(r.n, np.uint16), labels=np.zeros(r.n, np.uint32),
@@ -432,6 +450,8 @@ class Context:
         )
         if want_image:
             out["bgr"] = np.zeros((self.H, self.W, 3), np.uint8)
+        if want_boxes:
+            out["boxes"] = np.zeros(r.num_clusters, BBOX_DTYPE)
         for k, v in out.items():
             setattr(r, k, v.ctypes.data if v.size else None)
         self._chk(self.lib.lpl_pipeline_download(self.h, f, C.byref(r)))

@@ -108,6 +108,13 @@ class RefOracle:
         L.ref_dror_timed.argtypes = [C.c_void_p, C.c_int32, C.c_uint32, C.c_int32]
         L.ref_dror_timed.restype = C.c_double
         L.ref_shim_dilate5x5.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+        self.has_polygonizer = hasattr(L, "ref_convex_hull")
+        if self.has_polygonizer:
+            L.ref_convex_hull.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+            L.ref_convex_hull.restype = C.c_int32
+            L.ref_antipodal_pairs.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+            L.ref_antipodal_pairs.restype = C.c_int32
+            L.ref_bounding_box.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
         self._seg = C.c_void_p(L.ref_segmenter_create())
         self._clu = C.c_void_p(L.ref_clusterer_create())
         self.seg_cfg = default_seg_cfg()
@@ -120,6 +127,29 @@ class RefOracle:
             self.lib.ref_clusterer_destroy(self._clu)
         except Exception:
             pass
+
+
+    # -- polygonizer (convex hull, antipodal pairs, oriented boxes) ---------------------
+    def convex_hull(self, xy):
+        xy = np.ascontiguousarray(xy, np.float64)
+        n = xy.shape[0]
+        idx = np.zeros(max(n, 1), np.int32)
+        k = self.lib.ref_convex_hull(xy.ctypes.data, n, idx.ctypes.data)
+        return idx[:k].copy()
+
+    def antipodal_pairs(self, hull_xy):
+        hull_xy = np.ascontiguousarray(hull_xy, np.float64)
+        n = hull_xy.shape[0]
+        out = np.zeros((3 * n + 4, 2), np.int32)
+        k = self.lib.ref_antipodal_pairs(hull_xy.ctypes.data, n, out.ctypes.data)
+        return out[:k].copy()
+
+    def bounding_box(self, hull_xy, method=0):
+        """[11] = 4 corners (x, y), area, angle_rad, is_valid; method 0 rotating calipers, 1 PCA."""
+        hull_xy = np.ascontiguousarray(hull_xy, np.float64)
+        out = np.zeros(11, np.float64)
+        self.lib.ref_bounding_box(hull_xy.ctypes.data, hull_xy.shape[0], method, out.ctypes.data)
+        return out
 
     # -- segmentation -----------------------------------------------------------------
     def segment_config(self, cfg: SegCfg):
@@ -252,6 +282,9 @@ class PortOracle:
         L.port_cluster.restype = C.c_int
         L.port_convex_hull.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.port_convex_hull.restype = C.c_int32
+        L.port_antipodal_pairs.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        L.port_antipodal_pairs.restype = C.c_int32
+        L.port_bounding_box.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
         L.port_cluster_hulls.argtypes = [C.c_void_p, C.c_int32, C.c_uint32, C.c_void_p, C.c_int32,
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.port_cluster_hulls.restype = C.c_int32
@@ -332,12 +365,27 @@ class PortOracle:
         self.last_num_voxels = nvox.value
         return (labels, dims) if want_dims else labels
 
+    # -- polygonizer (convex hull, antipodal pairs, oriented boxes) ---------------------
     def convex_hull(self, xy):
         xy = np.ascontiguousarray(xy, np.float64)
         n = xy.shape[0]
         idx = np.zeros(max(n, 1), np.int32)
         k = self.lib.port_convex_hull(xy.ctypes.data, n, idx.ctypes.data)
         return idx[:k].copy()
+
+    def antipodal_pairs(self, hull_xy):
+        hull_xy = np.ascontiguousarray(hull_xy, np.float64)
+        n = hull_xy.shape[0]
+        out = np.zeros((3 * n + 4, 2), np.int32)
+        k = self.lib.port_antipodal_pairs(hull_xy.ctypes.data, n, out.ctypes.data)
+        return out[:k].copy()
+
+    def bounding_box(self, hull_xy, method=0):
+        """[11] = 4 corners (x, y), area, angle_rad, is_valid; method 0 rotating calipers, 1 PCA."""
+        hull_xy = np.ascontiguousarray(hull_xy, np.float64)
+        out = np.zeros(11, np.float64)
+        self.lib.port_bounding_box(hull_xy.ctypes.data, hull_xy.shape[0], method, out.ctypes.data)
+        return out
 
     def cluster_hulls(self, pts, labels):
         """Per-cluster gather + hull (processor.cpp:627-658, polygonizer.cpp:33-91)."""

@@ -1086,6 +1086,314 @@ int port_cluster(const float* xyz,
     return next;
 }
 
+// =================================================================== oriented bounding boxes
+// Restated from polygonizer.cpp:93-163 (Shamos antipodal pairs), :165-278 (rotating calipers) and
+// :280-362 (PCA box; the SVD is the 2 x 2 two-sided Jacobi iteration of Eigen 3.4 restated -
+// Eigen itself is absent from this image, so the PCA box is "parity unpinned").
+namespace
+{
+struct PXY
+{
+    double x, y;
+};
+
+inline double tri_area(const PXY& p1, const PXY& p2, const PXY& p3)
+{
+    // polygonizer.hpp:226-231
+    return std::fabs((p1.x * (p2.y - p3.y) + p2.x * (p3.y - p1.y) + p3.x * (p1.y - p2.y)) * 0.5);
+}
+
+inline float atan2_approx_f(float y, float x)
+{
+    // common.hpp:33-62
+    const float ax = std::fabs(x), ay = std::fabs(y);
+    const float mx = std::max(ay, ax), mn = std::min(ay, ax);
+    const float a = mn / mx;
+    const float s = a * a, c = s * a, q = s * s;
+    float r = 0.024840285F * q + 0.18681418F;
+    const float t = -0.094097948F * q - 0.33213072F;
+    r = r * s + t;
+    r = r * c + a;
+    if (ay > ax)
+    {
+        r = 1.57079637F - r;
+    }
+    if (x < 0)
+    {
+        r = 3.14159274F - r;
+    }
+    if (y < 0)
+    {
+        r = -r;
+    }
+    return r;
+}
+
+void antipodal_pairs(const PXY* h, std::int32_t n, std::vector<std::pair<std::int32_t, std::int32_t>>& out)
+{
+    out.clear();
+    if (n < 2)
+    {
+        return;
+    }
+    const std::int32_t i0 = n - 1;
+    std::int32_t i = 0, j = 1;
+    auto nx = [n](std::int32_t k) { return (k + 1 == n) ? 0 : (k + 1); };
+    while (tri_area(h[i], h[nx(i)], h[nx(j)]) > tri_area(h[i], h[nx(i)], h[j]))
+    {
+        j = nx(j);
+    }
+    const std::int32_t j0 = j;
+    while (i != j0)
+    {
+        i = nx(i);
+        out.emplace_back(i, j);
+        while (tri_area(h[i], h[nx(i)], h[nx(j)]) > tri_area(h[i], h[nx(i)], h[j]))
+        {
+            j = nx(j);
+            if (!(i == j0 && j == i0))
+            {
+                out.emplace_back(i, j);
+            }
+            else
+            {
+                return;
+            }
+        }
+        if (tri_area(h[j], h[nx(i)], h[nx(j)]) == tri_area(h[i], h[nx(i)], h[j]))
+        {
+            if (!(i == j0 && j == i0))
+            {
+                out.emplace_back(i, nx(j));
+            }
+            else
+            {
+                out.emplace_back(nx(i), j);
+            }
+        }
+    }
+}
+} // namespace
+
+// pairs_out needs 2 * (3 * n + 4) entries; returns the number of pairs
+std::int32_t port_antipodal_pairs(const double* hull_xy, std::int32_t n, std::int32_t* pairs_out)
+{
+    std::vector<std::pair<std::int32_t, std::int32_t>> pr;
+    antipodal_pairs(reinterpret_cast<const PXY*>(hull_xy), n, pr);
+    for (std::size_t k = 0; k < pr.size(); ++k)
+    {
+        pairs_out[2 * k] = pr[k].first;
+        pairs_out[2 * k + 1] = pr[k].second;
+    }
+    return static_cast<std::int32_t>(pr.size());
+}
+
+// out[11] = 4 corners (x, y), area (float), angle_rad (float), is_valid; method 0 = rotating
+// calipers, 1 = PCA. An invalid box leaves the rest zero.
+void port_bounding_box(const double* hull_xy, std::int32_t n, std::int32_t method, double* out)
+{
+    std::fill(out, out + 11, 0.0);
+    if (n < 3)
+    {
+        return;
+    }
+    const PXY* h = reinterpret_cast<const PXY*>(hull_xy);
+    if (method == 0)
+    {
+        std::vector<std::pair<std::int32_t, std::int32_t>> pr;
+        antipodal_pairs(h, n, pr);
+        PXY c = {0.0, 0.0};
+        for (std::int32_t k = 0; k < n; ++k)
+        {
+            c.x += h[k].x;
+            c.y += h[k].y;
+        }
+        c.x /= n;
+        c.y /= n;
+        float best = static_cast<float>(std::numeric_limits<double>::max()); // BoundingBox::area is a float
+        bool valid = false;
+        for (const auto& [pi, pj] : pr)
+        {
+            const std::int32_t two[2] = {pi, pj};
+            for (const std::int32_t index : two)
+            {
+                for (const std::int32_t offset : {-1, 1})
+                {
+                    std::int32_t nb = index + offset;
+                    nb = nb < 0 ? nb + n : (nb >= n ? nb - n : nb);
+                    const double ex = h[nb].x - h[index].x, ey = h[nb].y - h[index].y;
+                    const double len = std::sqrt(ex * ex + ey * ey);
+                    if (len < 1.0e-6)
+                    {
+                        continue;
+                    }
+                    const double ux = ex / len, uy = ey / len;
+                    double min_x = std::numeric_limits<double>::max(), max_x = std::numeric_limits<double>::lowest();
+                    double min_y = min_x, max_y = max_x;
+                    for (std::int32_t k = 0; k < n; ++k)
+                    {
+                        const double tx = h[k].x - c.x, ty = h[k].y - c.y;
+                        const double rx = tx * ux + ty * uy;
+                        const double ry = -tx * uy + ty * ux;
+                        min_x = std::min(min_x, rx);
+                        max_x = std::max(max_x, rx);
+                        min_y = std::min(min_y, ry);
+                        max_y = std::max(max_y, ry);
+                    }
+                    const double area = (max_x - min_x) * (max_y - min_y);
+                    if (area < best)
+                    {
+                        best = static_cast<float>(area);
+                        out[0] = min_x * ux - min_y * uy + c.x;
+                        out[1] = min_x * uy + min_y * ux + c.y;
+                        out[2] = max_x * ux - min_y * uy + c.x;
+                        out[3] = max_x * uy + min_y * ux + c.y;
+                        out[4] = max_x * ux - max_y * uy + c.x;
+                        out[5] = max_x * uy + max_y * ux + c.y;
+                        out[6] = min_x * ux - max_y * uy + c.x;
+                        out[7] = min_x * uy + max_y * ux + c.y;
+                        out[9] = static_cast<double>(atan2_approx_f(static_cast<float>(uy), static_cast<float>(ux)));
+                        valid = true;
+                    }
+                }
+            }
+        }
+        out[8] = valid ? static_cast<double>(best) : 0.0;
+        out[10] = valid ? 1.0 : 0.0;
+        if (!valid)
+        {
+            std::fill(out, out + 10, 0.0);
+        }
+        return;
+    }
+    // PCA (polygonizer.cpp:280-362)
+    double mx = 0.0, my = 0.0;
+    for (std::int32_t k = 0; k < n; ++k)
+    {
+        mx += h[k].x;
+        my += h[k].y;
+    }
+    mx /= n;
+    my /= n;
+    double cxx = 0.0, cxy = 0.0, cyy = 0.0;
+    for (std::int32_t k = 0; k < n; ++k)
+    {
+        const double dx = h[k].x - mx, dy = h[k].y - my;
+        cxx += dx * dx;
+        cxy += dx * dy;
+        cyy += dy * dy;
+    }
+    const double dn = static_cast<double>(static_cast<std::uint32_t>(n) - 1u);
+    double a00 = cxx / dn, a01 = cxy / dn, a10 = cxy / dn, a11 = cyy / dn;
+    // JacobiSVD (right singular vectors), 2 x 2
+    double v[2][2] = {{1.0, 0.0}, {0.0, 1.0}};
+    {
+        const double precision = 2.0 * std::numeric_limits<double>::epsilon();
+        const double tiny = std::numeric_limits<double>::min();
+        double scale = std::max(std::max(std::fabs(a00), std::fabs(a01)), std::max(std::fabs(a10), std::fabs(a11)));
+        if (!std::isfinite(scale))
+        {
+            return; // svd_.info() != Success
+        }
+        if (scale == 0.0)
+        {
+            scale = 1.0;
+        }
+        double w[2][2] = {{a00 / scale, a01 / scale}, {a10 / scale, a11 / scale}};
+        double max_diag = std::max(std::fabs(w[0][0]), std::fabs(w[1][1]));
+        bool finished = false;
+        const int p = 1, q = 0;
+        while (!finished)
+        {
+            finished = true;
+            const double threshold = std::max(tiny, precision * max_diag);
+            if (std::fabs(w[p][q]) > threshold || std::fabs(w[q][p]) > threshold)
+            {
+                finished = false;
+                double m00 = w[p][p], m01 = w[p][q], m10 = w[q][p], m11 = w[q][q];
+                double r1c = 1.0, r1s = 0.0;
+                const double t = m00 + m11, d = m10 - m01;
+                if (std::fabs(d) >= tiny)
+                {
+                    const double u = t / d;
+                    const double tmp = std::sqrt(1.0 + u * u);
+                    r1s = 1.0 / tmp;
+                    r1c = u / tmp;
+                }
+                {
+                    const double b0 = r1c * m00 + r1s * m10, b1 = r1c * m01 + r1s * m11;
+                    const double c0 = -r1s * m00 + r1c * m10, c1 = -r1s * m01 + r1c * m11;
+                    m00 = b0;
+                    m01 = b1;
+                    m10 = c0;
+                    m11 = c1;
+                }
+                double jc = 1.0, js = 0.0;
+                {
+                    const double deno = 2.0 * std::fabs(m01);
+                    if (!(deno < tiny))
+                    {
+                        const double tau = (m00 - m11) / deno;
+                        const double ww = std::sqrt(tau * tau + 1.0);
+                        const double tt = tau > 0.0 ? 1.0 / (tau + ww) : 1.0 / (tau - ww);
+                        const double sign_t = tt > 0.0 ? 1.0 : -1.0;
+                        const double nn = 1.0 / std::sqrt(tt * tt + 1.0);
+                        js = -sign_t * (m01 / std::fabs(m01)) * std::fabs(tt) * nn;
+                        jc = nn;
+                    }
+                }
+                const double tc = jc, ts = -js;
+                const double lc = r1c * tc - r1s * ts;
+                const double ls = r1c * ts + r1s * tc;
+                {
+                    const double b0 = lc * w[p][0] + ls * w[q][0], b1 = lc * w[p][1] + ls * w[q][1];
+                    const double c0 = -ls * w[p][0] + lc * w[q][0], c1 = -ls * w[p][1] + lc * w[q][1];
+                    w[p][0] = b0;
+                    w[p][1] = b1;
+                    w[q][0] = c0;
+                    w[q][1] = c1;
+                }
+                for (int i = 0; i < 2; ++i)
+                {
+                    const double xp = w[i][p], xq = w[i][q];
+                    w[i][p] = jc * xp - js * xq;
+                    w[i][q] = js * xp + jc * xq;
+                    const double vp = v[i][p], vq = v[i][q];
+                    v[i][p] = jc * vp - js * vq;
+                    v[i][q] = js * vp + jc * vq;
+                }
+                max_diag = std::max(max_diag, std::max(std::fabs(w[p][p]), std::fabs(w[q][q])));
+            }
+        }
+        if (std::fabs(w[1][1]) > std::fabs(w[0][0]))
+        {
+            std::swap(v[0][0], v[0][1]);
+            std::swap(v[1][0], v[1][1]);
+        }
+    }
+    double min_x = std::numeric_limits<double>::max(), max_x = std::numeric_limits<double>::lowest();
+    double min_y = min_x, max_y = max_x;
+    for (std::int32_t k = 0; k < n; ++k)
+    {
+        const double dx = h[k].x - mx, dy = h[k].y - my;
+        const double rx = dx * v[0][0] + dy * v[1][0];
+        const double ry = dx * v[0][1] + dy * v[1][1];
+        min_x = std::min(min_x, rx);
+        max_x = std::max(max_x, rx);
+        min_y = std::min(min_y, ry);
+        max_y = std::max(max_y, ry);
+    }
+    const double cx[4] = {min_x, max_x, max_x, min_x}, cy[4] = {min_y, min_y, max_y, max_y};
+    for (int k = 0; k < 4; ++k)
+    {
+        out[2 * k] = (cx[k] * v[0][0] + cy[k] * v[0][1]) + mx;
+        out[2 * k + 1] = (cx[k] * v[1][0] + cy[k] * v[1][1]) + my;
+    }
+    out[8] = static_cast<double>(static_cast<float>((max_x - min_x) * (max_y - min_y)));
+    out[9] = static_cast<double>(static_cast<float>(std::atan2(v[1][0], v[0][0])));
+    out[10] = 1.0;
+}
+
 // =================================================================== convex hull
 // polygonizer.cpp:33-91 on PointXY{double x, y}. Returns the vertex count; idx receives local
 // indices, counter-clockwise from the lexicographic minimum, collinear points dropped.

@@ -1,7 +1,7 @@
 // TEST INFRASTRUCTURE ONLY (oracle/): C wrapper around the UNMODIFIED reference library.
 //
 // oracle/Makefile compiles, in place and without edits,
-//   /root/reference/lidar_processing_lib/src/{segmenter,clusterer,noise_remover}.cpp
+//   /root/reference/lidar_processing_lib/src/{segmenter,clusterer,noise_remover,polygonizer}.cpp
 // against the stand-in headers in oracle/shim/ (PCL, OpenCV and Eigen are not in this image)
 // and links them with this file into oracle/_ref/libref_oracle.so.  Nothing here is shipped
 // or used by the product path; tests and bench.py's cpu_baseline leg load it through ctypes
@@ -12,6 +12,9 @@
 //   Clusterer::config / cluster             include/lidar_processing_lib/clusterer.hpp:77-94
 //   NoiseRemover::config / filter           include/lidar_processing_lib/noise_remover.hpp:56-80
 //   KDTree::rebuild / radius_search         include/lidar_processing_lib/kdtree.hpp:161-214,283-337
+//   Polygonizer::convexHull / findAntipodalPairsOfConvexHull / boundingBoxRotatingCalipers /
+//   boundingBoxPrincipalComponentAnalysis   include/lidar_processing_lib/polygonizer.hpp:105-123
+//   (the PCA box runs on oracle/shim/Eigen's JacobiSVD restatement, not on Eigen: unpinned)
 #include <algorithm>
 #include <array>
 #include <chrono>
@@ -37,6 +40,7 @@
 #define private public
 #include "clusterer.hpp"
 #include "noise_remover.hpp"
+#include "polygonizer.hpp"
 #include "segmenter.hpp"
 #undef private
 
@@ -451,5 +455,65 @@ void ref_shim_dilate5x5(const std::uint8_t* src, std::int32_t rows, std::int32_t
     cv::Mat k = cv::getStructuringElement(cv::MORPH_RECT, cv::Size(5, 5));
     cv::dilate(m, m, k);
     std::memcpy(dst, m.data(), static_cast<std::size_t>(rows) * cols);
+}
+// ---- Polygonizer (src/polygonizer.cpp:33-362) ------------------------------------------------
+// xy: n interleaved (x, y) doubles. idx_out needs n entries; returns the vertex count.
+std::int32_t ref_convex_hull(const double* xy, std::int32_t n, std::int32_t* idx_out)
+{
+    static thread_local lpl::Polygonizer poly;
+    std::vector<lpl::PointXY> pts(static_cast<std::size_t>(n));
+    for (std::int32_t i = 0; i < n; ++i)
+    {
+        pts[i] = {xy[2 * i], xy[2 * i + 1]};
+    }
+    std::vector<std::int32_t> idx;
+    poly.convexHull(pts, idx);
+    std::copy(idx.begin(), idx.end(), idx_out);
+    return static_cast<std::int32_t>(idx.size());
+}
+
+// pairs_out needs 2 * (3 * n + 4) entries; returns the number of pairs.
+std::int32_t ref_antipodal_pairs(const double* hull_xy, std::int32_t n, std::int32_t* pairs_out)
+{
+    static thread_local lpl::Polygonizer poly;
+    std::vector<lpl::PointXY> pts(static_cast<std::size_t>(n));
+    for (std::int32_t i = 0; i < n; ++i)
+    {
+        pts[i] = {hull_xy[2 * i], hull_xy[2 * i + 1]};
+    }
+    std::vector<lpl::AntipodalPair> pairs;
+    poly.findAntipodalPairsOfConvexHull(pts, pairs);
+    for (std::size_t k = 0; k < pairs.size(); ++k)
+    {
+        pairs_out[2 * k] = pairs[k].index_1;
+        pairs_out[2 * k + 1] = pairs[k].index_2;
+    }
+    return static_cast<std::int32_t>(pairs.size());
+}
+
+// method 0 = boundingBoxRotatingCalipers, 1 = boundingBoxPrincipalComponentAnalysis.
+// out[11] = 4 corners (x, y), area, angle_rad, is_valid. An invalid box leaves the rest zero.
+void ref_bounding_box(const double* hull_xy, std::int32_t n, std::int32_t method, double* out)
+{
+    static thread_local lpl::Polygonizer poly;
+    std::vector<lpl::PointXY> pts(static_cast<std::size_t>(n));
+    for (std::int32_t i = 0; i < n; ++i)
+    {
+        pts[i] = {hull_xy[2 * i], hull_xy[2 * i + 1]};
+    }
+    const lpl::BoundingBox b = method == 0 ? poly.boundingBoxRotatingCalipers(pts)
+                                           : poly.boundingBoxPrincipalComponentAnalysis(pts);
+    std::fill(out, out + 11, 0.0);
+    out[10] = b.is_valid ? 1.0 : 0.0;
+    if (b.is_valid)
+    {
+        for (int k = 0; k < 4; ++k)
+        {
+            out[2 * k] = b.corners[k].x;
+            out[2 * k + 1] = b.corners[k].y;
+        }
+        out[8] = static_cast<double>(b.area);
+        out[9] = static_cast<double>(b.angle_rad);
+    }
 }
 } // extern "C"

@@ -117,6 +117,57 @@ def test_convex_hull_entry_point(ctx, port):
         ctx.convex_hull(np.array([[0.1, 0.2], [1.0, 1.0], [0.0, 3.0]]))  # not float-representable
 
 
+def _boxes_equal(got, exp, exact=True):
+    """got: BBOX_DTYPE records, exp: [K][11] oracle rows (4 corners, area, angle, valid)."""
+    assert np.array_equal(got["is_valid"] != 0, exp[:, 10] != 0)
+    v = exp[:, 10] != 0
+    if exact:
+        assert np.array_equal(got["corners"].reshape(-1, 8)[v].view(np.uint64), exp[v, :8].view(np.uint64))
+        assert np.array_equal(got["area"][v].view(np.uint32), exp[v, 8].astype(np.float32).view(np.uint32))
+        assert np.array_equal(got["angle_rad"][v].view(np.uint32), exp[v, 9].astype(np.float32).view(np.uint32))
+    else:
+        assert np.abs(got["corners"].reshape(-1, 8)[v] - exp[v, :8]).max(initial=0.0) <= 1e-9
+        assert np.abs(got["area"][v] - exp[v, 8]).max(initial=0.0) <= 1e-5 * max(1.0, np.abs(exp[v, 8]).max(initial=0.0))
+        assert np.abs(got["angle_rad"][v] - exp[v, 9]).max(initial=0.0) <= 1e-6
+    assert not got["corners"][~v].any()
+
+
+def test_bounding_boxes_entry_point(ctx, port):
+    """lpl_bounding_boxes against the restated / reference polygonizer (src/polygonizer.cpp:93-362):
+    rotating calipers bit-exact; PCA within 1e-9 m (device atan2 vs glibc for the yaw, 1e-6 rad)."""
+    rng = np.random.default_rng(3)
+    hulls = []
+    for n in list(rng.integers(3, 40, 300)) + [3, 4, 200, 700, 1, 2, 0]:
+        t = np.sort(rng.uniform(0, 2 * np.pi, int(n)))
+        r = rng.uniform(0.5, 6.0)
+        xy = np.c_[np.cos(t) * r * rng.uniform(0.3, 1.0), np.sin(t) * r] + rng.uniform(-40, 40, 2)
+        xy = np.round(xy, 3).astype(np.float32).astype(np.float64)
+        hulls.append(xy[port.convex_hull(xy)] if len(xy) else xy.reshape(0, 2))
+    hulls.append(np.array([[0, 0], [2, 0], [2, 1], [0, 1]], float))          # rectangle: parallel edges everywhere
+    hulls.append(np.array([[0, 0], [1, 0], [0.5, 1e-7]], float))               # sliver
+    off = np.concatenate([[0], np.cumsum([len(h) for h in hulls])]).astype(np.uint32)
+    allxy = np.concatenate(hulls)
+    for method, exact in ((lpl.BOX_ROTATING_CALIPERS, True), (lpl.BOX_PCA, False)):
+        got = ctx.bounding_boxes(allxy, off, method)
+        exp = np.stack([port.bounding_box(h, method) for h in hulls])
+        _boxes_equal(got, exp, exact)
+    assert ctx.bounding_boxes(np.zeros((0, 2)), np.zeros(1, np.uint32)).shape == (0,)
+
+
+def test_pipeline_boxes_vs_reference_golden(ctx, golden0):
+    """LPL_STAGE_BOXES on the chained pipeline: one rotating-calipers box per cluster hull, against the
+    boxes the reference's own polygonizer.cpp produced for this frame (tests/golden/kitti_polygonizer.npz)."""
+    gp = np.load(os.path.join(F.GOLDEN_DIR, "kitti_polygonizer.npz"))
+    ctx.cluster_config(**NODE_CLUSTER_CFG)
+    nf = ctx.upload([golden0["pts"]])
+    ctx.run(nf, (lpl.STAGE_ALL & ~lpl.STAGE_DROR) | lpl.STAGE_BOXES)
+    ctx.sync(nf)
+    out = ctx.download(0, want_boxes=True)
+    assert np.array_equal(out["hull_offsets"], gp["kitti_f000_hull_offsets"])
+    assert np.array_equal(out["hull_xy"], gp["kitti_f000_hull_xy"])
+    _boxes_equal(out["boxes"], gp["kitti_f000_boxes"][:, :11], exact=True)
+
+
 def test_edge_cases(ctx, port):
     empty = np.zeros((0, 4), np.float32)
     assert ctx.ring_partition(empty).shape == (0,)

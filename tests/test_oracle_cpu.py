@@ -175,3 +175,52 @@ def test_port_matches_reference_summary_all_154(port):
         assert xy.shape[0] == s["hull_vertices"]
         assert label_hash(xy.astype(np.float32).view(np.uint32).reshape(-1)) == s["hull_xy_hash"]
         assert int(port.dror(pts).sum()) == s["dror_noise_exact"]
+
+
+def _random_hull_inputs(rng, trials):
+    for trial in range(trials):
+        n = int(rng.integers(1, 60))
+        kind = trial % 4
+        if kind == 0:
+            xy = np.round(rng.normal(0, 3, (n, 2)), 3)
+        elif kind == 1:
+            xy = np.round(rng.uniform(-5, 5, (n, 2)), 1)  # many ties and collinear runs
+        elif kind == 2:
+            t = rng.uniform(0, 2 * np.pi, n)
+            xy = np.round(np.c_[np.cos(t) * 4, np.sin(t) * 2], 3)
+        else:
+            xy = np.round(np.c_[rng.uniform(0, 10, n), rng.integers(0, 2, n).astype(float)], 2)  # two parallel lines
+        yield xy.astype(np.float32).astype(np.float64)
+
+
+def test_polygonizer_port_equals_reference(port, ref):
+    """convexHull, findAntipodalPairsOfConvexHull, boundingBoxRotatingCalipers and the PCA box of the
+    restatement against the reference's own polygonizer.cpp (oracle/_ref): bit-exact. (The PCA box
+    goes through the Eigen stand-in on both sides: that one is a consistency check, not a pin.)"""
+    if not ref.has_polygonizer:
+        pytest.skip("oracle/_ref predates the polygonizer wrappers")
+    rng = np.random.default_rng(7)
+    for xy in _random_hull_inputs(rng, 1500):
+        a, b = port.convex_hull(xy), ref.convex_hull(xy)
+        assert a.shape == b.shape and np.array_equal(xy[a], xy[b])
+        h = xy[b]
+        assert np.array_equal(port.antipodal_pairs(h), ref.antipodal_pairs(h))
+        for m in (0, 1):
+            assert np.array_equal(port.bounding_box(h, m).view(np.uint64), ref.bounding_box(h, m).view(np.uint64))
+
+
+def test_polygonizer_golden(port, golden0, golden100):
+    """The hulls of the golden fixtures (made with the restated hull) equal the reference's own
+    convexHull output, and the restated boxes equal the reference's (tests/golden/kitti_polygonizer.npz,
+    tools/make_golden_boxes.py)."""
+    gp = np.load(os.path.join(F.GOLDEN_DIR, "kitti_polygonizer.npz"))
+    for name, g in (("kitti_f000", golden0), ("kitti_f100", golden100)):
+        off, hxy = gp[name + "_hull_offsets"], gp[name + "_hull_xy"]
+        assert np.array_equal(off, g["hull_offsets"])
+        assert np.array_equal(hxy, g["hull_xy"])
+        boxes = gp[name + "_boxes"]
+        for k in range(len(off) - 1):
+            h = hxy[off[k]:off[k + 1]].astype(np.float64)
+            assert len(port.antipodal_pairs(h)) == gp[name + "_pairs"][k]
+            assert np.array_equal(port.bounding_box(h, 0).view(np.uint64), boxes[k, :11].view(np.uint64))
+            assert np.array_equal(port.bounding_box(h, 1).view(np.uint64), boxes[k, 11:].view(np.uint64))
