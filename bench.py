@@ -121,21 +121,28 @@ def algorithmic_bytes(name: str, s: dict) -> float:
     t = {
         "ring_count": 16 * N, "ring_write": 16 * N + 2 * N,
         "dror_near": 16 * N + 1 * N + 4 * U,
-        "dror_grid_count": 16 * N, "dror_grid_scan": 8 * 65536 * F, "dror_grid_scatter": 32 * N,
+        "dror_mark": 20 * U + 16384 * F, "dror_grid_count": 16 * N, "dror_grid_scan": 8 * 131072 * F,
+        "dror_grid_scatter": 16 * N + 16 * U * 8,
         "dror_query": 20 * U + U,
         "take_valid": (16 + 2 + 1) * N + 20 * V, "take_all": (16 + 2) * N + 20 * V,
         "seg_bin": 16 * V + 12 * V, "seg_cell_scan": 8 * CELLS, "seg_scatter": (16 + 8) * V + 8 * NB,
         "seg_cell": 8 * NB + 8 * CELLS, "seg_elev": 12 * CELLS,
         "seg_label": (16 + 4) * V + 4 * NB + 1 * V,
-        "ransac_setup": 1024 * F + 8 * CELLS, "ransac_count": 1 * V + 16 * C,
+        "ransac_draw": 1024 * F + 8 * CELLS, "ransac_plane": 120 * 64 * F, "ransac_count": 16 * C,
         "seg_image": (16 + 4 + 4 + 1) * V + 1 * NB + 8 * NB, "seg_px": 8 * PX + 17 * PX + 17 * PX,
         "seg_dilate": 2 * PX, "jcp_queue": 2 * PX + 4 * Q,
         "jcp_pre": Q * (25 * 17 + 24 * 4 + 8), "jcp_resolve": PX * 1 + Q * (8 + 4 + 96) + PX * 17 + V * 2,
         "take_obstacles": 1 * V + 20 * M + 20 * M,
-        "clu_sph": 16 * M + 16 * M, "clu_insert": 16 * M + 4 * M, "clu_union": 8 * M,
-        "clu_flatten": 8 * M, "clu_rank": 8 * M, "clu_labels": 8 * M,
-        "hull_seg_scan": 8 * K, "hull_scatter": 20 * M + 12 * M, "hull": 16 * M + 8 * K + 4 * HV,
-        "hull_off_scan": 8 * K, "hull_gather": 4 * HV + 16 * HV + 12 * HV,
+        "clu_sph": 16 * M + 16 * M, "clu_insert": 16 * M + 4 * M, "clu_edges": 8 * M + 52 * M // 3,
+        "clu_union_sm": 52 * M // 3 + 8 * M // 3, "clu_union": 8 * M, "clu_flatten": 8 * M,
+        "clu_rank": 8 * M, "clu_labels": 8 * M + 16 * M,
+        # hulls: the stage as a whole must read every obstacle point's (x, y) and label once and write
+        # the vertices (8M + 4M + 4 Hv + 12 K); the chain kernels are charged with that
+        "hull_octagon": 64 * K, "hull_keep": (16 + 4) * M + 16 * M, "hull_seg_scan": 8 * K,
+        "hull_tilesort": 32 * M, "hull_merge": 32 * M,
+        "hull_thin_big": 12 * M + 4 * HV + 12 * K, "hull_thin": 12 * M + 4 * HV + 12 * K,
+        "hull_final": 16 * HV + 12 * K, "hull_off_scan": 8 * K, "hull_gather": 4 * HV + 16 * HV + 12 * HV,
+        "obb_frames": 8 * HV + 80 * K,
         "label_count": 4 * M,
     }
     return float(t.get(name, 0.0))

@@ -21,6 +21,8 @@
  *                           (+ findAntipodalPairsOfConvexHull)  .../polygonizer.hpp:108-123, src/polygonizer.cpp:93-362
  *   lpl_pipeline_*          Processor::run (segment -> split -> cluster -> hulls), batched
  *                                                              src/processor/src/processor.cpp:552-663
+ *   lpl_pipeline_upload_cloud2  convert<PointT>(PointCloud2)   src/processor/src/processor.cpp:42-179
+ *   lpl_pcd_read            pcl::io::loadPCDFile<PointXYZI>    src/dataloader/src/dataloader.cpp:165
  */
 #ifndef LPL_B200_H
 #define LPL_B200_H
@@ -181,6 +183,20 @@ typedef struct lpl_frame
 int lpl_pipeline_upload(lpl_ctx* ctx, const lpl_frame* frames, uint32_t num_frames);
 /* Same, from device-resident frames (device-to-device copies). */
 int lpl_pipeline_upload_device(lpl_ctx* ctx, const lpl_frame* frames, uint32_t num_frames);
+/* One frame as a sensor_msgs/PointCloud2 payload (what Processor::convert<PointT> reads,
+ * src/processor/src/processor.cpp:42-179): height * width records, point_step bytes apart inside a
+ * row, rows row_step bytes apart; x / y / z are float32 at the given byte offsets, ring (uint16) at
+ * ring_offset or -1 when the point type has none. Up to 32 bytes per point of capacity. The raw
+ * bytes are uploaded as they are and unpacked by a kernel (no host-side conversion loop). */
+typedef struct lpl_cloud2_frame
+{
+    const void* data;
+    uint32_t width, height;
+    uint32_t point_step, row_step;
+    int32_t x_offset, y_offset, z_offset;
+    int32_t ring_offset;
+} lpl_cloud2_frame;
+int lpl_pipeline_upload_cloud2(lpl_ctx* ctx, const lpl_cloud2_frame* frames, uint32_t num_frames);
 /* Enqueue the selected stages for the uploaded batch (async). */
 int lpl_pipeline_run(lpl_ctx* ctx, uint32_t num_frames, uint32_t stages);
 /* Wait for the stream; fails if any kernel raised a capacity flag. */
@@ -231,6 +247,11 @@ typedef struct lpl_batch_result
     lpl_bbox* boxes;          /* one box per element (LPL_STAGE_BOXES)             */
 } lpl_batch_result;
 int lpl_pipeline_download_batch(lpl_ctx* ctx, uint32_t num_frames, lpl_batch_result* res);
+
+/* PCD v0.7 reader for the reference's data set (FIELDS x y z [intensity], float32, DATA binary or
+ * ascii): fills xyzi_out[n][4] (intensity 0 when absent) and *n_out; xyzi_out == NULL only queries
+ * the point count. Host-only, needs no context. */
+int lpl_pcd_read(const char* path, float* xyzi_out, uint32_t capacity, uint32_t* n_out);
 
 /* Pinned host memory for frame / result buffers (cudaMallocHost / cudaFreeHost). */
 int lpl_host_alloc(void** out, size_t bytes);

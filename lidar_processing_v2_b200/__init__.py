@@ -26,4 +26,5 @@ from .native import (  # noqa: F401
     PinnedBuffer,
     SegmenterCfg,
     load_library,
+    pcd_read,
 )

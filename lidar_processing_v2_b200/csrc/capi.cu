@@ -1,6 +1,7 @@
 // C ABI (include/lpl_b200.h): context, configuration, staging and stage orchestration.
 // No torch types, no CPU fallback: every entry point fails with LPL_ERR_NO_DEVICE / LPL_ERR_CUDA
 // when the GPU is not usable.
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 #include <cstdlib>
@@ -138,6 +139,8 @@ void carve(Dev& d, Carver& cv, int npx, int ncell_cap, std::uint32_t** mt_raw)
     cv.take(d.n_h, B);
     cv.take(d.hull_next, B);
     cv.take(d.boxes, B * cap);
+    cv.take(d.raw, B * cap * kRawRecord);
+    cv.take(d.raw_desc, B * 32);
     const std::size_t tl = std::max<std::size_t>(d.tiles, d.ptiles);
     cv.take(d.tile_cnt, B * tl);
     cv.take(d.status, B);
@@ -665,6 +668,75 @@ int lpl_pipeline_upload(lpl_ctx* ctx, const lpl_frame* frames, std::uint32_t nf)
 int lpl_pipeline_upload_device(lpl_ctx* ctx, const lpl_frame* frames, std::uint32_t nf)
 {
     return upload_impl(ctx, frames, nf, true);
+}
+
+int lpl_pipeline_upload_cloud2(lpl_ctx* ctx, const lpl_cloud2_frame* frames, std::uint32_t nf)
+{
+    if (ctx == nullptr || frames == nullptr || nf == 0 || nf > ctx->c.d.B)
+    {
+        return fail(ctx, LPL_ERR_INVALID_ARGUMENT, "bad frame batch (null, empty or larger than max_frames)");
+    }
+    Ctx& c = ctx->c;
+    Dev& d = c.d;
+    LPL_TRY(cudaSetDevice(c.device));
+    struct Desc
+    {
+        std::uint32_t width, height, point_step, row_step;
+        std::int32_t x_off, y_off, z_off, ring_off;
+    };
+    static_assert(sizeof(Desc) == 32, "record layout descriptor is 32 bytes");
+    if (ensure_stage(ctx, (sizeof(std::uint32_t) + sizeof(Desc)) * d.B) != 0)
+    {
+        return LPL_ERR_CUDA;
+    }
+    LPL_TRY(cudaStreamSynchronize(c.stream)); // the staging may still be in flight from the previous batch
+    auto* h_n = static_cast<std::uint32_t*>(c.h_stage);
+    auto* h_d = reinterpret_cast<Desc*>(h_n + d.B);
+    const std::size_t raw_stride = static_cast<std::size_t>(d.cap) * kRawRecord;
+    bool any_ring = false;
+    for (std::uint32_t f = 0; f < nf; ++f)
+    {
+        const lpl_cloud2_frame& fr = frames[f];
+        const unsigned long long n = static_cast<unsigned long long>(fr.width) * fr.height;
+        if (n > d.cap)
+        {
+            return fail(ctx, LPL_ERR_CAPACITY, "frame has more points than the context was created for");
+        }
+        const std::size_t bytes = static_cast<std::size_t>(fr.height) * fr.row_step;
+        const std::int32_t hi = std::max(std::max(fr.x_offset, fr.y_offset), fr.z_offset) + 4;
+        if (n != 0 && (fr.data == nullptr || fr.point_step == 0 || fr.row_step < static_cast<std::uint64_t>(fr.width) * fr.point_step ||
+                       fr.x_offset < 0 || fr.y_offset < 0 || fr.z_offset < 0 || static_cast<std::uint32_t>(hi) > fr.point_step ||
+                       (fr.ring_offset >= 0 && static_cast<std::uint32_t>(fr.ring_offset) + 2u > fr.point_step)))
+        {
+            return fail(ctx, LPL_ERR_INVALID_ARGUMENT, "inconsistent PointCloud2 layout (steps / field offsets)");
+        }
+        if (bytes > raw_stride)
+        {
+            return fail(ctx, LPL_ERR_CAPACITY, "raw records larger than 32 bytes per point of capacity");
+        }
+        h_n[f] = static_cast<std::uint32_t>(n);
+        h_d[f] = Desc{fr.width, fr.height, fr.point_step, fr.row_step, fr.x_offset, fr.y_offset, fr.z_offset,
+                      fr.ring_offset >= 0 ? fr.ring_offset : -1};
+        any_ring = any_ring || fr.ring_offset >= 0;
+    }
+    LPL_TRY(cudaMemcpyAsync(d.n_in, h_n, sizeof(std::uint32_t) * nf, cudaMemcpyHostToDevice, c.stream));
+    LPL_TRY(cudaMemcpyAsync(d.raw_desc, h_d, sizeof(Desc) * nf, cudaMemcpyHostToDevice, c.stream));
+    if (any_ring)
+    {
+        // frames without a ring field read as ring 0, as in the xyzw upload
+        LPL_TRY(cudaMemsetAsync(d.ring, 0, sizeof(std::uint16_t) * static_cast<std::size_t>(d.cap) * nf, c.stream));
+    }
+    for (std::uint32_t f = 0; f < nf; ++f)
+    {
+        const std::size_t bytes = static_cast<std::size_t>(frames[f].height) * frames[f].row_step;
+        if (bytes != 0)
+        {
+            LPL_TRY(cudaMemcpyAsync(d.raw + f * raw_stride, frames[f].data, bytes, cudaMemcpyHostToDevice, c.stream));
+        }
+    }
+    launch_unpack_cloud2(&c, nf, d.raw, raw_stride, d.raw_desc);
+    ctx->have_ring = any_ring ? 1 : 0;
+    return LPL_OK;
 }
 
 int lpl_pipeline_run(lpl_ctx* ctx, std::uint32_t nf, std::uint32_t stages)

@@ -23,6 +23,7 @@ constexpr int kDrorCells = 2 * kDrorLevelCells;
 constexpr int kRansacIters = 60;    // segmenter.cpp:324
 constexpr int kRansacBins = 4;      // segmenter.cpp:323
 constexpr int kMtRaws = 8192;       // pre-generated std::mt19937{42} outputs
+constexpr int kRawRecord = 32;      // bytes reserved per point for raw records (pcl::PointXYZIR = 32)
 
 // pixel codes of the range image
 enum : std::uint8_t
@@ -184,6 +185,8 @@ struct Dev
     std::uint32_t* n_h;       // [B]       survivors per frame (input size of the hull sort)
     std::uint32_t* hull_next; // [B]       next cluster to hand out in k_hull_thin
     ObbBox* boxes;            // [B][cap]  oriented bounding box per cluster (LPL_STAGE_BOXES)
+    unsigned char* raw;       // [B][cap * kRawRecord] raw PointCloud2 records before the device unpack
+    unsigned char* raw_desc;  // [B] record layouts (Cloud2Desc)
     // ---- generic
     std::uint32_t* tile_cnt;  // [B][max(tiles, ptiles)]
     std::uint32_t* status;    // [B]  error bits raised by kernels
@@ -519,6 +522,7 @@ void launch_take_obstacles(Ctx* c, std::uint32_t nf);
 void launch_cluster(Ctx* c, std::uint32_t nf);
 void launch_hulls(Ctx* c, std::uint32_t nf);
 void launch_boxes(Ctx* c, std::uint32_t nf, int method);
+void launch_unpack_cloud2(Ctx* c, std::uint32_t nf, const unsigned char* raw, std::size_t raw_stride, const void* desc);
 void launch_boxes_hulls(Ctx* c, const double2* xy, const std::uint32_t* off, std::uint32_t K, int method, ObbBox* out);
 
 struct Ctx

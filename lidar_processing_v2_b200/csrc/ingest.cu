@@ -1,0 +1,326 @@
+// Ingest: the two ways a frame reaches the hot path in the reference.
+//
+//   lpl_pcd_read                 pcl::io::loadPCDFile<pcl::PointXYZI>  src/dataloader/src/dataloader.cpp:165
+//                                (PCD v0.7, float32 FIELDS x y z [intensity ...], DATA binary or ascii;
+//                                exactly POINTS * record bytes are consumed - the KITTI files carry a few
+//                                KB of padding behind the payload)
+//   lpl_pipeline_upload_cloud2   Processor::convert<PointT>            src/processor/src/processor.cpp:42-179
+//                                (sensor_msgs/PointCloud2 layout: height x width records, point_step /
+//                                row_step, float32 x / y / z and an optional uint16 ring at byte offsets).
+//                                The raw message bytes cross PCIe once and are unpacked on the device
+//                                into the float4 / ring planes every stage reads (the reference converts
+//                                with a scalar host loop, one point at a time).
+#include <cerrno>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/lpl_b200.h"
+#include "common.cuh"
+
+namespace lpl
+{
+struct Cloud2Desc
+{
+    std::uint32_t width, height, point_step, row_step;
+    std::int32_t x_off, y_off, z_off, ring_off;
+};
+
+__device__ __forceinline__ std::uint32_t load_u32_bytes(const unsigned char* p)
+{
+    return static_cast<std::uint32_t>(p[0]) | (static_cast<std::uint32_t>(p[1]) << 8) |
+           (static_cast<std::uint32_t>(p[2]) << 16) | (static_cast<std::uint32_t>(p[3]) << 24);
+}
+
+// one thread per point: AoS records (any stride) -> float4 plane (+ ring plane)
+__global__ void __launch_bounds__(256)
+    k_unpack_cloud2(Dev d, const unsigned char* __restrict__ raw, std::size_t raw_stride, const Cloud2Desc* __restrict__ desc)
+{
+    const std::uint32_t f = blockIdx.y;
+    const Cloud2Desc c = desc[f];
+    const std::uint32_t n = c.width * c.height;
+    const std::uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    if (i >= n)
+    {
+        return;
+    }
+    const std::uint32_t row = i / c.width, col = i - row * c.width;
+    const unsigned char* rec = raw + static_cast<std::size_t>(f) * raw_stride + static_cast<std::size_t>(row) * c.row_step +
+                               static_cast<std::size_t>(col) * c.point_step;
+    float x, y, z;
+    if (((c.point_step | c.row_step | static_cast<std::uint32_t>(c.x_off) | static_cast<std::uint32_t>(c.y_off) |
+          static_cast<std::uint32_t>(c.z_off)) & 3u) == 0u)
+    {
+        x = *reinterpret_cast<const float*>(rec + c.x_off);
+        y = *reinterpret_cast<const float*>(rec + c.y_off);
+        z = *reinterpret_cast<const float*>(rec + c.z_off);
+    }
+    else
+    {
+        x = __uint_as_float(load_u32_bytes(rec + c.x_off));
+        y = __uint_as_float(load_u32_bytes(rec + c.y_off));
+        z = __uint_as_float(load_u32_bytes(rec + c.z_off));
+    }
+    const std::size_t o = static_cast<std::size_t>(f) * d.cap + i;
+    d.pts_in[o] = make_float4(x, y, z, 0.f);
+    if (c.ring_off >= 0)
+    {
+        const unsigned char* r = rec + c.ring_off;
+        d.ring[o] = static_cast<std::uint16_t>(r[0] | (r[1] << 8));
+    }
+}
+
+void launch_unpack_cloud2(Ctx* c, std::uint32_t nf, const unsigned char* raw, std::size_t raw_stride, const void* desc)
+{
+    k_unpack_cloud2<<<dim3((c->d.cap + 255) / 256, nf), 256, 0, c->stream>>>(c->d, raw, raw_stride,
+                                                                             static_cast<const Cloud2Desc*>(desc));
+    mark(c, "unpack_cloud2");
+}
+} // namespace lpl
+
+// ------------------------------------------------------------------------------------------
+// PCD reader (host)
+// ------------------------------------------------------------------------------------------
+namespace
+{
+struct PcdHeader
+{
+    std::vector<std::string> fields;
+    std::vector<int> size, count;
+    std::vector<char> type;
+    unsigned long long points = 0, width = 0, height = 1;
+    std::string data;
+    bool have_points = false;
+};
+
+std::vector<std::string> split_ws(const std::string& s)
+{
+    std::vector<std::string> out;
+    std::size_t i = 0;
+    while (i < s.size())
+    {
+        while (i < s.size() && (s[i] == ' ' || s[i] == '\t' || s[i] == '\r'))
+        {
+            ++i;
+        }
+        std::size_t j = i;
+        while (j < s.size() && s[j] != ' ' && s[j] != '\t' && s[j] != '\r')
+        {
+            ++j;
+        }
+        if (j > i)
+        {
+            out.push_back(s.substr(i, j - i));
+        }
+        i = j;
+    }
+    return out;
+}
+
+bool read_line(std::FILE* fp, std::string& line)
+{
+    line.clear();
+    int ch;
+    while ((ch = std::fgetc(fp)) != EOF)
+    {
+        if (ch == '\n')
+        {
+            return true;
+        }
+        line.push_back(static_cast<char>(ch));
+    }
+    return !line.empty();
+}
+} // namespace
+
+extern "C" int lpl_pcd_read(const char* path, float* xyzi_out, uint32_t capacity, uint32_t* n_out)
+{
+    if (path == nullptr || n_out == nullptr)
+    {
+        return LPL_ERR_INVALID_ARGUMENT;
+    }
+    *n_out = 0;
+    std::FILE* fp = std::fopen(path, "rb");
+    if (fp == nullptr)
+    {
+        return LPL_ERR_INVALID_ARGUMENT;
+    }
+    PcdHeader h;
+    std::string line;
+    while (read_line(fp, line))
+    {
+        const std::vector<std::string> t = split_ws(line);
+        if (t.empty() || t[0][0] == '#')
+        {
+            continue;
+        }
+        if (t[0] == "FIELDS" || t[0] == "COLUMNS")
+        {
+            h.fields.assign(t.begin() + 1, t.end());
+        }
+        else if (t[0] == "SIZE")
+        {
+            for (std::size_t k = 1; k < t.size(); ++k)
+            {
+                h.size.push_back(std::atoi(t[k].c_str()));
+            }
+        }
+        else if (t[0] == "TYPE")
+        {
+            for (std::size_t k = 1; k < t.size(); ++k)
+            {
+                h.type.push_back(t[k][0]);
+            }
+        }
+        else if (t[0] == "COUNT")
+        {
+            for (std::size_t k = 1; k < t.size(); ++k)
+            {
+                h.count.push_back(std::atoi(t[k].c_str()));
+            }
+        }
+        else if (t[0] == "WIDTH" && t.size() > 1)
+        {
+            h.width = std::strtoull(t[1].c_str(), nullptr, 10);
+        }
+        else if (t[0] == "HEIGHT" && t.size() > 1)
+        {
+            h.height = std::strtoull(t[1].c_str(), nullptr, 10);
+        }
+        else if (t[0] == "POINTS" && t.size() > 1)
+        {
+            h.points = std::strtoull(t[1].c_str(), nullptr, 10);
+            h.have_points = true;
+        }
+        else if (t[0] == "DATA" && t.size() > 1)
+        {
+            h.data = t[1];
+            break; // the payload follows this line
+        }
+    }
+    const std::size_t nf = h.fields.size();
+    if (h.count.empty())
+    {
+        h.count.assign(nf, 1);
+    }
+    if (nf == 0 || h.size.size() != nf || h.type.size() != nf || h.count.size() != nf || h.data.empty())
+    {
+        std::fclose(fp);
+        return LPL_ERR_INVALID_ARGUMENT;
+    }
+    if (!h.have_points)
+    {
+        h.points = h.width * h.height;
+    }
+    // byte offset (binary) / column (ascii) of x, y, z, intensity
+    int off[4] = {-1, -1, -1, -1}, colidx[4] = {-1, -1, -1, -1};
+    int rec = 0, cols = 0;
+    const char* want[4] = {"x", "y", "z", "intensity"};
+    for (std::size_t k = 0; k < nf; ++k)
+    {
+        for (int w = 0; w < 4; ++w)
+        {
+            if (h.fields[k] == want[w])
+            {
+                if (h.size[k] != 4 || h.type[k] != 'F' || h.count[k] != 1)
+                {
+                    std::fclose(fp);
+                    return LPL_ERR_INVALID_ARGUMENT; // only float32 coordinates (what the node consumes)
+                }
+                off[w] = rec;
+                colidx[w] = cols;
+            }
+        }
+        rec += h.size[k] * h.count[k];
+        cols += h.count[k];
+    }
+    if (off[0] < 0 || off[1] < 0 || off[2] < 0 || rec <= 0)
+    {
+        std::fclose(fp);
+        return LPL_ERR_INVALID_ARGUMENT;
+    }
+    *n_out = static_cast<uint32_t>(h.points);
+    if (xyzi_out == nullptr)
+    {
+        std::fclose(fp);
+        return LPL_OK; // size query
+    }
+    if (h.points > capacity)
+    {
+        std::fclose(fp);
+        return LPL_ERR_CAPACITY;
+    }
+    int rc = LPL_OK;
+    if (h.data == "binary")
+    {
+        const bool packed = (rec == 16 && off[0] == 0 && off[1] == 4 && off[2] == 8 && off[3] == 12);
+        if (packed)
+        {
+            if (std::fread(xyzi_out, 16, h.points, fp) != h.points)
+            {
+                rc = LPL_ERR_INVALID_ARGUMENT;
+            }
+        }
+        else
+        {
+            std::vector<unsigned char> buf(static_cast<std::size_t>(rec) * 4096);
+            unsigned long long done = 0;
+            while (done < h.points && rc == LPL_OK)
+            {
+                const std::size_t take = static_cast<std::size_t>(std::min<unsigned long long>(4096, h.points - done));
+                if (std::fread(buf.data(), static_cast<std::size_t>(rec), take, fp) != take)
+                {
+                    rc = LPL_ERR_INVALID_ARGUMENT;
+                    break;
+                }
+                for (std::size_t i = 0; i < take; ++i)
+                {
+                    float* o = xyzi_out + (done + i) * 4;
+                    for (int w = 0; w < 4; ++w)
+                    {
+                        o[w] = 0.f;
+                        if (off[w] >= 0)
+                        {
+                            std::memcpy(&o[w], buf.data() + i * rec + off[w], 4);
+                        }
+                    }
+                }
+                done += take;
+            }
+        }
+    }
+    else if (h.data == "ascii")
+    {
+        for (unsigned long long i = 0; i < h.points && rc == LPL_OK; ++i)
+        {
+            if (!read_line(fp, line))
+            {
+                rc = LPL_ERR_INVALID_ARGUMENT;
+                break;
+            }
+            const std::vector<std::string> t = split_ws(line);
+            if (static_cast<int>(t.size()) < cols)
+            {
+                rc = LPL_ERR_INVALID_ARGUMENT;
+                break;
+            }
+            float* o = xyzi_out + i * 4;
+            for (int w = 0; w < 4; ++w)
+            {
+                o[w] = colidx[w] >= 0 ? std::strtof(t[colidx[w]].c_str(), nullptr) : 0.f;
+            }
+        }
+    }
+    else
+    {
+        rc = LPL_ERR_INVALID_ARGUMENT; // binary_compressed is not produced by the reference's data set
+    }
+    std::fclose(fp);
+    if (rc != LPL_OK)
+    {
+        *n_out = 0;
+    }
+    return rc;
+}

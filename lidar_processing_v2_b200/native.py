@@ -36,7 +36,8 @@ EXPORTS = [
     "lpl_segmenter_config", "lpl_dror_config", "lpl_cluster_config", "lpl_set_jcp_mode",
     "lpl_ring_partition", "lpl_dror_filter", "lpl_segment", "lpl_cluster", "lpl_convex_hull",
     "lpl_cluster_hulls", "lpl_bounding_boxes",
-    "lpl_pipeline_upload", "lpl_pipeline_upload_device", "lpl_pipeline_run", "lpl_pipeline_sync",
+    "lpl_pipeline_upload", "lpl_pipeline_upload_device", "lpl_pipeline_upload_cloud2", "lpl_pcd_read",
+    "lpl_pipeline_run", "lpl_pipeline_sync",
     "lpl_pipeline_want_image", "lpl_pipeline_counts", "lpl_pipeline_download",
     "lpl_pipeline_download_batch", "lpl_host_alloc", "lpl_host_free",
     "lpl_profile_enable", "lpl_profile_read",
@@ -89,6 +90,12 @@ class Frame(C.Structure):
     _fields_ = [("xyzw", C.c_void_p), ("n", C.c_uint32), ("ring", C.c_void_p)]
 
 
+class Cloud2Frame(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("width", C.c_uint32), ("height", C.c_uint32), ("point_step", C.c_uint32),
+                ("row_step", C.c_uint32), ("x_offset", C.c_int32), ("y_offset", C.c_int32), ("z_offset", C.c_int32),
+                ("ring_offset", C.c_int32)]
+
+
 class FrameResult(C.Structure):
     _fields_ = [
         ("noise", C.c_void_p),
@@ -125,6 +132,20 @@ class BatchResult(C.Structure):
         ("zminmax", C.c_void_p),
         ("boxes", C.c_void_p),
     ]
+
+
+def pcd_read(path: str, lib=None) -> np.ndarray:
+    """(n, 4) float32 x, y, z, intensity of a PCD file (lpl_pcd_read)."""
+    lib = lib or load_library()
+    n = C.c_uint32(0)
+    rc = lib.lpl_pcd_read(path.encode(), None, 0, C.byref(n))
+    if rc != 0:
+        raise LplError(rc, f"cannot read PCD header of {path}")
+    out = np.zeros((n.value, 4), np.float32)
+    rc = lib.lpl_pcd_read(path.encode(), out.ctypes.data, n.value, C.byref(n))
+    if rc != 0:
+        raise LplError(rc, f"cannot read PCD payload of {path}")
+    return out
 
 
 class LplError(RuntimeError):
@@ -172,6 +193,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     L.lpl_bounding_boxes.argtypes = [vp, vp, sz, vp, u32, C.c_int, vp]
     L.lpl_pipeline_upload.argtypes = [vp, C.POINTER(Frame), u32]
     L.lpl_pipeline_upload_device.argtypes = [vp, C.POINTER(Frame), u32]
+    L.lpl_pipeline_upload_cloud2.argtypes = [vp, C.POINTER(Cloud2Frame), u32]
+    L.lpl_pcd_read.argtypes = [C.c_char_p, vp, u32, C.POINTER(u32)]
     L.lpl_pipeline_run.argtypes = [vp, u32, u32]
     L.lpl_pipeline_sync.argtypes = [vp, u32]
     L.lpl_pipeline_want_image.argtypes = [vp, C.c_int]
@@ -421,6 +444,21 @@ class Context:
         fn = self.lib.lpl_pipeline_upload_device if device else self.lib.lpl_pipeline_upload
         self._chk(fn(self.h, arr, nf))
         self._keep = keep
+        return nf
+
+    def upload_cloud2(self, messages) -> int:
+        """messages: dicts with data (uint8 array), width, height, point_step, row_step, x/y/z_offset and
+        ring_offset (-1 = none) - the PointCloud2 fields Processor::convert reads."""
+        nf = len(messages)
+        arr = (Cloud2Frame * nf)()
+        keep = []
+        for f, m in enumerate(messages):
+            data = np.ascontiguousarray(m["data"], np.uint8)
+            keep.append(data)
+            arr[f] = Cloud2Frame(data.ctypes.data if data.size else None, m["width"], m["height"], m["point_step"],
+                                 m["row_step"], m["x_offset"], m["y_offset"], m["z_offset"], m.get("ring_offset", -1))
+        self._chk(self.lib.lpl_pipeline_upload_cloud2(self.h, arr, nf))
+        self._keep = keep  # the copies are asynchronous: the host arrays must outlive them
         return nf
 
     def run(self, nf: int, stages: int = STAGE_ALL):

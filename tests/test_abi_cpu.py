@@ -4,6 +4,7 @@ import ctypes as C
 import os
 import re
 
+import numpy as np
 import pytest
 
 import lidar_processing_v2_b200 as lpl
@@ -54,3 +55,46 @@ def test_product_package_never_imports_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 txt = open(os.path.join(dirpath, fn), errors="replace").read()
                 assert "oracle" not in txt, os.path.join(dirpath, fn)
+
+
+def _write_pcd(path, pts, mode="binary", extra_field=False, padding=0):
+    n = pts.shape[0]
+    fields = "x y z intensity" + (" t" if extra_field else "")
+    nf = 5 if extra_field else 4
+    hdr = ("# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS %s\nSIZE %s\nTYPE %s\nCOUNT %s\n"
+           "WIDTH %d\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS %d\nDATA %s\n") % (
+        fields, " ".join(["4"] * nf), " ".join(["F"] * nf), " ".join(["1"] * nf), n, n, mode)
+    with open(path, "wb") as f:
+        f.write(hdr.encode())
+        if mode == "binary":
+            rec = np.zeros((n, nf), np.float32)
+            rec[:, :4] = pts
+            f.write(rec.tobytes())
+            f.write(b"\x00" * padding)  # the reference's files carry padding behind the payload
+        else:
+            for r in pts:
+                f.write((" ".join(repr(float(v)) for v in r) + (" 0" if extra_field else "") + "\n").encode())
+
+
+def test_pcd_reader(tmp_path):
+    """lpl_pcd_read (replaces pcl::io::loadPCDFile<PointXYZI>, dataloader.cpp:165) on the layout of the
+    reference's data/*.pcd (binary, x y z intensity, trailing padding), a wider record, and ascii."""
+    import numpy as np
+
+    from oracle.oracle import read_pcd_xyzi
+
+    rng = np.random.default_rng(0)
+    pts = np.round(rng.normal(0, 20, (5000, 4)), 3).astype(np.float32)
+    for name, kw in (("a.pcd", dict(padding=3906)), ("b.pcd", dict(extra_field=True)), ("c.pcd", dict(mode="ascii"))):
+        path = str(tmp_path / name)
+        _write_pcd(path, pts, **kw)
+        got = lpl.pcd_read(path)
+        assert got.shape == pts.shape and np.array_equal(got.view(np.uint32), pts.view(np.uint32)), name
+    # the oracle's own reader (tests only) agrees on the reference layout
+    assert np.array_equal(read_pcd_xyzi(str(tmp_path / "a.pcd")), lpl.pcd_read(str(tmp_path / "a.pcd")))
+    with pytest.raises(lpl.LplError):
+        lpl.pcd_read(str(tmp_path / "missing.pcd"))
+    if os.path.isdir("/root/reference/data"):
+        ref_file = "/root/reference/data/0000000000.pcd"
+        got = lpl.pcd_read(ref_file)
+        assert got.shape == (123398, 4) and np.array_equal(got, read_pcd_xyzi(ref_file))

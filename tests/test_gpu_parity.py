@@ -168,6 +168,51 @@ def test_pipeline_boxes_vs_reference_golden(ctx, golden0):
     _boxes_equal(out["boxes"], gp["kitti_f000_boxes"][:, :11], exact=True)
 
 
+def test_pointcloud2_ingest(ctx, golden0, golden100):
+    """lpl_pipeline_upload_cloud2 (replaces Processor::convert<PointT>, processor.cpp:42-179): raw
+    PointXYZIR / PointXYZ records unpacked on the device give the very same results as the packed upload."""
+    ctx.cluster_config(**NODE_CLUSTER_CFG)
+    frames = [golden0["pts"], golden100["pts"][:70001]]
+    rings = [golden0["ring"].astype(np.uint16), golden100["ring"].astype(np.uint16)[:70001]]
+    nf = ctx.upload(frames, rings=rings)
+    stages = lpl.STAGE_ALL & ~lpl.STAGE_RING
+    ctx.run(nf, stages)
+    ctx.sync(nf)
+    want = [ctx.download(f) for f in range(nf)]
+    msgs = []
+    for pts, ring in zip(frames, rings):
+        n = pts.shape[0]
+        rec = np.zeros((n, 32), np.uint8)           # pcl::PointXYZIR: x y z pad | intensity ring pad
+        rec[:, 0:12] = pts[:, :3].copy().view(np.uint8).reshape(n, 12)
+        rec[:, 16:20] = pts[:, 3:4].copy().view(np.uint8).reshape(n, 4)
+        rec[:, 20:22] = ring.view(np.uint8).reshape(n, 2)
+        msgs.append(dict(data=rec.reshape(-1), width=n, height=1, point_step=32, row_step=32 * n,
+                         x_offset=0, y_offset=4, z_offset=8, ring_offset=20))
+    nf = ctx.upload_cloud2(msgs)
+    ctx.run(nf, stages)
+    ctx.sync(nf)
+    for f in range(nf):
+        got = ctx.download(f)
+        for k in ("ring", "noise", "labels", "cluster_labels", "hull_offsets", "hull_xy", "zminmax"):
+            assert np.array_equal(got[k], want[f][k]), (f, k)
+    # organized 2-row layout with a row pitch and unaligned (packed 14-byte) records, no ring
+    pts = golden0["pts"][:4000]
+    rec = np.zeros((2, 2000 * 14 + 6), np.uint8)
+    body = np.zeros((4000, 14), np.uint8)
+    body[:, 1:13] = pts[:, :3].copy().view(np.uint8).reshape(4000, 12)
+    rec[:, :2000 * 14] = body.reshape(2, 2000 * 14)
+    ctx.upload_cloud2([dict(data=rec.reshape(-1), width=2000, height=2, point_step=14, row_step=2000 * 14 + 6,
+                            x_offset=1, y_offset=5, z_offset=9, ring_offset=-1)])
+    ctx.run(1, lpl.STAGE_RING | lpl.STAGE_DROR)
+    ctx.sync(1)
+    a = ctx.download(0)
+    ctx.upload([pts])
+    ctx.run(1, lpl.STAGE_RING | lpl.STAGE_DROR)
+    ctx.sync(1)
+    b = ctx.download(0)
+    assert a["n"] == 4000 and np.array_equal(a["ring"], b["ring"]) and np.array_equal(a["noise"], b["noise"])
+
+
 def test_edge_cases(ctx, port):
     empty = np.zeros((0, 4), np.float32)
     assert ctx.ring_partition(empty).shape == (0,)
