@@ -8,7 +8,9 @@
 // usage: adaptor_main <in.bin> <out.bin>
 //   in : u32 n, n x (float x, y, z, w), n x u16 ring
 //   out: u32 n, n x u8 noise, n x u32 label, u32 m, m x i32 cluster label, u32 K, K x u32 hull size,
-//        sum(hull size) x (double x, y)
+//        sum(hull size) x (double x, y), K x (8 double corners, float area, float yaw, u32 valid) from
+//        Polygonizer::boundingBoxRotatingCalipers on every hull (processor.cpp:704 passes its points
+//        the same way; dead code in the node)
 // exit code 3: no CUDA device (std::runtime_error from the adaptors), 4: any other exception
 #include <cstdint>
 #include <cstdio>
@@ -109,6 +111,8 @@ int main(int argc, char** argv)
         lpl::Polygonizer polygonizer;
         std::vector<std::uint32_t> hull_sizes;
         std::vector<double> hull_xy;
+        std::vector<lpl::BoundingBox> boxes;
+        std::vector<lpl::PointXY> hull_pts;
         std::vector<lpl::PointXY> pts;
         std::vector<std::int32_t> idx;
         for (std::int32_t l = 0; l <= max_label; ++l)
@@ -123,11 +127,14 @@ int main(int argc, char** argv)
             }
             polygonizer.convexHull(pts, idx);
             hull_sizes.push_back(static_cast<std::uint32_t>(idx.size()));
+            hull_pts.clear();
             for (const auto j : idx)
             {
                 hull_xy.push_back(pts[j].x);
                 hull_xy.push_back(pts[j].y);
+                hull_pts.push_back(pts[j]);
             }
+            boxes.push_back(polygonizer.boundingBoxRotatingCalipers(hull_pts));
         }
 
         std::FILE* fo = std::fopen(argv[2], "wb");
@@ -145,6 +152,21 @@ int main(int argc, char** argv)
         std::fwrite(&K, 4, 1, fo);
         std::fwrite(hull_sizes.data(), 4, K, fo);
         std::fwrite(hull_xy.data(), 8, hull_xy.size(), fo);
+        for (const auto& b : boxes)
+        {
+            double c[8];
+            for (int k = 0; k < 4; ++k)
+            {
+                c[2 * k] = b.is_valid ? b.corners[k].x : 0.0;
+                c[2 * k + 1] = b.is_valid ? b.corners[k].y : 0.0;
+            }
+            const float area = b.is_valid ? b.area : 0.0F, yaw = b.is_valid ? b.angle_rad : 0.0F;
+            const std::uint32_t valid = b.is_valid ? 1U : 0U;
+            std::fwrite(c, 8, 8, fo);
+            std::fwrite(&area, 4, 1, fo);
+            std::fwrite(&yaw, 4, 1, fo);
+            std::fwrite(&valid, 4, 1, fo);
+        }
         std::fclose(fo);
         std::printf("ok n=%u obstacles=%u clusters=%u hull_vertices=%zu\n", n, m, K, hull_xy.size() / 2);
         return 0;

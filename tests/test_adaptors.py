@@ -65,6 +65,9 @@ def test_adaptors_reproduce_the_reference_call_sequence(exe, tmp_path, golden0, 
     (K,) = struct.unpack_from("<I", raw, o); o += 4
     sizes = np.frombuffer(raw, np.uint32, K, o); o += 4 * K
     hxy = np.frombuffer(raw, np.float64, 2 * int(sizes.sum()), o).reshape(-1, 2)
+    o += 16 * int(sizes.sum())
+    box_dt = np.dtype([("c", np.float64, 8), ("area", np.float32), ("yaw", np.float32), ("valid", np.uint32)])
+    boxes = np.frombuffer(raw, box_dt, K, o)
     assert n == pts.shape[0]
     assert np.array_equal(noise, np.unpackbits(golden0["dror_exact"])[:n])
     assert np.array_equal(labels, golden0["labels"].astype(np.uint32))
@@ -72,4 +75,10 @@ def test_adaptors_reproduce_the_reference_call_sequence(exe, tmp_path, golden0, 
     off = golden0["hull_offsets"]
     assert np.array_equal(np.diff(off), sizes)
     assert np.abs(hxy - golden0["hull_xy"].astype(np.float64)).max() <= 1e-5
+    # Polygonizer::boundingBoxRotatingCalipers against the reference's own boxes for this frame
+    gb = np.load(os.path.join(ROOT, "tests", "golden", "kitti_polygonizer.npz"))["kitti_f000_boxes"][:, :11]
+    assert np.array_equal(boxes["valid"] != 0, gb[:, 10] != 0)
+    assert np.array_equal(boxes["c"].view(np.uint64), gb[:, :8].view(np.uint64))
+    assert np.array_equal(boxes["area"], gb[:, 8].astype(np.float32))
+    assert np.array_equal(boxes["yaw"], gb[:, 9].astype(np.float32))
     _ = (port, NODE_CLUSTER_CFG)
