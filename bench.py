@@ -427,7 +427,7 @@ def run_e2e(lpl, ctx0, frames, device, args, barrier, stages):
     per = (nf + n_parts - 1) // n_parts
     pipe = FramePipeline(device, max_pts, per, stages=stages, n_ctx=n_ctx)
     parts = [frames[a:a + per] for a in range(0, nf, per)]
-    pinned, views = [], []
+    pinned, views, packed = [], [], []
     for part in parts:
         buf = lpl.PinnedBuffer((sum(f.shape[0] for f in part), 4), np.float32)
         v, o = [], 0
@@ -437,11 +437,13 @@ def run_e2e(lpl, ctx0, frames, device, args, barrier, stages):
             o += f.shape[0]
         pinned.append(buf)
         views.append(v)
+        # the frames of a part-batch lie back to back in pinned memory: one H2D transfer per batch
+        packed.append((buf.array, np.array([f.shape[0] for f in part], np.uint32)))
 
     def run_steps(k):
         for _ in range(k):
             for i in range(len(views)):
-                pipe.submit(views[i])  # returns (and thereby downloads) the batch this slot held before
+                pipe.submit(views[i], packed=packed[i])  # returns (and thereby downloads) the batch this slot held before
         pipe.drain()
 
     run_steps(max(args.warmup, 1))

@@ -183,6 +183,11 @@ typedef struct lpl_frame
 int lpl_pipeline_upload(lpl_ctx* ctx, const lpl_frame* frames, uint32_t num_frames);
 /* Same, from device-resident frames (device-to-device copies). */
 int lpl_pipeline_upload_device(lpl_ctx* ctx, const lpl_frame* frames, uint32_t num_frames);
+/* Same as lpl_pipeline_upload for a batch whose frames lie back to back in ONE host buffer (pinned for
+ * an asynchronous copy): counts[num_frames] points per frame, 16 bytes per point. One DMA transfer
+ * for the whole batch instead of one per frame; a kernel spreads the frames into place. No ring planes
+ * (run with LPL_STAGE_RING, or ring-less). */
+int lpl_pipeline_upload_packed(lpl_ctx* ctx, const float* xyzw, const uint32_t* counts, uint32_t num_frames);
 /* One frame as a sensor_msgs/PointCloud2 payload (what Processor::convert<PointT> reads,
  * src/processor/src/processor.cpp:42-179): height * width records, point_step bytes apart inside a
  * row, rows row_step bytes apart; x / y / z are float32 at the given byte offsets, ring (uint16) at

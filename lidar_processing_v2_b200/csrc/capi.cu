@@ -670,6 +670,51 @@ int lpl_pipeline_upload_device(lpl_ctx* ctx, const lpl_frame* frames, std::uint3
     return upload_impl(ctx, frames, nf, true);
 }
 
+int lpl_pipeline_upload_packed(lpl_ctx* ctx, const float* xyzw, const std::uint32_t* counts, std::uint32_t nf)
+{
+    if (ctx == nullptr || counts == nullptr || nf == 0 || nf > ctx->c.d.B)
+    {
+        return fail(ctx, LPL_ERR_INVALID_ARGUMENT, "bad frame batch (null, empty or larger than max_frames)");
+    }
+    Ctx& c = ctx->c;
+    Dev& d = c.d;
+    LPL_TRY(cudaSetDevice(c.device));
+    if (ensure_stage(ctx, sizeof(std::uint32_t) * 2 * d.B) != 0)
+    {
+        return LPL_ERR_CUDA;
+    }
+    LPL_TRY(cudaStreamSynchronize(c.stream)); // the staging may still be in flight from the previous batch
+    auto* h_n = static_cast<std::uint32_t*>(c.h_stage);
+    std::uint32_t* h_start = h_n + d.B;
+    unsigned long long total = 0;
+    for (std::uint32_t f = 0; f < nf; ++f)
+    {
+        if (counts[f] > d.cap)
+        {
+            return fail(ctx, LPL_ERR_CAPACITY, "frame has more points than the context was created for");
+        }
+        h_n[f] = counts[f];
+        h_start[f] = static_cast<std::uint32_t>(total);
+        total += counts[f];
+    }
+    // the raw-record area (32 bytes per point of capacity) doubles as the packed staging: 2 x the need
+    if (total != 0 && xyzw == nullptr)
+    {
+        return fail(ctx, LPL_ERR_INVALID_ARGUMENT, "null points");
+    }
+    std::uint32_t* d_start = reinterpret_cast<std::uint32_t*>(d.raw_desc);
+    static_assert(sizeof(std::uint32_t) <= 32, "one start offset fits a descriptor slot");
+    LPL_TRY(cudaMemcpyAsync(d.n_in, h_n, sizeof(std::uint32_t) * nf, cudaMemcpyHostToDevice, c.stream));
+    LPL_TRY(cudaMemcpyAsync(d_start, h_start, sizeof(std::uint32_t) * nf, cudaMemcpyHostToDevice, c.stream));
+    if (total != 0)
+    {
+        LPL_TRY(cudaMemcpyAsync(d.raw, xyzw, static_cast<std::size_t>(total) * 16, cudaMemcpyHostToDevice, c.stream));
+        launch_spread_packed(&c, nf, d.raw, d_start);
+    }
+    ctx->have_ring = 0;
+    return LPL_OK;
+}
+
 int lpl_pipeline_upload_cloud2(lpl_ctx* ctx, const lpl_cloud2_frame* frames, std::uint32_t nf)
 {
     if (ctx == nullptr || frames == nullptr || nf == 0 || nf > ctx->c.d.B)

@@ -522,6 +522,7 @@ void launch_take_obstacles(Ctx* c, std::uint32_t nf);
 void launch_cluster(Ctx* c, std::uint32_t nf);
 void launch_hulls(Ctx* c, std::uint32_t nf);
 void launch_boxes(Ctx* c, std::uint32_t nf, int method);
+void launch_spread_packed(Ctx* c, std::uint32_t nf, const void* packed, const std::uint32_t* start);
 void launch_unpack_cloud2(Ctx* c, std::uint32_t nf, const unsigned char* raw, std::size_t raw_stride, const void* desc);
 void launch_boxes_hulls(Ctx* c, const double2* xy, const std::uint32_t* off, std::uint32_t K, int method, ObbBox* out);
 

@@ -72,6 +72,26 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// packed upload: the frames of a batch lie back to back in one buffer (one DMA transfer); this kernel
+// spreads them into the frame-major planes. start[f] = first point of frame f in the packed buffer.
+__global__ void __launch_bounds__(256)
+    k_spread_packed(Dev d, const float4* __restrict__ packed, const std::uint32_t* __restrict__ start)
+{
+    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t n = d.n_in[f];
+    const std::uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    if (i < n)
+    {
+        d.pts_in[static_cast<std::size_t>(f) * d.cap + i] = packed[static_cast<std::size_t>(start[f]) + i];
+    }
+}
+
+void launch_spread_packed(Ctx* c, std::uint32_t nf, const void* packed, const std::uint32_t* start)
+{
+    k_spread_packed<<<dim3((c->d.cap + 255) / 256, nf), 256, 0, c->stream>>>(c->d, static_cast<const float4*>(packed), start);
+    mark(c, "spread_packed");
+}
+
 void launch_unpack_cloud2(Ctx* c, std::uint32_t nf, const unsigned char* raw, std::size_t raw_stride, const void* desc)
 {
     k_unpack_cloud2<<<dim3((c->d.cap + 255) / 256, nf), 256, 0, c->stream>>>(c->d, raw, raw_stride,

@@ -36,7 +36,7 @@ EXPORTS = [
     "lpl_segmenter_config", "lpl_dror_config", "lpl_cluster_config", "lpl_set_jcp_mode",
     "lpl_ring_partition", "lpl_dror_filter", "lpl_segment", "lpl_cluster", "lpl_convex_hull",
     "lpl_cluster_hulls", "lpl_bounding_boxes",
-    "lpl_pipeline_upload", "lpl_pipeline_upload_device", "lpl_pipeline_upload_cloud2", "lpl_pcd_read",
+    "lpl_pipeline_upload", "lpl_pipeline_upload_device", "lpl_pipeline_upload_cloud2", "lpl_pipeline_upload_packed", "lpl_pcd_read",
     "lpl_pipeline_run", "lpl_pipeline_sync",
     "lpl_pipeline_want_image", "lpl_pipeline_counts", "lpl_pipeline_download",
     "lpl_pipeline_download_batch", "lpl_host_alloc", "lpl_host_free",
@@ -195,6 +195,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     L.lpl_pipeline_upload_device.argtypes = [vp, C.POINTER(Frame), u32]
     L.lpl_pipeline_upload_cloud2.argtypes = [vp, C.POINTER(Cloud2Frame), u32]
     L.lpl_pcd_read.argtypes = [C.c_char_p, vp, u32, C.POINTER(u32)]
+    L.lpl_pipeline_upload_packed.argtypes = [vp, vp, vp, u32]
     L.lpl_pipeline_run.argtypes = [vp, u32, u32]
     L.lpl_pipeline_sync.argtypes = [vp, u32]
     L.lpl_pipeline_want_image.argtypes = [vp, C.c_int]
@@ -445,6 +446,15 @@ class Context:
         self._chk(fn(self.h, arr, nf))
         self._keep = keep
         return nf
+
+    def upload_packed(self, xyzw, counts) -> int:
+        """xyzw: (sum(counts), 4) float32, the frames back to back (ideally pinned); counts: points per frame."""
+        a = np.ascontiguousarray(xyzw, dtype=np.float32)
+        cn = np.ascontiguousarray(counts, dtype=np.uint32)
+        assert a.ndim == 2 and a.shape[1] == 4 and int(cn.sum()) == a.shape[0]
+        self._chk(self.lib.lpl_pipeline_upload_packed(self.h, a.ctypes.data if a.size else None, cn.ctypes.data, len(cn)))
+        self._keep = [a, cn]
+        return len(cn)
 
     def upload_cloud2(self, messages) -> int:
         """messages: dicts with data (uint8 array), width, height, point_step, row_step, x/y/z_offset and

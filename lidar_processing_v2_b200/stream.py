@@ -67,15 +67,20 @@ class FramePipeline:
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
-    def submit(self, frames):
-        """Enqueue a batch (list of (n, 4) float32 arrays, ideally views of pinned memory). Returns
-        (counts[5][nf], BatchBuffers) of the batch that previously used this slot, or None."""
+    def submit(self, frames, packed=None):
+        """Enqueue a batch (list of (n, 4) float32 arrays, ideally views of pinned memory). When the
+        frames lie back to back in one buffer, pass it as packed=(array, counts): the batch then crosses
+        PCIe as one transfer. Returns (counts[5][nf], BatchBuffers) of the batch that previously used
+        this slot, or None."""
         i = self.turn
         done = self.collect(i)
-        nf = self.ctx[i].upload(frames)
+        if packed is not None:
+            nf = self.ctx[i].upload_packed(packed[0], packed[1])
+        else:
+            nf = self.ctx[i].upload(frames)
         self.ctx[i].run(nf, self.stages)
         self.inflight[i] = nf
-        self.h2d_bytes += sum(int(f.shape[0]) for f in frames) * 16
+        self.h2d_bytes += (int(np.sum(packed[1])) if packed is not None else sum(int(f.shape[0]) for f in frames)) * 16
         self.turn = (self.turn + 1) % self.n_ctx
         return done
 

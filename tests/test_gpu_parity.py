@@ -213,6 +213,22 @@ def test_pointcloud2_ingest(ctx, golden0, golden100):
     assert a["n"] == 4000 and np.array_equal(a["ring"], b["ring"]) and np.array_equal(a["noise"], b["noise"])
 
 
+def test_packed_upload_equals_per_frame_upload(ctx, golden0, golden100):
+    frames = [golden0["pts"][:50000], golden100["pts"], golden0["pts"][:0], golden0["pts"][:7]]
+    ctx.cluster_config(**NODE_CLUSTER_CFG)
+    nf = ctx.upload(frames)
+    ctx.run(nf, lpl.STAGE_ALL)
+    ctx.sync(nf)
+    want = [ctx.download(f) for f in range(nf)]
+    nf = ctx.upload_packed(np.concatenate(frames), [f.shape[0] for f in frames])
+    ctx.run(nf, lpl.STAGE_ALL)
+    ctx.sync(nf)
+    for f in range(nf):
+        got = ctx.download(f)
+        for k in ("ring", "noise", "labels", "cluster_labels", "hull_offsets", "hull_xy", "zminmax"):
+            assert np.array_equal(got[k], want[f][k]), (f, k)
+
+
 def test_edge_cases(ctx, port):
     empty = np.zeros((0, 4), np.float32)
     assert ctx.ring_partition(empty).shape == (0,)
