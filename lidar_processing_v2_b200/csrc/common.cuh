@@ -368,22 +368,27 @@ __device__ __forceinline__ void accumulate_cluster_stats(unsigned long long* ext
         return;
     }
     const bool lead = static_cast<int>(lane_id()) == __ffs(peers) - 1;
+    // the leader fetches the cluster's running values up front, all loads in flight together: their
+    // L2 latency overlaps the reductions below (loads placed behind the first atomic could not be
+    // hoisted by the compiler and would cost one round trip each)
+    unsigned long long* e = ext + static_cast<std::size_t>(label) * 8;
+    ulonglong2 cur01 = make_ulonglong2(0, 0), cur23 = cur01, cur45 = cur01, cur67 = cur01;
+    std::uint32_t cur_zmin = 0, cur_zmax = 0;
+    if (lead)
+    {
+        const ulonglong2* e2 = reinterpret_cast<const ulonglong2*>(e);
+        cur01 = __ldcg(e2);
+        cur23 = __ldcg(e2 + 1);
+        cur45 = __ldcg(e2 + 2);
+        cur67 = __ldcg(e2 + 3);
+        cur_zmin = __ldcg(zmin_u + label);
+        cur_zmax = __ldcg(zmax_u + label);
+    }
     const std::uint32_t zk = ord_f32(z);
     const std::uint32_t zlo = __reduce_min_sync(peers, zk);
     const std::uint32_t zhi = __reduce_max_sync(peers, zk);
-    if (lead)
-    {
-        if (zlo < __ldcg(zmin_u + label))
-        {
-            atomicMin(&zmin_u[label], zlo);
-        }
-        if (zhi > __ldcg(zmax_u + label))
-        {
-            atomicMax(&zmax_u[label], zhi);
-        }
-    }
-    unsigned long long* e = ext + static_cast<std::size_t>(label) * 8;
     const float v[8] = {x, x + y, y, x - y, x, x + y, y, x - y};
+    unsigned long long key[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k)
     {
@@ -400,19 +405,32 @@ __device__ __forceinline__ void accumulate_cluster_stats(unsigned long long* ext
             b = __reduce_max_sync(peers, vk);
             bi = __reduce_max_sync(peers, vk == b ? idx : 0u);
         }
-        if (lead)
+        key[k] = (static_cast<unsigned long long>(b) << 32) | bi;
+    }
+    if (lead)
+    {
+        if (zlo < cur_zmin)
         {
-            const unsigned long long key = (static_cast<unsigned long long>(b) << 32) | bi;
-            const unsigned long long cur = __ldcg(e + k);
-            if (is_min ? key < cur : key > cur)
+            atomicMin(&zmin_u[label], zlo);
+        }
+        if (zhi > cur_zmax)
+        {
+            atomicMax(&zmax_u[label], zhi);
+        }
+        const unsigned long long cur[8] = {cur01.x, cur01.y, cur23.x, cur23.y, cur45.x, cur45.y, cur67.x, cur67.y};
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+        {
+            const bool is_min = (k == 0 || k == 1 || k == 2 || k == 7);
+            if (is_min ? key[k] < cur[k] : key[k] > cur[k])
             {
                 if (is_min)
                 {
-                    atomicMin(e + k, key);
+                    atomicMin(e + k, key[k]);
                 }
                 else
                 {
-                    atomicMax(e + k, key);
+                    atomicMax(e + k, key[k]);
                 }
             }
         }

@@ -19,6 +19,14 @@ namespace lpl
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ int quadrant_of(float x, float y)
 {
+    // More than ~1e-3 rad away from every axis the quadrant follows from the signs alone: neither the
+    // rounding of atan2f nor of the "+ 2 pi" / the float thresholds can move the azimuth across a
+    // boundary there. Only points next to an axis (and zeros / NaNs) take the exact glibc path.
+    const float ax = fabsf(x), ay = fabsf(y);
+    if (ay > ax * 9.765625e-4f && ax > ay * 9.765625e-4f)
+    {
+        return y > 0.f ? (x > 0.f ? 0 : 1) : (x > 0.f ? 3 : 2);
+    }
     // dataloader.cpp:96-114; M_PI_2f, M_PIf and 1.5F * M_PIf as float constants
     float az = atan2f_glibc(y, x);
     az = (az < 0.f) ? (az + 2.0f * 3.14159265358979323846f) : az;
