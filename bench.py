@@ -124,15 +124,14 @@ def algorithmic_bytes(name: str, s: dict) -> float:
         "dror_mark": 20 * U + 16384 * F, "dror_grid_count": 16 * N, "dror_grid_scan": 8 * 131072 * F,
         "dror_grid_scatter": 16 * N + 16 * U * 8,
         "dror_query": 20 * U + U,
-        "take_valid": (16 + 2 + 1) * N + 20 * V, "take_all": (16 + 2) * N + 20 * V,
-        "seg_bin": 16 * V + 12 * V, "seg_cell_scan": 8 * CELLS, "seg_scatter": (16 + 8) * V + 8 * NB,
+        "seg_bin": (16 + 2 + 1) * N + 12 * N, "seg_cell_scan": 8 * CELLS, "seg_scatter": (16 + 8) * N + 8 * NB,
         "seg_cell": 8 * NB + 8 * CELLS, "seg_elev": 12 * CELLS,
-        "seg_label": (16 + 4) * V + 4 * NB + 1 * V,
+        "seg_label": (16 + 4) * N + 4 * NB + 1 * N + 16 * C,
         "ransac_draw": 1024 * F + 8 * CELLS, "ransac_plane": 120 * 64 * F, "ransac_count": 16 * C,
-        "seg_image": (16 + 4 + 4 + 1) * V + 1 * NB + 8 * NB, "seg_px": 8 * PX + 17 * PX + 17 * PX,
+        "seg_image": (16 + 4 + 4 + 1) * N + 1 * NB + 8 * NB, "seg_px": 8 * PX + 17 * PX + 17 * PX,
         "seg_dilate": 2 * PX, "jcp_queue": 2 * PX + 4 * Q,
         "jcp_pre": Q * (25 * 17 + 24 * 4 + 8), "jcp_resolve": PX * 1 + Q * (8 + 4 + 96) + PX * 17 + V * 2,
-        "take_obstacles": 1 * V + 20 * M + 20 * M,
+        "take_obstacles": 1 * N + 16 * M + 20 * M,
         "clu_sph": 16 * M + 16 * M, "clu_insert": 16 * M + 4 * M, "clu_edges": 8 * M + 52 * M // 3,
         "clu_union_sm": 52 * M // 3 + 8 * M // 3, "clu_union": 8 * M, "clu_flatten": 8 * M,
         "clu_rank": 8 * M, "clu_labels": 8 * M + 16 * M,

@@ -61,8 +61,6 @@ void carve(Dev& d, Carver& cv, int npx, int ncell_cap, std::uint32_t** mt_raw)
     cv.take(d.grid_pts, B * cap);
     cv.take(d.unres, B * cap);
     cv.take(d.n_unres, B);
-    cv.take(d.pts_v, B * cap);
-    cv.take(d.idx_v, B * cap);
     cv.take(d.n_v, B);
     cv.take(d.cell, B * cap);
     cv.take(d.px, B * cap);
@@ -96,7 +94,6 @@ void carve(Dev& d, Carver& cv, int npx, int ncell_cap, std::uint32_t** mt_raw)
     cv.take(d.runs, B * q);
     cv.take(d.n_runs, B);
     cv.take(d.jcp_rounds, B);
-    cv.take(d.seg_label, B * cap);
     cv.take(d.labels_out, B * cap);
     cv.take(d.bgr, B * npx * 3);
     cv.take(d.pts_o, B * cap);
@@ -822,16 +819,10 @@ int lpl_pipeline_run(lpl_ctx* ctx, std::uint32_t nf, std::uint32_t stages)
     {
         launch_dror(&c, nf);
     }
-    if (stages & (LPL_STAGE_SEGMENT | LPL_STAGE_CLUSTER | LPL_STAGE_HULLS))
+    if ((stages & LPL_STAGE_SEGMENT) == 0 && (stages & (LPL_STAGE_CLUSTER | LPL_STAGE_HULLS)) != 0)
     {
-        if (stages & LPL_STAGE_DROR)
-        {
-            launch_take_valid(&c, nf);
-        }
-        else
-        {
-            launch_take_all(&c, nf);
-        }
+        // no labels in this run: the obstacle cloud is empty rather than a previous batch's
+        LPL_TRY(cudaMemsetAsync(d.labels_out, 0, static_cast<std::size_t>(d.cap) * nf, c.stream));
     }
     if (stages & LPL_STAGE_SEGMENT)
     {
@@ -1078,7 +1069,7 @@ int lpl_segment(lpl_ctx* ctx, const void* points, std::size_t stride, std::int32
         LPL_TRY(cudaMemsetAsync(d.ring, 0, sizeof(std::uint16_t) * d.cap, c.stream));
     }
     c.seg.use_ring = (ring_offset >= 0 && ctx->seg_cfg.assume_unorganized_cloud == 0) ? 1 : 0;
-    launch_take_all(&c, 1);
+    LPL_TRY(cudaMemsetAsync(d.noise, 0, d.cap, c.stream)); // every point enters the segmenter
     launch_segment(&c, 1, bgr_image_out != nullptr);
     std::uint8_t* raw = reinterpret_cast<std::uint8_t*>(labels_out) + static_cast<std::size_t>(n) * 3;
     if (n != 0)

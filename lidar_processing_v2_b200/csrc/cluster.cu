@@ -540,34 +540,33 @@ __global__ void __launch_bounds__(256) k_clu_labels(Dev d)
 // (src/processor/src/processor.cpp:562-579)
 struct ObstaclePred
 {
-    const std::uint8_t* seg_label;
+    const std::uint8_t* labels; // Label per input point
     std::uint32_t cap;
     __device__ bool operator()(std::uint32_t f, std::uint32_t i) const
     {
-        return seg_label[static_cast<std::size_t>(f) * cap + i] == PX_OBSTACLE;
+        return labels[static_cast<std::size_t>(f) * cap + i] == PX_OBSTACLE;
     }
 };
 
 struct ObstacleEmit
 {
-    const float4* pts_v;
-    const std::uint32_t* idx_v;
+    const float4* pts_in;
     float4* pts_o;
     std::uint32_t* idx_o;
     std::uint32_t cap;
     __device__ void operator()(std::uint32_t f, std::uint32_t i, std::uint32_t pos) const
     {
         const std::size_t o = static_cast<std::size_t>(f) * cap;
-        pts_o[o + pos] = pts_v[o + i];
-        idx_o[o + pos] = idx_v[o + i];
+        pts_o[o + pos] = pts_in[o + i];
+        idx_o[o + pos] = i;
     }
 };
 
 void launch_take_obstacles(Ctx* c, std::uint32_t nf)
 {
     Dev& d = c->d;
-    launch_compact(c, "take_obstacles", nf, d.tiles, d.n_v, 0u, d.tile_cnt, d.n_o, ObstaclePred{d.seg_label, d.cap},
-                   ObstacleEmit{d.pts_v, d.idx_v, d.pts_o, d.idx_o, d.cap});
+    launch_compact(c, "take_obstacles", nf, d.tiles, d.n_in, 0u, d.tile_cnt, d.n_o, ObstaclePred{d.labels_out, d.cap},
+                   ObstacleEmit{d.pts_in, d.pts_o, d.idx_o, d.cap});
 }
 
 void launch_cluster(Ctx* c, std::uint32_t nf)

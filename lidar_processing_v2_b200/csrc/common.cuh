@@ -101,9 +101,7 @@ struct Dev
     float4* grid_pts;         // [B][cap]  points in cell order
     std::uint32_t* unres;     // [B][cap]  unresolved point indices after the scan-line pass
     std::uint32_t* n_unres;   // [B]
-    // ---- cloud entering segmentation (valid points, ring packed into .w)
-    float4* pts_v;            // [B][cap]
-    std::uint32_t* idx_v;     // [B][cap]  index in the input cloud
+    // ---- segmentation works on the input cloud in place (noise-masked); n_v counts the valid points
     std::uint32_t* n_v;       // [B]
     // ---- segmentation scratch
     std::int32_t* cell;       // [B][cap]  polar cell or -1
@@ -117,7 +115,7 @@ struct Dev
     std::uint32_t* ccnt;      // [B][ncell] RANSAC candidates per cell, then their exclusive prefix in (slice, bin) order
     float* cell_zmin;         // [B][ncell]
     float* elev;              // [B][ncell]
-    std::uint8_t* lab;        // [B][cap]  label per point of the segmented cloud; bit 7 = RANSAC candidate
+    std::uint8_t* lab;        // [B][cap]  RECM label per input point; bit 7 = RANSAC candidate
     std::uint32_t* n_cand;    // [B]
     float4* cpts;             // [B][cap]  dense unordered copy of the candidate points (inlier count)
     std::uint32_t* n_cpts;    // [B]
@@ -139,7 +137,6 @@ struct Dev
     std::uint32_t* runs;      // [B][qcap] first queue entry of every run of horizontally adjacent queued pixels
     std::uint32_t* n_runs;    // [B]
     std::uint32_t* jcp_rounds;// [B]
-    std::uint8_t* seg_label;  // [B][cap]  label per point of the segmented cloud
     std::uint8_t* labels_out; // [B][cap]  Label (0/1/2) per *input* point
     std::uint8_t* bgr;        // [B][npx*3]
     // ---- obstacle cloud / clustering
@@ -533,8 +530,6 @@ __global__ void k_excl_scan(const std::uint32_t* __restrict__ in, std::uint32_t 
 struct Ctx;
 void launch_ring(Ctx* c, std::uint32_t nf);
 void launch_dror(Ctx* c, std::uint32_t nf);
-void launch_take_all(Ctx* c, std::uint32_t nf);   // pts_in (+ ring) -> pts_v without DROR
-void launch_take_valid(Ctx* c, std::uint32_t nf); // DROR-valid points -> pts_v
 void launch_segment(Ctx* c, std::uint32_t nf, bool want_image);
 void launch_take_obstacles(Ctx* c, std::uint32_t nf);
 void launch_cluster(Ctx* c, std::uint32_t nf);

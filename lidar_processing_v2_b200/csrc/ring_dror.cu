@@ -542,48 +542,4 @@ void launch_dror(Ctx* c, std::uint32_t nf)
     mark(c, "dror_query");
 }
 
-// ------------------------------------------------------------------------------------------
-// Hand-over to segmentation: stable compaction of the DROR-valid points (or all points), with
-// the ring index carried in the .w lane and the original index kept for the label scatter.
-// ------------------------------------------------------------------------------------------
-struct ValidPred
-{
-    const std::uint8_t* noise; // nullptr = take all
-    std::uint32_t cap;
-    __device__ bool operator()(std::uint32_t f, std::uint32_t i) const
-    {
-        return noise == nullptr || noise[static_cast<std::size_t>(f) * cap + i] == 0;
-    }
-};
-
-struct ValidEmit
-{
-    const float4* pts_in;
-    const std::uint16_t* ring;
-    float4* pts_v;
-    std::uint32_t* idx_v;
-    std::uint32_t cap;
-    __device__ void operator()(std::uint32_t f, std::uint32_t i, std::uint32_t pos) const
-    {
-        const std::size_t o = static_cast<std::size_t>(f) * cap;
-        float4 p = pts_in[o + i];
-        p.w = __uint_as_float(static_cast<std::uint32_t>(ring[o + i]));
-        pts_v[o + pos] = p;
-        idx_v[o + pos] = i;
-    }
-};
-
-void launch_take_valid(Ctx* c, std::uint32_t nf)
-{
-    Dev& d = c->d;
-    launch_compact(c, "take_valid", nf, d.tiles, d.n_in, 0u, d.tile_cnt, d.n_v, ValidPred{d.noise, d.cap},
-                   ValidEmit{d.pts_in, d.ring, d.pts_v, d.idx_v, d.cap});
-}
-
-void launch_take_all(Ctx* c, std::uint32_t nf)
-{
-    Dev& d = c->d;
-    launch_compact(c, "take_all", nf, d.tiles, d.n_in, 0u, d.tile_cnt, d.n_v, ValidPred{nullptr, d.cap},
-                   ValidEmit{d.pts_in, d.ring, d.pts_v, d.idx_v, d.cap});
-}
 } // namespace lpl

@@ -45,19 +45,30 @@ __constant__ int c_off_w[24] = {-2, -1, 0, 1, 2, -2, -1, 0, 1, 2, -2, -1,
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_seg_bin(Dev d, SegParams sp)
 {
+    // The segmenter works on the input cloud in place: points DROR flagged as NOISE simply are not
+    // binned. Everything order dependent downstream only uses the relative order of the points,
+    // which a stable compaction of the VALID points would preserve - so the compaction (and the
+    // index indirection it needs) is skipped; n_v only counts the valid points.
+    __shared__ std::uint32_t s_valid;
     const std::uint32_t f = blockIdx.y;
-    const std::uint32_t n = d.n_v[f];
+    const std::uint32_t n = d.n_in[f];
     if (blockIdx.x * 256u >= n)
     {
         return;
     }
+    if (threadIdx.x == 0)
+    {
+        s_valid = 0;
+    }
+    __syncthreads();
     const std::uint32_t i = blockIdx.x * 256u + threadIdx.x;
     const std::size_t o = static_cast<std::size_t>(f) * d.cap;
     std::int32_t cell = -1;
     std::uint32_t px = 0;
-    if (i < n)
+    const bool valid = i < n && d.noise[o + i] == 0;
+    if (valid)
     {
-        const float4 p = d.pts_v[o + i];
+        const float4 p = d.pts_in[o + i];
         if (!(p.z < sp.z_lo || p.z > sp.z_hi))
         {
             const float dist = sqrtf(p.x * p.x + p.y * p.y);
@@ -71,7 +82,7 @@ __global__ void __launch_bounds__(256) k_seg_bin(Dev d, SegParams sp)
                 bool ok = true;
                 if (sp.use_ring)
                 {
-                    hgt = static_cast<std::int32_t>(__float_as_uint(p.w) & 0xffffu);
+                    hgt = static_cast<std::int32_t>(d.ring[o + i]);
                     ok = hgt < sp.H;
                 }
                 else
@@ -90,6 +101,11 @@ __global__ void __launch_bounds__(256) k_seg_bin(Dev d, SegParams sp)
                 }
             }
         }
+    }
+    const std::uint32_t nvalid = __popc(__ballot_sync(0xffffffffu, valid));
+    if (lane_id() == 0 && nvalid != 0)
+    {
+        atomicAdd(&s_valid, nvalid);
     }
     // consecutive points of a scan line mostly share a cell: one atomic per (warp, cell)
     const std::uint32_t peers = __match_any_sync(0xffffffffu, cell);
@@ -111,6 +127,11 @@ __global__ void __launch_bounds__(256) k_seg_bin(Dev d, SegParams sp)
         d.px[o + i] = px;
         d.slot[o + i] = slot;
     }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_valid != 0)
+    {
+        atomicAdd(&d.n_v[f], s_valid);
+    }
 }
 
 // cell-major copy of (point index, z): the only per-cell consumers are the height statistics of
@@ -118,7 +139,7 @@ __global__ void __launch_bounds__(256) k_seg_bin(Dev d, SegParams sp)
 __global__ void __launch_bounds__(256) k_seg_scatter(Dev d, SegParams sp)
 {
     const std::uint32_t f = blockIdx.y;
-    const std::uint32_t n = d.n_v[f];
+    const std::uint32_t n = d.n_in[f];
     const std::uint32_t i = blockIdx.x * 256u + threadIdx.x;
     if (i >= n)
     {
@@ -129,7 +150,7 @@ __global__ void __launch_bounds__(256) k_seg_scatter(Dev d, SegParams sp)
     if (cell >= 0)
     {
         const std::uint32_t s = d.cell_start[static_cast<std::size_t>(f) * (sp.ncell + 1) + cell];
-        d.zo[o + s + d.slot[o + i]] = make_uint2(i, __float_as_uint(d.pts_v[o + i].z));
+        d.zo[o + s + d.slot[o + i]] = make_uint2(i, __float_as_uint(d.pts_in[o + i].z));
     }
 }
 
@@ -414,7 +435,7 @@ __global__ void __launch_bounds__(128) k_seg_elev(Dev d, SegParams sp)
 __global__ void __launch_bounds__(256) k_seg_label(Dev d, SegParams sp)
 {
     const std::uint32_t f = blockIdx.y;
-    const std::uint32_t n = d.n_v[f];
+    const std::uint32_t n = d.n_in[f];
     if (blockIdx.x * 256u >= n)
     {
         return;
@@ -429,7 +450,7 @@ __global__ void __launch_bounds__(256) k_seg_label(Dev d, SegParams sp)
         std::uint8_t l = 0;
         if (c >= 0)
         {
-            pt = d.pts_v[o + i];
+            pt = d.pts_in[o + i];
             const float z = pt.z;
             const float e = d.elev[static_cast<std::size_t>(f) * sp.ncell + c];
             l = (z >= e + sp.thr) ? PX_OBSTACLE : PX_GROUND;
@@ -691,8 +712,8 @@ __global__ void __launch_bounds__(64) k_ransac_plane(Dev d, SegParams sp)
     float4 plane = make_float4(0.f, 0.f, __int_as_float(0x7fc00000), 0.f); // skipped
     if (runit)
     {
-        const float4 p2 = d.pts_v[o + pidx[0]];
-        const float4 p3 = d.pts_v[o + pidx[1]];
+        const float4 p2 = d.pts_in[o + pidx[0]];
+        const float4 p3 = d.pts_in[o + pidx[1]];
         const float p1x = 0.0f, p1y = 0.0f, p1z = sp.p1z;
         float nx = ((p2.y - p1y) * (p3.z - p1z)) - ((p2.z - p1z) * (p3.y - p1y));
         float ny = ((p2.z - p1z) * (p3.x - p1x)) - ((p2.x - p1x) * (p3.z - p1z));
@@ -789,7 +810,7 @@ __global__ void __launch_bounds__(256) k_seg_image(Dev d, SegParams sp)
     __shared__ float4 s_plane;
     __shared__ int s_have;
     const std::uint32_t f = blockIdx.y;
-    const std::uint32_t n = d.n_v[f];
+    const std::uint32_t n = d.n_in[f];
     if (blockIdx.x * 256u >= n)
     {
         return;
@@ -839,7 +860,7 @@ __global__ void __launch_bounds__(256) k_seg_image(Dev d, SegParams sp)
     {
         return;
     }
-    const float4 p = d.pts_v[o + i];
+    const float4 p = d.pts_in[o + i];
     std::uint8_t l = d.lab[o + i] & 0x7f;
     if (s_have && (c % sp.rings) < kRansacBins)
     {
@@ -874,7 +895,7 @@ __global__ void __launch_bounds__(256) k_seg_px(Dev d, SegParams sp)
     {
         const std::size_t o = static_cast<std::size_t>(f) * d.cap;
         const std::uint32_t i = static_cast<std::uint32_t>(key & ((1ULL << sp.idx_bits) - 1ULL));
-        const float4 q = d.pts_v[o + i];
+        const float4 q = d.pts_in[o + i];
         v = make_float4(q.x, q.y, q.z, __int_as_float(static_cast<int>(i)));
         c = d.lab[o + i];
     }
@@ -1383,8 +1404,7 @@ __global__ void __launch_bounds__(256) k_seg_labels_out(Dev d, SegParams sp, int
         const int idx = __float_as_int(d.pxpt[po + p].w);
         if (idx >= 0)
         {
-            d.seg_label[o + idx] = c;
-            d.labels_out[o + d.idx_v[o + idx]] = c;
+            d.labels_out[o + idx] = c;
         }
     }
     if (want_image)
@@ -1424,7 +1444,7 @@ void launch_segment(Ctx* c, std::uint32_t nf, bool want_image)
     cudaMemsetAsync(d.ccnt, 0, sizeof(std::uint32_t) * sp.ncell * nf, s);
     cudaMemsetAsync(d.n_cpts, 0, sizeof(std::uint32_t) * nf, s);
     cudaMemsetAsync(d.key, 0xff, sizeof(unsigned long long) * sp.npx * nf, s);
-    cudaMemsetAsync(d.seg_label, 0, static_cast<std::size_t>(d.cap) * nf, s);
+    cudaMemsetAsync(d.n_v, 0, sizeof(std::uint32_t) * nf, s);
     cudaMemsetAsync(d.labels_out, 0, static_cast<std::size_t>(d.cap) * nf, s);
     cudaMemsetAsync(d.n_border, 0, sizeof(std::uint32_t) * nf, s);
 
