@@ -300,6 +300,7 @@ int check_status(lpl_ctx* ctx, std::uint32_t nf)
         const std::uint32_t s = ctx->h_status[f];
         if (s != 0)
         {
+            c.hash_clean = false; // an aborted batch may leave voxel hash slots behind: clear all next time
             std::snprintf(c.err, sizeof(c.err),
                           "frame %u exceeded a reserved capacity:%s%s%s%s", f,
                           (s & ST_QUEUE_OVERFLOW) ? " JCP queue" : "", (s & ST_RNG_EXHAUSTED) ? " RANSAC RNG table" : "",

@@ -555,6 +555,7 @@ struct Ctx
     std::size_t h_stage_bytes = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     unsigned long long launches = 0; // kernels launched since the last reset
+    bool hash_clean = false;         // the voxel hash planes are in their cleared state (cluster.cu)
     // per-kernel CUDA-event profile of the last lpl_pipeline_run (lpl_profile_*)
     static constexpr int kProfMax = 96;
     bool prof_on = false;
