@@ -828,6 +828,11 @@ int lpl_pipeline_run(lpl_ctx* ctx, std::uint32_t nf, std::uint32_t stages)
     if (stages & LPL_STAGE_SEGMENT)
     {
         launch_segment(&c, nf, ctx->want_image != 0);
+        if (c.launch_failed)
+        {
+            c.launch_failed = false;
+            return LPL_ERR_CUDA; // message already in err
+        }
     }
     if (stages & LPL_STAGE_CLUSTER)
     {
@@ -1072,6 +1077,11 @@ int lpl_segment(lpl_ctx* ctx, const void* points, std::size_t stride, std::int32
     c.seg.use_ring = (ring_offset >= 0 && ctx->seg_cfg.assume_unorganized_cloud == 0) ? 1 : 0;
     LPL_TRY(cudaMemsetAsync(d.noise, 0, d.cap, c.stream)); // every point enters the segmenter
     launch_segment(&c, 1, bgr_image_out != nullptr);
+    if (c.launch_failed)
+    {
+        c.launch_failed = false;
+        return LPL_ERR_CUDA;
+    }
     std::uint8_t* raw = reinterpret_cast<std::uint8_t*>(labels_out) + static_cast<std::size_t>(n) * 3;
     if (n != 0)
     {

@@ -5,6 +5,7 @@
 // and per-frame point counts living in device memory (no host sync between stages).
 #pragma once
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -556,6 +557,9 @@ struct Ctx
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     unsigned long long launches = 0; // kernels launched since the last reset
     bool hash_clean = false;         // the voxel hash planes are in their cleared state (cluster.cu)
+    alignas(64) CUtensorMap code_map{}; // TMA descriptor of the pixel-code planes (segment.cu: k_seg_dilate_tma)
+    bool have_code_map = false;
+    bool launch_failed = false;      // a launcher could not set up its kernel (message in err)
     // per-kernel CUDA-event profile of the last lpl_pipeline_run (lpl_profile_*)
     static constexpr int kProfMax = 96;
     bool prof_on = false;

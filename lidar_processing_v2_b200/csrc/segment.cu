@@ -6,7 +6,7 @@
 //   RANSAC             :321-479   -> candidate flags (k_seg_label), k_ransac_draw, k_ransac_plane,
 //                                    k_ransac_count
 //   image scatter      :291-318   -> k_seg_image (64-bit atomicMin keys), k_seg_px
-//   JCP                :481-638   -> k_seg_dilate (5x5 stencil on shared-memory tiles),
+//   JCP                :481-638   -> k_seg_dilate_tma (5x5 stencil on range-image tiles staged by TMA),
 //                                    queue compaction, k_jcp_pre, k_jcp_resolve
 //   populateLabels     :640-669   -> k_seg_labels_out
 //
@@ -908,33 +908,15 @@ __global__ void __launch_bounds__(256) k_seg_px(Dev d, SegParams sp)
 // One CTA per 16 x 128 pixel tile; the tile and its 2-pixel halo are staged in shared memory.
 // ------------------------------------------------------------------------------------------
 constexpr int kDilTh = 16, kDilTw = 128;
+constexpr int kDilBoxW = 160; // tile + 16 columns on both sides: TMA wants the innermost box coordinate (in bytes)
+                              // and extent to be multiples of 16, the stencil only needs 2 of those 16 columns
 
-__global__ void __launch_bounds__(256) k_seg_dilate(Dev d, SegParams sp)
+// vertical 5-tap maximum over the horizontal maxima + the queue / dilated flags (segmenter.cpp:491-514)
+template <int kPitch>
+__device__ __forceinline__ void dilate_finish(const Dev& d, const SegParams& sp, std::uint32_t f, int h0, int w0,
+                                              const std::uint8_t (*hmax)[kPitch])
 {
-    __shared__ std::uint8_t tile[kDilTh + 4][kDilTw + 4 + 4];
-    __shared__ std::uint8_t hmax[kDilTh + 4][kDilTw + 4];
-    const std::uint32_t f = blockIdx.z;
-    const int h0 = blockIdx.y * kDilTh, w0 = blockIdx.x * kDilTw;
     std::uint8_t* code = d.code + static_cast<std::size_t>(f) * sp.npx;
-    for (int t = threadIdx.x; t < (kDilTh + 4) * (kDilTw + 4); t += 256)
-    {
-        const int r = t / (kDilTw + 4), c = t % (kDilTw + 4);
-        const int h = h0 + r - 2, w = w0 + c - 2;
-        std::uint8_t v = 0;
-        if (h >= 0 && h < sp.H && w >= 0 && w < sp.W)
-        {
-            v = ((code[h * sp.W + w] & 0xf) == PX_OBSTACLE) ? 1 : 0;
-        }
-        tile[r][c] = v;
-    }
-    __syncthreads();
-    // separable maximum: horizontal 5 taps on (kDilTh + 4) rows, then vertical 5 taps
-    for (int t = threadIdx.x; t < (kDilTh + 4) * kDilTw; t += 256)
-    {
-        const int r = t / kDilTw, c = t % kDilTw;
-        hmax[r][c] = tile[r][c] | tile[r][c + 1] | tile[r][c + 2] | tile[r][c + 3] | tile[r][c + 4];
-    }
-    __syncthreads();
     for (int t = threadIdx.x; t < kDilTh * kDilTw; t += 256)
     {
         const int r = t / kDilTw, c = t % kDilTw;
@@ -957,6 +939,120 @@ __global__ void __launch_bounds__(256) k_seg_dilate(Dev d, SegParams sp)
             }
         }
     }
+}
+
+// Tile + halo staged by TMA: one elected thread issues a 3-D tiled bulk copy (x = column, y = row,
+// z = frame) of the (16 + 4) x 160-byte box whose corner lies two rows up and 16 columns left of the tile;
+// the tensor map's out-of-bounds fill supplies the zeros beyond the image borders, which is exactly
+// the reference's in-bounds 5x5 maximum (cv::dilate over the image rectangle). Neighbouring tiles
+// rewrite GROUND -> QUEUED / EMPTY -> DILATED in the same plane while this box is read, but never an
+// OBSTACLE pixel, and only (code & 0xf) == OBSTACLE is looked at.
+__global__ void __launch_bounds__(256) k_seg_dilate_tma(Dev d, SegParams sp, const __grid_constant__ CUtensorMap code_map)
+{
+    __shared__ __align__(128) std::uint8_t raw[kDilTh + 4][kDilBoxW];
+    __shared__ std::uint8_t hmax[kDilTh + 4][kDilTw + 4];
+    __shared__ __align__(8) unsigned long long mbar;
+    const std::uint32_t f = blockIdx.z;
+    const int h0 = blockIdx.y * kDilTh, w0 = blockIdx.x * kDilTw;
+    const std::uint32_t mbar_s = static_cast<std::uint32_t>(__cvta_generic_to_shared(&mbar));
+    if (threadIdx.x == 0)
+    {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_s));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        constexpr std::uint32_t kBytes = (kDilTh + 4) * kDilBoxW;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_s), "r"(kBytes) : "memory");
+        const std::uint32_t dst = static_cast<std::uint32_t>(__cvta_generic_to_shared(&raw[0][0]));
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+            "l"(reinterpret_cast<unsigned long long>(&code_map)), "r"(mbar_s), "r"(w0 - 16), "r"(h0 - 2),
+            "r"(static_cast<int>(f))
+            : "memory");
+    }
+    // every thread waits for the transaction bytes (phase 0)
+    {
+        std::uint32_t done = 0;
+        while (done == 0)
+        {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(mbar_s)
+                : "memory");
+        }
+    }
+    // separable maximum: horizontal 5 taps on (kDilTh + 4) rows, then vertical 5 taps
+    for (int t = threadIdx.x; t < (kDilTh + 4) * kDilTw; t += 256)
+    {
+        const int r = t / kDilTw, c = t % kDilTw;
+        std::uint8_t m = 0;
+#pragma unroll
+        for (int k = 0; k < 5; ++k)
+        {
+            m |= ((raw[r][c + 14 + k] & 0xf) == PX_OBSTACLE) ? 1 : 0; // column w0 + c - 2 + k
+        }
+        hmax[r][c] = m;
+    }
+    __syncthreads();
+    dilate_finish(d, sp, f, h0, w0, hmax);
+}
+
+// same stencil with the tile staged by plain loads: image widths that are not a multiple of 16 bytes
+// cannot be described by a tensor map (global strides must be)
+__global__ void __launch_bounds__(256) k_seg_dilate(Dev d, SegParams sp)
+{
+    __shared__ std::uint8_t tile[kDilTh + 4][kDilTw + 4 + 4];
+    __shared__ std::uint8_t hmax[kDilTh + 4][kDilTw + 4];
+    const std::uint32_t f = blockIdx.z;
+    const int h0 = blockIdx.y * kDilTh, w0 = blockIdx.x * kDilTw;
+    const std::uint8_t* code = d.code + static_cast<std::size_t>(f) * sp.npx;
+    for (int t = threadIdx.x; t < (kDilTh + 4) * (kDilTw + 4); t += 256)
+    {
+        const int r = t / (kDilTw + 4), c = t % (kDilTw + 4);
+        const int h = h0 + r - 2, w = w0 + c - 2;
+        std::uint8_t v = 0;
+        if (h >= 0 && h < sp.H && w >= 0 && w < sp.W)
+        {
+            v = ((code[h * sp.W + w] & 0xf) == PX_OBSTACLE) ? 1 : 0;
+        }
+        tile[r][c] = v;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < (kDilTh + 4) * kDilTw; t += 256)
+    {
+        const int r = t / kDilTw, c = t % kDilTw;
+        hmax[r][c] = tile[r][c] | tile[r][c + 1] | tile[r][c + 2] | tile[r][c + 3] | tile[r][c + 4];
+    }
+    __syncthreads();
+    dilate_finish(d, sp, f, h0, w0, hmax);
+}
+
+// Tensor map of the pixel-code planes [B][H][W] (uint8) with a (kDilTh + 4) x kDilBoxW box. The driver
+// entry point is looked up at run time (no link-time dependency on libcuda).
+bool make_code_map(Ctx* c)
+{
+    using Encode = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || fn == nullptr ||
+        qres != cudaDriverEntryPointSuccess)
+    {
+        return false;
+    }
+    const SegParams& sp = c->seg;
+    const cuuint64_t dims[3] = {static_cast<cuuint64_t>(sp.W), static_cast<cuuint64_t>(sp.H), static_cast<cuuint64_t>(c->d.B)};
+    const cuuint64_t strides[2] = {static_cast<cuuint64_t>(sp.W), static_cast<cuuint64_t>(sp.W) * sp.H};
+    const cuuint32_t box[3] = {kDilBoxW, kDilTh + 4, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = reinterpret_cast<Encode>(fn)(&c->code_map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, c->d.code, dims, strides, box,
+                                                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
 }
 
 struct QueuePred
@@ -1472,7 +1568,25 @@ void launch_segment(Ctx* c, std::uint32_t nf, bool want_image)
     mark(c, "seg_image");
     k_seg_px<<<dim3((sp.npx + 255) / 256, nf), 256, 0, s>>>(d, sp);
     mark(c, "seg_px");
-    k_seg_dilate<<<dim3((sp.W + kDilTw - 1) / kDilTw, (sp.H + kDilTh - 1) / kDilTh, nf), 256, 0, s>>>(d, sp);
+    const dim3 gdil((sp.W + kDilTw - 1) / kDilTw, (sp.H + kDilTh - 1) / kDilTh, nf);
+    if (sp.W % 16 == 0)
+    {
+        if (!c->have_code_map)
+        {
+            c->have_code_map = make_code_map(c);
+            if (!c->have_code_map)
+            {
+                std::snprintf(c->err, sizeof(c->err), "cuTensorMapEncodeTiled failed for the %d x %d pixel-code planes", sp.H, sp.W);
+                c->launch_failed = true;
+                return;
+            }
+        }
+        k_seg_dilate_tma<<<gdil, 256, 0, s>>>(d, sp, c->code_map);
+    }
+    else
+    {
+        k_seg_dilate<<<gdil, 256, 0, s>>>(d, sp);
+    }
     mark(c, "seg_dilate");
     launch_compact(c, "jcp_queue", nf, d.ptiles, nullptr, static_cast<std::uint32_t>(sp.npx), d.tile_cnt, d.n_queue,
                    QueuePred{d.code, static_cast<std::uint32_t>(sp.npx)},

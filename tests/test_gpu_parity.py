@@ -322,6 +322,25 @@ def test_128_beam_config(port):
         c.close()
 
 
+def test_image_width_not_a_multiple_of_16(port, golden0):
+    """64 x 1000 range image: the dilation tile cannot be described by a TMA tensor map (row stride
+    must be a multiple of 16 bytes) and is staged with plain loads instead; same results as the oracle."""
+    pts, ring = golden0["pts"], golden0["ring"].astype(np.uint16)
+    c = lpl.Context(0, max_points=pts.shape[0], max_frames=1, image_height=64, image_width=1000)
+    cfg = c.segmenter_default_cfg()
+    cfg.image_width = 1000
+    c.segmenter_config(cfg)
+    port.segment_config(default_seg_cfg(image_width=1000))
+    try:
+        exp, img_o = port.segment(pts, ring, want_image=True)
+        got, img_g = c.segment(pts, ring, want_image=True)
+        assert np.array_equal(got, exp)
+        assert np.array_equal(img_g, img_o)
+    finally:
+        port.segment_config(default_seg_cfg())
+        c.close()
+
+
 def test_unorganized_2m_cloud_properties(port):
     """BASELINE.json configs[4] at reduced size against the oracle, and at full size (2 M points)
     through size-independent properties: idempotence and DROR monotonicity in the radius."""
