@@ -230,6 +230,7 @@ def test_packed_upload_equals_per_frame_upload(ctx, golden0, golden100):
 
 
 def test_edge_cases(ctx, port):
+    ctx.cluster_config(**NODE_CLUSTER_CFG)
     empty = np.zeros((0, 4), np.float32)
     assert ctx.ring_partition(empty).shape == (0,)
     assert ctx.dror_filter(empty).shape == (0,)
