@@ -283,6 +283,9 @@ int lpl_debug_segment(lpl_ctx* ctx, uint32_t frame, float* elevation, float* pla
 int lpl_debug_dror(lpl_ctx* ctx, uint32_t frame, uint32_t* n_unresolved);
 /* Intermediates of the last clustering: dims[3] = num_range, num_azimuth, num_elevation. */
 int lpl_debug_cluster(lpl_ctx* ctx, uint32_t frame, int32_t* dims);
+/* Hull / cluster stage counters of the last run: counters[2] = {points that survived the octagon
+ * filter and entered the hull sort, occupied voxels}. */
+int lpl_debug_hulls(lpl_ctx* ctx, uint32_t frame, uint32_t* counters);
 /* cudaStream_t of the context (as void*), for callers that order their own work after ours. */
 void* lpl_stream(lpl_ctx* ctx);
 

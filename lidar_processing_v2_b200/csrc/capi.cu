@@ -1524,5 +1524,18 @@ int lpl_debug_cluster(lpl_ctx* ctx, std::uint32_t f, std::int32_t* dims)
     return LPL_OK;
 }
 
+int lpl_debug_hulls(lpl_ctx* ctx, std::uint32_t f, std::uint32_t* counters)
+{
+    if (ctx == nullptr || counters == nullptr || f >= ctx->c.d.B)
+    {
+        return LPL_ERR_INVALID_ARGUMENT;
+    }
+    Ctx& c = ctx->c;
+    LPL_TRY(cudaStreamSynchronize(c.stream));
+    LPL_TRY(cudaMemcpy(&counters[0], c.d.n_h + f, 4, cudaMemcpyDeviceToHost));
+    LPL_TRY(cudaMemcpy(&counters[1], c.d.n_vox + f, 4, cudaMemcpyDeviceToHost));
+    return LPL_OK;
+}
+
 void* lpl_stream(lpl_ctx* ctx) { return ctx != nullptr ? static_cast<void*>(ctx->c.stream) : nullptr; }
 } // extern "C"

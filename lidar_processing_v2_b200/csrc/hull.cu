@@ -21,10 +21,25 @@
 namespace lpl
 {
 constexpr int kHullThreads = 32;   // one warp per CTA: the hardware balances clusters of very different size
-constexpr int kHullCtasPerFrame = 24;  // single-warp CTAs per frame (about one resident wave for a 154-frame batch);
+#ifndef LPL_HULL_CTAS
+#define LPL_HULL_CTAS 24
+#endif
+#ifndef LPL_HULL_BIG
+#define LPL_HULL_BIG 1024
+#endif
+#ifndef LPL_HULL_LANEDIV
+#define LPL_HULL_LANEDIV 2
+#endif
+#ifndef LPL_HULL_FILTER_ABOVE
+#define LPL_HULL_FILTER_ABOVE 48
+#endif
+#ifndef LPL_HULL_FINAL_MAX
+#define LPL_HULL_FINAL_MAX 256
+#endif
+constexpr int kHullCtasPerFrame = LPL_HULL_CTAS;  // single-warp CTAs per frame (about one resident wave for a 154-frame batch);
                                        // clusters are handed out dynamically, their sizes differ by orders of magnitude
 constexpr std::uint32_t kChainSmem = 512; // survivors swept from shared memory
-constexpr std::uint32_t kFilterAbove = 48;  // clusters above this are thinned by all lanes first
+constexpr std::uint32_t kFilterAbove = LPL_HULL_FILTER_ABOVE;  // clusters above this are thinned by all lanes first
 constexpr std::uint32_t kLaneStack = 16;  // per-lane chain stack entries kept in shared memory
 
 // per-lane stack of (position, x, y): the first kLaneStack entries live in shared memory - a pop
@@ -398,91 +413,95 @@ __device__ __forceinline__ P2 elem_pt(const uint4& e)
 
 // One lane's share of a thinning pass: the lower chain (left to right) and the upper chain (right to
 // left, as the reference walks it) over the contiguous chunk src[a..b). A point that is on neither
-// chain of its chunk cannot be on the cluster's hull. The next block of four elements is in flight
-// while the current one is swept.
+// chain of its chunk cannot be on the cluster's hull.
+// Both chains advance in ONE warp-uniform loop as two independent state machines: per iteration a
+// lane evaluates one orientation predicate per chain and either pops its stack or pushes the
+// current point and moves on. Compared with a loop over points with an inner pop loop this keeps
+// the lanes of a warp converged (a step costs one predicate, not the longest pop run among the
+// lanes) and gives every lane two independent fp64 dependency chains to overlap. The next two
+// elements of each direction are in flight while the current one is worked on.
+// Must be called by all lanes of the warp (lanes with an empty chunk just vote).
 __device__ __forceinline__ void lane_chains(const uint4* __restrict__ src, std::uint32_t a, std::uint32_t b,
                                             const LaneStack& L, const LaneStack& U, std::uint32_t& kl,
                                             std::uint32_t& ku)
 {
     kl = 0;
     ku = 0;
-    if (b <= a)
+    bool act_l = b > a, act_u = b > a;
+    std::uint32_t il = a, iu = b - 1u; // current point of each chain (valid while active)
+    P2 s2l = {0.0, 0.0}, s1l = s2l, s2u = s2l, s1u = s2l;
+    uint4 el = make_uint4(0, 0, 0, 0), el1 = el, el2 = el, eu = el, eu1 = el, eu2 = el;
+    if (act_l)
     {
-        return;
+        el = ldg4(src + a);
+        el1 = ldg4(src + min(a + 1u, b - 1u));
+        el2 = ldg4(src + min(a + 2u, b - 1u));
+        eu = ldg4(src + (b - 1u));
+        eu1 = ldg4(src + max(b - 1u, a + 1u) - 1u);
+        eu2 = ldg4(src + max(b - 1u, a + 2u) - 2u);
     }
-    P2 s2 = {0.0, 0.0}, s1 = {0.0, 0.0};
-    uint4 nx[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
+    while (__any_sync(0xffffffffu, act_l || act_u))
     {
-        nx[u] = ldg4(src + min(a + u, b - 1u));
-    }
-    for (std::uint32_t i0 = a; i0 < b; i0 += 4)
-    {
-        uint4 cu[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
+        if (act_l)
         {
-            cu[u] = nx[u];
-            nx[u] = ldg4(src + min(i0 + 4u + u, b - 1u));
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-        {
-            const std::uint32_t i = i0 + u;
-            if (i < b)
+            const P2 p = elem_pt(el);
+            if (kl >= 2 && not_left(s2l, s1l, p))
             {
-                const P2 p = elem_pt(cu[u]);
-                while (kl >= 2 && not_left(s2, s1, p))
+                --kl;
+                s1l = s2l;
+                if (kl >= 2)
                 {
-                    --kl;
-                    s1 = s2;
-                    if (kl >= 2)
-                    {
-                        s2 = stack_pt(L, kl - 2, src);
-                    }
+                    s2l = stack_pt(L, kl - 2, src);
                 }
-                L.set(kl, i, elem_xy(cu[u]));
+            }
+            else
+            {
+                L.set(kl, il, elem_xy(el));
                 ++kl;
-                s2 = s1;
-                s1 = p;
+                s2l = s1l;
+                s1l = p;
+                ++il;
+                if (il < b)
+                {
+                    el = el1;
+                    el1 = el2;
+                    el2 = ldg4(src + min(il + 2u, b - 1u));
+                }
+                else
+                {
+                    act_l = false;
+                }
             }
         }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-    {
-        nx[u] = ldg4(src + (b - 1u - min(static_cast<std::uint32_t>(u), b - 1u - a)));
-    }
-    for (std::uint32_t done = 0; done < b - a; done += 4)
-    {
-        uint4 cu[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
+        if (act_u)
         {
-            cu[u] = nx[u];
-            nx[u] = ldg4(src + (b - 1u - min(done + 4u + u, b - 1u - a)));
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-        {
-            if (done + u < b - a)
+            const P2 p = elem_pt(eu);
+            if (ku >= 2 && not_left(s2u, s1u, p))
             {
-                const std::uint32_t i = b - 1u - (done + u);
-                const P2 p = elem_pt(cu[u]);
-                while (ku >= 2 && not_left(s2, s1, p))
+                --ku;
+                s1u = s2u;
+                if (ku >= 2)
                 {
-                    --ku;
-                    s1 = s2;
-                    if (ku >= 2)
-                    {
-                        s2 = stack_pt(U, ku - 2, src);
-                    }
+                    s2u = stack_pt(U, ku - 2, src);
                 }
-                U.set(ku, i, elem_xy(cu[u]));
+            }
+            else
+            {
+                U.set(ku, iu, elem_xy(eu));
                 ++ku;
-                s2 = s1;
-                s1 = p;
+                s2u = s1u;
+                s1u = p;
+                if (iu > a)
+                {
+                    --iu;
+                    eu = eu1;
+                    eu1 = eu2;
+                    eu2 = ldg4(src + max(iu, a + 2u) - 2u);
+                }
+                else
+                {
+                    act_u = false;
+                }
             }
         }
     }
@@ -531,7 +550,7 @@ __device__ std::uint32_t hull_filter(const uint4* __restrict__ src, std::uint32_
     // balance the two sequential phases: a lane sweeps m / lanes points now and every lane leaves
     // roughly eight survivors for the next (sequential or thinner) sweep -> lanes ~ sqrt(m / 8)
     std::uint32_t lanes = 2u;
-    while (lanes < 32u && lanes * lanes * 8u < m)
+    while (lanes < 32u && lanes * lanes * LPL_HULL_LANEDIV < m)
     {
         ++lanes;
     }
@@ -594,10 +613,10 @@ __device__ __forceinline__ std::uint32_t monotone_chain(Get P, std::uint32_t m, 
 // hfin[c]: what k_hull_thin leaves for k_hull_final
 constexpr std::uint32_t kFinDone = 0x80000000u;   // hull already written by k_hull_thin
 constexpr std::uint32_t kFinOther = 0x40000000u;  // survivors live in the second sort buffer
-constexpr std::uint32_t kFinalMax = 256;          // survivors swept by one thread (local-memory stack)
+constexpr std::uint32_t kFinalMax = LPL_HULL_FINAL_MAX;          // survivors swept by one thread (local-memory stack)
 
 constexpr std::uint32_t kFinPre = 0x20000000u;    // k_hull_thin_big already thinned the cluster once (into the other buffer)
-constexpr std::uint32_t kBigAbove = 1024;         // clusters above this get a CTA-wide first thinning pass
+constexpr std::uint32_t kBigAbove = LPL_HULL_BIG;         // clusters above this get a CTA-wide first thinning pass
 constexpr int kBigThreads = 256;
 constexpr int kBigCtasPerFrame = 8;
 
@@ -688,20 +707,37 @@ __global__ void __launch_bounds__(kHullThreads) k_hull_thin(Dev d)
         const std::uint32_t seg = cstart[c];
         const std::uint32_t n = cstart[c + 1] - seg;
 #ifdef LPL_HULL_TRACE
-        const long long t_begin = clock64();
+        // diagnostics (build with LPL_NVCC_EXTRA=-DLPL_HULL_TRACE): per cluster, the survivors and the
+        // cycles of every thinning pass and of what follows; printed for clusters above 50k cycles
         struct Trace
         {
-            long long t0;
-            std::uint32_t f, c, n;
-            __device__ ~Trace()
+            long long t0, tp[6];
+            std::uint32_t f, c, n, mp[6], np;
+            __device__ void pass(std::uint32_t m)
             {
-                const long long dt = clock64() - t0;
-                if (dt > 100000 && (threadIdx.x & 31u) == 0)
+                if (np < 6)
                 {
-                    printf("hull_thin frame %u cluster %u n %u cycles %lld\n", f, c, n, dt);
+                    tp[np] = clock64();
+                    mp[np] = m;
+                    ++np;
                 }
             }
-        } trace{t_begin, f, c, n};
+            __device__ ~Trace()
+            {
+                const long long t1 = clock64();
+                if (t1 - t0 > 50000 && (threadIdx.x & 31u) == 0)
+                {
+                    printf("hull_thin f %u c %u n %u total %lld passes %u:", f, c, n, t1 - t0, np);
+                    long long prev = t0;
+                    for (std::uint32_t k = 0; k < np; ++k)
+                    {
+                        printf(" [m %u cyc %lld]", mp[k], tp[k] - prev);
+                        prev = tp[k];
+                    }
+                    printf(" tail %lld\n", t1 - prev);
+                }
+            }
+        } trace{clock64(), {}, f, c, n, {}, 0u};
 #endif
         if (n <= kFilterAbove)
         {
@@ -725,7 +761,7 @@ __global__ void __launch_bounds__(kHullThreads) k_hull_thin(Dev d)
             nxt = sorted + seg;
             in_other = true;
         }
-        bool stalled = (pre & kFinPre) != 0u && m * 4u > n * 3u;
+        bool stalled = false;
         while (m > kFilterAbove && !stalled)
         {
             const std::uint32_t m2 = hull_filter(cur, m, nxt, d.hstL + o + seg, d.hstU + o + seg, s_lane[0], s_lane[1], s_lxy[0], s_lxy[1]);
@@ -735,6 +771,9 @@ __global__ void __launch_bounds__(kHullThreads) k_hull_thin(Dev d)
             in_other = !in_other;
             stalled = m2 * 4u > m * 3u; // convex-position input: thinning does not pay
             m = m2;
+#ifdef LPL_HULL_TRACE
+            trace.pass(m);
+#endif
         }
         if (m <= kFinalMax)
         {

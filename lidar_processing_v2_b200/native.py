@@ -42,7 +42,7 @@ EXPORTS = [
     "lpl_pipeline_download_batch", "lpl_host_alloc", "lpl_host_free",
     "lpl_profile_enable", "lpl_profile_read",
     "lpl_timer_start", "lpl_timer_stop_ms", "lpl_launch_count", "lpl_debug_segment",
-    "lpl_debug_dror", "lpl_debug_cluster", "lpl_stream",
+    "lpl_debug_dror", "lpl_debug_cluster", "lpl_debug_hulls", "lpl_stream",
 ]
 
 
@@ -162,6 +162,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
+    path = path or os.environ.get("LPL_B200_LIBRARY")  # a prebuilt library (experiments: tools/variants.sh)
     so = path or _build.SO_PATH
     if path is None and _build.needs_build():
         _build.build_native()
@@ -215,6 +216,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     L.lpl_debug_segment.argtypes = [vp, u32, vp, vp, vp, vp]
     L.lpl_debug_cluster.argtypes = [vp, u32, vp]
     L.lpl_debug_dror.argtypes = [vp, u32, C.POINTER(u32)]
+    L.lpl_debug_hulls.argtypes = [vp, u32, vp]
     L.lpl_debug_dror.restype = C.c_int
     L.lpl_stream.argtypes = [vp]
     L.lpl_stream.restype = vp
@@ -563,6 +565,11 @@ class Context:
         return dict(n_binned=int(cnt[0]), n_candidates=int(cnt[1]), n_queued=int(cnt[2]), rounds=int(cnt[3]),
                     border_rows=int(cnt[4]), cells=int(cnt[5]) * int(cnt[6]), status=int(cnt[7]),
                     n_unresolved=int(nu.value))
+
+    def debug_hulls(self, f: int = 0) -> dict:
+        v = np.zeros(2, np.uint32)
+        self._chk(self.lib.lpl_debug_hulls(self.h, f, v.ctypes.data))
+        return dict(n_hull_sort=int(v[0]), n_voxels=int(v[1]))
 
     def debug_cluster(self, f: int = 0) -> np.ndarray:
         dims = np.zeros(3, np.int32)
