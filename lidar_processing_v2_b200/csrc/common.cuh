@@ -18,7 +18,7 @@ namespace lpl
 constexpr int kTile = 2048;         // items per compaction / scan tile
 constexpr int kTileThreads = 256;   // threads per tile block (8 items per thread)
 constexpr int kItems = kTile / kTileThreads;
-constexpr int kDrorGrid = 256;      // DROR grids: kDrorGrid x kDrorGrid cells, two levels (1 m over +-128 m, 0.25 m over +-32 m)
+constexpr int kDrorGrid = 256;      // DROR grids: kDrorGrid x kDrorGrid cells, two levels (1 m over +-128 m, 0.125 m over +-16 m)
 constexpr int kDrorLevelCells = kDrorGrid * kDrorGrid;
 constexpr int kDrorCells = 2 * kDrorLevelCells;
 constexpr int kRansacIters = 60;    // segmenter.cpp:324

@@ -142,7 +142,10 @@ __device__ __forceinline__ bool dror_within(const float4& target, const float4& 
     return dist <= r_sqr;
 }
 
-constexpr int kNearHalo = 8; // scan-line neighbours examined on each side
+#ifndef LPL_DROR_HALO
+#define LPL_DROR_HALO 5
+#endif
+constexpr int kNearHalo = LPL_DROR_HALO; // scan-line neighbours examined on each side
 
 // Pass A: LiDAR clouds arrive in firing order, so a point's nearest neighbours are almost always
 // its predecessors / successors on the same ring. Counting those first settles the vast majority
@@ -211,13 +214,20 @@ __global__ void __launch_bounds__(256)
 }
 
 // Two grid levels share one cell index space: level 0 = 1 m cells over +-128 m (cells
-// [0, kDrorLevelCells)), level 1 = 0.25 m cells over the inner +-32 m (cells [kDrorLevelCells,
+// [0, kDrorLevelCells)), level 1 = 0.125 m cells over the inner +-16 m (cells [kDrorLevelCells,
 // 2 * kDrorLevelCells)). A point lives in exactly one level (the fine one iff it lies inside the
 // inner square), a query scans its search box in both. The search radius grows with range
 // (0.1 m below 5 m, 0.02 * range beyond), so near the sensor - where a 1 m cell holds hundreds of
 // points - the fine level cuts the candidates per query several times.
-constexpr float kDrorInner = 32.0f;
-constexpr float kDrorFineScale = 4.0f;
+#ifndef LPL_DROR_INNER
+#define LPL_DROR_INNER 16.0f
+#endif
+constexpr float kDrorInner = LPL_DROR_INNER;
+#ifndef LPL_DROR_FINE
+#define LPL_DROR_FINE 8.0f
+#endif
+constexpr float kDrorFineScale = LPL_DROR_FINE;
+static_assert(2.0f * kDrorInner * kDrorFineScale == static_cast<float>(kDrorGrid), "the fine level spans exactly kDrorGrid cells");
 
 __device__ __forceinline__ int dror_cell_coord(float v)
 {
@@ -387,9 +397,18 @@ __global__ void __launch_bounds__(256) k_dror_grid_scatter(Dev d)
 // short far from the sensor (where most unresolved points live), so a query is served by a group
 // of 8 lanes: four queries per warp in flight, 32 points per step, early exit at min_neighbours.
 constexpr int kDrorQueryWarps = 8;
-constexpr int kDrorGroup = 8;      // lanes per query
-constexpr int kDrorQueryCtas = 48; // per frame; groups stride over the unresolved list
-constexpr int kDrorUnroll = 4;     // points per lane and step
+#ifndef LPL_DROR_GROUP
+#define LPL_DROR_GROUP 8
+#endif
+constexpr int kDrorGroup = LPL_DROR_GROUP; // lanes per query
+#ifndef LPL_DROR_CTAS
+#define LPL_DROR_CTAS 24
+#endif
+constexpr int kDrorQueryCtas = LPL_DROR_CTAS; // per frame; groups stride over the unresolved list
+#ifndef LPL_DROR_UNROLL
+#define LPL_DROR_UNROLL 4
+#endif
+constexpr int kDrorUnroll = LPL_DROR_UNROLL; // points per lane and step
 
 __global__ void __launch_bounds__(kDrorQueryWarps * 32) k_dror_query(Dev d, DrorParams prm)
 {

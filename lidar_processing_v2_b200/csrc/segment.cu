@@ -245,8 +245,14 @@ __device__ __forceinline__ void warp_sort_regs(T (&v)[E])
     }
 }
 
-constexpr int kCellWarps = 8;     // warps per CTA
-constexpr int kCellsPerWarp = 8;  // cells per warp, interleaved across the CTA's warps (most cells are empty)
+#ifndef LPL_CELL_WARPS
+#define LPL_CELL_WARPS 8
+#endif
+constexpr int kCellWarps = LPL_CELL_WARPS; // warps per CTA
+#ifndef LPL_CELL_PER_WARP
+#define LPL_CELL_PER_WARP 8
+#endif
+constexpr int kCellsPerWarp = LPL_CELL_PER_WARP; // cells per warp, interleaved across the CTA's warps (most cells are empty)
 
 // largest i in [1, n/2] with zs[i] - zs[i-1] > 0.5 on the ascending heights zs[0..n), scanned from
 // the top by whole warps (segmenter.cpp:249-259); returns zs[i] or zs[0] when there is no such gap
@@ -1245,7 +1251,10 @@ __device__ __forceinline__ std::uint32_t plane_get(const volatile std::uint32_t*
 }
 
 constexpr int kJcpThreads = 1024;
-constexpr int kJcpAhead = 4; // queue entries whose weights / masks are in flight ahead of the vote
+#ifndef LPL_JCP_AHEAD
+#define LPL_JCP_AHEAD 4
+#endif
+constexpr int kJcpAhead = LPL_JCP_AHEAD; // queue entries whose weights / masks are in flight ahead of the vote
 constexpr int kJcpRunTable = 4096; // runs whose (first queue entry, first pixel) are staged in shared memory
 constexpr std::uint32_t kJcpSpinLimit = 1u << 22;
 
@@ -1418,7 +1427,13 @@ __global__ void __launch_bounds__(1024) k_jcp_resolve(Dev d, SegParams sp)
                 // back-off that grows with the wait (a spinning warp must not take issue slots
                 // from the warp it waits for)
                 std::uint32_t pending = __ballot_sync(0xffffffffu, mi == 3u);
-                std::uint32_t backoff = 32;
+#ifndef LPL_JCP_BACKOFF0
+#define LPL_JCP_BACKOFF0 32
+#endif
+#ifndef LPL_JCP_BACKOFF1
+#define LPL_JCP_BACKOFF1 512
+#endif
+                std::uint32_t backoff = LPL_JCP_BACKOFF0;
                 while (pending != 0u)
                 {
                     if (++spins > kJcpSpinLimit)
@@ -1431,7 +1446,7 @@ __global__ void __launch_bounds__(1024) k_jcp_resolve(Dev d, SegParams sp)
                         break;
                     }
                     __nanosleep(backoff);
-                    backoff = min(backoff * 2u, 512u);
+                    backoff = min(backoff * 2u, static_cast<std::uint32_t>(LPL_JCP_BACKOFF1));
                     if (mi == 3u)
                     {
                         mi = plane_get(plane, ref);
