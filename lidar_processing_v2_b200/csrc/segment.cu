@@ -741,13 +741,19 @@ __global__ void __launch_bounds__(64) k_ransac_plane(Dev d, SegParams sp)
     d.planes[f * kRansacIters + it] = plane;
 }
 
+#ifndef LPL_RANSAC_PER
+#define LPL_RANSAC_PER 8
+#endif
+constexpr int kRansacPer = LPL_RANSAC_PER; // candidates per thread: one plane fetch serves all of them
+
 __global__ void __launch_bounds__(256) k_ransac_count(Dev d, SegParams sp)
 {
     __shared__ float4 pl[kRansacIters];
     __shared__ std::uint32_t cnt[kRansacIters];
     const std::uint32_t f = blockIdx.y;
     const std::uint32_t nc = d.n_cpts[f]; // = n_cand, the dense copy is unordered
-    if (nc < 2 || blockIdx.x * 256u >= nc)
+    const std::uint32_t base = blockIdx.x * (256u * kRansacPer);
+    if (nc < 2 || base >= nc)
     {
         return;
     }
@@ -757,12 +763,14 @@ __global__ void __launch_bounds__(256) k_ransac_count(Dev d, SegParams sp)
         cnt[threadIdx.x] = 0;
     }
     __syncthreads();
-    const std::uint32_t k = blockIdx.x * 256u + threadIdx.x;
-    const bool live = k < nc;
-    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (live)
+    float4 p[kRansacPer];
+    bool live[kRansacPer];
+#pragma unroll
+    for (int j = 0; j < kRansacPer; ++j)
     {
-        p = d.cpts[static_cast<std::size_t>(f) * d.cap + k];
+        const std::uint32_t k = base + j * 256u + threadIdx.x;
+        live[j] = k < nc;
+        p[j] = live[j] ? d.cpts[static_cast<std::size_t>(f) * d.cap + k] : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     // lane j keeps the counts of planes j and j + 32 of its warp in registers
     std::uint32_t c0 = 0, c1 = 0;
@@ -775,8 +783,13 @@ __global__ void __launch_bounds__(256) k_ransac_count(Dev d, SegParams sp)
         {
             continue; // skipped draw (uniform branch)
         }
-        const float od = fabsf((q.x * p.x) + (q.y * p.y) + (q.z * p.z) - q.w);
-        const std::uint32_t hits = __popc(__ballot_sync(0xffffffffu, live && od < sp.thr));
+        std::uint32_t hits = 0;
+#pragma unroll
+        for (int j = 0; j < kRansacPer; ++j)
+        {
+            const float od = fabsf((q.x * p[j].x) + (q.y * p[j].y) + (q.z * p[j].z) - q.w);
+            hits += __popc(__ballot_sync(0xffffffffu, live[j] && od < sp.thr));
+        }
         if (static_cast<int>(lane) == (it & 31))
         {
             if (it < 32)
@@ -1130,6 +1143,10 @@ __device__ __forceinline__ void jcp_slot(const Dev& d, const SegParams& sp, std:
     }
 }
 
+#ifndef LPL_JCP_PRE_UNROLL
+#define LPL_JCP_PRE_UNROLL 4
+#endif
+constexpr int kJcpPreUnroll = LPL_JCP_PRE_UNROLL; // neighbour slots of a queued pixel evaluated per loop trip
 __global__ void __launch_bounds__(128) k_jcp_pre(Dev d, SegParams sp)
 {
     __shared__ float s_w[128][25]; // raw weights of the CTA's 128 queued pixels (+1 pad: no bank conflicts)
@@ -1151,7 +1168,7 @@ __global__ void __launch_bounds__(128) k_jcp_pre(Dev d, SegParams sp)
     unsigned long long mk = 0;
     std::uint32_t brow = 0; // 1 + stale_ref row once allocated
     float sum = 0.f;
-#pragma unroll 1
+#pragma unroll kJcpPreUnroll
     for (int i = 0; i < 24; ++i)
     {
         const int hh = h + c_off_h[i], ww = w + c_off_w[i];
@@ -1577,7 +1594,7 @@ void launch_segment(Ctx* c, std::uint32_t nf, bool want_image)
     mark(c, "ransac_draw");
     k_ransac_plane<<<dim3(kRansacIters, nf), 64, 0, s>>>(d, sp);
     mark(c, "ransac_plane");
-    k_ransac_count<<<gpts, 256, 0, s>>>(d, sp);
+    k_ransac_count<<<dim3((d.cap + 256 * kRansacPer - 1) / (256 * kRansacPer), nf), 256, 0, s>>>(d, sp);
     mark(c, "ransac_count");
     k_seg_image<<<gpts, 256, 0, s>>>(d, sp);
     mark(c, "seg_image");
