@@ -130,7 +130,7 @@ def algorithmic_bytes(name: str, s: dict) -> float:
         "ransac_draw": 1024 * F + 8 * CELLS, "ransac_plane": 120 * 64 * F, "ransac_count": 16 * C,
         "seg_image": (16 + 4 + 4 + 1) * N + 1 * NB + 8 * NB, "seg_px": 8 * PX + 17 * PX + 17 * PX,
         "seg_dilate": 2 * PX, "jcp_queue": 2 * PX + 4 * Q,
-        "jcp_pre": Q * (25 * 17 + 24 * 4 + 8), "jcp_resolve": PX * 1 + Q * (8 + 4 + 96) + PX * 17 + V * 2,
+        "jcp_pre": Q * (25 * 17 + 24 * 4 + 8), "jcp_resolve": PX * 1 + Q * (8 + 4 + 96) + Q * 1 + 8 * Q // 3,
         "take_obstacles": 1 * N + 16 * M + 20 * M,
         "clu_sph": 16 * M + 16 * M, "clu_insert": 16 * M + 4 * M, "clu_edges": 8 * M + 52 * M // 3,
         "clu_union_sm": 52 * M // 3 + 8 * M // 3, "clu_union": 8 * M, "clu_flatten": 8 * M,

@@ -11,6 +11,8 @@ import lidar_processing_v2_b200 as lpl  # noqa: E402
 def main():
     want = sys.argv[1:]
     frames, workload, _ = bench.load_frames(None)
+    if os.environ.get("LPL_FRAMES"):
+        frames = frames[: int(os.environ["LPL_FRAMES"])]
     nf = len(frames)
     ctx = lpl.Context(0, max_points=max(f.shape[0] for f in frames), max_frames=nf)
     ctx.cluster_config(range_m=0.4, az_deg=1.0, el_deg=3.0, min_size=3)
