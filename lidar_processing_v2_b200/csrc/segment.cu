@@ -29,7 +29,6 @@
 // slots from the previously popped pixel (hazard H2); k_jcp_pre reproduces that by
 // locating the most recent earlier queued pixel for which the slot was inside the image.
 #include <cfloat>
-#include <cstdlib>
 
 #include "common.cuh"
 
@@ -1267,7 +1266,10 @@ __device__ __forceinline__ std::uint32_t plane_get(const volatile std::uint32_t*
     return (plane[p >> 4] >> ((p & 15u) * 2u)) & 3u;
 }
 
-constexpr int kJcpThreads = 1024;
+#ifndef LPL_JCP_THREADS
+#define LPL_JCP_THREADS 1024 // measured per 154-frame batch: 256 -> 1.6 ms, 512 -> 0.85 ms, 1024 -> 0.53 ms
+#endif
+constexpr int kJcpThreads = LPL_JCP_THREADS;
 #ifndef LPL_JCP_AHEAD
 #define LPL_JCP_AHEAD 4
 #endif
@@ -1631,8 +1633,7 @@ void launch_segment(Ctx* c, std::uint32_t nf, bool want_image)
     // state plane (32 KB for 64 x 2048, 64 KB for 128-beam images) on top of ~39 KB of static shared
     // memory: above the 48 KB default, opt in (up to 227 KB per CTA on sm_100a)
     cudaFuncSetAttribute(k_jcp_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(plane_bytes));
-    static const int jcp_threads = std::getenv("LPL_JCP_THREADS") ? std::atoi(std::getenv("LPL_JCP_THREADS")) : kJcpThreads;
-    k_jcp_resolve<<<nf, jcp_threads, plane_bytes, s>>>(d, sp);
+    k_jcp_resolve<<<nf, kJcpThreads, plane_bytes, s>>>(d, sp);
     mark(c, "jcp_resolve");
     k_seg_labels_out<<<dim3((sp.npx + 255) / 256, nf), 256, 0, s>>>(d, sp, want_image ? 1 : 0);
     mark(c, "seg_labels_out");
