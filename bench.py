@@ -359,7 +359,8 @@ def run_ours(args, rank, local_rank, world):
         by = algorithmic_bytes(name, stats)
         kernels.append({"kernel": name, "launches": cnt, "ms_per_launch": per_launch_ms,
                         "share": ms / (ms_total if ms_total > 0 else 1.0),
-                        "alg_bytes_per_launch": by, "gbs": by / (per_launch_ms * 1e6) if per_launch_ms > 0 else 0.0})
+                        "alg_bytes_per_launch": by, "gbs": by / (per_launch_ms * 1e6) if per_launch_ms > 0 else 0.0,
+                        "frac_of_hbm_peak": (by / (per_launch_ms * 1e6) / peak) if per_launch_ms > 0 else 0.0})
     # kernels launched twice per step under one name (two-pass compactions) are merged above
     kernels.sort(key=lambda k: -k["share"])
     top = kernels[0]
@@ -403,7 +404,7 @@ def run_ours(args, rank, local_rank, world):
                 "pipelining": f"{args.e2e_parts} part-batches per step over {args.e2e_ctx} contexts (streams) in rotation, pinned host memory"},
         "gpu_launches": int(launches),
         "roofline": roofline,
-        "kernels": [{k: (round(v, 6) if isinstance(v, float) else v) for k, v in kk.items()} for kk in kernels[:12]],
+        "kernels": [{k: (round(v, 6) if isinstance(v, float) else v) for k, v in kk.items()} for kk in kernels[:20]],
         "latency_ms": lat,
         "wall_s_timed_region": t_wall,
     }

@@ -342,6 +342,35 @@ def test_image_width_not_a_multiple_of_16(port, golden0):
         c.close()
 
 
+def test_dense_polar_cells(ctx, port):
+    """Thousands of points in single polar cells near the sensor: exercises the oversized-cell path of
+    the RECM statistics (> 256 heights per cell) and the RANSAC rank selection when one cell holds more
+    candidates than its shared-memory staging (> 1024), against the oracle."""
+    rng = np.random.default_rng(11)
+    parts = []
+    for az_deg, r0, n in ((10.3, 3.0, 3000), (10.6, 5.0, 1500), (200.2, 2.5, 2200), (95.0, 7.0, 400)):
+        a = np.deg2rad(az_deg + rng.uniform(0, 0.35, n))
+        r = r0 + rng.uniform(0, 0.9, n)
+        z = -1.73 + rng.normal(0, 0.03, n)
+        z[rng.random(n) < 0.05] += rng.uniform(0.6, 1.5)     # a few obstacle returns inside the cells
+        parts.append(np.stack([r * np.cos(a), r * np.sin(a), z], -1))
+    scan, ring_scan = F.synth_scan(4003)
+    xyz = np.concatenate(parts + [scan[::7, :3]])
+    pts = np.zeros((xyz.shape[0], 4), np.float32)
+    pts[:, :3] = np.round(xyz * 1000) / 1000
+    order = rng.permutation(pts.shape[0])
+    pts = np.ascontiguousarray(pts[order])
+    ring = rng.integers(0, 64, pts.shape[0]).astype(np.uint16)
+    exp, img_o, dbg_o = port.segment(pts, ring, want_image=True, want_debug=True)
+    got, img_g = ctx.segment(pts, ring, want_image=True)
+    dbg_g = ctx.debug_segment(0)
+    assert dbg_g["n_candidates"] == dbg_o["n_candidates"] and dbg_o["n_candidates"] > 5000
+    assert np.array_equal(dbg_o["plane"].view(np.uint32), dbg_g["plane"].view(np.uint32))
+    assert np.array_equal(dbg_o["elevation"].view(np.uint32), dbg_g["elevation"].view(np.uint32))
+    assert np.array_equal(got, exp) and np.array_equal(img_g, img_o)
+    assert np.array_equal(ctx.segment(pts, None), port.segment(pts, None))
+
+
 def test_unorganized_2m_cloud_properties(port):
     """BASELINE.json configs[4] at reduced size against the oracle, and at full size (2 M points)
     through size-independent properties: idempotence and DROR monotonicity in the radius."""
