@@ -184,7 +184,8 @@ __global__ void __launch_bounds__(256) k_clu_insert(Dev d, ClusterParams cp)
         atomicAdd(&d.hcount[ho + slot], static_cast<std::uint32_t>(__popc(peers)));
     }
     // the voxels this CTA created are appended to the frame's voxel list with one atomic per CTA
-    // (a per-voxel atomic on the frame's counter serialises ~17k updates on one address)
+    // (a per-voxel atomic on the frame's counter serialises ~17k updates on one address; measured:
+    // per voxel 0.55 ms, per warp 0.53 ms, per CTA 0.19 ms for the 154-frame batch)
     const std::uint32_t cm = __ballot_sync(0xffffffffu, created);
     std::uint32_t woff = 0;
     if (lane_id() == 0 && cm != 0)

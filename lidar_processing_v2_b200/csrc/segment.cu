@@ -823,50 +823,55 @@ __global__ void __launch_bounds__(256) k_ransac_count(Dev d, SegParams sp)
 // wins. Equal depth^2 means equal radial bin, hence cell order = azimuth-slice order: the key
 // (depth^2 bits, slice, point index) under atomicMin reproduces the winner without any sorted list.
 // ------------------------------------------------------------------------------------------
+// best plane of a frame (segmenter.cpp:434-453): the first iteration with the strictly largest inlier
+// count, flipped so that c >= 0. One warp per frame, once - not once per CTA of k_seg_image.
+__global__ void __launch_bounds__(32) k_ransac_best(Dev d)
+{
+    const std::uint32_t f = blockIdx.x;
+    const std::uint32_t lane = lane_id();
+    unsigned long long key = 0; // (count << 8) | (255 - iteration): maximum = largest count, earliest iteration
+    if (d.n_cand[f] >= 2)
+    {
+        for (std::uint32_t it = lane; it < static_cast<std::uint32_t>(kRansacIters); it += 32)
+        {
+            const std::uint32_t c = d.inliers[f * kRansacIters + it];
+            const unsigned long long k = (static_cast<unsigned long long>(c) << 8) | (255u - it);
+            key = (c != 0 && k > key) ? k : key;
+        }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1)
+    {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, s);
+        key = other > key ? other : key;
+    }
+    if (lane == 0)
+    {
+        float4 pl = make_float4(0.f, 0.f, 1.f, 0.f);
+        const std::uint32_t best = static_cast<std::uint32_t>(key >> 8);
+        if (best != 0)
+        {
+            pl = d.planes[f * kRansacIters + (255u - static_cast<std::uint32_t>(key & 0xffu))];
+            if (pl.z < 0.f)
+            {
+                pl = make_float4(-pl.x, -pl.y, -pl.z, -pl.w);
+            }
+        }
+        d.best_plane[f] = pl;
+        d.best_cnt[f] = best; // 0 = no plane was accepted
+    }
+}
+
 __global__ void __launch_bounds__(256) k_seg_image(Dev d, SegParams sp)
 {
-    __shared__ float4 s_plane;
-    __shared__ int s_have;
     const std::uint32_t f = blockIdx.y;
     const std::uint32_t n = d.n_in[f];
     if (blockIdx.x * 256u >= n)
     {
         return;
     }
-    if (threadIdx.x == 0)
-    {
-        std::uint32_t best = 0;
-        int sel = -1;
-        if (d.n_cand[f] >= 2)
-        {
-            for (int it = 0; it < kRansacIters; ++it)
-            {
-                const std::uint32_t c = d.inliers[f * kRansacIters + it];
-                if (c > best) // strictly greater: first maximum wins
-                {
-                    best = c;
-                    sel = it;
-                }
-            }
-        }
-        float4 pl = make_float4(0.f, 0.f, 1.f, 0.f);
-        if (sel >= 0)
-        {
-            pl = d.planes[f * kRansacIters + sel];
-            if (pl.z < 0.f)
-            {
-                pl = make_float4(-pl.x, -pl.y, -pl.z, -pl.w);
-            }
-        }
-        s_plane = pl;
-        s_have = sel >= 0;
-        if (blockIdx.x == 0)
-        {
-            d.best_plane[f] = pl;
-            d.best_cnt[f] = best;
-        }
-    }
-    __syncthreads();
+    const float4 s_plane = d.best_plane[f];
+    const bool s_have = d.best_cnt[f] != 0;
     const std::uint32_t i = blockIdx.x * 256u + threadIdx.x;
     if (i >= n)
     {
@@ -1598,6 +1603,8 @@ void launch_segment(Ctx* c, std::uint32_t nf, bool want_image)
     mark(c, "ransac_plane");
     k_ransac_count<<<dim3((d.cap + 256 * kRansacPer - 1) / (256 * kRansacPer), nf), 256, 0, s>>>(d, sp);
     mark(c, "ransac_count");
+    k_ransac_best<<<nf, 32, 0, s>>>(d);
+    mark(c, "ransac_best");
     k_seg_image<<<gpts, 256, 0, s>>>(d, sp);
     mark(c, "seg_image");
     k_seg_px<<<dim3((sp.npx + 255) / 256, nf), 256, 0, s>>>(d, sp);

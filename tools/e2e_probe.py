@@ -23,6 +23,7 @@ def run(frames, n_ctx, want, steps=8, warm=2):
         buf.array[o:o + f.shape[0]] = f
         views.append(buf.array[o:o + f.shape[0]])
         o += f.shape[0]
+    counts_arr = np.array([f.shape[0] for f in frames], np.uint32)
     t_collect = t_upload = t_run = 0.0
 
     def step():
@@ -31,7 +32,7 @@ def run(frames, n_ctx, want, steps=8, warm=2):
         a = time.perf_counter()
         pipe.collect(i)
         b = time.perf_counter()
-        n = pipe.ctx[i].upload(views)
+        n = pipe.ctx[i].upload_packed(buf.array, counts_arr)
         c = time.perf_counter()
         pipe.ctx[i].run(n, pipe.stages)
         d = time.perf_counter()
