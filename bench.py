@@ -117,6 +117,7 @@ def algorithmic_bytes(name: str, s: dict) -> float:
     HV hull vertices, PX pixels, CELLS polar cells, Q queued pixels, C RANSAC candidates,
     U DROR-unresolved points, F frames)."""
     N, V, NB, M, K, HV = s["N"], s["V"], s["NB"], s["M"], s["K"], s["HV"]
+    NH = s.get("NH", M)  # points that survive the octagon filter and enter the hull sort
     PX, CELLS, Q, C, U, F = s["PX"], s["CELLS"], s["Q"], s["C"], s["U"], s["F"]
     t = {
         "ring_count": 16 * N, "ring_write": 16 * N + 2 * N,
@@ -128,7 +129,7 @@ def algorithmic_bytes(name: str, s: dict) -> float:
         "seg_cell": 8 * NB + 8 * CELLS, "seg_elev": 12 * CELLS,
         "seg_label": (16 + 4) * N + 4 * NB + 1 * N + 16 * C,
         "ransac_draw": 1024 * F + 8 * CELLS, "ransac_plane": 120 * 64 * F, "ransac_count": 16 * C,
-        "seg_image": (16 + 4 + 4 + 1) * N + 1 * NB + 8 * NB, "seg_px": 8 * PX + 17 * PX + 17 * PX,
+        "seg_image": (16 + 4 + 4 + 1) * N + 1 * NB + 8 * NB, "seg_px": 8 * PX + 17 * PX,  # + 17 B for every pixel that has a winner (not counted)
         "seg_dilate": 2 * PX, "jcp_queue": 2 * PX + 4 * Q,
         "jcp_pre": Q * (25 * 17 + 24 * 4 + 8), "jcp_resolve": PX * 1 + Q * (8 + 4 + 96) + Q * 1 + 8 * Q // 3,
         "take_obstacles": 1 * N + 16 * M + 20 * M,
@@ -137,9 +138,9 @@ def algorithmic_bytes(name: str, s: dict) -> float:
         "clu_rank": 8 * M, "clu_labels": 8 * M + 16 * M,
         # hulls: the stage as a whole must read every obstacle point's (x, y) and label once and write
         # the vertices (8M + 4M + 4 Hv + 12 K); the chain kernels are charged with that
-        "hull_octagon": 64 * K, "hull_keep": (16 + 4) * M + 16 * M, "hull_seg_scan": 8 * K,
-        "hull_tilesort": 32 * M, "hull_merge": 32 * M,
-        "hull_thin_big": 12 * M + 4 * HV + 12 * K, "hull_thin": 12 * M + 4 * HV + 12 * K,
+        "hull_octagon": 64 * K, "hull_keep": (16 + 4) * M + 16 * NH, "hull_seg_scan": 8 * K,
+        "hull_tilesort": 32 * NH, "hull_merge": 32 * NH,
+        "hull_thin_big": 16 * NH + 4 * HV + 12 * K, "hull_thin": 16 * NH + 4 * HV + 12 * K,
         "hull_final": 16 * HV + 12 * K, "hull_off_scan": 8 * K, "hull_gather": 4 * HV + 16 * HV + 12 * HV,
         "obb_frames": 8 * HV + 80 * K,
         "label_count": 4 * M,
@@ -148,7 +149,7 @@ def algorithmic_bytes(name: str, s: dict) -> float:
 
 
 def batch_stats(ctx, nf, seg_dbg=True) -> dict:
-    s = dict(N=0, V=0, NB=0, M=0, K=0, HV=0, Q=0, C=0, U=0, F=nf, PX=nf * ctx.H * ctx.W, CELLS=0)
+    s = dict(N=0, V=0, NB=0, M=0, K=0, HV=0, Q=0, C=0, U=0, NH=0, F=nf, PX=nf * ctx.H * ctx.W, CELLS=0)
     for f in range(nf):
         r = ctx.counts(f)
         s["N"] += r.n
@@ -163,6 +164,7 @@ def batch_stats(ctx, nf, seg_dbg=True) -> dict:
             s["Q"] += d["n_queued"]
             s["U"] += d["n_unresolved"]
             s["CELLS"] += d["cells"]
+            s["NH"] += ctx.debug_hulls(f)["n_hull_sort"]
     return s
 
 
