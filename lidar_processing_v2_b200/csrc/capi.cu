@@ -341,7 +341,7 @@ __global__ void k_label_count(Dev d, std::uint32_t K)
             d.clabel[o + i] = -1;
         }
     }
-    accumulate_cluster_stats(d.ext + o * 8, d.zmin_u + o, d.zmax_u + o, l, x, y, z, i);
+    accumulate_cluster_stats(d.ext + o * 8, d.zmin_u + o, d.zmax_u + o, l, x, y, z, i, true);
 }
 
 __global__ void k_ext_init(Dev d, std::uint32_t K)

@@ -555,7 +555,9 @@ __global__ void __launch_bounds__(256) k_clu_labels(Dev d)
         y = p.y;
         z = p.z;
     }
-    accumulate_cluster_stats(d.ext + o * 8, d.zmin_u + o, d.zmax_u + o, l, x, y, z, i);
+    // every kExtWarpStride-th warp of the frame contributes to the extreme points
+    const bool with_extremes = (((blockIdx.x * 256u + threadIdx.x) >> 5) % kExtWarpStride) == 0u;
+    accumulate_cluster_stats(d.ext + o * 8, d.zmin_u + o, d.zmax_u + o, l, x, y, z, i, with_extremes);
 }
 
 // hand-over from segmentation: stable compaction of OBSTACLE points in cloud order

@@ -128,6 +128,10 @@ __global__ void __launch_bounds__(128) k_hull_octagon(Dev d)
     {
         float2 v[8];
         bool ok = d.ccount[o + c] >= kOctaMinPoints;
+        // the extreme points come from a subset of the cluster's points (cluster.cu): a cluster none of
+        // whose points was sampled still has its slots in the initial state and skips the filter
+        const unsigned long long first = ok ? d.ext[(o + c) * 8] : ~0ULL;
+        ok = ok && first != ~0ULL;
         if (ok)
         {
 #pragma unroll
