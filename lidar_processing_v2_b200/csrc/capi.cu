@@ -130,8 +130,8 @@ void carve(Dev& d, Carver& cv, int npx, int ncell_cap, std::uint32_t** mt_raw)
     cv.take(d.n_hull, B);
     cv.take(d.zmin_u, B * cap);
     cv.take(d.zmax_u, B * cap);
-    cv.take(d.ext, B * cap * 8);
-    cv.take(d.octa, B * cap * 8);
+    cv.take(d.ext, B * cap * kExtDirs);
+    cv.take(d.octa, B * cap * kExtDirs);
     cv.take(d.hseg_cnt, B * cap);
     cv.take(d.n_h, B);
     cv.take(d.hull_next, B);
@@ -341,7 +341,7 @@ __global__ void k_label_count(Dev d, std::uint32_t K)
             d.clabel[o + i] = -1;
         }
     }
-    accumulate_cluster_stats(d.ext + o * 8, d.zmin_u + o, d.zmax_u + o, l, x, y, z, i, true);
+    accumulate_cluster_stats(d.ext + o * kExtDirs, d.zmin_u + o, d.zmax_u + o, l, x, y, z, i, true);
 }
 
 __global__ void k_ext_init(Dev d, std::uint32_t K)
@@ -349,7 +349,7 @@ __global__ void k_ext_init(Dev d, std::uint32_t K)
     const std::uint32_t c = blockIdx.x * 256u + threadIdx.x;
     if (c < K)
     {
-        ext_init(d.ext + static_cast<std::size_t>(c) * 8);
+        ext_init(d.ext + static_cast<std::size_t>(c) * kExtDirs);
     }
 }
 } // namespace

@@ -99,7 +99,7 @@ __device__ __forceinline__ std::uint32_t sort_passes(std::uint32_t n)
 }
 
 // ------------------------------------------------------------------------------------------
-// octagon filter (Akl-Toussaint): a point strictly inside the polygon spanned by up to eight
+// polygon filter (Akl-Toussaint): a point strictly inside the polygon spanned by up to kExtDirs
 // extreme points of its cluster cannot be a hull vertex, so it never enters the sort. The
 // extreme points are actual points of the cluster (found while labelling, cluster.cu), the test
 // is the reference's own fp64 orientation predicate, and a polygon that is not convex in
@@ -126,32 +126,31 @@ __global__ void __launch_bounds__(128) k_hull_octagon(Dev d)
     const std::size_t o = static_cast<std::size_t>(f) * d.cap;
     for (std::uint32_t c = blockIdx.x * 128u + threadIdx.x; c < K; c += gridDim.x * 128u)
     {
-        float2 v[8];
+        float2 v[kExtDirs];
         bool ok = d.ccount[o + c] >= kOctaMinPoints;
-        // the extreme points come from a subset of the cluster's points (cluster.cu): a cluster none of
-        // whose points was sampled still has its slots in the initial state and skips the filter
-        const unsigned long long first = ok ? d.ext[(o + c) * 8] : ~0ULL;
-        ok = ok && first != ~0ULL;
+        // a slot still in its initial state (possible when only a subset of the points contributes,
+        // cluster.cu) leaves the cluster without a filter polygon
+        ok = ok && d.ext[(o + c) * kExtDirs] != 0ULL;
         if (ok)
         {
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
+            for (int k = 0; k < kExtDirs; ++k)
             {
-                const std::uint32_t idx = static_cast<std::uint32_t>(d.ext[(o + c) * 8 + k]);
+                const std::uint32_t idx = static_cast<std::uint32_t>(d.ext[(o + c) * kExtDirs + k]);
                 const float4 p = d.pts_o[o + idx];
                 v[k] = make_float2(p.x + 0.0f, p.y + 0.0f);
             }
             // convex and counter-clockwise (repeated vertices allowed), and not degenerate
             bool any_turn = false;
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
+            for (int k = 0; k < kExtDirs; ++k)
             {
                 const P2 a = {static_cast<double>(v[k].x), static_cast<double>(v[k].y)};
-                const P2 b = {static_cast<double>(v[(k + 1) & 7].x), static_cast<double>(v[(k + 1) & 7].y)};
+                const P2 b = {static_cast<double>(v[(k + 1) % kExtDirs].x), static_cast<double>(v[(k + 1) % kExtDirs].y)};
 #pragma unroll
-                for (int j = 2; j < 8; ++j)
+                for (int j = 2; j < kExtDirs; ++j)
                 {
-                    const P2 q = {static_cast<double>(v[(k + j) & 7].x), static_cast<double>(v[(k + j) & 7].y)};
+                    const P2 q = {static_cast<double>(v[(k + j) % kExtDirs].x), static_cast<double>(v[(k + j) % kExtDirs].y)};
                     const double cr = (b.x - a.x) * (q.y - a.y) - (b.y - a.y) * (q.x - a.x);
                     ok = ok && !(cr < 0.0); // every other vertex on or left of every edge
                     any_turn = any_turn || cr > 0.0;
@@ -160,9 +159,9 @@ __global__ void __launch_bounds__(128) k_hull_octagon(Dev d)
             ok = ok && any_turn;
         }
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
+        for (int k = 0; k < kExtDirs; ++k)
         {
-            d.octa[(o + c) * 8 + k] = ok ? v[k] : make_float2(__int_as_float(0x7fc00000), 0.f);
+            d.octa[(o + c) * kExtDirs + k] = ok ? v[k] : make_float2(__int_as_float(0x7fc00000), 0.f);
         }
         d.hseg_cnt[o + c] = 0;
     }
@@ -179,20 +178,20 @@ struct HullKeepPred
         {
             return false;
         }
-        const float2* v = d.octa + (o + l) * 8;
+        const float2* v = d.octa + (o + l) * kExtDirs;
         const float2 v0 = v[0];
         if (v0.x != v0.x)
         {
-            return true; // no usable octagon for this cluster
+            return true; // no usable polygon for this cluster
         }
         const float4 pt = d.pts_o[o + i];
         const P2 q = {static_cast<double>(pt.x), static_cast<double>(pt.y)};
         P2 a = {static_cast<double>(v0.x), static_cast<double>(v0.y)};
         bool inside = true;
 #pragma unroll
-        for (int k = 1; k <= 8; ++k)
+        for (int k = 1; k <= kExtDirs; ++k)
         {
-            const float2 vk = v[k & 7];
+            const float2 vk = v[k % kExtDirs];
             const P2 b = {static_cast<double>(vk.x), static_cast<double>(vk.y)};
             const bool degenerate = (a.x == b.x) && (a.y == b.y);
             inside = inside && (degenerate || !not_left(a, b, q)); // strictly left of every proper edge
