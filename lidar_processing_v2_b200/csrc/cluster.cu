@@ -625,8 +625,9 @@ void launch_cluster(Ctx* c, std::uint32_t nf)
     mark(c, "clu_union");
     k_clu_flatten<<<gbig, 256, 0, s>>>(d);
     mark(c, "clu_flatten");
-    launch_compact(c, "clu_rank", nf, d.tiles, d.n_o, 0u, d.tile_cnt, d.n_clusters,
-                   ClusterRepPred{d, c->clu.min_cluster_size}, ClusterRepEmit{d});
+    // d.lab (RECM labels of the segmenter) is free by now: it holds the recorded verdicts
+    launch_compact_recorded(c, "clu_rank", nf, d.tiles, d.n_o, d.tile_cnt, d.n_clusters, d.lab,
+                            ClusterRepPred{d, c->clu.min_cluster_size}, ClusterRepEmit{d});
     k_clu_clean<<<gbig, 256, 0, s>>>(d);
     mark(c, "clu_clean");
     k_clu_labels<<<g, 256, 0, s>>>(d);

@@ -596,6 +596,46 @@ inline void mark(Ctx* c, const char* name)
 }
 
 
+// a predicate that is expensive to evaluate (fp64 polygon tests, dependent gathers) is evaluated once:
+// the counting pass stores its verdicts as bytes, the scatter pass reads them back
+template <class Pred>
+struct RecordingPred
+{
+    Pred pred;
+    std::uint8_t* flags;
+    std::uint32_t cap;
+    __device__ bool operator()(std::uint32_t f, std::uint32_t i) const
+    {
+        const bool r = pred(f, i);
+        flags[static_cast<std::size_t>(f) * cap + i] = r ? 1 : 0;
+        return r;
+    }
+};
+
+struct RecordedPred
+{
+    const std::uint8_t* flags;
+    std::uint32_t cap;
+    __device__ bool operator()(std::uint32_t f, std::uint32_t i) const
+    {
+        return flags[static_cast<std::size_t>(f) * cap + i] != 0;
+    }
+};
+
+template <class Pred, class Emit>
+inline void launch_compact_recorded(Ctx* c, const char* name, std::uint32_t B, std::uint32_t tiles_per_frame,
+                                    const std::uint32_t* n_arr, std::uint32_t* tile_cnt, std::uint32_t* n_out,
+                                    std::uint8_t* flags, Pred pred, Emit emit)
+{
+    const dim3 grid(tiles_per_frame, B);
+    k_compact_count<<<grid, kTileThreads, 0, c->stream>>>(RecordingPred<Pred>{pred, flags, c->d.cap}, n_arr, 0u, tile_cnt,
+                                                          tiles_per_frame);
+    mark(c, name);
+    k_compact_scatter<<<grid, kTileThreads, 0, c->stream>>>(RecordedPred{flags, c->d.cap}, emit, n_arr, 0u, tile_cnt,
+                                                            tiles_per_frame, n_out);
+    mark(c, name);
+}
+
 template <class Pred, class Emit>
 inline void launch_compact(Ctx* c, const char* name, std::uint32_t B, std::uint32_t tiles_per_frame,
                            const std::uint32_t* n_arr, std::uint32_t n_const,

@@ -935,7 +935,8 @@ void launch_hulls(Ctx* c, std::uint32_t nf)
     cudaStream_t s = c->stream;
     k_hull_octagon<<<dim3(4, nf), 128, 0, s>>>(d);
     mark(c, "hull_octagon");
-    launch_compact(c, "hull_keep", nf, d.tiles, d.n_o, 0u, d.tile_cnt, d.n_h, HullKeepPred{d}, HullKeepEmit{d});
+    // d.lab (RECM labels of the segmenter) is free by now: it holds the recorded verdicts
+    launch_compact_recorded(c, "hull_keep", nf, d.tiles, d.n_o, d.tile_cnt, d.n_h, d.lab, HullKeepPred{d}, HullKeepEmit{d});
     k_excl_scan<<<nf, 1024, 0, s>>>(d.hseg_cnt, d.cap, d.cstart, d.cap + 1, d.cap, d.n_clusters, nullptr);
     mark(c, "hull_seg_scan");
     k_hull_tilesort<<<dim3(d.tiles, nf), kTileThreads, 0, s>>>(d);
