@@ -67,7 +67,7 @@ struct RingWrapPred
 };
 
 __global__ void __launch_bounds__(kTileThreads)
-    k_ring_write(RingWrapPred pred, const std::uint32_t* __restrict__ n_arr,
+    k_ring_write(RecordedPred pred, const std::uint32_t* __restrict__ n_arr,
                  const std::uint32_t* __restrict__ tile_cnt, std::uint32_t tiles_per_frame,
                  std::uint16_t* __restrict__ ring, std::uint32_t cap)
 {
@@ -113,10 +113,13 @@ void launch_ring(Ctx* c, std::uint32_t nf)
 {
     Dev& d = c->d;
     const dim3 grid(d.tiles, nf);
-    RingWrapPred pred{d.pts_in, d.cap};
-    k_compact_count<<<grid, kTileThreads, 0, c->stream>>>(pred, d.n_in, 0u, d.tile_cnt, d.tiles);
+    // the wrap flags are evaluated once (first pass) and recorded in d.lab, which the segmenter only
+    // writes later in the chain
+    const RingWrapPred pred{d.pts_in, d.cap};
+    k_compact_count<<<grid, kTileThreads, 0, c->stream>>>(RecordingPred<RingWrapPred>{pred, d.lab, d.cap}, d.n_in, 0u,
+                                                          d.tile_cnt, d.tiles);
     mark(c, "ring_count");
-    k_ring_write<<<grid, kTileThreads, 0, c->stream>>>(pred, d.n_in, d.tile_cnt, d.tiles, d.ring,
+    k_ring_write<<<grid, kTileThreads, 0, c->stream>>>(RecordedPred{d.lab, d.cap}, d.n_in, d.tile_cnt, d.tiles, d.ring,
                                                       d.cap);
     mark(c, "ring_write");
 }
