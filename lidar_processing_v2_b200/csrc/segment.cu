@@ -292,6 +292,24 @@ __device__ __forceinline__ float zval(std::uint32_t key)
     return __uint_as_float((key & 0x80000000u) ? (key & 0x7fffffffu) : ~key);
 }
 
+// shuffle-only bitonic network over the first KMAX lanes (ascending), one key per lane
+template <int KMAX>
+__device__ __forceinline__ std::uint32_t sort_lanes(std::uint32_t zk, std::uint32_t lane)
+{
+#pragma unroll
+    for (std::uint32_t k = 2; k <= static_cast<std::uint32_t>(KMAX); k <<= 1)
+    {
+#pragma unroll
+        for (std::uint32_t j = k >> 1; j > 0; j >>= 1)
+        {
+            const std::uint32_t other = __shfl_xor_sync(0xffffffffu, zk, j);
+            const bool take_min = ((lane & j) == 0) == ((lane & k) == 0);
+            zk = take_min ? min(zk, other) : max(zk, other);
+        }
+    }
+    return zk;
+}
+
 // E values per lane sorted in registers, then the gap scan over shared memory
 template <int E>
 __device__ __forceinline__ float cell_zmin_regs(const uint2* zo, std::uint32_t n, float* zb)
@@ -327,16 +345,23 @@ __device__ __forceinline__ void seg_cell_one(const Dev& d, const SegParams& sp, 
         // the common case: one height per lane, shuffle-only bitonic network
         const std::uint32_t lane = lane_id();
         std::uint32_t zk = lane < n ? zkey(zo[lane].y) : 0xffffffffu;
-#pragma unroll
-        for (std::uint32_t k = 2; k <= 32; k <<= 1)
+        // most cells far from the sensor hold a handful of points: the network only runs up to the
+        // next power of two of n (lanes beyond hold the +inf padding and sort among themselves)
+        if (n <= 4)
         {
-#pragma unroll
-            for (std::uint32_t j = k >> 1; j > 0; j >>= 1)
-            {
-                const std::uint32_t other = __shfl_xor_sync(0xffffffffu, zk, j);
-                const bool take_min = ((lane & j) == 0) == ((lane & k) == 0);
-                zk = take_min ? min(zk, other) : max(zk, other);
-            }
+            zk = sort_lanes<4>(zk, lane);
+        }
+        else if (n <= 8)
+        {
+            zk = sort_lanes<8>(zk, lane);
+        }
+        else if (n <= 16)
+        {
+            zk = sort_lanes<16>(zk, lane);
+        }
+        else
+        {
+            zk = sort_lanes<32>(zk, lane);
         }
         const float z = zval(zk);
         const float prev = __shfl_up_sync(0xffffffffu, z, 1);
