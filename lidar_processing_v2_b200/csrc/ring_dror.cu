@@ -444,8 +444,17 @@ __global__ void __launch_bounds__(kDrorQueryWarps * 32) k_dror_query(Dev d, Dror
                 rb = start[bx.base + cy * kDrorGrid + bx.x1 + 1];
             }
             const int rows = min(kDrorGroup, bx.y1 - cy0 + 1);
-            for (int r = 0; r < rows && cnt < prm.min_neighbours; ++r)
+            // rows are visited outwards from the query's own row: a query that does have its
+            // min_neighbours finds them in the nearest cells and leaves early
+            const float yq = (level == 1) ? p.y * kDrorFineScale : p.y;
+            const int own = min(max(dror_cell_coord(yq) - cy0, 0), rows - 1);
+            for (int t = 0; t < 2 * rows && cnt < prm.min_neighbours; ++t)
             {
+                const int r = own + (((t & 1) != 0) ? (t + 1) / 2 : -(t / 2));
+                if (r < 0 || r >= rows)
+                {
+                    continue;
+                }
                 const std::uint32_t a = __shfl_sync(gmask, ra, r, kDrorGroup);
                 const std::uint32_t b = __shfl_sync(gmask, rb, r, kDrorGroup);
                 // kDrorUnroll independent loads per lane and step: a dense row (hundreds of points in
