@@ -351,6 +351,10 @@ __global__ void __launch_bounds__(256) k_dror_grid_count(Dev d)
             cell = c;
         }
     }
+    if (i < n)
+    {
+        d.cell[static_cast<std::size_t>(f) * d.cap + i] = cell; // recorded for k_dror_grid_scatter (the segmenter's plane is free here)
+    }
     const std::uint32_t peers = __match_any_sync(0xffffffffu, cell);
     if (cell >= 0 && static_cast<int>(lane_id()) == __ffs(peers) - 1)
     {
@@ -371,11 +375,10 @@ __global__ void __launch_bounds__(256) k_dror_grid_scatter(Dev d)
     float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
     if (i < n)
     {
-        p = d.pts_in[static_cast<std::size_t>(f) * d.cap + i];
-        const int c = dror_point_cell(p);
-        if (dror_marked(d.grid_mask + static_cast<std::size_t>(f) * (kDrorCells / 32), c))
+        cell = d.cell[static_cast<std::size_t>(f) * d.cap + i]; // recorded by k_dror_grid_count (-1: cell not marked)
+        if (cell >= 0)
         {
-            cell = c;
+            p = d.pts_in[static_cast<std::size_t>(f) * d.cap + i];
         }
     }
     const std::uint32_t peers = __match_any_sync(0xffffffffu, cell);
