@@ -43,16 +43,46 @@ UNIT = "frames/s"
 # --------------------------------------------------------------------------------------------
 # workload
 # --------------------------------------------------------------------------------------------
-def load_frames(limit=None):
+WORKLOADS = ("kitti154", "synth64", "synth128", "cloud2m")
+
+
+def load_frames(limit=None, workload=None):
+    """-> (frames, workload name, description, options). `workload` None = kitti154 when the pack is there.
+    options: image_height (Context + segmenter configuration), stages (None = the node's whole chain),
+    cpu (False: the reference CPU arm cannot run it)."""
     from tools import frames as F
 
-    if F.have_pack():
+    opts = {"image_height": 64, "stages": None, "cpu": True, "rings": None}
+    if workload in (None, "kitti154") and F.have_pack():
         fr = F.load_pack(limit=limit)
-        return fr, "kitti154", "KITTI HDL-64E frames of the reference repository (data/*.pcd, repacked)"
+        return fr, "kitti154", "KITTI HDL-64E frames of the reference repository (data/*.pcd, repacked)", opts
+    if workload == "synth128":
+        # BASELINE.json configs[2]: 128 beams x 2048 columns, 400 boxes + 300 poles, 1 % dropout, seed 3000 + frame
+        n = limit or 64
+        base = [F.synth_scan(3000 + i, beams=128, n_boxes=400, n_poles=300, n_walls=0, dropout=0.01)
+                for i in range(min(n, 16))]
+        opts["image_height"] = 128
+        # the reference's ring partition (dataloader.cpp:68-137) is written for 64 rings: a 128-beam cloud
+        # arrives with its ring field (pcl::PointXYZIR input of Segmenter::segment) and skips that stage
+        opts["stages"] = "ring_field"
+        opts["rings"] = [base[i % len(base)][1] for i in range(n)]
+        return ([base[i % len(base)][0] for i in range(n)], "synth128",
+                f"synthetic 128-beam x 2048-column sweeps with a ring field (seeded ray-cast scenes, {len(base)} "
+                f"distinct scenes cycled); chain: DROR + segmentation + clustering + hulls", opts)
+    if workload == "cloud2m":
+        # BASELINE.json configs[4]: 2 M-point unorganised clouds (no ring structure: ring-less segmentation)
+        n = limit or 5
+        opts["stages"] = "ringless"
+        opts["cpu"] = False  # the reference Clusterer's 200k-voxel table overflows on this cloud (SURVEY H9)
+        return ([F.synth_unorganized(5000 + i) for i in range(n)], "cloud2m",
+                "synthetic unorganised 2,000,000-point clouds (ground disc + 5,000 blobs + 5 % background), "
+                "ring-less chain: DROR + segmentation + clustering + hulls", opts)
+    # BASELINE.json configs[3]: synthetic HDL-64E sweeps, 6 % dropout, 60 boxes + 40 poles + 2 walls, seed 4000 + frame
     n = limit or 154
-    base = [F.synth_scan(4000 + i)[0] for i in range(min(n, 16))]
-    fr = [base[i % len(base)] for i in range(n)]
-    return fr, "synth64", "synthetic HDL-64E sweeps (seeded ray-cast scenes; data/kitti154.npz absent)"
+    base = [F.synth_scan(4000 + i)[0] for i in range(min(n, 32))]
+    why = "" if workload == "synth64" else "; data/kitti154.npz absent"
+    return ([base[i % len(base)] for i in range(n)], "synth64",
+            f"synthetic HDL-64E sweeps (seeded ray-cast scenes, {len(base)} distinct scenes cycled{why})", opts)
 
 
 # --------------------------------------------------------------------------------------------
@@ -175,19 +205,24 @@ def batch_stats(ctx, nf, seg_dbg=True) -> dict:
 _W = {}
 
 
-def _cpu_worker_init(limit):
-    from oracle.oracle import PortOracle, RefOracle, have_ref
+def _cpu_worker_init(limit, workload=None):
+    from oracle.oracle import PortOracle, RefOracle, default_seg_cfg, have_ref
 
-    _W["frames"] = load_frames(limit)[0]
+    _W["frames"], _, _, opts = load_frames(limit, workload)
+    _W["rings"] = opts["rings"]
     _W["ref"] = RefOracle() if have_ref() else None
     _W["port"] = PortOracle()
+    if opts["image_height"] != 64:
+        for o in (_W["ref"], _W["port"]):
+            if o is not None:
+                o.segment_config(default_seg_cfg(image_height=opts["image_height"]))
 
 
 def _cpu_worker_frame(i):
     """Whole hot path on frame i, chained as in DESIGN.md (ring -> DROR -> segment VALID ->
     cluster OBSTACLE -> hulls), through the reference's own code where it is a library function."""
     ref, port, pts = _W["ref"], _W["port"], _W["frames"][i]
-    ring = port.ring_partition(pts)
+    ring = port.ring_partition(pts) if _W.get("rings") is None else _W["rings"][i]
     noise = ref.dror(pts, mode="as_is") if ref is not None else port.dror(pts)
     keep = noise == 0
     pv = np.ascontiguousarray(pts[keep])
@@ -203,7 +238,7 @@ class CpuReference:
     """The reference's CPU path on `procs` worker processes (the library is single-threaded and
     its objects are not thread-safe, so one process per core with its own instances)."""
 
-    def __init__(self, procs: int, limit: int):
+    def __init__(self, procs: int, limit: int, workload=None):
         import multiprocessing as mp
 
         from oracle.oracle import build, have_ref
@@ -211,7 +246,7 @@ class CpuReference:
         build()
         self.kind = "reference" if have_ref() else "port"
         self.procs = procs
-        self.pool = mp.get_context("spawn").Pool(procs, initializer=_cpu_worker_init, initargs=(limit,))
+        self.pool = mp.get_context("spawn").Pool(procs, initializer=_cpu_worker_init, initargs=(limit, workload))
         self.pool.map(_cpu_worker_frame, list(range(min(limit, procs))))  # warm-up: imports, page faults
 
     def run(self, idx) -> float:
@@ -234,10 +269,14 @@ def host_cores() -> int:
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return 0
-    frames, workload, data_desc = load_frames()
+    frames, workload, data_desc, opts = load_frames(args.frames, args.workload)
+    if not opts["cpu"]:
+        print(json.dumps({"impl": "reference", "unavailable":
+                          f"workload {workload}: the reference Clusterer's fixed 200k-voxel table overflows"}), flush=True)
+        return 0
     cores = host_cores()
     per_step = min(len(frames), 2 * cores)
-    cpu = CpuReference(cores, per_step)
+    cpu = CpuReference(cores, per_step, args.workload)
     for _ in range(min(args.warmup, 1)):
         cpu.run(range(per_step))
     t = 0.0
@@ -286,19 +325,34 @@ def run_ours(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
-    frames, workload, data_desc = load_frames(args.frames)
+    frames, workload, data_desc, opts = load_frames(args.frames, args.workload)
     # every rank runs the same number of frames; rotate the sequence so ranks do not share inputs
     rot = (rank * 19) % len(frames)
     frames = frames[rot:] + frames[:rot]
+    rings = opts["rings"]
+    if rings is not None:
+        rings = rings[rot:] + rings[:rot]
     nf = len(frames)
     max_pts = max(f.shape[0] for f in frames)
     stages = lpl.STAGE_ALL
-    ctx = lpl.Context(local_rank, max_points=max_pts, max_frames=nf)
-    ctx.cluster_config(range_m=0.4, az_deg=1.0, el_deg=3.0, min_size=3)  # processor.param.yaml:31-35
+    if opts["stages"] in ("ringless", "ring_field"):
+        stages = lpl.STAGE_ALL & ~lpl.STAGE_RING
+    img_h = opts["image_height"]
+
+    def make_ctx(max_frames):
+        c = lpl.Context(local_rank, max_points=max_pts, max_frames=max_frames, image_height=img_h)
+        if img_h != 64:
+            cfg = c.segmenter_default_cfg()
+            cfg.image_height = img_h
+            c.segmenter_config(cfg)
+        c.cluster_config(range_m=0.4, az_deg=1.0, el_deg=3.0, min_size=3)  # processor.param.yaml:31-35
+        return c
+
+    ctx = make_ctx(nf)
     total_pts = sum(f.shape[0] for f in frames)
 
     # ---- device-resident throughput ("value")
-    ctx.upload(frames)
+    ctx.upload(frames, rings=rings)
     ctx.sync(nf)
     for _ in range(args.warmup):
         ctx.run(nf, stages)
@@ -329,10 +383,10 @@ def run_ours(args, rank, local_rank, world):
     stats = batch_stats(ctx, nf)
 
     # ---- end to end through the C ABI with host buffers ("e2e")
-    e2e = run_e2e(lpl, ctx, frames, local_rank, args, barrier, stages)
+    e2e = run_e2e(lpl, ctx, frames, local_rank, args, barrier, stages, img_h, rings)
 
     # ---- p50 latency of single-frame batches (H2D -> all results on the host)
-    lat = run_latency(lpl, frames, local_rank, stages, max_pts) if rank == 0 else None
+    lat = run_latency(lpl, frames, local_rank, stages, max_pts, make_ctx, rings) if rank == 0 else None
 
     t_ms = torch.tensor([ms_total, e2e["seconds"] * 1e3], dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -380,10 +434,10 @@ def run_ours(args, rank, local_rank, world):
 
     # ---- CPU baseline on this box's host cores (bounded sample)
     cpu_baseline = None
-    if world == 1 and not args.no_cpu:
+    if world == 1 and not args.no_cpu and opts["cpu"]:
         cores = host_cores()
         ns = min(nf, 4 * cores)
-        cpu = CpuReference(cores, ns)
+        cpu = CpuReference(cores, ns, args.workload)
         secs = cpu.run(range(ns))
         cpu.close()
         cpu_baseline = {"value": ns / secs, "unit": UNIT, "cores": cores, "kind": cpu.kind,
@@ -398,7 +452,7 @@ def run_ours(args, rank, local_rank, world):
         "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": data_desc,
         "config": {"workload": workload, "frames_per_step_per_gpu": nf, "points_per_step_per_gpu": total_pts,
-                   "stages": "ring+dror+segment+cluster+hulls", "l2": "inputs (300 MB/step) larger than L2, no flush",
+                   "stages": ("ring+" if stages & lpl.STAGE_RING else "") + "dror+segment+cluster+hulls", "l2": f"inputs ({16 * total_pts / 1e6:.0f} MB/step) larger than the 126 MB L2, no flush",
                    "parallelism": f"frame-sharded x{world}, no data-path collective"},
         "points_per_s": world * total_pts * args.steps / (ms_max * 1e-3),
         "clocks": clocks,
@@ -418,7 +472,7 @@ def run_ours(args, rank, local_rank, world):
     return 0
 
 
-def run_e2e(lpl, ctx0, frames, device, args, barrier, stages):
+def run_e2e(lpl, ctx0, frames, device, args, barrier, stages, img_h=64, rings=None):
     """Upload (pinned host -> device) + run + batch download through the package's FramePipeline
     (args.e2e_ctx contexts / CUDA streams rotating over args.e2e_parts part-batches of the step)."""
     from lidar_processing_v2_b200.stream import FramePipeline
@@ -427,9 +481,18 @@ def run_e2e(lpl, ctx0, frames, device, args, barrier, stages):
     max_pts = max(f.shape[0] for f in frames)
     n_parts, n_ctx = args.e2e_parts, args.e2e_ctx
     per = (nf + n_parts - 1) // n_parts
-    pipe = FramePipeline(device, max_pts, per, stages=stages, n_ctx=n_ctx)
+    pipe = FramePipeline(device, max_pts, per, stages=stages, n_ctx=n_ctx, image_height=img_h)
     parts = [frames[a:a + per] for a in range(0, nf, per)]
-    pinned, views, packed = [], [], []
+    pinned, views, packed, ring_views = [], [], [], []
+    for a in range(0, nf, per) if rings is not None else ():
+        rbuf = lpl.PinnedBuffer((sum(r.shape[0] for r in rings[a:a + per]),), np.uint16)
+        rv, o = [], 0
+        for r in rings[a:a + per]:
+            rbuf.array[o:o + r.shape[0]] = r
+            rv.append(rbuf.array[o:o + r.shape[0]])
+            o += r.shape[0]
+        pinned.append(rbuf)
+        ring_views.append(rv)
     for part in parts:
         buf = lpl.PinnedBuffer((sum(f.shape[0] for f in part), 4), np.float32)
         v, o = [], 0
@@ -445,6 +508,9 @@ def run_e2e(lpl, ctx0, frames, device, args, barrier, stages):
     def run_steps(k):
         for _ in range(k):
             for i in range(len(views)):
+                if rings is not None:
+                    pipe.submit(views[i], rings=ring_views[i])  # per-frame copies: points + ring field
+                    continue
                 pipe.submit(views[i], packed=packed[i])  # returns (and thereby downloads) the batch this slot held before
         pipe.drain()
 
@@ -460,22 +526,23 @@ def run_e2e(lpl, ctx0, frames, device, args, barrier, stages):
     return {"seconds": secs, "h2d": h2d, "d2h": d2h}
 
 
-def run_latency(lpl, frames, device, stages, max_pts):
-    ctx = lpl.Context(device, max_points=max_pts, max_frames=1)
-    ctx.cluster_config(range_m=0.4, az_deg=1.0, el_deg=3.0, min_size=3)
+def run_latency(lpl, frames, device, stages, max_pts, make_ctx, rings=None):
+    ctx = make_ctx(1)
     stride = ((max_pts + 2047) // 2048) * 2048
     out = lpl.BatchBuffers(1, stride)
     pin = lpl.PinnedBuffer((max_pts, 4), np.float32)
     ts = []
-    for k, f in enumerate(frames[:64] + frames[:8]):
+    sel = list(range(min(64, len(frames)))) + list(range(min(8, len(frames))))
+    for k in sel:
+        f = frames[k]
         v = pin.array[: f.shape[0]]
         v[:] = f
         t0 = time.perf_counter()
-        ctx.upload([v])
+        ctx.upload([v], rings=None if rings is None else [rings[k]])
         ctx.run(1, stages)
         ctx.download_batch(1, out)
         ts.append((time.perf_counter() - t0) * 1e3)
-    ts = np.array(ts[8:])
+    ts = np.array(ts[min(8, len(ts) // 2):])
     ctx.close()
     return {"p50": float(np.percentile(ts, 50)), "p95": float(np.percentile(ts, 95)), "frames": int(ts.size),
             "what": "batch of 1: pinned H2D + all stages + labels/clusters/hulls D2H"}
@@ -487,6 +554,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None, choices=WORKLOADS,
+                    help="default: kitti154 (BASELINE.json configs[1]); the synthetic shapes are configs[2..4]")
     ap.add_argument("--frames", type=int, default=None, help="frames per batch (default: the whole sequence)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--e2e-parts", type=int, default=1, help="part-batches one step is split into on the e2e path")

@@ -584,6 +584,16 @@ struct Ctx
 // Called after every kernel launch: counts it and, when profiling, drops an event behind it so
 // the time between consecutive marks is that kernel's duration on the context stream
 // (preceding memsets are attributed to the kernel that follows them).
+// CTAs per frame of the kernels that stride a fixed number of CTAs over a frame's work list. The
+// defaults are tuned on 154-frame batches; a small batch (single-frame latency mode, a few very large
+// clouds) gets proportionally more CTAs per frame so that the whole GPU stays occupied.
+inline unsigned per_frame_ctas(unsigned tuned, unsigned nf, unsigned cap)
+{
+    const unsigned total = tuned * 154u;
+    const unsigned scaled = (total + nf - 1u) / (nf == 0u ? 1u : nf);
+    return scaled < tuned ? tuned : (scaled > cap ? cap : scaled);
+}
+
 inline void mark(Ctx* c, const char* name)
 {
     c->launches += 1;

@@ -954,11 +954,11 @@ void launch_hulls(Ctx* c, std::uint32_t nf)
     }
     constexpr std::size_t big_smem = static_cast<std::size_t>(2) * kBigThreads * kLaneStack * (sizeof(float2) + sizeof(std::uint32_t));
     cudaFuncSetAttribute(k_hull_thin_big, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(big_smem));
-    k_hull_thin_big<<<dim3(kBigCtasPerFrame, nf), kBigThreads, big_smem, s>>>(d);
+    k_hull_thin_big<<<dim3(per_frame_ctas(kBigCtasPerFrame, nf, 64), nf), kBigThreads, big_smem, s>>>(d);
     mark(c, "hull_thin_big");
-    k_hull_thin<<<dim3(kHullCtasPerFrame, nf), kHullThreads, 0, s>>>(d);
+    k_hull_thin<<<dim3(per_frame_ctas(kHullCtasPerFrame, nf, 1024), nf), kHullThreads, 0, s>>>(d);
     mark(c, "hull_thin");
-    k_hull_final<<<dim3(16, nf), 64, 0, s>>>(d);
+    k_hull_final<<<dim3(per_frame_ctas(16, nf, 256), nf), 64, 0, s>>>(d);
     mark(c, "hull_final");
     k_excl_scan<<<nf, 1024, 0, s>>>(d.hcnt, d.cap, d.hull_off, d.cap + 1, d.cap, d.n_clusters, d.n_hull);
     mark(c, "hull_off_scan");

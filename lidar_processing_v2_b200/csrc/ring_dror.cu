@@ -563,7 +563,7 @@ void launch_dror(Ctx* c, std::uint32_t nf)
     k_dror_near<<<grid, 256, 0, c->stream>>>(d, c->dror);
     mark(c, "dror_near");
     cudaMemsetAsync(d.grid_mask, 0, sizeof(std::uint32_t) * (kDrorCells / 32) * nf, c->stream);
-    k_dror_mark<<<dim3(8, nf), 256, 0, c->stream>>>(d, c->dror);
+    k_dror_mark<<<dim3(per_frame_ctas(8, nf, 256), nf), 256, 0, c->stream>>>(d, c->dror);
     mark(c, "dror_mark");
     k_dror_grid_count<<<grid, 256, 0, c->stream>>>(d);
     mark(c, "dror_grid_count");
@@ -572,7 +572,7 @@ void launch_dror(Ctx* c, std::uint32_t nf)
     mark(c, "dror_grid_scan");
     k_dror_grid_scatter<<<grid, 256, 0, c->stream>>>(d);
     mark(c, "dror_grid_scatter");
-    k_dror_query<<<dim3(kDrorQueryCtas, nf), kDrorQueryWarps * 32, 0, c->stream>>>(d, c->dror);
+    k_dror_query<<<dim3(per_frame_ctas(kDrorQueryCtas, nf, 2048), nf), kDrorQueryWarps * 32, 0, c->stream>>>(d, c->dror);
     mark(c, "dror_query");
 }
 

@@ -51,14 +51,20 @@ class FramePipeline:
 
     def __init__(self, device: int, max_points: int, batch: int, stages: int = _n.STAGE_ALL,
                  cluster_cfg: dict | None = None, want=("labels_u8", "obstacle_index", "cluster_labels",
-                                                         "hull_offsets", "hull_xy", "zminmax"), n_ctx: int = 2):
+                                                         "hull_offsets", "hull_xy", "zminmax"), n_ctx: int = 2,
+                 image_height: int = 64):
         if n_ctx < 1:
             raise ValueError("n_ctx must be >= 1")
         self.stages = stages
         self.batch = batch
         self.n_ctx = n_ctx
-        self.ctx = [_n.Context(device, max_points=max_points, max_frames=batch) for _ in range(n_ctx)]
+        self.ctx = [_n.Context(device, max_points=max_points, max_frames=batch, image_height=image_height)
+                    for _ in range(n_ctx)]
         for c in self.ctx:
+            if image_height != 64:
+                cfg = c.segmenter_default_cfg()
+                cfg.image_height = image_height
+                c.segmenter_config(cfg)
             c.cluster_config(**(cluster_cfg or dict(range_m=0.4, az_deg=1.0, el_deg=3.0, min_size=3)))
         stride = ((max_points + 2047) // 2048) * 2048
         self.out = [_n.BatchBuffers(batch, stride, want=want) for _ in range(n_ctx)]
@@ -67,7 +73,7 @@ class FramePipeline:
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
-    def submit(self, frames, packed=None):
+    def submit(self, frames, packed=None, rings=None):
         """Enqueue a batch (list of (n, 4) float32 arrays, ideally views of pinned memory). When the
         frames lie back to back in one buffer, pass it as packed=(array, counts): the batch then crosses
         PCIe as one transfer. Returns (counts[5][nf], BatchBuffers) of the batch that previously used
@@ -77,7 +83,9 @@ class FramePipeline:
         if packed is not None:
             nf = self.ctx[i].upload_packed(packed[0], packed[1])
         else:
-            nf = self.ctx[i].upload(frames)
+            nf = self.ctx[i].upload(frames, rings=rings)
+            if rings is not None:
+                self.h2d_bytes += sum(int(r.shape[0]) for r in rings if r is not None) * 2
         self.ctx[i].run(nf, self.stages)
         self.inflight[i] = nf
         self.h2d_bytes += (int(np.sum(packed[1])) if packed is not None else sum(int(f.shape[0]) for f in frames)) * 16
