@@ -1296,6 +1296,10 @@ __device__ __forceinline__ std::uint32_t plane_get(const volatile std::uint32_t*
     return (plane[p >> 4] >> ((p & 15u) * 2u)) & 3u;
 }
 
+#ifndef LPL_JCP_ROWS
+#define LPL_JCP_ROWS 1 // 1: row-synchronous sweep (k_jcp_rows, below); 0: data-flow sweep with polling (k_jcp_resolve)
+#endif
+#if !LPL_JCP_ROWS
 #ifndef LPL_JCP_THREADS
 #define LPL_JCP_THREADS 1024 // measured per 154-frame batch: 256 -> 1.6 ms, 512 -> 0.85 ms, 1024 -> 0.53 ms
 #endif
@@ -1546,6 +1550,341 @@ __global__ void __launch_bounds__(1024) k_jcp_resolve(Dev d, SegParams sp)
     }
 }
 
+#endif // !LPL_JCP_ROWS
+
+// ------------------------------------------------------------------------------------------
+// Row-synchronous JCP sweep, one THREAD per queued pixel (LPL_JCP_ROWS = 1).
+// Within an image row a queued pixel depends only on its two left neighbours (kernel slots 10 / 11):
+// every other dynamic slot - in-image slots of the two rows above and the inherited (stale) slots of
+// border pixels, which always refer to rows above - is final once the rows are swept top to bottom.
+//   vote:  a thread reads the rows-above slots of its pixel from the state plane and evaluates the vote
+//     for every outcome of the two left neighbours at once. The ground sum depends only on [left-2 is
+//     ground], [left-1 is ground] and the obstacle sum on [.. is obstacle]: four variants each, every
+//     one the reference's exact 24-term chain in slot order (x + 0.0f == x), folded into a 9-bit table
+//     (state of left-2, state of left-1) -> outcome.
+//   chain: the raster recurrence along the row is a composition of finite maps. With the state
+//     X = (outcome of the previous-but-one entry, outcome of the previous entry) in {0,1,2}^2, entry q
+//     is a map X -> X' (9 x 4 bits); a warp-level inclusive scan composes the maps of 32 consecutive
+//     entries, the warps' totals are chained through shared memory, and every thread reads its outcome
+//     off its prefix map. No sequential walk, no polling.
+// Two CTA barriers per 512 queue entries of a row; the queue records of the next chunk are loaded into
+// registers before the current chunk is voted on.
+// ------------------------------------------------------------------------------------------
+#if LPL_JCP_ROWS
+#ifndef LPL_JCP_ROWS_THREADS
+#define LPL_JCP_ROWS_THREADS 256 // measured per 154-frame batch: 128 -> 0.43 ms, 256 -> 0.33, 384 -> 0.37, 512 -> 0.42
+#endif
+constexpr int kJcpRowsThreads = LPL_JCP_ROWS_THREADS;
+#ifndef LPL_JCP_ROWS_MINB
+#define LPL_JCP_ROWS_MINB 2 // CTAs per SM: a 154-frame batch must not spill into a second wave on 148 SMs
+#endif
+constexpr unsigned long long kJcpIdentityMap = 0x876543210ULL;
+
+// (later o earlier)[x] = later[earlier[x]] on maps of the nine states, 4 bits per state
+__device__ __forceinline__ unsigned long long jcp_compose(unsigned long long later, unsigned long long earlier)
+{
+    const std::uint32_t lo = static_cast<std::uint32_t>(later), hi = static_cast<std::uint32_t>(later >> 32);
+    unsigned long long r = 0;
+#pragma unroll
+    for (int x = 0; x < 9; ++x)
+    {
+        const std::uint32_t idx = static_cast<std::uint32_t>(earlier >> (4 * x)) & 15u;
+        const std::uint32_t v = idx < 8u ? ((lo >> (4u * idx)) & 15u) : (hi & 15u);
+        r |= static_cast<unsigned long long>(v) << (4 * x);
+    }
+    return r;
+}
+
+__device__ __forceinline__ std::uint32_t jcp_apply(unsigned long long map, std::uint32_t x)
+{
+    return static_cast<std::uint32_t>(map >> (4u * x)) & 15u;
+}
+
+struct JcpEntry
+{
+    unsigned long long m;
+    std::uint32_t p, p_before; // pixel, pixel of the previous queue entry (0xffffffff: none in this row)
+    float4 w[6];
+    bool valid;
+};
+
+__global__ void __launch_bounds__(kJcpRowsThreads, LPL_JCP_ROWS_MINB) k_jcp_rows(Dev d, SegParams sp)
+{
+    extern __shared__ std::uint32_t plane[]; // npx / 16 words, then row_start[H + 1]
+    __shared__ unsigned long long s_tot[2][kJcpRowsThreads / 32];
+    __shared__ std::uint32_t s_carry[2];
+    const std::uint32_t f = blockIdx.x;
+    const std::size_t po = static_cast<std::size_t>(f) * sp.npx;
+    std::uint8_t* code = d.code + po;
+    const std::uint32_t nwords = (sp.npx + 15) / 16;
+    const std::uint32_t W = static_cast<std::uint32_t>(sp.W), H = static_cast<std::uint32_t>(sp.H);
+    std::uint32_t* row_start = plane + nwords;
+    for (std::uint32_t wi = threadIdx.x; wi < nwords; wi += blockDim.x)
+    {
+        std::uint32_t v = 0;
+        const uint4 raw = *reinterpret_cast<const uint4*>(code + static_cast<std::size_t>(wi) * 16);
+        const std::uint32_t r[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int b = 0; b < 16; ++b)
+        {
+            const std::uint32_t c = (r[b >> 2] >> ((b & 3) * 8)) & 0xfu;
+            v |= (c & 3u) << (2 * b); // EMPTY 0, GROUND 1, OBSTACLE 2, QUEUED 3
+        }
+        plane[wi] = v;
+    }
+    const std::uint32_t nq = min(d.n_queue[f], d.qcap);
+    const std::uint32_t* queue = d.queue + static_cast<std::size_t>(f) * d.qcap;
+    const unsigned long long* mkv = d.mk + static_cast<std::size_t>(f) * d.qcap;
+    const float* wn = d.wn + static_cast<std::size_t>(f) * 24 * d.qcap;
+    const std::uint32_t* sref = d.stale_ref + static_cast<std::size_t>(f) * d.nborder_cap * 12;
+    // first queue entry of every row (the queue is in raster order)
+    for (std::uint32_t h = threadIdx.x; h <= H; h += blockDim.x)
+    {
+        const std::uint32_t target = h * W;
+        std::uint32_t lo = 0, hi = nq;
+        while (lo < hi)
+        {
+            const std::uint32_t mid = (lo + hi) >> 1;
+            if (queue[mid] < target)
+            {
+                lo = mid + 1;
+            }
+            else
+            {
+                hi = mid;
+            }
+        }
+        row_start[h] = lo;
+    }
+    __syncthreads();
+    const std::uint32_t T = blockDim.x, lane = lane_id(), warp = threadIdx.x >> 5;
+    // chunks of T consecutive queue entries of one row, in raster order
+    auto skip_empty = [&](std::uint32_t& hh, std::uint32_t& bb) {
+        while (hh < H && row_start[hh] + bb >= row_start[hh + 1])
+        {
+            ++hh;
+            bb = 0;
+        }
+    };
+    auto load = [&](std::uint32_t hh, std::uint32_t bb) {
+        JcpEntry en;
+        en.valid = false;
+        en.m = 0;
+        en.p = 0;
+        en.p_before = 0xffffffffu;
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+        {
+            en.w[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (hh < H)
+        {
+            const std::uint32_t ks = row_start[hh];
+            const std::uint32_t e = ks + bb + threadIdx.x;
+            if (e < row_start[hh + 1])
+            {
+                en.valid = true;
+                en.m = mkv[e];
+                en.p = queue[e];
+                if (lane == 0 && e > ks)
+                {
+                    en.p_before = queue[e - 1];
+                }
+                const float4* wrow = reinterpret_cast<const float4*>(wn + static_cast<std::size_t>(e) * 24);
+#pragma unroll
+                for (int i = 0; i < 6; ++i)
+                {
+                    en.w[i] = wrow[i];
+                }
+            }
+        }
+        return en;
+    };
+    bool bad = false;
+    std::uint32_t h = 0, base = 0, parity = 0, chunks = 0;
+    skip_empty(h, base);
+    JcpEntry cur = load(h, base);
+    while (h < H)
+    {
+        std::uint32_t nh = h, nb = base + T;
+        skip_empty(nh, nb);
+        const JcpEntry nxt = load(nh, nb); // in flight while this chunk is voted on
+        // ---- vote tables
+        const int wv = static_cast<int>(cur.p - h * W);
+        std::uint32_t entry = 0;
+        if (cur.valid && ((cur.m >> 48) & 1ULL))
+        {
+            const unsigned long long m = cur.m;
+            float wt[24];
+#pragma unroll
+            for (int i = 0; i < 6; ++i)
+            {
+                wt[4 * i] = cur.w[i].x;
+                wt[4 * i + 1] = cur.w[i].y;
+                wt[4 * i + 2] = cur.w[i].z;
+                wt[4 * i + 3] = cur.w[i].w;
+            }
+            bool spec10 = false, spec11 = false;
+            float g = 0.f, o = 0.f; // sums over slots 0..9
+            float g10 = 0.f, o10 = 0.f, g11 = 0.f, o11 = 0.f;
+#pragma unroll
+            for (int s = 0; s < 12; ++s)
+            {
+                const int dh = s < 5 ? -2 : (s < 10 ? -1 : 0);
+                const int dw = s < 5 ? s - 2 : (s < 10 ? s - 7 : s - 12);
+                std::uint32_t mi = static_cast<std::uint32_t>(m >> (2 * s)) & 3u;
+                if (mi == 3u)
+                {
+                    const int hh = static_cast<int>(h) + dh, ww = wv + dw;
+                    if (hh >= 0 && ww >= 0 && ww < sp.W)
+                    {
+                        if (dh == 0)
+                        {
+                            // left neighbour in this row: resolved by the chain scan
+                            spec10 = spec10 || s == 10;
+                            spec11 = spec11 || s == 11;
+                            mi = 0u;
+                        }
+                        else
+                        {
+                            mi = plane_get(plane, static_cast<std::uint32_t>(hh * sp.W + ww));
+                            bad = bad || mi == 3u;
+                        }
+                    }
+                    else
+                    {
+                        // inherited (stale) slot of a border pixel: explicit reference into an earlier row
+                        const std::uint32_t brow = static_cast<std::uint32_t>(m >> 49);
+                        mi = plane_get(plane, sref[static_cast<std::size_t>(brow - 1) * 12 + s]);
+                        bad = bad || mi == 3u;
+                    }
+                }
+                const float cg = mi == 1u ? wt[s] : 0.f, co = mi == 2u ? wt[s] : 0.f;
+                if (s < 10)
+                {
+                    g += cg;
+                    o += co;
+                }
+                else if (s == 10)
+                {
+                    g10 = cg;
+                    o10 = co;
+                }
+                else
+                {
+                    g11 = cg;
+                    o11 = co;
+                }
+            }
+            // variants [a][b]: a = left-2 is of the class, b = left-1 is of the class
+            float G[4], O[4];
+#pragma unroll
+            for (int v = 0; v < 4; ++v)
+            {
+                const bool a = (v & 2) != 0, b = (v & 1) != 0;
+                G[v] = (g + (spec10 ? (a ? wt[10] : 0.f) : g10)) + (spec11 ? (b ? wt[11] : 0.f) : g11);
+                O[v] = (o + (spec10 ? (a ? wt[10] : 0.f) : o10)) + (spec11 ? (b ? wt[11] : 0.f) : o11);
+            }
+#pragma unroll
+            for (int s = 12; s < 24; ++s)
+            {
+                const std::uint32_t mi = static_cast<std::uint32_t>(m >> (2 * s)) & 3u;
+                const float cg = mi == 1u ? wt[s] : 0.f, co = mi == 2u ? wt[s] : 0.f;
+#pragma unroll
+                for (int v = 0; v < 4; ++v)
+                {
+                    G[v] += cg;
+                    O[v] += co;
+                }
+            }
+            std::uint32_t table = 0;
+#pragma unroll
+            for (int c = 0; c < 9; ++c)
+            {
+                const int s10 = c / 3, s11 = c % 3;
+                const int vg = (s10 == 1 ? 2 : 0) | (s11 == 1 ? 1 : 0);
+                const int vo = (s10 == 2 ? 2 : 0) | (s11 == 2 ? 1 : 0);
+                table |= (O[vo] > G[vg]) ? (1u << c) : 0u;
+            }
+            entry = table | (1u << 9) | (spec10 ? 1u << 10 : 0u) | (spec11 ? 1u << 11 : 0u);
+        }
+        // ---- the entry as a map on X = (outcome of entry q-2, outcome of entry q-1)
+        std::uint32_t p_before = __shfl_up_sync(0xffffffffu, cur.p, 1);
+        if (lane == 0)
+        {
+            p_before = cur.p_before;
+        }
+        unsigned long long map = kJcpIdentityMap;
+        if (cur.valid)
+        {
+            // slot 10 (pixel w - 2) is the previous entry when that is not the pixel w - 1
+            const bool prev_is_w2 = p_before + 2u == cur.p;
+            map = 0;
+#pragma unroll
+            for (int x = 0; x < 9; ++x)
+            {
+                const std::uint32_t a = x / 3, b = x % 3;
+                std::uint32_t out = 0;
+                if (entry & 0x200u)
+                {
+                    const std::uint32_t s11 = (entry & 0x800u) ? b : 0u;
+                    const std::uint32_t s10 = (entry & 0x400u) ? (prev_is_w2 ? b : a) : 0u;
+                    out = ((entry >> (s10 * 3u + s11)) & 1u) ? 2u : 1u;
+                }
+                map |= static_cast<unsigned long long>(b * 3u + out) << (4 * x);
+            }
+        }
+        // ---- inclusive scan of the maps over the warp, totals chained across the warps
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1)
+        {
+            const unsigned long long earlier = __shfl_up_sync(0xffffffffu, map, off);
+            if (lane >= static_cast<std::uint32_t>(off))
+            {
+                map = jcp_compose(map, earlier);
+            }
+        }
+        if (lane == 31u)
+        {
+            s_tot[parity][warp] = map;
+        }
+        __syncthreads();
+        std::uint32_t x = (base == 0u) ? 0u : s_carry[parity ^ 1u]; // state at the chunk start
+        for (std::uint32_t w2 = 0; w2 < warp; ++w2)
+        {
+            x = jcp_apply(s_tot[parity][w2], x);
+        }
+        x = jcp_apply(map, x); // state after this entry: (outcome before, own outcome)
+        if (threadIdx.x == T - 1u)
+        {
+            s_carry[parity] = x;
+        }
+        if (cur.valid)
+        {
+            const std::uint32_t out = x % 3u;
+            const std::uint32_t px = cur.p;
+            atomicAnd(&plane[px >> 4], ~((3u ^ out) << ((px & 15u) * 2u)));
+            code[px] = (out == 0u) ? PX_UNDECIDED : static_cast<std::uint8_t>(out);
+        }
+        __syncthreads(); // the plane is final for the next row; s_tot / s_carry alternate between chunks
+        parity ^= 1u;
+        ++chunks;
+        cur = nxt;
+        h = nh;
+        base = nb;
+    }
+    if (bad)
+    {
+        atomicOr(&d.status[f], ST_JCP_STALL); // a rows-above dependency was not final: internal error
+    }
+    if (threadIdx.x == 0)
+    {
+        d.jcp_rounds[f] = chunks;
+    }
+}
+
+#endif // LPL_JCP_ROWS
+
 // populateLabels (segmenter.cpp:640-669): only pixel winners receive a label; optional BGR image
 __global__ void __launch_bounds__(256) k_seg_labels_out(Dev d, SegParams sp, int want_image)
 {
@@ -1657,15 +1996,23 @@ void launch_segment(Ctx* c, std::uint32_t nf, bool want_image)
     launch_compact(c, "jcp_queue", nf, d.ptiles, nullptr, static_cast<std::uint32_t>(sp.npx), d.tile_cnt, d.n_queue,
                    QueuePred{d.code, static_cast<std::uint32_t>(sp.npx)},
                    QueueEmit{d.queue, d.status, d.qcap});
+#if !LPL_JCP_ROWS
     launch_compact(c, "jcp_runs", nf, (d.qcap + kTile - 1) / kTile, d.n_queue, 0u, d.tile_cnt, d.n_runs,
                    RunHeadPred{d.queue, d.qcap, static_cast<std::uint32_t>(sp.W)}, RunHeadEmit{d.runs, d.qcap});
+#endif
     k_jcp_pre<<<dim3((d.qcap + 127) / 128, nf), 128, 0, s>>>(d, sp);
     mark(c, "jcp_pre");
+    // state plane (32 KB for 64 x 2048, 64 KB for 128-beam images): above the 48 KB default for the
+    // larger images, opt in (up to 227 KB per CTA on sm_100a)
     const std::size_t plane_bytes = static_cast<std::size_t>((sp.npx + 15) / 16) * 4;
-    // state plane (32 KB for 64 x 2048, 64 KB for 128-beam images) on top of ~39 KB of static shared
-    // memory: above the 48 KB default, opt in (up to 227 KB per CTA on sm_100a)
+#if LPL_JCP_ROWS
+    const std::size_t rows_bytes = plane_bytes + sizeof(std::uint32_t) * (sp.H + 1);
+    cudaFuncSetAttribute(k_jcp_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(rows_bytes));
+    k_jcp_rows<<<nf, kJcpRowsThreads, rows_bytes, s>>>(d, sp);
+#else
     cudaFuncSetAttribute(k_jcp_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(plane_bytes));
     k_jcp_resolve<<<nf, kJcpThreads, plane_bytes, s>>>(d, sp);
+#endif
     mark(c, "jcp_resolve");
     k_seg_labels_out<<<dim3((sp.npx + 255) / 256, nf), 256, 0, s>>>(d, sp, want_image ? 1 : 0);
     mark(c, "seg_labels_out");

@@ -57,7 +57,7 @@ def run(frames, n_ctx, want, steps=8, warm=2):
 
 
 def main():
-    frames, workload, _ = bench.load_frames(None)
+    frames, workload, _, _ = bench.load_frames(None)
     full = ("labels_u8", "obstacle_index", "cluster_labels", "hull_offsets", "hull_xy", "zminmax")
     for n_ctx, want, tag in ((4, full, "all results"), (4, ("hull_offsets",), "counts + hull offsets only"),
                              (2, full, "all results"), (1, full, "all results, one context")):

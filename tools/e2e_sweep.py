@@ -11,7 +11,7 @@ import lidar_processing_v2_b200 as lpl  # noqa: E402
 
 def main():
     combos = [tuple(int(v) for v in a.split(":")) for a in sys.argv[1:]] or [(2, 2), (3, 3), (4, 2), (4, 3), (4, 4), (6, 3)]
-    frames, workload, _ = bench.load_frames(None)
+    frames, workload, _, _ = bench.load_frames(None)
     for parts, nctx in combos:
         args = argparse.Namespace(steps=6, warmup=2, e2e_parts=parts, e2e_ctx=nctx)
         r = bench.run_e2e(lpl, None, frames, 0, args, lambda: None, lpl.STAGE_ALL)

@@ -12,7 +12,7 @@ import lidar_processing_v2_b200 as lpl  # noqa: E402
 
 
 def main():
-    frames, workload, _ = bench.load_frames(None)
+    frames, workload, _, _ = bench.load_frames(None)
     nf = len(frames)
     ctx = lpl.Context(0, max_points=max(f.shape[0] for f in frames), max_frames=nf)
     ctx.cluster_config(range_m=0.4, az_deg=1.0, el_deg=3.0, min_size=3)

@@ -10,7 +10,7 @@ import lidar_processing_v2_b200 as lpl  # noqa: E402
 
 def main():
     want = sys.argv[1:]
-    frames, workload, _ = bench.load_frames(None)
+    frames, workload, _, _ = bench.load_frames(None, os.environ.get("LPL_WORKLOAD"))
     if os.environ.get("LPL_FRAMES"):
         frames = frames[: int(os.environ["LPL_FRAMES"])]
     nf = len(frames)
