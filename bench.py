@@ -89,16 +89,57 @@ def load_frames(limit=None, workload=None):
 # clocks
 # --------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region: an NVML polling thread (every
+    2 ms: the timed region of the default run is ~50 ms, too short for `nvidia-smi -lms`), with the
+    nvidia-smi loop of B200_PROFILING.md as the fallback when NVML cannot be loaded."""
+
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    REASON_BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+                   0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, index: int):
         self.index = index
         self.rows = []
         self.proc = None
+        self.nvml = None
+        self.handle = None
+        self.samples = []  # (sm_mhz, reasons bitmask)
+        self.stop_flag = threading.Event()
+        self.th = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            handle = None
+            try:
+                import torch
+
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)
+            self.nvml, self.handle = pynvml, handle
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        nv, h = self.nvml, self.handle
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), int(get_reasons(h))))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        if self.nvml is not None:
+            self.th = threading.Thread(target=self._poll, daemon=True)
+            self.th.start()
+            return
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
@@ -113,6 +154,20 @@ class ClockSampler:
             self.rows.append(line.strip())
 
     def stop(self) -> dict:
+        if self.nvml is not None:
+            self.stop_flag.set()
+            self.th.join(timeout=2)
+            sm = [x[0] for x in self.samples]
+            bits = 0
+            for x in self.samples:
+                bits |= x[1]
+            try:
+                mx = float(self.nvml.nvmlDeviceGetMaxClockInfo(self.handle, self.nvml.NVML_CLOCK_SM))
+            except Exception:
+                mx = None
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
+                    "reasons": sorted(n for b, n in self.REASON_BITS.items() if bits & b),
+                    "samples": len(sm), "source": "nvml, 2 ms polling inside the timed region"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -135,7 +190,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 # --------------------------------------------------------------------------------------------
@@ -162,6 +217,7 @@ def algorithmic_bytes(name: str, s: dict) -> float:
         "seg_image": (16 + 4 + 4 + 1) * N + 1 * NB + 8 * NB, "seg_px": 8 * PX + 17 * PX,  # + 17 B for every pixel that has a winner (not counted)
         "seg_dilate": 2 * PX, "jcp_queue": 2 * PX + 4 * Q,
         "jcp_pre": Q * (25 * 17 + 24 * 4 + 8), "jcp_resolve": PX * 1 + Q * (8 + 4 + 96) + Q * 1 + 8 * Q // 3,
+        "jcp_rows": PX * 1 + Q * (8 + 4 + 96) + Q * 1,
         "take_obstacles": 1 * N + 16 * M + 20 * M,
         "clu_sph": 16 * M + 16 * M, "clu_insert": 16 * M + 4 * M, "clu_edges": 8 * M + 52 * M // 3,
         "clu_union_sm": 52 * M // 3 + 8 * M // 3, "clu_union": 8 * M, "clu_flatten": 8 * M,

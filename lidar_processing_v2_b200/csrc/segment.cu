@@ -2009,11 +2009,12 @@ void launch_segment(Ctx* c, std::uint32_t nf, bool want_image)
     const std::size_t rows_bytes = plane_bytes + sizeof(std::uint32_t) * (sp.H + 1);
     cudaFuncSetAttribute(k_jcp_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(rows_bytes));
     k_jcp_rows<<<nf, kJcpRowsThreads, rows_bytes, s>>>(d, sp);
+    mark(c, "jcp_rows");
 #else
     cudaFuncSetAttribute(k_jcp_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(plane_bytes));
     k_jcp_resolve<<<nf, kJcpThreads, plane_bytes, s>>>(d, sp);
-#endif
     mark(c, "jcp_resolve");
+#endif
     k_seg_labels_out<<<dim3((sp.npx + 255) / 256, nf), 256, 0, s>>>(d, sp, want_image ? 1 : 0);
     mark(c, "seg_labels_out");
 }

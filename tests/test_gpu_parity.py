@@ -371,6 +371,21 @@ def test_dense_polar_cells(ctx, port):
     assert np.array_equal(ctx.segment(pts, None), port.segment(pts, None))
 
 
+def test_jcp_whole_rows_queued(ctx, port):
+    """Concentric walls: boundaries run along entire image rows, so the JCP queue holds whole rows of
+    consecutive pixels (2048-long dependency chains, several chunks of the row scan with the carried
+    state), with and without the ring field; labels and image against the oracle."""
+    pts, ring = F.synth_ring_walls(7)
+    exp, img_o, dbg_o = port.segment(pts, ring, want_image=True, want_debug=True)
+    assert dbg_o["n_queued"] > 30000
+    got, img_g = ctx.segment(pts, ring, want_image=True)
+    assert ctx.debug_segment(0)["n_queued"] == dbg_o["n_queued"]
+    assert np.array_equal(got, exp) and np.array_equal(img_g, img_o)
+    assert np.array_equal(ctx.segment(pts, None), port.segment(pts, None))
+    pts2, ring2 = F.synth_ring_walls(8, radii=(5.0, 5.6, 7.5, 11.0), height=1.2)
+    assert np.array_equal(ctx.segment(pts2, ring2), port.segment(pts2, ring2))
+
+
 def test_unorganized_2m_cloud_properties(port):
     """BASELINE.json configs[4] at reduced size against the oracle, and at full size (2 M points)
     through size-independent properties: idempotence and DROR monotonicity in the radius."""

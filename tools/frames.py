@@ -159,6 +159,30 @@ def synth_scan(seed: int, beams: int = 64, cols: int = 2048, n_boxes: int = 60, 
     return out, np.concatenate(ring)
 
 
+def synth_ring_walls(seed: int, beams: int = 64, cols: int = 2048,
+                     radii=(4.5, 6.5, 9.0, 13.0, 19.0, 28.0), height: float = 0.6):
+    """Concentric low walls around the sensor on flat ground: obstacle / ground boundaries that run
+    along whole image rows, so the JCP queue holds complete rows of consecutive pixels (the longest
+    dependency chains the sweep can meet). Returns (pts (n, 4) float32 in firing order, ring uint16)."""
+    rng = np.random.default_rng(seed)
+    el = np.deg2rad(-24.8 + (np.arange(beams) + 0.5) * 26.8 / beams)[::-1]
+    az = 2.0 * np.pi * (np.arange(cols) + 0.5) / cols
+    e, a = np.meshgrid(el, az, indexing="ij")
+    t = np.where(e < 0, -1.73 / np.sin(np.minimum(e, -1e-3)), 200.0)
+    for r in radii:
+        tk = r / np.cos(e)
+        zk = tk * np.sin(e)
+        t = np.where((zk >= -1.73) & (zk <= -1.73 + height) & (tk < t), tk, t)
+    keep = (t < 100.0).ravel()
+    zn = rng.normal(0, 0.02, a.shape)
+    xyz = (t * np.cos(e) * np.cos(a), t * np.cos(e) * np.sin(a), t * np.sin(e) + zn)
+    pts = np.zeros((beams * cols, 4), np.float32)
+    for i, v in enumerate(xyz):
+        pts[:, i] = np.round(v.ravel() * 1000.0) / 1000.0
+    ring = np.repeat(np.arange(beams - 1, -1, -1), cols).astype(np.uint16)
+    return np.ascontiguousarray(pts[keep]), np.ascontiguousarray(ring[keep])
+
+
 def synth_unorganized(seed: int, n: int = 2_000_000, n_blobs: int = 5000, r_max: float = 120.0):
     """Unorganised cloud: 60 % ground disc (density ~ 1/r), 35 % small Gaussian blobs, 5 % uniform
     background (DROR targets). BASELINE.json config 5."""

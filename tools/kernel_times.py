@@ -14,7 +14,8 @@ def main():
     if os.environ.get("LPL_FRAMES"):
         frames = frames[: int(os.environ["LPL_FRAMES"])]
     nf = len(frames)
-    ctx = lpl.Context(0, max_points=max(f.shape[0] for f in frames), max_frames=nf)
+    cap = int(max(f.shape[0] for f in frames) * float(os.environ.get("LPL_CAP_SCALE", "1")))  # >1: how much do capacity-sized grids cost?
+    ctx = lpl.Context(0, max_points=cap, max_frames=nf)
     ctx.cluster_config(range_m=0.4, az_deg=1.0, el_deg=3.0, min_size=3)
     ctx.upload(frames)
     for _ in range(3):
