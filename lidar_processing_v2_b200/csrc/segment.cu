@@ -1866,7 +1866,12 @@ __global__ void __launch_bounds__(kJcpRowsThreads, LPL_JCP_ROWS_MINB) k_jcp_rows
             atomicAnd(&plane[px >> 4], ~((3u ^ out) << ((px & 15u) * 2u)));
             code[px] = (out == 0u) ? PX_UNDECIDED : static_cast<std::uint8_t>(out);
         }
-        __syncthreads(); // the plane is final for the next row; s_tot / s_carry alternate between chunks
+        if (nh != h)
+        {
+            __syncthreads(); // the plane is final for the next row
+        }
+        // (within a row the next chunk's votes only read rows above, and s_tot / s_carry alternate
+        // between chunks: the first barrier of the next chunk orders their reuse)
         parity ^= 1u;
         ++chunks;
         cur = nxt;
