@@ -235,12 +235,20 @@ __global__ void __launch_bounds__(kTileThreads) k_hull_tilesort(Dev d)
         s[t] = d.hsB[o + base + t]; // (label, x, y, index) of the points that survived the octagon filter
     }
     __syncthreads();
+    // every thread owns compare-exchange PAIRS (q-th pair of a stage: insert a zero bit at the stride
+    // position), so no lane idles on the upper element of a pair
     for (std::uint32_t k = 2; (k >> 1) < m; k <<= 1)
     {
-        for (std::uint32_t t = threadIdx.x; t < m; t += kTileThreads)
+        const std::uint32_t hk = k >> 1;
+        for (std::uint32_t q = threadIdx.x; q < kTile / 2; q += kTileThreads)
         {
-            const std::uint32_t u = t ^ (k - 1);
-            if (u > t && u < m)
+            const std::uint32_t t = ((q & ~(hk - 1u)) << 1) | (q & (hk - 1u));
+            const std::uint32_t u = t ^ (k - 1u);
+            if (t >= m)
+            {
+                break; // t grows with q
+            }
+            if (u < m)
             {
                 const uint4 a = s[t], b = s[u];
                 if (elem_less(b, a))
@@ -253,10 +261,15 @@ __global__ void __launch_bounds__(kTileThreads) k_hull_tilesort(Dev d)
         __syncthreads();
         for (std::uint32_t j = k >> 2; j > 0; j >>= 1)
         {
-            for (std::uint32_t t = threadIdx.x; t < m; t += kTileThreads)
+            for (std::uint32_t q = threadIdx.x; q < kTile / 2; q += kTileThreads)
             {
-                const std::uint32_t u = t ^ j;
-                if (u > t && u < m)
+                const std::uint32_t t = ((q & ~(j - 1u)) << 1) | (q & (j - 1u));
+                const std::uint32_t u = t | j;
+                if (t >= m)
+                {
+                    break;
+                }
+                if (u < m)
                 {
                     const uint4 a = s[t], b = s[u];
                     if (elem_less(b, a))
