@@ -135,8 +135,18 @@ class ClockSampler:
                 pass
             time.sleep(0.002)
 
+    def _sample(self):
+        nv, h = self.nvml, self.handle
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        try:
+            self.samples.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), int(get_reasons(h))))
+        except Exception:
+            pass
+
     def start(self):
         if self.nvml is not None:
+            self._sample()  # first calls are slow: take them before the timed region
+            self.samples.clear()
             self.th = threading.Thread(target=self._poll, daemon=True)
             self.th.start()
             return
