@@ -11,12 +11,15 @@ curved-voxel clustering -> per-cluster hulls) over one batch of frames on every 
                        (18.7 M points, 300 MB of float4 input > the 126 MB L2, so no L2 flush is needed)
                        as one batch; every rank runs its own copy (weak scaling, no collective on
                        the data path - NCCL only reduces the timing).
-  workload "synth64"   used only when data/kitti154.npz is absent: seeded synthetic HDL-64E sweeps.
+  workload "synth64"   BASELINE.json configs[3]: seeded synthetic HDL-64E sweeps (also the fallback when
+                       data/kitti154.npz is absent); "synth128" = configs[2] (128 beams x 2048 columns with a
+                       ring field); "cloud2m" = configs[4] (unorganised 2 M-point clouds, ring-less chain).
+                       Select with --workload; the default and the headline is kitti154.
 
 `value`  = frames/s with the inputs already resident in HBM (CUDA events on the context stream).
 `e2e`    = frames/s through the C ABI with HOST buffers: every step uploads the batch from pinned
-           host memory, runs the pipeline and reads labels / clusters / hulls back; two contexts are
-           double-buffered so copies overlap compute.
+           host memory (one packed transfer), runs the pipeline and reads labels / clusters / hulls
+           back; --e2e-ctx contexts (streams, default 4) rotate so copies overlap compute.
 `roofline` describes the dominant kernel (largest share of the step) from per-kernel CUDA events
 recorded inside the timed region; `cpu_baseline` / `--impl reference` time the reference's own CPU
 code (oracle/_ref, compiled from the unmodified sources) on the host cores.
