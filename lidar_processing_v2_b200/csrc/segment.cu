@@ -1567,8 +1567,9 @@ __global__ void __launch_bounds__(1024) k_jcp_resolve(Dev d, SegParams sp)
 //     is a map X -> X' (9 x 4 bits); a warp-level inclusive scan composes the maps of 32 consecutive
 //     entries, the warps' totals are chained through shared memory, and every thread reads its outcome
 //     off its prefix map. No sequential walk, no polling.
-// Two CTA barriers per 512 queue entries of a row; the queue records of the next chunk are loaded into
-// registers before the current chunk is voted on.
+// A row is processed in chunks of kJcpRowsThreads queue entries: one CTA barrier per chunk plus one at
+// the end of the row; the queue records of the next chunk are loaded into registers before the
+// current chunk is voted on. Reference: the queue loop of Segmenter::JCP (segmenter.cpp:535-637).
 // ------------------------------------------------------------------------------------------
 #if LPL_JCP_ROWS
 #ifndef LPL_JCP_ROWS_THREADS
