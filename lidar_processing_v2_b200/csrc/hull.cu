@@ -309,6 +309,28 @@ __device__ __forceinline__ std::uint32_t merge_path(GetA A, std::uint32_t la, Ge
     return lo;
 }
 
+// the same split found by a whole warp: 32 probe positions per round (the predicate is true on a prefix
+// of the range), so a run of 131,072 elements takes four dependent rounds of loads instead of seventeen
+template <class GetA, class GetB>
+__device__ __forceinline__ std::uint32_t merge_path_warp(GetA A, std::uint32_t la, GetB B, std::uint32_t lb, std::uint32_t diag)
+{
+    std::uint32_t lo = diag > lb ? diag - lb : 0u;
+    std::uint32_t hi = min(diag, la);
+    const std::uint32_t lane = lane_id();
+    while (lo < hi) // warp-uniform
+    {
+        const unsigned long long span = hi - lo;
+        const std::uint32_t m = lo + static_cast<std::uint32_t>((span * lane) >> 5);
+        const bool before = elem_less(A(m), B(diag - 1u - m));
+        const std::uint32_t cnt = __popc(__ballot_sync(0xffffffffu, before));
+        const std::uint32_t new_hi = cnt < 32u ? lo + static_cast<std::uint32_t>((span * cnt) >> 5) : hi;
+        const std::uint32_t new_lo = cnt > 0u ? lo + static_cast<std::uint32_t>((span * (cnt - 1u)) >> 5) + 1u : lo;
+        lo = new_lo;
+        hi = new_hi;
+    }
+    return lo;
+}
+
 // merge pass p: runs of (kTile << p) elements, pairwise, one output tile per CTA
 __global__ void __launch_bounds__(kTileThreads) k_hull_merge(Dev d, std::uint32_t pass)
 {
@@ -340,11 +362,16 @@ __global__ void __launch_bounds__(kTileThreads) k_hull_merge(Dev d, std::uint32_
         }
         return;
     }
-    if (threadIdx.x == 0 || threadIdx.x == 32)
+    if (threadIdx.x < 64u)
     {
-        const std::uint32_t dg = threadIdx.x == 0 ? d0 : d1;
-        s_split[threadIdx.x >> 5] = merge_path([&](std::uint32_t i) { return src[a0 + i]; }, la,
-                                               [&](std::uint32_t i) { return src[b0 + i]; }, lb, dg);
+        // warp 0 finds the split of the tile's first output, warp 1 of its last
+        const std::uint32_t dg = threadIdx.x < 32u ? d0 : d1;
+        const std::uint32_t split = merge_path_warp([&](std::uint32_t i) { return src[a0 + i]; }, la,
+                                                    [&](std::uint32_t i) { return src[b0 + i]; }, lb, dg);
+        if (lane_id() == 0)
+        {
+            s_split[threadIdx.x >> 5] = split;
+        }
     }
     __syncthreads();
     const std::uint32_t ai0 = s_split[0], ai1 = s_split[1];
