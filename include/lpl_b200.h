@@ -275,8 +275,8 @@ int lpl_profile_read(lpl_ctx* ctx, uint32_t max_entries, const char** names_out,
 /* Kernels launched by this context since the last call with reset != 0. */
 uint64_t lpl_launch_count(lpl_ctx* ctx, int reset);
 /* Intermediates of the last segmentation of `frame` (all nullable): elevation[slices*rings],
- * plane[4] + best inlier count, counters[8] = {binned, candidates, queued, jcp_rounds,
- * border_rows, slices, rings, status}. */
+ * plane[4] + best inlier count, counters[8] = {binned, candidates, queued, jcp_rounds (chunks of queue
+ * entries the row-synchronous JCP sweep processed), border_rows, slices, rings, status}. */
 int lpl_debug_segment(lpl_ctx* ctx, uint32_t frame, float* elevation, float* plane,
                       uint32_t* best_inliers, uint32_t* counters);
 /* Points the DROR scan-line pass left to the exhaustive grid search in the last run. */

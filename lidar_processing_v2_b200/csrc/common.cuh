@@ -137,7 +137,7 @@ struct Dev
     std::uint32_t nborder_cap;
     std::uint32_t* runs;      // [B][qcap] first queue entry of every run of horizontally adjacent queued pixels
     std::uint32_t* n_runs;    // [B]
-    std::uint32_t* jcp_rounds;// [B]
+    std::uint32_t* jcp_rounds;// [B] chunks of queue entries swept by k_jcp_rows (diagnostic)
     std::uint8_t* labels_out; // [B][cap]  Label (0/1/2) per *input* point
     std::uint8_t* bgr;        // [B][npx*3]
     // ---- obstacle cloud / clustering
