@@ -99,6 +99,19 @@ def test_port_equals_reference_on_synthetic(port, ref):
         assert np.array_equal(port.dror(pts), ref.dror(pts, mode="exact"))
 
 
+def test_port_equals_reference_on_whole_row_queues(port, ref):
+    """Concentric walls: the JCP queue holds whole image rows (the longest in-row dependency chains).
+    The GPU parity test for this scene checks against the port, so the port is pinned to the
+    unmodified reference sources here, labels and image."""
+    for seed, kw in ((7, {}), (8, dict(radii=(5.0, 5.6, 7.5, 11.0), height=1.2))):
+        pts, ring = F.synth_ring_walls(seed, **kw)
+        a, img_a, dbg = port.segment(pts, ring, want_image=True, want_debug=True)
+        b, img_b = ref.segment(pts, ring, want_image=True)
+        assert dbg["n_queued"] > 8000
+        assert np.array_equal(a, b) and np.array_equal(img_a, img_b)
+        assert np.array_equal(port.segment(pts, None), ref.segment(pts, None))
+
+
 def test_port_equals_reference_128_beams(port, ref):
     from oracle.oracle import default_seg_cfg
 
