@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the per-frame LiDAR perception hot path on B200 (driver contract: see README/DESIGN).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ...]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
 A *step* is one pass of the whole hot path (ring partition -> DROR -> JCP/RECM segmentation ->
@@ -11,18 +11,22 @@ curved-voxel clustering -> per-cluster hulls) over one batch of frames on every 
                        (18.7 M points, 300 MB of float4 input > the 126 MB L2, so no L2 flush is needed)
                        as one batch; every rank runs its own copy (weak scaling, no collective on
                        the data path - NCCL only reduces the timing).
-  workload "synth64"   BASELINE.json configs[3]: seeded synthetic HDL-64E sweeps (also the fallback when
+  workload "synth64"   BASELINE.json configs[3] shapes: seeded synthetic HDL-64E sweeps (also the fallback when
                        data/kitti154.npz is absent); "synth128" = configs[2] (128 beams x 2048 columns with a
                        ring field); "cloud2m" = configs[4] (unorganised 2 M-point clouds, ring-less chain).
-                       Select with --workload; the default and the headline is kitti154.
+                       The default run measures kitti154 as the headline and appends the synthetic shapes and
+                       the frame-sharded 8,192-frame stream (configs[3]) under "workloads".
 
-`value`  = frames/s with the inputs already resident in HBM (CUDA events on the context stream).
-`e2e`    = frames/s through the C ABI with HOST buffers: every step uploads the batch from pinned
-           host memory (one packed transfer), runs the pipeline and reads labels / clusters / hulls
-           back; --e2e-ctx contexts (streams, default 4) rotate so copies overlap compute.
-`roofline` describes the dominant kernel (largest share of the step) from per-kernel CUDA events
-recorded inside the timed region; `cpu_baseline` / `--impl reference` time the reference's own CPU
-code (oracle/_ref, compiled from the unmodified sources) on the host cores.
+`value`  = frames/s with the inputs already resident in HBM (CUDA events on the context stream, no
+           per-kernel events inside this region).
+`e2e`    = frames/s through the C ABI with HOST buffers: every step uploads the batch from pinned host
+           memory as ONE transfer of 12 bytes per point (the std::array<float, 3> cloud NoiseRemover::filter
+           takes), runs the pipeline and reads labels / clusters / hulls back as ONE packed transfer;
+           --e2e-ctx contexts (streams, default 4) rotate so copies overlap compute.
+`roofline` describes the dominant kernel (largest share of the step) from per-kernel CUDA events recorded in a
+second pass of the same K steps; `stages` gives the SURVEY 8(d) stage bytes over the stage times;
+`parity` compares the timed batch with the reference CPU code; `cpu_baseline` / `--impl reference` time the
+reference's own CPU code (oracle/_ref, compiled from the unmodified sources) on the host cores.
 """
 from __future__ import annotations
 
@@ -47,6 +51,7 @@ UNIT = "frames/s"
 # workload
 # --------------------------------------------------------------------------------------------
 WORKLOADS = ("kitti154", "synth64", "synth128", "cloud2m")
+STREAM_FRAMES = 8192  # BASELINE.json configs[3]
 
 
 def load_frames(limit=None, workload=None):
@@ -76,7 +81,8 @@ def load_frames(limit=None, workload=None):
         # BASELINE.json configs[4]: 2 M-point unorganised clouds (no ring structure: ring-less segmentation)
         n = limit or 5
         opts["stages"] = "ringless"
-        opts["cpu"] = False  # the reference Clusterer's 200k-voxel table overflows on this cloud
+        # chained, the reference Clusterer only sees the ~30k OBSTACLE points of a cloud (pixel winners), far below
+        # its 200k-voxel table (SURVEY H9 bites when the raw cloud is clustered: tests/test_gpu_parity.py)
         return ([F.synth_unorganized(5000 + i) for i in range(n)], "cloud2m",
                 "synthetic unorganised 2,000,000-point clouds (ground disc + 5,000 blobs + 5 % background), "
                 "ring-less chain: DROR + segmentation + clustering + hulls", opts)
@@ -219,6 +225,7 @@ def algorithmic_bytes(name: str, s: dict) -> float:
     PX, CELLS, Q, C, U, F = s["PX"], s["CELLS"], s["Q"], s["C"], s["U"], s["F"]
     t = {
         "ring_count": 16 * N, "ring_write": 16 * N + 2 * N,
+        "front": 16 * N + 1 * N + 1 * N + 4 * U,
         "dror_near": 16 * N + 1 * N + 4 * U,
         "dror_mark": 20 * U + 16384 * F, "dror_grid_count": 16 * N, "dror_grid_scan": 8 * 131072 * F,
         "dror_grid_scatter": 16 * N + 16 * U * 8,
@@ -227,10 +234,13 @@ def algorithmic_bytes(name: str, s: dict) -> float:
         "seg_cell": 8 * NB + 8 * CELLS, "seg_elev": 12 * CELLS,
         "seg_label": (16 + 4) * N + 4 * NB + 1 * N + 16 * C,
         "ransac_draw": 1024 * F + 8 * CELLS, "ransac_plane": 120 * 64 * F, "ransac_count": 16 * C,
-        "seg_image": (16 + 4 + 4 + 1) * N + 1 * NB + 8 * NB, "seg_px": 8 * PX + 17 * PX,  # + 17 B for every pixel that has a winner (not counted)
+        "seg_image": (16 + 4 + 4 + 1) * N + 1 * NB + 8 * NB, "seg_px": 8 * PX + 17 * PX,
         "seg_dilate": 2 * PX, "jcp_queue": 2 * PX + 4 * Q,
-        "jcp_pre": Q * (25 * 17 + 24 * 4 + 8), "jcp_resolve": PX * 1 + Q * (8 + 4 + 96) + Q * 1 + 8 * Q // 3,
+        # the 5 x 5 neighbourhoods of queued pixels overlap: ~4 distinct pixel records (16 B point + 1 B code) are
+        # fetched per queued pixel (ncu dram__bytes: profiles/traffic.json), 104 B of weights + masks are written
+        "jcp_pre": min(PX, 4 * Q) * 17 + Q * (24 * 4 + 8),
         "jcp_rows": PX * 1 + Q * (8 + 4 + 96) + Q * 1,
+        "seg_labels_out": PX * (1 + 4) + 1 * NB,
         "take_obstacles": 1 * N + 16 * M + 20 * M,
         "clu_sph": 16 * M + 16 * M, "clu_insert": 16 * M + 4 * M, "clu_edges": 8 * M + 52 * M // 3,
         "clu_union_sm": 52 * M // 3 + 8 * M // 3, "clu_union": 8 * M, "clu_flatten": 8 * M,
@@ -245,6 +255,27 @@ def algorithmic_bytes(name: str, s: dict) -> float:
         "label_count": 4 * M,
     }
     return float(t.get(name, 0.0))
+
+
+def stage_of(kernel: str) -> str:
+    if kernel.startswith("ring") or kernel == "front":
+        return "S0+S1 ring+dror" if kernel == "front" else "S0 ring"
+    if kernel.startswith("dror"):
+        return "S1 dror"
+    if kernel.startswith(("seg_", "ransac", "jcp")):
+        return "S2 segment"
+    if kernel.startswith(("take_obstacles", "clu_")):
+        return "S3 cluster"
+    if kernel.startswith(("hull", "obb")):
+        return "S4 hulls"
+    return "other"
+
+
+def stage_bytes(s: dict) -> dict:
+    """every stage reads its inputs once and writes its outputs once."""
+    N, M, K, HV = s["N"], s["M"], s["K"], s["HV"]
+    return {"S0 ring": 18 * N, "S1 dror": 17 * N, "S0+S1 ring+dror": 19 * N, "S2 segment": 22 * N, "S3 cluster": 20 * M,
+            "S4 hulls": 12 * M + 4 * HV + 12 * K}
 
 
 def batch_stats(ctx, nf, seg_dbg=True) -> dict:
@@ -279,6 +310,7 @@ def _cpu_worker_init(limit, workload=None):
 
     _W["frames"], _, _, opts = load_frames(limit, workload)
     _W["rings"] = opts["rings"]
+    _W["ringless"] = opts["stages"] == "ringless"
     _W["ref"] = RefOracle() if have_ref() else None
     _W["port"] = PortOracle()
     if opts["image_height"] != 64:
@@ -287,20 +319,30 @@ def _cpu_worker_init(limit, workload=None):
                 o.segment_config(default_seg_cfg(image_height=opts["image_height"]))
 
 
-def _cpu_worker_frame(i):
+def _cpu_worker_frame(task):
     """Whole hot path on frame i, chained as in DESIGN.md (ring -> DROR -> segment VALID ->
-    cluster OBSTACLE -> hulls), through the reference's own code where it is a library function."""
+    cluster OBSTACLE -> hulls), through the reference's own code where it is a library function.
+    task = (i, dror mode "as_is" | "exact", want arrays)."""
+    i, mode, want = task
     ref, port, pts = _W["ref"], _W["port"], _W["frames"][i]
-    ring = port.ring_partition(pts) if _W.get("rings") is None else _W["rings"][i]
-    noise = ref.dror(pts, mode="as_is") if ref is not None else port.dror(pts)
+    if _W.get("ringless"):
+        ring = None
+    else:
+        ring = port.ring_partition(pts) if _W.get("rings") is None else _W["rings"][i]
+    noise = ref.dror(pts, mode=mode) if ref is not None else port.dror(pts)
     keep = noise == 0
     pv = np.ascontiguousarray(pts[keep])
-    rv = np.ascontiguousarray(ring[keep])
+    rv = None if ring is None else np.ascontiguousarray(ring[keep])
     labels = ref.segment(pv, rv) if ref is not None else port.segment(pv, rv)
     obs = np.ascontiguousarray(pv[labels == 2])
     cl = ref.cluster(obs) if ref is not None else port.cluster(obs)
     off, xy, idx, zmm = port.cluster_hulls(obs, cl)
-    return int(off[-1]) if off.size else 0
+    if not want:
+        return int(off[-1]) if off.size else 0
+    full = np.zeros(pts.shape[0], np.uint8)
+    full[keep] = labels
+    return dict(noise=noise.astype(np.uint8), labels=full, cluster_labels=cl.astype(np.int32), hull_offsets=off.astype(np.uint32),
+                hull_xy=xy.astype(np.float32))
 
 
 class CpuReference:
@@ -316,12 +358,13 @@ class CpuReference:
         self.kind = "reference" if have_ref() else "port"
         self.procs = procs
         self.pool = mp.get_context("spawn").Pool(procs, initializer=_cpu_worker_init, initargs=(limit, workload))
-        self.pool.map(_cpu_worker_frame, list(range(min(limit, procs))))  # warm-up: imports, page faults
+        self.pool.map(_cpu_worker_frame, [(i, "as_is", False) for i in range(min(limit, procs))])  # warm-up: imports, page faults
 
-    def run(self, idx) -> float:
+    def run(self, idx, mode="as_is", want=False):
+        """-> (seconds, results)"""
         t0 = time.perf_counter()
-        self.pool.map(_cpu_worker_frame, list(idx), chunksize=1)
-        return time.perf_counter() - t0
+        res = self.pool.map(_cpu_worker_frame, [(i, mode, want) for i in idx], chunksize=1)
+        return time.perf_counter() - t0, res
 
     def close(self):
         self.pool.close()
@@ -335,34 +378,42 @@ def host_cores() -> int:
         return max(1, os.cpu_count() or 1)
 
 
+def step_config(workload, nf, total_pts, stages_txt, world):
+    """The `config` object both arms print (same workload, same batch)."""
+    return {"workload": workload, "frames_per_step_per_gpu": nf, "points_per_step_per_gpu": total_pts,
+            "stages": stages_txt, "l2": f"inputs ({16 * total_pts / 1e6:.0f} MB/step) larger than the 126 MB L2, no flush",
+            "parallelism": f"frame-sharded x{world}, no data-path collective"}
+
+
+def stages_text(opts):
+    return ("" if opts["stages"] in ("ringless", "ring_field") else "ring+") + "dror+segment+cluster+hulls"
+
+
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return 0
     frames, workload, data_desc, opts = load_frames(args.frames, args.workload)
-    if not opts["cpu"]:
-        print(json.dumps({"impl": "reference", "unavailable":
-                          f"workload {workload}: the reference Clusterer's fixed 200k-voxel table overflows"}), flush=True)
-        return 0
     cores = host_cores()
-    per_step = min(len(frames), 2 * cores)
+    per_step = len(frames)  # the whole batch of our arm: same config
     cpu = CpuReference(cores, per_step, args.workload)
     for _ in range(min(args.warmup, 1)):
         cpu.run(range(per_step))
     t = 0.0
     for _ in range(args.steps):
-        t += cpu.run(range(per_step))
+        t += cpu.run(range(per_step))[0]
     cpu.close()
     fps = per_step * args.steps / t
+    total_pts = sum(f.shape[0] for f in frames)
     desc = (f"{per_step} frames of {workload} per step through the reference's own CPU code "
-            f"(oracle/_ref: unmodified segmenter/clusterer/noise_remover sources; ring partition and hull "
+            f"(oracle/_ref: unmodified segmenter/clusterer/noise_remover sources, DROR as built; ring partition and hull "
             f"gather restated) on {cores} worker processes")
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": data_desc,
-        "config": {"workload": workload, "frames_per_step": per_step, "stages": "ring+dror+segment+cluster+hulls",
-                   "host_threads": cores},
+        "config": step_config(workload, per_step, total_pts, stages_text(opts), world),
+        "points_per_s": total_pts * args.steps / t,
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": cpu.kind, "sample": desc},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -374,6 +425,300 @@ def run_reference_arm(args, rank, world):
 # --------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------
+class Measure:
+    """Everything measured for one workload on this rank (times in seconds; reduced over ranks later)."""
+
+    def __init__(self):
+        self.t = {}      # name -> seconds (MAX over ranks)
+        self.info = {}   # rank-0 facts
+
+
+def make_ctx_factory(lpl, device, max_pts, img_h):
+    def make_ctx(max_frames):
+        c = lpl.Context(device, max_points=max_pts, max_frames=max_frames, image_height=img_h)
+        if img_h != 64:
+            cfg = c.segmenter_default_cfg()
+            cfg.image_height = img_h
+            c.segmenter_config(cfg)
+        c.cluster_config(range_m=0.4, az_deg=1.0, el_deg=3.0, min_size=3)  # processor.param.yaml:31-35
+        return c
+
+    return make_ctx
+
+
+def measure_workload(lpl, args, frames, rings, opts, device, rank, barrier, steps, warmup, full: bool, e2e_seconds: float):
+    """Device-resident steps, (full: per-kernel profile pass), e2e through host buffers, single-frame latency."""
+    m = Measure()
+    nf = len(frames)
+    max_pts = max(f.shape[0] for f in frames)
+    stages = lpl.STAGE_ALL
+    if opts["stages"] in ("ringless", "ring_field"):
+        stages = lpl.STAGE_ALL & ~lpl.STAGE_RING
+    img_h = opts["image_height"]
+    make_ctx = make_ctx_factory(lpl, device, max_pts, img_h)
+    ctx = make_ctx(nf)
+    ctx.upload(frames, rings=rings)
+    ctx.sync(nf)
+    for _ in range(warmup):
+        ctx.run(nf, stages)
+    ctx.sync(nf)
+    sampler = ClockSampler(device) if full else None
+    barrier()
+    if sampler:
+        sampler.start()
+    ctx.launch_count(reset=True)
+    t_wall = time.perf_counter()
+    ctx.timer_start()
+    for _ in range(steps):
+        ctx.run(nf, stages)
+    m.t["value"] = ctx.timer_stop_ms() * 1e-3
+    barrier()
+    m.info["wall_s_timed_region"] = time.perf_counter() - t_wall
+    if sampler:
+        m.info["clocks"] = sampler.stop()
+    m.info["launches"] = ctx.launch_count()
+    ctx.sync(nf)
+    if full:
+        # second pass of the same K steps with an event behind every kernel (the events cost ~0.3 ms per step,
+        # which is why `value` is timed without them)
+        prof = {}
+        ctx.profile(True)
+        ctx.timer_start()
+        for _ in range(steps):
+            ctx.run(nf, stages)
+            for name, ms in ctx.profile_read():
+                a = prof.setdefault(name, [0.0, 0])
+                a[0] += ms
+                a[1] += 1
+        m.info["profiled_ms_total"] = ctx.timer_stop_ms()
+        ctx.profile(False)
+        ctx.sync(nf)
+        m.info["prof"] = prof
+        m.info["stats"] = batch_stats(ctx, nf)
+    m.info["ctx"] = ctx
+    m.info["stages"] = stages
+    m.info["make_ctx"] = make_ctx
+    m.info["max_pts"] = max_pts
+    return m
+
+
+def run_e2e(lpl, frames, device, args, barrier, stages, img_h, rings, steps, min_seconds, xyz12=True, n_ctx=None):
+    """Upload (pinned host -> device) + run + packed download through the package's FramePipeline
+    (n_ctx contexts / CUDA streams rotating over the step's batch). Steps are repeated until the timed region
+    lasts min_seconds. Returns dict(seconds, steps, h2d, d2h)."""
+    from lidar_processing_v2_b200.stream import FramePipeline
+
+    nf = len(frames)
+    max_pts = max(f.shape[0] for f in frames)
+    n_ctx = n_ctx or args.e2e_ctx
+    pipe = FramePipeline(device, max_pts, nf, stages=stages, n_ctx=n_ctx, image_height=img_h)
+    pinned = []
+    ring_views = None
+    counts = np.array([f.shape[0] for f in frames], np.uint32)
+    width = 3 if (xyz12 and rings is None) else 4
+    buf = lpl.PinnedBuffer((int(counts.sum()), width), np.float32)
+    pinned.append(buf)
+    views, o = [], 0
+    for f in frames:
+        buf.array[o:o + f.shape[0]] = f[:, :width]
+        views.append(buf.array[o:o + f.shape[0]])
+        o += f.shape[0]
+    if rings is not None:
+        rbuf = lpl.PinnedBuffer((int(counts.sum()),), np.uint16)
+        pinned.append(rbuf)
+        ring_views, o = [], 0
+        for r in rings:
+            rbuf.array[o:o + r.shape[0]] = r
+            ring_views.append(rbuf.array[o:o + r.shape[0]])
+            o += r.shape[0]
+
+    def run_steps(k):
+        for _ in range(k):
+            if rings is not None:
+                pipe.submit(views, rings=ring_views)  # per-frame copies: points + ring field
+            else:
+                pipe.submit(None, packed=(buf.array, counts))  # returns (and thereby downloads) the batch this slot held before
+        pipe.drain()
+
+    run_steps(max(args.warmup, n_ctx))
+    t0 = time.perf_counter()
+    run_steps(2 * n_ctx)
+    est = (time.perf_counter() - t0) / (2 * n_ctx)  # includes one pipeline fill / drain: an over-estimate
+    k = max(steps, int(np.ceil(1.6 * min_seconds / max(est, 1e-6))))
+    barrier()
+    pipe.h2d_bytes = pipe.d2h_bytes = 0
+    t0 = time.perf_counter()
+    run_steps(k)
+    barrier()
+    secs = time.perf_counter() - t0
+    out = {"seconds": secs, "steps": k, "h2d": pipe.h2d_bytes // k, "d2h": pipe.d2h_bytes // k}
+    pipe.close()
+    for b in pinned:
+        b.close()
+    return out
+
+
+def run_latency(lpl, frames, device, stages, max_pts, make_ctx, rings=None):
+    ctx = make_ctx(1)
+    stride = ((max_pts + 2047) // 2048) * 2048
+    out = lpl.PackedBuffers(1, stride * 12)
+    width = 3 if rings is None else 4
+    pin = lpl.PinnedBuffer((max_pts, width), np.float32)
+    ts = []
+    sel = list(range(min(64, len(frames)))) + list(range(min(8, len(frames))))
+    for k in sel:
+        f = frames[k]
+        v = pin.array[: f.shape[0]]
+        v[:] = f[:, :width]
+        cn = np.array([f.shape[0]], np.uint32)
+        t0 = time.perf_counter()
+        if rings is None:
+            ctx.upload_packed_xyz(v, cn)
+        else:
+            ctx.upload([v], rings=[rings[k]])
+        ctx.run(1, stages)
+        ctx.download_packed(1, out)
+        ts.append((time.perf_counter() - t0) * 1e3)
+    ts = np.array(ts[min(8, len(ts) // 2):])
+    ctx.close()
+    out.close()
+    pin.close()
+    return {"p50": float(np.percentile(ts, 50)), "p95": float(np.percentile(ts, 95)), "frames": int(ts.size),
+            "what": "batch of 1: pinned H2D + all stages + labels/clusters/hulls D2H"}
+
+
+def run_stream_workload(lpl, args, device, rank, world, barrier):
+    """BASELINE.json configs[3]: ONE stream of 8,192 synthetic HDL-64E frames, contiguous blocks per rank
+    (stream.shard_range), every rank streaming its block from pinned host memory through its own FramePipeline
+    (12-byte uploads, packed downloads). Returns (seconds, info)."""
+    from lidar_processing_v2_b200.stream import FramePipeline, shard_range
+    from tools import frames as F
+
+    total = args.stream_frames
+    a, b = shard_range(total, rank, world)
+    batch = args.stream_batch
+    scenes = [F.synth_scan(4000 + i)[0] for i in range(32)]     # frame k of the stream = scene k % 32
+    max_pts = max(s.shape[0] for s in scenes)
+    # pinned pool: two packed batches (the scenes of frames a .. a + batch and the next batch), reused in turn
+    pool = []
+    for j in range(2):
+        ids = [(a + j * batch + k) % 32 for k in range(batch)]
+        cn = np.array([scenes[i].shape[0] for i in ids], np.uint32)
+        buf = lpl.PinnedBuffer((int(cn.sum()), 3), np.float32)
+        o = 0
+        for i in ids:
+            buf.array[o:o + scenes[i].shape[0]] = scenes[i][:, :3]
+            o += scenes[i].shape[0]
+        pool.append((buf, cn))
+    pipe = FramePipeline(device, max_pts, batch, n_ctx=args.e2e_ctx)
+    stats = dict(frames=0, points=0, clusters=0, hull_vertices=0)
+
+    def account(res):
+        if res is not None:
+            counts = res[0]
+            stats["frames"] += int(counts.shape[1])
+            stats["points"] += int(counts[0].sum())
+            stats["clusters"] += int(counts[3].sum())
+            stats["hull_vertices"] += int(counts[4].sum())
+
+    def go(lo, hi, acc):
+        j = 0
+        for s0 in range(lo, hi, batch):
+            nb = min(batch, hi - s0)
+            buf, cn = pool[j & 1]
+            j += 1
+            npts = int(cn[:nb].sum())
+            r = pipe.submit(None, packed=(buf.array[:npts], cn[:nb]))
+            if acc:
+                account(r)
+        for r in pipe.drain():
+            if acc:
+                account(r)
+
+    go(a, min(b, a + args.e2e_ctx * batch), False)  # warm-up: every context once
+    barrier()
+    pipe.h2d_bytes = pipe.d2h_bytes = 0
+    t0 = time.perf_counter()
+    go(a, b, True)
+    barrier()
+    secs = time.perf_counter() - t0
+    info = dict(stats, h2d_bytes=pipe.h2d_bytes, d2h_bytes=pipe.d2h_bytes, shard=[a, b], batch=batch)
+    pipe.close()
+    for buf, _ in pool:
+        buf.close()
+    return secs, info
+
+
+def parity_block(lpl, ctx, nf, frames, workload, args, stages, cores):
+    """The timed batch against the reference's CPU code (exact DROR semantics: the GPU's), all frames; plus the
+    delta of the reference as built (as-is DROR) on a sample. Also times both legs (cpu_baseline)."""
+    bufs = lpl.PackedBuffers(nf, nf * ctx.max_points * 8 + (1 << 20),
+                             want=("labels_u8", "noise", "cluster_labels", "hull_offsets", "hull_xy"))
+    ctx.run(nf, stages)
+    counts = ctx.download_packed(nf, bufs)
+    cpu = CpuReference(cores, nf, args.workload)
+    n_exact = nf
+    secs_exact, res = cpu.run(range(n_exact), mode="exact", want=True)
+    mism = dict(noise=0, labels=0, cluster_labels=0, cluster_frames=0, hull_frames=0)
+    for f in range(n_exact):
+        e = res[f]
+        g_noise, g_lab = bufs.frame("noise", f), bufs.frame("labels_u8", f)
+        mism["noise"] += int((g_noise != e["noise"]).sum())
+        mism["labels"] += int((g_lab != e["labels"]).sum())
+        g_cl = bufs.frame("cluster_labels", f)
+        same_cl = g_cl.shape == e["cluster_labels"].shape and np.array_equal(g_cl, e["cluster_labels"])
+        if not same_cl:
+            mism["cluster_frames"] += 1
+            mism["cluster_labels"] += int((g_cl != e["cluster_labels"]).sum()) if g_cl.shape == e["cluster_labels"].shape else int(g_cl.size)
+        g_off, g_xy = bufs.frame("hull_offsets", f), bufs.frame("hull_xy", f)
+        same_h = (g_off.shape == e["hull_offsets"].shape and np.array_equal(g_off, e["hull_offsets"])
+                  and g_xy.shape == e["hull_xy"].shape and (np.abs(g_xy - e["hull_xy"]).max(initial=0.0) <= 1e-5))
+        mism["hull_frames"] += 0 if same_h else 1
+    ns = min(nf, 4 * cores)
+    secs_as_is, res_a = cpu.run(range(ns), mode="as_is", want=True)
+    d_noise = sum(int((res_a[f]["noise"] != res[f]["noise"]).sum()) for f in range(ns))
+    d_lab = sum(int((res_a[f]["labels"] != res[f]["labels"]).sum()) for f in range(ns))
+    kind = cpu.kind
+    cpu.close()
+    bufs.close()
+    parity = {"frames_checked": n_exact, "points_checked": int(counts[0].sum()),
+              "against": f"oracle/_ref ({kind}), DROR exact semantics (SURVEY H1), chained pipeline",
+              "dror_mask_mismatches": mism["noise"], "label_mismatches": mism["labels"],
+              "cluster_label_mismatches": mism["cluster_labels"], "frames_with_cluster_mismatch": mism["cluster_frames"],
+              "frames_with_hull_mismatch": mism["hull_frames"], "hull_tolerance_m": 1e-5,
+              "near_threshold_points": 0,
+              "dror_as_is_delta": {"frames": ns, "noise_points": d_noise, "label_points": d_lab,
+                                   "what": "points whose DROR verdict / final label differ between the reference as built "
+                                           "(stale KD-tree stack, one-directional) and exact semantics"}}
+    base = {"value": ns / secs_as_is, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"first {ns} frames of {workload}, whole chained pipeline, DROR as built, {cores} worker processes, {secs_as_is:.1f} s",
+            "exact_dror": {"value": n_exact / secs_exact, "frames": n_exact, "seconds": secs_exact,
+                           "what": "same chain with the stack-drained (exact) DROR the GPU implements"}}
+    return parity, base
+
+
+def light_parity(lpl, ctx, frames, rings, opts, stages, nchk):
+    """First nchk frames of a synthetic workload against the port (chained, exact DROR)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import parity as P
+    from oracle.oracle import PortOracle, default_seg_cfg
+
+    port = PortOracle()
+    if opts["image_height"] != 64:
+        port.segment_config(default_seg_cfg(image_height=opts["image_height"]))
+    nchk = min(nchk, len(frames))
+    ctx.upload(frames[:nchk], rings=None if rings is None else rings[:nchk])
+    ctx.run(nchk, stages)
+    ctx.sync(nchk)
+    bad = 0
+    for f in range(nchk):
+        ring = None if opts["stages"] == "ringless" else (rings[f] if rings is not None else "partition")
+        exp = P.oracle_chain(port, frames[f], dror=True, ring=ring)
+        rep = P.chain_report(ctx.download(f), exp, skip=("ring",) if ring is None else ())
+        bad += sum(1 for v in rep.values() if v != 0)
+    return {"frames_checked": nchk, "mismatching_planes": bad, "against": "oracle/port.cpp (chained, exact DROR)"}
+
+
 def run_ours(args, rank, local_rank, world):
     import torch
 
@@ -394,6 +739,9 @@ def run_ours(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
+    times = {}  # name -> seconds on this rank; MAX-reduced over ranks at the end
+
+    # =========================== headline workload
     frames, workload, data_desc, opts = load_frames(args.frames, args.workload)
     # every rank runs the same number of frames; rotate the sequence so ranks do not share inputs
     rot = (rank * 19) % len(frames)
@@ -402,219 +750,169 @@ def run_ours(args, rank, local_rank, world):
     if rings is not None:
         rings = rings[rot:] + rings[:rot]
     nf = len(frames)
-    max_pts = max(f.shape[0] for f in frames)
-    stages = lpl.STAGE_ALL
-    if opts["stages"] in ("ringless", "ring_field"):
-        stages = lpl.STAGE_ALL & ~lpl.STAGE_RING
+    total_pts = sum(f.shape[0] for f in frames)
+    m = measure_workload(lpl, args, frames, rings, opts, local_rank, rank, barrier, args.steps, args.warmup, True, 2.0)
+    times["value"] = m.t["value"]
+    ctx, stages, make_ctx, max_pts = m.info["ctx"], m.info["stages"], m.info["make_ctx"], m.info["max_pts"]
     img_h = opts["image_height"]
 
-    def make_ctx(max_frames):
-        c = lpl.Context(local_rank, max_points=max_pts, max_frames=max_frames, image_height=img_h)
-        if img_h != 64:
-            cfg = c.segmenter_default_cfg()
-            cfg.image_height = img_h
-            c.segmenter_config(cfg)
-        c.cluster_config(range_m=0.4, az_deg=1.0, el_deg=3.0, min_size=3)  # processor.param.yaml:31-35
-        return c
+    parity = cpu_baseline = None
+    if world == 1 and not args.no_cpu:
+        parity, cpu_baseline = parity_block(lpl, ctx, nf, frames, workload, args, stages, host_cores())
+    ctx.close()
 
-    ctx = make_ctx(nf)
-    total_pts = sum(f.shape[0] for f in frames)
-
-    # ---- device-resident throughput ("value")
-    ctx.upload(frames, rings=rings)
-    ctx.sync(nf)
-    for _ in range(args.warmup):
-        ctx.run(nf, stages)
-    ctx.sync(nf)
-    sampler = ClockSampler(local_rank)
-    ctx.profile(True)
-    prof = {}
-    barrier()
-    sampler.start()
-    ctx.launch_count(reset=True)
-    t_wall = time.perf_counter()
-    ctx.timer_start()
-    for _ in range(args.steps):
-        ctx.run(nf, stages)
-        # per-kernel events of this step; reading them waits for the step (the stream itself stays
-        # busy: the next run is enqueued right after)
-        for name, ms in ctx.profile_read():
-            a = prof.setdefault(name, [0.0, 0])
-            a[0] += ms
-            a[1] += 1
-    ms_total = ctx.timer_stop_ms()
-    barrier()
-    t_wall = time.perf_counter() - t_wall
-    clocks = sampler.stop()
-    launches = ctx.launch_count()
-    ctx.profile(False)
-    ctx.sync(nf)
-    stats = batch_stats(ctx, nf)
-
-    # ---- end to end through the C ABI with host buffers ("e2e")
-    e2e = run_e2e(lpl, ctx, frames, local_rank, args, barrier, stages, img_h, rings)
-
-    # ---- p50 latency of single-frame batches (H2D -> all results on the host)
+    e2e = run_e2e(lpl, frames, local_rank, args, barrier, stages, img_h, rings, args.steps, args.e2e_seconds)
+    times["e2e"] = e2e["seconds"]
+    e2e16 = None
+    if rings is None:
+        e2e16 = run_e2e(lpl, frames, local_rank, args, barrier, stages, img_h, rings, max(2, args.steps // 4), 0.5, xyz12=False)
+        times["e2e16"] = e2e16["seconds"]
     lat = run_latency(lpl, frames, local_rank, stages, max_pts, make_ctx, rings) if rank == 0 else None
 
-    t_ms = torch.tensor([ms_total, e2e["seconds"] * 1e3], dtype=torch.float64, device="cuda")
+    # =========================== the other BASELINE.json shapes (brief)
+    extra = {}
+    if args.workload is None and not args.no_extra:
+        for wl in ("synth64", "synth128", "cloud2m"):
+            fr, _, desc, op = load_frames(None, wl)
+            rg = op["rings"]
+            r2 = (rank * 5) % len(fr)
+            fr = fr[r2:] + fr[:r2]
+            if rg is not None:
+                rg = rg[r2:] + rg[:r2]
+            mm = measure_workload(lpl, args, fr, rg, op, local_rank, rank, barrier, args.extra_steps, 3, False, 0.5)
+            times[wl + ".value"] = mm.t["value"]
+            c2 = mm.info["ctx"]
+            par = light_parity(lpl, c2, fr, rg, op, mm.info["stages"], 1 if wl == "cloud2m" else 2) if (rank == 0 and not args.no_cpu) else None
+            c2.close()
+            ee = run_e2e(lpl, fr, local_rank, args, barrier, mm.info["stages"], op["image_height"], rg, args.extra_steps, 0.5,
+                         n_ctx=2 if wl == "cloud2m" else None)
+            times[wl + ".e2e"] = ee["seconds"]
+            la = run_latency(lpl, fr, local_rank, mm.info["stages"], mm.info["max_pts"], mm.info["make_ctx"], rg) if rank == 0 else None
+            extra[wl] = dict(frames=len(fr), points=sum(f.shape[0] for f in fr), steps=args.extra_steps, e2e_steps=ee["steps"],
+                             h2d=ee["h2d"], d2h=ee["d2h"], lat=la, parity=par, data=desc, stages=stages_text(op))
+        secs, info = run_stream_workload(lpl, args, local_rank, rank, world, barrier)
+        times["stream.e2e"] = secs
+        extra["stream"] = info
+
+    # =========================== reduce over ranks
+    keys = sorted(times)
+    t = torch.tensor([times[k] for k in keys], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([float(extra.get("stream", {}).get(k, 0)) for k in ("frames", "points", "clusters", "hull_vertices", "h2d_bytes", "d2h_bytes")]
+                       + [float(nf * e2e["steps"]), float(nf * e2e16["steps"]) if e2e16 else 0.0]
+                       + [float(extra[w]["frames"] * extra[w]["e2e_steps"]) if w in extra else 0.0 for w in ("synth64", "synth128", "cloud2m")],
+                       dtype=torch.float64, device="cuda")
     if dist is not None:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms_max, e2e_ms_max = float(t_ms[0]), float(t_ms[1])
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)  # NCCL only carries statistics
+    tmax = dict(zip(keys, t.tolist()))
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return 0
 
-    value = world * nf * args.steps / (ms_max * 1e-3)
-    e2e_value = world * nf * args.steps / (e2e_ms_max * 1e-3)
+    ms_max = tmax["value"] * 1e3
+    value = world * nf * args.steps / tmax["value"]
+    e2e_value = cnt[6].item() / tmax["e2e"]  # every rank sizes its own step count: frames summed over ranks / slowest rank
 
-    # ---- roofline of the dominant kernel
-    import json as _json
-
+    # ---- roofline of the dominant kernel + stage table
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
-        peak = float(_json.load(open(peaks_path))["hbm_gbs"])
+        peak = float(json.load(open(peaks_path))["hbm_gbs"])
         peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)"
     else:
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
-    kernels = []
-    for name, (ms, cnt) in prof.items():
-        per_launch_ms = ms / cnt
-        by = algorithmic_bytes(name, stats)
-        kernels.append({"kernel": name, "launches": cnt, "ms_per_launch": per_launch_ms,
-                        "share": ms / (ms_total if ms_total > 0 else 1.0),
-                        "alg_bytes_per_launch": by, "gbs": by / (per_launch_ms * 1e6) if per_launch_ms > 0 else 0.0,
-                        "frac_of_hbm_peak": (by / (per_launch_ms * 1e6) / peak) if per_launch_ms > 0 else 0.0})
-    # kernels launched twice per step under one name (two-pass compactions) are merged above
+    stats, prof = m.info["stats"], m.info["prof"]
+    prof_total = m.info["profiled_ms_total"]
+    kernels, stage_ms = [], {}
+    for name, (ms, cnt_) in prof.items():
+        # kernels launched several times per step under one name (two-pass compactions, merge passes) are merged:
+        # time per STEP against the bytes of one step
+        per_step_ms = ms / args.steps
+        by = algorithmic_bytes(name, stats) * (cnt_ / args.steps if name in ("hull_merge",) else 1.0)
+        kernels.append({"kernel": name, "launches": cnt_, "ms_per_step": per_step_ms, "ms_per_launch": ms / cnt_,
+                        "share": ms / (prof_total if prof_total > 0 else 1.0),
+                        "alg_bytes_per_step": by, "gbs": by / (per_step_ms * 1e6) if per_step_ms > 0 else 0.0,
+                        "frac_of_hbm_peak": (by / (per_step_ms * 1e6) / peak) if per_step_ms > 0 else 0.0})
+        stage_ms[stage_of(name)] = stage_ms.get(stage_of(name), 0.0) + per_step_ms
     kernels.sort(key=lambda k: -k["share"])
     top = kernels[0]
-    roofline = {"bound": "hbm", "kernel": top["kernel"], "achieved": top["gbs"], "peak": peak, "unit": "GB/s",
-                "frac": top["gbs"] / peak, "traffic": None, "peak_source": peak_src,
-                "share_of_step": top["share"], "ms_per_launch": top["ms_per_launch"],
-                "note": "sequential sub-steps (JCP relaxation, hull chains, RECM scans) are latency-bound; see "
-                        "DESIGN.md and profiles/ for stall counters"}
+    traffic = None
     traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_path):
         try:
-            roofline["traffic"] = _json.load(open(traffic_path)).get(top["kernel"])
+            traffic = json.load(open(traffic_path)).get(top["kernel"])
         except Exception:
             pass
-
-    # ---- CPU baseline on this box's host cores (bounded sample)
-    cpu_baseline = None
-    if world == 1 and not args.no_cpu and opts["cpu"]:
-        cores = host_cores()
-        ns = min(nf, 4 * cores)
-        cpu = CpuReference(cores, ns, args.workload)
-        secs = cpu.run(range(ns))
-        cpu.close()
-        cpu_baseline = {"value": ns / secs, "unit": UNIT, "cores": cores, "kind": cpu.kind,
-                        "sample": f"first {ns} frames of {workload} (unrotated), whole chained pipeline, "
-                                  f"{cores} worker processes, {secs:.1f} s"}
+    roofline = {"bound": "hbm", "kernel": top["kernel"], "achieved": top["gbs"], "peak": peak, "unit": "GB/s",
+                "frac": top["gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
+                "share_of_step": top["share"], "ms_per_launch": top["ms_per_launch"],
+                "measured": f"CUDA events behind every kernel, second pass of the same {args.steps} steps "
+                            f"({prof_total / args.steps:.3f} ms/step with the events, {ms_max / args.steps:.3f} without)",
+                "note": "sequential sub-steps (JCP sweep, hull chains, RECM scans) are latency-bound; see "
+                        "DESIGN.md and profiles/ for stall counters"}
+    sb = stage_bytes(stats)
+    stages_tbl = {k: {"ms_per_step": round(v, 4), "alg_bytes_per_step": sb.get(k), "gbs": round(sb[k] / (v * 1e6), 1) if k in sb and v > 0 else None,
+                      "frac_of_hbm_peak": round(sb[k] / (v * 1e6) / peak, 4) if k in sb and v > 0 else None}
+                  for k, v in sorted(stage_ms.items())}
+    whole = sum(v for k, v in sb.items() if k in stage_ms)
+    stages_tbl["whole step"] = {"ms_per_step": round(ms_max / args.steps, 4), "alg_bytes_per_step": whole,
+                                "gbs": round(whole / (ms_max / args.steps * 1e6), 1),
+                                "frac_of_hbm_peak": round(whole / (ms_max / args.steps * 1e6) / peak, 4)}
 
     if os.environ.get("LPL_BENCH_KERNELS"):
         with open(os.environ["LPL_BENCH_KERNELS"], "w") as fh:
-            _json.dump(kernels, fh, indent=1)
+            json.dump(kernels, fh, indent=1)
+    layout = "12 B/pt std::array<float,3> (NoiseRemover::filter input), one transfer per batch" if rings is None else \
+        "16 B/pt + ring field, per-frame copies"
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": data_desc,
-        "config": {"workload": workload, "frames_per_step_per_gpu": nf, "points_per_step_per_gpu": total_pts,
-                   "stages": ("ring+" if stages & lpl.STAGE_RING else "") + "dror+segment+cluster+hulls", "l2": f"inputs ({16 * total_pts / 1e6:.0f} MB/step) larger than the 126 MB L2, no flush",
-                   "parallelism": f"frame-sharded x{world}, no data-path collective"},
-        "points_per_s": world * total_pts * args.steps / (ms_max * 1e-3),
-        "clocks": clocks,
+        "config": step_config(workload, nf, total_pts, stages_text(opts), world),
+        "points_per_s": world * total_pts * args.steps / tmax["value"],
+        "clocks": m.info["clocks"],
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
-                "pipelining": f"{args.e2e_parts} part-batches per step over {args.e2e_ctx} contexts (streams) in rotation, pinned host memory"},
-        "gpu_launches": int(launches),
+                "steps": e2e["steps"], "seconds": tmax["e2e"], "upload": layout,
+                "download": "labels_u8 + cluster_labels + hull offsets / vertices + z extents, one packed transfer per batch",
+                "pipelining": f"{args.e2e_ctx} contexts (CUDA streams) in rotation, pinned host memory"},
+        "gpu_launches": int(m.info["launches"]),
         "roofline": roofline,
-        "kernels": [{k: (round(v, 6) if isinstance(v, float) else v) for k, v in kk.items()} for kk in kernels[:20]],
+        "stages": stages_tbl,
+        "kernels": [{k: (round(v, 6) if isinstance(v, float) else v) for k, v in kk.items()} for kk in kernels[:24]],
         "latency_ms": lat,
-        "wall_s_timed_region": t_wall,
+        "wall_s_timed_region": m.info["wall_s_timed_region"],
     }
+    if e2e16 is not None:
+        line["e2e_pcl16"] = {"value": cnt[7].item() / tmax["e2e16"], "unit": UNIT, "h2d_bytes_per_step": e2e16["h2d"],
+                             "d2h_bytes_per_step": e2e16["d2h"], "upload": "16 B/pt PCL PointXYZ layout, one transfer per batch"}
+    if parity is not None:
+        line["parity"] = parity
     if cpu_baseline is not None:
         line["cpu_baseline"] = cpu_baseline
+    if extra:
+        wl_out = {}
+        for wi, wl in enumerate(("synth64", "synth128", "cloud2m")):
+            e = extra[wl]
+            wl_out[wl] = {"value": world * e["frames"] * e["steps"] / tmax[wl + ".value"], "unit": UNIT,
+                          "points_per_s": world * e["points"] * e["steps"] / tmax[wl + ".value"],
+                          "ms_per_step": 1e3 * tmax[wl + ".value"] / e["steps"], "frames_per_step_per_gpu": e["frames"],
+                          "e2e": cnt[8 + wi].item() / tmax[wl + ".e2e"],
+                          "h2d_bytes_per_step": e["h2d"], "d2h_bytes_per_step": e["d2h"],
+                          "latency_ms_p50": e["lat"]["p50"] if e["lat"] else None, "stages": e["stages"],
+                          "parity": e["parity"], "data": e["data"]}
+        st = extra["stream"]
+        frames_all, pts_all = cnt[0].item(), cnt[1].item()
+        wl_out["stream8192"] = {"value": frames_all / tmax["stream.e2e"], "unit": UNIT, "points_per_s": pts_all / tmax["stream.e2e"],
+                                "frames": int(frames_all), "seconds": tmax["stream.e2e"], "scaling": "strong (one stream, contiguous blocks per rank)",
+                                "clusters": int(cnt[2].item()), "hull_vertices": int(cnt[3].item()),
+                                "h2d_bytes": int(cnt[4].item()), "d2h_bytes": int(cnt[5].item()), "batch": st["batch"],
+                                "inputs": "streamed over PCIe from pinned host memory (12 B/pt), results read back; "
+                                          "32 distinct seeded scenes cycled, two pinned batches per rank reused in turn"}
+        line["workloads"] = wl_out
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
     return 0
-
-
-def run_e2e(lpl, ctx0, frames, device, args, barrier, stages, img_h=64, rings=None):
-    """Upload (pinned host -> device) + run + batch download through the package's FramePipeline
-    (args.e2e_ctx contexts / CUDA streams rotating over args.e2e_parts part-batches of the step)."""
-    from lidar_processing_v2_b200.stream import FramePipeline
-
-    nf = len(frames)
-    max_pts = max(f.shape[0] for f in frames)
-    n_parts, n_ctx = args.e2e_parts, args.e2e_ctx
-    per = (nf + n_parts - 1) // n_parts
-    pipe = FramePipeline(device, max_pts, per, stages=stages, n_ctx=n_ctx, image_height=img_h)
-    parts = [frames[a:a + per] for a in range(0, nf, per)]
-    pinned, views, packed, ring_views = [], [], [], []
-    for a in range(0, nf, per) if rings is not None else ():
-        rbuf = lpl.PinnedBuffer((sum(r.shape[0] for r in rings[a:a + per]),), np.uint16)
-        rv, o = [], 0
-        for r in rings[a:a + per]:
-            rbuf.array[o:o + r.shape[0]] = r
-            rv.append(rbuf.array[o:o + r.shape[0]])
-            o += r.shape[0]
-        pinned.append(rbuf)
-        ring_views.append(rv)
-    for part in parts:
-        buf = lpl.PinnedBuffer((sum(f.shape[0] for f in part), 4), np.float32)
-        v, o = [], 0
-        for f in part:
-            buf.array[o:o + f.shape[0]] = f
-            v.append(buf.array[o:o + f.shape[0]])
-            o += f.shape[0]
-        pinned.append(buf)
-        views.append(v)
-        # the frames of a part-batch lie back to back in pinned memory: one H2D transfer per batch
-        packed.append((buf.array, np.array([f.shape[0] for f in part], np.uint32)))
-
-    def run_steps(k):
-        for _ in range(k):
-            for i in range(len(views)):
-                if rings is not None:
-                    pipe.submit(views[i], rings=ring_views[i])  # per-frame copies: points + ring field
-                    continue
-                pipe.submit(views[i], packed=packed[i])  # returns (and thereby downloads) the batch this slot held before
-        pipe.drain()
-
-    run_steps(max(args.warmup, 1))
-    barrier()
-    pipe.h2d_bytes = pipe.d2h_bytes = 0
-    t0 = time.perf_counter()
-    run_steps(args.steps)
-    barrier()
-    secs = time.perf_counter() - t0
-    h2d, d2h = pipe.h2d_bytes // args.steps, pipe.d2h_bytes // args.steps
-    pipe.close()
-    return {"seconds": secs, "h2d": h2d, "d2h": d2h}
-
-
-def run_latency(lpl, frames, device, stages, max_pts, make_ctx, rings=None):
-    ctx = make_ctx(1)
-    stride = ((max_pts + 2047) // 2048) * 2048
-    out = lpl.BatchBuffers(1, stride)
-    pin = lpl.PinnedBuffer((max_pts, 4), np.float32)
-    ts = []
-    sel = list(range(min(64, len(frames)))) + list(range(min(8, len(frames))))
-    for k in sel:
-        f = frames[k]
-        v = pin.array[: f.shape[0]]
-        v[:] = f
-        t0 = time.perf_counter()
-        ctx.upload([v], rings=None if rings is None else [rings[k]])
-        ctx.run(1, stages)
-        ctx.download_batch(1, out)
-        ts.append((time.perf_counter() - t0) * 1e3)
-    ts = np.array(ts[min(8, len(ts) // 2):])
-    ctx.close()
-    return {"p50": float(np.percentile(ts, 50)), "p95": float(np.percentile(ts, 95)), "frames": int(ts.size),
-            "what": "batch of 1: pinned H2D + all stages + labels/clusters/hulls D2H"}
 
 
 def main():
@@ -624,11 +922,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=WORKLOADS,
-                    help="default: kitti154 (BASELINE.json configs[1]); the synthetic shapes are configs[2..4]")
+                    help="default: kitti154 (BASELINE.json configs[1]) + the synthetic shapes under 'workloads'")
     ap.add_argument("--frames", type=int, default=None, help="frames per batch (default: the whole sequence)")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--e2e-parts", type=int, default=1, help="part-batches one step is split into on the e2e path")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity legs")
+    ap.add_argument("--no-extra", action="store_true", help="skip the synthetic workloads of the default run")
+    ap.add_argument("--extra-steps", type=int, default=5)
+    ap.add_argument("--e2e-seconds", type=float, default=2.0, help="minimum length of the e2e timed region")
     ap.add_argument("--e2e-ctx", type=int, default=4, help="contexts (CUDA streams) the e2e path rotates over")
+    ap.add_argument("--stream-frames", type=int, default=STREAM_FRAMES)
+    ap.add_argument("--stream-batch", type=int, default=64)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

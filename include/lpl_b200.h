@@ -22,6 +22,7 @@
  *   lpl_pipeline_*          Processor::run (segment -> split -> cluster -> hulls), batched
  *                                                              src/processor/src/processor.cpp:552-663
  *   lpl_pipeline_upload_cloud2  convert<PointT>(PointCloud2)   src/processor/src/processor.cpp:42-179
+ *   lpl_pipeline_upload_packed_xyz  the std::array<float,3> cloud of NoiseRemover::filter   .../noise_remover.hpp:68
  *   lpl_pcd_read            pcl::io::loadPCDFile<PointXYZI>    src/dataloader/src/dataloader.cpp:165
  */
 #ifndef LPL_B200_H
@@ -188,6 +189,10 @@ int lpl_pipeline_upload_device(lpl_ctx* ctx, const lpl_frame* frames, uint32_t n
  * for the whole batch instead of one per frame; a kernel spreads the frames into place. No ring planes
  * (run with LPL_STAGE_RING, or ring-less). */
 int lpl_pipeline_upload_packed(lpl_ctx* ctx, const float* xyzw, const uint32_t* counts, uint32_t num_frames);
+/* Same with 12 bytes per point: x, y, z floats back to back - the std::vector<std::array<float, 3>> cloud that
+ * NoiseRemover::filter takes (noise_remover.hpp:68), the first library call of the chained pipeline. A quarter
+ * fewer bytes cross PCIe than with the 16-byte PCL layout. */
+int lpl_pipeline_upload_packed_xyz(lpl_ctx* ctx, const float* xyz, const uint32_t* counts, uint32_t num_frames);
 /* One frame as a sensor_msgs/PointCloud2 payload (what Processor::convert<PointT> reads,
  * src/processor/src/processor.cpp:42-179): height * width records, point_step bytes apart inside a
  * row, rows row_step bytes apart; x / y / z are float32 at the given byte offsets, ring (uint16) at
@@ -206,6 +211,11 @@ int lpl_pipeline_upload_cloud2(lpl_ctx* ctx, const lpl_cloud2_frame* frames, uin
 int lpl_pipeline_run(lpl_ctx* ctx, uint32_t num_frames, uint32_t stages);
 /* Wait for the stream; fails if any kernel raised a capacity flag. */
 int lpl_pipeline_sync(lpl_ctx* ctx, uint32_t num_frames);
+/* Wait for the stream and report the per-frame capacity flags of the last run: status_out[num_frames], 0 = the
+ * frame is good; bit 0 JCP queue, 1 RANSAC RNG table, 2 voxel hash, 3 / 4 JCP border rows / sweep. The batch
+ * downloads deliver every frame's planes and return LPL_ERR_CAPACITY when any frame is flagged: only the
+ * flagged frames' results are to be discarded. */
+int lpl_pipeline_status(lpl_ctx* ctx, uint32_t num_frames, uint32_t* status_out);
 
 /* Per-frame results of the last batch (host buffers, any pointer may be NULL to skip).
  * Copies are synchronous with respect to the context stream. */
@@ -252,6 +262,37 @@ typedef struct lpl_batch_result
     lpl_bbox* boxes;          /* one box per element (LPL_STAGE_BOXES)             */
 } lpl_batch_result;
 int lpl_pipeline_download_batch(lpl_ctx* ctx, uint32_t num_frames, lpl_batch_result* res);
+
+/* Results of the whole batch as ONE device-to-host transfer of exactly the occupied bytes: a kernel first packs
+ * the selected planes back to back on the device (frames of a plane follow each other without padding, planes
+ * start on 16-byte boundaries in the order of the LPL_PLANE_* bits). Frame f of a plane starts at
+ * offset[plane] + (sum of that plane's count over the frames before f) * element size, where the count is n for
+ * LABELS_U8 / NOISE / RING, num_obstacles for OBSTACLE_INDEX / CLUSTER_LABELS, num_clusters + 1 for HULL_OFFSETS,
+ * num_hull_vertices for HULL_INDICES / HULL_XY and num_clusters for ZMINMAX / BOXES - all in `counts`. */
+enum
+{
+    LPL_PLANE_LABELS_U8 = 1u << 0,      /* uint8  per input point: Label 0 / 1 / 2          */
+    LPL_PLANE_NOISE = 1u << 1,          /* uint8  per input point: NoiseRemoverLabel        */
+    LPL_PLANE_RING = 1u << 2,           /* uint16 per input point                           */
+    LPL_PLANE_OBSTACLE_INDEX = 1u << 3, /* uint32 per obstacle point (= positions of Label 2, ascending) */
+    LPL_PLANE_CLUSTER_LABELS = 1u << 4, /* int32  per obstacle point                        */
+    LPL_PLANE_HULL_OFFSETS = 1u << 5,   /* uint32, num_clusters + 1 per frame               */
+    LPL_PLANE_HULL_INDICES = 1u << 6,   /* uint32 per hull vertex                           */
+    LPL_PLANE_HULL_XY = 1u << 7,        /* 2 floats per hull vertex                         */
+    LPL_PLANE_ZMINMAX = 1u << 8,        /* 2 floats per cluster                             */
+    LPL_PLANE_BOXES = 1u << 9,          /* lpl_bbox per cluster (LPL_STAGE_BOXES)           */
+    LPL_PLANE_COUNT = 10
+};
+typedef struct lpl_packed_result
+{
+    uint32_t* counts;     /* [5][num_frames] = n, num_valid, num_obstacles, num_clusters, num_hull_vertices (required) */
+    void* buffer;         /* host buffer for the packed planes (pinned: lpl_host_alloc)                         */
+    size_t buffer_bytes;  /* its capacity                                                                       */
+    uint32_t planes;      /* LPL_PLANE_* bits to pack                                                           */
+    size_t offset[LPL_PLANE_COUNT]; /* out: byte offset of every selected plane in `buffer` ((size_t)-1 otherwise) */
+    size_t bytes_used;    /* out: bytes transferred                                                             */
+} lpl_packed_result;
+int lpl_pipeline_download_packed(lpl_ctx* ctx, uint32_t num_frames, lpl_packed_result* res);
 
 /* PCD v0.7 reader for the reference's data set (FIELDS x y z [intensity], float32, DATA binary or
  * ascii): fills xyzi_out[n][4] (intensity 0 when absent) and *n_out; xyzi_out == NULL only queries

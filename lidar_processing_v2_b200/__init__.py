@@ -19,6 +19,8 @@ from .native import (  # noqa: F401
     STAGE_RING,
     STAGE_SEGMENT,
     BatchBuffers,
+    PackedBuffers,
+    PLANES,
     ClusterCfg,
     Context,
     DrorCfg,

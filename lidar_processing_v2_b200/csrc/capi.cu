@@ -25,6 +25,7 @@ struct lpl_ctx
     int want_image = 0;
     int jcp_mode = LPL_JCP_AS_REFERENCE;
     int have_ring = 0; // ring plane of the current batch is meaningful
+    bool ran_hulls = false; // the last lpl_pipeline_run included LPL_STAGE_HULLS (hull_off is this batch's)
     std::vector<std::uint32_t> h_status;
 };
 
@@ -130,6 +131,7 @@ void carve(Dev& d, Carver& cv, int npx, int ncell_cap, std::uint32_t** mt_raw)
     cv.take(d.n_hull, B);
     cv.take(d.zmin_u, B * cap);
     cv.take(d.zmax_u, B * cap);
+    cv.take(d.zzero, B * cap);
     cv.take(d.ext, B * cap * kExtDirs);
     cv.take(d.octa, B * cap * kExtDirs);
     cv.take(d.hseg_cnt, B * cap);
@@ -287,6 +289,8 @@ void pack(void* dst, std::size_t dst_pitch, const void* src, std::size_t stride,
     }
 }
 
+// Syncs the stream and reads the per-frame status words. Returns LPL_ERR_CAPACITY (message names the first
+// flagged frame) when any frame raised a capacity bit; ctx->h_status keeps all of them (lpl_pipeline_status).
 int check_status(lpl_ctx* ctx, std::uint32_t nf)
 {
     Ctx& c = ctx->c;
@@ -341,7 +345,7 @@ __global__ void k_label_count(Dev d, std::uint32_t K)
             d.clabel[o + i] = -1;
         }
     }
-    accumulate_cluster_stats(d.ext + o * kExtDirs, d.zmin_u + o, d.zmax_u + o, l, x, y, z, i, true);
+    accumulate_cluster_stats(d.ext + o * kExtDirs, d.zmin_u + o, d.zmax_u + o, d.zzero + o, l, x, y, z, i, true);
 }
 
 __global__ void k_ext_init(Dev d, std::uint32_t K)
@@ -429,7 +433,15 @@ int lpl_create(lpl_ctx** out, int device, std::uint32_t max_points, std::uint32_
     d.B = max_frames;
     const int npx = H * W;
     d.ptiles = (npx + kTile - 1) / kTile;
-    d.qcap = static_cast<std::uint32_t>(npx / 2);
+    // the reference reserves H * W queue entries (segmenter.cpp: index_queue_.reserve): wall scenes queue well
+    // over half of the image
+    d.qcap = static_cast<std::uint32_t>(npx);
+    // k_jcp_rows keeps the 2-bit state plane of one frame (npx / 4 bytes) + H + 1 row starts in shared memory
+    if (static_cast<std::size_t>(npx) / 4 + sizeof(std::uint32_t) * (H + 2) + 4096 > 227u * 1024u)
+    {
+        delete ctx;
+        return LPL_ERR_CAPACITY;
+    }
     std::uint32_t h = 1024;
     while (h < 2u * d.cap)
     {
@@ -668,7 +680,8 @@ int lpl_pipeline_upload_device(lpl_ctx* ctx, const lpl_frame* frames, std::uint3
     return upload_impl(ctx, frames, nf, true);
 }
 
-int lpl_pipeline_upload_packed(lpl_ctx* ctx, const float* xyzw, const std::uint32_t* counts, std::uint32_t nf)
+static int upload_packed_impl(lpl_ctx* ctx, const float* pts, const std::uint32_t* counts, std::uint32_t nf,
+                              std::uint32_t bytes_per_point)
 {
     if (ctx == nullptr || counts == nullptr || nf == 0 || nf > ctx->c.d.B)
     {
@@ -695,8 +708,8 @@ int lpl_pipeline_upload_packed(lpl_ctx* ctx, const float* xyzw, const std::uint3
         h_start[f] = static_cast<std::uint32_t>(total);
         total += counts[f];
     }
-    // the raw-record area (32 bytes per point of capacity) doubles as the packed staging: 2 x the need
-    if (total != 0 && xyzw == nullptr)
+    // the raw-record area (32 bytes per point of capacity) doubles as the packed staging: >= 2 x the need
+    if (total != 0 && pts == nullptr)
     {
         return fail(ctx, LPL_ERR_INVALID_ARGUMENT, "null points");
     }
@@ -706,11 +719,22 @@ int lpl_pipeline_upload_packed(lpl_ctx* ctx, const float* xyzw, const std::uint3
     LPL_TRY(cudaMemcpyAsync(d_start, h_start, sizeof(std::uint32_t) * nf, cudaMemcpyHostToDevice, c.stream));
     if (total != 0)
     {
-        LPL_TRY(cudaMemcpyAsync(d.raw, xyzw, static_cast<std::size_t>(total) * 16, cudaMemcpyHostToDevice, c.stream));
-        launch_spread_packed(&c, nf, d.raw, d_start);
+        LPL_TRY(cudaMemcpyAsync(d.raw, pts, static_cast<std::size_t>(total) * bytes_per_point, cudaMemcpyHostToDevice,
+                                c.stream));
+        launch_spread_packed(&c, nf, d.raw, d_start, bytes_per_point == 12u);
     }
     ctx->have_ring = 0;
     return LPL_OK;
+}
+
+int lpl_pipeline_upload_packed(lpl_ctx* ctx, const float* xyzw, const std::uint32_t* counts, std::uint32_t nf)
+{
+    return upload_packed_impl(ctx, xyzw, counts, nf, 16u);
+}
+
+int lpl_pipeline_upload_packed_xyz(lpl_ctx* ctx, const float* xyz, const std::uint32_t* counts, std::uint32_t nf)
+{
+    return upload_packed_impl(ctx, xyz, counts, nf, 12u);
 }
 
 int lpl_pipeline_upload_cloud2(lpl_ctx* ctx, const lpl_cloud2_frame* frames, std::uint32_t nf)
@@ -839,6 +863,7 @@ int lpl_pipeline_run(lpl_ctx* ctx, std::uint32_t nf, std::uint32_t stages)
         launch_take_obstacles(&c, nf);
         launch_cluster(&c, nf);
     }
+    ctx->ran_hulls = (stages & LPL_STAGE_HULLS) != 0;
     if (stages & LPL_STAGE_HULLS)
     {
         launch_hulls(&c, nf);
@@ -858,6 +883,24 @@ int lpl_pipeline_sync(lpl_ctx* ctx, std::uint32_t nf)
         return LPL_ERR_INVALID_ARGUMENT;
     }
     return check_status(ctx, nf);
+}
+
+int lpl_pipeline_status(lpl_ctx* ctx, std::uint32_t nf, std::uint32_t* status_out)
+{
+    if (ctx == nullptr || status_out == nullptr || nf == 0 || nf > ctx->c.d.B)
+    {
+        return LPL_ERR_INVALID_ARGUMENT;
+    }
+    const int rc = check_status(ctx, nf);
+    if (rc != 0 && rc != LPL_ERR_CAPACITY)
+    {
+        return rc;
+    }
+    for (std::uint32_t f = 0; f < nf; ++f)
+    {
+        status_out[f] = ctx->h_status[f];
+    }
+    return LPL_OK;
 }
 
 int lpl_pipeline_want_image(lpl_ctx* ctx, int enable)
@@ -884,13 +927,10 @@ int lpl_pipeline_counts(lpl_ctx* ctx, std::uint32_t f, lpl_frame_result* r)
     LPL_TRY(cudaMemcpyAsync(&v[1], d.n_v + f, 4, cudaMemcpyDeviceToHost, c.stream));
     LPL_TRY(cudaMemcpyAsync(&v[2], d.n_o + f, 4, cudaMemcpyDeviceToHost, c.stream));
     LPL_TRY(cudaMemcpyAsync(&v[3], d.n_clusters + f, 4, cudaMemcpyDeviceToHost, c.stream));
+    // n_hull is zeroed by every run and only written by the hull stage: a run without LPL_STAGE_HULLS reports
+    // no vertices instead of the previous batch's offsets
+    LPL_TRY(cudaMemcpyAsync(&v[4], d.n_hull + f, 4, cudaMemcpyDeviceToHost, c.stream));
     LPL_TRY(cudaStreamSynchronize(c.stream));
-    if (v[3] <= d.cap)
-    {
-        LPL_TRY(cudaMemcpyAsync(&v[4], d.hull_off + static_cast<std::size_t>(f) * (d.cap + 1) + v[3], 4,
-                                cudaMemcpyDeviceToHost, c.stream));
-        LPL_TRY(cudaStreamSynchronize(c.stream));
-    }
     r->n = v[0];
     r->num_valid = v[1];
     r->num_obstacles = v[2];
@@ -939,8 +979,15 @@ int lpl_pipeline_download(lpl_ctx* ctx, std::uint32_t f, lpl_frame_result* r)
     }
     if (r->hull_offsets != nullptr)
     {
-        LPL_TRY(cudaMemcpyAsync(r->hull_offsets, d.hull_off + static_cast<std::size_t>(f) * (d.cap + 1),
-                                sizeof(std::uint32_t) * (r->num_clusters + 1), k, c.stream));
+        if (ctx->ran_hulls)
+        {
+            LPL_TRY(cudaMemcpyAsync(r->hull_offsets, d.hull_off + static_cast<std::size_t>(f) * (d.cap + 1),
+                                    sizeof(std::uint32_t) * (r->num_clusters + 1), k, c.stream));
+        }
+        else
+        {
+            std::memset(r->hull_offsets, 0, sizeof(std::uint32_t) * (r->num_clusters + 1)); // no hull stage in this run
+        }
     }
     if (r->hull_indices != nullptr && r->num_hull_vertices != 0)
     {
@@ -1167,11 +1214,13 @@ int lpl_cluster_hulls(lpl_ctx* ctx, const void* points, std::size_t stride, cons
     LPL_TRY(cudaMemsetAsync(d.ccount, 0, sizeof(std::uint32_t) * num_clusters, c.stream));
     LPL_TRY(cudaMemsetAsync(d.zmin_u, 0xff, sizeof(std::uint32_t) * num_clusters, c.stream));
     LPL_TRY(cudaMemsetAsync(d.zmax_u, 0, sizeof(std::uint32_t) * num_clusters, c.stream));
+    LPL_TRY(cudaMemsetAsync(d.zzero, 0xff, sizeof(std::uint32_t) * num_clusters, c.stream));
     k_ext_init<<<(num_clusters + 255) / 256, 256, 0, c.stream>>>(d, num_clusters);
     mark(&c, "ext_init");
     k_label_count<<<dim3((d.cap + 255) / 256, 1), 256, 0, c.stream>>>(d, num_clusters);
     mark(&c, "label_count");
     launch_hulls(&c, 1);
+    ctx->ran_hulls = true;
     LPL_TRY(cudaMemcpyAsync(hull_offsets, d.hull_off, sizeof(std::uint32_t) * (num_clusters + 1), cudaMemcpyDeviceToHost,
                             c.stream));
     LPL_TRY(cudaStreamSynchronize(c.stream));
@@ -1270,8 +1319,17 @@ int lpl_convex_hull(lpl_ctx* ctx, const void* xy, std::size_t stride, std::uint3
     }
     // The device path sorts on float keys: every PCL-derived PointXY is float-representable
     // (processor.cpp:645-646). Anything else is rejected rather than silently rounded.
-    std::vector<float> pts(static_cast<std::size_t>(n) * 4, 0.f);
-    std::vector<std::int32_t> lab(n, 0);
+    std::vector<float> pts;
+    std::vector<std::int32_t> lab;
+    try
+    {
+        pts.assign(static_cast<std::size_t>(n) * 4, 0.f);
+        lab.assign(n, 0);
+    }
+    catch (...)
+    {
+        return fail(ctx, LPL_ERR_CAPACITY, "convexHull: host staging allocation failed"); // nothing unwinds through the C ABI
+    }
     for (std::uint32_t i = 0; i < n; ++i)
     {
         double v[2];
@@ -1285,8 +1343,8 @@ int lpl_convex_hull(lpl_ctx* ctx, const void* xy, std::size_t stride, std::uint3
         pts[4 * i] = fx;
         pts[4 * i + 1] = fy;
     }
-    std::vector<std::uint32_t> off(2, 0);
-    const int rc = lpl_cluster_hulls(ctx, pts.data(), 16, lab.data(), n, 1, off.data(), indices_out, nullptr, nullptr);
+    std::uint32_t off[2] = {0, 0};
+    const int rc = lpl_cluster_hulls(ctx, pts.data(), 16, lab.data(), n, 1, off, indices_out, nullptr, nullptr);
     if (rc == 0)
     {
         *count_out = off[1];
@@ -1311,10 +1369,12 @@ int lpl_pipeline_download_batch(lpl_ctx* ctx, std::uint32_t nf, lpl_batch_result
     LPL_TRY(cudaMemcpyAsync(cn + 2 * nf, d.n_o, 4 * nf, k, c.stream));
     LPL_TRY(cudaMemcpyAsync(cn + 3 * nf, d.n_clusters, 4 * nf, k, c.stream));
     LPL_TRY(cudaMemcpyAsync(cn + 4 * nf, d.n_hull, 4 * nf, k, c.stream));
-    const int rc = check_status(ctx, nf);
-    if (rc != 0)
+    // a frame that ran out of a reserved capacity does not hold back the others: every plane is still delivered
+    // and the call returns LPL_ERR_CAPACITY afterwards (lpl_pipeline_status tells which frames to discard)
+    const int rc_status = check_status(ctx, nf);
+    if (rc_status != 0 && rc_status != LPL_ERR_CAPACITY)
     {
-        return rc;
+        return rc_status;
     }
     std::uint32_t mx[5] = {0, 0, 0, 0, 0};
     for (int a = 0; a < 5; ++a)
@@ -1348,7 +1408,70 @@ int lpl_pipeline_download_batch(lpl_ctx* ctx, std::uint32_t nf, lpl_batch_result
     LPL_TRY(plane(r->zminmax, d.zminmax, 8, d.cap, mx[3]));
     LPL_TRY(plane(r->boxes, d.boxes, sizeof(ObbBox), d.cap, mx[3]));
     LPL_TRY(cudaStreamSynchronize(c.stream));
-    return LPL_OK;
+    return rc_status;
+}
+
+static_assert(LPL_PLANE_COUNT == kPackPlanes, "plane bits of the C ABI = planes the pack kernels know");
+
+int lpl_pipeline_download_packed(lpl_ctx* ctx, std::uint32_t nf, lpl_packed_result* r)
+{
+    if (ctx == nullptr || r == nullptr || nf == 0 || nf > ctx->c.d.B || r->counts == nullptr ||
+        (r->planes >> LPL_PLANE_COUNT) != 0u)
+    {
+        return fail(ctx, LPL_ERR_INVALID_ARGUMENT, "bad packed download request");
+    }
+    Ctx& c = ctx->c;
+    Dev& d = c.d;
+    LPL_TRY(cudaSetDevice(c.device));
+    const cudaMemcpyKind k = cudaMemcpyDeviceToHost;
+    // device staging = the raw-record area (32 bytes per point of capacity), idle once a batch is uploaded
+    unsigned char* staging = d.raw;
+    const std::size_t staging_bytes = static_cast<std::size_t>(d.B) * d.cap * kRawRecord;
+    const std::size_t head = pack_payload_start(nf);
+    if (staging_bytes <= head)
+    {
+        return fail(ctx, LPL_ERR_CAPACITY, "context too small for a packed download");
+    }
+    launch_pack_results(&c, nf, r->planes, staging, staging_bytes);
+    // phase 1: counts, status and the layout header
+    std::uint32_t* cn = r->counts;
+    LPL_TRY(cudaMemcpyAsync(cn + 0 * nf, d.n_in, 4 * nf, k, c.stream));
+    LPL_TRY(cudaMemcpyAsync(cn + 1 * nf, d.n_v, 4 * nf, k, c.stream));
+    LPL_TRY(cudaMemcpyAsync(cn + 2 * nf, d.n_o, 4 * nf, k, c.stream));
+    LPL_TRY(cudaMemcpyAsync(cn + 3 * nf, d.n_clusters, 4 * nf, k, c.stream));
+    LPL_TRY(cudaMemcpyAsync(cn + 4 * nf, d.n_hull, 4 * nf, k, c.stream));
+    if (ensure_stage(ctx, sizeof(std::uint32_t) * 2 * d.B + sizeof(PackHeader)) != 0)
+    {
+        return LPL_ERR_CUDA;
+    }
+    // (the upload staging at the front of h_stage is consumed by then: the copies above are behind it in the stream)
+    auto* h_hdr = reinterpret_cast<PackHeader*>(static_cast<char*>(c.h_stage) + sizeof(std::uint32_t) * 2 * d.B);
+    LPL_TRY(cudaMemcpyAsync(h_hdr, staging, sizeof(PackHeader), k, c.stream));
+    const int rc_status = check_status(ctx, nf); // flagged frames do not hold back the others (see download_batch)
+    if (rc_status != 0 && rc_status != LPL_ERR_CAPACITY)
+    {
+        return rc_status;
+    }
+    for (int p = 0; p < LPL_PLANE_COUNT; ++p)
+    {
+        r->offset[p] = (r->planes & (1u << p)) ? static_cast<std::size_t>(h_hdr->offset[p]) : static_cast<std::size_t>(-1);
+    }
+    r->bytes_used = static_cast<std::size_t>(h_hdr->total);
+    if (h_hdr->fits == 0u)
+    {
+        return fail(ctx, LPL_ERR_CAPACITY, "packed results exceed the device staging area (32 bytes per point of capacity)");
+    }
+    if (r->bytes_used > r->buffer_bytes || (r->bytes_used != 0 && r->buffer == nullptr))
+    {
+        return fail(ctx, LPL_ERR_CAPACITY, "host buffer smaller than the packed results");
+    }
+    // phase 2: the payload, one transfer
+    if (r->bytes_used != 0)
+    {
+        LPL_TRY(cudaMemcpyAsync(r->buffer, staging + head, r->bytes_used, k, c.stream));
+    }
+    LPL_TRY(cudaStreamSynchronize(c.stream));
+    return rc_status;
 }
 
 int lpl_host_alloc(void** out, std::size_t bytes)

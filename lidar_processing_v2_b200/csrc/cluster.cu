@@ -529,6 +529,7 @@ struct ClusterRepEmit
         d.ccount[o + pos] = d.hcount[ho + root];
         d.zmin_u[o + pos] = 0xffffffffu; // z extent accumulators of the new label
         d.zmax_u[o + pos] = 0u;
+        d.zzero[o + pos] = 0xffffffffu;
         ext_init(d.ext + (o + pos) * kExtDirs);
     }
 };
@@ -557,7 +558,7 @@ __global__ void __launch_bounds__(256) k_clu_labels(Dev d)
     }
     // every kExtWarpStride-th warp of the frame contributes to the extreme points
     const bool with_extremes = (((blockIdx.x * 256u + threadIdx.x) >> 5) % kExtWarpStride) == 0u;
-    accumulate_cluster_stats(d.ext + o * kExtDirs, d.zmin_u + o, d.zmax_u + o, l, x, y, z, i, with_extremes);
+    accumulate_cluster_stats(d.ext + o * kExtDirs, d.zmin_u + o, d.zmax_u + o, d.zzero + o, l, x, y, z, i, with_extremes);
 }
 
 // hand-over from segmentation: stable compaction of OBSTACLE points in cloud order

@@ -79,6 +79,35 @@ struct ObbBox
     std::int32_t pad;
 };
 
+// packed result download (ingest.cu: launch_pack_results; C ABI: lpl_pipeline_download_packed). Plane order =
+// the LPL_PLANE_* bits of include/lpl_b200.h.
+constexpr int kPackPlanes = 10;
+struct PackHeader
+{
+    unsigned long long offset[kPackPlanes]; // byte offset of every selected plane inside the payload, ~0 = not selected
+    unsigned long long total;               // payload bytes
+    std::uint32_t fits;                     // 0: the payload would not fit the staging area (nothing was packed)
+    std::uint32_t pad;
+};
+
+// bytes per element of plane p: labels_u8, noise, ring, obstacle_index, cluster_labels, hull_offsets, hull_indices,
+// hull_xy, zminmax, boxes
+__host__ __device__ inline std::uint32_t pack_elem(int p)
+{
+    return p < 2 ? 1u : p == 2 ? 2u : p < 7 ? 4u : p < 9 ? 8u : 80u;
+}
+
+// which per-frame count sizes plane p: 0 = n, 1 = n_o, 2 = K + 1, 3 = K, 4 = Hv
+__host__ __device__ inline int pack_count_of(int p)
+{
+    return p < 3 ? 0 : p < 5 ? 1 : p == 5 ? 2 : p < 8 ? 4 : 3;
+}
+
+inline std::size_t pack_payload_start(std::uint32_t nf)
+{
+    return (sizeof(PackHeader) + static_cast<std::size_t>(5) * nf * sizeof(unsigned long long) + 15u) & ~static_cast<std::size_t>(15);
+}
+
 // All device buffers of a context. Pointers are to the start of frame 0; frame f lives at
 // ptr + f * stride (stride noted per field).
 struct Dev
@@ -176,6 +205,7 @@ struct Dev
     std::uint32_t* n_hull;    // [B]       hull vertices of the frame
     std::uint32_t* zmin_u;    // [B][cap]  per cluster: order-preserving bits of min z
     std::uint32_t* zmax_u;    // [B][cap]  per cluster: order-preserving bits of max z
+    std::uint32_t* zzero;     // [B][cap]  per cluster: (first point in cloud order with z == +-0) << 1 | its sign bit, ~0 = none
     unsigned long long* ext;  // [B][cap][kExtDirs] per cluster: extreme points (ordered value bits << 32 | point index) for
                               //             min x, min x+y, min y, max x-y, max x, max x+y, max y, min x-y (CCW order)
     float2* octa;             // [B][cap][kExtDirs] per cluster: the polygon of those points, or NaN when unusable
@@ -383,13 +413,20 @@ __device__ __forceinline__ void ext_init(unsigned long long* e)
 constexpr std::uint32_t kExtWarpStride = LPL_EXT_WARP_STRIDE;
 
 __device__ __forceinline__ void accumulate_cluster_stats(unsigned long long* ext, std::uint32_t* zmin_u,
-                                                         std::uint32_t* zmax_u, std::int32_t label, float x, float y,
-                                                         float z, std::uint32_t idx, bool with_extremes)
+                                                         std::uint32_t* zmax_u, std::uint32_t* zzero, std::int32_t label,
+                                                         float x, float y, float z, std::uint32_t idx, bool with_extremes)
 {
     const std::uint32_t peers = __match_any_sync(0xffffffffu, label);
     if (label < 0)
     {
         return;
+    }
+    // The reference keeps the FIRST point in cloud order among equal extremes (strict compares,
+    // processor.cpp:648-655), which is only observable for z == +-0: the ordered keys below fold -0.0 into
+    // +0.0, so the sign of a zero extent is taken from the first zero-height point of the cluster (rare).
+    if (z == 0.0f)
+    {
+        atomicMin(&zzero[label], (idx << 1) | (__float_as_uint(z) >> 31));
     }
     const bool lead = static_cast<int>(lane_id()) == __ffs(peers) - 1;
     // the leader fetches the cluster's running values up front, all loads in flight together: their
@@ -549,7 +586,8 @@ void launch_take_obstacles(Ctx* c, std::uint32_t nf);
 void launch_cluster(Ctx* c, std::uint32_t nf);
 void launch_hulls(Ctx* c, std::uint32_t nf);
 void launch_boxes(Ctx* c, std::uint32_t nf, int method);
-void launch_spread_packed(Ctx* c, std::uint32_t nf, const void* packed, const std::uint32_t* start);
+void launch_spread_packed(Ctx* c, std::uint32_t nf, const void* packed, const std::uint32_t* start, bool xyz12);
+void launch_pack_results(Ctx* c, std::uint32_t nf, std::uint32_t planes, unsigned char* staging, std::size_t staging_bytes);
 void launch_unpack_cloud2(Ctx* c, std::uint32_t nf, const unsigned char* raw, std::size_t raw_stride, const void* desc);
 void launch_boxes_hulls(Ctx* c, const double2* xy, const std::uint32_t* off, std::uint32_t K, int method, ObbBox* out);
 

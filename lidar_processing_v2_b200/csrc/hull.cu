@@ -906,7 +906,17 @@ __global__ void __launch_bounds__(64) k_hull_final(Dev d)
     const std::uint32_t seg = cstart[c];
     const std::uint32_t n = cstart[c + 1] - seg;
     // z extent of the cluster (processor.cpp:648-655), reduced while labelling (cluster.cu)
-    d.zminmax[o + c] = make_float2(unord_f32(d.zmin_u[o + c]), unord_f32(d.zmax_u[o + c]));
+    {
+        float zlo = unord_f32(d.zmin_u[o + c]), zhi = unord_f32(d.zmax_u[o + c]);
+        const std::uint32_t zz = d.zzero[o + c];
+        if (zz != 0xffffffffu && (zz & 1u) != 0u)
+        {
+            // a zero extent carries the sign of the cluster's first zero-height point (see accumulate_cluster_stats)
+            zlo = zlo == 0.0f ? -0.0f : zlo;
+            zhi = zhi == 0.0f ? -0.0f : zhi;
+        }
+        d.zminmax[o + c] = make_float2(zlo, zhi);
+    }
     const std::uint32_t fin = d.hfin[o + c];
     if (fin & kFinDone)
     {

@@ -86,10 +86,191 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-void launch_spread_packed(Ctx* c, std::uint32_t nf, const void* packed, const std::uint32_t* start)
+// same for 12-byte records (x, y, z floats back to back: the std::array<float, 3> cloud NoiseRemover::filter takes,
+// noise_remover.hpp:68). Consecutive threads read consecutive records, so every fetched sector is fully used.
+__global__ void __launch_bounds__(256)
+    k_spread_packed_xyz(Dev d, const float* __restrict__ packed, const std::uint32_t* __restrict__ start)
 {
-    k_spread_packed<<<dim3((c->d.cap + 255) / 256, nf), 256, 0, c->stream>>>(c->d, static_cast<const float4*>(packed), start);
+    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t n = d.n_in[f];
+    const std::uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    if (i < n)
+    {
+        const float* p = packed + (static_cast<std::size_t>(start[f]) + i) * 3u;
+        d.pts_in[static_cast<std::size_t>(f) * d.cap + i] = make_float4(p[0], p[1], p[2], 0.f);
+    }
+}
+
+void launch_spread_packed(Ctx* c, std::uint32_t nf, const void* packed, const std::uint32_t* start, bool xyz12)
+{
+    const dim3 grid((c->d.cap + 255) / 256, nf);
+    if (xyz12)
+    {
+        k_spread_packed_xyz<<<grid, 256, 0, c->stream>>>(c->d, static_cast<const float*>(packed), start);
+    }
+    else
+    {
+        k_spread_packed<<<grid, 256, 0, c->stream>>>(c->d, static_cast<const float4*>(packed), start);
+    }
     mark(c, "spread_packed");
+}
+
+// ------------------------------------------------------------------------------------------
+// packed result download: the occupied part of every selected result plane of a batch is copied
+// back to back into one device staging area, so the batch's results cross PCIe as ONE transfer
+// of exactly the bytes that carry information (the frame-major planes have a fixed stride of
+// `cap` elements; a strided copy moves the widest frame's width for every frame).
+// ------------------------------------------------------------------------------------------
+// header (PackHeader) written by k_pack_layout at the start of the staging area
+__global__ void __launch_bounds__(1024) k_pack_layout(Dev d, std::uint32_t nf, std::uint32_t planes, PackHeader* hdr,
+                                                      unsigned long long* frame_off, unsigned long long capacity)
+{
+    // five running sums over the frames: n, n_o, K + 1, K, Hv  (one block; nf is a few thousand at most)
+    __shared__ unsigned long long tot[5];
+    __shared__ std::uint32_t sh[33];
+    for (int q = 0; q < 5; ++q)
+    {
+        std::uint32_t carry = 0;
+        for (std::uint32_t base = 0; base < nf; base += blockDim.x)
+        {
+            const std::uint32_t f = base + threadIdx.x;
+            std::uint32_t v = 0;
+            if (f < nf)
+            {
+                v = q == 0 ? d.n_in[f] : q == 1 ? d.n_o[f] : q == 2 ? d.n_clusters[f] + 1u : q == 3 ? d.n_clusters[f] : d.n_hull[f];
+            }
+            std::uint32_t t;
+            const std::uint32_t ex = block_excl_scan(v, sh, &t);
+            if (f < nf)
+            {
+                frame_off[static_cast<std::size_t>(q) * nf + f] = carry + ex;
+            }
+            carry += t;
+            __syncthreads();
+        }
+        if (threadIdx.x == 0)
+        {
+            tot[q] = carry;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        unsigned long long off = 0;
+        for (int p = 0; p < kPackPlanes; ++p)
+        {
+            hdr->offset[p] = ~0ULL;
+            if (planes & (1u << p))
+            {
+                hdr->offset[p] = off;
+                off += tot[pack_count_of(p)] * pack_elem(p);
+                off = (off + 15ULL) & ~15ULL;
+            }
+        }
+        hdr->total = off;
+        hdr->fits = off <= capacity ? 1u : 0u;
+    }
+}
+
+// one launch per plane: element e of frame f -> dst[offset + (frame_off[f] + e) * elem]; units of 4 bytes when
+// the element is a multiple of 4 bytes, bytes otherwise
+template <int kUnit>
+__global__ void __launch_bounds__(256)
+    k_pack_plane(const unsigned char* __restrict__ src, std::size_t src_frame_bytes, std::uint32_t elem,
+                 const std::uint32_t* __restrict__ count, std::uint32_t count_add, const unsigned long long* __restrict__ frame_off,
+                 const PackHeader* __restrict__ hdr, int plane, unsigned char* __restrict__ staging)
+{
+    if (hdr->fits == 0u)
+    {
+        return;
+    }
+    const std::uint32_t f = blockIdx.y;
+    const std::size_t bytes = static_cast<std::size_t>(count[f] + count_add) * elem;
+    const unsigned char* s = src + static_cast<std::size_t>(f) * src_frame_bytes;
+    unsigned char* o = staging + hdr->offset[plane] + frame_off[f] * elem;
+    // the source frame starts 16-byte aligned and is padded to a multiple of 2048 elements, so it is read in
+    // whole words (the last one may run past the count, still inside the frame's plane); the destination of a
+    // byte / half-word plane starts wherever the previous frame ended and is written in its own unit
+    const std::size_t words = (bytes + 3u) / 4u;
+    for (std::size_t u = static_cast<std::size_t>(blockIdx.x) * 256u + threadIdx.x; u < words; u += static_cast<std::size_t>(gridDim.x) * 256u)
+    {
+        const std::uint32_t w = reinterpret_cast<const std::uint32_t*>(s)[u];
+        if (kUnit == 4)
+        {
+            reinterpret_cast<std::uint32_t*>(o)[u] = w;
+        }
+        else if (kUnit == 2)
+        {
+            reinterpret_cast<std::uint16_t*>(o)[2u * u] = static_cast<std::uint16_t>(w);
+            if (4u * u + 2u < bytes)
+            {
+                reinterpret_cast<std::uint16_t*>(o)[2u * u + 1u] = static_cast<std::uint16_t>(w >> 16);
+            }
+        }
+        else
+        {
+#pragma unroll
+            for (std::uint32_t k = 0; k < 4u; ++k)
+            {
+                if (4u * u + k < bytes)
+                {
+                    o[4u * u + k] = static_cast<unsigned char>(w >> (8u * k));
+                }
+            }
+        }
+    }
+}
+
+void launch_pack_results(Ctx* c, std::uint32_t nf, std::uint32_t planes, unsigned char* staging, std::size_t staging_bytes)
+{
+    Dev& d = c->d;
+    // staging: [PackHeader][frame_off: 5 x nf u64][payload ...]
+    PackHeader* hdr = reinterpret_cast<PackHeader*>(staging);
+    unsigned long long* frame_off = reinterpret_cast<unsigned long long*>(staging + sizeof(PackHeader));
+    const std::size_t head = pack_payload_start(nf);
+    unsigned char* payload = staging + head;
+    k_pack_layout<<<1, 1024, 0, c->stream>>>(d, nf, planes, hdr, frame_off, staging_bytes > head ? staging_bytes - head : 0);
+    mark(c, "pack_layout");
+    const std::size_t cap = d.cap;
+    struct Src
+    {
+        const void* p;
+        std::size_t frame_elems;
+        const std::uint32_t* cnt;
+        std::uint32_t add;
+    };
+    const Src src[kPackPlanes] = {
+        {d.labels_out, cap, d.n_in, 0},  {d.noise, cap, d.n_in, 0},        {d.ring, cap, d.n_in, 0},
+        {d.idx_o, cap, d.n_o, 0},        {d.clabel, cap, d.n_o, 0},        {d.hull_off, cap + 1, d.n_clusters, 1},
+        {d.hull_idx, cap, d.n_hull, 0},  {d.hull_xy, cap, d.n_hull, 0},    {d.zminmax, cap, d.n_clusters, 0},
+        {d.boxes, cap, d.n_clusters, 0},
+    };
+    for (int p = 0; p < kPackPlanes; ++p)
+    {
+        if ((planes & (1u << p)) == 0u)
+        {
+            continue;
+        }
+        const std::uint32_t elem = pack_elem(p);
+        const unsigned long long* fo = frame_off + static_cast<std::size_t>(pack_count_of(p)) * nf;
+        const auto* sp = static_cast<const unsigned char*>(src[p].p);
+        const std::size_t fb = src[p].frame_elems * elem;
+        // CTAs per frame: enough to cover a typical frame in two or three trips
+        const dim3 grid(p < 3 ? 128 : (p < 5 ? 64 : 8), nf);
+        if (elem % 4u == 0u)
+        {
+            k_pack_plane<4><<<grid, 256, 0, c->stream>>>(sp, fb, elem, src[p].cnt, src[p].add, fo, hdr, p, payload);
+        }
+        else if (elem == 2u)
+        {
+            k_pack_plane<2><<<grid, 256, 0, c->stream>>>(sp, fb, elem, src[p].cnt, src[p].add, fo, hdr, p, payload);
+        }
+        else
+        {
+            k_pack_plane<1><<<grid, 256, 0, c->stream>>>(sp, fb, elem, src[p].cnt, src[p].add, fo, hdr, p, payload);
+        }
+        mark(c, "pack_plane");
+    }
 }
 
 void launch_unpack_cloud2(Ctx* c, std::uint32_t nf, const unsigned char* raw, std::size_t raw_stride, const void* desc)
@@ -149,13 +330,22 @@ bool read_line(std::FILE* fp, std::string& line)
         {
             return true;
         }
+        if (line.size() >= (std::size_t(1) << 20))
+        {
+            return false; // no header or ascii record line is this long: refuse rather than grow without bound
+        }
         line.push_back(static_cast<char>(ch));
     }
     return !line.empty();
 }
 } // namespace
 
-extern "C" int lpl_pcd_read(const char* path, float* xyzi_out, uint32_t capacity, uint32_t* n_out)
+namespace
+{
+constexpr int kPcdMaxRecord = 4096; // bytes per point record accepted from a header
+constexpr int kPcdMaxFields = 256;
+
+int pcd_read_impl(const char* path, float* xyzi_out, uint32_t capacity, uint32_t* n_out)
 {
     if (path == nullptr || n_out == nullptr)
     {
@@ -167,6 +357,11 @@ extern "C" int lpl_pcd_read(const char* path, float* xyzi_out, uint32_t capacity
     {
         return LPL_ERR_INVALID_ARGUMENT;
     }
+    struct Closer
+    {
+        std::FILE* f;
+        ~Closer() { std::fclose(f); }
+    } closer{fp}; // also closes when an allocation throws
     PcdHeader h;
     std::string line;
     while (read_line(fp, line))
@@ -225,14 +420,31 @@ extern "C" int lpl_pcd_read(const char* path, float* xyzi_out, uint32_t capacity
     {
         h.count.assign(nf, 1);
     }
-    if (nf == 0 || h.size.size() != nf || h.type.size() != nf || h.count.size() != nf || h.data.empty())
+    if (nf == 0 || nf > static_cast<std::size_t>(kPcdMaxFields) || h.size.size() != nf || h.type.size() != nf ||
+        h.count.size() != nf || h.data.empty())
     {
-        std::fclose(fp);
         return LPL_ERR_INVALID_ARGUMENT;
+    }
+    // every field - not only the ones that are read - must have a sane size and count: the record
+    // length and the byte offsets / columns of x, y, z, intensity are sums over all of them
+    for (std::size_t k = 0; k < nf; ++k)
+    {
+        if (h.size[k] <= 0 || h.size[k] > 8 || h.count[k] <= 0 || h.count[k] > kPcdMaxRecord)
+        {
+            return LPL_ERR_INVALID_ARGUMENT;
+        }
     }
     if (!h.have_points)
     {
+        if (h.height != 0 && h.width > 0xffffffffULL / h.height)
+        {
+            return LPL_ERR_CAPACITY;
+        }
         h.points = h.width * h.height;
+    }
+    if (h.points > 0xffffffffULL)
+    {
+        return LPL_ERR_CAPACITY; // n_out is 32 bits wide
     }
     // byte offset (binary) / column (ascii) of x, y, z, intensity
     int off[4] = {-1, -1, -1, -1}, colidx[4] = {-1, -1, -1, -1};
@@ -246,7 +458,6 @@ extern "C" int lpl_pcd_read(const char* path, float* xyzi_out, uint32_t capacity
             {
                 if (h.size[k] != 4 || h.type[k] != 'F' || h.count[k] != 1)
                 {
-                    std::fclose(fp);
                     return LPL_ERR_INVALID_ARGUMENT; // only float32 coordinates (what the node consumes)
                 }
                 off[w] = rec;
@@ -255,21 +466,29 @@ extern "C" int lpl_pcd_read(const char* path, float* xyzi_out, uint32_t capacity
         }
         rec += h.size[k] * h.count[k];
         cols += h.count[k];
+        if (rec > kPcdMaxRecord)
+        {
+            return LPL_ERR_INVALID_ARGUMENT;
+        }
     }
     if (off[0] < 0 || off[1] < 0 || off[2] < 0 || rec <= 0)
     {
-        std::fclose(fp);
         return LPL_ERR_INVALID_ARGUMENT;
+    }
+    for (int w = 0; w < 4; ++w)
+    {
+        if (off[w] >= 0 && (off[w] + 4 > rec || colidx[w] >= cols))
+        {
+            return LPL_ERR_INVALID_ARGUMENT;
+        }
     }
     *n_out = static_cast<uint32_t>(h.points);
     if (xyzi_out == nullptr)
     {
-        std::fclose(fp);
         return LPL_OK; // size query
     }
     if (h.points > capacity)
     {
-        std::fclose(fp);
         return LPL_ERR_CAPACITY;
     }
     int rc = LPL_OK;
@@ -337,10 +556,27 @@ extern "C" int lpl_pcd_read(const char* path, float* xyzi_out, uint32_t capacity
     {
         rc = LPL_ERR_INVALID_ARGUMENT; // binary_compressed is not produced by the reference's data set
     }
-    std::fclose(fp);
     if (rc != LPL_OK)
     {
         *n_out = 0;
     }
     return rc;
+}
+} // namespace
+
+extern "C" int lpl_pcd_read(const char* path, float* xyzi_out, uint32_t capacity, uint32_t* n_out)
+{
+    // nothing may unwind through the C ABI (std::string / std::vector growth can throw)
+    try
+    {
+        return pcd_read_impl(path, xyzi_out, capacity, n_out);
+    }
+    catch (...)
+    {
+        if (n_out != nullptr)
+        {
+            *n_out = 0;
+        }
+        return LPL_ERR_INVALID_ARGUMENT;
+    }
 }

@@ -28,6 +28,7 @@
 // The reference leaves out-of-image kernel slots untouched, so border pixels inherit those
 // slots from the previously popped pixel (hazard H2); k_jcp_pre reproduces that by
 // locating the most recent earlier queued pixel for which the slot was inside the image.
+#include <algorithm>
 #include <cfloat>
 
 #include "common.cuh"
@@ -1182,14 +1183,13 @@ __global__ void __launch_bounds__(128) k_jcp_pre(Dev d, SegParams sp)
     __shared__ float s_inv[128];   // the divisor (sum) or 0 when the pixel cannot be decided
     const std::uint32_t f = blockIdx.y;
     const std::uint32_t nq = min(d.n_queue[f], d.qcap);
-    if (blockIdx.x * 128u >= nq)
-    {
-        return;
-    }
-    const std::uint32_t k = min(blockIdx.x * 128u + threadIdx.x, nq - 1u); // tail threads redo the last pixel
-    const bool live = blockIdx.x * 128u + threadIdx.x < nq;
     const std::size_t po = static_cast<std::size_t>(f) * sp.npx;
     const std::uint32_t* queue = d.queue + static_cast<std::size_t>(f) * d.qcap;
+    // the grid covers a typical queue (~11k entries per HDL-64E frame) in one trip; longer queues loop
+    for (std::uint32_t blk = blockIdx.x; blk * 128u < nq; blk += gridDim.x)
+    {
+    const std::uint32_t k = min(blk * 128u + threadIdx.x, nq - 1u); // tail threads redo the last pixel
+    const bool live = blk * 128u + threadIdx.x < nq;
     const std::uint32_t p = queue[k];
     const int h = static_cast<int>(p / sp.W), w = static_cast<int>(p % sp.W);
     const float4 core = d.pxpt[po + p];
@@ -1268,13 +1268,15 @@ __global__ void __launch_bounds__(128) k_jcp_pre(Dev d, SegParams sp)
     __syncthreads();
     // weight_matrix = unnormalized / sum (segmenter.cpp:611); the CTA's rows are one contiguous
     // block of the entry-major array -> coalesced stores
-    const std::uint32_t rows = min(128u, nq - blockIdx.x * 128u);
-    float* out = wn + static_cast<std::size_t>(blockIdx.x) * 128u * 24u;
+    const std::uint32_t rows = min(128u, nq - blk * 128u);
+    float* out = wn + static_cast<std::size_t>(blk) * 128u * 24u;
     for (std::uint32_t t = threadIdx.x; t < rows * 24u; t += 128u)
     {
         const std::uint32_t e = t / 24u, i = t % 24u;
         const float dv = s_inv[e];
         out[t] = dv != 0.f ? s_w[e][i] / dv : 0.f;
+    }
+    __syncthreads(); // s_w / s_inv are rewritten by the next trip
     }
 }
 
@@ -2006,14 +2008,21 @@ void launch_segment(Ctx* c, std::uint32_t nf, bool want_image)
     launch_compact(c, "jcp_runs", nf, (d.qcap + kTile - 1) / kTile, d.n_queue, 0u, d.tile_cnt, d.n_runs,
                    RunHeadPred{d.queue, d.qcap, static_cast<std::uint32_t>(sp.W)}, RunHeadEmit{d.runs, d.qcap});
 #endif
-    k_jcp_pre<<<dim3((d.qcap + 127) / 128, nf), 128, 0, s>>>(d, sp);
+    k_jcp_pre<<<dim3(std::min<std::uint32_t>((d.qcap + 127) / 128, per_frame_ctas(128, nf, 1024)), nf), 128, 0, s>>>(d, sp);
     mark(c, "jcp_pre");
     // state plane (32 KB for 64 x 2048, 64 KB for 128-beam images): above the 48 KB default for the
     // larger images, opt in (up to 227 KB per CTA on sm_100a)
     const std::size_t plane_bytes = static_cast<std::size_t>((sp.npx + 15) / 16) * 4;
 #if LPL_JCP_ROWS
     const std::size_t rows_bytes = plane_bytes + sizeof(std::uint32_t) * (sp.H + 1);
-    cudaFuncSetAttribute(k_jcp_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(rows_bytes));
+    if (cudaFuncSetAttribute(k_jcp_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(rows_bytes)) != cudaSuccess)
+    {
+        cudaGetLastError();
+        std::snprintf(c->err, sizeof(c->err), "the %d x %d range image needs %zu bytes of shared memory per CTA for the JCP sweep", sp.H,
+                      sp.W, rows_bytes);
+        c->launch_failed = true;
+        return;
+    }
     k_jcp_rows<<<nf, kJcpRowsThreads, rows_bytes, s>>>(d, sp);
     mark(c, "jcp_rows");
 #else

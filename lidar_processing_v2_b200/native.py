@@ -36,8 +36,9 @@ EXPORTS = [
     "lpl_segmenter_config", "lpl_dror_config", "lpl_cluster_config", "lpl_set_jcp_mode",
     "lpl_ring_partition", "lpl_dror_filter", "lpl_segment", "lpl_cluster", "lpl_convex_hull",
     "lpl_cluster_hulls", "lpl_bounding_boxes",
-    "lpl_pipeline_upload", "lpl_pipeline_upload_device", "lpl_pipeline_upload_cloud2", "lpl_pipeline_upload_packed", "lpl_pcd_read",
-    "lpl_pipeline_run", "lpl_pipeline_sync",
+    "lpl_pipeline_upload", "lpl_pipeline_upload_device", "lpl_pipeline_upload_cloud2", "lpl_pipeline_upload_packed",
+    "lpl_pipeline_upload_packed_xyz", "lpl_pcd_read",
+    "lpl_pipeline_run", "lpl_pipeline_sync", "lpl_pipeline_status", "lpl_pipeline_download_packed",
     "lpl_pipeline_want_image", "lpl_pipeline_counts", "lpl_pipeline_download",
     "lpl_pipeline_download_batch", "lpl_host_alloc", "lpl_host_free",
     "lpl_profile_enable", "lpl_profile_read",
@@ -134,6 +135,25 @@ class BatchResult(C.Structure):
     ]
 
 
+# LPL_PLANE_* bits of lpl_pipeline_download_packed, in bit order: (name, dtype, floats/ints per element, count row)
+PLANES = (("labels_u8", np.uint8, 1, 0), ("noise", np.uint8, 1, 0), ("ring", np.uint16, 1, 0),
+          ("obstacle_index", np.uint32, 1, 2), ("cluster_labels", np.int32, 1, 2),
+          ("hull_offsets", np.uint32, 1, 3), ("hull_indices", np.uint32, 1, 4),
+          ("hull_xy", np.float32, 2, 4), ("zminmax", np.float32, 2, 3), ("boxes", BBOX_DTYPE, 1, 3))
+PLANE_BIT = {name: 1 << i for i, (name, _, _, _) in enumerate(PLANES)}
+
+
+class PackedResult(C.Structure):
+    _fields_ = [
+        ("counts", C.c_void_p),
+        ("buffer", C.c_void_p),
+        ("buffer_bytes", C.c_size_t),
+        ("planes", C.c_uint32),
+        ("offset", C.c_size_t * len(PLANES)),
+        ("bytes_used", C.c_size_t),
+    ]
+
+
 def pcd_read(path: str, lib=None) -> np.ndarray:
     """(n, 4) float32 x, y, z, intensity of a PCD file (lpl_pcd_read)."""
     lib = lib or load_library()
@@ -197,6 +217,9 @@ def load_library(path: str | None = None) -> C.CDLL:
     L.lpl_pipeline_upload_cloud2.argtypes = [vp, C.POINTER(Cloud2Frame), u32]
     L.lpl_pcd_read.argtypes = [C.c_char_p, vp, u32, C.POINTER(u32)]
     L.lpl_pipeline_upload_packed.argtypes = [vp, vp, vp, u32]
+    L.lpl_pipeline_upload_packed_xyz.argtypes = [vp, vp, vp, u32]
+    L.lpl_pipeline_status.argtypes = [vp, u32, vp]
+    L.lpl_pipeline_download_packed.argtypes = [vp, u32, C.POINTER(PackedResult)]
     L.lpl_pipeline_run.argtypes = [vp, u32, u32]
     L.lpl_pipeline_sync.argtypes = [vp, u32]
     L.lpl_pipeline_want_image.argtypes = [vp, C.c_int]
@@ -225,7 +248,9 @@ def load_library(path: str | None = None) -> C.CDLL:
                  "lpl_convex_hull", "lpl_cluster_hulls", "lpl_pipeline_upload",
                  "lpl_pipeline_upload_device", "lpl_pipeline_run", "lpl_pipeline_sync",
                  "lpl_pipeline_want_image", "lpl_pipeline_counts", "lpl_pipeline_download",
-                 "lpl_pipeline_download_batch", "lpl_profile_enable", "lpl_profile_read",
+                 "lpl_pipeline_download_batch", "lpl_pipeline_upload_packed", "lpl_pipeline_upload_packed_xyz",
+                 "lpl_pipeline_upload_cloud2", "lpl_pipeline_status", "lpl_pipeline_download_packed",
+                 "lpl_profile_enable", "lpl_profile_read",
                  "lpl_timer_start", "lpl_timer_stop_ms", "lpl_debug_segment", "lpl_debug_cluster"):
         getattr(L, name).restype = C.c_int
     if path is None:
@@ -293,6 +318,46 @@ class BatchBuffers:
         self.counts.close()
         for b in self.planes.values():
             b.close()
+
+
+class PackedBuffers:
+    """Pinned host buffer for lpl_pipeline_download_packed: the selected planes of a batch back to back, every
+    frame's occupied part only. `frame(name, f)` gives frame f of a plane as a numpy view."""
+
+    def __init__(self, max_frames: int, nbytes: int, want=("labels_u8", "cluster_labels", "hull_offsets", "hull_xy", "zminmax")):
+        self.max_frames = max_frames
+        self.want = tuple(want)
+        self.planes_mask = sum(PLANE_BIT[n] for n in self.want)
+        self.counts = PinnedBuffer((5, max_frames), np.uint32)
+        self.buf = PinnedBuffer((int(nbytes),), np.uint8)
+        self.offset = {}
+        self.bytes_used = 0
+        self.nf = 0
+        self._starts = {}
+
+    def _set(self, nf: int, res: "PackedResult"):
+        self.nf = nf
+        self.bytes_used = int(res.bytes_used)
+        self.offset = {name: int(res.offset[i]) for i, (name, _, _, _) in enumerate(PLANES) if name in self.want}
+        cn = self.counts.array.reshape(-1)[: 5 * nf].reshape(5, nf).astype(np.int64)
+        per = {0: cn[0], 2: cn[2], 3: cn[3], 4: cn[4], 5: cn[3] + 1}
+        self._starts = {k: np.concatenate([[0], np.cumsum(v)]) for k, v in per.items()}
+        return cn
+
+    def frame(self, name: str, f: int) -> np.ndarray:
+        i = [p[0] for p in PLANES].index(name)
+        _, dt, width, row = PLANES[i]
+        key = 5 if name == "hull_offsets" else row
+        st = self._starts[key]
+        esz = np.dtype(dt).itemsize * width
+        a = self.offset[name] + int(st[f]) * esz
+        n = int(st[f + 1] - st[f])
+        v = self.buf.array[a:a + n * esz].view(dt)
+        return v.reshape(n, width) if width > 1 else v
+
+    def close(self):
+        self.counts.close()
+        self.buf.close()
 
 
 def _points_arg(pts):
@@ -458,6 +523,15 @@ class Context:
         self._keep = [a, cn]
         return len(cn)
 
+    def upload_packed_xyz(self, xyz, counts) -> int:
+        """xyz: (sum(counts), 3) float32, 12 bytes per point (the std::array<float, 3> cloud of NoiseRemover::filter)."""
+        a = np.ascontiguousarray(xyz, dtype=np.float32)
+        cn = np.ascontiguousarray(counts, dtype=np.uint32)
+        assert a.ndim == 2 and a.shape[1] == 3 and int(cn.sum()) == a.shape[0]
+        self._chk(self.lib.lpl_pipeline_upload_packed_xyz(self.h, a.ctypes.data if a.size else None, cn.ctypes.data, len(cn)))
+        self._keep = [a, cn]
+        return len(cn)
+
     def upload_cloud2(self, messages) -> int:
         """messages: dicts with data (uint8 array), width, height, point_step, row_step, x/y/z_offset and
         ring_offset (-1 = none) - the PointCloud2 fields Processor::convert reads."""
@@ -519,6 +593,22 @@ class Context:
         # counts are laid out [5][nf] for this call's nf
         self._chk(self.lib.lpl_pipeline_download_batch(self.h, nf, C.byref(r)))
         return bufs.counts.array.reshape(-1)[: 5 * nf].reshape(5, nf)
+
+    def download_packed(self, nf: int, bufs: PackedBuffers) -> np.ndarray:
+        """ONE D2H transfer of the occupied bytes of the selected planes; returns counts[5][nf]."""
+        r = PackedResult()
+        r.counts = bufs.counts.ptr
+        r.buffer = bufs.buf.ptr
+        r.buffer_bytes = bufs.buf.array.nbytes
+        r.planes = bufs.planes_mask
+        self._chk(self.lib.lpl_pipeline_download_packed(self.h, nf, C.byref(r)))
+        return bufs._set(nf, r)
+
+    def status(self, nf: int) -> np.ndarray:
+        """Per-frame capacity flags of the last run (0 = good)."""
+        st = np.zeros(nf, np.uint32)
+        self._chk(self.lib.lpl_pipeline_status(self.h, nf, st.ctypes.data))
+        return st
 
     # ---- measurement / debugging
     def profile(self, enable: bool):

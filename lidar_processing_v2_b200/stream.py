@@ -50,9 +50,12 @@ class FramePipeline:
     earlier."""
 
     def __init__(self, device: int, max_points: int, batch: int, stages: int = _n.STAGE_ALL,
-                 cluster_cfg: dict | None = None, want=("labels_u8", "obstacle_index", "cluster_labels",
-                                                         "hull_offsets", "hull_xy", "zminmax"), n_ctx: int = 2,
-                 image_height: int = 64):
+                 cluster_cfg: dict | None = None, want=("labels_u8", "cluster_labels", "hull_offsets", "hull_xy",
+                                                         "zminmax"), n_ctx: int = 2,
+                 image_height: int = 64, packed_results: bool = True, result_bytes_per_point: int = 8):
+        """`want`: result planes that come back (obstacle_index is derivable on the host: the ascending positions
+        of label 2). packed_results: one D2H transfer per batch of exactly the occupied bytes
+        (lpl_pipeline_download_packed) instead of one strided copy per plane."""
         if n_ctx < 1:
             raise ValueError("n_ctx must be >= 1")
         self.stages = stages
@@ -67,7 +70,11 @@ class FramePipeline:
                 c.segmenter_config(cfg)
             c.cluster_config(**(cluster_cfg or dict(range_m=0.4, az_deg=1.0, el_deg=3.0, min_size=3)))
         stride = ((max_points + 2047) // 2048) * 2048
-        self.out = [_n.BatchBuffers(batch, stride, want=want) for _ in range(n_ctx)]
+        self.packed_results = packed_results
+        if packed_results:
+            self.out = [_n.PackedBuffers(batch, batch * stride * result_bytes_per_point, want=want) for _ in range(n_ctx)]
+        else:
+            self.out = [_n.BatchBuffers(batch, stride, want=want) for _ in range(n_ctx)]
         self.inflight = [0] * n_ctx
         self.turn = 0
         self.h2d_bytes = 0
@@ -76,19 +83,24 @@ class FramePipeline:
     def submit(self, frames, packed=None, rings=None):
         """Enqueue a batch (list of (n, 4) float32 arrays, ideally views of pinned memory). When the
         frames lie back to back in one buffer, pass it as packed=(array, counts): the batch then crosses
-        PCIe as one transfer. Returns (counts[5][nf], BatchBuffers) of the batch that previously used
-        this slot, or None."""
+        PCIe as one transfer; an (N, 3) array is the 12-byte std::array<float, 3> layout, an (N, 4) array the
+        16-byte PCL layout. Returns (counts[5][nf], result buffers) of the batch that previously used this
+        slot, or None."""
         i = self.turn
         done = self.collect(i)
         if packed is not None:
-            nf = self.ctx[i].upload_packed(packed[0], packed[1])
+            if packed[0].shape[1] == 3:
+                nf = self.ctx[i].upload_packed_xyz(packed[0], packed[1])
+            else:
+                nf = self.ctx[i].upload_packed(packed[0], packed[1])
+            self.h2d_bytes += int(np.sum(packed[1])) * 4 * int(packed[0].shape[1])
         else:
             nf = self.ctx[i].upload(frames, rings=rings)
+            self.h2d_bytes += sum(int(f.shape[0]) for f in frames) * 16
             if rings is not None:
                 self.h2d_bytes += sum(int(r.shape[0]) for r in rings if r is not None) * 2
         self.ctx[i].run(nf, self.stages)
         self.inflight[i] = nf
-        self.h2d_bytes += (int(np.sum(packed[1])) if packed is not None else sum(int(f.shape[0]) for f in frames)) * 16
         self.turn = (self.turn + 1) % self.n_ctx
         return done
 
@@ -96,8 +108,12 @@ class FramePipeline:
         nf = self.inflight[i]
         if nf == 0:
             return None
-        counts = self.ctx[i].download_batch(nf, self.out[i])
-        self.d2h_bytes += self.out[i].bytes_for(counts)
+        if self.packed_results:
+            counts = self.ctx[i].download_packed(nf, self.out[i])
+            self.d2h_bytes += self.out[i].bytes_used + counts.size * 4
+        else:
+            counts = self.ctx[i].download_batch(nf, self.out[i])
+            self.d2h_bytes += self.out[i].bytes_for(counts)
         self.inflight[i] = 0
         return counts, self.out[i]
 

@@ -99,15 +99,21 @@ def parity_ok(rep: dict) -> bool:
     return all(v == 0 for k, v in rep.items() if k.endswith("_diff")) and rep.get("seg_status", 0) == 0
 
 
-def oracle_chain(port: PortOracle, pts, dror: bool, jcp_mode=JCP_AS_IS, cluster_cfg=None):
+def oracle_chain(port: PortOracle, pts, dror: bool, jcp_mode=JCP_AS_IS, cluster_cfg=None, ring="partition"):
     """Chained CPU pipeline: ring -> [DROR -> compaction] -> segment -> obstacle
-    compaction -> cluster -> hulls. Returns a dict in input-index space like Context.download."""
+    compaction -> cluster -> hulls. Returns a dict in input-index space like Context.download.
+    ring: "partition" (stage 0 from the point order), an array (the cloud's own ring field) or None
+    (ring-less point type: height index from the elevation angle)."""
     ccfg = cluster_cfg or NODE_CLUSTER_CFG
     n = pts.shape[0]
-    ring = port.ring_partition(pts)
+    if isinstance(ring, str):
+        ring = port.ring_partition(pts)
     noise = port.dror(pts) if dror else np.zeros(n, np.uint8)
     keep = np.flatnonzero(noise == 0)
-    lv = port.segment(np.ascontiguousarray(pts[keep]), ring[keep], jcp_mode=jcp_mode)
+    lv = port.segment(np.ascontiguousarray(pts[keep]), None if ring is None else np.ascontiguousarray(ring[keep]),
+                      jcp_mode=jcp_mode)
+    if ring is None:
+        ring = np.zeros(n, np.uint16)
     labels = np.zeros(n, np.uint32)
     labels[keep] = lv
     obs_idx = keep[lv == 2]
@@ -119,12 +125,16 @@ def oracle_chain(port: PortOracle, pts, dror: bool, jcp_mode=JCP_AS_IS, cluster_
                 num_clusters=int(cl.max() + 1) if cl.size else 0)
 
 
-def chain_report(got: dict, exp: dict) -> dict:
+def chain_report(got: dict, exp: dict, skip=()) -> dict:
     rep = {}
     for k in ("ring", "noise", "labels", "obstacle_index", "cluster_labels", "hull_offsets"):
+        if k in skip:
+            continue
         a, b = np.asarray(got[k]), np.asarray(exp[k])
         rep[k + "_diff"] = int((a != b).sum()) if a.shape == b.shape else -1
-    for k in ("hull_xy", "zminmax"):
-        a, b = np.asarray(got[k]), np.asarray(exp[k])
-        rep[k + "_diff"] = int((a != b).sum()) if a.shape == b.shape else -1
+    a, b = np.asarray(got["hull_xy"]), np.asarray(exp["hull_xy"])
+    rep["hull_xy_diff"] = int((a != b).sum()) if a.shape == b.shape else -1
+    # z extents bit for bit: the reference keeps the first of equal extremes, observable as the sign of a zero
+    a, b = np.asarray(got["zminmax"], np.float32), np.asarray(exp["zminmax"], np.float32)
+    rep["zminmax_diff"] = int((a.view(np.uint32) != b.view(np.uint32)).sum()) if a.shape == b.shape else -1
     return rep

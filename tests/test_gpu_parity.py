@@ -229,6 +229,58 @@ def test_packed_upload_equals_per_frame_upload(ctx, golden0, golden100):
             assert np.array_equal(got[k], want[f][k]), (f, k)
 
 
+def test_packed_xyz_upload_and_packed_download(ctx, golden0, golden100):
+    """The 12-byte std::array<float, 3> batch upload (noise_remover.hpp:68) and the one-transfer packed
+    download give what the per-frame calls give, for every plane, on a ragged batch with an empty frame."""
+    frames = [golden0["pts"][:50000], golden100["pts"], golden0["pts"][:0], golden0["pts"][:7], golden0["pts"][:2049]]
+    ctx.cluster_config(**NODE_CLUSTER_CFG)
+    stages = lpl.STAGE_ALL | lpl.STAGE_BOXES
+    nf = ctx.upload(frames)
+    ctx.run(nf, stages)
+    ctx.sync(nf)
+    want = [ctx.download(f, want_boxes=True) for f in range(nf)]
+    xyz = np.ascontiguousarray(np.concatenate(frames)[:, :3])
+    nf = ctx.upload_packed_xyz(xyz, [f.shape[0] for f in frames])
+    ctx.run(nf, stages)
+    names = [p[0] for p in lpl.PLANES]
+    bufs = lpl.PackedBuffers(8, 8 * 131072 * 40, want=names)
+    counts = ctx.download_packed(nf, bufs)
+    assert not ctx.status(nf).any()
+    total = 0
+    for f in range(nf):
+        w = want[f]
+        assert counts[:, f].tolist() == [w["n"], w["num_valid"], w["num_obstacles"], w["num_clusters"], w["num_hull_vertices"]]
+        assert np.array_equal(bufs.frame("labels_u8", f), w["labels"].astype(np.uint8))
+        for k in ("noise", "ring", "obstacle_index", "cluster_labels", "hull_offsets", "hull_indices", "hull_xy", "zminmax"):
+            assert np.array_equal(bufs.frame(k, f), w[k]), (f, k)
+        assert bufs.frame("boxes", f).tobytes() == w["boxes"].tobytes()
+        total += w["n"] * 4 + w["num_obstacles"] * 8 + (w["num_clusters"] + 1) * 4 + w["num_hull_vertices"] * 12 + w["num_clusters"] * 88
+    assert total <= bufs.bytes_used <= total + 16 * len(names)   # only the occupied bytes cross PCIe (+ plane alignment)
+    # a subset of the planes, and a host buffer that is too small
+    sub = lpl.PackedBuffers(8, 1 << 20, want=("labels_u8", "hull_xy"))
+    ctx.download_packed(nf, sub)
+    assert np.array_equal(sub.frame("hull_xy", 1), want[1]["hull_xy"])
+    tiny = lpl.PackedBuffers(8, 1024, want=("labels_u8",))
+    with pytest.raises(lpl.LplError) as e:
+        ctx.download_packed(nf, tiny)
+    assert e.value.code == lpl.native.LPL_ERR_CAPACITY
+    for b in (bufs, sub, tiny):
+        b.close()
+
+
+def test_run_without_hulls_reports_no_stale_vertices(ctx, golden0):
+    ctx.cluster_config(**NODE_CLUSTER_CFG)
+    nf = ctx.upload([golden0["pts"]])
+    no_dror = lpl.STAGE_ALL & ~lpl.STAGE_DROR   # the golden counts are those of the node's chain (no DROR)
+    ctx.run(nf, no_dror)
+    ctx.sync(nf)
+    assert ctx.download(0)["num_hull_vertices"] == 1803
+    ctx.run(nf, no_dror & ~lpl.STAGE_HULLS)
+    ctx.sync(nf)
+    out = ctx.download(0)
+    assert out["num_clusters"] == 262 and out["num_hull_vertices"] == 0 and not out["hull_offsets"].any()
+
+
 def test_edge_cases(ctx, port):
     ctx.cluster_config(**NODE_CLUSTER_CFG)
     empty = np.zeros((0, 4), np.float32)
@@ -300,6 +352,35 @@ def test_chained_batch_ragged(ctx, port, golden0, golden100):
             assert np.array_equal(P["hull_xy"][f, :hv], got["hull_xy"])
             assert np.array_equal(P["zminmax"][f, :k], got["zminmax"])
         bufs.close()
+
+
+def test_128_beam_spec_size_full_chain(port):
+    """BASELINE.json configs[2] at the specified size: 128 beams x 2048 columns, 400 boxes + 300 poles, 1 % dropout
+    (~253k points) with its ring field through the WHOLE chain - DROR, segmentation, clustering, hulls - against the
+    port, frame by frame in one batch of two scenes."""
+    scenes = [F.synth_scan(3000 + i, beams=128, n_boxes=400, n_poles=300, n_walls=0, dropout=0.01) for i in range(2)]
+    frames = [s[0] for s in scenes]
+    rings = [s[1] for s in scenes]
+    assert min(f.shape[0] for f in frames) > 240_000
+    c = lpl.Context(0, max_points=max(f.shape[0] for f in frames), max_frames=2, image_height=128, image_width=2048)
+    cfg = c.segmenter_default_cfg()
+    cfg.image_height = 128
+    c.segmenter_config(cfg)
+    c.cluster_config(**NODE_CLUSTER_CFG)
+    port.segment_config(default_seg_cfg(image_height=128))
+    try:
+        nf = c.upload(frames, rings=rings)
+        c.run(nf, lpl.STAGE_ALL & ~lpl.STAGE_RING)
+        c.sync(nf)
+        for f in range(nf):
+            got = c.download(f)
+            exp = parity.oracle_chain(port, frames[f], dror=True, ring=rings[f])
+            rep = parity.chain_report(got, exp)
+            assert all(v == 0 for v in rep.values()), (f, rep)
+            assert got["num_clusters"] > 100 and got["num_hull_vertices"] > 1000
+    finally:
+        port.segment_config(default_seg_cfg())
+        c.close()
 
 
 def test_128_beam_config(port):
@@ -414,6 +495,83 @@ def test_unorganized_2m_cloud_properties(port):
         assert np.all(np.diff(first) > 0)
         sizes = np.bincount(cl1[cl1 >= 0], minlength=k1)
         assert sizes.min() >= 3
+    finally:
+        c.close()
+
+
+def test_unorganized_2m_cloud_full_size_parity(port):
+    """BASELINE.json configs[4] at FULL size against the port (which has no voxel cap): the chained
+    ring-less pipeline on the 2,000,000-point cloud (DROR mask, labels, cluster partition, hulls), and - the
+    part of the config that stresses thousands of small clusters - fine-voxel clustering + hulls + oriented
+    boxes of the 735k DROR-valid non-ground points (5,877 clusters, 333,739 voxels: above the reference's
+    200k-voxel table and above the shared-memory union-find, so the global path runs)."""
+    big = F.synth_unorganized(5000)
+    c = lpl.Context(0, max_points=big.shape[0], max_frames=1)
+    try:
+        c.cluster_config(**NODE_CLUSTER_CFG)
+        nf = c.upload([big])
+        c.run(nf, lpl.STAGE_ALL & ~lpl.STAGE_RING)
+        c.sync(nf)
+        got = c.download(0)
+        exp = parity.oracle_chain(port, big, dror=True, ring=None)
+        rep = parity.chain_report(got, exp, skip=("ring",))
+        assert all(v == 0 for v in rep.values()), rep
+        assert int(exp["noise"].sum()) > 10_000 and exp["num_clusters"] > 300
+        sub = np.ascontiguousarray(big[(exp["noise"] == 0) & (big[:, 2] > -1.55)])
+        fine = dict(range_m=0.2, az_deg=0.25, el_deg=0.5, min_size=3)
+        c.cluster_config(**fine)
+        cl, k = c.cluster(sub)
+        ecl = port.cluster(sub, **fine)
+        assert port.last_num_voxels > 200_000 and k > 5000
+        assert np.array_equal(cl, ecl)
+        off, xy, idx, zmm = c.cluster_hulls(sub, cl)
+        eo, exy, eidx, ezmm = port.cluster_hulls(sub, ecl)
+        assert np.array_equal(off, eo) and np.array_equal(xy, exy.astype(np.float32))
+        assert np.array_equal(zmm, ezmm.astype(np.float32))
+        boxes = c.bounding_boxes(exy, eo, lpl.BOX_ROTATING_CALIPERS)
+        sel = np.random.default_rng(0).choice(k, 400, replace=False)
+        ebox = np.stack([port.bounding_box(exy[eo[j]:eo[j + 1]], lpl.BOX_ROTATING_CALIPERS) for j in sel])
+        _boxes_equal(boxes[sel], ebox, exact=True)
+    finally:
+        c.close()
+
+
+@pytest.mark.skipif(not F.have_pack(), reason="data/kitti154.npz not built")
+def test_full_sequence_chained_with_dror_vs_reference():
+    """BASELINE.json configs[1] at full size, the whole chain INCLUDING DROR as one 154-frame batch: every
+    frame's DROR mask, labels, cluster labels, hull offsets / vertices and z extents hash to what the
+    unmodified reference (exact DROR semantics) produced (tests/golden/kitti154_chain_dror.json,
+    tools/make_golden_chain.py)."""
+    import hashlib
+
+    def sha(a, dt):
+        return hashlib.sha1(np.ascontiguousarray(a, dtype=dt).tobytes()).hexdigest()
+
+    gold = json.load(open(os.path.join(F.GOLDEN_DIR, "kitti154_chain_dror.json")))["frames"]
+    frames = F.load_pack()
+    assert len(gold) == len(frames) == 154
+    c = lpl.Context(0, max_points=max(f.shape[0] for f in frames), max_frames=len(frames))
+    try:
+        c.cluster_config(**NODE_CLUSTER_CFG)
+        xyz = np.ascontiguousarray(np.concatenate(frames)[:, :3])
+        nf = c.upload_packed_xyz(xyz, [f.shape[0] for f in frames])   # the bench's e2e upload path
+        c.run(nf, lpl.STAGE_ALL)
+        bufs = lpl.PackedBuffers(nf, nf * 131072 * 8, want=("labels_u8", "noise", "cluster_labels", "hull_offsets",
+                                                             "hull_xy", "zminmax"))
+        counts = c.download_packed(nf, bufs)
+        bad = []
+        for f, g in enumerate(gold):
+            ok = (counts[0, f] == g["n"] and counts[3, f] == g["clusters"] and counts[4, f] == g["hull_vertices"]
+                  and sha(bufs.frame("noise", f), np.uint8) == g["noise_sha1"]
+                  and sha(bufs.frame("labels_u8", f), np.uint8) == g["labels_sha1"]
+                  and sha(bufs.frame("cluster_labels", f), np.int32) == g["cluster_sha1"]
+                  and sha(bufs.frame("hull_offsets", f), np.uint32) == g["hull_offsets_sha1"]
+                  and sha(bufs.frame("hull_xy", f), np.float32) == g["hull_xy_sha1"]
+                  and sha(bufs.frame("zminmax", f), np.float32) == g["zminmax_sha1"])
+            if not ok:
+                bad.append(f)
+        assert not bad, bad
+        bufs.close()
     finally:
         c.close()
 
