@@ -26,6 +26,19 @@ struct lpl_ctx
     int jcp_mode = LPL_JCP_AS_REFERENCE;
     int have_ring = 0; // ring plane of the current batch is meaningful
     bool ran_hulls = false; // the last lpl_pipeline_run included LPL_STAGE_HULLS (hull_off is this batch's)
+    // CUDA graphs of lpl_pipeline_run, keyed by (frames, stages, image / ring flags); cfg_epoch moves with every
+    // configuration call because kernel arguments (SegParams, ...) are baked into a captured graph
+    struct RunGraph
+    {
+        unsigned long long key;
+        unsigned long long epoch;
+        cudaGraphExec_t exec;
+        unsigned long long launches;
+        int use_ring;
+    };
+    std::vector<RunGraph> graphs;
+    unsigned long long cfg_epoch = 0;
+    bool use_graphs = true;
     std::vector<std::uint32_t> h_status;
 };
 
@@ -55,6 +68,7 @@ void carve(Dev& d, Carver& cv, int npx, int ncell_cap, std::uint32_t** mt_raw)
     cv.take(d.pts_in, B * cap);
     cv.take(d.n_in, B);
     cv.take(d.ring, B * cap);
+    cv.take(d.wrap_cnt, B * (cap / 256));
     cv.take(d.noise, B * cap);
     cv.take(d.grid_cnt, B * kDrorCells);
     cv.take(d.grid_start, B * (kDrorCells + 1));
@@ -144,6 +158,18 @@ void carve(Dev& d, Carver& cv, int npx, int ncell_cap, std::uint32_t** mt_raw)
     cv.take(d.tile_cnt, B * tl);
     cv.take(d.status, B);
     cv.take(*mt_raw, kMtRaws);
+}
+
+void drop_graphs(lpl_ctx* ctx)
+{
+    for (auto& g : ctx->graphs)
+    {
+        if (g.exec != nullptr)
+        {
+            cudaGraphExecDestroy(g.exec);
+        }
+    }
+    ctx->graphs.clear();
 }
 
 int fail(lpl_ctx* ctx, int code, const char* msg)
@@ -461,7 +487,13 @@ int lpl_create(lpl_ctx** out, int device, std::uint32_t max_points, std::uint32_
     {
         return bail(LPL_ERR_CUDA);
     }
-    if (cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking) != cudaSuccess ||
+    // experiment hook (tools/overlap_probe.py): LPL_STREAM_PRIORITY = 0 (default) .. -5 (highest on B200)
+    int prio = 0;
+    if (const char* e = std::getenv("LPL_STREAM_PRIORITY"))
+    {
+        prio = std::atoi(e);
+    }
+    if (cudaStreamCreateWithPriority(&c.stream, cudaStreamNonBlocking, prio) != cudaSuccess ||
         cudaEventCreate(&c.ev0) != cudaSuccess || cudaEventCreate(&c.ev1) != cudaSuccess)
     {
         return bail(LPL_ERR_CUDA);
@@ -498,6 +530,7 @@ int lpl_create(lpl_ctx** out, int device, std::uint32_t max_points, std::uint32_
             return bail(LPL_ERR_CUDA);
         }
     }
+    ctx->use_graphs = std::getenv("LPL_NO_GRAPH") == nullptr;
     lpl_segmenter_default_cfg(&ctx->seg_cfg);
     ctx->seg_cfg.image_height = H;
     ctx->seg_cfg.image_width = W;
@@ -525,6 +558,7 @@ void lpl_destroy(lpl_ctx* ctx)
     {
         cudaStreamSynchronize(c.stream);
     }
+    drop_graphs(ctx);
     if (c.slab != nullptr)
     {
         cudaFree(c.slab);
@@ -559,6 +593,10 @@ const char* lpl_last_error(const lpl_ctx* ctx) { return ctx != nullptr ? ctx->c.
 
 int lpl_segmenter_config(lpl_ctx* ctx, const lpl_segmenter_cfg* cfg)
 {
+    if (ctx != nullptr)
+    {
+        ctx->cfg_epoch += 1; // captured graphs carry the old parameters
+    }
     if (ctx == nullptr || cfg == nullptr)
     {
         return LPL_ERR_INVALID_ARGUMENT;
@@ -576,6 +614,10 @@ int lpl_segmenter_config(lpl_ctx* ctx, const lpl_segmenter_cfg* cfg)
 
 int lpl_dror_config(lpl_ctx* ctx, const lpl_dror_cfg* cfg)
 {
+    if (ctx != nullptr)
+    {
+        ctx->cfg_epoch += 1; // captured graphs carry the old parameters
+    }
     if (ctx == nullptr || cfg == nullptr)
     {
         return LPL_ERR_INVALID_ARGUMENT;
@@ -587,6 +629,10 @@ int lpl_dror_config(lpl_ctx* ctx, const lpl_dror_cfg* cfg)
 
 int lpl_cluster_config(lpl_ctx* ctx, const lpl_cluster_cfg* cfg)
 {
+    if (ctx != nullptr)
+    {
+        ctx->cfg_epoch += 1; // captured graphs carry the old parameters
+    }
     if (ctx == nullptr || cfg == nullptr)
     {
         return LPL_ERR_INVALID_ARGUMENT;
@@ -603,6 +649,10 @@ int lpl_cluster_config(lpl_ctx* ctx, const lpl_cluster_cfg* cfg)
 
 int lpl_set_jcp_mode(lpl_ctx* ctx, int mode)
 {
+    if (ctx != nullptr)
+    {
+        ctx->cfg_epoch += 1; // captured graphs carry the old parameters
+    }
     if (ctx == nullptr || (mode != LPL_JCP_AS_REFERENCE && mode != LPL_JCP_CLEAN))
     {
         return LPL_ERR_INVALID_ARGUMENT;
@@ -806,15 +856,11 @@ int lpl_pipeline_upload_cloud2(lpl_ctx* ctx, const lpl_cloud2_frame* frames, std
     return LPL_OK;
 }
 
-int lpl_pipeline_run(lpl_ctx* ctx, std::uint32_t nf, std::uint32_t stages)
+// every kernel and memset of one pass of the selected stages, on the context stream (also what a graph captures)
+static int enqueue_stages(lpl_ctx* ctx, std::uint32_t nf, std::uint32_t stages)
 {
-    if (ctx == nullptr || nf == 0 || nf > ctx->c.d.B)
-    {
-        return fail(ctx, LPL_ERR_INVALID_ARGUMENT, "bad frame count");
-    }
     Ctx& c = ctx->c;
     Dev& d = c.d;
-    LPL_TRY(cudaSetDevice(c.device));
     if (c.prof_on)
     {
         c.prof_n = 0;
@@ -831,7 +877,8 @@ int lpl_pipeline_run(lpl_ctx* ctx, std::uint32_t nf, std::uint32_t stages)
     LPL_TRY(cudaMemsetAsync(d.n_clusters, 0, sizeof(std::uint32_t) * nf, c.stream));
     LPL_TRY(cudaMemsetAsync(d.n_hull, 0, sizeof(std::uint32_t) * nf, c.stream));
     const bool ring_stage = (stages & LPL_STAGE_RING) != 0;
-    if (ring_stage)
+    const bool fused_front = ring_stage && (stages & LPL_STAGE_DROR) != 0; // one read of the cloud for both stages
+    if (ring_stage && !fused_front)
     {
         launch_ring(&c, nf);
     }
@@ -842,7 +889,7 @@ int lpl_pipeline_run(lpl_ctx* ctx, std::uint32_t nf, std::uint32_t stages)
     c.seg.use_ring = ((ring_stage || ctx->have_ring) && ctx->seg_cfg.assume_unorganized_cloud == 0) ? 1 : 0;
     if (stages & LPL_STAGE_DROR)
     {
-        launch_dror(&c, nf);
+        launch_dror(&c, nf, fused_front);
     }
     if ((stages & LPL_STAGE_SEGMENT) == 0 && (stages & (LPL_STAGE_CLUSTER | LPL_STAGE_HULLS)) != 0)
     {
@@ -873,6 +920,102 @@ int lpl_pipeline_run(lpl_ctx* ctx, std::uint32_t nf, std::uint32_t stages)
         launch_boxes(&c, nf, LPL_BOX_ROTATING_CALIPERS);
     }
     LPL_TRY(cudaGetLastError());
+    return LPL_OK;
+}
+
+
+// The chain is a fixed sequence of ~55 kernels and ~15 memsets whose arguments only depend on (frame count,
+// stages, configuration): from the second run with the same key on, the sequence is replayed as one CUDA graph -
+// one launch instead of ~70, no host work between the kernels (what the single-frame latency is made of).
+// Not while the per-kernel profile is on (its events sit between the kernels), nor with LPL_NO_GRAPH set.
+int lpl_pipeline_run(lpl_ctx* ctx, std::uint32_t nf, std::uint32_t stages)
+{
+    if (ctx == nullptr || nf == 0 || nf > ctx->c.d.B)
+    {
+        return fail(ctx, LPL_ERR_INVALID_ARGUMENT, "bad frame count");
+    }
+    Ctx& c = ctx->c;
+    LPL_TRY(cudaSetDevice(c.device));
+    const bool ring_stage = (stages & LPL_STAGE_RING) != 0;
+    const unsigned long long key = (static_cast<unsigned long long>(nf) << 32) | (static_cast<unsigned long long>(stages & 0xffffu) << 8) |
+                                   (ctx->want_image ? 1u : 0u) | (ctx->have_ring ? 2u : 0u) | (ring_stage ? 4u : 0u);
+    if (c.prof_on || !ctx->use_graphs || !c.hash_clean)
+    {
+        // (the first run of a context also clears the voxel hash planes: not something to replay)
+        return enqueue_stages(ctx, nf, stages);
+    }
+    for (auto& g : ctx->graphs)
+    {
+        if (g.key == key && g.epoch == ctx->cfg_epoch)
+        {
+            ctx->ran_hulls = (stages & LPL_STAGE_HULLS) != 0;
+            c.seg.use_ring = g.use_ring;
+            LPL_TRY(cudaGraphLaunch(g.exec, c.stream));
+            c.launches += g.launches;
+            return LPL_OK;
+        }
+    }
+    if (!ctx->graphs.empty() && ctx->graphs.front().epoch != ctx->cfg_epoch)
+    {
+        drop_graphs(ctx); // configuration changed: kernel arguments baked into the graphs are stale
+    }
+    if (ctx->graphs.size() >= 8)
+    {
+        if (ctx->graphs.front().exec != nullptr)
+        {
+            cudaGraphExecDestroy(ctx->graphs.front().exec);
+        }
+        ctx->graphs.erase(ctx->graphs.begin());
+    }
+    const unsigned long long before = c.launches;
+    if (cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return enqueue_stages(ctx, nf, stages);
+    }
+    const int rc = enqueue_stages(ctx, nf, stages);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(c.stream, &graph);
+    if (rc != 0 || ce != cudaSuccess || graph == nullptr)
+    {
+        cudaGetLastError();
+        if (graph != nullptr)
+        {
+            cudaGraphDestroy(graph);
+        }
+        c.launches = before;
+        return rc != 0 ? rc : enqueue_stages(ctx, nf, stages);
+    }
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess || exec == nullptr)
+    {
+        cudaGetLastError();
+        c.launches = before;
+        return enqueue_stages(ctx, nf, stages);
+    }
+    try
+    {
+        ctx->graphs.push_back({key, ctx->cfg_epoch, exec, c.launches - before, c.seg.use_ring});
+    }
+    catch (...)
+    {
+        cudaGraphExecDestroy(exec);
+        c.launches = before;
+        return enqueue_stages(ctx, nf, stages);
+    }
+    LPL_TRY(cudaGraphLaunch(exec, c.stream));
+    return LPL_OK;
+}
+
+int lpl_pipeline_use_graph(lpl_ctx* ctx, int enable)
+{
+    if (ctx == nullptr)
+    {
+        return LPL_ERR_INVALID_ARGUMENT;
+    }
+    ctx->use_graphs = enable != 0 && std::getenv("LPL_NO_GRAPH") == nullptr;
     return LPL_OK;
 }
 
@@ -1091,7 +1234,7 @@ int lpl_dror_filter(lpl_ctx* ctx, const void* points, std::size_t stride, std::u
     {
         return rc; // empty cloud: valid no-op (kdtree.hpp:167-170)
     }
-    launch_dror(&c, 1);
+    launch_dror(&c, 1, false);
     LPL_TRY(cudaMemcpyAsync(labels_out, c.d.noise, n, cudaMemcpyDeviceToHost, c.stream));
     LPL_TRY(cudaStreamSynchronize(c.stream));
     LPL_TRY(cudaGetLastError());

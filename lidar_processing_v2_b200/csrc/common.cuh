@@ -123,6 +123,7 @@ struct Dev
     float4* pts_in;           // [B][cap]  x,y,z,(unused)
     std::uint32_t* n_in;      // [B]
     std::uint16_t* ring;      // [B][cap]
+    std::uint32_t* wrap_cnt;  // [B][cap / 256] ring wraps per 256-point block (fused ring + DROR scan-line pass)
     // ---- DROR
     std::uint8_t* noise;      // [B][cap]  0 valid, 1 noise
     std::uint32_t* grid_cnt;  // [B][kDrorCells]  (self-cleaning)
@@ -580,7 +581,7 @@ __global__ void k_excl_scan(const std::uint32_t* __restrict__ in, std::uint32_t 
 // host-side launchers implemented per stage
 struct Ctx;
 void launch_ring(Ctx* c, std::uint32_t nf);
-void launch_dror(Ctx* c, std::uint32_t nf);
+void launch_dror(Ctx* c, std::uint32_t nf, bool with_ring);
 void launch_segment(Ctx* c, std::uint32_t nf, bool want_image);
 void launch_take_obstacles(Ctx* c, std::uint32_t nf);
 void launch_cluster(Ctx* c, std::uint32_t nf);

@@ -68,7 +68,7 @@ struct RingWrapPred
 
 __global__ void __launch_bounds__(kTileThreads)
     k_ring_write(RecordedPred pred, const std::uint32_t* __restrict__ n_arr,
-                 const std::uint32_t* __restrict__ tile_cnt, std::uint32_t tiles_per_frame,
+                 const std::uint32_t* __restrict__ tile_cnt, std::uint32_t tiles_per_frame, std::uint32_t cnt_per_tile,
                  std::uint16_t* __restrict__ ring, std::uint32_t cap)
 {
     __shared__ std::uint32_t sh[kItems * (kTileThreads / 32) + 1];
@@ -80,10 +80,12 @@ __global__ void __launch_bounds__(kTileThreads)
     {
         return;
     }
+    // wrap counts of everything ahead of this tile: `cnt_per_tile` counters per 2048-point tile (1 from the
+    // stand-alone counting pass, 8 from the fused DROR scan-line pass with its 256-point blocks)
     std::uint32_t before = 0;
-    for (std::uint32_t t = threadIdx.x; t < blockIdx.x; t += kTileThreads)
+    for (std::uint32_t t = threadIdx.x; t < blockIdx.x * cnt_per_tile; t += kTileThreads)
     {
-        before += tile_cnt[f * tiles_per_frame + t];
+        before += tile_cnt[static_cast<std::size_t>(f) * tiles_per_frame * cnt_per_tile + t];
     }
     before = block_sum(before, sh2);
     bool flag[kItems];
@@ -119,7 +121,7 @@ void launch_ring(Ctx* c, std::uint32_t nf)
     k_compact_count<<<grid, kTileThreads, 0, c->stream>>>(RecordingPred<RingWrapPred>{pred, d.lab, d.cap}, d.n_in, 0u,
                                                           d.tile_cnt, d.tiles);
     mark(c, "ring_count");
-    k_ring_write<<<grid, kTileThreads, 0, c->stream>>>(RecordedPred{d.lab, d.cap}, d.n_in, d.tile_cnt, d.tiles, d.ring,
+    k_ring_write<<<grid, kTileThreads, 0, c->stream>>>(RecordedPred{d.lab, d.cap}, d.n_in, d.tile_cnt, d.tiles, 1u, d.ring,
                                                       d.cap);
     mark(c, "ring_write");
 }
@@ -154,10 +156,12 @@ constexpr int kNearHalo = LPL_DROR_HALO; // scan-line neighbours examined on eac
 // its predecessors / successors on the same ring. Counting those first settles the vast majority
 // of points (VALID as soon as min_neighbours are found) with one coalesced tile load; the
 // remaining points go to the exhaustive grid search. Any input order gives the same result.
+template <bool kWithRing>
 __global__ void __launch_bounds__(256)
     k_dror_near(Dev d, DrorParams prm)
 {
     __shared__ float4 sh[256 + 2 * kNearHalo];
+    __shared__ std::uint32_t s_red[33];
     const std::uint32_t f = blockIdx.y;
     const std::uint32_t n = d.n_in[f];
     const std::uint32_t base = blockIdx.x * 256u;
@@ -179,21 +183,39 @@ __global__ void __launch_bounds__(256)
     __syncthreads();
     const std::uint32_t i = base + threadIdx.x;
     bool unresolved = false;
+    bool wrap = false;
     if (i < n)
     {
         const float4 p = sh[threadIdx.x + kNearHalo];
+        if (kWithRing)
+        {
+            // ring partition, pass 1 (RingWrapPred) on the tile that is in shared memory anyway: the wrap flag of
+            // point i needs point i - 1, which the halo holds
+            if (i != 0 && quadrant_of(p.x, p.y) == 0)
+            {
+                const float4 b = sh[threadIdx.x + kNearHalo - 1];
+                wrap = quadrant_of(b.x, b.y) == 3;
+            }
+            d.lab[static_cast<std::size_t>(f) * d.cap + i] = wrap ? 1 : 0;
+        }
         const float r_sqr = dror_radius_sqr(p.x, p.y, prm);
         std::uint32_t cnt = dror_within(p, p, r_sqr) ? 1u : 0u; // self (dist 0 unless NaN)
+        bool done = false;
 #pragma unroll
         for (int o = 1; o <= kNearHalo; ++o)
         {
-            if (i >= static_cast<std::uint32_t>(o))
+            if (!done)
             {
-                cnt += dror_within(p, sh[threadIdx.x + kNearHalo - o], r_sqr) ? 1u : 0u;
-            }
-            if (i + o < n)
-            {
-                cnt += dror_within(p, sh[threadIdx.x + kNearHalo + o], r_sqr) ? 1u : 0u;
+                if (i >= static_cast<std::uint32_t>(o))
+                {
+                    cnt += dror_within(p, sh[threadIdx.x + kNearHalo - o], r_sqr) ? 1u : 0u;
+                }
+                if (i + o < n)
+                {
+                    cnt += dror_within(p, sh[threadIdx.x + kNearHalo + o], r_sqr) ? 1u : 0u;
+                }
+                // on a continuous surface the two nearest scan neighbours on each side already settle the point
+                done = cnt >= prm.min_neighbours;
             }
         }
         unresolved = cnt < prm.min_neighbours;
@@ -212,6 +234,15 @@ __global__ void __launch_bounds__(256)
         if (unresolved)
         {
             d.unres[static_cast<std::size_t>(f) * d.cap + pos + __popc(m & ((1u << lane_id()) - 1u))] = i;
+        }
+    }
+    if (kWithRing)
+    {
+        // wraps of this 256-point block; k_ring_write sums the blocks ahead of its tile
+        const std::uint32_t wraps = block_sum(wrap ? 1u : 0u, s_red);
+        if (threadIdx.x == 0)
+        {
+            d.wrap_cnt[static_cast<std::size_t>(f) * (d.cap / 256u) + blockIdx.x] = wraps;
         }
     }
 }
@@ -662,13 +693,27 @@ __global__ void __launch_bounds__(1024) k_dror_grid_scan(Dev d)
     }
 }
 
-void launch_dror(Ctx* c, std::uint32_t nf)
+// with_ring: the ring partition (stage 0) rides along - its wrap flags are evaluated by the scan-line pass, which has
+// every point and its predecessor in shared memory, and k_ring_write turns them into ring indices; the cloud is
+// then read once for both stages instead of twice.
+void launch_dror(Ctx* c, std::uint32_t nf, bool with_ring)
 {
     Dev& d = c->d;
     cudaMemsetAsync(d.n_unres, 0, sizeof(std::uint32_t) * nf, c->stream);
     const dim3 grid((d.cap + 255) / 256, nf);
-    k_dror_near<<<grid, 256, 0, c->stream>>>(d, c->dror);
-    mark(c, "dror_near");
+    if (with_ring)
+    {
+        k_dror_near<true><<<grid, 256, 0, c->stream>>>(d, c->dror);
+        mark(c, "front");
+        k_ring_write<<<dim3(d.tiles, nf), kTileThreads, 0, c->stream>>>(RecordedPred{d.lab, d.cap}, d.n_in, d.wrap_cnt, d.tiles,
+                                                                         static_cast<std::uint32_t>(kTile / 256), d.ring, d.cap);
+        mark(c, "ring_write");
+    }
+    else
+    {
+        k_dror_near<false><<<grid, 256, 0, c->stream>>>(d, c->dror);
+        mark(c, "dror_near");
+    }
     cudaMemsetAsync(d.grid_mask, 0, sizeof(std::uint32_t) * (kDrorCells / 32) * nf, c->stream);
     k_dror_mark<<<dim3(per_frame_ctas(8, nf, 256), nf), 256, 0, c->stream>>>(d, c->dror);
     mark(c, "dror_mark");

@@ -38,7 +38,7 @@ EXPORTS = [
     "lpl_cluster_hulls", "lpl_bounding_boxes",
     "lpl_pipeline_upload", "lpl_pipeline_upload_device", "lpl_pipeline_upload_cloud2", "lpl_pipeline_upload_packed",
     "lpl_pipeline_upload_packed_xyz", "lpl_pcd_read",
-    "lpl_pipeline_run", "lpl_pipeline_sync", "lpl_pipeline_status", "lpl_pipeline_download_packed",
+    "lpl_pipeline_run", "lpl_pipeline_use_graph", "lpl_pipeline_sync", "lpl_pipeline_status", "lpl_pipeline_download_packed",
     "lpl_pipeline_want_image", "lpl_pipeline_counts", "lpl_pipeline_download",
     "lpl_pipeline_download_batch", "lpl_host_alloc", "lpl_host_free",
     "lpl_profile_enable", "lpl_profile_read",
@@ -221,6 +221,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     L.lpl_pipeline_status.argtypes = [vp, u32, vp]
     L.lpl_pipeline_download_packed.argtypes = [vp, u32, C.POINTER(PackedResult)]
     L.lpl_pipeline_run.argtypes = [vp, u32, u32]
+    L.lpl_pipeline_use_graph.argtypes = [vp, C.c_int]
+    L.lpl_pipeline_use_graph.restype = C.c_int
     L.lpl_pipeline_sync.argtypes = [vp, u32]
     L.lpl_pipeline_want_image.argtypes = [vp, C.c_int]
     L.lpl_pipeline_counts.argtypes = [vp, u32, C.POINTER(FrameResult)]
@@ -246,7 +248,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     for name in ("lpl_segmenter_config", "lpl_dror_config", "lpl_cluster_config", "lpl_set_jcp_mode",
                  "lpl_ring_partition", "lpl_dror_filter", "lpl_segment", "lpl_cluster",
                  "lpl_convex_hull", "lpl_cluster_hulls", "lpl_pipeline_upload",
-                 "lpl_pipeline_upload_device", "lpl_pipeline_run", "lpl_pipeline_sync",
+                 "lpl_pipeline_upload_device", "lpl_pipeline_run", "lpl_pipeline_use_graph", "lpl_pipeline_sync",
                  "lpl_pipeline_want_image", "lpl_pipeline_counts", "lpl_pipeline_download",
                  "lpl_pipeline_download_batch", "lpl_pipeline_upload_packed", "lpl_pipeline_upload_packed_xyz",
                  "lpl_pipeline_upload_cloud2", "lpl_pipeline_status", "lpl_pipeline_download_packed",
@@ -549,6 +551,9 @@ class Context:
 
     def run(self, nf: int, stages: int = STAGE_ALL):
         self._chk(self.lib.lpl_pipeline_run(self.h, nf, stages))
+
+    def use_graph(self, enable: bool):
+        self._chk(self.lib.lpl_pipeline_use_graph(self.h, 1 if enable else 0))
 
     def sync(self, nf: int):
         self._chk(self.lib.lpl_pipeline_sync(self.h, nf))

@@ -64,6 +64,9 @@ class FramePipeline:
         self.ctx = [_n.Context(device, max_points=max_points, max_frames=batch, image_height=image_height)
                     for _ in range(n_ctx)]
         for c in self.ctx:
+            # several streams rotating on one GPU overlap best kernel by kernel: a whole-chain graph per batch
+            # measured ~5 % slower end to end than plain launches (and ~2 % faster for one stream working alone)
+            c.use_graph(n_ctx == 1)
             if image_height != 64:
                 cfg = c.segmenter_default_cfg()
                 cfg.image_height = image_height

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--splits", default="1,2,3,4")
     ap.add_argument("--workload", default=None)
+    ap.add_argument("--prio", default="", help="comma list of stream priorities per context (0 .. -5), e.g. -5,0,0")
     args = ap.parse_args()
     frames, workload, _, opts = load_frames(None, args.workload)
     stages = lpl.STAGE_ALL if opts["stages"] is None else (lpl.STAGE_ALL & ~lpl.STAGE_RING)
@@ -32,7 +33,9 @@ def main():
         per = (len(frames) + k - 1) // k
         parts = [frames[a:a + per] for a in range(0, len(frames), per)]
         ctxs = []
-        for p in parts:
+        prios = [int(v) for v in args.prio.split(",")] if args.prio else []
+        for j, p in enumerate(parts):
+            os.environ["LPL_STREAM_PRIORITY"] = str(prios[j] if j < len(prios) else 0)
             c = lpl.Context(0, max_points=max_pts, max_frames=len(p), image_height=opts["image_height"])
             c.cluster_config(range_m=0.4, az_deg=1.0, el_deg=3.0, min_size=3)
             c.upload(p, rings=None)
