@@ -19,6 +19,15 @@ namespace lidar_processing_lib
 {
 using ClusterLabel = std::int32_t;
 
+// spherical image of a point (clusterer.hpp:54-59 of the reference); the GPU path keeps these as device planes,
+// the type stays for source compatibility
+struct SphericalPoint
+{
+    float range_m;
+    float azimuth_rad;   // Convention: 0 -> 2 * pi
+    float elevation_rad; // Convention: 0 -> pi
+};
+
 struct ClustererConfiguration
 {
     float voxel_grid_range_resolution_m = 0.4F;
@@ -44,6 +53,7 @@ class Clusterer
     void cluster(const pcl::PointCloud<PointT>& cloud, std::vector<ClusterLabel>& labels)
     {
         labels.assign(cloud.points.size(), INVALID_LABEL);
+        detail::cluster_cache().invalidate();
         if (cloud.points.empty())
         {
             return; // clusterer.cpp:62-65
@@ -57,6 +67,21 @@ class Clusterer
         detail::check(lpl_cluster(ctx, cloud.points.data(), sizeof(PointT), n, labels.data(), &num_clusters), ctx,
                       "Clusterer::cluster");
         num_clusters_ = num_clusters;
+        // remembered for the Polygonizer calls that follow (detail::ClusterCache)
+        detail::ClusterCache& cache = detail::cluster_cache();
+        cache.xyz.resize(static_cast<std::size_t>(n) * 3);
+        for (std::uint32_t i = 0; i < n; ++i)
+        {
+            cache.xyz[3 * i] = cloud.points[i].x;
+            cache.xyz[3 * i + 1] = cloud.points[i].y;
+            cache.xyz[3 * i + 2] = cloud.points[i].z;
+        }
+        cache.labels = labels;
+        cache.num_clusters = num_clusters;
+        cache.next_label = 0;
+        cache.hulls_ready = false;
+        cache.valid = true;
+        cache.index_members();
     }
 
     // extension: number of clusters found by the last call (max label + 1)

@@ -35,6 +35,11 @@ class NoiseRemover final
 {
   public:
     using PointT = std::array<float, 3>; // == KDTree<float, 3>::PointT of the reference
+    struct NeighbourT                     // == KDTree<float, 3>::Neighbour (kdtree.hpp:50-54)
+    {
+        std::uint32_t index;
+        float distance;
+    };
 
     NoiseRemover() = default;
 

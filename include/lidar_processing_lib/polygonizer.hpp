@@ -86,12 +86,63 @@ class Polygonizer final
             return;
         }
         const auto n = static_cast<std::uint32_t>(points.size());
+        if (from_cluster_cache(points, indices))
+        {
+            return;
+        }
         lpl_ctx* ctx = handle_.ensure(n > config_.max_points ? n : config_.max_points);
         indices.resize(n);
         std::uint32_t count = 0;
         detail::check(lpl_convex_hull(ctx, points.data(), sizeof(PointT), n, indices.data(), &count), ctx,
                       "Polygonizer::convexHull");
         indices.resize(count);
+    }
+
+    /// Batched form of the node's per-label loop (processor.cpp:627-663: for every label, gather the cluster's
+    /// points in cloud order, z extent, convexHull): ONE device pass for all clusters of a frame instead of one
+    /// host <-> device round trip per cluster. `cloud` is any container of points with float x, y, z whose first
+    /// 12 bytes are x, y, z (every PCL point type), `labels[i]` in [-1, num_clusters).
+    /// hull k = hull_points[hull_offsets[k] .. hull_offsets[k + 1]) with hull_indices pointing into `cloud`
+    /// (the reference's per-call indices are positions inside the gathered cluster; these are cloud positions);
+    /// z_min_max[k] = {z_min, z_max} as the node computes them.
+    template <typename CloudPointT>
+    void convexHulls(const std::vector<CloudPointT>& cloud, const std::vector<std::int32_t>& labels,
+                     std::uint32_t num_clusters, std::vector<std::uint32_t>& hull_offsets,
+                     std::vector<std::int32_t>& hull_indices, std::vector<PointXY>& hull_points,
+                     std::vector<std::array<double, 2>>& z_min_max)
+    {
+        static_assert(sizeof(CloudPointT) >= 3 * sizeof(float), "points start with float x, y, z");
+        if (labels.size() != cloud.size())
+        {
+            throw std::invalid_argument("Polygonizer::convexHulls: one label per point");
+        }
+        const auto n = static_cast<std::uint32_t>(cloud.size());
+        hull_offsets.assign(static_cast<std::size_t>(num_clusters) + 1, 0U);
+        hull_indices.assign(n, 0);
+        hull_points.clear();
+        z_min_max.assign(num_clusters, {0.0, 0.0});
+        if (n == 0 || num_clusters == 0)
+        {
+            hull_indices.clear();
+            return;
+        }
+        lpl_ctx* ctx = handle_.ensure(n > config_.max_points ? n : config_.max_points);
+        xy_scratch_.resize(static_cast<std::size_t>(n) * 2);
+        z_scratch_.resize(static_cast<std::size_t>(num_clusters) * 2);
+        detail::check(lpl_cluster_hulls(ctx, cloud.data(), sizeof(CloudPointT), labels.data(), n, num_clusters,
+                                        hull_offsets.data(), hull_indices.data(), xy_scratch_.data(), z_scratch_.data()),
+                      ctx, "Polygonizer::convexHulls");
+        const std::uint32_t total = hull_offsets[num_clusters];
+        hull_indices.resize(total);
+        hull_points.resize(total);
+        for (std::uint32_t v = 0; v < total; ++v)
+        {
+            hull_points[v] = {static_cast<double>(xy_scratch_[2 * v]), static_cast<double>(xy_scratch_[2 * v + 1])};
+        }
+        for (std::uint32_t k = 0; k < num_clusters; ++k)
+        {
+            z_min_max[k] = {static_cast<double>(z_scratch_[2 * k]), static_cast<double>(z_scratch_[2 * k + 1])};
+        }
     }
 
     /// Shamos' antipodal pairs of a convex polygon (src/polygonizer.cpp:93-163), host-side.
@@ -178,6 +229,56 @@ class Polygonizer final
     const PolygonizerConfiguration& config() const noexcept { return config_; }
 
   private:
+    // The node calls convexHull once per cluster right after Clusterer::cluster, labels ascending
+    // (processor.cpp:627-663). If `points` is exactly the gather of the next cluster of the thread's last
+    // clustered cloud, answer from ONE batched device pass over all clusters of that cloud. Everything is verified
+    // against the coordinates given, so a caller that does something else simply takes the per-call path.
+    template <typename PointT>
+    bool from_cluster_cache(const std::vector<PointT>& points, std::vector<std::int32_t>& indices)
+    {
+        detail::ClusterCache& c = detail::cluster_cache();
+        if (!c.valid || c.num_clusters == 0)
+        {
+            return false;
+        }
+        const auto n = static_cast<std::uint32_t>(points.size());
+        std::uint32_t l = c.next_label < c.num_clusters ? c.next_label : 0U;
+        if (c.start[l + 1] - c.start[l] != n)
+        {
+            return false;
+        }
+        const std::uint32_t* mem = c.members.data() + c.start[l];
+        for (std::uint32_t j = 0; j < n; ++j)
+        {
+            const float* q = c.xyz.data() + static_cast<std::size_t>(mem[j]) * 3;
+            if (points[j].x != static_cast<double>(q[0]) || points[j].y != static_cast<double>(q[1]))
+            {
+                return false;
+            }
+        }
+        if (!c.hulls_ready)
+        {
+            const auto m = static_cast<std::uint32_t>(c.labels.size());
+            lpl_ctx* ctx = handle_.ensure(m > config_.max_points ? m : config_.max_points);
+            c.hull_off.assign(static_cast<std::size_t>(c.num_clusters) + 1, 0U);
+            c.hull_idx.assign(m, 0);
+            c.hull_xy.assign(static_cast<std::size_t>(m) * 2, 0.F);
+            c.zminmax.assign(static_cast<std::size_t>(c.num_clusters) * 2, 0.F);
+            detail::check(lpl_cluster_hulls(ctx, c.xyz.data(), 3 * sizeof(float), c.labels.data(), m, c.num_clusters,
+                                            c.hull_off.data(), c.hull_idx.data(), c.hull_xy.data(), c.zminmax.data()),
+                          ctx, "Polygonizer::convexHull (batched over the clustered cloud)");
+            c.hulls_ready = true;
+        }
+        const std::uint32_t a = c.hull_off[l], b = c.hull_off[l + 1];
+        indices.resize(b - a);
+        for (std::uint32_t v = a; v < b; ++v)
+        {
+            indices[v - a] = static_cast<std::int32_t>(c.rank[static_cast<std::size_t>(c.hull_idx[v])]);
+        }
+        c.next_label = l + 1;
+        return true;
+    }
+
     static BoundingBox convert(const lpl_bbox& r)
     {
         BoundingBox b{};
@@ -208,6 +309,7 @@ class Polygonizer final
     }
 
     PolygonizerConfiguration config_{};
+    std::vector<float> xy_scratch_, z_scratch_;
     detail::Handle handle_;
 };
 } // namespace lidar_processing_lib

@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstddef>
 #include <cstdint>
+#include <limits>
 #include <ostream>
 #include <type_traits>
 #include <vector>
@@ -85,11 +86,34 @@ struct RingOffset<PointT, std::void_t<decltype(std::declval<PointT>().ring)>>
 };
 } // namespace detail
 
+// One binned point of the polar grid (segmenter.hpp:76-85 of the reference). The GPU path keeps the grid as
+// device planes; the type stays for source compatibility.
+struct SegmenterPoint
+{
+    float x;
+    float y;
+    float z;
+    Label label;
+    std::uint16_t height_index;
+    std::uint16_t width_index;
+    std::uint32_t cloud_index;
+};
+
 class Segmenter
 {
   public:
+    // public constants of the reference class (segmenter.hpp:131-151)
     static constexpr float DEG_TO_RAD = static_cast<float>(M_PI / 180.0);
+    static constexpr float TWO_M_PIf = static_cast<float>(2.0 * M_PI);
+    static constexpr std::int32_t INVALID_INDEX = -1;
+    static constexpr float INVALID_Z = std::numeric_limits<float>::max();
+    static constexpr float INVALID_DEPTH_M = std::numeric_limits<float>::max();
     static constexpr std::uint32_t MAX_CLOUD_SIZE = 200'000U;
+    inline static const cv::Vec3b CV_OBSTACLE{0, 0, 255};
+    inline static const cv::Vec3b CV_GROUND{0, 255, 0};
+    inline static const cv::Vec3b CV_INTERSECTION_OR_UNKNOWN{0, 255, 255};
+    inline static const cv::Vec3b CV_INTERSECTION{255, 0, 0};
+    inline static const cv::Vec3b CV_UNKNOWN{255, 255, 255};
 
     Segmenter() { config(SegmenterConfiguration{}); }
     ~Segmenter() = default;
@@ -99,7 +123,6 @@ class Segmenter
         config_ = config;
         image_.create(config_.image_height, config_.image_width, CV_8UC3);
         image_.setTo(cv::Scalar(0, 0, 0));
-        configured_ = false; // pushed to the device context on the next segment()
     }
 
     inline const SegmenterConfiguration& config() const noexcept { return config_; }
@@ -113,8 +136,8 @@ class Segmenter
         labels.assign(cloud.points.size(), Label::UNKNOWN);
         const auto n = static_cast<std::uint32_t>(cloud.points.size());
         lpl_ctx* ctx = handle_.ensure(n > MAX_CLOUD_SIZE ? n : MAX_CLOUD_SIZE, config_.image_height, config_.image_width);
-        if (!configured_ || ctx != configured_ctx_)
         {
+            // the context is shared with the thread's other adaptor objects: the configuration goes with every call
             lpl_segmenter_cfg c{};
             c.elevation_up_deg = config_.elevation_up_deg;
             c.elevation_down_deg = config_.elevation_down_deg;
@@ -133,8 +156,6 @@ class Segmenter
             c.z_min_m = config_.z_min_m;
             c.z_max_m = config_.z_max_m;
             detail::check(lpl_segmenter_config(ctx, &c), ctx, "Segmenter::config");
-            configured_ = true;
-            configured_ctx_ = ctx;
         }
         // an empty cloud is a valid no-op that still clears the image (segmenter.cpp:73-85,116-119)
         detail::check(lpl_segment(ctx, cloud.points.data(), sizeof(PointT), detail::RingOffset<PointT>::value, n,
@@ -145,8 +166,6 @@ class Segmenter
   private:
     SegmenterConfiguration config_{};
     cv::Mat image_;
-    bool configured_ = false;
-    lpl_ctx* configured_ctx_ = nullptr;
     detail::Handle handle_;
 };
 } // namespace lidar_processing_lib

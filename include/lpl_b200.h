@@ -1,7 +1,7 @@
 /* lpl_b200.h — C ABI of the B200-native LiDAR perception hot path.
  *
  * Drop-in boundary for the reference's `lidar_processing_lib` (a C++ class API, see
- * include/lidar_processing_lib/*.hpp in this repo for the header-only C++ adaptors that keep the
+ * the headers under include/lidar_processing_lib/ in this repo for the header-only C++ adaptors that keep the
  * reference's class / enum / struct names). Every entry point takes plain pointers and sizes;
  * host pointers unless a name ends in `_device`. All functions return 0 on success or a negative
  * lpl_status; lpl_last_error() gives the text. A context owns one CUDA stream, all device scratch

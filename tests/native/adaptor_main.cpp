@@ -6,14 +6,19 @@
 // infrastructure) and linked with liblpl_b200.so.
 //
 // usage: adaptor_main <in.bin> <out.bin>
+//        adaptor_main --time <in.bin> <reps>     per-call latency of the same sequence (JSON on stdout): the node's
+//                                                per-cluster convexHull loop and the batched Polygonizer::convexHulls
 //   in : u32 n, n x (float x, y, z, w), n x u16 ring
 //   out: u32 n, n x u8 noise, n x u32 label, u32 m, m x i32 cluster label, u32 K, K x u32 hull size,
 //        sum(hull size) x (double x, y), K x (8 double corners, float area, float yaw, u32 valid) from
 //        Polygonizer::boundingBoxRotatingCalipers on every hull (processor.cpp:704 passes its points
 //        the same way; dead code in the node)
 // exit code 3: no CUDA device (std::runtime_error from the adaptors), 4: any other exception
+#include <algorithm>
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <iostream>
 #include <vector>
@@ -25,6 +30,145 @@
 
 namespace lpl = lidar_processing_lib;
 
+namespace
+{
+bool read_frame(const char* path, std::vector<float>& xyzw, std::vector<std::uint16_t>& ring)
+{
+    std::FILE* fi = std::fopen(path, "rb");
+    if (fi == nullptr)
+    {
+        return false;
+    }
+    std::uint32_t n = 0;
+    bool ok = std::fread(&n, 4, 1, fi) == 1;
+    if (ok)
+    {
+        xyzw.resize(static_cast<std::size_t>(n) * 4);
+        ring.resize(n);
+        ok = n == 0 || (std::fread(xyzw.data(), 16, n, fi) == n && std::fread(ring.data(), 2, n, fi) == n);
+    }
+    std::fclose(fi);
+    return ok;
+}
+
+double median(std::vector<double> v)
+{
+    std::sort(v.begin(), v.end());
+    return v.empty() ? 0.0 : v[v.size() / 2];
+}
+
+// the node's sequence (processor.cpp:552-663), timed call by call
+int time_sequence(const char* path, int reps)
+{
+    using clk = std::chrono::steady_clock;
+    const auto ms = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    std::vector<float> xyzw;
+    std::vector<std::uint16_t> ring;
+    if (!read_frame(path, xyzw, ring))
+    {
+        return 2;
+    }
+    const auto n = static_cast<std::uint32_t>(ring.size());
+    std::vector<lpl::NoiseRemover::PointT> raw(n);
+    pcl::PointCloud<pcl::PointXYZIR> cloud;
+    cloud.points.resize(n);
+    for (std::uint32_t i = 0; i < n; ++i)
+    {
+        raw[i] = {xyzw[4 * i], xyzw[4 * i + 1], xyzw[4 * i + 2]};
+        auto& p = cloud.points[i];
+        p.x = xyzw[4 * i];
+        p.y = xyzw[4 * i + 1];
+        p.z = xyzw[4 * i + 2];
+        p.intensity = 0.5F;
+        p.ring = ring[i];
+    }
+    lpl::NoiseRemover noise_remover;
+    noise_remover.reserve(200'000U);
+    lpl::Segmenter segmenter;
+    lpl::Clusterer clusterer;
+    lpl::ClustererConfiguration ccfg;
+    ccfg.voxel_grid_elevation_resolution_deg = 3.0F;
+    clusterer.config(ccfg);
+    lpl::Polygonizer polygonizer;
+    std::vector<lpl::NoiseRemoverLabel> noise;
+    std::vector<lpl::Label> labels;
+    std::vector<lpl::ClusterLabel> clabels;
+    pcl::PointCloud<pcl::PointXYZRGB> obstacles;
+    std::vector<double> t_dror, t_seg, t_split, t_clu, t_loop, t_batched;
+    std::size_t hv_loop = 0, hv_batched = 0;
+    std::int32_t max_label = -1;
+    for (int r = 0; r < reps + 2; ++r)
+    {
+        const auto t0 = clk::now();
+        noise_remover.filter(raw, noise);
+        const auto t1 = clk::now();
+        segmenter.segment(cloud, labels);
+        const auto t2 = clk::now();
+        obstacles.points.clear();
+        for (std::uint32_t i = 0; i < n; ++i)
+        {
+            if (labels[i] == lpl::Label::OBSTACLE)
+            {
+                pcl::PointXYZRGB q;
+                q.x = cloud.points[i].x;
+                q.y = cloud.points[i].y;
+                q.z = cloud.points[i].z;
+                obstacles.points.push_back(q);
+            }
+        }
+        const auto t3 = clk::now();
+        clusterer.cluster(obstacles, clabels);
+        const auto t4 = clk::now();
+        max_label = -1;
+        for (const auto l : clabels)
+        {
+            max_label = l > max_label ? l : max_label;
+        }
+        // (a) the node's loop: O(K * M) gather + one convexHull call per cluster
+        std::vector<lpl::PointXY> pts;
+        std::vector<std::int32_t> idx;
+        hv_loop = 0;
+        for (std::int32_t l = 0; l <= max_label; ++l)
+        {
+            pts.clear();
+            for (std::size_t i = 0; i < clabels.size(); ++i)
+            {
+                if (clabels[i] == l)
+                {
+                    pts.push_back({static_cast<double>(obstacles.points[i].x), static_cast<double>(obstacles.points[i].y)});
+                }
+            }
+            polygonizer.convexHull(pts, idx);
+            hv_loop += idx.size();
+        }
+        const auto t5 = clk::now();
+        // (b) the batched extension: one call for all clusters (gather + z extent + hulls on the device)
+        std::vector<std::uint32_t> off;
+        std::vector<std::int32_t> hidx;
+        std::vector<lpl::PointXY> hpts;
+        std::vector<std::array<double, 2>> zmm;
+        polygonizer.convexHulls(obstacles.points, clabels, static_cast<std::uint32_t>(max_label + 1), off, hidx, hpts, zmm);
+        hv_batched = hpts.size();
+        const auto t6 = clk::now();
+        if (r >= 2)
+        {
+            t_dror.push_back(ms(t0, t1));
+            t_seg.push_back(ms(t1, t2));
+            t_split.push_back(ms(t2, t3));
+            t_clu.push_back(ms(t3, t4));
+            t_loop.push_back(ms(t4, t5));
+            t_batched.push_back(ms(t5, t6));
+        }
+    }
+    std::printf("{\"n\": %u, \"clusters\": %d, \"hull_vertices_loop\": %zu, \"hull_vertices_batched\": %zu, \"reps\": %d, "
+                "\"ms\": {\"noise_filter\": %.3f, \"segment\": %.3f, \"label_split_host\": %.3f, \"cluster\": %.3f, "
+                "\"hulls_per_cluster_calls\": %.3f, \"hulls_batched_call\": %.3f}}\n",
+                n, max_label + 1, hv_loop, hv_batched, reps, median(t_dror), median(t_seg), median(t_split), median(t_clu),
+                median(t_loop), median(t_batched));
+    return 0;
+}
+} // namespace
+
 int main(int argc, char** argv)
 {
     if (argc < 3)
@@ -33,6 +177,10 @@ int main(int argc, char** argv)
     }
     try
     {
+        if (std::strcmp(argv[1], "--time") == 0)
+        {
+            return argc >= 4 ? time_sequence(argv[2], std::atoi(argv[3])) : 2;
+        }
         std::FILE* fi = std::fopen(argv[1], "rb");
         if (fi == nullptr)
         {

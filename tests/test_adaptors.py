@@ -48,6 +48,33 @@ def test_adaptors_compile_link_and_fail_loudly_without_gpu(exe, tmp_path, golden
     assert "no CUDA device" in res.stderr and not os.path.exists(fout)
 
 
+def test_find_package_resolves_like_the_reference_package(tmp_path):
+    """cmake/lidar_processing_libConfig.cmake: the node's own `find_package(lidar_processing_lib REQUIRED)` +
+    `target_link_libraries(processor lidar_processing_lib)` (src/processor/CMakeLists.txt:17,51-56) configure and
+    build against this repository with the node's warning flags (-Wall -Wextra -Werror), no edit of the node."""
+    import shutil
+
+    cmake = shutil.which("cmake")
+    if cmake is None:
+        pytest.skip("cmake not installed")
+    lpl.load_library()
+    (tmp_path / "CMakeLists.txt").write_text(
+        "cmake_minimum_required(VERSION 3.16)\nproject(node_like CXX)\nset(CMAKE_CXX_STANDARD 17)\n"
+        "find_package(lidar_processing_lib REQUIRED)\n"
+        f"add_executable(node_like {SRC})\n"
+        "target_compile_options(node_like PRIVATE -Wall -Wextra -Werror)\n"
+        f"target_include_directories(node_like PRIVATE {os.path.join(ROOT, 'oracle', 'shim')})\n"
+        "target_link_libraries(node_like lidar_processing_lib)\n")
+    build = tmp_path / "build"
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    res = subprocess.run([cmake, "-S", str(tmp_path), "-B", str(build), f"-Dlidar_processing_lib_DIR={os.path.join(ROOT, 'cmake')}",
+                          f"-DCMAKE_CXX_COMPILER={cxx}", "-DCMAKE_BUILD_TYPE=Release"], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
+    res = subprocess.run([cmake, "--build", str(build), "-j", "4"], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert os.path.exists(build / "node_like")
+
+
 @pytest.mark.gpu
 def test_adaptors_reproduce_the_reference_call_sequence(exe, tmp_path, golden0, port):
     pts, ring = golden0["pts"], golden0["ring"].astype(np.uint16)
