@@ -24,6 +24,7 @@
  *   lpl_pipeline_upload_cloud2  convert<PointT>(PointCloud2)   src/processor/src/processor.cpp:42-179
  *   lpl_pipeline_upload_packed_xyz  the std::array<float,3> cloud of NoiseRemover::filter   .../noise_remover.hpp:68
  *   lpl_pcd_read            pcl::io::loadPCDFile<PointXYZI>    src/dataloader/src/dataloader.cpp:165
+ *   lpl_pipeline_split_clouds  label split, clustered cloud, marker lines   src/processor/src/processor.cpp:562-579,627-647,206-343
  */
 #ifndef LPL_B200_H
 #define LPL_B200_H
@@ -298,6 +299,38 @@ typedef struct lpl_packed_result
     size_t bytes_used;    /* out: bytes transferred                                                             */
 } lpl_packed_result;
 int lpl_pipeline_download_packed(lpl_ctx* ctx, uint32_t num_frames, lpl_packed_result* res);
+
+/* Processor glue on the device (src/processor/src/processor.cpp): what the node does on the host around the
+ * library calls, for the whole last batch in one call.
+ *   ground / obstacle / unsegmented   the label split of :562-579 - every input point, in cloud order, as a 32-byte
+ *       pcl::PointXYZRGB record (x, y, z, 1.0f | b, g, r, a = 255 | 12 zero bytes) with the node's colours
+ *       (124, 252, 0) / (200, 0, 0) / (255, 255, 0); NOISE points of a DROR run carry label UNKNOWN
+ *   clustered   the cloud of :627-647 - for every cluster label ascending, the cluster's points in obstacle-cloud
+ *       order, one colour per cluster: cluster_colors[frame][k] = {r, g, b}, or (NULL) three std::rand() % 256 draws
+ *       per cluster from the C library stream of a never-seeded process, continued from call to call, as the node does
+ *   marker_points   the LINE_LIST vertices of convertPolygonPointsToMarker (:254-343) for every hull with >= 3
+ *       vertices: 6 * n points of 3 doubles per hull (bottom ring at z_min, top ring at z_max, vertical edges),
+ *       hulls in label order; needs a batch that ran LPL_STAGE_HULLS; at most half the point capacity per frame
+ * Host planes are frame-major: frame f of a cloud plane starts `stride` records after frame f - 1 (marker vertices:
+ * `marker_stride`). counts: [5][num_frames] = ground, obstacle, unsegmented, clustered points, marker vertices.
+ * Any plane pointer may be NULL. Uses the hull stage's sort buffers: call it after the results were downloaded. */
+typedef struct lpl_split_result
+{
+    uint32_t* counts;
+    size_t stride;
+    void* ground;
+    void* obstacle;
+    void* unsegmented;
+    void* clustered;
+    size_t marker_stride;
+    double* marker_points;
+    const uint8_t* cluster_colors; /* nullable; [num_frames][colors_stride][3] */
+    size_t colors_stride;
+} lpl_split_result;
+int lpl_pipeline_split_clouds(lpl_ctx* ctx, uint32_t num_frames, lpl_split_result* res);
+/* First `count` outputs of the C library's rand() after srand(seed) (glibc TYPE_3 generator), host-only: the stream
+ * lpl_pipeline_split_clouds colours clusters with. */
+void lpl_glibc_rand_stream(uint32_t seed, uint32_t count, int32_t* out);
 
 /* PCD v0.7 reader for the reference's data set (FIELDS x y z [intensity], float32, DATA binary or
  * ascii): fills xyzi_out[n][4] (intensity 0 when absent) and *n_out; xyzi_out == NULL only queries

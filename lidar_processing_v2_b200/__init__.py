@@ -21,6 +21,8 @@ from .native import (  # noqa: F401
     BatchBuffers,
     PackedBuffers,
     PLANES,
+    RGB_DTYPE,
+    glibc_rand_stream,
     ClusterCfg,
     Context,
     DrorCfg,

@@ -37,6 +37,12 @@ struct lpl_ctx
         int use_ring;
     };
     std::vector<RunGraph> graphs;
+    // device scratch of lpl_pipeline_split_clouds (allocated on first use) and the replica of the C library's
+    // rand() stream the node colours its clusters with (processor.cpp:629-631)
+    void* split_dev = nullptr;
+    std::size_t split_bytes = 0;
+    std::int32_t rand_r[34] = {0};
+    int rand_i = -1; // -1: not seeded yet
     unsigned long long cfg_epoch = 0;
     bool use_graphs = true;
     std::vector<std::uint32_t> h_status;
@@ -559,6 +565,10 @@ void lpl_destroy(lpl_ctx* ctx)
         cudaStreamSynchronize(c.stream);
     }
     drop_graphs(ctx);
+    if (ctx->split_dev != nullptr)
+    {
+        cudaFree(ctx->split_dev);
+    }
     if (c.slab != nullptr)
     {
         cudaFree(c.slab);
@@ -1615,6 +1625,225 @@ int lpl_pipeline_download_packed(lpl_ctx* ctx, std::uint32_t nf, lpl_packed_resu
     }
     LPL_TRY(cudaStreamSynchronize(c.stream));
     return rc_status;
+}
+
+// ------------------------------------------------------------------------------------------
+// glibc rand() (TYPE_3 additive feedback generator, r[i] = r[i-3] + r[i-31], top 31 bits): the node colours
+// cluster k of every frame with three consecutive std::rand() % 256 draws of the process-wide, never seeded
+// stream (processor.cpp:629-631). A context replays that stream from srand(1), the state a fresh process has.
+// ------------------------------------------------------------------------------------------
+static void glibc_srand(std::int32_t* r, int* pos, std::uint32_t seed)
+{
+    r[0] = static_cast<std::int32_t>(seed == 0u ? 1u : seed);
+    for (int i = 1; i < 31; ++i)
+    {
+        const long long hi = r[i - 1] / 127773, lo = r[i - 1] % 127773;
+        long long w = 16807 * lo - 2836 * hi;
+        if (w < 0)
+        {
+            w += 2147483647;
+        }
+        r[i] = static_cast<std::int32_t>(w);
+    }
+    for (int i = 31; i < 34; ++i)
+    {
+        r[i] = r[i - 31];
+    }
+    *pos = 0;
+    // the state is a ring of 34 words holding the last 34 outputs-before-shift; 310 draws are discarded
+    for (int k = 0; k < 310; ++k)
+    {
+        const int i = *pos;
+        const std::uint32_t v = static_cast<std::uint32_t>(r[(i + 3) % 34]) + static_cast<std::uint32_t>(r[(i + 31) % 34]);
+        r[i % 34] = static_cast<std::int32_t>(v);
+        *pos = (i + 1) % 34;
+    }
+}
+
+static std::int32_t glibc_rand(std::int32_t* r, int* pos)
+{
+    const int i = *pos;
+    // ring index i holds o[t - 34]; o[t] = o[t - 31] + o[t - 3]
+    const std::uint32_t v = static_cast<std::uint32_t>(r[(i + 3) % 34]) + static_cast<std::uint32_t>(r[(i + 31) % 34]);
+    r[i] = static_cast<std::int32_t>(v);
+    *pos = (i + 1) % 34;
+    return static_cast<std::int32_t>(v >> 1);
+}
+
+void lpl_glibc_rand_stream(std::uint32_t seed, std::uint32_t count, std::int32_t* out)
+{
+    std::int32_t r[34];
+    int pos = 0;
+    glibc_srand(r, &pos, seed);
+    for (std::uint32_t k = 0; k < count && out != nullptr; ++k)
+    {
+        out[k] = glibc_rand(r, &pos);
+    }
+}
+
+int lpl_pipeline_split_clouds(lpl_ctx* ctx, std::uint32_t nf, lpl_split_result* r)
+{
+    if (ctx == nullptr || r == nullptr || nf == 0 || nf > ctx->c.d.B || r->counts == nullptr)
+    {
+        return fail(ctx, LPL_ERR_INVALID_ARGUMENT, "bad cloud split request");
+    }
+    Ctx& c = ctx->c;
+    Dev& d = c.d;
+    LPL_TRY(cudaSetDevice(c.device));
+    const cudaMemcpyKind k = cudaMemcpyDeviceToHost;
+    const std::size_t cap = d.cap, B = d.B;
+    // device scratch: 4 cloud planes of B x cap records, marker vertices (cap / 2 per frame), colours (3 B per cluster),
+    // counters: tile counts [B][tiles][3], totals [B][4], marker counts / offsets / totals
+    const std::size_t rec_bytes = 4 * B * cap * 32;
+    const std::size_t mk_verts = cap / 2;
+    const std::size_t mk_bytes = B * mk_verts * 24;
+    const std::size_t col_bytes = (B * cap * 3 + 255) / 256 * 256;
+    const std::size_t cnt_bytes = (B * d.tiles * 3 + B * 4 + B * cap + B * (cap + 1) + B) * 4 + 1024;
+    const std::size_t need = rec_bytes + mk_bytes + col_bytes + cnt_bytes;
+    if (ctx->split_bytes < need)
+    {
+        LPL_TRY(cudaStreamSynchronize(c.stream));
+        if (ctx->split_dev != nullptr)
+        {
+            cudaFree(ctx->split_dev);
+            ctx->split_dev = nullptr;
+            ctx->split_bytes = 0;
+        }
+        if (cudaMalloc(&ctx->split_dev, need) != cudaSuccess)
+        {
+            cudaGetLastError();
+            return fail(ctx, LPL_ERR_CAPACITY, "device allocation for the cloud split failed");
+        }
+        ctx->split_bytes = need;
+    }
+    auto* base = static_cast<unsigned char*>(ctx->split_dev);
+    unsigned char* d_rec = base;
+    auto* d_mk = reinterpret_cast<double*>(base + rec_bytes);
+    auto* d_col = base + rec_bytes + mk_bytes;
+    auto* d_cnt3 = reinterpret_cast<std::uint32_t*>(base + rec_bytes + mk_bytes + col_bytes);
+    std::uint32_t* d_tot = d_cnt3 + B * d.tiles * 3;
+    std::uint32_t* d_mcount = d_tot + B * 4;
+    std::uint32_t* d_moff = d_mcount + B * cap;
+    std::uint32_t* d_mtot = d_moff + B * (cap + 1);
+    // colours: from the caller, or the node's own rand() stream (needs the cluster counts of the batch)
+    std::vector<std::uint32_t> K;
+    std::vector<std::uint8_t> col;
+    try
+    {
+        K.resize(nf);
+        LPL_TRY(cudaMemcpyAsync(K.data(), d.n_clusters, 4 * nf, k, c.stream));
+        const int rc_status = check_status(ctx, nf);
+        if (rc_status != 0)
+        {
+            return rc_status;
+        }
+        col.assign(static_cast<std::size_t>(nf) * cap * 3, 0);
+        for (std::uint32_t f = 0; f < nf; ++f)
+        {
+            if (K[f] > cap)
+            {
+                return fail(ctx, LPL_ERR_CUDA, "internal error: more clusters than points");
+            }
+            for (std::uint32_t q = 0; q < K[f]; ++q)
+            {
+                std::uint8_t* o = col.data() + (static_cast<std::size_t>(f) * cap + q) * 3;
+                if (r->cluster_colors != nullptr)
+                {
+                    const std::uint8_t* src = r->cluster_colors + (static_cast<std::size_t>(f) * r->colors_stride + q) * 3;
+                    if (q >= r->colors_stride)
+                    {
+                        return fail(ctx, LPL_ERR_CAPACITY, "fewer colours than clusters");
+                    }
+                    o[0] = src[0];
+                    o[1] = src[1];
+                    o[2] = src[2];
+                }
+                else
+                {
+                    if (ctx->rand_i < 0)
+                    {
+                        glibc_srand(ctx->rand_r, &ctx->rand_i, 1u);
+                    }
+                    for (int ch = 0; ch < 3; ++ch)
+                    {
+                        o[ch] = static_cast<std::uint8_t>(glibc_rand(ctx->rand_r, &ctx->rand_i) % 256);
+                    }
+                }
+            }
+        }
+    }
+    catch (...)
+    {
+        return fail(ctx, LPL_ERR_CAPACITY, "host allocation for the cluster colours failed");
+    }
+    // one strided H2D copy: K[f] colours per frame (pageable source: the call returns after the bytes are staged)
+    std::uint32_t kmax = 0;
+    for (std::uint32_t f = 0; f < nf; ++f)
+    {
+        kmax = std::max(kmax, K[f]);
+    }
+    if (kmax != 0)
+    {
+        LPL_TRY(cudaMemcpy2DAsync(d_col, cap * 3, col.data(), cap * 3, static_cast<std::size_t>(kmax) * 3, nf, cudaMemcpyHostToDevice,
+                                  c.stream));
+    }
+    launch_split_clouds(&c, nf, d_rec, cap, d_col, static_cast<std::uint32_t>(cap * 3), d_cnt3, d_tot);
+    const bool want_markers = r->marker_points != nullptr;
+    if (want_markers)
+    {
+        if (!ctx->ran_hulls)
+        {
+            return fail(ctx, LPL_ERR_INVALID_ARGUMENT, "marker lines need a batch that ran LPL_STAGE_HULLS");
+        }
+        launch_marker_lines(&c, nf, d_mcount, d_moff, d_mtot, d_mk, mk_verts);
+    }
+    else
+    {
+        LPL_TRY(cudaMemsetAsync(d_mtot, 0, 4 * nf, c.stream));
+    }
+    // counts: [5][nf] = ground, obstacle, unsegmented, clustered, marker vertices
+    std::uint32_t* cn = r->counts;
+    for (int q = 0; q < 4; ++q)
+    {
+        LPL_TRY(cudaMemcpy2DAsync(cn + static_cast<std::size_t>(q) * nf, 4, d_tot + q, 16, 4, nf, k, c.stream));
+    }
+    LPL_TRY(cudaMemcpyAsync(cn + 4 * static_cast<std::size_t>(nf), d_mtot, 4 * nf, k, c.stream));
+    LPL_TRY(cudaStreamSynchronize(c.stream));
+    std::uint32_t mx[5] = {0, 0, 0, 0, 0};
+    for (int q = 0; q < 5; ++q)
+    {
+        for (std::uint32_t f = 0; f < nf; ++f)
+        {
+            mx[q] = std::max(mx[q], cn[static_cast<std::size_t>(q) * nf + f]);
+        }
+    }
+    if (r->stride < std::max(std::max(mx[0], mx[1]), std::max(mx[2], mx[3])))
+    {
+        return fail(ctx, LPL_ERR_CAPACITY, "host cloud stride smaller than the largest cloud");
+    }
+    if (want_markers && (mx[4] > mk_verts || mx[4] > r->marker_stride))
+    {
+        return fail(ctx, LPL_ERR_CAPACITY, "more marker vertices than reserved (half the point capacity) or than the host stride");
+    }
+    void* host[4] = {r->ground, r->obstacle, r->unsegmented, r->clustered};
+    const std::size_t plane = B * cap * 32; // device plane q starts at q * nf * cap records (launch_split_clouds)
+    (void)plane;
+    for (int q = 0; q < 4; ++q)
+    {
+        if (host[q] != nullptr && mx[q] != 0)
+        {
+            LPL_TRY(cudaMemcpy2DAsync(host[q], r->stride * 32, d_rec + static_cast<std::size_t>(q) * nf * cap * 32, cap * 32,
+                                      static_cast<std::size_t>(mx[q]) * 32, nf, k, c.stream));
+        }
+    }
+    if (want_markers && mx[4] != 0)
+    {
+        LPL_TRY(cudaMemcpy2DAsync(r->marker_points, r->marker_stride * 24, d_mk, mk_verts * 24, static_cast<std::size_t>(mx[4]) * 24, nf, k,
+                                  c.stream));
+    }
+    LPL_TRY(cudaStreamSynchronize(c.stream));
+    LPL_TRY(cudaGetLastError());
+    return LPL_OK;
 }
 
 int lpl_host_alloc(void** out, std::size_t bytes)

@@ -355,6 +355,18 @@ __device__ __forceinline__ void tile_ranks(const bool (&flag)[kItems], std::uint
 
 static_assert(kItems * (kTileThreads / 32) == 64, "tile_ranks assumes 64 (round, warp) counters");
 
+// merge passes the frame-wide sort of hull.cu needs for n elements (tiles of kTile): ceil(log2(tiles))
+__host__ __device__ __forceinline__ std::uint32_t sort_passes(std::uint32_t n)
+{
+    const std::uint32_t nt = (n + kTile - 1) / kTile;
+    std::uint32_t p = 0;
+    while ((1u << p) < nt)
+    {
+        ++p;
+    }
+    return p;
+}
+
 // order-preserving float <-> uint32 map (-0.0 folded into +0.0)
 __device__ __forceinline__ std::uint32_t ord_f32(float v)
 {
@@ -588,6 +600,11 @@ void launch_cluster(Ctx* c, std::uint32_t nf);
 void launch_hulls(Ctx* c, std::uint32_t nf);
 void launch_boxes(Ctx* c, std::uint32_t nf, int method);
 void launch_spread_packed(Ctx* c, std::uint32_t nf, const void* packed, const std::uint32_t* start, bool xyz12);
+void launch_hull_sort(Ctx* c, std::uint32_t nf);
+void launch_split_clouds(Ctx* c, std::uint32_t nf, unsigned char* out, std::size_t frame_records, const std::uint8_t* colours,
+                         std::uint32_t colour_stride, std::uint32_t* cnt3, std::uint32_t* totals);
+void launch_marker_lines(Ctx* c, std::uint32_t nf, std::uint32_t* mcount, std::uint32_t* moff, std::uint32_t* mtotal, double* out,
+                         std::size_t frame_stride);
 void launch_pack_results(Ctx* c, std::uint32_t nf, std::uint32_t planes, unsigned char* staging, std::size_t staging_bytes);
 void launch_unpack_cloud2(Ctx* c, std::uint32_t nf, const unsigned char* raw, std::size_t raw_stride, const void* desc);
 void launch_boxes_hulls(Ctx* c, const double2* xy, const std::uint32_t* off, std::uint32_t K, int method, ObbBox* out);

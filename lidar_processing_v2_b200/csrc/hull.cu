@@ -92,12 +92,6 @@ __device__ __forceinline__ bool elem_less(const uint4& a, const uint4& b)
     return a.w < b.w;
 }
 
-__device__ __forceinline__ std::uint32_t sort_passes(std::uint32_t n)
-{
-    const std::uint32_t nt = (n + kTile - 1) / kTile;
-    return nt <= 1 ? 0u : 32u - __clz(nt - 1u); // ceil(log2(nt))
-}
-
 // ------------------------------------------------------------------------------------------
 // polygon filter (Akl-Toussaint): a point strictly inside the polygon spanned by up to kExtDirs
 // extreme points of its cluster cannot be a hull vertex, so it never enters the sort. The
@@ -979,16 +973,12 @@ __global__ void __launch_bounds__(128) k_hull_gather(Dev d)
     }
 }
 
-void launch_hulls(Ctx* c, std::uint32_t nf)
+// frame-wide merge sort of the n_h[f] elements in hsB by (x = label, y, z as floats, w = index); the result is in
+// hsB when sort_passes(n_h[f]) is odd, else in hsA
+void launch_hull_sort(Ctx* c, std::uint32_t nf)
 {
     Dev& d = c->d;
     cudaStream_t s = c->stream;
-    k_hull_octagon<<<dim3(4, nf), 128, 0, s>>>(d);
-    mark(c, "hull_octagon");
-    // d.lab (RECM labels of the segmenter) is free by now: it holds the recorded verdicts
-    launch_compact_recorded(c, "hull_keep", nf, d.tiles, d.n_o, d.tile_cnt, d.n_h, d.lab, HullKeepPred{d}, HullKeepEmit{d});
-    k_excl_scan<<<nf, 1024, 0, s>>>(d.hseg_cnt, d.cap, d.cstart, d.cap + 1, d.cap, d.n_clusters, nullptr);
-    mark(c, "hull_seg_scan");
     k_hull_tilesort<<<dim3(d.tiles, nf), kTileThreads, 0, s>>>(d);
     mark(c, "hull_tilesort");
     std::uint32_t passes = 0;
@@ -1002,6 +992,19 @@ void launch_hulls(Ctx* c, std::uint32_t nf)
         k_hull_merge<<<dim3(d.tiles, nf), kTileThreads, 0, s>>>(d, p);
         mark(c, "hull_merge");
     }
+}
+
+void launch_hulls(Ctx* c, std::uint32_t nf)
+{
+    Dev& d = c->d;
+    cudaStream_t s = c->stream;
+    k_hull_octagon<<<dim3(4, nf), 128, 0, s>>>(d);
+    mark(c, "hull_octagon");
+    // d.lab (RECM labels of the segmenter) is free by now: it holds the recorded verdicts
+    launch_compact_recorded(c, "hull_keep", nf, d.tiles, d.n_o, d.tile_cnt, d.n_h, d.lab, HullKeepPred{d}, HullKeepEmit{d});
+    k_excl_scan<<<nf, 1024, 0, s>>>(d.hseg_cnt, d.cap, d.cstart, d.cap + 1, d.cap, d.n_clusters, nullptr);
+    mark(c, "hull_seg_scan");
+    launch_hull_sort(c, nf);
     constexpr std::size_t big_smem = static_cast<std::size_t>(2) * kBigThreads * kLaneStack * (sizeof(float2) + sizeof(std::uint32_t));
     cudaFuncSetAttribute(k_hull_thin_big, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(big_smem));
     k_hull_thin_big<<<dim3(per_frame_ctas(kBigCtasPerFrame, nf, 64), nf), kBigThreads, big_smem, s>>>(d);

@@ -39,6 +39,7 @@ EXPORTS = [
     "lpl_pipeline_upload", "lpl_pipeline_upload_device", "lpl_pipeline_upload_cloud2", "lpl_pipeline_upload_packed",
     "lpl_pipeline_upload_packed_xyz", "lpl_pcd_read",
     "lpl_pipeline_run", "lpl_pipeline_use_graph", "lpl_pipeline_sync", "lpl_pipeline_status", "lpl_pipeline_download_packed",
+    "lpl_pipeline_split_clouds", "lpl_glibc_rand_stream",
     "lpl_pipeline_want_image", "lpl_pipeline_counts", "lpl_pipeline_download",
     "lpl_pipeline_download_batch", "lpl_host_alloc", "lpl_host_free",
     "lpl_profile_enable", "lpl_profile_read",
@@ -154,6 +155,32 @@ class PackedResult(C.Structure):
     ]
 
 
+class SplitResult(C.Structure):
+    _fields_ = [
+        ("counts", C.c_void_p),
+        ("stride", C.c_size_t),
+        ("ground", C.c_void_p),
+        ("obstacle", C.c_void_p),
+        ("unsegmented", C.c_void_p),
+        ("clustered", C.c_void_p),
+        ("marker_stride", C.c_size_t),
+        ("marker_points", C.c_void_p),
+        ("cluster_colors", C.c_void_p),
+        ("colors_stride", C.c_size_t),
+    ]
+
+
+# numpy view of pcl::PointXYZRGB (32 bytes)
+RGB_DTYPE = np.dtype([("xyz", np.float32, 3), ("w", np.float32), ("bgra", np.uint8, 4), ("pad", np.uint32, 3)])
+
+
+def glibc_rand_stream(seed: int, count: int) -> np.ndarray:
+    """First `count` outputs of the C library's rand() after srand(seed) (host-only utility)."""
+    out = np.zeros(count, np.int32)
+    load_library().lpl_glibc_rand_stream(seed, count, out.ctypes.data)
+    return out
+
+
 def pcd_read(path: str, lib=None) -> np.ndarray:
     """(n, 4) float32 x, y, z, intensity of a PCD file (lpl_pcd_read)."""
     lib = lib or load_library()
@@ -220,6 +247,10 @@ def load_library(path: str | None = None) -> C.CDLL:
     L.lpl_pipeline_upload_packed_xyz.argtypes = [vp, vp, vp, u32]
     L.lpl_pipeline_status.argtypes = [vp, u32, vp]
     L.lpl_pipeline_download_packed.argtypes = [vp, u32, C.POINTER(PackedResult)]
+    L.lpl_pipeline_split_clouds.argtypes = [vp, u32, C.POINTER(SplitResult)]
+    L.lpl_pipeline_split_clouds.restype = C.c_int
+    L.lpl_glibc_rand_stream.argtypes = [u32, u32, vp]
+    L.lpl_glibc_rand_stream.restype = None
     L.lpl_pipeline_run.argtypes = [vp, u32, u32]
     L.lpl_pipeline_use_graph.argtypes = [vp, C.c_int]
     L.lpl_pipeline_use_graph.restype = C.c_int
@@ -252,6 +283,7 @@ def load_library(path: str | None = None) -> C.CDLL:
                  "lpl_pipeline_want_image", "lpl_pipeline_counts", "lpl_pipeline_download",
                  "lpl_pipeline_download_batch", "lpl_pipeline_upload_packed", "lpl_pipeline_upload_packed_xyz",
                  "lpl_pipeline_upload_cloud2", "lpl_pipeline_status", "lpl_pipeline_download_packed",
+    "lpl_pipeline_split_clouds", "lpl_glibc_rand_stream",
                  "lpl_profile_enable", "lpl_profile_read",
                  "lpl_timer_start", "lpl_timer_stop_ms", "lpl_debug_segment", "lpl_debug_cluster"):
         getattr(L, name).restype = C.c_int
@@ -608,6 +640,32 @@ class Context:
         r.planes = bufs.planes_mask
         self._chk(self.lib.lpl_pipeline_download_packed(self.h, nf, C.byref(r)))
         return bufs._set(nf, r)
+
+    def split_clouds(self, nf: int, stride: int, markers: bool = True, colors=None) -> dict:
+        """Label split + clustered cloud (+ marker lines) of the last batch (lpl_pipeline_split_clouds). Returns per
+        frame lists of RGB_DTYPE record arrays and (n, 3) float64 marker vertices. colors: (nf, K, 3) uint8 or None
+        (the node's rand() stream)."""
+        counts = np.zeros((5, nf), np.uint32)
+        planes = {k: np.zeros((nf, stride), RGB_DTYPE) for k in ("ground", "obstacle", "unsegmented", "clustered")}
+        mk_stride = max(stride // 2, 1)
+        mk = np.zeros((nf, mk_stride, 3), np.float64) if markers else None
+        r = SplitResult()
+        r.counts = counts.ctypes.data
+        r.stride = stride
+        for k, v in planes.items():
+            setattr(r, k, v.ctypes.data)
+        r.marker_stride = mk_stride
+        r.marker_points = mk.ctypes.data if markers else None
+        keep = None
+        if colors is not None:
+            keep = np.ascontiguousarray(colors, np.uint8)
+            r.cluster_colors = keep.ctypes.data
+            r.colors_stride = keep.shape[1]
+        self._chk(self.lib.lpl_pipeline_split_clouds(self.h, nf, C.byref(r)))
+        out = {k: [planes[k][f, : counts[i, f]] for f in range(nf)] for i, k in enumerate(("ground", "obstacle", "unsegmented", "clustered"))}
+        out["markers"] = [mk[f, : counts[4, f]] for f in range(nf)] if markers else None
+        out["counts"] = counts
+        return out
 
     def status(self, nf: int) -> np.ndarray:
         """Per-frame capacity flags of the last run (0 = good)."""

@@ -98,3 +98,18 @@ def test_pcd_reader(tmp_path):
         ref_file = "/root/reference/data/0000000000.pcd"
         got = lpl.pcd_read(ref_file)
         assert got.shape == (123398, 4) and np.array_equal(got, read_pcd_xyzi(ref_file))
+
+
+def test_glibc_rand_replica_matches_libc():
+    """lpl_pipeline_split_clouds colours clusters with the C library's rand() % 256 as the node does
+    (processor.cpp:629-631); the replica of glibc's generator is checked against libc itself."""
+    import ctypes
+
+    import lidar_processing_v2_b200 as lpl
+
+    libc = ctypes.CDLL("libc.so.6")
+    for seed in (1, 42, 2024):
+        libc.srand(seed)
+        exp = np.array([libc.rand() for _ in range(2000)], np.int32)
+        assert np.array_equal(lpl.glibc_rand_stream(seed, 2000), exp)
+    assert np.array_equal(lpl.glibc_rand_stream(0, 10), lpl.glibc_rand_stream(1, 10))  # srand(0) == srand(1)

@@ -281,6 +281,71 @@ def test_run_without_hulls_reports_no_stale_vertices(ctx, golden0):
     assert out["num_clusters"] == 262 and out["num_hull_vertices"] == 0 and not out["hull_offsets"].any()
 
 
+def test_processor_glue_split_clouds_and_markers(port, golden0, golden100):
+    """lpl_pipeline_split_clouds against the node's host loops (processor.cpp:562-579 label split, :627-647 clustered
+    cloud with std::rand() colours, :254-343 marker line lists), restated here in numpy on the oracle's chain."""
+    frames = [golden0["pts"], golden100["pts"][:70001].copy(), golden0["pts"][:0], golden0["pts"][:300].copy()]
+    c = lpl.Context(0, max_points=131072, max_frames=4)
+    try:
+        c.cluster_config(**NODE_CLUSTER_CFG)
+        nf = c.upload(frames)
+        c.run(nf, lpl.STAGE_ALL & ~lpl.STAGE_DROR)     # the node's chain
+        c.sync(nf)
+        res = [c.download(f) for f in range(nf)]
+        got = c.split_clouds(nf, 131072)
+        rnd = lpl.glibc_rand_stream(1, 3 * sum(r["num_clusters"] for r in res)) % 256   # a fresh context = a fresh process
+        ro = 0
+        for f, pts in enumerate(frames):
+            exp = parity.oracle_chain(port, pts, dror=False)
+            lab = exp["labels"]
+            for name, sel, rgb in (("ground", lab == 1, (124, 252, 0)), ("obstacle", lab == 2, (200, 0, 0)),
+                                   ("unsegmented", (lab != 1) & (lab != 2), (255, 255, 0))):
+                g = got[name][f]
+                assert g.shape[0] == int(sel.sum()), (f, name)
+                assert np.array_equal(g["xyz"], pts[sel][:, :3]) and np.all(g["w"] == 1.0)
+                assert np.all(g["bgra"] == np.array([rgb[2], rgb[1], rgb[0], 255], np.uint8)) and not g["pad"].any()
+            obs = pts[lab == 2]
+            cl = exp["cluster_labels"]
+            K = exp["num_clusters"]
+            order = np.concatenate([np.flatnonzero(cl == k) for k in range(K)]) if K else np.zeros(0, np.int64)
+            g = got["clustered"][f]
+            assert g.shape[0] == order.shape[0]
+            assert np.array_equal(g["xyz"], obs[order][:, :3])
+            cols = rnd[ro:ro + 3 * K].reshape(K, 3).astype(np.uint8)   # r, g, b per cluster, in label order
+            ro += 3 * K
+            exp_bgra = np.stack([cols[cl[order], 2], cols[cl[order], 1], cols[cl[order], 0], np.full(order.shape[0], 255, np.uint8)], -1) \
+                if K else np.zeros((0, 4), np.uint8)
+            assert np.array_equal(g["bgra"], exp_bgra)
+            # markers
+            off, xy, zmm = exp["hull_offsets"], exp["hull_xy"].astype(np.float64), exp["zminmax"].astype(np.float64)
+            lines = []
+            for k in range(K):
+                p = xy[off[k]:off[k + 1]]
+                n = p.shape[0]
+                if n < 3:
+                    continue
+                for z in (zmm[k, 0], zmm[k, 1]):
+                    for i in list(range(1, n)) + [0]:
+                        a, b = p[i - 1], p[i]
+                        lines += [[a[0], a[1], z], [b[0], b[1], z]]
+                for q in p:
+                    lines += [[q[0], q[1], zmm[k, 0]], [q[0], q[1], zmm[k, 1]]]
+            lines = np.array(lines, np.float64).reshape(-1, 3)
+            assert got["markers"][f].shape == lines.shape and np.array_equal(got["markers"][f], lines), f
+        # caller-supplied colours
+        kmax = max(r["num_clusters"] for r in res)
+        mine = np.random.default_rng(0).integers(0, 256, (nf, kmax, 3)).astype(np.uint8)
+        got2 = c.split_clouds(nf, 131072, markers=False, colors=mine)
+        g = got2["clustered"][0]
+        cl0 = res[0]["cluster_labels"]
+        order = np.concatenate([np.flatnonzero(cl0 == k) for k in range(res[0]["num_clusters"])])
+        assert np.array_equal(g["bgra"][:, 2], mine[0, cl0[order], 0]) and np.array_equal(g["bgra"][:, 0], mine[0, cl0[order], 2])
+        # the hull results of the batch are still intact after the split reused the sort buffers
+        assert np.array_equal(c.download(0)["hull_xy"], res[0]["hull_xy"])
+    finally:
+        c.close()
+
+
 def test_edge_cases(ctx, port):
     ctx.cluster_config(**NODE_CLUSTER_CFG)
     empty = np.zeros((0, 4), np.float32)
