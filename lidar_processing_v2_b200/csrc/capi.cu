@@ -74,7 +74,7 @@ void carve(Dev& d, Carver& cv, int npx, int ncell_cap, std::uint32_t** mt_raw)
     cv.take(d.pts_in, B * cap);
     cv.take(d.n_in, B);
     cv.take(d.ring, B * cap);
-    cv.take(d.wrap_cnt, B * (cap / 256));
+    cv.take(d.wrap_cnt, B * (cap / 32));
     cv.take(d.noise, B * cap);
     cv.take(d.grid_cnt, B * kDrorCells);
     cv.take(d.grid_start, B * (kDrorCells + 1));

@@ -549,9 +549,9 @@ __global__ void __launch_bounds__(256) k_clu_labels(Dev d)
     if (i < n)
     {
         const std::size_t ho = static_cast<std::size_t>(f) * d.hcap;
+        const float4 p = d.pts_o[o + i]; // in flight while the three dependent look-ups below resolve
         l = d.hlabel[ho + d.hroot[ho + d.vslot[o + i]]];
         d.clabel[o + i] = l;
-        const float4 p = d.pts_o[o + i];
         x = p.x;
         y = p.y;
         z = p.z;

@@ -123,7 +123,7 @@ struct Dev
     float4* pts_in;           // [B][cap]  x,y,z,(unused)
     std::uint32_t* n_in;      // [B]
     std::uint16_t* ring;      // [B][cap]
-    std::uint32_t* wrap_cnt;  // [B][cap / 256] ring wraps per 256-point block (fused ring + DROR scan-line pass)
+    std::uint32_t* wrap_cnt;  // [B][cap / 32] ring wraps per warp of 32 points (fused ring + DROR scan-line pass)
     // ---- DROR
     std::uint8_t* noise;      // [B][cap]  0 valid, 1 noise
     std::uint32_t* grid_cnt;  // [B][kDrorCells]  (self-cleaning)

@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(kTileThreads)
         return;
     }
     // wrap counts of everything ahead of this tile: `cnt_per_tile` counters per 2048-point tile (1 from the
-    // stand-alone counting pass, 8 from the fused DROR scan-line pass with its 256-point blocks)
+    // stand-alone counting pass, 64 per-warp counters from the fused DROR scan-line pass)
     std::uint32_t before = 0;
     for (std::uint32_t t = threadIdx.x; t < blockIdx.x * cnt_per_tile; t += kTileThreads)
     {
@@ -161,7 +161,6 @@ __global__ void __launch_bounds__(256)
     k_dror_near(Dev d, DrorParams prm)
 {
     __shared__ float4 sh[256 + 2 * kNearHalo];
-    __shared__ std::uint32_t s_red[33];
     const std::uint32_t f = blockIdx.y;
     const std::uint32_t n = d.n_in[f];
     const std::uint32_t base = blockIdx.x * 256u;
@@ -238,11 +237,12 @@ __global__ void __launch_bounds__(256)
     }
     if (kWithRing)
     {
-        // wraps of this 256-point block; k_ring_write sums the blocks ahead of its tile
-        const std::uint32_t wraps = block_sum(wrap ? 1u : 0u, s_red);
-        if (threadIdx.x == 0)
+        // wraps of this warp's 32 points (no block reduction: its barriers were the kernel's top stall);
+        // k_ring_write sums the counters ahead of its tile
+        const std::uint32_t wm = __ballot_sync(0xffffffffu, wrap);
+        if (lane_id() == 0)
         {
-            d.wrap_cnt[static_cast<std::size_t>(f) * (d.cap / 256u) + blockIdx.x] = wraps;
+            d.wrap_cnt[static_cast<std::size_t>(f) * (d.cap / 32u) + (i >> 5)] = __popc(wm);
         }
     }
 }
@@ -706,7 +706,7 @@ void launch_dror(Ctx* c, std::uint32_t nf, bool with_ring)
         k_dror_near<true><<<grid, 256, 0, c->stream>>>(d, c->dror);
         mark(c, "front");
         k_ring_write<<<dim3(d.tiles, nf), kTileThreads, 0, c->stream>>>(RecordedPred{d.lab, d.cap}, d.n_in, d.wrap_cnt, d.tiles,
-                                                                         static_cast<std::uint32_t>(kTile / 256), d.ring, d.cap);
+                                                                         static_cast<std::uint32_t>(kTile / 32), d.ring, d.cap);
         mark(c, "ring_write");
     }
     else

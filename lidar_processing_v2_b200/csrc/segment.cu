@@ -65,10 +65,20 @@ __global__ void __launch_bounds__(256) k_seg_bin(Dev d, SegParams sp)
     const std::size_t o = static_cast<std::size_t>(f) * d.cap;
     std::int32_t cell = -1;
     std::uint32_t px = 0;
-    const bool valid = i < n && d.noise[o + i] == 0;
+    // the three loads of a point (noise flag, coordinates, ring) are independent: issue them together instead of
+    // one round trip after the other (the kernel is bound by exactly that latency chain, not by bandwidth)
+    std::uint8_t nz = 1;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    std::uint16_t ring_i = 0;
+    if (i < n)
+    {
+        nz = d.noise[o + i];
+        p = d.pts_in[o + i];
+        ring_i = sp.use_ring ? d.ring[o + i] : std::uint16_t(0);
+    }
+    const bool valid = i < n && nz == 0;
     if (valid)
     {
-        const float4 p = d.pts_in[o + i];
         if (!(p.z < sp.z_lo || p.z > sp.z_hi))
         {
             const float dist = sqrtf(p.x * p.x + p.y * p.y);
@@ -82,7 +92,7 @@ __global__ void __launch_bounds__(256) k_seg_bin(Dev d, SegParams sp)
                 bool ok = true;
                 if (sp.use_ring)
                 {
-                    hgt = static_cast<std::int32_t>(d.ring[o + i]);
+                    hgt = static_cast<std::int32_t>(ring_i);
                     ok = hgt < sp.H;
                 }
                 else
@@ -146,11 +156,14 @@ __global__ void __launch_bounds__(256) k_seg_scatter(Dev d, SegParams sp)
         return;
     }
     const std::size_t o = static_cast<std::size_t>(f) * d.cap;
+    // independent loads first (cell, slot, z), then the one dependent look-up (the cell's start)
     const std::int32_t cell = d.cell[o + i];
+    const std::uint32_t slot = d.slot[o + i];
+    const float z = d.pts_in[o + i].z;
     if (cell >= 0)
     {
         const std::uint32_t s = d.cell_start[static_cast<std::size_t>(f) * (sp.ncell + 1) + cell];
-        d.zo[o + s + d.slot[o + i]] = make_uint2(i, __float_as_uint(d.pts_in[o + i].z));
+        d.zo[o + s + slot] = make_uint2(i, __float_as_uint(z));
     }
 }
 
@@ -478,10 +491,10 @@ __global__ void __launch_bounds__(256) k_seg_label(Dev d, SegParams sp)
     if (i < n)
     {
         const std::int32_t c = d.cell[o + i];
+        pt = d.pts_in[o + i]; // in flight together with the cell index (only the elevation look-up depends on it)
         std::uint8_t l = 0;
         if (c >= 0)
         {
-            pt = d.pts_in[o + i];
             const float z = pt.z;
             const float e = d.elev[static_cast<std::size_t>(f) * sp.ncell + c];
             l = (z >= e + sp.thr) ? PX_OBSTACLE : PX_GROUND;
@@ -904,13 +917,16 @@ __global__ void __launch_bounds__(256) k_seg_image(Dev d, SegParams sp)
         return;
     }
     const std::size_t o = static_cast<std::size_t>(f) * d.cap;
+    // cell, coordinates, label and pixel are independent loads: all in flight before the first use
     const std::int32_t c = d.cell[o + i];
+    const float4 p = d.pts_in[o + i];
+    const std::uint8_t lab_i = d.lab[o + i];
+    const std::uint32_t px_i = d.px[o + i];
     if (c < 0)
     {
         return;
     }
-    const float4 p = d.pts_in[o + i];
-    std::uint8_t l = d.lab[o + i] & 0x7f;
+    std::uint8_t l = lab_i & 0x7f;
     if (s_have && (c % sp.rings) < kRansacBins)
     {
         const float4 pl = s_plane;
@@ -925,7 +941,7 @@ __global__ void __launch_bounds__(256) k_seg_image(Dev d, SegParams sp)
     const unsigned long long key = (static_cast<unsigned long long>(__float_as_uint(d2)) << 33) |
                                    (static_cast<unsigned long long>(c / sp.rings) << sp.idx_bits) |
                                    static_cast<unsigned long long>(i);
-    atomicMin(&d.key[static_cast<std::size_t>(f) * sp.npx + d.px[o + i]], key);
+    atomicMin(&d.key[static_cast<std::size_t>(f) * sp.npx + px_i], key);
 }
 
 __global__ void __launch_bounds__(256) k_seg_px(Dev d, SegParams sp)
