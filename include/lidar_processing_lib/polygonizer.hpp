@@ -67,6 +67,57 @@ struct AntipodalPair final
     std::int32_t index_2;
 };
 
+// free helpers of the reference header (polygonizer.hpp:176-231), used by the node's shape matching
+template <typename PointT>
+inline double crossProduct(const PointT& p1, const PointT& p2) noexcept
+{
+    return (p1.x * p2.y) - (p2.x * p1.y);
+}
+
+/// Polygon area by the shoelace formula.
+template <typename PointT>
+inline double polygonArea(const std::vector<PointT>& points) noexcept
+{
+    double area = 0.0;
+    if (const auto n = static_cast<std::int32_t>(points.size()); n > 2)
+    {
+        for (std::int32_t i = 0; i < n - 1; ++i)
+        {
+            area += crossProduct(points[i], points[i + 1]);
+        }
+        area += crossProduct(points[n - 1], points[0]);
+    }
+    return std::fabs(area) * 0.5;
+}
+
+template <typename PointT>
+inline double distanceSquared(const PointT& p1, const PointT& p2) noexcept
+{
+    const double dx = p1.x - p2.x;
+    const double dy = p1.y - p2.y;
+    return dx * dx + dy * dy;
+}
+
+template <typename PointT>
+inline double distance(const PointT& p1, const PointT& p2) noexcept
+{
+    return std::sqrt(distanceSquared(p1, p2));
+}
+
+/// Area of a rectangle with 4 ordered vertices.
+template <typename PointT>
+inline double areaOfRectangle(const PointT& p1, const PointT& p2, const PointT& p3, [[maybe_unused]] const PointT& p4) noexcept
+{
+    return std::sqrt(distanceSquared(p1, p2) * distanceSquared(p2, p3));
+}
+
+/// Area of a triangle with 3 ordered vertices.
+template <typename PointT>
+inline double areaOfTriangle(const PointT& p1, const PointT& p2, const PointT& p3) noexcept
+{
+    return std::fabs((p1.x * (p2.y - p3.y) + p2.x * (p3.y - p1.y) + p3.x * (p1.y - p2.y)) * 0.5);
+}
+
 class Polygonizer final
 {
   public:

@@ -24,6 +24,8 @@
  *   lpl_pipeline_upload_cloud2  convert<PointT>(PointCloud2)   src/processor/src/processor.cpp:42-179
  *   lpl_pipeline_upload_packed_xyz  the std::array<float,3> cloud of NoiseRemover::filter   .../noise_remover.hpp:68
  *   lpl_pcd_read            pcl::io::loadPCDFile<PointXYZI>    src/dataloader/src/dataloader.cpp:165
+ *   lpl_vehicle_match       vehicle shape matching             src/processor/src/processor.cpp:680-757, processor.hpp:60-192
+ *   lpl_knn_build / k_nearest / radius_search   KDTree<float,3>::rebuild / k_nearest / radius_search(_k_nearest)   .../kdtree.hpp:66-77,216-400
  *   lpl_pipeline_split_clouds  label split, clustered cloud, marker lines   src/processor/src/processor.cpp:562-579,627-647,206-343
  */
 #ifndef LPL_B200_H
@@ -160,6 +162,16 @@ enum
  * offsets[num_hulls + 1] delimits the hulls; boxes_out[num_hulls]. */
 int lpl_bounding_boxes(lpl_ctx* ctx, const void* xy, size_t stride, const uint32_t* offsets, uint32_t num_hulls,
                        int method, lpl_bbox* boxes_out);
+
+/* Vehicle shape matching of the node (src/processor/src/processor.cpp:680-757, tables of processor.hpp:60-192; kept
+ * behind `perform_polygon_simplification = false` there): per cluster, from its hull (vertices as (x, y) doubles
+ * `stride` bytes apart, hulls back to back, offsets[num_hulls + 1]), its z extent z_min_max[k][2], its point count
+ * and its oriented box (lpl_bounding_boxes of whatever points the caller boxes - the node passes all cluster
+ * points, processor.cpp:704). class_out[k] = 0 compact, 1 sedan, 2 SUV, 3 truck, 4 minivan, or -1 (the polygon is
+ * kept); polygon_area_out[k] (nullable) = lidar_processing_lib::polygonArea of the hull (polygonizer.hpp:185-198). */
+int lpl_vehicle_match(lpl_ctx* ctx, const void* hull_xy, size_t stride, const uint32_t* offsets, uint32_t num_hulls,
+                      const double* z_min_max, const uint32_t* cluster_sizes, const lpl_bbox* boxes, int32_t* class_out,
+                      double* polygon_area_out);
 
 /* ---- batched, chained pipeline ----------------------------------------------------------- */
 enum
@@ -331,6 +343,27 @@ int lpl_pipeline_split_clouds(lpl_ctx* ctx, uint32_t num_frames, lpl_split_resul
 /* First `count` outputs of the C library's rand() after srand(seed) (glibc TYPE_3 generator), host-only: the stream
  * lpl_pipeline_split_clouds colours clusters with. */
 void lpl_glibc_rand_stream(uint32_t seed, uint32_t count, int32_t* out);
+
+/* General nearest-neighbour queries: the public KDTree<float, 3> API of the reference
+ * (lidar_processing_lib/include/lidar_processing_lib/kdtree.hpp:66-77: rebuild, k_nearest, radius_search,
+ * radius_search_k_nearest), BATCHED over queries and exact (an exhaustive tiled scan on the device; the node's hot
+ * path does not use it - DROR has its own grid search). Distances are the reference's squared float distances
+ * (kdtree.hpp:131-143); results are ordered by ascending (distance, point index) for k_nearest and by ascending point
+ * index for radius_search (the reference leaves ties / radius order to its tree traversal).
+ *   lpl_knn_build        KDTree::rebuild: uploads the searched set (stride >= 12 bytes, float x, y, z first)
+ *   lpl_knn_k_nearest    KDTree::k_nearest for m queries, k <= 128; radius_sqr nullable [m]: with it, only points with
+ *                        dist^2 <= radius_sqr[q] count (the k nearest of KDTree::radius_search_k_nearest's candidates).
+ *                        idx_out / dist_out [m][k], count_out [m] = neighbours written per query
+ *   lpl_knn_radius_search KDTree::radius_search: count_out[q] = points within radius_sqr[q] (may exceed
+ *                        max_per_query); the first max_per_query of them by point index are written */
+int lpl_knn_build(lpl_ctx* ctx, const void* points, size_t stride, uint32_t n);
+/* Identifies the point set resident on the device: changes with every lpl_knn_build, 0 once another call of the
+ * context (a segment / filter / pipeline upload) has overwritten it - the caller then builds again. */
+unsigned long long lpl_knn_token(const lpl_ctx* ctx);
+int lpl_knn_k_nearest(lpl_ctx* ctx, const void* queries, size_t stride, uint32_t m, uint32_t k, const float* radius_sqr,
+                      uint32_t* idx_out, float* dist_out, uint32_t* count_out);
+int lpl_knn_radius_search(lpl_ctx* ctx, const void* queries, size_t stride, uint32_t m, const float* radius_sqr,
+                          uint32_t max_per_query, uint32_t* idx_out, float* dist_out, uint32_t* count_out);
 
 /* PCD v0.7 reader for the reference's data set (FIELDS x y z [intensity], float32, DATA binary or
  * ascii): fills xyzi_out[n][4] (intensity 0 when absent) and *n_out; xyzi_out == NULL only queries

@@ -8,7 +8,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO_PATH = os.path.join(HERE, "liblpl_b200.so")
-SOURCES = ["capi.cu", "ring_dror.cu", "segment.cu", "cluster.cu", "hull.cu", "obb.cu", "ingest.cu", "split.cu"]
+SOURCES = ["capi.cu", "ring_dror.cu", "segment.cu", "cluster.cu", "hull.cu", "obb.cu", "ingest.cu", "split.cu", "knn.cu"]
 HEADERS = ["common.cuh", "libm_exact.cuh", os.path.join("..", "..", "include", "lpl_b200.h")]
 
 # -fmad=false / -ffp-contract=off: the reference binary (x86-64 baseline, no FMA) evaluates

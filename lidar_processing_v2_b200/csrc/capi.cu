@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <new>
 #include <random>
 #include <vector>
@@ -41,6 +42,12 @@ struct lpl_ctx
     // rand() stream the node colours its clusters with (processor.cpp:629-631)
     void* split_dev = nullptr;
     std::size_t split_bytes = 0;
+    // lpl_knn_*: the searched point set lives in frame 0 of the input plane; per-chunk query / result scratch
+    std::uint32_t knn_n = 0;
+    bool knn_built = false;          // false again as soon as anything else writes the input plane
+    unsigned long long knn_token = 0; // identifies the resident point set (lpl_knn_token)
+    void* knn_dev = nullptr;
+    std::size_t knn_bytes = 0;
     std::int32_t rand_r[34] = {0};
     int rand_i = -1; // -1: not seeded yet
     unsigned long long cfg_epoch = 0;
@@ -569,6 +576,10 @@ void lpl_destroy(lpl_ctx* ctx)
     {
         cudaFree(ctx->split_dev);
     }
+    if (ctx->knn_dev != nullptr)
+    {
+        cudaFree(ctx->knn_dev);
+    }
     if (c.slab != nullptr)
     {
         cudaFree(c.slab);
@@ -677,6 +688,10 @@ int lpl_set_jcp_mode(lpl_ctx* ctx, int mode)
 // ------------------------------------------------------------------------------------------
 static int upload_impl(lpl_ctx* ctx, const lpl_frame* frames, std::uint32_t nf, bool from_device)
 {
+    if (ctx != nullptr)
+    {
+        ctx->knn_built = false;
+    }
     if (ctx == nullptr || frames == nullptr || nf == 0 || nf > ctx->c.d.B)
     {
         return fail(ctx, LPL_ERR_INVALID_ARGUMENT, "bad frame batch (null, empty or larger than max_frames)");
@@ -743,6 +758,10 @@ int lpl_pipeline_upload_device(lpl_ctx* ctx, const lpl_frame* frames, std::uint3
 static int upload_packed_impl(lpl_ctx* ctx, const float* pts, const std::uint32_t* counts, std::uint32_t nf,
                               std::uint32_t bytes_per_point)
 {
+    if (ctx != nullptr)
+    {
+        ctx->knn_built = false;
+    }
     if (ctx == nullptr || counts == nullptr || nf == 0 || nf > ctx->c.d.B)
     {
         return fail(ctx, LPL_ERR_INVALID_ARGUMENT, "bad frame batch (null, empty or larger than max_frames)");
@@ -799,6 +818,10 @@ int lpl_pipeline_upload_packed_xyz(lpl_ctx* ctx, const float* xyz, const std::ui
 
 int lpl_pipeline_upload_cloud2(lpl_ctx* ctx, const lpl_cloud2_frame* frames, std::uint32_t nf)
 {
+    if (ctx != nullptr)
+    {
+        ctx->knn_built = false;
+    }
     if (ctx == nullptr || frames == nullptr || nf == 0 || nf > ctx->c.d.B)
     {
         return fail(ctx, LPL_ERR_INVALID_ARGUMENT, "bad frame batch (null, empty or larger than max_frames)");
@@ -1184,6 +1207,10 @@ static int stage_points(lpl_ctx* ctx, const void* points, std::size_t stride, st
         return fail(ctx, LPL_ERR_INVALID_ARGUMENT, "null points or stride < 12 bytes");
     }
     LPL_TRY(cudaSetDevice(c.device));
+    if (dst == d.pts_in)
+    {
+        ctx->knn_built = false; // the searched point set of lpl_knn_* lives there
+    }
     const std::size_t need = 64 + static_cast<std::size_t>(n) * 16 + static_cast<std::size_t>(n) * 2;
     if (ensure_stage(ctx, need) != 0)
     {
@@ -1453,6 +1480,75 @@ int lpl_bounding_boxes(lpl_ctx* ctx, const void* xy, std::size_t stride, const s
                             c.stream));
     launch_boxes_hulls(&c, dxy, doff, num_hulls, method, d.boxes);
     LPL_TRY(cudaMemcpyAsync(boxes_out, d.boxes, sizeof(ObbBox) * num_hulls, cudaMemcpyDeviceToHost, c.stream));
+    LPL_TRY(cudaStreamSynchronize(c.stream));
+    LPL_TRY(cudaGetLastError());
+    return LPL_OK;
+}
+
+int lpl_vehicle_match(lpl_ctx* ctx, const void* hull_xy, std::size_t stride, const std::uint32_t* offsets, std::uint32_t num_hulls,
+                      const double* z_min_max, const std::uint32_t* cluster_sizes, const lpl_bbox* boxes, std::int32_t* class_out,
+                      double* polygon_area_out)
+{
+    if (ctx == nullptr || stride < 16 ||
+        (num_hulls != 0 && (offsets == nullptr || z_min_max == nullptr || cluster_sizes == nullptr || boxes == nullptr || class_out == nullptr)))
+    {
+        return fail(ctx, LPL_ERR_INVALID_ARGUMENT, "bad vehicle match request");
+    }
+    if (num_hulls == 0)
+    {
+        return LPL_OK;
+    }
+    Ctx& c = ctx->c;
+    Dev& d = c.d;
+    const std::size_t total = offsets[num_hulls];
+    for (std::uint32_t k = 0; k < num_hulls; ++k)
+    {
+        if (offsets[k] > offsets[k + 1])
+        {
+            return fail(ctx, LPL_ERR_INVALID_ARGUMENT, "hull offsets must be non-decreasing");
+        }
+    }
+    const std::size_t room = static_cast<std::size_t>(d.B) * d.cap;
+    if (total > room || static_cast<std::size_t>(num_hulls) * 3 >= room)
+    {
+        return fail(ctx, LPL_ERR_CAPACITY, "more hull vertices / hulls than the context was created for");
+    }
+    if (total != 0 && hull_xy == nullptr)
+    {
+        return fail(ctx, LPL_ERR_INVALID_ARGUMENT, "null hull points");
+    }
+    LPL_TRY(cudaSetDevice(c.device));
+    const std::size_t K = num_hulls;
+    const std::size_t need = total * 16 + (K + 1) * 4;
+    if (ensure_stage(ctx, need) != 0)
+    {
+        return LPL_ERR_CUDA;
+    }
+    LPL_TRY(cudaStreamSynchronize(c.stream));
+    auto* hbase = static_cast<char*>(c.h_stage);
+    pack(hbase, 16, hull_xy, stride, 16, static_cast<std::uint32_t>(total));
+    std::memcpy(hbase + total * 16, offsets, (K + 1) * 4);
+    // device scratch that is idle outside a pipeline run: the hull sort buffers, the segment starts, the box plane
+    auto* dxy = reinterpret_cast<double2*>(d.hsA);
+    std::uint32_t* doff = d.cstart;
+    auto* dz = reinterpret_cast<double2*>(d.hsB);
+    auto* darea = reinterpret_cast<double*>(dz + K);
+    auto* dsize = reinterpret_cast<std::uint32_t*>(darea + K);
+    auto* dcls = reinterpret_cast<std::int32_t*>(dsize + K);
+    if (total != 0)
+    {
+        LPL_TRY(cudaMemcpyAsync(dxy, hbase, total * 16, cudaMemcpyHostToDevice, c.stream));
+    }
+    LPL_TRY(cudaMemcpyAsync(doff, hbase + total * 16, (K + 1) * 4, cudaMemcpyHostToDevice, c.stream));
+    LPL_TRY(cudaMemcpyAsync(dz, z_min_max, K * 16, cudaMemcpyHostToDevice, c.stream));
+    LPL_TRY(cudaMemcpyAsync(dsize, cluster_sizes, K * 4, cudaMemcpyHostToDevice, c.stream));
+    LPL_TRY(cudaMemcpyAsync(d.boxes, boxes, K * sizeof(ObbBox), cudaMemcpyHostToDevice, c.stream));
+    launch_vehicle_match(&c, dxy, doff, num_hulls, dz, dsize, d.boxes, dcls, darea);
+    LPL_TRY(cudaMemcpyAsync(class_out, dcls, K * 4, cudaMemcpyDeviceToHost, c.stream));
+    if (polygon_area_out != nullptr)
+    {
+        LPL_TRY(cudaMemcpyAsync(polygon_area_out, darea, K * 8, cudaMemcpyDeviceToHost, c.stream));
+    }
     LPL_TRY(cudaStreamSynchronize(c.stream));
     LPL_TRY(cudaGetLastError());
     return LPL_OK;
@@ -1844,6 +1940,134 @@ int lpl_pipeline_split_clouds(lpl_ctx* ctx, std::uint32_t nf, lpl_split_result* 
     LPL_TRY(cudaStreamSynchronize(c.stream));
     LPL_TRY(cudaGetLastError());
     return LPL_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// general nearest-neighbour queries (KDTree<float, 3> of the reference, kdtree.hpp:216-400), batched
+// ------------------------------------------------------------------------------------------
+int lpl_knn_build(lpl_ctx* ctx, const void* points, std::size_t stride, std::uint32_t n)
+{
+    if (ctx == nullptr)
+    {
+        return LPL_ERR_INVALID_ARGUMENT;
+    }
+    Ctx& c = ctx->c;
+    const int rc = stage_points(ctx, points, stride, n, c.d.pts_in, c.d.n_in, -1);
+    if (rc != 0)
+    {
+        return rc;
+    }
+    LPL_TRY(cudaStreamSynchronize(c.stream)); // the staging buffer is reused by the queries
+    ctx->knn_n = n;
+    ctx->knn_built = true;
+    ctx->knn_token += 1;
+    return LPL_OK;
+}
+
+unsigned long long lpl_knn_token(const lpl_ctx* ctx)
+{
+    return (ctx != nullptr && ctx->knn_built) ? ctx->knn_token : 0ULL;
+}
+
+// mode 0: k nearest (within radius when one is given); mode 1: everything within the radius (first `k` by index)
+static int knn_queries(lpl_ctx* ctx, int mode, const void* queries, std::size_t stride, std::uint32_t m, std::uint32_t k,
+                       const float* radius_sqr, float radius_all, std::uint32_t* idx_out, float* dist_out, std::uint32_t* count_out)
+{
+    if (ctx == nullptr || count_out == nullptr || (m != 0 && queries == nullptr) || stride < 12 || k == 0 ||
+        (m != 0 && (idx_out == nullptr || dist_out == nullptr)))
+    {
+        return fail(ctx, LPL_ERR_INVALID_ARGUMENT, "bad neighbour query");
+    }
+    if (!ctx->knn_built)
+    {
+        return fail(ctx, LPL_ERR_INVALID_ARGUMENT, "lpl_knn_build has not been called on this context");
+    }
+    if (mode == 0 && k > 128)
+    {
+        return fail(ctx, LPL_ERR_CAPACITY, "k_nearest supports up to 128 neighbours per query");
+    }
+    Ctx& c = ctx->c;
+    LPL_TRY(cudaSetDevice(c.device));
+    const std::uint32_t chunk = 16384;
+    const std::size_t per_q = 16 + 4 + 4 + static_cast<std::size_t>(k) * 8;
+    const std::size_t need = per_q * chunk + 1024;
+    if (ctx->knn_bytes < need)
+    {
+        LPL_TRY(cudaStreamSynchronize(c.stream));
+        if (ctx->knn_dev != nullptr)
+        {
+            cudaFree(ctx->knn_dev);
+            ctx->knn_dev = nullptr;
+            ctx->knn_bytes = 0;
+        }
+        if (cudaMalloc(&ctx->knn_dev, need) != cudaSuccess)
+        {
+            cudaGetLastError();
+            return fail(ctx, LPL_ERR_CAPACITY, "device allocation for the neighbour queries failed");
+        }
+        ctx->knn_bytes = need;
+    }
+    auto* base = static_cast<unsigned char*>(ctx->knn_dev);
+    auto* d_q = reinterpret_cast<float4*>(base);
+    auto* d_r = reinterpret_cast<float*>(base + static_cast<std::size_t>(chunk) * 16);
+    auto* d_cnt = reinterpret_cast<std::uint32_t*>(base + static_cast<std::size_t>(chunk) * 20);
+    auto* d_d = reinterpret_cast<float*>(base + static_cast<std::size_t>(chunk) * 24);
+    auto* d_i = reinterpret_cast<std::uint32_t*>(base + static_cast<std::size_t>(chunk) * 24 + static_cast<std::size_t>(chunk) * k * 4);
+    if (ensure_stage(ctx, static_cast<std::size_t>(chunk) * 16) != 0)
+    {
+        return LPL_ERR_CUDA;
+    }
+    for (std::uint32_t q0 = 0; q0 < m; q0 += chunk)
+    {
+        const std::uint32_t mc = std::min(chunk, m - q0);
+        LPL_TRY(cudaStreamSynchronize(c.stream)); // staging free again
+        auto* hp = static_cast<char*>(c.h_stage);
+        if (stride < 16)
+        {
+            std::memset(hp, 0, static_cast<std::size_t>(mc) * 16);
+        }
+        pack(hp, 16, static_cast<const char*>(queries) + static_cast<std::size_t>(q0) * stride, stride, stride < 16 ? 12 : 16, mc);
+        LPL_TRY(cudaMemcpyAsync(d_q, hp, static_cast<std::size_t>(mc) * 16, cudaMemcpyHostToDevice, c.stream));
+        if (radius_sqr != nullptr)
+        {
+            LPL_TRY(cudaMemcpyAsync(d_r, radius_sqr + q0, static_cast<std::size_t>(mc) * 4, cudaMemcpyHostToDevice, c.stream));
+        }
+        if (mode == 0)
+        {
+            if (launch_knn(&c, c.d.pts_in, ctx->knn_n, d_q, mc, k, radius_sqr != nullptr ? d_r : nullptr, radius_all, d_d, d_i, d_cnt) != 0)
+            {
+                return fail(ctx, LPL_ERR_CAPACITY, "unsupported k");
+            }
+        }
+        else
+        {
+            launch_radius(&c, c.d.pts_in, ctx->knn_n, d_q, mc, radius_sqr != nullptr ? d_r : nullptr, radius_all, k, d_d, d_i, d_cnt);
+        }
+        LPL_TRY(cudaMemcpyAsync(count_out + q0, d_cnt, static_cast<std::size_t>(mc) * 4, cudaMemcpyDeviceToHost, c.stream));
+        LPL_TRY(cudaMemcpyAsync(dist_out + static_cast<std::size_t>(q0) * k, d_d, static_cast<std::size_t>(mc) * k * 4,
+                                cudaMemcpyDeviceToHost, c.stream));
+        LPL_TRY(cudaMemcpyAsync(idx_out + static_cast<std::size_t>(q0) * k, d_i, static_cast<std::size_t>(mc) * k * 4,
+                                cudaMemcpyDeviceToHost, c.stream));
+    }
+    LPL_TRY(cudaStreamSynchronize(c.stream));
+    LPL_TRY(cudaGetLastError());
+    return LPL_OK;
+}
+
+int lpl_knn_k_nearest(lpl_ctx* ctx, const void* queries, std::size_t stride, std::uint32_t m, std::uint32_t k, const float* radius_sqr,
+                      std::uint32_t* idx_out, float* dist_out, std::uint32_t* count_out)
+{
+    return knn_queries(ctx, 0, queries, stride, m, k, radius_sqr, std::numeric_limits<float>::infinity(), idx_out, dist_out, count_out);
+}
+
+int lpl_knn_radius_search(lpl_ctx* ctx, const void* queries, std::size_t stride, std::uint32_t m, const float* radius_sqr,
+                          std::uint32_t max_per_query, std::uint32_t* idx_out, float* dist_out, std::uint32_t* count_out)
+{
+    if (radius_sqr == nullptr)
+    {
+        return fail(ctx, LPL_ERR_INVALID_ARGUMENT, "radius_search needs a squared radius per query");
+    }
+    return knn_queries(ctx, 1, queries, stride, m, max_per_query, radius_sqr, 0.f, idx_out, dist_out, count_out);
 }
 
 int lpl_host_alloc(void** out, std::size_t bytes)

@@ -605,6 +605,12 @@ void launch_split_clouds(Ctx* c, std::uint32_t nf, unsigned char* out, std::size
                          std::uint32_t colour_stride, std::uint32_t* cnt3, std::uint32_t* totals);
 void launch_marker_lines(Ctx* c, std::uint32_t nf, std::uint32_t* mcount, std::uint32_t* moff, std::uint32_t* mtotal, double* out,
                          std::size_t frame_stride);
+int launch_knn(Ctx* c, const float4* pts, std::uint32_t n, const float4* queries, std::uint32_t m, std::uint32_t k,
+               const float* radius_sqr, float radius_all, float* best_d, std::uint32_t* best_i, std::uint32_t* count);
+void launch_radius(Ctx* c, const float4* pts, std::uint32_t n, const float4* queries, std::uint32_t m, const float* radius_sqr,
+                   float radius_all, std::uint32_t cap, float* out_d, std::uint32_t* out_i, std::uint32_t* count);
+void launch_vehicle_match(Ctx* c, const double2* xy, const std::uint32_t* off, std::uint32_t K, const double2* zmm,
+                          const std::uint32_t* sizes, const ObbBox* boxes, std::int32_t* cls, double* area_out);
 void launch_pack_results(Ctx* c, std::uint32_t nf, std::uint32_t planes, unsigned char* staging, std::size_t staging_bytes);
 void launch_unpack_cloud2(Ctx* c, std::uint32_t nf, const unsigned char* raw, std::size_t raw_stride, const void* desc);
 void launch_boxes_hulls(Ctx* c, const double2* xy, const std::uint32_t* off, std::uint32_t K, int method, ObbBox* out);

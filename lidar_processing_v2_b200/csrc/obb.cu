@@ -492,6 +492,109 @@ __global__ void __launch_bounds__(kObbWarps * 32)
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Vehicle shape matching (src/processor/src/processor.cpp:680-757 with the tables of processor.hpp:60-192; the node
+// keeps it behind `perform_polygon_simplification = false`). Per cluster, in the node's order of tests: a hull of
+// >= 3 vertices, more than 150 points, a height inside the range any vehicle class allows, the polygon volume
+// (shoelace area x height) inside the overall bounds, a valid box whose area holds the hull area to more than 0.4,
+// then the first of the five classes (compact, sedan, SUV, truck, minivan; dimensions widened by the tolerances)
+// whose length / width / height / volume / area windows all hold. All in double, in the node's expression order.
+// ------------------------------------------------------------------------------------------
+struct VehicleTables
+{
+    double dim[5][6];    // min / max length, width, height (adjusted)
+    double bound[5][4];  // min / max volume, min / max area
+    double min_height, max_height, min_volume, max_volume, min_iou;
+    std::uint32_t min_points;
+};
+
+__global__ void __launch_bounds__(128)
+    k_vehicle_match(const double2* __restrict__ xy, const std::uint32_t* __restrict__ off, std::uint32_t K,
+                    const double2* __restrict__ zmm, const std::uint32_t* __restrict__ sizes, const ObbBox* __restrict__ boxes,
+                    VehicleTables t, std::int32_t* __restrict__ cls, double* __restrict__ area_out)
+{
+    const std::uint32_t c = blockIdx.x * 128u + threadIdx.x;
+    if (c >= K)
+    {
+        return;
+    }
+    const std::uint32_t a = off[c], n = off[c + 1] - a;
+    // polygonArea (polygonizer.hpp:185-198): shoelace, terms added in vertex order, the closing term last
+    double area = 0.0;
+    if (n > 2)
+    {
+        for (std::uint32_t i = 0; i + 1 < n; ++i)
+        {
+            area += (xy[a + i].x * xy[a + i + 1].y) - (xy[a + i + 1].x * xy[a + i].y);
+        }
+        area += (xy[a + n - 1].x * xy[a].y) - (xy[a].x * xy[a + n - 1].y);
+    }
+    area = fabs(area) * 0.5;
+    area_out[c] = area;
+    std::int32_t found = -1;
+    const double height = zmm[c].y - zmm[c].x;
+    if (n >= 3 && sizes[c] > t.min_points && height > t.min_height && height < t.max_height)
+    {
+        const double volume = area * height;
+        const ObbBox b = boxes[c];
+        if (volume > t.min_volume && volume < t.max_volume && b.valid != 0)
+        {
+            const double iou = area / static_cast<double>(b.area);
+            if (iou > t.min_iou)
+            {
+                const double dx1 = b.c[0] - b.c[2], dy1 = b.c[1] - b.c[3];
+                const double dx2 = b.c[2] - b.c[4], dy2 = b.c[3] - b.c[5];
+                const double e1 = sqrt(dx1 * dx1 + dy1 * dy1), e2 = sqrt(dx2 * dx2 + dy2 * dy2);
+                const double len = fmax(e1, e2), wid = fmin(e1, e2);
+                for (int v = 0; v < 5 && found < 0; ++v)
+                {
+                    if (len > t.dim[v][0] && len < t.dim[v][1] && wid > t.dim[v][2] && wid < t.dim[v][3] && height > t.dim[v][4] &&
+                        height < t.dim[v][5] && volume > t.bound[v][0] && volume < t.bound[v][1] && area > t.bound[v][2] &&
+                        area < t.bound[v][3])
+                    {
+                        found = v;
+                    }
+                }
+            }
+        }
+    }
+    cls[c] = found;
+}
+
+void launch_vehicle_match(Ctx* c, const double2* xy, const std::uint32_t* off, std::uint32_t K, const double2* zmm,
+                          const std::uint32_t* sizes, const ObbBox* boxes, std::int32_t* cls, double* area_out)
+{
+    // processor.hpp:60-192, evaluated in double exactly as its constexpr lambdas do
+    const double base[5][6] = {{4.3, 4.6, 1.6, 1.9, 1.4, 1.5}, {4.6, 5.0, 1.6, 1.9, 1.4, 1.5}, {4.6, 5.2, 1.7, 2.1, 1.7, 1.8},
+                               {5.2, 5.8, 1.9, 2.2, 1.8, 2.0}, {4.9, 5.2, 1.7, 2.1, 1.7, 1.8}};
+    const double tol[3] = {0.8, 0.5, 0.5};
+    VehicleTables t{};
+    t.min_height = 1e300;
+    t.max_height = -1e300;
+    t.min_volume = 1e300;
+    t.max_volume = -1e300;
+    for (int v = 0; v < 5; ++v)
+    {
+        for (int q = 0; q < 3; ++q)
+        {
+            t.dim[v][2 * q] = base[v][2 * q] - tol[q];
+            t.dim[v][2 * q + 1] = base[v][2 * q + 1] + tol[q];
+        }
+        t.bound[v][0] = t.dim[v][0] * t.dim[v][2] * t.dim[v][4];
+        t.bound[v][1] = t.dim[v][1] * t.dim[v][3] * t.dim[v][5];
+        t.bound[v][2] = t.dim[v][0] * t.dim[v][2];
+        t.bound[v][3] = t.dim[v][1] * t.dim[v][3];
+        t.min_height = std::min(t.min_height, t.dim[v][4]);
+        t.max_height = std::max(t.max_height, t.dim[v][5]);
+        t.min_volume = std::min(t.min_volume, t.bound[v][0]);
+        t.max_volume = std::max(t.max_volume, t.bound[v][1]);
+    }
+    t.min_iou = 0.4;
+    t.min_points = 150;
+    k_vehicle_match<<<(K + 127) / 128, 128, 0, c->stream>>>(xy, off, K, zmm, sizes, boxes, t, cls, area_out);
+    mark(c, "vehicle_match");
+}
+
 void launch_boxes(Ctx* c, std::uint32_t nf, int method)
 {
     k_obb_frames<<<dim3(16, nf), kObbWarps * 32, 0, c->stream>>>(c->d, method);

@@ -35,11 +35,12 @@ EXPORTS = [
     "lpl_segmenter_default_cfg", "lpl_dror_default_cfg", "lpl_cluster_default_cfg",
     "lpl_segmenter_config", "lpl_dror_config", "lpl_cluster_config", "lpl_set_jcp_mode",
     "lpl_ring_partition", "lpl_dror_filter", "lpl_segment", "lpl_cluster", "lpl_convex_hull",
-    "lpl_cluster_hulls", "lpl_bounding_boxes",
+    "lpl_cluster_hulls", "lpl_bounding_boxes", "lpl_vehicle_match",
     "lpl_pipeline_upload", "lpl_pipeline_upload_device", "lpl_pipeline_upload_cloud2", "lpl_pipeline_upload_packed",
     "lpl_pipeline_upload_packed_xyz", "lpl_pcd_read",
     "lpl_pipeline_run", "lpl_pipeline_use_graph", "lpl_pipeline_sync", "lpl_pipeline_status", "lpl_pipeline_download_packed",
     "lpl_pipeline_split_clouds", "lpl_glibc_rand_stream",
+    "lpl_knn_build", "lpl_knn_token", "lpl_knn_k_nearest", "lpl_knn_radius_search",
     "lpl_pipeline_want_image", "lpl_pipeline_counts", "lpl_pipeline_download",
     "lpl_pipeline_download_batch", "lpl_host_alloc", "lpl_host_free",
     "lpl_profile_enable", "lpl_profile_read",
@@ -239,6 +240,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     L.lpl_convex_hull.argtypes = [vp, vp, sz, u32, vp, C.POINTER(u32)]
     L.lpl_cluster_hulls.argtypes = [vp, vp, sz, vp, u32, u32, vp, vp, vp, vp]
     L.lpl_bounding_boxes.argtypes = [vp, vp, sz, vp, u32, C.c_int, vp]
+    L.lpl_vehicle_match.argtypes = [vp, vp, sz, vp, u32, vp, vp, vp, vp, vp]
+    L.lpl_vehicle_match.restype = C.c_int
     L.lpl_pipeline_upload.argtypes = [vp, C.POINTER(Frame), u32]
     L.lpl_pipeline_upload_device.argtypes = [vp, C.POINTER(Frame), u32]
     L.lpl_pipeline_upload_cloud2.argtypes = [vp, C.POINTER(Cloud2Frame), u32]
@@ -249,6 +252,14 @@ def load_library(path: str | None = None) -> C.CDLL:
     L.lpl_pipeline_download_packed.argtypes = [vp, u32, C.POINTER(PackedResult)]
     L.lpl_pipeline_split_clouds.argtypes = [vp, u32, C.POINTER(SplitResult)]
     L.lpl_pipeline_split_clouds.restype = C.c_int
+    L.lpl_knn_build.argtypes = [vp, vp, sz, u32]
+    L.lpl_knn_build.restype = C.c_int
+    L.lpl_knn_token.argtypes = [vp]
+    L.lpl_knn_token.restype = C.c_ulonglong
+    L.lpl_knn_k_nearest.argtypes = [vp, vp, sz, u32, u32, vp, vp, vp, vp]
+    L.lpl_knn_k_nearest.restype = C.c_int
+    L.lpl_knn_radius_search.argtypes = [vp, vp, sz, u32, vp, u32, vp, vp, vp]
+    L.lpl_knn_radius_search.restype = C.c_int
     L.lpl_glibc_rand_stream.argtypes = [u32, u32, vp]
     L.lpl_glibc_rand_stream.restype = None
     L.lpl_pipeline_run.argtypes = [vp, u32, u32]
@@ -284,6 +295,7 @@ def load_library(path: str | None = None) -> C.CDLL:
                  "lpl_pipeline_download_batch", "lpl_pipeline_upload_packed", "lpl_pipeline_upload_packed_xyz",
                  "lpl_pipeline_upload_cloud2", "lpl_pipeline_status", "lpl_pipeline_download_packed",
     "lpl_pipeline_split_clouds", "lpl_glibc_rand_stream",
+    "lpl_knn_build", "lpl_knn_token", "lpl_knn_k_nearest", "lpl_knn_radius_search",
                  "lpl_profile_enable", "lpl_profile_read",
                  "lpl_timer_start", "lpl_timer_stop_ms", "lpl_debug_segment", "lpl_debug_cluster"):
         getattr(L, name).restype = C.c_int
@@ -509,6 +521,20 @@ class Context:
                                               method, out.ctypes.data))
         return out[:K].copy()
 
+    def vehicle_match(self, hull_xy, offsets, z_min_max, cluster_sizes, boxes):
+        """Vehicle class per cluster (-1 none) and the hull's polygon area (lpl_vehicle_match)."""
+        a = np.ascontiguousarray(hull_xy, dtype=np.float64).reshape(-1, 2)
+        off = np.ascontiguousarray(offsets, dtype=np.uint32)
+        K = max(len(off) - 1, 0)
+        z = np.ascontiguousarray(z_min_max, np.float64).reshape(-1, 2)
+        sz_ = np.ascontiguousarray(cluster_sizes, np.uint32)
+        bx = np.ascontiguousarray(boxes, BBOX_DTYPE)
+        cls = np.full(max(K, 1), -1, np.int32)
+        area = np.zeros(max(K, 1), np.float64)
+        self._chk(self.lib.lpl_vehicle_match(self.h, a.ctypes.data if a.size else None, 16, off.ctypes.data, K, z.ctypes.data,
+                                             sz_.ctypes.data, bx.ctypes.data, cls.ctypes.data, area.ctypes.data))
+        return cls[:K].copy(), area[:K].copy()
+
     def cluster_hulls(self, pts, labels, num_clusters=None):
         p, stride, n, keep = _points_arg(pts)
         lab = np.ascontiguousarray(labels, np.int32)
@@ -666,6 +692,35 @@ class Context:
         out["markers"] = [mk[f, : counts[4, f]] for f in range(nf)] if markers else None
         out["counts"] = counts
         return out
+
+    # ---- general neighbour queries (KDTree<float, 3> of the reference)
+    def knn_build(self, pts):
+        p, stride, n, keep = _points_arg(pts)
+        self._chk(self.lib.lpl_knn_build(self.h, p, stride, n))
+
+    def knn_token(self) -> int:
+        return int(self.lib.lpl_knn_token(self.h))
+
+    def k_nearest(self, queries, k: int, radius_sqr=None):
+        """-> (idx [m][k] uint32, dist [m][k] float32 squared distances, count [m])."""
+        p, stride, m, keep = _points_arg(queries)
+        idx = np.zeros((m, k), np.uint32)
+        dist = np.zeros((m, k), np.float32)
+        cnt = np.zeros(m, np.uint32)
+        r = None if radius_sqr is None else np.ascontiguousarray(radius_sqr, np.float32)
+        self._chk(self.lib.lpl_knn_k_nearest(self.h, p, stride, m, k, None if r is None else r.ctypes.data, idx.ctypes.data,
+                                             dist.ctypes.data, cnt.ctypes.data))
+        return idx, dist, cnt
+
+    def radius_search(self, queries, radius_sqr, max_per_query: int):
+        p, stride, m, keep = _points_arg(queries)
+        idx = np.zeros((m, max_per_query), np.uint32)
+        dist = np.zeros((m, max_per_query), np.float32)
+        cnt = np.zeros(m, np.uint32)
+        r = np.ascontiguousarray(radius_sqr, np.float32)
+        self._chk(self.lib.lpl_knn_radius_search(self.h, p, stride, m, r.ctypes.data, max_per_query, idx.ctypes.data,
+                                                 dist.ctypes.data, cnt.ctypes.data))
+        return idx, dist, cnt
 
     def status(self, nf: int) -> np.ndarray:
         """Per-frame capacity flags of the last run (0 = good)."""

@@ -108,6 +108,10 @@ class RefOracle:
         L.ref_dror_timed.argtypes = [C.c_void_p, C.c_int32, C.c_uint32, C.c_int32]
         L.ref_dror_timed.restype = C.c_double
         L.ref_shim_dilate5x5.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+        if hasattr(L, "ref_kdtree_query"):
+            L.ref_kdtree_query.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int32,
+                                           C.c_void_p, C.c_void_p, C.c_void_p]
+            L.ref_kdtree_query.restype = C.c_int
         self.has_polygonizer = hasattr(L, "ref_convex_hull")
         if self.has_polygonizer:
             L.ref_convex_hull.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
@@ -128,6 +132,23 @@ class RefOracle:
         except Exception:
             pass
 
+
+    # -- KDTree<float, 3> (kdtree.hpp:216-337) ----------------------------------------
+    def kdtree_query(self, pts, queries, k, radius_sqr=None):
+        """The reference's own radius_search (sorted by distance), one query at a time; its k_nearest template does not
+        compile (kdtree.hpp:246), so radius_sqr is required. Returns (idx [m][k], dist [m][k], count [m])."""
+        p = np.ascontiguousarray(np.asarray(pts, np.float32)[:, :3])
+        q = np.ascontiguousarray(np.asarray(queries, np.float32)[:, :3])
+        m = q.shape[0]
+        idx = np.zeros((m, k), np.uint32)
+        dist = np.zeros((m, k), np.float32)
+        cnt = np.zeros(m, np.uint32)
+        r = None if radius_sqr is None else np.ascontiguousarray(radius_sqr, np.float32)
+        rc = self.lib.ref_kdtree_query(p.ctypes.data, p.shape[0], q.ctypes.data, m, k, None if r is None else r.ctypes.data,
+                                       0 if r is None else 1, idx.ctypes.data, dist.ctypes.data, cnt.ctypes.data)
+        if rc != 0:
+            raise RuntimeError(self.lib.ref_last_error().decode())
+        return idx, dist, cnt
 
     # -- polygonizer (convex hull, antipodal pairs, oriented boxes) ---------------------
     def convex_hull(self, xy):

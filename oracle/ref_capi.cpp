@@ -446,6 +446,55 @@ double ref_dror_timed(const float* xyz, std::int32_t stride_f, std::uint32_t n, 
     return std::chrono::duration<double>(t1 - t0).count();
 }
 
+// ---- KDTree<float, 3>::radius_search (kdtree.hpp:283-337), query by query. idx_out / dist_out: [m][k] = the first k
+// of the distance-sorted result; count_out[q] = all neighbours found.
+// (KDTree::k_nearest cannot be wrapped: instantiating it fails to compile - kdtree.hpp:246,251 call
+// PriorityQueue::push_back, which priority_queue.hpp does not have; the template is never instantiated by the
+// reference. The k-nearest checker is therefore a restatement: tests/test_gpu_parity.py, brute force.)
+int ref_kdtree_query(const float* xyz, std::uint32_t n, const float* queries, std::uint32_t m, std::uint32_t k,
+                     const float* radius_sqr, std::int32_t mode, std::uint32_t* idx_out, float* dist_out, std::uint32_t* count_out)
+{
+    try
+    {
+        using Tree = lpl::KDTree<float, 3>;
+        std::vector<Tree::PointT> pts(n);
+        for (std::uint32_t i = 0; i < n; ++i)
+        {
+            pts[i] = {xyz[3 * static_cast<std::size_t>(i)], xyz[3 * static_cast<std::size_t>(i) + 1], xyz[3 * static_cast<std::size_t>(i) + 2]};
+        }
+        Tree tree(true); // radius results sorted by distance
+        tree.reserve(n + 16);
+        if (n > 0)
+        {
+            tree.rebuild(pts);
+        }
+        std::vector<Tree::Neighbour> neigh;
+        for (std::uint32_t q = 0; q < m; ++q)
+        {
+            const Tree::PointT t = {queries[3 * static_cast<std::size_t>(q)], queries[3 * static_cast<std::size_t>(q) + 1],
+                                    queries[3 * static_cast<std::size_t>(q) + 2]};
+            if (mode == 0)
+            {
+                g_last_error = "KDTree::k_nearest does not compile in the reference (PriorityQueue::push_back)";
+                return -2;
+            }
+            tree.radius_search(t, radius_sqr[q], neigh);
+            count_out[q] = static_cast<std::uint32_t>(neigh.size());
+            for (std::uint32_t j = 0; j < k && j < neigh.size(); ++j)
+            {
+                idx_out[static_cast<std::size_t>(q) * k + j] = neigh[j].index;
+                dist_out[static_cast<std::size_t>(q) * k + j] = neigh[j].distance;
+            }
+        }
+    }
+    catch (const std::exception& e)
+    {
+        g_last_error = e.what();
+        return -1;
+    }
+    return 0;
+}
+
 // shim self-check: 5x5 dilation of a single-channel image (compared with cv2.dilate in tests)
 void ref_shim_dilate5x5(const std::uint8_t* src, std::int32_t rows, std::int32_t cols, std::uint8_t* dst)
 {

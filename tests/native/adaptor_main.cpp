@@ -24,6 +24,7 @@
 #include <vector>
 
 #include <lidar_processing_lib/clusterer.hpp>
+#include <lidar_processing_lib/kdtree.hpp>
 #include <lidar_processing_lib/noise_remover.hpp>
 #include <lidar_processing_lib/polygonizer.hpp>
 #include <lidar_processing_lib/segmenter.hpp>
@@ -314,6 +315,36 @@ int main(int argc, char** argv)
             std::fwrite(&area, 4, 1, fo);
             std::fwrite(&yaw, 4, 1, fo);
             std::fwrite(&valid, 4, 1, fo);
+        }
+        // ---- KDTree<float, 3> (kdtree.hpp:66-77) on the first 5000 points: 3 nearest of 64 targets, their
+        // neighbourhoods within 0.5 m (sorted by distance) and the 2 nearest within that radius. Called AFTER the other
+        // adaptors used the thread's shared context: the tree re-uploads its points when they were displaced.
+        {
+            const std::uint32_t nt = n < 5000U ? n : 5000U, nq = nt < 64U ? nt : 64U;
+            std::vector<lpl::KDTree<float, 3>::PointT> tp(raw.begin(), raw.begin() + nt);
+            lpl::KDTree<float, 3> tree(true);
+            tree.rebuild(tp);
+            std::vector<lpl::KDTree<float, 3>::Neighbour> ne;
+            std::fwrite(&nq, 4, 1, fo);
+            for (std::uint32_t q = 0; q < nq; ++q)
+            {
+                tree.k_nearest(tp[q * 7U % nt], 3, ne);
+                std::uint32_t cnt = static_cast<std::uint32_t>(ne.size());
+                std::fwrite(&cnt, 4, 1, fo);
+                std::fwrite(ne.data(), sizeof(ne[0]), ne.size(), fo);
+                if (q < 4)
+                {
+                    noise_remover.filter(raw, noise); // displaces the tree's points on the device
+                }
+                tree.radius_search(tp[q * 7U % nt], 0.25F, ne);
+                cnt = static_cast<std::uint32_t>(ne.size());
+                std::fwrite(&cnt, 4, 1, fo);
+                std::fwrite(ne.data(), sizeof(ne[0]), ne.size(), fo);
+                tree.radius_search_k_nearest(tp[q * 7U % nt], 0.25F, 2, ne);
+                cnt = static_cast<std::uint32_t>(ne.size());
+                std::fwrite(&cnt, 4, 1, fo);
+                std::fwrite(ne.data(), sizeof(ne[0]), ne.size(), fo);
+            }
         }
         std::fclose(fo);
         std::printf("ok n=%u obstacles=%u clusters=%u hull_vertices=%zu\n", n, m, K, hull_xy.size() / 2);

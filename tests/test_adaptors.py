@@ -108,4 +108,27 @@ def test_adaptors_reproduce_the_reference_call_sequence(exe, tmp_path, golden0, 
     assert np.array_equal(boxes["c"].view(np.uint64), gb[:, :8].view(np.uint64))
     assert np.array_equal(boxes["area"], gb[:, 8].astype(np.float32))
     assert np.array_equal(boxes["yaw"], gb[:, 9].astype(np.float32))
+    o += box_dt.itemsize * K
+    # KDTree<float, 3> adaptor: k_nearest / radius_search / radius_search_k_nearest on the first 5000 points
+    (nq,) = struct.unpack_from("<I", raw, o); o += 4
+    assert nq == 64
+    ne_dt = np.dtype([("index", np.uint32), ("distance", np.float32)])
+    tp = pts[:5000, :3].astype(np.float32)
+    for q in range(nq):
+        t = tp[q * 7 % 5000]
+        d = tp - t
+        dist = (d[:, 0] * d[:, 0] + (d[:, 1] * d[:, 1] + (d[:, 2] * d[:, 2] + np.float32(0)))).astype(np.float32)
+        order = np.argsort(dist, kind="stable")
+        (c,) = struct.unpack_from("<I", raw, o); o += 4
+        ne = np.frombuffer(raw, ne_dt, c, o); o += 8 * c
+        assert c == 3 and np.array_equal(ne["index"], order[:3]) and np.array_equal(ne["distance"], dist[order[:3]])
+        within = order[dist[order] <= np.float32(0.25)]
+        (c,) = struct.unpack_from("<I", raw, o); o += 4
+        ne = np.frombuffer(raw, ne_dt, c, o); o += 8 * c
+        assert c == within.size and np.array_equal(np.sort(ne["index"]), np.sort(within))
+        assert np.all(np.diff(ne["distance"]) >= 0)           # KDTree(sort = true)
+        (c,) = struct.unpack_from("<I", raw, o); o += 4
+        ne = np.frombuffer(raw, ne_dt, c, o); o += 8 * c
+        assert c == min(2, within.size) and np.array_equal(ne["index"], within[:c])
+    assert o == len(raw)
     _ = (port, NODE_CLUSTER_CFG)

@@ -346,6 +346,123 @@ def test_processor_glue_split_clouds_and_markers(port, golden0, golden100):
         c.close()
 
 
+def test_general_neighbour_queries_vs_reference_kdtree(ctx, ref, golden0):
+    """lpl_knn_radius_search against the reference's own KDTree<float, 3>::radius_search (kdtree.hpp:283-337):
+    neighbourhoods as sets, squared distances bit for bit. lpl_knn_k_nearest against a brute-force restatement
+    (parity unpinned: the reference's k_nearest template does not compile - kdtree.hpp:246 calls a
+    PriorityQueue::push_back that does not exist - and is never instantiated): the k smallest of the reference's
+    dist_sqr expression (kdtree.hpp:131-143), ties by point index."""
+    pts = golden0["pts"][::6]                      # ~20k points
+    rng = np.random.default_rng(2)
+    q = np.concatenate([pts[rng.choice(pts.shape[0], 300, replace=False)],
+                        np.c_[rng.uniform(-60, 60, (100, 2)), rng.uniform(-2, 1, 100), np.zeros(100)].astype(np.float32)])
+    ctx.knn_build(pts)
+    assert ctx.knn_token() != 0
+    for k in (1, 5, 24, 100):
+        gi, gd, gc = ctx.k_nearest(q, k)
+        P, Q = pts[:, :3].astype(np.float32), q[:, :3].astype(np.float32)
+        d0, d1, d2 = (Q[:, None, 0] - P[None, :, 0]), (Q[:, None, 1] - P[None, :, 1]), (Q[:, None, 2] - P[None, :, 2])
+        dall = (d0 * d0 + (d1 * d1 + (d2 * d2 + np.float32(0)))).astype(np.float32)
+        ri = np.argsort(dall, axis=1, kind="stable")[:, :k].astype(np.uint32)    # stable: ties by index
+        rd = np.take_along_axis(dall, ri.astype(np.int64), 1)
+        assert np.all(gc == k)
+        assert np.array_equal(gd.view(np.uint32), rd.view(np.uint32))
+        uniq = np.ones_like(gd, bool)
+        uniq[:, 1:] &= gd[:, 1:] != gd[:, :-1]
+        uniq[:, :-1] &= gd[:, :-1] != gd[:, 1:]
+        assert np.array_equal(gi[uniq], ri[uniq])
+        # every returned index really is at the returned distance
+        d = pts[gi.reshape(-1), :3].astype(np.float32) - np.repeat(q[:, :3], k, 0)
+        assert np.array_equal((d[:, 0] * d[:, 0] + (d[:, 1] * d[:, 1] + (d[:, 2] * d[:, 2]))).astype(np.float32) == gd.reshape(-1),
+                              np.ones(gd.size, bool))
+    r2 = (np.maximum(0.02 * np.hypot(q[:, 0], q[:, 1]), 0.3) ** 2).astype(np.float32)
+    gi, gd, gc = ctx.radius_search(q, r2, 256)
+    ri, rd, rc = ref.kdtree_query(pts, q, 256, radius_sqr=r2)
+    assert np.array_equal(gc, rc) and gc.max() <= 256 and gc.max() > 20
+    for j in range(q.shape[0]):
+        assert np.array_equal(np.sort(gi[j, :gc[j]]), np.sort(ri[j, :rc[j]]))
+        assert np.array_equal(np.sort(gd[j, :gc[j]]).view(np.uint32), rd[j, :rc[j]].view(np.uint32))
+    # k nearest within a radius (radius_search_k_nearest's candidates), and truncation by max_per_query
+    gi2, gd2, gc2 = ctx.k_nearest(q, 4, radius_sqr=r2)
+    assert np.array_equal(gc2, np.minimum(gc, 4))
+    gi3, gd3, gc3 = ctx.radius_search(q, r2, 8)
+    assert np.array_equal(gc3, gc) and np.array_equal(gi3[:, :8][gc[:, None] > np.arange(8)], gi[:, :8][gc[:, None] > np.arange(8)])
+    # another call of the context replaces the resident point set: the token says so
+    ctx.dror_filter(pts[:100])
+    assert ctx.knn_token() == 0
+    with pytest.raises(lpl.LplError):
+        ctx.k_nearest(q, 3)
+
+
+def _vehicle_match_node(hull, zmm, size, box):
+    """processor.cpp:680-757 + processor.hpp:60-192, restated in float64 numpy (the node is ROS code, not in the oracle)."""
+    base = np.array([[4.3, 4.6, 1.6, 1.9, 1.4, 1.5], [4.6, 5.0, 1.6, 1.9, 1.4, 1.5], [4.6, 5.2, 1.7, 2.1, 1.7, 1.8],
+                     [5.2, 5.8, 1.9, 2.2, 1.8, 2.0], [4.9, 5.2, 1.7, 2.1, 1.7, 1.8]])
+    tol = np.array([0.8, 0.8, 0.5, 0.5, 0.5, 0.5]) * np.array([-1, 1, -1, 1, -1, 1])
+    dim = base + tol
+    vol = np.stack([dim[:, 0] * dim[:, 2] * dim[:, 4], dim[:, 1] * dim[:, 3] * dim[:, 5]], -1)
+    ar = np.stack([dim[:, 0] * dim[:, 2], dim[:, 1] * dim[:, 3]], -1)
+    n = hull.shape[0]
+    area = 0.0
+    if n > 2:
+        for i in range(n - 1):
+            area += hull[i, 0] * hull[i + 1, 1] - hull[i + 1, 0] * hull[i, 1]
+        area += hull[n - 1, 0] * hull[0, 1] - hull[0, 0] * hull[n - 1, 1]
+    area = abs(area) * 0.5
+    h = zmm[1] - zmm[0]
+    cls = -1
+    if n >= 3 and size > 150 and dim[:, 4].min() < h < dim[:, 5].max():
+        v = area * h
+        if vol[:, 0].min() < v < vol[:, 1].max() and box["is_valid"]:
+            if area / float(box["area"]) > 0.4:
+                c = box["corners"]
+                e1 = np.sqrt((c[0, 0] - c[1, 0]) ** 2 + (c[0, 1] - c[1, 1]) ** 2)
+                e2 = np.sqrt((c[1, 0] - c[2, 0]) ** 2 + (c[1, 1] - c[2, 1]) ** 2)
+                ln, wd = max(e1, e2), min(e1, e2)
+                for k in range(5):
+                    if (dim[k, 0] < ln < dim[k, 1] and dim[k, 2] < wd < dim[k, 3] and dim[k, 4] < h < dim[k, 5]
+                            and vol[k, 0] < v < vol[k, 1] and ar[k, 0] < area < ar[k, 1]):
+                        cls = k
+                        break
+    return cls, area
+
+
+def test_vehicle_shape_matching(ctx, port, golden0):
+    """lpl_vehicle_match against the node's disabled polygon simplification (processor.cpp:680-757): class index
+    and polygon area per cluster, on synthetic car-sized rectangles of every class and on the clusters of a KITTI frame."""
+    rng = np.random.default_rng(4)
+    hulls, zmm, sizes = [], [], []
+    for ln, wd, ht in [(4.4, 1.7, 1.45), (4.8, 1.8, 1.45), (5.0, 1.9, 1.75), (5.5, 2.0, 1.9), (5.0, 2.0, 1.75), (9.0, 2.5, 3.0),
+                       (1.0, 0.5, 1.7), (4.4, 1.7, 0.3), (4.5, 1.8, 1.5), (3.2, 1.0, 1.2), (6.7, 2.8, 2.6)]:
+        for _ in range(4):
+            t = rng.uniform(0, np.pi)
+            R = np.array([[np.cos(t), -np.sin(t)], [np.sin(t), np.cos(t)]])
+            rect = np.array([[-ln / 2, -wd / 2], [ln / 2, -wd / 2], [ln / 2, wd / 2], [-ln / 2, wd / 2]]) @ R.T + rng.uniform(-30, 30, 2)
+            rect = np.round(rect, 3).astype(np.float32).astype(np.float64)
+            hulls.append(rect[port.convex_hull(rect)])
+            z0 = np.float32(rng.uniform(-1.8, -1.5))
+            zmm.append([float(z0), float(np.float32(z0 + ht))])
+            sizes.append(int(rng.integers(100, 400)))
+    # the clusters of a KITTI frame
+    pts = golden0["pts"]
+    lab = golden0["labels"]
+    obs = np.ascontiguousarray(pts[lab == 2])
+    cl = golden0["cluster_labels"].astype(np.int32)
+    off0, xy0 = golden0["hull_offsets"], golden0["hull_xy"].astype(np.float64)
+    for k in range(len(off0) - 1):
+        hulls.append(xy0[off0[k]:off0[k + 1]])
+        zmm.append([float(v) for v in golden0["zminmax"][k]])
+        sizes.append(int((cl == k).sum()))
+    off = np.concatenate([[0], np.cumsum([len(h) for h in hulls])]).astype(np.uint32)
+    allxy = np.concatenate(hulls)
+    boxes = ctx.bounding_boxes(allxy, off, lpl.BOX_ROTATING_CALIPERS)
+    cls, area = ctx.vehicle_match(allxy, off, np.array(zmm), np.array(sizes, np.uint32), boxes)
+    exp = [_vehicle_match_node(h, z, s, b) for h, z, s, b in zip(hulls, zmm, sizes, boxes)]
+    assert np.array_equal(cls, np.array([e[0] for e in exp], np.int32))
+    assert np.array_equal(area.view(np.uint64), np.array([e[1] for e in exp], np.float64).view(np.uint64))
+    assert set(cls[:44].tolist()) >= {-1, 0} and (cls[:20] >= 0).sum() >= 4   # car-sized rectangles do match
+
+
 def test_edge_cases(ctx, port):
     ctx.cluster_config(**NODE_CLUSTER_CFG)
     empty = np.zeros((0, 4), np.float32)

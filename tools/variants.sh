@@ -11,6 +11,6 @@ for v in "$@"; do
   name=${v%%:*}; flags=${v#*:}
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -std=c++17 -Xcompiler -fPIC,-ffp-contract=off \
        -shared -cudart static --threads 4 $flags -o ../variants/lib_$name.so \
-       capi.cu ring_dror.cu segment.cu cluster.cu hull.cu obb.cu ingest.cu split.cu 2>&1 | grep -i "error" || true
+       capi.cu ring_dror.cu segment.cu cluster.cu hull.cu obb.cu ingest.cu split.cu knn.cu 2>&1 | grep -i "error" || true
 done
 ls ../variants
