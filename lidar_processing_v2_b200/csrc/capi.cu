@@ -164,6 +164,10 @@ void carve(Dev& d, Carver& cv, int npx, int ncell_cap, std::uint32_t** mt_raw)
     cv.take(d.hseg_cnt, B * cap);
     cv.take(d.n_h, B);
     cv.take(d.hull_next, B);
+    cv.take(d.hwk_off, B * (cap + 1));
+    cv.take(d.hck_cnt, B * 2 * cap);
+    cv.take(d.n_work, B);
+    cv.take(d.n_multi, B);
     cv.take(d.boxes, B * cap);
     cv.take(d.raw, B * cap * kRawRecord);
     cv.take(d.raw_desc, B * 32);

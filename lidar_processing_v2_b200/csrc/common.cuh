@@ -213,6 +213,10 @@ struct Dev
     std::uint32_t* hseg_cnt;  // [B][cap]  per cluster: points that survive the octagon filter
     std::uint32_t* n_h;       // [B]       survivors per frame (input size of the hull sort)
     std::uint32_t* hull_next; // [B]       next cluster to hand out in k_hull_thin
+    std::uint32_t* hwk_off;   // [B][cap+1] per cluster: first chunk (work item) of the smem hull pass; [K] = chunks of the frame
+    std::uint32_t* hck_cnt;   // [B][2*cap] per chunk: points that survived its thinning (multi-chunk clusters)
+    std::uint32_t* n_work;    // [B]       chunks of the frame
+    std::uint32_t* n_multi;   // [B]       clusters of several chunks (listed in hfin) for the join pass
     ObbBox* boxes;            // [B][cap]  oriented bounding box per cluster (LPL_STAGE_BOXES)
     unsigned char* raw;       // [B][cap * kRawRecord] raw PointCloud2 records before the device unpack
     unsigned char* raw_desc;  // [B] record layouts (Cloud2Desc)

@@ -961,6 +961,19 @@ __global__ void __launch_bounds__(128) k_hull_gather(Dev d)
     const std::uint32_t warp = threadIdx.x >> 5, lane = lane_id();
     for (std::uint32_t c = blockIdx.x * 4u + warp; c < K; c += gridDim.x * 4u)
     {
+        if (lane == 0)
+        {
+            // z extent of the cluster (processor.cpp:648-655), reduced while labelling (cluster.cu)
+            float zlo = unord_f32(d.zmin_u[o + c]), zhi = unord_f32(d.zmax_u[o + c]);
+            const std::uint32_t zz = d.zzero[o + c];
+            if (zz != 0xffffffffu && (zz & 1u) != 0u)
+            {
+                // a zero extent carries the sign of the cluster's first zero-height point (see accumulate_cluster_stats)
+                zlo = zlo == 0.0f ? -0.0f : zlo;
+                zhi = zhi == 0.0f ? -0.0f : zhi;
+            }
+            d.zminmax[o + c] = make_float2(zlo, zhi);
+        }
         const std::uint32_t* gst = d.hstack + static_cast<std::size_t>(f) * 2 * d.cap + cstart[c] + c;
         const std::uint32_t off = hoff[c], hc = hoff[c + 1] - off;
         for (std::uint32_t t = lane; t < hc; t += 32)
@@ -970,6 +983,545 @@ __global__ void __launch_bounds__(128) k_hull_gather(Dev d)
             d.hull_idx[o + off + t] = idx;
             d.hull_xy[o + off + t] = make_float2(p.x, p.y);
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Shared-memory hull pass (the default path of launch_hulls).
+//
+// After the frame-wide sort every cluster is a contiguous, (x, y)-sorted segment. The segment is cut into chunks of
+// at most kChunk points and ONE WARP turns a chunk into its hull entirely in shared memory: thinning by per-lane
+// monotone chains over contiguous slices (a point that is on neither chain of its slice cannot be a hull vertex),
+// then the reference's own sweep (polygonizer.cpp:67-90) over what is left, by one lane, with its operands a
+// shared-memory access away - the global-memory round trips of the chains were what the old thinning passes spent
+// their time on. A cluster of several chunks - the walls and hedges of 5-20k points that used to keep one warp busy
+// while the rest of the GPU had finished - is thinned by as many warps in parallel (hull(A u B) = hull(hull(A) u
+// hull(B))), and a second pass joins the chunks' survivors, which are still in sorted order.
+// The orientation predicate is the reference's fp64 expression throughout, so the vertex set is the reference's.
+// ------------------------------------------------------------------------------------------
+#ifndef LPL_HULL_CHUNK
+#define LPL_HULL_CHUNK 256 // measured per 154-frame batch (chunk pass): 1024 -> 0.34 ms, 512 -> 0.22, 256 -> 0.15, 128 -> 0.11 (join pass grows)
+#endif
+#ifndef LPL_HULL_JOIN
+#define LPL_HULL_JOIN 1024 // buffer of the join pass: a cluster's chunk survivors should fit in one go
+#endif
+constexpr std::uint32_t kChunk = LPL_HULL_CHUNK;      // points one warp of the chunk pass holds in shared memory
+constexpr std::uint32_t kJoin = LPL_HULL_JOIN;        // points one warp of the join pass holds
+constexpr std::uint32_t kChunkWarps = 4;              // warps per CTA
+#ifndef LPL_HULL_SWEEP
+#define LPL_HULL_SWEEP 64 // survivors one lane sweeps without further thinning
+#endif
+#ifndef LPL_HULL_CHUNK_CTAS
+#define LPL_HULL_CHUNK_CTAS 12 // CTAs per frame of the chunk pass (154-frame batch: about one resident wave)
+#endif
+constexpr std::uint32_t kSweepBelow = LPL_HULL_SWEEP;             // survivors one lane sweeps without further thinning
+static_assert(kChunk % 32u == 0 && kChunk >= 64u && kChunk <= 2048u && kJoin % 32u == 0 && kJoin >= kChunk && kJoin <= 2048u, "buffer sizes");
+
+template <std::uint32_t C>
+struct WarpBufT
+{
+    static constexpr std::uint32_t kCap = C;
+    static constexpr std::uint32_t kSliceLen = C / 32u; // points per lane in a thinning pass (= chain stack depth)
+    float x[C];
+    float y[C];
+    std::uint32_t id[C];
+    std::uint16_t st[2u * C + 2u]; // lane chain stacks (lower | upper); the sweep's m + 1 vertex stack + m vertex flags
+};
+
+template <class WarpBuf>
+__device__ __forceinline__ P2 buf_pt(const WarpBuf& b, std::uint32_t i)
+{
+    P2 p;
+    p.x = static_cast<double>(b.x[i]);
+    p.y = static_cast<double>(b.y[i]);
+    return p;
+}
+
+// cnt elements from global memory into the buffer at position `at`: four independent 16-byte loads per lane in flight
+// before the first store (a load - store loop would pay one memory round trip per 32 elements)
+template <class WarpBuf>
+__device__ __forceinline__ void buf_load(WarpBuf& buf, std::uint32_t at, const uint4* __restrict__ src, std::uint32_t cnt)
+{
+    const std::uint32_t lane = lane_id();
+    for (std::uint32_t t0 = 0; t0 < cnt; t0 += 128u)
+    {
+        uint4 e[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+        {
+            const std::uint32_t t = t0 + k * 32u + lane;
+            e[k] = t < cnt ? src[t] : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+        {
+            const std::uint32_t t = t0 + k * 32u + lane;
+            if (t < cnt)
+            {
+                buf.x[at + t] = __uint_as_float(e[k].y);
+                buf.y[at + t] = __uint_as_float(e[k].z);
+                buf.id[at + t] = e[k].w;
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// One thinning pass over the m sorted entries: lane l sweeps slice [a, b) with a lower (left to right) and an
+// upper (right to left) chain; the survivors - the union of both chains - are compacted to the front in sorted
+// order. Returns how many are left.
+template <class WarpBuf>
+__device__ std::uint32_t buf_thin(WarpBuf& buf, std::uint32_t m)
+{
+    const std::uint32_t lane = lane_id();
+    constexpr std::uint32_t kSliceCap = WarpBuf::kSliceLen;
+    // slices of ~sqrt(2 m) points balance this pass against what it leaves for the next one (a slice of s sorted points
+    // keeps a handful); never more than the stack depth kSlice, so large inputs use all 32 lanes
+    std::uint32_t per = min(8u, kSliceCap);
+    while (per * per < 2u * m && per < kSliceCap)
+    {
+        ++per;
+    }
+    per = max(per, (m + 31u) / 32u);
+    const std::uint32_t a = min(m, lane * per), b = min(m, a + per);
+    std::uint16_t* L = buf.st + lane;                // entry k at L[k * 32]
+    constexpr std::uint32_t kSlice = WarpBuf::kSliceLen;
+    std::uint16_t* U = buf.st + 32u * kSlice + lane;
+    std::uint32_t kl = 0, ku = 0;
+    for (std::uint32_t i = a; i < b; ++i)
+    {
+        const P2 p = buf_pt(buf, i);
+        while (kl >= 2 && not_left(buf_pt(buf, L[(kl - 2) * 32u]), buf_pt(buf, L[(kl - 1) * 32u]), p))
+        {
+            --kl;
+        }
+        L[kl * 32u] = static_cast<std::uint16_t>(i);
+        ++kl;
+    }
+    for (std::uint32_t i = b; i > a; --i)
+    {
+        const P2 p = buf_pt(buf, i - 1u);
+        while (ku >= 2 && not_left(buf_pt(buf, U[(ku - 2) * 32u]), buf_pt(buf, U[(ku - 1) * 32u]), p))
+        {
+            --ku;
+        }
+        U[ku * 32u] = static_cast<std::uint16_t>(i - 1u);
+        ++ku;
+    }
+    // survivors of the slice, ascending position: merge of L (ascending) and U read from its top (ascending)
+    float kx[kSlice], ky[kSlice];
+    std::uint32_t kid[kSlice];
+    std::uint32_t cnt = 0;
+    {
+        std::uint32_t i = 0, j = ku;
+        while (i < kl || j > 0)
+        {
+            const std::uint32_t pl = i < kl ? L[i * 32u] : 0xffffffffu;
+            const std::uint32_t pu = j > 0 ? U[(j - 1u) * 32u] : 0xffffffffu;
+            i += (pl <= pu) ? 1u : 0u;
+            j -= (pu <= pl) ? 1u : 0u;
+            const std::uint32_t p = min(pl, pu);
+            kx[cnt] = buf.x[p];
+            ky[cnt] = buf.y[p];
+            kid[cnt] = buf.id[p];
+            ++cnt;
+        }
+    }
+    const std::uint32_t incl = warp_incl_scan(cnt);
+    const std::uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    __syncwarp(); // every lane has read its survivors
+    const std::uint32_t w = incl - cnt;
+    for (std::uint32_t k = 0; k < cnt; ++k)
+    {
+        buf.x[w + k] = kx[k];
+        buf.y[w + k] = ky[k];
+        buf.id[w + k] = kid[k];
+    }
+    __syncwarp();
+    return total;
+}
+
+// thin the m sorted entries until few enough are left for one lane's sweep (or thinning stops paying: points in
+// convex position); returns the survivor count, the survivors still sorted at the front of the buffer
+template <class WarpBuf>
+__device__ std::uint32_t buf_reduce(WarpBuf& buf, std::uint32_t m)
+{
+    bool stalled = false;
+    while (m > kSweepBelow && !stalled)
+    {
+        const std::uint32_t m2 = buf_thin(buf, m);
+        stalled = m2 * 4u > m * 3u;
+        m = m2;
+    }
+    return m;
+}
+
+// exact reduction: the m sorted entries are replaced by their hull vertices (still sorted). Used by the join pass when
+// thinning alone does not make room - its input is what earlier passes already thinned, so slices drop little.
+template <class WarpBuf>
+__device__ std::uint32_t buf_hull_only(WarpBuf& buf, std::uint32_t m)
+{
+    if (m < 3u)
+    {
+        return m; // nothing to drop (and the sweep is only defined from three points on)
+    }
+    const std::uint32_t lane = lane_id();
+    std::uint16_t* flag = buf.st + WarpBuf::kCap + 1u; // behind the sweep's m + 1 stack entries
+    for (std::uint32_t t = lane; t < m; t += 32u)
+    {
+        flag[t] = 0;
+    }
+    __syncwarp();
+    if (lane == 0)
+    {
+        const std::uint32_t hc = monotone_chain([&](std::uint32_t i) { return buf_pt(buf, i); }, m, buf.st);
+        for (std::uint32_t t = 0; t < hc; ++t)
+        {
+            flag[buf.st[t]] = 1;
+        }
+    }
+    __syncwarp();
+    std::uint32_t w = 0;
+    for (std::uint32_t base = 0; base < m; base += 32u)
+    {
+        const std::uint32_t t = base + lane;
+        const bool keep = t < m && flag[t] != 0;
+        float x = 0.f, y = 0.f;
+        std::uint32_t id = 0;
+        if (keep)
+        {
+            x = buf.x[t];
+            y = buf.y[t];
+            id = buf.id[t];
+        }
+        const std::uint32_t mask = __ballot_sync(0xffffffffu, keep);
+        __syncwarp(); // all reads of this batch before its writes (destinations never lie ahead of their sources)
+        if (keep)
+        {
+            const std::uint32_t dst = w + __popc(mask & ((1u << lane) - 1u));
+            buf.x[dst] = x;
+            buf.y[dst] = y;
+            buf.id[dst] = id;
+        }
+        w += __popc(mask);
+        __syncwarp();
+    }
+    return w;
+}
+
+// the reference's sweep over the m sorted survivors by lane 0; vertex ids (obstacle-cloud indices) to gst, count returned
+template <class WarpBuf>
+__device__ std::uint32_t buf_sweep(WarpBuf& buf, std::uint32_t m, std::uint32_t* __restrict__ gst)
+{
+    std::uint32_t hc = 0;
+    if (lane_id() == 0)
+    {
+        hc = monotone_chain([&](std::uint32_t i) { return buf_pt(buf, i); }, m, buf.st);
+    }
+    hc = __shfl_sync(0xffffffffu, hc, 0);
+    __syncwarp();
+    for (std::uint32_t t = lane_id(); t < hc; t += 32u)
+    {
+        gst[t] = buf.id[buf.st[t]];
+    }
+    __syncwarp();
+    return hc;
+}
+
+// fewer than three points: identity order = obstacle-cloud order (polygonizer.cpp:36-41)
+__device__ void hull_trivial(const uint4* __restrict__ seg, std::uint32_t m, std::uint32_t* __restrict__ gst, std::uint32_t* hcnt)
+{
+    if (lane_id() == 0)
+    {
+        std::uint32_t a = m > 0 ? seg[0].w : 0u, b = m > 1 ? seg[1].w : 0u;
+        if (m == 2 && b < a)
+        {
+            const std::uint32_t t = a;
+            a = b;
+            b = t;
+        }
+        if (m > 0)
+        {
+            gst[0] = a;
+        }
+        if (m > 1)
+        {
+            gst[1] = b;
+        }
+        *hcnt = m;
+    }
+}
+
+// chunks per cluster and their running sum (one CTA per frame)
+__global__ void __launch_bounds__(1024) k_hull_plan(Dev d)
+{
+    __shared__ std::uint32_t sh[33];
+    __shared__ std::uint32_t s_multi;
+    if (threadIdx.x == 0)
+    {
+        s_multi = 0;
+    }
+    __syncthreads();
+    const std::uint32_t f = blockIdx.x;
+    const std::uint32_t K = d.n_clusters[f];
+    const std::size_t o = static_cast<std::size_t>(f) * d.cap;
+    std::uint32_t* off = d.hwk_off + static_cast<std::size_t>(f) * (d.cap + 1);
+    std::uint32_t carry = 0;
+    for (std::uint32_t base = 0; base < K; base += 1024u)
+    {
+        const std::uint32_t c = base + threadIdx.x;
+        const std::uint32_t m = c < K ? d.hseg_cnt[o + c] : 0u;
+        const std::uint32_t chunks = (m + kChunk - 1u) / kChunk;
+        std::uint32_t total;
+        const std::uint32_t ex = block_excl_scan(chunks, sh, &total);
+        if (c < K)
+        {
+            off[c] = carry + ex;
+            d.hcnt[o + c] = 0; // clusters without a kept point keep an empty hull
+            if (chunks > 1u)
+            {
+                d.hfin[o + atomicAdd(&s_multi, 1u)] = c; // work list of the join pass (order does not matter)
+            }
+        }
+        carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+    {
+        off[K] = carry;
+        d.n_work[f] = carry;
+        d.n_multi[f] = s_multi;
+        d.hull_next[f] = 0; // hand-out counter of k_hull_chunks
+    }
+}
+
+// pass 1: one warp per chunk, chunks handed out dynamically (their cost differs by orders of magnitude); the
+// cluster of a chunk is found by bisection over the chunk offsets, staged in shared memory when they fit
+constexpr std::uint32_t kOffCache = 2048;
+
+__global__ void __launch_bounds__(kChunkWarps * 32) k_hull_chunks(Dev d)
+{
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    __shared__ std::uint32_t s_off[kOffCache];
+    using WarpBuf = WarpBufT<kChunk>;
+    WarpBuf& buf = reinterpret_cast<WarpBuf*>(s_raw)[threadIdx.x >> 5];
+    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t K = d.n_clusters[f];
+    const std::uint32_t W = d.n_work[f];
+    const std::size_t o = static_cast<std::size_t>(f) * d.cap;
+    const std::uint32_t* cstart = d.cstart + static_cast<std::size_t>(f) * (d.cap + 1);
+    const std::uint32_t* goff = d.hwk_off + static_cast<std::size_t>(f) * (d.cap + 1);
+    const bool cached = K + 1u <= kOffCache;
+    if (cached)
+    {
+        for (std::uint32_t t = threadIdx.x; t <= K; t += blockDim.x)
+        {
+            s_off[t] = goff[t];
+        }
+    }
+    __syncthreads();
+    const std::uint32_t* off = cached ? s_off : goff;
+    const bool in_b = (sort_passes(d.n_h[f]) & 1u) != 0u;
+    const uint4* sorted = (in_b ? d.hsB : d.hsA) + o;
+    uint4* other = (in_b ? d.hsA : d.hsB) + o;
+    const std::uint32_t lane = lane_id();
+    while (true)
+    {
+        std::uint32_t w = 0;
+        if (lane == 0)
+        {
+            w = atomicAdd(&d.hull_next[f], 1u);
+        }
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w >= W)
+        {
+            break;
+        }
+        // cluster of chunk w: the last c with off[c] <= w (clusters without chunks repeat the offset)
+        std::uint32_t lo = 0, hi = K;
+        while (hi - lo > 1u)
+        {
+            const std::uint32_t mid = (lo + hi) >> 1;
+            if (off[mid] <= w)
+            {
+                lo = mid;
+            }
+            else
+            {
+                hi = mid;
+            }
+        }
+        const std::uint32_t c = lo;
+        const std::uint32_t j = w - off[c];
+        const std::uint32_t mc = d.hseg_cnt[o + c];
+        const std::uint32_t first = j * kChunk;
+        const std::uint32_t m = min(kChunk, mc - first);
+        const uint4* seg = sorted + cstart[c] + first;
+        std::uint32_t* gst = d.hstack + static_cast<std::size_t>(f) * 2 * d.cap + cstart[c] + c; // segment length + 1 entries
+        const bool single = mc <= kChunk;
+        if (single && m < 3u)
+        {
+            hull_trivial(seg, m, gst, &d.hcnt[o + c]);
+            continue;
+        }
+        buf_load(buf, 0u, seg, m);
+        const std::uint32_t thinned = buf_reduce(buf, m);
+        if (single)
+        {
+            const std::uint32_t hc = buf_sweep(buf, thinned, gst);
+            if (lane == 0)
+            {
+                d.hcnt[o + c] = hc;
+            }
+        }
+        else
+        {
+            // this chunk's own hull vertices (an exact reduction: the join pass gathers a few dozen points per chunk
+            // instead of the up to kSweepBelow the thinning stops at), for the join pass
+            const std::uint32_t left = buf_hull_only(buf, thinned);
+            uint4* out = other + cstart[c] + first;
+            for (std::uint32_t t = lane; t < left; t += 32u)
+            {
+                out[t] = make_uint4(c, __float_as_uint(buf.x[t]), __float_as_uint(buf.y[t]), buf.id[t]);
+            }
+            if (lane == 0)
+            {
+                d.hck_cnt[static_cast<std::size_t>(f) * 2 * d.cap + w] = left;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// pass 2: clusters of several chunks. The chunks' survivors (consecutive x ranges, so their concatenation is sorted)
+// are gathered into the warp's buffer, thinned whenever the next chunk would not fit, and swept at the end. A cluster
+// whose survivors cannot be brought under one buffer (more than ~kChunk points in convex position) is swept from
+// its sorted segment in global memory: slow, always correct.
+constexpr std::uint32_t kJoinWarps = 2; // warps per CTA of the join pass
+
+__global__ void __launch_bounds__(kJoinWarps * 32) k_hull_join(Dev d)
+{
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    using WarpBuf = WarpBufT<kJoin>;
+    WarpBuf& buf = reinterpret_cast<WarpBuf*>(s_raw)[threadIdx.x >> 5];
+    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t K = d.n_clusters[f];
+    const std::size_t o = static_cast<std::size_t>(f) * d.cap;
+    const std::uint32_t* cstart = d.cstart + static_cast<std::size_t>(f) * (d.cap + 1);
+    const std::uint32_t* off = d.hwk_off + static_cast<std::size_t>(f) * (d.cap + 1);
+    const std::uint32_t* ck = d.hck_cnt + static_cast<std::size_t>(f) * 2 * d.cap;
+    const bool in_b = (sort_passes(d.n_h[f]) & 1u) != 0u;
+    const uint4* sorted = (in_b ? d.hsB : d.hsA) + o;
+    const uint4* other = (in_b ? d.hsA : d.hsB) + o;
+    const std::uint32_t lane = lane_id();
+    const std::uint32_t warps = gridDim.x * kJoinWarps;
+    const std::uint32_t nm = d.n_multi[f];
+    (void)K;
+    for (std::uint32_t q = blockIdx.x * kJoinWarps + (threadIdx.x >> 5); q < nm; q += warps)
+    {
+        const std::uint32_t c = d.hfin[o + q];
+        const std::uint32_t w0 = off[c], nchunks = off[c + 1] - w0;
+        std::uint32_t* gst = d.hstack + static_cast<std::size_t>(f) * 2 * d.cap + cstart[c] + c;
+        std::uint32_t fill = 0;
+        bool overflow = false;
+        // rounds over up to 32 chunks: lane j holds the survivor count of chunk j0 + j; as many leading chunks as fit
+        // the buffer are gathered in one flat loop (every lane loading, four loads in flight each); when none fits,
+        // the buffer is thinned first
+        std::uint32_t j0 = 0;
+        while (j0 < nchunks && !overflow)
+        {
+            const std::uint32_t cntj = j0 + lane < nchunks ? ck[w0 + j0 + lane] : 0u;
+            const std::uint32_t incl = warp_incl_scan(cntj);
+            std::uint32_t fit = __popc(__ballot_sync(0xffffffffu, j0 + lane < nchunks && fill + incl <= kJoin));
+            if (fit == 0u)
+            {
+                fill = buf_reduce(buf, fill);
+                fit = __popc(__ballot_sync(0xffffffffu, j0 + lane < nchunks && fill + incl <= kJoin));
+                if (fit == 0u)
+                {
+                    fill = buf_hull_only(buf, fill);
+                    fit = __popc(__ballot_sync(0xffffffffu, j0 + lane < nchunks && fill + incl <= kJoin));
+                }
+                if (fit == 0u)
+                {
+                    overflow = true; // even thinned, buffer + next chunk do not fit: points in convex position
+                    break;
+                }
+            }
+            const std::uint32_t total = __shfl_sync(0xffffffffu, incl, fit - 1u);
+            const uint4* base = other + cstart[c] + j0 * kChunk;
+            for (std::uint32_t e0 = 0; e0 < total; e0 += 128u)
+            {
+                uint4 v[4];
+                std::uint32_t pos[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                {
+                    const std::uint32_t e = e0 + k * 32u + lane;
+                    // chunk of flat element e: the first lane whose inclusive count exceeds e
+                    std::uint32_t jj = 0;
+#pragma unroll
+                    for (std::uint32_t step = 16u; step > 0u; step >>= 1)
+                    {
+                        const std::uint32_t probe = __shfl_sync(0xffffffffu, incl, jj + step - 1u);
+                        jj += (probe <= e) ? step : 0u;
+                    }
+                    jj = min(jj, 31u);
+                    const std::uint32_t before = __shfl_sync(0xffffffffu, incl - cntj, jj);
+                    pos[k] = e;
+                    v[k] = e < total ? base[static_cast<std::size_t>(jj) * kChunk + (e - before)] : make_uint4(0u, 0u, 0u, 0u);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                {
+                    if (pos[k] < total)
+                    {
+                        buf.x[fill + pos[k]] = __uint_as_float(v[k].y);
+                        buf.y[fill + pos[k]] = __uint_as_float(v[k].z);
+                        buf.id[fill + pos[k]] = v[k].w;
+                    }
+                }
+            }
+            fill += total;
+            j0 += fit;
+            __syncwarp();
+        }
+        std::uint32_t hc = 0;
+        if (!overflow)
+        {
+            hc = buf_sweep(buf, buf_reduce(buf, fill), gst);
+        }
+        else
+        {
+            const uint4* seg = sorted + cstart[c];
+            const std::uint32_t m = d.hseg_cnt[o + c];
+            if (lane == 0) // the vertex stack lives in the cluster's own output slots (segment length + 1 entries)
+            {
+                hc = monotone_chain([&](std::uint32_t i) { return elem_pt(seg[i]); }, m, gst);
+            }
+            hc = __shfl_sync(0xffffffffu, hc, 0);
+            __syncwarp();
+            for (std::uint32_t t0 = 0; t0 < hc; t0 += 32u)
+            {
+                const std::uint32_t t = t0 + lane;
+                std::uint32_t v = 0;
+                if (t < hc)
+                {
+                    v = seg[gst[t]].w;
+                }
+                __syncwarp();
+                if (t < hc)
+                {
+                    gst[t] = v;
+                }
+            }
+            __syncwarp();
+        }
+        if (lane == 0)
+        {
+            d.hcnt[o + c] = hc;
+        }
+        __syncwarp();
     }
 }
 
@@ -994,12 +1546,17 @@ void launch_hull_sort(Ctx* c, std::uint32_t nf)
     }
 }
 
+#ifndef LPL_HULL_V1
+#define LPL_HULL_V1 0 // 1: the frame-wide merge sort + global-memory thinning passes of round 1
+#endif
+
 void launch_hulls(Ctx* c, std::uint32_t nf)
 {
     Dev& d = c->d;
     cudaStream_t s = c->stream;
     k_hull_octagon<<<dim3(4, nf), 128, 0, s>>>(d);
     mark(c, "hull_octagon");
+#if LPL_HULL_V1
     // d.lab (RECM labels of the segmenter) is free by now: it holds the recorded verdicts
     launch_compact_recorded(c, "hull_keep", nf, d.tiles, d.n_o, d.tile_cnt, d.n_h, d.lab, HullKeepPred{d}, HullKeepEmit{d});
     k_excl_scan<<<nf, 1024, 0, s>>>(d.hseg_cnt, d.cap, d.cstart, d.cap + 1, d.cap, d.n_clusters, nullptr);
@@ -1013,6 +1570,22 @@ void launch_hulls(Ctx* c, std::uint32_t nf)
     mark(c, "hull_thin");
     k_hull_final<<<dim3(per_frame_ctas(16, nf, 256), nf), 64, 0, s>>>(d);
     mark(c, "hull_final");
+#else
+    // d.lab (RECM labels of the segmenter) is free by now: it holds the recorded verdicts
+    launch_compact_recorded(c, "hull_keep", nf, d.tiles, d.n_o, d.tile_cnt, d.n_h, d.lab, HullKeepPred{d}, HullKeepEmit{d});
+    k_excl_scan<<<nf, 1024, 0, s>>>(d.hseg_cnt, d.cap, d.cstart, d.cap + 1, d.cap, d.n_clusters, nullptr);
+    mark(c, "hull_seg_scan");
+    launch_hull_sort(c, nf);
+    k_hull_plan<<<nf, 1024, 0, s>>>(d);
+    mark(c, "hull_plan");
+    constexpr std::size_t smem = sizeof(WarpBufT<kChunk>) * kChunkWarps, smem_join = sizeof(WarpBufT<kJoin>) * kJoinWarps;
+    cudaFuncSetAttribute(k_hull_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaFuncSetAttribute(k_hull_join, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_join));
+    k_hull_chunks<<<dim3(per_frame_ctas(LPL_HULL_CHUNK_CTAS, nf, 256), nf), kChunkWarps * 32, smem, s>>>(d);
+    mark(c, "hull_chunks");
+    k_hull_join<<<dim3(per_frame_ctas(4, nf, 64), nf), kJoinWarps * 32, smem_join, s>>>(d);
+    mark(c, "hull_join");
+#endif
     k_excl_scan<<<nf, 1024, 0, s>>>(d.hcnt, d.cap, d.hull_off, d.cap + 1, d.cap, d.n_clusters, d.n_hull);
     mark(c, "hull_off_scan");
     k_hull_gather<<<dim3(64, nf), 128, 0, s>>>(d);

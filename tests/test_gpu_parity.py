@@ -104,6 +104,11 @@ def test_convex_hull_entry_point(ctx, port):
         np.array([[0, 0], [1, 0], [1, 1], [0, 1], [0.5, 0.5]], float),
         np.array([[3.0, 4.0]]), np.array([[0.0, 0.0], [1.0, 1.0]]),
         np.repeat(np.array([[2.0, 2.0]]), 7, 0),                 # all identical
+        rng.normal(0, 8, (30000, 2)),                             # 30 chunks of the shared-memory hull pass + the join
+        np.c_[100 * np.cos(np.linspace(0, 2 * np.pi, 3000, endpoint=False)),
+              100 * np.sin(np.linspace(0, 2 * np.pi, 3000, endpoint=False))],   # ~3000 points in convex position: more hull
+                                                                  # vertices than a warp's buffer holds -> the global-memory path
+        np.c_[np.linspace(-5, 5, 1500), np.linspace(-5, 5, 1500) ** 2],        # a parabola: every point a vertex, 2 chunks
     ]
     for xy in cases:
         xy = xy.astype(np.float32).astype(np.float64)
