@@ -249,8 +249,8 @@ def algorithmic_bytes(name: str, s: dict) -> float:
         # the vertices (8M + 4M + 4 Hv + 12 K); the chain kernels are charged with that
         "hull_octagon": 64 * K, "hull_keep": (16 + 4) * M + 16 * NH, "hull_seg_scan": 8 * K,
         "hull_tilesort": 32 * NH, "hull_merge": 32 * NH,
-        "hull_thin_big": 16 * NH + 4 * HV + 12 * K, "hull_thin": 16 * NH + 4 * HV + 12 * K,
-        "hull_final": 16 * HV + 12 * K, "hull_off_scan": 8 * K, "hull_gather": 4 * HV + 16 * HV + 12 * HV,
+        "hull_plan": 12 * K, "hull_chunks": 16 * NH + 4 * HV + 12 * K, "hull_join": 4 * HV + 12 * K,
+        "hull_off_scan": 8 * K, "hull_gather": 4 * HV + 16 * HV + 12 * HV + 8 * K,
         "obb_frames": 8 * HV + 80 * K,
         "label_count": 4 * M,
     }

@@ -119,8 +119,6 @@ void carve(Dev& d, Carver& cv, int npx, int ncell_cap, std::uint32_t** mt_raw)
     cv.take(d.mk, B * q);
     cv.take(d.stale_ref, B * d.nborder_cap * 12);
     cv.take(d.n_border, B);
-    cv.take(d.runs, B * q);
-    cv.take(d.n_runs, B);
     cv.take(d.jcp_rounds, B);
     cv.take(d.labels_out, B * cap);
     cv.take(d.bgr, B * npx * 3);
@@ -146,8 +144,6 @@ void carve(Dev& d, Carver& cv, int npx, int ncell_cap, std::uint32_t** mt_raw)
     cv.take(d.cstart, B * (cap + 1));
     cv.take(d.hsA, B * cap);
     cv.take(d.hsB, B * cap);
-    cv.take(d.hstL, B * cap);
-    cv.take(d.hstU, B * cap);
     cv.take(d.hstack, B * 2 * cap);
     cv.take(d.hfin, B * cap);
     cv.take(d.hcnt, B * cap);

@@ -165,8 +165,6 @@ struct Dev
     std::uint32_t* stale_ref; // [B][nborder][12] explicit pixel refs for inherited slots
     std::uint32_t* n_border;  // [B]
     std::uint32_t nborder_cap;
-    std::uint32_t* runs;      // [B][qcap] first queue entry of every run of horizontally adjacent queued pixels
-    std::uint32_t* n_runs;    // [B]
     std::uint32_t* jcp_rounds;// [B] chunks of queue entries swept by k_jcp_rows (diagnostic)
     std::uint8_t* labels_out; // [B][cap]  Label (0/1/2) per *input* point
     std::uint8_t* bgr;        // [B][npx*3]
@@ -194,10 +192,8 @@ struct Dev
     std::uint32_t* cstart;    // [B][cap+1]
     uint4* hsA;               // [B][cap]  sort elements (label, ord x, ord y, index), ping
     uint4* hsB;               // [B][cap]  pong
-    std::uint32_t* hstL;      // [B][cap]  per-lane lower-chain stacks of the thinning passes
-    std::uint32_t* hstU;      // [B][cap]  per-lane upper-chain stacks
     std::uint32_t* hstack;    // [B][2*cap] per-cluster hull vertices (at segment offset + cluster id)
-    std::uint32_t* hfin;      // [B][cap]  per cluster: survivor count | buffer flag | done flag after thinning
+    std::uint32_t* hfin;      // [B][cap]  clusters of several chunks: work list of the join pass
     std::uint32_t* hcnt;      // [B][cap]  hull vertex count per cluster
     std::uint32_t* hull_off;  // [B][cap+1]
     std::uint32_t* hull_idx;  // [B][cap]  obstacle-cloud index per hull vertex
@@ -212,7 +208,7 @@ struct Dev
     float2* octa;             // [B][cap][kExtDirs] per cluster: the polygon of those points, or NaN when unusable
     std::uint32_t* hseg_cnt;  // [B][cap]  per cluster: points that survive the octagon filter
     std::uint32_t* n_h;       // [B]       survivors per frame (input size of the hull sort)
-    std::uint32_t* hull_next; // [B]       next cluster to hand out in k_hull_thin
+    std::uint32_t* hull_next; // [B]       next chunk to hand out in k_hull_chunks
     std::uint32_t* hwk_off;   // [B][cap+1] per cluster: first chunk (work item) of the smem hull pass; [K] = chunks of the frame
     std::uint32_t* hck_cnt;   // [B][2*cap] per chunk: points that survived its thinning (multi-chunk clusters)
     std::uint32_t* n_work;    // [B]       chunks of the frame
@@ -232,7 +228,7 @@ enum : std::uint32_t
     ST_RNG_EXHAUSTED = 2u,   // RANSAC needed more than kMtRaws generator outputs
     ST_HASH_FULL = 4u,       // voxel hash table full
     ST_BORDER_OVERFLOW = 8u, // more queued border pixels than reserved
-    ST_JCP_STALL = 16u,      // JCP sweep waited beyond its spin limit (internal error)
+    ST_JCP_STALL = 16u,      // JCP sweep met a rows-above dependency that was not final (internal error)
 };
 
 // ---------------------------------------------------------------- small device helpers

@@ -9,68 +9,15 @@
 // per-label gather and the per-cluster std::sort: after it every cluster is a contiguous,
 // (x, y)-sorted segment (k_hull_tilesort: 2048-element bitonic tiles in shared memory;
 // k_hull_merge: merge-path passes, each output tile merged in shared memory).
-// One warp then builds each hull (k_hull_chain): clusters above 128 points are first thinned
-// by per-lane monotone chains over contiguous chunks (a point that is not on the lower or upper
-// hull of its chunk cannot be on the cluster's hull), repeatedly, and the survivors are swept by
-// the reference's own lower/upper chain with the same fp64 orientation predicate evaluated
-// without FMA contraction. The vertex list (coordinates) equals the reference's; only the *index*
-// reported for exactly duplicated (x, y) points may differ, as it does between std::sort
-// implementations.
+// The segments are then cut into chunks and one warp per chunk thins and sweeps it in shared memory
+// (k_hull_chunks, k_hull_join - see "Shared-memory hull pass" below) with the reference's own lower / upper
+// chain and its fp64 orientation predicate evaluated without FMA contraction. The vertex list
+// (coordinates) equals the reference's; only the *index* reported for exactly duplicated (x, y)
+// points may differ, as it does between std::sort implementations.
 #include "common.cuh"
 
 namespace lpl
 {
-constexpr int kHullThreads = 32;   // one warp per CTA: the hardware balances clusters of very different size
-#ifndef LPL_HULL_CTAS
-#define LPL_HULL_CTAS 24
-#endif
-#ifndef LPL_HULL_BIG
-#define LPL_HULL_BIG 1024
-#endif
-#ifndef LPL_HULL_LANEDIV
-#define LPL_HULL_LANEDIV 2
-#endif
-#ifndef LPL_HULL_FILTER_ABOVE
-#define LPL_HULL_FILTER_ABOVE 48
-#endif
-#ifndef LPL_HULL_FINAL_MAX
-#define LPL_HULL_FINAL_MAX 256
-#endif
-constexpr int kHullCtasPerFrame = LPL_HULL_CTAS;  // single-warp CTAs per frame (about one resident wave for a 154-frame batch);
-                                       // clusters are handed out dynamically, their sizes differ by orders of magnitude
-constexpr std::uint32_t kChainSmem = 512; // survivors swept from shared memory
-constexpr std::uint32_t kFilterAbove = LPL_HULL_FILTER_ABOVE;  // clusters above this are thinned by all lanes first
-constexpr std::uint32_t kLaneStack = 16;  // per-lane chain stack entries kept in shared memory
-
-// per-lane stack of (position, x, y): the first kLaneStack entries live in shared memory - a pop
-// is on the critical path of the sweep and must not cost a trip to L2 for the popped point's
-// coordinates - deeper ones spill to the lane's slice of a global scratch array (positions only).
-// Entries of the lanes are interleaved (entry k of lane l at k * stride + l): no bank conflicts
-// when the lanes work at the same depth.
-struct LaneStack
-{
-    std::uint32_t* sm;    // shared-memory positions, already offset by the lane
-    float2* smp;          // shared-memory coordinates, same layout
-    std::uint32_t stride; // lanes in the group
-    std::uint32_t* gl;    // this lane's global slice
-    __device__ __forceinline__ std::uint32_t get(std::uint32_t k) const { return k < kLaneStack ? sm[k * stride] : gl[k]; }
-    __device__ __forceinline__ void set(std::uint32_t k, std::uint32_t v, float2 xy) const
-    {
-        if (k < kLaneStack)
-        {
-            sm[k * stride] = v;
-            smp[k * stride] = xy;
-        }
-        else
-        {
-            gl[k] = v;
-        }
-    }
-};
-
-// plain (coherent) load: the thinning passes re-read what earlier passes of the same kernel wrote
-__device__ __forceinline__ uint4 ldg4(const uint4* p) { return *p; }
-
 // element = (label, x bits, y bits, obstacle-cloud index) with -0.0 folded into +0.0 (the
 // reference comparator treats them as equal); the index makes the order total
 __device__ __forceinline__ bool elem_less(const uint4& a, const uint4& b)
@@ -417,192 +364,12 @@ __global__ void __launch_bounds__(kTileThreads) k_hull_merge(Dev d, std::uint32_
 // ------------------------------------------------------------------------------------------
 // hull chains
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float2 elem_xy(const uint4& e)
-{
-    return make_float2(__uint_as_float(e.y), __uint_as_float(e.z));
-}
-
-__device__ __forceinline__ P2 stack_pt(const LaneStack& S, std::uint32_t k, const uint4* __restrict__ src)
-{
-    P2 p;
-    if (k < kLaneStack)
-    {
-        const float2 v = S.smp[k * S.stride];
-        p.x = static_cast<double>(v.x);
-        p.y = static_cast<double>(v.y);
-    }
-    else
-    {
-        const uint4 e = src[S.gl[k]];
-        p.x = static_cast<double>(__uint_as_float(e.y));
-        p.y = static_cast<double>(__uint_as_float(e.z));
-    }
-    return p;
-}
-
 __device__ __forceinline__ P2 elem_pt(const uint4& e)
 {
     P2 p;
     p.x = static_cast<double>(__uint_as_float(e.y));
     p.y = static_cast<double>(__uint_as_float(e.z));
     return p;
-}
-
-// One lane's share of a thinning pass: the lower chain (left to right) and the upper chain (right to
-// left, as the reference walks it) over the contiguous chunk src[a..b). A point that is on neither
-// chain of its chunk cannot be on the cluster's hull.
-// Both chains advance in ONE warp-uniform loop as two independent state machines: per iteration a
-// lane evaluates one orientation predicate per chain and either pops its stack or pushes the
-// current point and moves on. Compared with a loop over points with an inner pop loop this keeps
-// the lanes of a warp converged (a step costs one predicate, not the longest pop run among the
-// lanes) and gives every lane two independent fp64 dependency chains to overlap. The next two
-// elements of each direction are in flight while the current one is worked on.
-// Must be called by all lanes of the warp (lanes with an empty chunk just vote).
-__device__ __forceinline__ void lane_chains(const uint4* __restrict__ src, std::uint32_t a, std::uint32_t b,
-                                            const LaneStack& L, const LaneStack& U, std::uint32_t& kl,
-                                            std::uint32_t& ku)
-{
-    kl = 0;
-    ku = 0;
-    bool act_l = b > a, act_u = b > a;
-    std::uint32_t il = a, iu = b - 1u; // current point of each chain (valid while active)
-    P2 s2l = {0.0, 0.0}, s1l = s2l, s2u = s2l, s1u = s2l;
-    uint4 el = make_uint4(0, 0, 0, 0), el1 = el, el2 = el, eu = el, eu1 = el, eu2 = el;
-    if (act_l)
-    {
-        el = ldg4(src + a);
-        el1 = ldg4(src + min(a + 1u, b - 1u));
-        el2 = ldg4(src + min(a + 2u, b - 1u));
-        eu = ldg4(src + (b - 1u));
-        eu1 = ldg4(src + max(b - 1u, a + 1u) - 1u);
-        eu2 = ldg4(src + max(b - 1u, a + 2u) - 2u);
-    }
-    while (__any_sync(0xffffffffu, act_l || act_u))
-    {
-        if (act_l)
-        {
-            const P2 p = elem_pt(el);
-            if (kl >= 2 && not_left(s2l, s1l, p))
-            {
-                --kl;
-                s1l = s2l;
-                if (kl >= 2)
-                {
-                    s2l = stack_pt(L, kl - 2, src);
-                }
-            }
-            else
-            {
-                L.set(kl, il, elem_xy(el));
-                ++kl;
-                s2l = s1l;
-                s1l = p;
-                ++il;
-                if (il < b)
-                {
-                    el = el1;
-                    el1 = el2;
-                    el2 = ldg4(src + min(il + 2u, b - 1u));
-                }
-                else
-                {
-                    act_l = false;
-                }
-            }
-        }
-        if (act_u)
-        {
-            const P2 p = elem_pt(eu);
-            if (ku >= 2 && not_left(s2u, s1u, p))
-            {
-                --ku;
-                s1u = s2u;
-                if (ku >= 2)
-                {
-                    s2u = stack_pt(U, ku - 2, src);
-                }
-            }
-            else
-            {
-                U.set(ku, iu, elem_xy(eu));
-                ++ku;
-                s2u = s1u;
-                s1u = p;
-                if (iu > a)
-                {
-                    --iu;
-                    eu = eu1;
-                    eu1 = eu2;
-                    eu2 = ldg4(src + max(iu, a + 2u) - 2u);
-                }
-                else
-                {
-                    act_u = false;
-                }
-            }
-        }
-    }
-}
-
-// survivors of one lane = union of its ascending lower list and its descending upper list
-__device__ __forceinline__ std::uint32_t lane_survivors(const LaneStack& L, const LaneStack& U, std::uint32_t kl,
-                                                        std::uint32_t ku)
-{
-    std::uint32_t cnt = 0;
-    std::uint32_t i = 0, j = ku;
-    while (i < kl || j > 0)
-    {
-        const std::uint32_t pl = i < kl ? L.get(i) : 0xffffffffu;
-        const std::uint32_t pu = j > 0 ? U.get(j - 1) : 0xffffffffu;
-        i += (pl <= pu) ? 1u : 0u;
-        j -= (pu <= pl) ? 1u : 0u;
-        ++cnt;
-    }
-    return cnt;
-}
-
-__device__ __forceinline__ void lane_emit(const uint4* __restrict__ src, uint4* __restrict__ dst, std::uint32_t w,
-                                          const LaneStack& L, const LaneStack& U, std::uint32_t kl, std::uint32_t ku)
-{
-    std::uint32_t i = 0, j = ku;
-    while (i < kl || j > 0)
-    {
-        const std::uint32_t pl = i < kl ? L.get(i) : 0xffffffffu;
-        const std::uint32_t pu = j > 0 ? U.get(j - 1) : 0xffffffffu;
-        i += (pl <= pu) ? 1u : 0u;
-        j -= (pu <= pl) ? 1u : 0u;
-        dst[w++] = ldg4(src + min(pl, pu));
-    }
-}
-
-// Warp-wide thinning pass: lane l sweeps its contiguous chunk of src[0..m); the survivor lists, in
-// sorted order, are compacted into dst. stL / stU: global spill space for the per-lane stacks
-// (m entries each); smL / smU / spL / spU: 32 * kLaneStack shared-memory entries each. Returns the
-// survivor count.
-__device__ std::uint32_t hull_filter(const uint4* __restrict__ src, std::uint32_t m, uint4* __restrict__ dst,
-                                     std::uint32_t* __restrict__ stL, std::uint32_t* __restrict__ stU,
-                                     std::uint32_t* smL, std::uint32_t* smU, float2* spL, float2* spU)
-{
-    const std::uint32_t lane = lane_id();
-    // balance the two sequential phases: a lane sweeps m / lanes points now and every lane leaves
-    // roughly eight survivors for the next (sequential or thinner) sweep -> lanes ~ sqrt(m / 8)
-    std::uint32_t lanes = 2u;
-    while (lanes < 32u && lanes * lanes * LPL_HULL_LANEDIV < m)
-    {
-        ++lanes;
-    }
-    const std::uint32_t chunk = (m + lanes - 1u) / lanes;
-    const std::uint32_t a = min(m, lane * chunk), b = min(m, a + chunk);
-    const LaneStack L{smL + lane, spL + lane, 32u, stL + a};
-    const LaneStack U{smU + lane, spU + lane, 32u, stU + a};
-    std::uint32_t kl, ku;
-    lane_chains(src, a, b, L, U, kl, ku);
-    const std::uint32_t cnt = lane_survivors(L, U, kl, ku);
-    const std::uint32_t incl = warp_incl_scan(cnt);
-    const std::uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-    lane_emit(src, dst, incl - cnt, L, U, kl, ku);
-    __syncwarp();
-    return total;
 }
 
 // the reference's sweep (polygonizer.cpp:67-90) over m >= 1 sorted points; st needs m + 1 entries.
@@ -645,310 +412,6 @@ __device__ __forceinline__ std::uint32_t monotone_chain(Get P, std::uint32_t m, 
         s1 = pi;
     }
     return static_cast<std::uint32_t>(k - 1);
-}
-
-// hfin[c]: what k_hull_thin leaves for k_hull_final
-constexpr std::uint32_t kFinDone = 0x80000000u;   // hull already written by k_hull_thin
-constexpr std::uint32_t kFinOther = 0x40000000u;  // survivors live in the second sort buffer
-constexpr std::uint32_t kFinalMax = LPL_HULL_FINAL_MAX;          // survivors swept by one thread (local-memory stack)
-
-constexpr std::uint32_t kFinPre = 0x20000000u;    // k_hull_thin_big already thinned the cluster once (into the other buffer)
-constexpr std::uint32_t kBigAbove = LPL_HULL_BIG;         // clusters above this get a CTA-wide first thinning pass
-constexpr int kBigThreads = 256;
-constexpr int kBigCtasPerFrame = 8;
-
-// Pass 0: the handful of very large clusters of a frame (walls, vegetation: up to ~20k points) would
-// leave one warp sweeping 600-point chunks per lane while everything else has finished; a whole
-// CTA thins them once first (256 chunks), the warp passes of k_hull_thin take over from there.
-// Also resets hfin for every cluster of the frame.
-__global__ void __launch_bounds__(kBigThreads) k_hull_thin_big(Dev d)
-{
-    extern __shared__ __align__(16) unsigned char s_big[]; // 2 x (positions + coordinates) x kBigThreads x kLaneStack
-    float2* s_xy = reinterpret_cast<float2*>(s_big);
-    std::uint32_t* s_pos = reinterpret_cast<std::uint32_t*>(s_xy + 2 * kBigThreads * kLaneStack);
-    __shared__ std::uint32_t s_scan[33];
-    const std::uint32_t f = blockIdx.y;
-    const std::uint32_t K = d.n_clusters[f];
-    const std::size_t o = static_cast<std::size_t>(f) * d.cap;
-    const std::uint32_t* cstart = d.cstart + static_cast<std::size_t>(f) * (d.cap + 1);
-    const bool in_b = (sort_passes(d.n_h[f]) & 1u) != 0u;
-    const uint4* sorted = (in_b ? d.hsB : d.hsA) + o;
-    uint4* other = (in_b ? d.hsA : d.hsB) + o;
-    if (blockIdx.x == 0 && threadIdx.x == 0)
-    {
-        d.hull_next[f] = 0; // hand-out counter of k_hull_thin
-    }
-    for (std::uint32_t c = blockIdx.x; c < K; c += gridDim.x)
-    {
-        const std::uint32_t seg = cstart[c];
-        const std::uint32_t m = cstart[c + 1] - seg;
-        if (m <= kBigAbove)
-        {
-            if (threadIdx.x == 0)
-            {
-                d.hfin[o + c] = 0;
-            }
-            continue;
-        }
-        const uint4* src = sorted + seg;
-        uint4* dst = other + seg;
-        const std::uint32_t chunk = (m + kBigThreads - 1u) / kBigThreads;
-        const std::uint32_t a = min(m, threadIdx.x * chunk), b = min(m, a + chunk);
-        const LaneStack L{s_pos + threadIdx.x, s_xy + threadIdx.x, kBigThreads, d.hstL + o + seg + a};
-        const LaneStack U{s_pos + kBigThreads * kLaneStack + threadIdx.x, s_xy + kBigThreads * kLaneStack + threadIdx.x,
-                          kBigThreads, d.hstU + o + seg + a};
-        std::uint32_t kl, ku;
-        lane_chains(src, a, b, L, U, kl, ku);
-        const std::uint32_t cnt = lane_survivors(L, U, kl, ku);
-        std::uint32_t total;
-        const std::uint32_t w = block_excl_scan(cnt, s_scan, &total);
-        lane_emit(src, dst, w, L, U, kl, ku);
-        if (threadIdx.x == 0)
-        {
-            d.hfin[o + c] = total | kFinPre;
-        }
-        __syncthreads(); // the stacks / s_scan are reused by the next cluster
-    }
-}
-
-// Pass 1, one warp per cluster above kFilterAbove points: thinning passes ping-pong between the two
-// sort buffers (the segment is private to the warp) until few enough points survive for a single
-// thread, or thinning stops paying (points in convex position), in which case the warp sweeps the
-// survivors itself.
-__global__ void __launch_bounds__(kHullThreads) k_hull_thin(Dev d)
-{
-    __shared__ float2 s_key[kChainSmem];
-    __shared__ std::uint16_t s_st[kChainSmem + 2];
-    __shared__ std::uint32_t s_lane[2][32 * kLaneStack];
-    __shared__ float2 s_lxy[2][32 * kLaneStack];
-    const std::uint32_t f = blockIdx.y;
-    const std::uint32_t K = d.n_clusters[f];
-    const std::uint32_t lane = lane_id();
-    const std::size_t o = static_cast<std::size_t>(f) * d.cap;
-    const std::uint32_t* cstart = d.cstart + static_cast<std::size_t>(f) * (d.cap + 1);
-    const bool in_b = (sort_passes(d.n_h[f]) & 1u) != 0u;
-    uint4* sorted = (in_b ? d.hsB : d.hsA) + o;
-    uint4* other = (in_b ? d.hsA : d.hsB) + o;
-    while (true)
-    {
-        std::uint32_t c = 0;
-        if (lane == 0)
-        {
-            c = atomicAdd(&d.hull_next[f], 1u);
-        }
-        c = __shfl_sync(0xffffffffu, c, 0);
-        if (c >= K)
-        {
-            break;
-        }
-        const std::uint32_t seg = cstart[c];
-        const std::uint32_t n = cstart[c + 1] - seg;
-#ifdef LPL_HULL_TRACE
-        // diagnostics (build with LPL_NVCC_EXTRA=-DLPL_HULL_TRACE): per cluster, the survivors and the
-        // cycles of every thinning pass and of what follows; printed for clusters above 50k cycles
-        struct Trace
-        {
-            long long t0, tp[6];
-            std::uint32_t f, c, n, mp[6], np;
-            __device__ void pass(std::uint32_t m)
-            {
-                if (np < 6)
-                {
-                    tp[np] = clock64();
-                    mp[np] = m;
-                    ++np;
-                }
-            }
-            __device__ ~Trace()
-            {
-                const long long t1 = clock64();
-                if (t1 - t0 > 50000 && (threadIdx.x & 31u) == 0)
-                {
-                    printf("hull_thin f %u c %u n %u total %lld passes %u:", f, c, n, t1 - t0, np);
-                    long long prev = t0;
-                    for (std::uint32_t k = 0; k < np; ++k)
-                    {
-                        printf(" [m %u cyc %lld]", mp[k], tp[k] - prev);
-                        prev = tp[k];
-                    }
-                    printf(" tail %lld\n", t1 - prev);
-                }
-            }
-        } trace{clock64(), {}, f, c, n, {}, 0u};
-#endif
-        if (n <= kFilterAbove)
-        {
-            if (lane == 0)
-            {
-                d.hfin[o + c] = n;
-            }
-            continue;
-        }
-        std::uint32_t* gst = d.hstack + static_cast<std::size_t>(f) * 2 * d.cap + seg + c; // n + 1 entries
-        uint4* cur = sorted + seg;
-        uint4* nxt = other + seg;
-        std::uint32_t m = n;
-        bool in_other = false;
-        const std::uint32_t pre = d.hfin[o + c];
-        if (pre & kFinPre)
-        {
-            // k_hull_thin_big left its survivors in the other buffer
-            m = pre & 0x1fffffffu;
-            cur = other + seg;
-            nxt = sorted + seg;
-            in_other = true;
-        }
-        bool stalled = false;
-        while (m > kFilterAbove && !stalled)
-        {
-            const std::uint32_t m2 = hull_filter(cur, m, nxt, d.hstL + o + seg, d.hstU + o + seg, s_lane[0], s_lane[1], s_lxy[0], s_lxy[1]);
-            uint4* t = cur;
-            cur = nxt;
-            nxt = t;
-            in_other = !in_other;
-            stalled = m2 * 4u > m * 3u; // convex-position input: thinning does not pay
-            m = m2;
-#ifdef LPL_HULL_TRACE
-            trace.pass(m);
-#endif
-        }
-        if (m <= kFinalMax)
-        {
-            if (lane == 0)
-            {
-                d.hfin[o + c] = m | (in_other ? kFinOther : 0u);
-            }
-            continue;
-        }
-        std::uint32_t hc = 0;
-        if (m <= kChainSmem)
-        {
-            for (std::uint32_t t = lane; t < m; t += 32)
-            {
-                const uint4 e = cur[t];
-                s_key[t] = make_float2(__uint_as_float(e.y), __uint_as_float(e.z));
-            }
-            __syncwarp();
-            if (lane == 0)
-            {
-                const float2* key = s_key;
-                hc = monotone_chain(
-                    [&](std::uint32_t i) {
-                        const float2 v = key[i];
-                        P2 p;
-                        p.x = static_cast<double>(v.x);
-                        p.y = static_cast<double>(v.y);
-                        return p;
-                    },
-                    m, s_st);
-            }
-            hc = __shfl_sync(0xffffffffu, hc, 0);
-            __syncwarp();
-            for (std::uint32_t t = lane; t < hc; t += 32)
-            {
-                gst[t] = cur[s_st[t]].w;
-            }
-            __syncwarp();
-        }
-        else
-        {
-            // rare: more than kChainSmem points in (near) convex position; sweep in global memory
-            std::uint32_t* st = (m == n) ? gst : (d.hstL + o + seg); // m + 1 entries
-            if (lane == 0)
-            {
-                hc = monotone_chain([&](std::uint32_t i) { return elem_pt(cur[i]); }, m, st);
-            }
-            hc = __shfl_sync(0xffffffffu, hc, 0);
-            __syncwarp();
-            // positions -> obstacle-cloud indices (in place when st == gst)
-            for (std::uint32_t t0 = 0; t0 < hc; t0 += 32)
-            {
-                const std::uint32_t t = t0 + lane;
-                std::uint32_t v = 0;
-                if (t < hc)
-                {
-                    v = cur[st[t]].w;
-                }
-                __syncwarp();
-                if (t < hc)
-                {
-                    gst[t] = v;
-                }
-            }
-            __syncwarp();
-        }
-        if (lane == 0)
-        {
-            d.hcnt[o + c] = hc;
-            d.hfin[o + c] = kFinDone;
-        }
-    }
-}
-
-// Pass 2, one thread per cluster: z extent, the trivial cases, and the reference's sweep over the
-// (at most kFinalMax) surviving points with the stack in local memory. 32 clusters per warp keep
-// the sequential sweeps from wasting 31 of 32 lanes.
-__global__ void __launch_bounds__(64) k_hull_final(Dev d)
-{
-    const std::uint32_t f = blockIdx.y;
-    const std::uint32_t K = d.n_clusters[f];
-    const std::size_t o = static_cast<std::size_t>(f) * d.cap;
-    const std::uint32_t* cstart = d.cstart + static_cast<std::size_t>(f) * (d.cap + 1);
-    const bool in_b = (sort_passes(d.n_h[f]) & 1u) != 0u;
-    for (std::uint32_t c = blockIdx.x * 64u + threadIdx.x; c < K; c += gridDim.x * 64u)
-    {
-    const std::uint32_t seg = cstart[c];
-    const std::uint32_t n = cstart[c + 1] - seg;
-    // z extent of the cluster (processor.cpp:648-655), reduced while labelling (cluster.cu)
-    {
-        float zlo = unord_f32(d.zmin_u[o + c]), zhi = unord_f32(d.zmax_u[o + c]);
-        const std::uint32_t zz = d.zzero[o + c];
-        if (zz != 0xffffffffu && (zz & 1u) != 0u)
-        {
-            // a zero extent carries the sign of the cluster's first zero-height point (see accumulate_cluster_stats)
-            zlo = zlo == 0.0f ? -0.0f : zlo;
-            zhi = zhi == 0.0f ? -0.0f : zhi;
-        }
-        d.zminmax[o + c] = make_float2(zlo, zhi);
-    }
-    const std::uint32_t fin = d.hfin[o + c];
-    if (fin & kFinDone)
-    {
-        continue;
-    }
-    const bool use_b = in_b != ((fin & kFinOther) != 0u);
-    const uint4* cur = (use_b ? d.hsB : d.hsA) + o + seg;
-    std::uint32_t* gst = d.hstack + static_cast<std::size_t>(f) * 2 * d.cap + seg + c; // n + 1 entries
-    if (n < 3)
-    {
-        // identity order = obstacle-cloud order (polygonizer.cpp:36-41)
-        std::uint32_t a = (n > 0) ? cur[0].w : 0u, b = (n > 1) ? cur[1].w : 0u;
-        if (n == 2 && b < a)
-        {
-            const std::uint32_t t = a;
-            a = b;
-            b = t;
-        }
-        if (n > 0)
-        {
-            gst[0] = a;
-        }
-        if (n > 1)
-        {
-            gst[1] = b;
-        }
-        d.hcnt[o + c] = n;
-        continue;
-    }
-    const std::uint32_t m = fin & 0x3fffffffu;
-    std::uint16_t st[kFinalMax + 2];
-    const std::uint32_t hc = monotone_chain([&](std::uint32_t i) { return elem_pt(cur[i]); }, m, st);
-    for (std::uint32_t t = 0; t < hc; ++t)
-    {
-        gst[t] = cur[st[t]].w;
-    }
-    d.hcnt[o + c] = hc;
-    }
 }
 
 __global__ void __launch_bounds__(128) k_hull_gather(Dev d)
@@ -1546,31 +1009,12 @@ void launch_hull_sort(Ctx* c, std::uint32_t nf)
     }
 }
 
-#ifndef LPL_HULL_V1
-#define LPL_HULL_V1 0 // 1: the frame-wide merge sort + global-memory thinning passes of round 1
-#endif
-
 void launch_hulls(Ctx* c, std::uint32_t nf)
 {
     Dev& d = c->d;
     cudaStream_t s = c->stream;
     k_hull_octagon<<<dim3(4, nf), 128, 0, s>>>(d);
     mark(c, "hull_octagon");
-#if LPL_HULL_V1
-    // d.lab (RECM labels of the segmenter) is free by now: it holds the recorded verdicts
-    launch_compact_recorded(c, "hull_keep", nf, d.tiles, d.n_o, d.tile_cnt, d.n_h, d.lab, HullKeepPred{d}, HullKeepEmit{d});
-    k_excl_scan<<<nf, 1024, 0, s>>>(d.hseg_cnt, d.cap, d.cstart, d.cap + 1, d.cap, d.n_clusters, nullptr);
-    mark(c, "hull_seg_scan");
-    launch_hull_sort(c, nf);
-    constexpr std::size_t big_smem = static_cast<std::size_t>(2) * kBigThreads * kLaneStack * (sizeof(float2) + sizeof(std::uint32_t));
-    cudaFuncSetAttribute(k_hull_thin_big, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(big_smem));
-    k_hull_thin_big<<<dim3(per_frame_ctas(kBigCtasPerFrame, nf, 64), nf), kBigThreads, big_smem, s>>>(d);
-    mark(c, "hull_thin_big");
-    k_hull_thin<<<dim3(per_frame_ctas(kHullCtasPerFrame, nf, 1024), nf), kHullThreads, 0, s>>>(d);
-    mark(c, "hull_thin");
-    k_hull_final<<<dim3(per_frame_ctas(16, nf, 256), nf), 64, 0, s>>>(d);
-    mark(c, "hull_final");
-#else
     // d.lab (RECM labels of the segmenter) is free by now: it holds the recorded verdicts
     launch_compact_recorded(c, "hull_keep", nf, d.tiles, d.n_o, d.tile_cnt, d.n_h, d.lab, HullKeepPred{d}, HullKeepEmit{d});
     k_excl_scan<<<nf, 1024, 0, s>>>(d.hseg_cnt, d.cap, d.cstart, d.cap + 1, d.cap, d.n_clusters, nullptr);
@@ -1585,7 +1029,6 @@ void launch_hulls(Ctx* c, std::uint32_t nf)
     mark(c, "hull_chunks");
     k_hull_join<<<dim3(per_frame_ctas(4, nf, 64), nf), kJoinWarps * 32, smem_join, s>>>(d);
     mark(c, "hull_join");
-#endif
     k_excl_scan<<<nf, 1024, 0, s>>>(d.hcnt, d.cap, d.hull_off, d.cap + 1, d.cap, d.n_clusters, d.n_hull);
     mark(c, "hull_off_scan");
     k_hull_gather<<<dim3(64, nf), 128, 0, s>>>(d);

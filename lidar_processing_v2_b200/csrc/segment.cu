@@ -7,7 +7,7 @@
 //                                    k_ransac_count
 //   image scatter      :291-318   -> k_seg_image (64-bit atomicMin keys), k_seg_px
 //   JCP                :481-638   -> k_seg_dilate_tma (5x5 stencil on range-image tiles staged by TMA),
-//                                    queue compaction, k_jcp_pre, k_jcp_resolve
+//                                    queue compaction, k_jcp_pre, k_jcp_rows
 //   populateLabels     :640-669   -> k_seg_labels_out
 //
 // Ordered semantics on an unordered machine: the reference iterates polar cells in index order
@@ -20,11 +20,10 @@
 // Everything else (heights per cell, inlier counts, labels) is order independent.
 //
 // JCP is a Gauss-Seidel sweep in raster order. A queued pixel only depends on queued pixels
-// that precede it in raster order and lie within the kernel distance, so the sweep is replayed
-// as a data-flow relaxation: weights and mask sources are computed for all queued pixels in
-// parallel (k_jcp_pre); then one CTA per frame walks the queue as *runs* of horizontally adjacent
-// queued pixels, one thread per run, left to right, waiting on a 2-bit state plane in shared
-// memory only for the earlier queued pixels of the rows above (k_jcp_resolve).
+// that precede it in raster order and lie within the kernel distance: weights and mask sources are
+// computed for all queued pixels in parallel (k_jcp_pre); then one CTA per frame sweeps the image
+// row by row, one thread per queued pixel, the in-row recurrence solved by a scan over finite maps
+// (k_jcp_rows).
 // The reference leaves out-of-image kernel slots untouched, so border pixels inherit those
 // slots from the previously popped pixel (hazard H2); k_jcp_pre reproduces that by
 // locating the most recent earlier queued pixel for which the slot was inside the image.
@@ -1296,282 +1295,15 @@ __global__ void __launch_bounds__(128) k_jcp_pre(Dev d, SegParams sp)
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// JCP relaxation: one CTA per frame, 2-bit state plane in shared memory
-// (0 unknown / empty / undecided, 1 ground, 2 obstacle, 3 queued and not yet relaxed).
-//
-// The raster-order sweep of the reference only couples a queued pixel to *earlier* queued pixels
-// of its 5x5 neighbourhood. Queued pixels that touch horizontally form runs; one thread walks a
-// run left to right (the in-row predecessors are its own results) and spin-waits on the state
-// plane for the queued pixels of the two rows above, so a row follows the row above it with a lag
-// of two pixels instead of a barrier per pixel. Runs are handed out in raster order
-// (thread t takes runs t, t + T, ...): the raster-first unfinished run never waits on anything
-// unfinished and its owner is working on it, so the sweep cannot deadlock.
-// Weights are entry-major (96 B per pixel) and loaded one pixel ahead of the vote.
-// ------------------------------------------------------------------------------------------
+// 2-bit state plane of a frame in shared memory: 0 unknown / empty / undecided, 1 ground, 2 obstacle, 3 queued and not yet swept
 __device__ __forceinline__ std::uint32_t plane_get(const volatile std::uint32_t* plane, std::uint32_t p)
 {
     return (plane[p >> 4] >> ((p & 15u) * 2u)) & 3u;
 }
 
-#ifndef LPL_JCP_ROWS
-#define LPL_JCP_ROWS 1 // 1: row-synchronous sweep (k_jcp_rows, below); 0: data-flow sweep with polling (k_jcp_resolve)
-#endif
-#if !LPL_JCP_ROWS
-#ifndef LPL_JCP_THREADS
-#define LPL_JCP_THREADS 1024 // measured per 154-frame batch: 256 -> 1.6 ms, 512 -> 0.85 ms, 1024 -> 0.53 ms
-#endif
-constexpr int kJcpThreads = LPL_JCP_THREADS;
-#ifndef LPL_JCP_AHEAD
-#define LPL_JCP_AHEAD 4
-#endif
-constexpr int kJcpAhead = LPL_JCP_AHEAD; // queue entries whose weights / masks are in flight ahead of the vote
-constexpr int kJcpRunTable = 4096; // runs whose (first queue entry, first pixel) are staged in shared memory
-constexpr std::uint32_t kJcpSpinLimit = 1u << 22;
-
-struct RunHeadPred
-{
-    const std::uint32_t* queue;
-    std::uint32_t qcap, W;
-    __device__ bool operator()(std::uint32_t f, std::uint32_t k) const
-    {
-        const std::uint32_t* q = queue + static_cast<std::size_t>(f) * qcap;
-        const std::uint32_t p = q[k];
-        return k == 0 || (p % W) == 0 || q[k - 1] + 1u != p;
-    }
-};
-
-struct RunHeadEmit
-{
-    std::uint32_t* runs;
-    std::uint32_t qcap;
-    __device__ void operator()(std::uint32_t f, std::uint32_t k, std::uint32_t pos) const
-    {
-        runs[static_cast<std::size_t>(f) * qcap + pos] = k;
-    }
-};
-
-__global__ void __launch_bounds__(1024) k_jcp_resolve(Dev d, SegParams sp)
-{
-    extern __shared__ std::uint32_t plane[]; // npx / 16 words
-    const std::uint32_t f = blockIdx.x;
-    const std::size_t po = static_cast<std::size_t>(f) * sp.npx;
-    std::uint8_t* code = d.code + po;
-    const std::uint32_t nwords = (sp.npx + 15) / 16;
-    for (std::uint32_t wi = threadIdx.x; wi < nwords; wi += blockDim.x)
-    {
-        std::uint32_t v = 0;
-        // 16 pixels = 16 bytes of code
-        const uint4 raw = *reinterpret_cast<const uint4*>(code + static_cast<std::size_t>(wi) * 16);
-        const std::uint32_t r[4] = {raw.x, raw.y, raw.z, raw.w};
-#pragma unroll
-        for (int b = 0; b < 16; ++b)
-        {
-            const std::uint32_t c = (r[b >> 2] >> ((b & 3) * 8)) & 0xfu;
-            v |= (c & 3u) << (2 * b); // EMPTY 0, GROUND 1, OBSTACLE 2, QUEUED 3
-        }
-        plane[wi] = v;
-    }
-    const std::uint32_t nq = min(d.n_queue[f], d.qcap);
-    const std::uint32_t nruns = min(d.n_runs[f], d.qcap);
-    const std::uint32_t* queue = d.queue + static_cast<std::size_t>(f) * d.qcap;
-    const std::uint32_t* runs = d.runs + static_cast<std::size_t>(f) * d.qcap;
-    const unsigned long long* mkv = d.mk + static_cast<std::size_t>(f) * d.qcap;
-    const float* wn = d.wn + static_cast<std::size_t>(f) * 24 * d.qcap;
-    const std::uint32_t* sref = d.stale_ref + static_cast<std::size_t>(f) * d.nborder_cap * 12;
-    const std::uint32_t W = static_cast<std::uint32_t>(sp.W);
-    const std::uint32_t lane = lane_id();
-    const int slot = static_cast<int>(min(lane, 23u)); // lanes 24..31 shadow slot 23 and contribute nothing
-    // kernel offsets of slots 0..11 (segmenter.cpp:527-530); slots >= 12 are never dynamic
-    const int dh = slot < 5 ? -2 : (slot < 10 ? -1 : 0);
-    const int dw = slot < 5 ? slot - 2 : (slot < 10 ? slot - 7 : slot - 12);
-    std::uint32_t spins = 0;
-    __shared__ std::uint32_t s_next_run;
-    __shared__ __align__(16) float s_vote[32][48];
-    __shared__ std::uint32_t s_runk[kJcpRunTable], s_runp[kJcpRunTable];
-    const std::uint32_t nrt = min(nruns, static_cast<std::uint32_t>(kJcpRunTable));
-    for (std::uint32_t t = threadIdx.x; t < nrt; t += blockDim.x)
-    {
-        const std::uint32_t kk = runs[t];
-        s_runk[t] = kk;
-        s_runp[t] = queue[kk];
-    }
-    if (threadIdx.x == 0)
-    {
-        s_next_run = 0;
-    }
-    __syncthreads();
-    // One warp per run, lane i = kernel slot i: the 96-byte weight row of a pixel is one coalesced
-    // load, every lane resolves its own slot (waiting on the plane only for a queued pixel that
-    // another warp has not fired yet), and the vote is the reference's ordered sum over the 24
-    // slots. Runs are handed out in raster order to whichever warp is free: the raster-first
-    // unfinished run is always being worked on and waits on nothing unfinished, so the sweep
-    // cannot deadlock. Handing out one run at a time keeps the raster front wide (claiming several
-    // runs per warp serialises rows that could advance together); what a run start costs in
-    // memory latency is cut by keeping the run table (first queue entry, first pixel) of the frame
-    // in shared memory and the per-pixel loads kJcpAhead pixels ahead of the vote.
-    while (true)
-    {
-        std::uint32_t r = 0;
-        if (lane == 0)
-        {
-            r = atomicAdd(&s_next_run, 1u);
-        }
-        r = __shfl_sync(0xffffffffu, r, 0);
-        if (r >= nruns)
-        {
-            break;
-        }
-        std::uint32_t k, kend, p;
-        if (r + 1u < nrt)
-        {
-            k = s_runk[r];
-            kend = s_runk[r + 1u];
-            p = s_runp[r];
-        }
-        else
-        {
-            // beyond the staged table (or its last entry): lanes 0 / 1 fetch the bounds together
-            std::uint32_t kk = nq;
-            if (lane < 2u && r + lane < nruns)
-            {
-                kk = runs[r + lane];
-            }
-            k = __shfl_sync(0xffffffffu, kk, 0);
-            kend = __shfl_sync(0xffffffffu, kk, 1); // first entry of the next run
-            p = queue[k];
-        }
-        const int h = static_cast<int>(p / W);
-        int wv = static_cast<int>(p % W);
-        // register ring: the weight rows / masks of the next kJcpAhead pixels of the run are in
-        // flight while the current pixel waits on its neighbours and votes
-        unsigned long long mq[kJcpAhead];
-        float wq[kJcpAhead];
-#pragma unroll
-        for (int j = 0; j < kJcpAhead; ++j)
-        {
-            mq[j] = 0;
-            wq[j] = 0.f;
-            if (k + j < kend)
-            {
-                mq[j] = mkv[k + j];
-                wq[j] = lane < 24u ? wn[static_cast<std::size_t>(k + j) * 24 + lane] : 0.f;
-            }
-        }
-        for (; k < kend; ++k, ++p, ++wv)
-        {
-            const unsigned long long m = mq[0];
-            const float wt = wq[0];
-#pragma unroll
-            for (int j = 0; j + 1 < kJcpAhead; ++j)
-            {
-                mq[j] = mq[j + 1];
-                wq[j] = wq[j + 1];
-            }
-            if (k + kJcpAhead < kend)
-            {
-                mq[kJcpAhead - 1] = mkv[k + kJcpAhead];
-                wq[kJcpAhead - 1] = lane < 24u ? wn[static_cast<std::size_t>(k + kJcpAhead) * 24 + lane] : 0.f;
-            }
-            std::uint32_t out = 0;
-            if ((m >> 48) & 1ULL)
-            {
-                std::uint32_t mi = lane < 24u ? static_cast<std::uint32_t>((m >> (2 * slot)) & 3ULL) : 0u;
-                std::uint32_t ref = 0;
-                if (mi == 3u)
-                {
-                    // final state of an earlier queued pixel
-                    const int hh = h + dh, ww = wv + dw;
-                    if (hh >= 0 && ww >= 0 && ww < sp.W)
-                    {
-                        ref = static_cast<std::uint32_t>(hh * sp.W + ww);
-                    }
-                    else
-                    {
-                        // inherited (stale) slot of a border pixel: explicit pixel reference
-                        const std::uint32_t brow = static_cast<std::uint32_t>(m >> 49);
-                        ref = sref[static_cast<std::size_t>(brow - 1) * 12 + slot];
-                    }
-                    mi = plane_get(plane, ref);
-                }
-                // warp-uniform wait: lanes still looking at an unfinished pixel poll again after a
-                // back-off that grows with the wait (a spinning warp must not take issue slots
-                // from the warp it waits for)
-                std::uint32_t pending = __ballot_sync(0xffffffffu, mi == 3u);
-#ifndef LPL_JCP_BACKOFF0
-#define LPL_JCP_BACKOFF0 32
-#endif
-#ifndef LPL_JCP_BACKOFF1
-#define LPL_JCP_BACKOFF1 512
-#endif
-                std::uint32_t backoff = LPL_JCP_BACKOFF0;
-                while (pending != 0u)
-                {
-                    if (++spins > kJcpSpinLimit)
-                    {
-                        if (lane == 0)
-                        {
-                            atomicOr(&d.status[f], ST_JCP_STALL);
-                        }
-                        mi = mi == 3u ? 0u : mi;
-                        break;
-                    }
-                    __nanosleep(backoff);
-                    backoff = min(backoff * 2u, static_cast<std::uint32_t>(LPL_JCP_BACKOFF1));
-                    if (mi == 3u)
-                    {
-                        mi = plane_get(plane, ref);
-                    }
-                    pending = __ballot_sync(0xffffffffu, mi == 3u);
-                }
-                // x + 0.0f == x: adding a zero for the slots of the other classes keeps the sums
-                // bit-identical to the reference's conditional accumulation in slot order. The 24
-                // (ground, obstacle) contributions go through shared memory (one store per lane);
-                // lane 0 sums the ground row and lane 1 the obstacle row, in slot order.
-                float* vg = s_vote[threadIdx.x >> 5];
-                float* vo = vg + 24;
-                if (lane < 24u)
-                {
-                    vg[lane] = mi == 1u ? wt : 0.f;
-                    vo[lane] = mi == 2u ? wt : 0.f;
-                }
-                __syncwarp();
-                float acc = 0.f;
-                if (lane < 2u)
-                {
-                    const float4* row = reinterpret_cast<const float4*>(vg + 24u * lane);
-#pragma unroll
-                    for (int i = 0; i < 6; ++i)
-                    {
-                        const float4 a = row[i];
-                        acc += a.x;
-                        acc += a.y;
-                        acc += a.z;
-                        acc += a.w;
-                    }
-                }
-                const float wo = __shfl_sync(0xffffffffu, acc, 1);
-                out = (wo > acc) ? 2u : 1u; // meaningful on lane 0 (acc = ground sum)
-            }
-            if (lane == 0)
-            {
-                // 3 -> out: clear the bits that differ
-                atomicAnd(&plane[p >> 4], ~((3u ^ out) << ((p & 15u) * 2u)));
-                code[p] = (out == 0u) ? PX_UNDECIDED : static_cast<std::uint8_t>(out);
-            }
-            __syncwarp(); // orders lane 0's plane update before the next pixel's look-ups
-        }
-    }
-    if (threadIdx.x == 0)
-    {
-        d.jcp_rounds[f] = nruns;
-    }
-}
-
-#endif // !LPL_JCP_ROWS
 
 // ------------------------------------------------------------------------------------------
-// Row-synchronous JCP sweep, one THREAD per queued pixel (LPL_JCP_ROWS = 1).
+// Row-synchronous JCP sweep, one THREAD per queued pixel.
 // Within an image row a queued pixel depends only on its two left neighbours (kernel slots 10 / 11):
 // every other dynamic slot - in-image slots of the two rows above and the inherited (stale) slots of
 // border pixels, which always refer to rows above - is final once the rows are swept top to bottom.
@@ -1589,7 +1321,6 @@ __global__ void __launch_bounds__(1024) k_jcp_resolve(Dev d, SegParams sp)
 // the end of the row; the queue records of the next chunk are loaded into registers before the
 // current chunk is voted on. Reference: the queue loop of Segmenter::JCP (segmenter.cpp:535-637).
 // ------------------------------------------------------------------------------------------
-#if LPL_JCP_ROWS
 #ifndef LPL_JCP_ROWS_THREADS
 #define LPL_JCP_ROWS_THREADS 256 // measured per 154-frame batch: 128 -> 0.43 ms, 256 -> 0.33, 384 -> 0.37, 512 -> 0.42
 #endif
@@ -1907,7 +1638,6 @@ __global__ void __launch_bounds__(kJcpRowsThreads, LPL_JCP_ROWS_MINB) k_jcp_rows
     }
 }
 
-#endif // LPL_JCP_ROWS
 
 // populateLabels (segmenter.cpp:640-669): only pixel winners receive a label; optional BGR image
 __global__ void __launch_bounds__(256) k_seg_labels_out(Dev d, SegParams sp, int want_image)
@@ -2020,16 +1750,11 @@ void launch_segment(Ctx* c, std::uint32_t nf, bool want_image)
     launch_compact(c, "jcp_queue", nf, d.ptiles, nullptr, static_cast<std::uint32_t>(sp.npx), d.tile_cnt, d.n_queue,
                    QueuePred{d.code, static_cast<std::uint32_t>(sp.npx)},
                    QueueEmit{d.queue, d.status, d.qcap});
-#if !LPL_JCP_ROWS
-    launch_compact(c, "jcp_runs", nf, (d.qcap + kTile - 1) / kTile, d.n_queue, 0u, d.tile_cnt, d.n_runs,
-                   RunHeadPred{d.queue, d.qcap, static_cast<std::uint32_t>(sp.W)}, RunHeadEmit{d.runs, d.qcap});
-#endif
     k_jcp_pre<<<dim3(std::min<std::uint32_t>((d.qcap + 127) / 128, per_frame_ctas(128, nf, 1024)), nf), 128, 0, s>>>(d, sp);
     mark(c, "jcp_pre");
     // state plane (32 KB for 64 x 2048, 64 KB for 128-beam images): above the 48 KB default for the
     // larger images, opt in (up to 227 KB per CTA on sm_100a)
     const std::size_t plane_bytes = static_cast<std::size_t>((sp.npx + 15) / 16) * 4;
-#if LPL_JCP_ROWS
     const std::size_t rows_bytes = plane_bytes + sizeof(std::uint32_t) * (sp.H + 1);
     if (cudaFuncSetAttribute(k_jcp_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(rows_bytes)) != cudaSuccess)
     {
@@ -2041,11 +1766,6 @@ void launch_segment(Ctx* c, std::uint32_t nf, bool want_image)
     }
     k_jcp_rows<<<nf, kJcpRowsThreads, rows_bytes, s>>>(d, sp);
     mark(c, "jcp_rows");
-#else
-    cudaFuncSetAttribute(k_jcp_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(plane_bytes));
-    k_jcp_resolve<<<nf, kJcpThreads, plane_bytes, s>>>(d, sp);
-    mark(c, "jcp_resolve");
-#endif
     k_seg_labels_out<<<dim3((sp.npx + 255) / 256, nf), 256, 0, s>>>(d, sp, want_image ? 1 : 0);
     mark(c, "seg_labels_out");
 }
