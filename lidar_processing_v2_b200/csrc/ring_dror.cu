@@ -447,7 +447,10 @@ constexpr int kDrorQueryCtas = LPL_DROR_CTAS; // per frame; groups stride over t
 #endif
 constexpr int kDrorUnroll = LPL_DROR_UNROLL; // points per lane and step
 
-__global__ void __launch_bounds__(kDrorQueryWarps * 32) k_dror_query(Dev d, DrorParams prm)
+#ifndef LPL_DROR_MINB
+#define LPL_DROR_MINB 6 // measured per 154-frame batch: 1 (64 registers, 50 % occupancy) -> 0.288 ms, 6 (40 registers) -> 0.266, 8 -> 0.273
+#endif
+__global__ void __launch_bounds__(kDrorQueryWarps * 32, LPL_DROR_MINB) k_dror_query(Dev d, DrorParams prm)
 {
     const std::uint32_t f = blockIdx.y;
     const std::uint32_t nu = d.n_unres[f];
