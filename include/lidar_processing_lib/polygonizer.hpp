@@ -125,8 +125,8 @@ class Polygonizer final
 
     /// Indices of the convex hull vertices, counter-clockwise from the lexicographically smallest
     /// point, collinear points dropped; fewer than three points are returned as they are.
-    /// Coordinates must be float-representable (they are when they come from a PCL cloud, as in
-    /// processor.cpp:645-646); otherwise std::invalid_argument.
+    /// Coordinates that are float-representable (they are when they come from a PCL cloud, as in
+    /// processor.cpp:645-646) take the batched fast path; any other doubles are sorted and swept in fp64 on the device.
     template <typename PointT>
     void convexHull(const std::vector<PointT>& points, std::vector<std::int32_t>& indices)
     {

@@ -1566,8 +1566,8 @@ int lpl_convex_hull(lpl_ctx* ctx, const void* xy, std::size_t stride, std::uint3
     {
         return LPL_OK;
     }
-    // The device path sorts on float keys: every PCL-derived PointXY is float-representable
-    // (processor.cpp:645-646). Anything else is rejected rather than silently rounded.
+    // The fast device path sorts on float keys: every PCL-derived PointXY is float-representable
+    // (processor.cpp:645-646). Anything else takes the fp64 path below - never a silent rounding.
     std::vector<float> pts;
     std::vector<std::int32_t> lab;
     try
@@ -1579,18 +1579,48 @@ int lpl_convex_hull(lpl_ctx* ctx, const void* xy, std::size_t stride, std::uint3
     {
         return fail(ctx, LPL_ERR_CAPACITY, "convexHull: host staging allocation failed"); // nothing unwinds through the C ABI
     }
-    for (std::uint32_t i = 0; i < n; ++i)
+    bool float_exact = true;
+    for (std::uint32_t i = 0; i < n && float_exact; ++i)
     {
         double v[2];
         std::memcpy(v, static_cast<const char*>(xy) + i * stride, 16);
         const float fx = static_cast<float>(v[0]), fy = static_cast<float>(v[1]);
-        if (static_cast<double>(fx) != v[0] || static_cast<double>(fy) != v[1])
-        {
-            return fail(ctx, LPL_ERR_INVALID_ARGUMENT,
-                        "convexHull: coordinates are not float-representable (device path sorts float keys)");
-        }
+        float_exact = static_cast<double>(fx) == v[0] && static_cast<double>(fy) == v[1];
         pts[4 * i] = fx;
         pts[4 * i + 1] = fy;
+    }
+    if (!float_exact)
+    {
+        Ctx& c = ctx->c;
+        Dev& d = c.d;
+        if (n > d.cap)
+        {
+            return fail(ctx, LPL_ERR_CAPACITY, "more points than the context was created for");
+        }
+        LPL_TRY(cudaSetDevice(c.device));
+        if (ensure_stage(ctx, static_cast<std::size_t>(n) * 16) != 0)
+        {
+            return LPL_ERR_CUDA;
+        }
+        LPL_TRY(cudaStreamSynchronize(c.stream));
+        pack(c.h_stage, 16, xy, stride, 16, n);
+        auto* dxy = reinterpret_cast<double2*>(d.hsA); // idle outside a pipeline run
+        LPL_TRY(cudaMemcpyAsync(dxy, c.h_stage, static_cast<std::size_t>(n) * 16, cudaMemcpyHostToDevice, c.stream));
+        launch_hull_f64(&c, dxy, n, d.hstack, d.hull_off, d.hull_idx, d.n_hull); // order: n entries, sweep stack: n + 1
+        LPL_TRY(cudaMemcpyAsync(count_out, d.n_hull, 4, cudaMemcpyDeviceToHost, c.stream));
+        LPL_TRY(cudaStreamSynchronize(c.stream));
+        if (*count_out > n)
+        {
+            *count_out = 0;
+            return fail(ctx, LPL_ERR_CUDA, "internal error: more hull vertices than points");
+        }
+        if (*count_out != 0)
+        {
+            LPL_TRY(cudaMemcpyAsync(indices_out, d.hull_idx, sizeof(std::uint32_t) * *count_out, cudaMemcpyDeviceToHost, c.stream));
+            LPL_TRY(cudaStreamSynchronize(c.stream));
+        }
+        LPL_TRY(cudaGetLastError());
+        return LPL_OK;
     }
     std::uint32_t off[2] = {0, 0};
     const int rc = lpl_cluster_hulls(ctx, pts.data(), 16, lab.data(), n, 1, off, indices_out, nullptr, nullptr);

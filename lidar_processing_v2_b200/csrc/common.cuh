@@ -611,6 +611,8 @@ void launch_radius(Ctx* c, const float4* pts, std::uint32_t n, const float4* que
                    float radius_all, std::uint32_t cap, float* out_d, std::uint32_t* out_i, std::uint32_t* count);
 void launch_vehicle_match(Ctx* c, const double2* xy, const std::uint32_t* off, std::uint32_t K, const double2* zmm,
                           const std::uint32_t* sizes, const ObbBox* boxes, std::int32_t* cls, double* area_out);
+void launch_hull_f64(Ctx* c, const double2* xy, std::uint32_t n, std::uint32_t* order, std::uint32_t* st, std::uint32_t* out_idx,
+                     std::uint32_t* out_cnt);
 void launch_pack_results(Ctx* c, std::uint32_t nf, std::uint32_t planes, unsigned char* staging, std::size_t staging_bytes);
 void launch_unpack_cloud2(Ctx* c, std::uint32_t nf, const unsigned char* raw, std::size_t raw_stride, const void* desc);
 void launch_boxes_hulls(Ctx* c, const double2* xy, const std::uint32_t* off, std::uint32_t K, int method, ObbBox* out);

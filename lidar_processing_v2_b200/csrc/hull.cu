@@ -1009,6 +1009,106 @@ void launch_hull_sort(Ctx* c, std::uint32_t nf)
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Polygonizer::convexHull on coordinates that are NOT float-representable (arbitrary doubles; nothing on the node's
+// path produces them - its points come from PCL floats - but the reference's signature accepts them): one CTA sorts
+// the point indices by (x, y, index) on the doubles themselves (bitonic network in global memory) and one thread
+// runs the reference's sweep. A fallback for generality, not a fast path.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool f64_less(const double2* xy, std::uint32_t a, std::uint32_t b)
+{
+    const double2 p = xy[a], q = xy[b];
+    if (p.x != q.x)
+    {
+        return p.x < q.x;
+    }
+    if (p.y != q.y)
+    {
+        return p.y < q.y;
+    }
+    return a < b;
+}
+
+__global__ void __launch_bounds__(1024)
+    k_hull_f64(const double2* __restrict__ xy, std::uint32_t n, std::uint32_t* __restrict__ order, std::uint32_t* __restrict__ st,
+               std::uint32_t* __restrict__ out_idx, std::uint32_t* __restrict__ out_cnt)
+{
+    for (std::uint32_t t = threadIdx.x; t < n; t += blockDim.x)
+    {
+        order[t] = t;
+    }
+    __syncthreads();
+    for (std::uint32_t k = 2; (k >> 1) < n; k <<= 1)
+    {
+        for (std::uint32_t t = threadIdx.x; t < n; t += blockDim.x)
+        {
+            const std::uint32_t u = t ^ (k - 1u);
+            if (u > t && u < n)
+            {
+                const std::uint32_t a = order[t], b = order[u];
+                if (f64_less(xy, b, a))
+                {
+                    order[t] = b;
+                    order[u] = a;
+                }
+            }
+        }
+        __syncthreads();
+        for (std::uint32_t j = k >> 2; j > 0; j >>= 1)
+        {
+            for (std::uint32_t t = threadIdx.x; t < n; t += blockDim.x)
+            {
+                const std::uint32_t u = t ^ j;
+                if (u > t && u < n)
+                {
+                    const std::uint32_t a = order[t], b = order[u];
+                    if (f64_less(xy, b, a))
+                    {
+                        order[t] = b;
+                        order[u] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x == 0)
+    {
+        std::uint32_t hc = n;
+        if (n < 3u)
+        {
+            for (std::uint32_t t = 0; t < n; ++t)
+            {
+                out_idx[t] = t; // polygonizer.cpp:36-41: fewer than three points are returned as they are
+            }
+        }
+        else
+        {
+            hc = monotone_chain(
+                [&](std::uint32_t i) {
+                    const double2 v = xy[order[i]];
+                    P2 p;
+                    p.x = v.x;
+                    p.y = v.y;
+                    return p;
+                },
+                n, st);
+            for (std::uint32_t t = 0; t < hc; ++t)
+            {
+                out_idx[t] = order[st[t]];
+            }
+        }
+        *out_cnt = hc;
+    }
+}
+
+void launch_hull_f64(Ctx* c, const double2* xy, std::uint32_t n, std::uint32_t* order, std::uint32_t* st, std::uint32_t* out_idx,
+                     std::uint32_t* out_cnt)
+{
+    k_hull_f64<<<1, 1024, 0, c->stream>>>(xy, n, order, st, out_idx, out_cnt);
+    mark(c, "hull_f64");
+}
+
 void launch_hulls(Ctx* c, std::uint32_t nf)
 {
     Dev& d = c->d;

@@ -820,13 +820,16 @@ __global__ void __launch_bounds__(256) k_ransac_count(Dev d, SegParams sp)
         {
             continue; // skipped draw (uniform branch)
         }
-        std::uint32_t hits = 0;
+        // per-thread count over its candidates, then one warp reduction per plane (redux.sync) instead of a ballot +
+        // popc per candidate
+        std::uint32_t mine = 0;
 #pragma unroll
         for (int j = 0; j < kRansacPer; ++j)
         {
             const float od = fabsf((q.x * p[j].x) + (q.y * p[j].y) + (q.z * p[j].z) - q.w);
-            hits += __popc(__ballot_sync(0xffffffffu, live[j] && od < sp.thr));
+            mine += (live[j] && od < sp.thr) ? 1u : 0u;
         }
+        const std::uint32_t hits = __reduce_add_sync(0xffffffffu, mine);
         if (static_cast<int>(lane) == (it & 31))
         {
             if (it < 32)

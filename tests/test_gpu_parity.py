@@ -118,8 +118,12 @@ def test_convex_hull_entry_point(ctx, port):
         # indices may differ between equal points (unstable sort), coordinates may not
         assert np.abs(xy[got] - xy[exp]).max() <= 1e-5 if got.size else True
         assert np.array_equal(xy[got], xy[exp])
-    with pytest.raises(lpl.LplError):
-        ctx.convex_hull(np.array([[0.1, 0.2], [1.0, 1.0], [0.0, 3.0]]))  # not float-representable
+    # coordinates that are not float-representable take the fp64 path (the reference accepts any doubles)
+    for xy in (np.array([[0.1, 0.2], [1.0, 1.0], [0.0, 3.0]]), rng.normal(0, 3, (4000, 2)), rng.uniform(-1, 1, (2, 2)),
+               np.c_[np.linspace(0, 1, 300) ** 3, np.linspace(0, 1, 300)]):
+        got = ctx.convex_hull(xy)
+        exp = port.convex_hull(xy)
+        assert got.shape == exp.shape and np.array_equal(xy[got], xy[exp])
 
 
 def _boxes_equal(got, exp, exact=True):
