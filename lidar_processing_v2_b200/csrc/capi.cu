@@ -88,8 +88,6 @@ void carve(Dev& d, Carver& cv, int npx, int ncell_cap, std::uint32_t** mt_raw)
     cv.take(d.grid_mask, B * (kDrorCells / 32));
     cv.take(d.grid_pts, B * cap);
     cv.take(d.unres, B * cap);
-    cv.take(d.n_unres, B);
-    cv.take(d.n_v, B);
     cv.take(d.cell, B * cap);
     cv.take(d.px, B * cap);
     cv.take(d.slot, B * cap);
@@ -104,7 +102,6 @@ void carve(Dev& d, Carver& cv, int npx, int ncell_cap, std::uint32_t** mt_raw)
     cv.take(d.lab, B * cap);
     cv.take(d.n_cand, B);
     cv.take(d.cpts, B * cap);
-    cv.take(d.n_cpts, B);
     cv.take(d.pairs, B * kRansacIters * 2);
     cv.take(d.planes, B * kRansacIters);
     cv.take(d.inliers, B * kRansacIters);
@@ -118,15 +115,12 @@ void carve(Dev& d, Carver& cv, int npx, int ncell_cap, std::uint32_t** mt_raw)
     cv.take(d.wn, B * 24 * q);
     cv.take(d.mk, B * q);
     cv.take(d.stale_ref, B * d.nborder_cap * 12);
-    cv.take(d.n_border, B);
     cv.take(d.jcp_rounds, B);
     cv.take(d.labels_out, B * cap);
     cv.take(d.bgr, B * npx * 3);
     cv.take(d.pts_o, B * cap);
     cv.take(d.idx_o, B * cap);
-    cv.take(d.n_o, B);
     cv.take(d.sph, B * cap);
-    cv.take(d.sph_max, B * 4);
     cv.take(d.hkey, B * h);
     cv.take(d.hparent, B * h);
     cv.take(d.hmin, B * h);
@@ -137,9 +131,7 @@ void carve(Dev& d, Carver& cv, int npx, int ncell_cap, std::uint32_t** mt_raw)
     cv.take(d.edges, B * cap * 13);
     cv.take(d.vslot, B * cap);
     cv.take(d.vlist, B * cap);
-    cv.take(d.n_vox, B);
     cv.take(d.clabel, B * cap);
-    cv.take(d.n_clusters, B);
     cv.take(d.ccount, B * cap);
     cv.take(d.cstart, B * (cap + 1));
     cv.take(d.hsA, B * cap);
@@ -151,7 +143,6 @@ void carve(Dev& d, Carver& cv, int npx, int ncell_cap, std::uint32_t** mt_raw)
     cv.take(d.hull_idx, B * cap);
     cv.take(d.hull_xy, B * cap);
     cv.take(d.zminmax, B * cap);
-    cv.take(d.n_hull, B);
     cv.take(d.zmin_u, B * cap);
     cv.take(d.zmax_u, B * cap);
     cv.take(d.zzero, B * cap);
@@ -169,7 +160,20 @@ void carve(Dev& d, Carver& cv, int npx, int ncell_cap, std::uint32_t** mt_raw)
     cv.take(d.raw_desc, B * 32);
     const std::size_t tl = std::max<std::size_t>(d.tiles, d.ptiles);
     cv.take(d.tile_cnt, B * tl);
+    // counter block (one memset per run): every array below is zero at the start of a run
     cv.take(d.status, B);
+    const std::size_t ctr_first = cv.off - B * sizeof(std::uint32_t);
+    cv.take(d.n_v, B);
+    cv.take(d.n_o, B);
+    cv.take(d.n_clusters, B);
+    cv.take(d.n_hull, B);
+    cv.take(d.n_unres, B);
+    cv.take(d.n_cpts, B);
+    cv.take(d.n_border, B);
+    cv.take(d.n_vox, B);
+    cv.take(d.sph_max, B * 4);
+    d.ctr_begin = cv.base != nullptr ? reinterpret_cast<unsigned char*>(cv.base) + ctr_first : nullptr;
+    d.ctr_bytes = cv.off - ctr_first;
     cv.take(*mt_raw, kMtRaws);
 }
 
@@ -899,16 +903,18 @@ static int enqueue_stages(lpl_ctx* ctx, std::uint32_t nf, std::uint32_t stages)
         c.prof_n = 0;
         LPL_TRY(cudaEventRecord(c.prof_ev[0], c.stream));
     }
-    LPL_TRY(cudaMemsetAsync(d.status, 0, sizeof(std::uint32_t) * nf, c.stream));
+    // status words and every per-frame counter in one memset (counts of stages that are not selected read as zero)
+    LPL_TRY(cudaMemsetAsync(d.ctr_begin, 0, d.ctr_bytes, c.stream));
+    struct Cleared
+    {
+        Ctx& c;
+        explicit Cleared(Ctx& cc) : c(cc) { c.counters_cleared = true; }
+        ~Cleared() { c.counters_cleared = false; }
+    } cleared(c);
     if ((stages & LPL_STAGE_DROR) == 0)
     {
         LPL_TRY(cudaMemsetAsync(d.noise, 0, static_cast<std::size_t>(d.cap) * nf, c.stream));
     }
-    // counts of stages that are not selected read as zero
-    LPL_TRY(cudaMemsetAsync(d.n_v, 0, sizeof(std::uint32_t) * nf, c.stream));
-    LPL_TRY(cudaMemsetAsync(d.n_o, 0, sizeof(std::uint32_t) * nf, c.stream));
-    LPL_TRY(cudaMemsetAsync(d.n_clusters, 0, sizeof(std::uint32_t) * nf, c.stream));
-    LPL_TRY(cudaMemsetAsync(d.n_hull, 0, sizeof(std::uint32_t) * nf, c.stream));
     const bool ring_stage = (stages & LPL_STAGE_RING) != 0;
     const bool fused_front = ring_stage && (stages & LPL_STAGE_DROR) != 0; // one read of the cloud for both stages
     if (ring_stage && !fused_front)
@@ -1712,25 +1718,22 @@ int lpl_pipeline_download_packed(lpl_ctx* ctx, std::uint32_t nf, lpl_packed_resu
         return fail(ctx, LPL_ERR_CAPACITY, "context too small for a packed download");
     }
     launch_pack_results(&c, nf, r->planes, staging, staging_bytes);
-    // phase 1: counts, status and the layout header
+    // phase 1: the layout header with the per-frame counts behind it (one small transfer) and the status words
     std::uint32_t* cn = r->counts;
-    LPL_TRY(cudaMemcpyAsync(cn + 0 * nf, d.n_in, 4 * nf, k, c.stream));
-    LPL_TRY(cudaMemcpyAsync(cn + 1 * nf, d.n_v, 4 * nf, k, c.stream));
-    LPL_TRY(cudaMemcpyAsync(cn + 2 * nf, d.n_o, 4 * nf, k, c.stream));
-    LPL_TRY(cudaMemcpyAsync(cn + 3 * nf, d.n_clusters, 4 * nf, k, c.stream));
-    LPL_TRY(cudaMemcpyAsync(cn + 4 * nf, d.n_hull, 4 * nf, k, c.stream));
-    if (ensure_stage(ctx, sizeof(std::uint32_t) * 2 * d.B + sizeof(PackHeader)) != 0)
+    const std::size_t hc_bytes = sizeof(PackHeader) + static_cast<std::size_t>(5) * nf * sizeof(std::uint32_t);
+    if (ensure_stage(ctx, sizeof(std::uint32_t) * 2 * d.B + hc_bytes) != 0)
     {
         return LPL_ERR_CUDA;
     }
-    // (the upload staging at the front of h_stage is consumed by then: the copies above are behind it in the stream)
+    // (the upload staging at the front of h_stage is consumed by then: this copy is behind it in the stream)
     auto* h_hdr = reinterpret_cast<PackHeader*>(static_cast<char*>(c.h_stage) + sizeof(std::uint32_t) * 2 * d.B);
-    LPL_TRY(cudaMemcpyAsync(h_hdr, staging, sizeof(PackHeader), k, c.stream));
+    LPL_TRY(cudaMemcpyAsync(h_hdr, staging, hc_bytes, k, c.stream));
     const int rc_status = check_status(ctx, nf); // flagged frames do not hold back the others (see download_batch)
     if (rc_status != 0 && rc_status != LPL_ERR_CAPACITY)
     {
         return rc_status;
     }
+    std::memcpy(cn, reinterpret_cast<const char*>(h_hdr) + sizeof(PackHeader), static_cast<std::size_t>(5) * nf * sizeof(std::uint32_t));
     for (int p = 0; p < LPL_PLANE_COUNT; ++p)
     {
         r->offset[p] = (r->planes & (1u << p)) ? static_cast<std::size_t>(h_hdr->offset[p]) : static_cast<std::size_t>(-1);

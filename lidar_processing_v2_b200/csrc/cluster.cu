@@ -383,9 +383,13 @@ __global__ void __launch_bounds__(kUfThreads) k_clu_union_sm(Dev d)
     }
     __syncthreads();
     const std::uint32_t* edges = d.edges + o * kFwd;
+    // the next edge word is in flight while the current one is united (a single frame has one CTA walking ~220k edge
+    // words: without this every trip waits for its own load)
+    std::uint32_t u_next = threadIdx.x < nv * kFwd ? edges[threadIdx.x] : 0xffffffffu;
     for (std::uint32_t e = threadIdx.x; e < nv * kFwd; e += kUfThreads)
     {
-        const std::uint32_t u = edges[e];
+        const std::uint32_t u = u_next;
+        u_next = e + kUfThreads < nv * kFwd ? edges[e + kUfThreads] : 0xffffffffu;
         if (u == 0xffffffffu)
         {
             continue;
@@ -598,8 +602,11 @@ void launch_cluster(Ctx* c, std::uint32_t nf)
 {
     Dev& d = c->d;
     cudaStream_t s = c->stream;
-    cudaMemsetAsync(d.sph_max, 0, sizeof(std::uint32_t) * 4 * nf, s);
-    cudaMemsetAsync(d.n_vox, 0, sizeof(std::uint32_t) * nf, s);
+    if (!c->counters_cleared)
+    {
+        cudaMemsetAsync(d.sph_max, 0, sizeof(std::uint32_t) * 4 * nf, s);
+        cudaMemsetAsync(d.n_vox, 0, sizeof(std::uint32_t) * nf, s);
+    }
     if (!c->hash_clean)
     {
         // first use of this context: all frames' tables; afterwards k_clu_clean keeps them clean

@@ -103,9 +103,15 @@ __host__ __device__ inline int pack_count_of(int p)
     return p < 3 ? 0 : p < 5 ? 1 : p == 5 ? 2 : p < 8 ? 4 : 3;
 }
 
+// staging layout: [PackHeader][counts: 5 x nf u32][pad to 8][frame_off: 5 x nf u64][pad to 16][payload]
+inline std::size_t pack_frame_off_start(std::uint32_t nf)
+{
+    return (sizeof(PackHeader) + static_cast<std::size_t>(5) * nf * sizeof(std::uint32_t) + 7u) & ~static_cast<std::size_t>(7);
+}
+
 inline std::size_t pack_payload_start(std::uint32_t nf)
 {
-    return (sizeof(PackHeader) + static_cast<std::size_t>(5) * nf * sizeof(unsigned long long) + 15u) & ~static_cast<std::size_t>(15);
+    return (pack_frame_off_start(nf) + static_cast<std::size_t>(5) * nf * sizeof(unsigned long long) + 15u) & ~static_cast<std::size_t>(15);
 }
 
 // All device buffers of a context. Pointers are to the start of frame 0; frame f lives at
@@ -220,6 +226,10 @@ struct Dev
     std::uint32_t* tile_cnt;  // [B][max(tiles, ptiles)]
     std::uint32_t* status;    // [B]  error bits raised by kernels
     const std::uint32_t* mt_raw; // [kMtRaws]
+    // the per-frame counters every run starts from zero (status, n_v, n_o, n_clusters, n_hull, n_unres, n_cpts, n_border,
+    // n_vox, sph_max) lie next to each other in the slab: lpl_pipeline_run clears them with ONE memset
+    unsigned char* ctr_begin;
+    std::size_t ctr_bytes;
 };
 
 enum : std::uint32_t
@@ -637,6 +647,7 @@ struct Ctx
     alignas(64) CUtensorMap code_map{}; // TMA descriptor of the pixel-code planes (segment.cu: k_seg_dilate_tma)
     bool have_code_map = false;
     bool launch_failed = false;      // a launcher could not set up its kernel (message in err)
+    bool counters_cleared = false;   // inside lpl_pipeline_run: the launchers' own counter memsets are already done
     // per-kernel CUDA-event profile of the last lpl_pipeline_run (lpl_profile_*)
     static constexpr int kProfMax = 96;
     bool prof_on = false;

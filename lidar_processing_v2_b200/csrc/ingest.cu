@@ -123,8 +123,17 @@ void launch_spread_packed(Ctx* c, std::uint32_t nf, const void* packed, const st
 // ------------------------------------------------------------------------------------------
 // header (PackHeader) written by k_pack_layout at the start of the staging area
 __global__ void __launch_bounds__(1024) k_pack_layout(Dev d, std::uint32_t nf, std::uint32_t planes, PackHeader* hdr,
-                                                      unsigned long long* frame_off, unsigned long long capacity)
+                                                      std::uint32_t* counts, unsigned long long* frame_off, unsigned long long capacity)
 {
+    // the per-frame counts, gathered behind the header so that one small transfer brings header + counts to the host
+    for (std::uint32_t f = threadIdx.x; f < nf; f += blockDim.x)
+    {
+        counts[0 * nf + f] = d.n_in[f];
+        counts[1 * nf + f] = d.n_v[f];
+        counts[2 * nf + f] = d.n_o[f];
+        counts[3 * nf + f] = d.n_clusters[f];
+        counts[4 * nf + f] = d.n_hull[f];
+    }
     // five running sums over the frames: n, n_o, K + 1, K, Hv  (one block; nf is a few thousand at most)
     __shared__ unsigned long long tot[5];
     __shared__ std::uint32_t sh[33];
@@ -172,18 +181,14 @@ __global__ void __launch_bounds__(1024) k_pack_layout(Dev d, std::uint32_t nf, s
     }
 }
 
-// one launch per plane: element e of frame f -> dst[offset + (frame_off[f] + e) * elem]; units of 4 bytes when
-// the element is a multiple of 4 bytes, bytes otherwise
+// element e of frame f of a plane -> dst[offset + (frame_off[f] + e) * elem]; units of 4 bytes when the element is a
+// multiple of 4 bytes, half-words / bytes otherwise
 template <int kUnit>
-__global__ void __launch_bounds__(256)
-    k_pack_plane(const unsigned char* __restrict__ src, std::size_t src_frame_bytes, std::uint32_t elem,
-                 const std::uint32_t* __restrict__ count, std::uint32_t count_add, const unsigned long long* __restrict__ frame_off,
-                 const PackHeader* __restrict__ hdr, int plane, unsigned char* __restrict__ staging)
+__device__ __forceinline__ void pack_plane(const unsigned char* __restrict__ src, std::size_t src_frame_bytes, std::uint32_t elem,
+                                           const std::uint32_t* __restrict__ count, std::uint32_t count_add,
+                                           const unsigned long long* __restrict__ frame_off, const PackHeader* __restrict__ hdr,
+                                           int plane, unsigned char* __restrict__ staging)
 {
-    if (hdr->fits == 0u)
-    {
-        return;
-    }
     const std::uint32_t f = blockIdx.y;
     const std::size_t bytes = static_cast<std::size_t>(count[f] + count_add) * elem;
     const unsigned char* s = src + static_cast<std::size_t>(f) * src_frame_bytes;
@@ -221,15 +226,51 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// all selected planes in ONE launch: blockIdx.z = plane (a launch per plane cost more than the copies of a small batch)
+struct PackPlanes
+{
+    const unsigned char* src[kPackPlanes];
+    std::size_t frame_bytes[kPackPlanes];
+    const std::uint32_t* cnt[kPackPlanes];
+    std::uint32_t add[kPackPlanes];
+    std::uint32_t selected; // plane bits
+};
+
+__global__ void __launch_bounds__(256)
+    k_pack_planes(PackPlanes pp, std::uint32_t nf, const unsigned long long* __restrict__ frame_off,
+                  const PackHeader* __restrict__ hdr, unsigned char* __restrict__ staging)
+{
+    const int p = static_cast<int>(blockIdx.z);
+    if ((pp.selected & (1u << p)) == 0u || hdr->fits == 0u)
+    {
+        return;
+    }
+    const std::uint32_t elem = pack_elem(p);
+    const unsigned long long* fo = frame_off + static_cast<std::size_t>(pack_count_of(p)) * nf;
+    if (elem % 4u == 0u)
+    {
+        pack_plane<4>(pp.src[p], pp.frame_bytes[p], elem, pp.cnt[p], pp.add[p], fo, hdr, p, staging);
+    }
+    else if (elem == 2u)
+    {
+        pack_plane<2>(pp.src[p], pp.frame_bytes[p], elem, pp.cnt[p], pp.add[p], fo, hdr, p, staging);
+    }
+    else
+    {
+        pack_plane<1>(pp.src[p], pp.frame_bytes[p], elem, pp.cnt[p], pp.add[p], fo, hdr, p, staging);
+    }
+}
+
 void launch_pack_results(Ctx* c, std::uint32_t nf, std::uint32_t planes, unsigned char* staging, std::size_t staging_bytes)
 {
     Dev& d = c->d;
-    // staging: [PackHeader][frame_off: 5 x nf u64][payload ...]
+    // staging: [PackHeader][counts: 5 x nf u32][frame_off: 5 x nf u64][payload ...] (common.cuh: pack_payload_start)
     PackHeader* hdr = reinterpret_cast<PackHeader*>(staging);
-    unsigned long long* frame_off = reinterpret_cast<unsigned long long*>(staging + sizeof(PackHeader));
+    std::uint32_t* counts = reinterpret_cast<std::uint32_t*>(staging + sizeof(PackHeader));
+    unsigned long long* frame_off = reinterpret_cast<unsigned long long*>(staging + pack_frame_off_start(nf));
     const std::size_t head = pack_payload_start(nf);
     unsigned char* payload = staging + head;
-    k_pack_layout<<<1, 1024, 0, c->stream>>>(d, nf, planes, hdr, frame_off, staging_bytes > head ? staging_bytes - head : 0);
+    k_pack_layout<<<1, 1024, 0, c->stream>>>(d, nf, planes, hdr, counts, frame_off, staging_bytes > head ? staging_bytes - head : 0);
     mark(c, "pack_layout");
     const std::size_t cap = d.cap;
     struct Src
@@ -245,32 +286,18 @@ void launch_pack_results(Ctx* c, std::uint32_t nf, std::uint32_t planes, unsigne
         {d.hull_idx, cap, d.n_hull, 0},  {d.hull_xy, cap, d.n_hull, 0},    {d.zminmax, cap, d.n_clusters, 0},
         {d.boxes, cap, d.n_clusters, 0},
     };
+    PackPlanes pp{};
+    pp.selected = planes;
     for (int p = 0; p < kPackPlanes; ++p)
     {
-        if ((planes & (1u << p)) == 0u)
-        {
-            continue;
-        }
-        const std::uint32_t elem = pack_elem(p);
-        const unsigned long long* fo = frame_off + static_cast<std::size_t>(pack_count_of(p)) * nf;
-        const auto* sp = static_cast<const unsigned char*>(src[p].p);
-        const std::size_t fb = src[p].frame_elems * elem;
-        // CTAs per frame: enough to cover a typical frame in two or three trips
-        const dim3 grid(p < 3 ? 128 : (p < 5 ? 64 : 8), nf);
-        if (elem % 4u == 0u)
-        {
-            k_pack_plane<4><<<grid, 256, 0, c->stream>>>(sp, fb, elem, src[p].cnt, src[p].add, fo, hdr, p, payload);
-        }
-        else if (elem == 2u)
-        {
-            k_pack_plane<2><<<grid, 256, 0, c->stream>>>(sp, fb, elem, src[p].cnt, src[p].add, fo, hdr, p, payload);
-        }
-        else
-        {
-            k_pack_plane<1><<<grid, 256, 0, c->stream>>>(sp, fb, elem, src[p].cnt, src[p].add, fo, hdr, p, payload);
-        }
-        mark(c, "pack_plane");
+        pp.src[p] = static_cast<const unsigned char*>(src[p].p);
+        pp.frame_bytes[p] = src[p].frame_elems * pack_elem(p);
+        pp.cnt[p] = src[p].cnt;
+        pp.add[p] = src[p].add;
     }
+    // CTAs per frame: enough to cover a typical frame's point planes in a few trips (the small planes finish at once)
+    k_pack_planes<<<dim3(per_frame_ctas(48, nf, 128), nf, kPackPlanes), 256, 0, c->stream>>>(pp, nf, frame_off, hdr, payload);
+    mark(c, "pack_planes");
 }
 
 void launch_unpack_cloud2(Ctx* c, std::uint32_t nf, const unsigned char* raw, std::size_t raw_stride, const void* desc)

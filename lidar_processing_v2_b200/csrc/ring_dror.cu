@@ -702,7 +702,10 @@ __global__ void __launch_bounds__(1024) k_dror_grid_scan(Dev d)
 void launch_dror(Ctx* c, std::uint32_t nf, bool with_ring)
 {
     Dev& d = c->d;
-    cudaMemsetAsync(d.n_unres, 0, sizeof(std::uint32_t) * nf, c->stream);
+    if (!c->counters_cleared)
+    {
+        cudaMemsetAsync(d.n_unres, 0, sizeof(std::uint32_t) * nf, c->stream);
+    }
     const dim3 grid((d.cap + 255) / 256, nf);
     if (with_ring)
     {

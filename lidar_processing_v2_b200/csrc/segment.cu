@@ -1698,11 +1698,14 @@ void launch_segment(Ctx* c, std::uint32_t nf, bool want_image)
     // per-batch resets
     cudaMemsetAsync(d.cell_cnt, 0, sizeof(std::uint32_t) * sp.ncell * nf, s);
     cudaMemsetAsync(d.ccnt, 0, sizeof(std::uint32_t) * sp.ncell * nf, s);
-    cudaMemsetAsync(d.n_cpts, 0, sizeof(std::uint32_t) * nf, s);
     cudaMemsetAsync(d.key, 0xff, sizeof(unsigned long long) * sp.npx * nf, s);
-    cudaMemsetAsync(d.n_v, 0, sizeof(std::uint32_t) * nf, s);
     cudaMemsetAsync(d.labels_out, 0, static_cast<std::size_t>(d.cap) * nf, s);
-    cudaMemsetAsync(d.n_border, 0, sizeof(std::uint32_t) * nf, s);
+    if (!c->counters_cleared)
+    {
+        cudaMemsetAsync(d.n_cpts, 0, sizeof(std::uint32_t) * nf, s);
+        cudaMemsetAsync(d.n_v, 0, sizeof(std::uint32_t) * nf, s);
+        cudaMemsetAsync(d.n_border, 0, sizeof(std::uint32_t) * nf, s);
+    }
 
     const dim3 gpts((d.cap + 255) / 256, nf);
     k_seg_bin<<<gpts, 256, 0, s>>>(d, sp);
