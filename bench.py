@@ -230,11 +230,12 @@ def algorithmic_bytes(name: str, s: dict) -> float:
         "dror_mark": 20 * U + 16384 * F, "dror_grid_count": 16 * N, "dror_grid_scan": 8 * 131072 * F,
         "dror_grid_scatter": 16 * N + 16 * U * 8,
         "dror_query": 20 * U + U,
-        "seg_bin": (16 + 2 + 1) * N + 12 * N, "seg_cell_scan": 8 * CELLS, "seg_scatter": (16 + 8) * N + 8 * NB,
+        # seg_scatter also issues the range-image keys (one 8-byte atomicMin per binned point)
+        "seg_bin": (16 + 2 + 1) * N + 12 * N, "seg_cell_scan": 8 * CELLS, "seg_scatter": (16 + 12) * N + (8 + 8) * NB,
         "seg_cell": 8 * NB + 8 * CELLS, "seg_elev": 12 * CELLS,
-        "seg_label": (16 + 4) * N + 4 * NB + 1 * N + 16 * C,
+        "seg_label": (16 + 4) * N + 16 * C,
         "ransac_draw": 1024 * F + 8 * CELLS, "ransac_plane": 120 * 64 * F, "ransac_count": 16 * C,
-        "seg_image": (16 + 4 + 4 + 1) * N + 1 * NB + 8 * NB, "seg_px": 8 * PX + 17 * PX,
+        "seg_px": 8 * PX + 20 * min(PX, NB) + 17 * PX,
         "seg_dilate": 2 * PX, "jcp_queue": 2 * PX + 4 * Q,
         # the 5 x 5 neighbourhoods of queued pixels overlap: ~4 distinct pixel records (16 B point + 1 B code) are
         # fetched per queued pixel (ncu dram__bytes: profiles/traffic.json), 104 B of weights + masks are written

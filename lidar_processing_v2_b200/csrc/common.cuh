@@ -152,7 +152,7 @@ struct Dev
     std::uint32_t* ccnt;      // [B][ncell] RANSAC candidates per cell, then their exclusive prefix in (slice, bin) order
     float* cell_zmin;         // [B][ncell]
     float* elev;              // [B][ncell]
-    std::uint8_t* lab;        // [B][cap]  RECM label per input point; bit 7 = RANSAC candidate
+    std::uint8_t* lab;        // [B][cap]  recorded verdicts of the two-pass compactions (ring wrap flags, cluster representatives, hull filter)
     std::uint32_t* n_cand;    // [B]
     float4* cpts;             // [B][cap]  dense unordered copy of the candidate points (inlier count)
     std::uint32_t* n_cpts;    // [B]

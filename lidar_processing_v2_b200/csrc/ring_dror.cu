@@ -218,7 +218,9 @@ __global__ void __launch_bounds__(256)
             }
         }
         unresolved = cnt < prm.min_neighbours;
-        d.noise[static_cast<std::size_t>(f) * d.cap + i] = 0; // provisional: VALID
+        // VALID, or 2 = "query of the grid search" (k_dror_grid_scatter tags the point's grid copy with it and
+        // k_dror_query writes the final verdict over it)
+        d.noise[static_cast<std::size_t>(f) * d.cap + i] = unresolved ? 2 : 0;
     }
     // warp-aggregated append
     const std::uint32_t m = __ballot_sync(0xffffffffu, unresolved);
@@ -330,6 +332,16 @@ __global__ void __launch_bounds__(256) k_dror_mark(Dev d, DrorParams prm)
     const std::uint32_t f = blockIdx.y;
     const std::uint32_t nu = d.n_unres[f];
     std::uint32_t* mask = d.grid_mask + static_cast<std::size_t>(f) * (kDrorCells / 32);
+    if (nu >= d.n_in[f] / 4u)
+    {
+        // an unorganised cloud leaves (nearly) every point to the grid search: their boxes cover every occupied
+        // cell anyway, and millions of atomicOr on 16 KB of bitmap would cost more than the whole search
+        for (std::uint32_t w = blockIdx.x * 256u + threadIdx.x; w < static_cast<std::uint32_t>(kDrorCells / 32); w += gridDim.x * 256u)
+        {
+            mask[w] = nu != 0u ? 0xffffffffu : 0u;
+        }
+        return;
+    }
     for (std::uint32_t u = blockIdx.x * 256u + threadIdx.x; u < nu; u += gridDim.x * 256u)
     {
         const std::uint32_t i = d.unres[static_cast<std::size_t>(f) * d.cap + u];
@@ -410,6 +422,9 @@ __global__ void __launch_bounds__(256) k_dror_grid_scatter(Dev d)
         if (cell >= 0)
         {
             p = d.pts_in[static_cast<std::size_t>(f) * d.cap + i];
+            // w: the point's index, bit 31 set when the point is itself a query (k_dror_query walks the grid copy)
+            const std::uint32_t q = d.noise[static_cast<std::size_t>(f) * d.cap + i] == 2 ? 0x80000000u : 0u;
+            p.w = __uint_as_float(i | q);
         }
     }
     const std::uint32_t peers = __match_any_sync(0xffffffffu, cell);
@@ -433,6 +448,13 @@ __global__ void __launch_bounds__(256) k_dror_grid_scatter(Dev d)
 // touch. Cells of one grid row are contiguous in grid_pts, so each row is one range. Rows are
 // short far from the sensor (where most unresolved points live), so a query is served by a group
 // of 8 lanes: four queries per warp in flight, 32 points per step, early exit at min_neighbours.
+//
+// The queries are taken in GRID order, not in list order: every unresolved point lies in a marked cell (its own
+// search box covers it), so its grid copy exists and carries the query flag. A warp reads 32 consecutive grid
+// points (one coalesced load: coordinates and index in one record, where the list order paid two dependent loads),
+// ballots the flagged ones and serves them four at a time. Consecutive grid points share a cell, so the queries a
+// warp - and its CTA - has in flight scan the same rows: the row bounds and the candidates are L1 hits instead of
+// one DRAM sector per query and row (the unorganised 2 M-point cloud, where every point is a query: 1.82 -> 0.x ms).
 constexpr int kDrorQueryWarps = 8;
 #ifndef LPL_DROR_GROUP
 #define LPL_DROR_GROUP 8
@@ -441,11 +463,15 @@ constexpr int kDrorGroup = LPL_DROR_GROUP; // lanes per query
 #ifndef LPL_DROR_CTAS
 #define LPL_DROR_CTAS 24
 #endif
-constexpr int kDrorQueryCtas = LPL_DROR_CTAS; // per frame; groups stride over the unresolved list
+constexpr int kDrorQueryCtas = LPL_DROR_CTAS; // per frame; warps stride over the chunks of 32 grid points
 #ifndef LPL_DROR_UNROLL
 #define LPL_DROR_UNROLL 4
 #endif
 constexpr int kDrorUnroll = LPL_DROR_UNROLL; // points per lane and step
+#ifndef LPL_DROR_DENSE
+#define LPL_DROR_DENSE 8
+#endif
+constexpr int kDrorDense = LPL_DROR_DENSE; // queries among 32 consecutive grid points from which the chunk-mate pass pays
 
 #ifndef LPL_DROR_MINB
 #define LPL_DROR_MINB 6 // measured per 154-frame batch: 1 (64 registers, 50 % occupancy) -> 0.288 ms, 6 (40 registers) -> 0.266, 8 -> 0.273
@@ -453,78 +479,146 @@ constexpr int kDrorUnroll = LPL_DROR_UNROLL; // points per lane and step
 __global__ void __launch_bounds__(kDrorQueryWarps * 32, LPL_DROR_MINB) k_dror_query(Dev d, DrorParams prm)
 {
     const std::uint32_t f = blockIdx.y;
-    const std::uint32_t nu = d.n_unres[f];
+    if (d.n_unres[f] == 0u)
+    {
+        return;
+    }
     const std::uint32_t lane = lane_id();
     const std::uint32_t gl = lane & (kDrorGroup - 1);                 // lane inside the group
+    const std::uint32_t grp = lane / kDrorGroup;                      // group inside the warp
     const std::uint32_t gmask = ((1u << kDrorGroup) - 1u) << (lane & ~(kDrorGroup - 1u));
+    constexpr std::uint32_t kGroups = 32 / kDrorGroup;
     const std::uint32_t* start = d.grid_start + static_cast<std::size_t>(f) * (kDrorCells + 1);
     const float4* gp = d.grid_pts + static_cast<std::size_t>(f) * d.cap;
-    const std::uint32_t groups_per_cta = kDrorQueryWarps * 32 / kDrorGroup;
-    for (std::uint32_t u = blockIdx.x * groups_per_cta + threadIdx.x / kDrorGroup; u < nu;
-         u += gridDim.x * groups_per_cta)
+    const std::uint32_t total = start[kDrorCells];
+    for (std::uint32_t c0 = (blockIdx.x * kDrorQueryWarps + (threadIdx.x >> 5)) * 32u; c0 < total;
+         c0 += gridDim.x * kDrorQueryWarps * 32u)
     {
-        const std::uint32_t i = d.unres[static_cast<std::size_t>(f) * d.cap + u];
-        const float4 p = d.pts_in[static_cast<std::size_t>(f) * d.cap + i];
-        const float r_sqr = dror_radius_sqr(p.x, p.y, prm);
-        std::uint32_t cnt = 0;
-        for (int level = 1; level >= 0 && cnt < prm.min_neighbours; --level)
+        float4 mine = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f); // beyond the end: NaN, within() of nothing
+        if (c0 + lane < total)
         {
-        const DrorBox bx = dror_box(p, r_sqr, level);
-        for (int cy0 = bx.y0; cy0 <= bx.y1 && cnt < prm.min_neighbours; cy0 += kDrorGroup)
-        {
-            // lane gl fetches the bounds of row cy0 + gl
-            const int cy = cy0 + static_cast<int>(gl);
-            std::uint32_t ra = 0, rb = 0;
-            if (cy <= bx.y1)
-            {
-                ra = start[bx.base + cy * kDrorGrid + bx.x0];
-                rb = start[bx.base + cy * kDrorGrid + bx.x1 + 1];
-            }
-            const int rows = min(kDrorGroup, bx.y1 - cy0 + 1);
-            // rows are visited outwards from the query's own row: a query that does have its
-            // min_neighbours finds them in the nearest cells and leaves early
-            const float yq = (level == 1) ? p.y * kDrorFineScale : p.y;
-            const int own = min(max(dror_cell_coord(yq) - cy0, 0), rows - 1);
-            for (int t = 0; t < 2 * rows && cnt < prm.min_neighbours; ++t)
-            {
-                const int r = own + (((t & 1) != 0) ? (t + 1) / 2 : -(t / 2));
-                if (r < 0 || r >= rows)
-                {
-                    continue;
-                }
-                const std::uint32_t a = __shfl_sync(gmask, ra, r, kDrorGroup);
-                const std::uint32_t b = __shfl_sync(gmask, rb, r, kDrorGroup);
-                // kDrorUnroll independent loads per lane and step: a dense row (hundreds of points in
-                // a near-range cell) is latency bound, a sparse one only ever issues the first load
-                for (std::uint32_t k0 = a; k0 < b && cnt < prm.min_neighbours; k0 += kDrorGroup * kDrorUnroll)
-                {
-                    float4 q[kDrorUnroll];
-#pragma unroll
-                    for (int j = 0; j < kDrorUnroll; ++j)
-                    {
-                        const std::uint32_t k = k0 + j * kDrorGroup + gl;
-                        q[j] = k < b ? gp[k] : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                    std::uint32_t hits = 0;
-#pragma unroll
-                    for (int j = 0; j < kDrorUnroll; ++j)
-                    {
-                        const std::uint32_t k = k0 + j * kDrorGroup + gl;
-                        hits += (k < b && dror_within(p, q[j], r_sqr)) ? 1u : 0u;
-                    }
-#pragma unroll
-                    for (int sft = kDrorGroup / 2; sft > 0; sft >>= 1)
-                    {
-                        hits += __shfl_xor_sync(gmask, hits, sft, kDrorGroup);
-                    }
-                    cnt += hits;
-                }
-            }
+            mine = gp[c0 + lane];
         }
-        }
-        if (gl == 0 && cnt < prm.min_neighbours)
+        const bool is_query = (__float_as_uint(mine.w) >> 31) != 0u;
+        std::uint32_t pending = __ballot_sync(0xffffffffu, is_query);
+        if (__popc(pending) >= kDrorDense)
         {
-            d.noise[static_cast<std::size_t>(f) * d.cap + i] = 1;
+            // Dense chunk (an unorganised cloud: every point is a query): the other 31 grid points of the chunk lie in
+            // the same or the next cells, and every point is a legitimate candidate (the distance test is exact, the
+            // search box only prunes) - so each lane first counts among its chunk mates, nearest in grid order first,
+            // entirely out of registers. Most queries of a dense region have their min_neighbours here; the verdict is
+            // final for them (the count can only grow), the others take the exhaustive search below from zero.
+            const float my_r = dror_radius_sqr(mine.x, mine.y, prm);
+            std::uint32_t cnt = dror_within(mine, mine, my_r) ? 1u : 0u;
+            bool open = is_query && cnt < prm.min_neighbours;
+#pragma unroll 1
+            for (int j0 = 1; j0 < 32 && __any_sync(0xffffffffu, open); j0 += 4)
+            {
+#pragma unroll
+                for (int j = j0; j < j0 + 4 && j < 32; ++j)
+                {
+                    const int sft = ((j & 1) != 0) ? (j + 1) / 2 : -(j / 2);
+                    const int src = (static_cast<int>(lane) + sft) & 31;
+                    float4 o;
+                    o.x = __shfl_sync(0xffffffffu, mine.x, src);
+                    o.y = __shfl_sync(0xffffffffu, mine.y, src);
+                    o.z = __shfl_sync(0xffffffffu, mine.z, src);
+                    cnt += dror_within(mine, o, my_r) ? 1u : 0u;
+                }
+                open = open && cnt < prm.min_neighbours;
+            }
+            if (is_query && !open)
+            {
+                d.noise[static_cast<std::size_t>(f) * d.cap + (__float_as_uint(mine.w) & 0x7fffffffu)] = 0;
+            }
+            pending = __ballot_sync(0xffffffffu, open);
+        }
+        while (pending != 0u)
+        {
+            // group g takes the g-th pending query
+            std::uint32_t pm = pending;
+#pragma unroll
+            for (std::uint32_t j = 0; j + 1 < kGroups; ++j)
+            {
+                pm = j < grp ? (pm & (pm - 1u)) : pm;
+            }
+            const bool active = pm != 0u;
+            const int src = active ? __ffs(pm) - 1 : 0;
+            float4 p;
+            p.x = __shfl_sync(0xffffffffu, mine.x, src);
+            p.y = __shfl_sync(0xffffffffu, mine.y, src);
+            p.z = __shfl_sync(0xffffffffu, mine.z, src);
+            const std::uint32_t i = __float_as_uint(__shfl_sync(0xffffffffu, mine.w, src)) & 0x7fffffffu;
+#pragma unroll
+            for (std::uint32_t j = 0; j < kGroups; ++j)
+            {
+                pending &= pending - 1u;
+            }
+            if (!active)
+            {
+                continue; // (whole groups only: the group-wide shuffles below stay converged)
+            }
+            const float r_sqr = dror_radius_sqr(p.x, p.y, prm);
+            std::uint32_t cnt = 0;
+            for (int level = 1; level >= 0 && cnt < prm.min_neighbours; --level)
+            {
+                const DrorBox bx = dror_box(p, r_sqr, level);
+                for (int cy0 = bx.y0; cy0 <= bx.y1 && cnt < prm.min_neighbours; cy0 += kDrorGroup)
+                {
+                    // lane gl fetches the bounds of row cy0 + gl
+                    const int cy = cy0 + static_cast<int>(gl);
+                    std::uint32_t ra = 0, rb = 0;
+                    if (cy <= bx.y1)
+                    {
+                        ra = start[bx.base + cy * kDrorGrid + bx.x0];
+                        rb = start[bx.base + cy * kDrorGrid + bx.x1 + 1];
+                    }
+                    const int rows = min(kDrorGroup, bx.y1 - cy0 + 1);
+                    // rows are visited outwards from the query's own row: a query that does have its
+                    // min_neighbours finds them in the nearest cells and leaves early
+                    const float yq = (level == 1) ? p.y * kDrorFineScale : p.y;
+                    const int own = min(max(dror_cell_coord(yq) - cy0, 0), rows - 1);
+                    for (int t = 0; t < 2 * rows && cnt < prm.min_neighbours; ++t)
+                    {
+                        const int r = own + (((t & 1) != 0) ? (t + 1) / 2 : -(t / 2));
+                        if (r < 0 || r >= rows)
+                        {
+                            continue;
+                        }
+                        const std::uint32_t a = __shfl_sync(gmask, ra, r, kDrorGroup);
+                        const std::uint32_t b = __shfl_sync(gmask, rb, r, kDrorGroup);
+                        // kDrorUnroll independent loads per lane and step: a dense row (hundreds of points in
+                        // a near-range cell) is latency bound, a sparse one only ever issues the first load
+                        for (std::uint32_t k0 = a; k0 < b && cnt < prm.min_neighbours; k0 += kDrorGroup * kDrorUnroll)
+                        {
+                            float4 q[kDrorUnroll];
+#pragma unroll
+                            for (int j = 0; j < kDrorUnroll; ++j)
+                            {
+                                const std::uint32_t k = k0 + j * kDrorGroup + gl;
+                                q[j] = k < b ? gp[k] : make_float4(0.f, 0.f, 0.f, 0.f);
+                            }
+                            std::uint32_t hits = 0;
+#pragma unroll
+                            for (int j = 0; j < kDrorUnroll; ++j)
+                            {
+                                const std::uint32_t k = k0 + j * kDrorGroup + gl;
+                                hits += (k < b && dror_within(p, q[j], r_sqr)) ? 1u : 0u;
+                            }
+#pragma unroll
+                            for (int sft = kDrorGroup / 2; sft > 0; sft >>= 1)
+                            {
+                                hits += __shfl_xor_sync(gmask, hits, sft, kDrorGroup);
+                            }
+                            cnt += hits;
+                        }
+                    }
+                }
+            }
+            if (gl == 0)
+            {
+                d.noise[static_cast<std::size_t>(f) * d.cap + i] = cnt < prm.min_neighbours ? 1 : 0;
+            }
         }
     }
 }

@@ -5,7 +5,7 @@
 //   RECM               :206-283   -> k_seg_cell (robust per-cell minimum), k_seg_elev, k_seg_label
 //   RANSAC             :321-479   -> candidate flags (k_seg_label), k_ransac_draw, k_ransac_plane,
 //                                    k_ransac_count
-//   image scatter      :291-318   -> k_seg_image (64-bit atomicMin keys), k_seg_px
+//   image scatter      :291-318   -> 64-bit atomicMin keys (issued by k_seg_scatter), k_seg_px (winner decode + its label)
 //   JCP                :481-638   -> k_seg_dilate_tma (5x5 stencil on range-image tiles staged by TMA),
 //                                    queue compaction, k_jcp_pre, k_jcp_rows
 //   populateLabels     :640-669   -> k_seg_labels_out
@@ -16,7 +16,7 @@
 // rank in (cell, cloud) order - a prefix over per-cell candidate counts plus a radix select over
 // the point indices of one cell resolves a rank (k_ransac_draw / k_ransac_plane); (ii) the range image keeps the
 // first point among equal depths - equal depth^2 implies the same radial bin, so the 64-bit key
-// (depth^2, azimuth slice, point index) under atomicMin picks the reference's winner (k_seg_image).
+// (depth^2, azimuth slice, point index) under atomicMin picks the reference's winner (k_seg_scatter / k_seg_px).
 // Everything else (heights per cell, inlier counts, labels) is order independent.
 //
 // JCP is a Gauss-Seidel sweep in raster order. A queued pixel only depends on queued pixels
@@ -158,11 +158,19 @@ __global__ void __launch_bounds__(256) k_seg_scatter(Dev d, SegParams sp)
     // independent loads first (cell, slot, z), then the one dependent look-up (the cell's start)
     const std::int32_t cell = d.cell[o + i];
     const std::uint32_t slot = d.slot[o + i];
-    const float z = d.pts_in[o + i].z;
+    const std::uint32_t px = d.px[o + i];
+    const float4 p = d.pts_in[o + i];
     if (cell >= 0)
     {
         const std::uint32_t s = d.cell_start[static_cast<std::size_t>(f) * (sp.ncell + 1) + cell];
-        d.zo[o + s + slot] = make_uint2(i, __float_as_uint(z));
+        d.zo[o + s + slot] = make_uint2(i, __float_as_uint(p.z));
+        // range-image scatter (segmenter.cpp:291-318), see k_seg_px: the winner of a pixel does not depend on the
+        // labels, so the key goes out with this pass and no later pass re-reads the cloud for it
+        const float d2 = (p.x * p.x) + (p.y * p.y);
+        const unsigned long long key = (static_cast<unsigned long long>(__float_as_uint(d2)) << 33) |
+                                       (static_cast<unsigned long long>(cell / sp.rings) << sp.idx_bits) |
+                                       static_cast<unsigned long long>(i);
+        atomicMin(&d.key[static_cast<std::size_t>(f) * sp.npx + px], key);
     }
 }
 
@@ -335,6 +343,26 @@ __device__ __forceinline__ float cell_zmin_regs(const uint2* zo, std::uint32_t n
         const std::uint32_t t = e * 32 + lane;
         z[e] = t < n ? zkey(zo[t].y) : 0xffffffffu;
     }
+    // no gap can open below the median when the lower half of the heights spans <= 0.5 m (see cell_is_flat)
+    {
+        std::uint32_t kmin = z[0];
+#pragma unroll
+        for (int e = 1; e < E; ++e)
+        {
+            kmin = min(kmin, z[e]);
+        }
+        const float zlo = zval(__reduce_min_sync(0xffffffffu, kmin));
+        std::uint32_t within = 0;
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+        {
+            within += (static_cast<std::uint32_t>(e) * 32u + lane < n && zval(z[e]) - zlo <= 0.5f) ? 1u : 0u;
+        }
+        if (__reduce_add_sync(0xffffffffu, within) >= n / 2u + 1u)
+        {
+            return zlo;
+        }
+    }
     warp_sort_regs<E>(z);
 #pragma unroll
     for (int e = 0; e < E; ++e)
@@ -358,6 +386,18 @@ __device__ __forceinline__ void seg_cell_one(const Dev& d, const SegParams& sp, 
         // the common case: one height per lane, shuffle-only bitonic network
         const std::uint32_t lane = lane_id();
         std::uint32_t zk = lane < n ? zkey(zo[lane].y) : 0xffffffffu;
+        // Flat cell (the common case: ground): the reference looks for the highest gap > 0.5 m among the sorted
+        // heights zs[0 .. n/2]. Rounding is monotonic, so when n/2 + 1 heights satisfy z - zs[0] <= 0.5f (in float,
+        // as the reference subtracts) every adjacent difference in that range is <= 0.5f as well: the answer is the
+        // plain minimum and the sort is skipped. (A NaN or infinite height fails the comparison and takes the sort.)
+        const float zlo = zval(__reduce_min_sync(0xffffffffu, zk));
+        const std::uint32_t flat = __ballot_sync(0xffffffffu, lane < n && zval(zk) - zlo <= 0.5f);
+        if (static_cast<std::uint32_t>(__popc(flat)) >= n / 2u + 1u)
+        {
+            zmin = zlo;
+        }
+        else
+        {
         // most cells far from the sensor hold a handful of points: the network only runs up to the
         // next power of two of n (lanes beyond hold the +inf padding and sort among themselves)
         if (n <= 4)
@@ -382,6 +422,7 @@ __device__ __forceinline__ void seg_cell_one(const Dev& d, const SegParams& sp, 
         const std::uint32_t m = __ballot_sync(0xffffffffu, hit);
         const int src_lane = m != 0 ? 31 - __clz(m) : 0;
         zmin = __shfl_sync(0xffffffffu, z, src_lane);
+        }
     }
     else if (n <= 64)
     {
@@ -399,14 +440,32 @@ __device__ __forceinline__ void seg_cell_one(const Dev& d, const SegParams& sp, 
     {
         // oversized cell (rare): the same bitonic network over global scratch; a warp's own
         // stores are visible to its lanes after __syncwarp
-        float* zt = d.zsort + o + a;
+        std::uint32_t kmin = 0xffffffffu;
         for (std::uint32_t t = lane_id(); t < n; t += 32)
         {
-            zt[t] = __uint_as_float(zo[t].y);
+            kmin = min(kmin, zkey(zo[t].y));
         }
-        __syncwarp();
-        warp_sort(zt, n);
-        zmin = gap_scan([&](std::uint32_t i) { return zt[i]; }, n);
+        const float zlo = zval(__reduce_min_sync(0xffffffffu, kmin));
+        std::uint32_t within = 0;
+        for (std::uint32_t t = lane_id(); t < n; t += 32)
+        {
+            within += (__uint_as_float(zo[t].y) - zlo <= 0.5f) ? 1u : 0u;
+        }
+        if (__reduce_add_sync(0xffffffffu, within) >= n / 2u + 1u)
+        {
+            zmin = zlo; // flat cell, see above
+        }
+        else
+        {
+            float* zt = d.zsort + o + a;
+            for (std::uint32_t t = lane_id(); t < n; t += 32)
+            {
+                zt[t] = __uint_as_float(zo[t].y);
+            }
+            __syncwarp();
+            warp_sort(zt, n);
+            zmin = gap_scan([&](std::uint32_t i) { return zt[i]; }, n);
+        }
     }
     if (lane_id() == 0)
     {
@@ -473,8 +532,9 @@ __global__ void __launch_bounds__(128) k_seg_elev(Dev d, SegParams sp)
     }
 }
 
-// obstacle classification (segmenter.cpp:271-283) and RANSAC candidate flags (:328-351), per point
-// of the segmented cloud. lab bit 7 marks a candidate; candidates are counted per cell.
+// RANSAC candidates (segmenter.cpp:328-351), per point of the segmented cloud: counted per cell and copied
+// densely. The obstacle classification itself (:271-283) is only ever observed for the pixel winners of the range
+// image, so it is evaluated there (k_seg_px) and no per-point label plane exists.
 __global__ void __launch_bounds__(256) k_seg_label(Dev d, SegParams sp)
 {
     const std::uint32_t f = blockIdx.y;
@@ -491,19 +551,15 @@ __global__ void __launch_bounds__(256) k_seg_label(Dev d, SegParams sp)
     {
         const std::int32_t c = d.cell[o + i];
         pt = d.pts_in[o + i]; // in flight together with the cell index (only the elevation look-up depends on it)
-        std::uint8_t l = 0;
-        if (c >= 0)
+        if (c >= 0 && (c % sp.rings) < kRansacBins)
         {
             const float z = pt.z;
             const float e = d.elev[static_cast<std::size_t>(f) * sp.ncell + c];
-            l = (z >= e + sp.thr) ? PX_OBSTACLE : PX_GROUND;
-            if ((c % sp.rings) < kRansacBins && fabsf(e - z) < sp.thr2)
+            if (fabsf(e - z) < sp.thr2)
             {
-                l |= 0x80;
                 ccell = c;
             }
         }
-        d.lab[o + i] = l;
     }
     const std::uint32_t peers = __match_any_sync(0xffffffffu, ccell);
     if (ccell >= 0 && static_cast<int>(lane_id()) == __ffs(peers) - 1)
@@ -679,6 +735,7 @@ __global__ void __launch_bounds__(64) k_ransac_plane(Dev d, SegParams sp)
         std::uint32_t r = t - ccnt[c]; // rank inside the cell, cloud order
         const std::uint32_t a = cs[c], n = cs[c + 1] - a;
         const uint2* zo = d.zo + o + a;
+        const float elev_c = d.elev[static_cast<std::size_t>(f) * sp.ncell + c];
         // stage the candidates' point indices
         std::uint32_t m = 0;
         for (std::uint32_t base = 0; base < n; base += 32)
@@ -688,8 +745,9 @@ __global__ void __launch_bounds__(64) k_ransac_plane(Dev d, SegParams sp)
             bool is = false;
             if (u < n)
             {
-                idx = zo[u].x;
-                is = (d.lab[o + idx] & 0x80) != 0;
+                const uint2 rec = zo[u];
+                idx = rec.x;
+                is = fabsf(elev_c - __uint_as_float(rec.y)) < sp.thr2; // the candidate test of k_seg_label
             }
             const std::uint32_t b = __ballot_sync(0xffffffffu, is);
             const std::uint32_t w = m + __popc(b & ((1u << lane) - 1u));
@@ -727,8 +785,9 @@ __global__ void __launch_bounds__(64) k_ransac_plane(Dev d, SegParams sp)
                 std::uint32_t cnt0 = 0;
                 for (std::uint32_t u = lane; u < n; u += 32)
                 {
-                    const std::uint32_t v = zo[u].x;
-                    if ((d.lab[o + v] & 0x80) != 0 && (v >> (bit + 1)) == (prefix >> (bit + 1)) &&
+                    const uint2 rec = zo[u];
+                    const std::uint32_t v = rec.x;
+                    if (fabsf(elev_c - __uint_as_float(rec.y)) < sp.thr2 && (v >> (bit + 1)) == (prefix >> (bit + 1)) &&
                         ((v >> bit) & 1u) == 0u)
                     {
                         cnt0 += 1;
@@ -865,7 +924,7 @@ __global__ void __launch_bounds__(256) k_ransac_count(Dev d, SegParams sp)
 // (depth^2 bits, slice, point index) under atomicMin reproduces the winner without any sorted list.
 // ------------------------------------------------------------------------------------------
 // best plane of a frame (segmenter.cpp:434-453): the first iteration with the strictly largest inlier
-// count, flipped so that c >= 0. One warp per frame, once - not once per CTA of k_seg_image.
+// count, flipped so that c >= 0. One warp per frame, once - not once per CTA of k_seg_px.
 __global__ void __launch_bounds__(32) k_ransac_best(Dev d)
 {
     const std::uint32_t f = blockIdx.x;
@@ -903,49 +962,6 @@ __global__ void __launch_bounds__(32) k_ransac_best(Dev d)
     }
 }
 
-__global__ void __launch_bounds__(256) k_seg_image(Dev d, SegParams sp)
-{
-    const std::uint32_t f = blockIdx.y;
-    const std::uint32_t n = d.n_in[f];
-    if (blockIdx.x * 256u >= n)
-    {
-        return;
-    }
-    const float4 s_plane = d.best_plane[f];
-    const bool s_have = d.best_cnt[f] != 0;
-    const std::uint32_t i = blockIdx.x * 256u + threadIdx.x;
-    if (i >= n)
-    {
-        return;
-    }
-    const std::size_t o = static_cast<std::size_t>(f) * d.cap;
-    // cell, coordinates, label and pixel are independent loads: all in flight before the first use
-    const std::int32_t c = d.cell[o + i];
-    const float4 p = d.pts_in[o + i];
-    const std::uint8_t lab_i = d.lab[o + i];
-    const std::uint32_t px_i = d.px[o + i];
-    if (c < 0)
-    {
-        return;
-    }
-    std::uint8_t l = lab_i & 0x7f;
-    if (s_have && (c % sp.rings) < kRansacBins)
-    {
-        const float4 pl = s_plane;
-        const float sd = (pl.x * p.x) + (pl.y * p.y) + (pl.z * p.z) - pl.w;
-        if (sd < sp.thr)
-        {
-            l = PX_GROUND;
-        }
-    }
-    d.lab[o + i] = l;
-    const float d2 = (p.x * p.x) + (p.y * p.y);
-    const unsigned long long key = (static_cast<unsigned long long>(__float_as_uint(d2)) << 33) |
-                                   (static_cast<unsigned long long>(c / sp.rings) << sp.idx_bits) |
-                                   static_cast<unsigned long long>(i);
-    atomicMin(&d.key[static_cast<std::size_t>(f) * sp.npx + px_i], key);
-}
-
 __global__ void __launch_bounds__(256) k_seg_px(Dev d, SegParams sp)
 {
     const std::uint32_t f = blockIdx.y;
@@ -963,8 +979,21 @@ __global__ void __launch_bounds__(256) k_seg_px(Dev d, SegParams sp)
         const std::size_t o = static_cast<std::size_t>(f) * d.cap;
         const std::uint32_t i = static_cast<std::uint32_t>(key & ((1ULL << sp.idx_bits) - 1ULL));
         const float4 q = d.pts_in[o + i];
+        const std::int32_t cell = d.cell[o + i];
         v = make_float4(q.x, q.y, q.z, __int_as_float(static_cast<int>(i)));
-        c = d.lab[o + i];
+        // obstacle classification against the cell's elevation (segmenter.cpp:271-283), then the RANSAC plane over the
+        // near-field bins (:455-477)
+        const float e = d.elev[static_cast<std::size_t>(f) * sp.ncell + cell];
+        c = (q.z >= e + sp.thr) ? PX_OBSTACLE : PX_GROUND;
+        if (d.best_cnt[f] != 0 && (cell % sp.rings) < kRansacBins)
+        {
+            const float4 pl = d.best_plane[f];
+            const float sd = (pl.x * q.x) + (pl.y * q.y) + (pl.z * q.z) - pl.w;
+            if (sd < sp.thr)
+            {
+                c = PX_GROUND;
+            }
+        }
     }
     d.pxpt[po + p] = v;
     d.code[po + p] = c;
@@ -1729,8 +1758,6 @@ void launch_segment(Ctx* c, std::uint32_t nf, bool want_image)
     mark(c, "ransac_count");
     k_ransac_best<<<nf, 32, 0, s>>>(d);
     mark(c, "ransac_best");
-    k_seg_image<<<gpts, 256, 0, s>>>(d, sp);
-    mark(c, "seg_image");
     k_seg_px<<<dim3((sp.npx + 255) / 256, nf), 256, 0, s>>>(d, sp);
     mark(c, "seg_px");
     const dim3 gdil((sp.W + kDilTw - 1) / kDilTw, (sp.H + kDilTh - 1) / kDilTh, nf);
