@@ -52,6 +52,15 @@ struct lpl_ctx
     int rand_i = -1; // -1: not seeded yet
     unsigned long long cfg_epoch = 0;
     bool use_graphs = true;
+    // sub-batches of one run on concurrent streams (enqueue_stages): streams and join events, created on first use
+    struct Aux
+    {
+        cudaStream_t stream;
+        cudaEvent_t done;
+    };
+    std::vector<Aux> aux;
+    cudaEvent_t fork_ev = nullptr;
+    std::uint32_t split_parts = 2;
     std::vector<std::uint32_t> h_status;
 };
 
@@ -548,6 +557,11 @@ int lpl_create(lpl_ctx** out, int device, std::uint32_t max_points, std::uint32_
         }
     }
     ctx->use_graphs = std::getenv("LPL_NO_GRAPH") == nullptr;
+    if (const char* sp = std::getenv("LPL_SPLIT"))
+    {
+        const int v = std::atoi(sp);
+        ctx->split_parts = v >= 1 && v <= 8 ? static_cast<std::uint32_t>(v) : 2u;
+    }
     lpl_segmenter_default_cfg(&ctx->seg_cfg);
     ctx->seg_cfg.image_height = H;
     ctx->seg_cfg.image_width = W;
@@ -606,6 +620,15 @@ void lpl_destroy(lpl_ctx* ctx)
         {
             cudaEventDestroy(e);
         }
+    }
+    for (auto& a : ctx->aux)
+    {
+        cudaEventDestroy(a.done);
+        cudaStreamDestroy(a.stream);
+    }
+    if (ctx->fork_ev != nullptr)
+    {
+        cudaEventDestroy(ctx->fork_ev);
     }
     if (c.stream != nullptr)
     {
@@ -893,7 +916,72 @@ int lpl_pipeline_upload_cloud2(lpl_ctx* ctx, const lpl_cloud2_frame* frames, std
     return LPL_OK;
 }
 
-// every kernel and memset of one pass of the selected stages, on the context stream (also what a graph captures)
+// one pass of the selected stages over the frames [c.d.f0, c.d.f0 + nf) on c.stream (c: the context itself or the
+// view of one sub-batch, see enqueue_stages)
+static int enqueue_chain(lpl_ctx* ctx, Ctx& c, std::uint32_t nf, std::uint32_t stages)
+{
+    Dev& d = c.d;
+    const std::uint32_t f0 = d.f0;
+    if ((stages & LPL_STAGE_DROR) == 0)
+    {
+        LPL_TRY(cudaMemsetAsync(at_frame(d.noise, d.cap, f0), 0, static_cast<std::size_t>(d.cap) * nf, c.stream));
+    }
+    const bool ring_stage = (stages & LPL_STAGE_RING) != 0;
+    const bool fused_front = ring_stage && (stages & LPL_STAGE_DROR) != 0; // one read of the cloud for both stages
+    if (ring_stage && !fused_front)
+    {
+        launch_ring(&c, nf);
+    }
+    else if (!ctx->have_ring)
+    {
+        LPL_TRY(cudaMemsetAsync(at_frame(d.ring, d.cap, f0), 0, sizeof(std::uint16_t) * static_cast<std::size_t>(d.cap) * nf, c.stream));
+    }
+    if (stages & LPL_STAGE_DROR)
+    {
+        launch_dror(&c, nf, fused_front);
+    }
+    if ((stages & LPL_STAGE_SEGMENT) == 0 && (stages & (LPL_STAGE_CLUSTER | LPL_STAGE_HULLS)) != 0)
+    {
+        // no labels in this run: the obstacle cloud is empty rather than a previous batch's
+        LPL_TRY(cudaMemsetAsync(at_frame(d.labels_out, d.cap, f0), 0, static_cast<std::size_t>(d.cap) * nf, c.stream));
+    }
+    if (stages & LPL_STAGE_SEGMENT)
+    {
+        launch_segment(&c, nf, ctx->want_image != 0);
+        if (c.launch_failed)
+        {
+            c.launch_failed = false;
+            return LPL_ERR_CUDA; // message already in err
+        }
+    }
+    if (stages & LPL_STAGE_CLUSTER)
+    {
+        launch_take_obstacles(&c, nf);
+        launch_cluster(&c, nf);
+    }
+    if (stages & LPL_STAGE_HULLS)
+    {
+        launch_hulls(&c, nf);
+    }
+    if ((stages & LPL_STAGE_BOXES) && (stages & LPL_STAGE_HULLS))
+    {
+        launch_boxes(&c, nf, LPL_BOX_ROTATING_CALIPERS);
+    }
+    return LPL_OK;
+}
+
+// Every kernel and memset of one pass of the selected stages (also what a graph captures).
+//
+// Sub-batches. Frames are independent, and the chain alternates between kernels that fill the GPU (the per-point
+// passes) and kernels that cannot (one CTA per frame: the JCP row sweep, the shared-memory union-find, the RECM
+// recurrence, the scans). A batch of >= kSplitMinFrames frames is therefore cut into `split_parts` contiguous
+// sub-batches whose chains run on concurrent streams (fork / join by events; inside a captured graph these become
+// parallel branches): while one sub-batch sits in a latency-bound kernel the per-point kernels of another use the
+// SMs it leaves idle. Every kernel takes its frame as blockIdx + Dev::f0, so a sub-batch is the same launch with a
+// smaller grid and a frame offset; all per-frame state is disjoint. Not while the per-kernel profile is on (its
+// events time one stream).
+constexpr std::uint32_t kSplitMinFrames = 16;
+
 static int enqueue_stages(lpl_ctx* ctx, std::uint32_t nf, std::uint32_t stages)
 {
     Ctx& c = ctx->c;
@@ -911,52 +999,99 @@ static int enqueue_stages(lpl_ctx* ctx, std::uint32_t nf, std::uint32_t stages)
         explicit Cleared(Ctx& cc) : c(cc) { c.counters_cleared = true; }
         ~Cleared() { c.counters_cleared = false; }
     } cleared(c);
-    if ((stages & LPL_STAGE_DROR) == 0)
-    {
-        LPL_TRY(cudaMemsetAsync(d.noise, 0, static_cast<std::size_t>(d.cap) * nf, c.stream));
-    }
     const bool ring_stage = (stages & LPL_STAGE_RING) != 0;
-    const bool fused_front = ring_stage && (stages & LPL_STAGE_DROR) != 0; // one read of the cloud for both stages
-    if (ring_stage && !fused_front)
-    {
-        launch_ring(&c, nf);
-    }
-    else if (!ctx->have_ring)
-    {
-        LPL_TRY(cudaMemsetAsync(d.ring, 0, sizeof(std::uint16_t) * static_cast<std::size_t>(d.cap) * nf, c.stream));
-    }
     c.seg.use_ring = ((ring_stage || ctx->have_ring) && ctx->seg_cfg.assume_unorganized_cloud == 0) ? 1 : 0;
-    if (stages & LPL_STAGE_DROR)
+    ctx->ran_hulls = (stages & LPL_STAGE_HULLS) != 0;
+    std::uint32_t parts = ctx->split_parts;
+    if (c.prof_on || !c.hash_clean || nf < kSplitMinFrames || parts > nf)
     {
-        launch_dror(&c, nf, fused_front);
+        parts = 1; // (the first run of a context clears whole hash planes: one stream)
     }
-    if ((stages & LPL_STAGE_SEGMENT) == 0 && (stages & (LPL_STAGE_CLUSTER | LPL_STAGE_HULLS)) != 0)
+    while (parts > 1 && ctx->aux.size() < parts - 1)
     {
-        // no labels in this run: the obstacle cloud is empty rather than a previous batch's
-        LPL_TRY(cudaMemsetAsync(d.labels_out, 0, static_cast<std::size_t>(d.cap) * nf, c.stream));
-    }
-    if (stages & LPL_STAGE_SEGMENT)
-    {
-        launch_segment(&c, nf, ctx->want_image != 0);
-        if (c.launch_failed)
+        lpl_ctx::Aux a{};
+        if (cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&a.done, cudaEventDisableTiming) != cudaSuccess)
         {
-            c.launch_failed = false;
-            return LPL_ERR_CUDA; // message already in err
+            cudaGetLastError();
+            if (a.stream != nullptr)
+            {
+                cudaStreamDestroy(a.stream);
+            }
+            parts = 1;
+            break;
+        }
+        try
+        {
+            ctx->aux.push_back(a);
+        }
+        catch (...)
+        {
+            cudaEventDestroy(a.done);
+            cudaStreamDestroy(a.stream);
+            parts = 1;
         }
     }
-    if (stages & LPL_STAGE_CLUSTER)
+    if (parts > 1 && ctx->fork_ev == nullptr && cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming) != cudaSuccess)
     {
-        launch_take_obstacles(&c, nf);
-        launch_cluster(&c, nf);
+        cudaGetLastError();
+        parts = 1;
     }
-    ctx->ran_hulls = (stages & LPL_STAGE_HULLS) != 0;
-    if (stages & LPL_STAGE_HULLS)
+    if (parts <= 1)
     {
-        launch_hulls(&c, nf);
+        d.f0 = 0;
+        const int rc = enqueue_chain(ctx, c, nf, stages);
+        if (rc != 0)
+        {
+            return rc;
+        }
+        LPL_TRY(cudaGetLastError());
+        return LPL_OK;
     }
-    if ((stages & LPL_STAGE_BOXES) && (stages & LPL_STAGE_HULLS))
+    LPL_TRY(cudaEventRecord(ctx->fork_ev, c.stream));
+    int rc = LPL_OK;
+    for (std::uint32_t p = 0; p < parts; ++p)
     {
-        launch_boxes(&c, nf, LPL_BOX_ROTATING_CALIPERS);
+        const std::uint32_t a = static_cast<std::uint32_t>(static_cast<unsigned long long>(nf) * p / parts);
+        const std::uint32_t b = static_cast<std::uint32_t>(static_cast<unsigned long long>(nf) * (p + 1) / parts);
+        Ctx sub = c; // a view: same buffers and parameters, its own stream and frame offset
+        sub.d.f0 = a;
+        sub.launches = 0;
+        if (p != 0)
+        {
+            sub.stream = ctx->aux[p - 1].stream;
+            if (cudaStreamWaitEvent(sub.stream, ctx->fork_ev, 0) != cudaSuccess)
+            {
+                rc = LPL_ERR_CUDA;
+                break;
+            }
+        }
+        const int r = rc == LPL_OK ? enqueue_chain(ctx, sub, b - a, stages) : LPL_OK;
+        c.launches += sub.launches;
+        if (sub.have_code_map && !c.have_code_map)
+        {
+            c.code_map = sub.code_map;
+            c.have_code_map = true;
+        }
+        if (r != LPL_OK)
+        {
+            std::memcpy(c.err, sub.err, sizeof(c.err));
+            rc = r;
+        }
+        if (p != 0)
+        {
+            // joined even after an error: a capture in progress must end with every forked stream back in
+            if (cudaEventRecord(ctx->aux[p - 1].done, sub.stream) != cudaSuccess ||
+                cudaStreamWaitEvent(c.stream, ctx->aux[p - 1].done, 0) != cudaSuccess)
+            {
+                rc = rc != LPL_OK ? rc : LPL_ERR_CUDA;
+            }
+        }
+    }
+    if (rc != LPL_OK)
+    {
+        cudaGetLastError();
+        return rc == LPL_ERR_CUDA && c.err[0] == 0 ? fail(ctx, LPL_ERR_CUDA, "sub-batch fork / join failed") : rc;
     }
     LPL_TRY(cudaGetLastError());
     return LPL_OK;
@@ -1055,6 +1190,20 @@ int lpl_pipeline_use_graph(lpl_ctx* ctx, int enable)
         return LPL_ERR_INVALID_ARGUMENT;
     }
     ctx->use_graphs = enable != 0 && std::getenv("LPL_NO_GRAPH") == nullptr;
+    return LPL_OK;
+}
+
+int lpl_pipeline_use_split(lpl_ctx* ctx, std::uint32_t parts)
+{
+    if (ctx == nullptr || parts == 0 || parts > 8)
+    {
+        return LPL_ERR_INVALID_ARGUMENT;
+    }
+    if (parts != ctx->split_parts)
+    {
+        ctx->split_parts = parts;
+        ctx->cfg_epoch += 1; // captured graphs hold the old branch structure
+    }
     return LPL_OK;
 }
 

@@ -26,7 +26,7 @@ namespace lpl
 __global__ void __launch_bounds__(256) k_clu_sph(Dev d)
 {
     __shared__ std::uint32_t smax[3];
-    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t f = blockIdx.y + d.f0;
     const std::uint32_t n = d.n_o[f];
     if (blockIdx.x * 256u >= n)
     {
@@ -127,7 +127,7 @@ __device__ __forceinline__ std::uint32_t voxel_home(std::int32_t key, std::uint3
 
 __global__ void __launch_bounds__(256) k_clu_insert(Dev d, ClusterParams cp)
 {
-    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t f = blockIdx.y + d.f0;
     const std::uint32_t n = d.n_o[f];
     if (blockIdx.x * 256u >= n)
     {
@@ -226,7 +226,7 @@ constexpr int kFwd = 13; // forward half of the 26-neighbourhood
 // consumed, and the ids of the neighbours found go to a fixed 13-entry row per voxel.
 __global__ void __launch_bounds__(256) k_clu_edges(Dev d, ClusterParams cp)
 {
-    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t f = blockIdx.y + d.f0;
     const std::uint32_t v = blockIdx.x * 256u + threadIdx.x;
     if (v >= d.n_vox[f])
     {
@@ -369,7 +369,7 @@ __device__ __forceinline__ void uf_publish(const Dev& d, std::size_t o, std::siz
 __global__ void __launch_bounds__(kUfThreads) k_clu_union_sm(Dev d)
 {
     extern __shared__ std::uint32_t par[];
-    const std::uint32_t f = blockIdx.x;
+    const std::uint32_t f = blockIdx.x + d.f0;
     const std::uint32_t nv = d.n_vox[f];
     if (nv == 0 || nv > kUfSmemVoxels)
     {
@@ -426,7 +426,7 @@ __global__ void __launch_bounds__(kUfThreads) k_clu_union_sm(Dev d)
 // (e.g. the 2M-point clouds): one thread per voxel walks its edge row.
 __global__ void __launch_bounds__(256) k_clu_union(Dev d)
 {
-    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t f = blockIdx.y + d.f0;
     const std::uint32_t nvox = d.n_vox[f];
     if (nvox <= kUfSmemVoxels)
     {
@@ -470,7 +470,7 @@ __global__ void __launch_bounds__(256) k_clu_union(Dev d)
 
 __global__ void __launch_bounds__(256) k_clu_flatten(Dev d)
 {
-    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t f = blockIdx.y + d.f0;
     const std::uint32_t nvox = d.n_vox[f];
     if (nvox <= kUfSmemVoxels)
     {
@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(256) k_clu_flatten(Dev d)
 // memsets (484 MB per 154-frame batch) ahead of every run.
 __global__ void __launch_bounds__(256) k_clu_clean(Dev d)
 {
-    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t f = blockIdx.y + d.f0;
     const std::uint32_t nvox = d.n_vox[f];
     const std::size_t o = static_cast<std::size_t>(f) * d.cap;
     const std::size_t ho = static_cast<std::size_t>(f) * d.hcap;
@@ -540,7 +540,7 @@ struct ClusterRepEmit
 
 __global__ void __launch_bounds__(256) k_clu_labels(Dev d)
 {
-    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t f = blockIdx.y + d.f0;
     const std::uint32_t n = d.n_o[f];
     const std::uint32_t i = blockIdx.x * 256u + threadIdx.x;
     if (blockIdx.x * 256u >= n)
@@ -604,8 +604,8 @@ void launch_cluster(Ctx* c, std::uint32_t nf)
     cudaStream_t s = c->stream;
     if (!c->counters_cleared)
     {
-        cudaMemsetAsync(d.sph_max, 0, sizeof(std::uint32_t) * 4 * nf, s);
-        cudaMemsetAsync(d.n_vox, 0, sizeof(std::uint32_t) * nf, s);
+        cudaMemsetAsync(at_frame(d.sph_max, 4, d.f0), 0, sizeof(std::uint32_t) * 4 * nf, s);
+        cudaMemsetAsync(at_frame(d.n_vox, 1, d.f0), 0, sizeof(std::uint32_t) * nf, s);
     }
     if (!c->hash_clean)
     {

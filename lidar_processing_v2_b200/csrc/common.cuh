@@ -124,6 +124,8 @@ struct Dev
     std::uint32_t qcap;   // JCP queue capacity per frame
     std::uint32_t hcap;   // voxel hash slots per frame (power of two)
     std::uint32_t ptiles; // pixel tiles per frame = ceil(npx / kTile)
+    std::uint32_t f0;     // first frame of this launch: a kernel's frame is blockIdx + f0 (sub-batches of one run on
+                          // concurrent streams, see capi.cu: enqueue_stages)
 
     // ---- input cloud
     float4* pts_in;           // [B][cap]  x,y,z,(unused)
@@ -515,10 +517,10 @@ __device__ __forceinline__ void accumulate_cluster_stats(unsigned long long* ext
 template <class Pred>
 __global__ void __launch_bounds__(kTileThreads)
     k_compact_count(Pred pred, const std::uint32_t* __restrict__ n_arr, std::uint32_t n_const,
-                    std::uint32_t* __restrict__ tile_cnt, std::uint32_t tiles_per_frame)
+                    std::uint32_t* __restrict__ tile_cnt, std::uint32_t tiles_per_frame, std::uint32_t f0)
 {
     __shared__ std::uint32_t sh[33];
-    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t f = blockIdx.y + f0;
     const std::uint32_t n = n_arr ? n_arr[f] : n_const;
     const std::uint32_t base = blockIdx.x * kTile;
     std::uint32_t c = 0;
@@ -542,11 +544,11 @@ template <class Pred, class Emit>
 __global__ void __launch_bounds__(kTileThreads)
     k_compact_scatter(Pred pred, Emit emit, const std::uint32_t* __restrict__ n_arr,
                       std::uint32_t n_const, const std::uint32_t* __restrict__ tile_cnt,
-                      std::uint32_t tiles_per_frame, std::uint32_t* __restrict__ n_out)
+                      std::uint32_t tiles_per_frame, std::uint32_t* __restrict__ n_out, std::uint32_t f0)
 {
     __shared__ std::uint32_t sh[kItems * (kTileThreads / 32) + 1];
     __shared__ std::uint32_t sh2[33];
-    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t f = blockIdx.y + f0;
     const std::uint32_t n = n_arr ? n_arr[f] : n_const;
     const std::uint32_t base = blockIdx.x * kTile;
     const std::uint32_t* tc = tile_cnt + f * tiles_per_frame;
@@ -598,7 +600,14 @@ __global__ void __launch_bounds__(kTileThreads)
 __global__ void k_excl_scan(const std::uint32_t* __restrict__ in, std::uint32_t in_stride,
                             std::uint32_t* __restrict__ out, std::uint32_t out_stride,
                             std::uint32_t len, const std::uint32_t* __restrict__ len_arr,
-                            std::uint32_t* __restrict__ total_out);
+                            std::uint32_t* __restrict__ total_out, std::uint32_t f0 = 0);
+
+// start of frame f0 in a frame-major array of `stride` elements per frame (memsets of a sub-batch)
+template <typename T>
+inline T* at_frame(T* p, std::size_t stride, std::uint32_t f0)
+{
+    return p + stride * f0;
+}
 
 // host-side launchers implemented per stage
 struct Ctx;
@@ -714,10 +723,10 @@ inline void launch_compact_recorded(Ctx* c, const char* name, std::uint32_t B, s
 {
     const dim3 grid(tiles_per_frame, B);
     k_compact_count<<<grid, kTileThreads, 0, c->stream>>>(RecordingPred<Pred>{pred, flags, c->d.cap}, n_arr, 0u, tile_cnt,
-                                                          tiles_per_frame);
+                                                          tiles_per_frame, c->d.f0);
     mark(c, name);
     k_compact_scatter<<<grid, kTileThreads, 0, c->stream>>>(RecordedPred{flags, c->d.cap}, emit, n_arr, 0u, tile_cnt,
-                                                            tiles_per_frame, n_out);
+                                                            tiles_per_frame, n_out, c->d.f0);
     mark(c, name);
 }
 
@@ -727,10 +736,10 @@ inline void launch_compact(Ctx* c, const char* name, std::uint32_t B, std::uint3
                            std::uint32_t* tile_cnt, std::uint32_t* n_out, Pred pred, Emit emit)
 {
     const dim3 grid(tiles_per_frame, B);
-    k_compact_count<<<grid, kTileThreads, 0, c->stream>>>(pred, n_arr, n_const, tile_cnt, tiles_per_frame);
+    k_compact_count<<<grid, kTileThreads, 0, c->stream>>>(pred, n_arr, n_const, tile_cnt, tiles_per_frame, c->d.f0);
     mark(c, name);
     k_compact_scatter<<<grid, kTileThreads, 0, c->stream>>>(pred, emit, n_arr, n_const, tile_cnt,
-                                                            tiles_per_frame, n_out);
+                                                            tiles_per_frame, n_out, c->d.f0);
     mark(c, name);
 }
 

@@ -62,7 +62,7 @@ constexpr std::uint32_t kOctaMinPoints = 16; // smaller clusters skip the filter
 
 __global__ void __launch_bounds__(128) k_hull_octagon(Dev d)
 {
-    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t f = blockIdx.y + d.f0;
     const std::uint32_t K = d.n_clusters[f];
     const std::size_t o = static_cast<std::size_t>(f) * d.cap;
     for (std::uint32_t c = blockIdx.x * 128u + threadIdx.x; c < K; c += gridDim.x * 128u)
@@ -162,7 +162,7 @@ struct HullKeepEmit
 __global__ void __launch_bounds__(kTileThreads) k_hull_tilesort(Dev d)
 {
     __shared__ uint4 s[kTile];
-    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t f = blockIdx.y + d.f0;
     const std::uint32_t n = d.n_h[f];
     const std::uint32_t base = blockIdx.x * kTile;
     if (base >= n)
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(kTileThreads) k_hull_merge(Dev d, std::uint32_
 {
     __shared__ uint4 s[kTile];
     __shared__ std::uint32_t s_split[2];
-    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t f = blockIdx.y + d.f0;
     const std::uint32_t n = d.n_h[f];
     const std::uint32_t out0 = blockIdx.x * kTile;
     if (out0 >= n || sort_passes(n) <= pass)
@@ -416,7 +416,7 @@ __device__ __forceinline__ std::uint32_t monotone_chain(Get P, std::uint32_t m, 
 
 __global__ void __launch_bounds__(128) k_hull_gather(Dev d)
 {
-    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t f = blockIdx.y + d.f0;
     const std::uint32_t K = d.n_clusters[f];
     const std::size_t o = static_cast<std::size_t>(f) * d.cap;
     const std::uint32_t* cstart = d.cstart + static_cast<std::size_t>(f) * (d.cap + 1);
@@ -725,7 +725,7 @@ __global__ void __launch_bounds__(1024) k_hull_plan(Dev d)
         s_multi = 0;
     }
     __syncthreads();
-    const std::uint32_t f = blockIdx.x;
+    const std::uint32_t f = blockIdx.x + d.f0;
     const std::uint32_t K = d.n_clusters[f];
     const std::size_t o = static_cast<std::size_t>(f) * d.cap;
     std::uint32_t* off = d.hwk_off + static_cast<std::size_t>(f) * (d.cap + 1);
@@ -768,7 +768,7 @@ __global__ void __launch_bounds__(kChunkWarps * 32) k_hull_chunks(Dev d)
     __shared__ std::uint32_t s_off[kOffCache];
     using WarpBuf = WarpBufT<kChunk>;
     WarpBuf& buf = reinterpret_cast<WarpBuf*>(s_raw)[threadIdx.x >> 5];
-    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t f = blockIdx.y + d.f0;
     const std::uint32_t K = d.n_clusters[f];
     const std::uint32_t W = d.n_work[f];
     const std::size_t o = static_cast<std::size_t>(f) * d.cap;
@@ -867,7 +867,7 @@ __global__ void __launch_bounds__(kJoinWarps * 32) k_hull_join(Dev d)
     extern __shared__ __align__(16) unsigned char s_raw[];
     using WarpBuf = WarpBufT<kJoin>;
     WarpBuf& buf = reinterpret_cast<WarpBuf*>(s_raw)[threadIdx.x >> 5];
-    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t f = blockIdx.y + d.f0;
     const std::uint32_t K = d.n_clusters[f];
     const std::size_t o = static_cast<std::size_t>(f) * d.cap;
     const std::uint32_t* cstart = d.cstart + static_cast<std::size_t>(f) * (d.cap + 1);
@@ -1117,7 +1117,7 @@ void launch_hulls(Ctx* c, std::uint32_t nf)
     mark(c, "hull_octagon");
     // d.lab (RECM labels of the segmenter) is free by now: it holds the recorded verdicts
     launch_compact_recorded(c, "hull_keep", nf, d.tiles, d.n_o, d.tile_cnt, d.n_h, d.lab, HullKeepPred{d}, HullKeepEmit{d});
-    k_excl_scan<<<nf, 1024, 0, s>>>(d.hseg_cnt, d.cap, d.cstart, d.cap + 1, d.cap, d.n_clusters, nullptr);
+    k_excl_scan<<<nf, 1024, 0, s>>>(d.hseg_cnt, d.cap, d.cstart, d.cap + 1, d.cap, d.n_clusters, nullptr, d.f0);
     mark(c, "hull_seg_scan");
     launch_hull_sort(c, nf);
     k_hull_plan<<<nf, 1024, 0, s>>>(d);
@@ -1129,7 +1129,7 @@ void launch_hulls(Ctx* c, std::uint32_t nf)
     mark(c, "hull_chunks");
     k_hull_join<<<dim3(per_frame_ctas(4, nf, 64), nf), kJoinWarps * 32, smem_join, s>>>(d);
     mark(c, "hull_join");
-    k_excl_scan<<<nf, 1024, 0, s>>>(d.hcnt, d.cap, d.hull_off, d.cap + 1, d.cap, d.n_clusters, d.n_hull);
+    k_excl_scan<<<nf, 1024, 0, s>>>(d.hcnt, d.cap, d.hull_off, d.cap + 1, d.cap, d.n_clusters, d.n_hull, d.f0);
     mark(c, "hull_off_scan");
     k_hull_gather<<<dim3(64, nf), 128, 0, s>>>(d);
     mark(c, "hull_gather");

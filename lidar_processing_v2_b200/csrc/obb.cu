@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(kObbWarps * 32) k_obb_frames(Dev d, int method
 {
     __shared__ int2 s_pairs[kObbWarps][32];
     __shared__ double s_area[kObbWarps][128];
-    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t f = blockIdx.y + d.f0;
     const std::uint32_t K = d.n_clusters[f];
     const std::uint32_t warp = threadIdx.x >> 5;
     const std::size_t o = static_cast<std::size_t>(f) * d.cap;

@@ -69,11 +69,11 @@ struct RingWrapPred
 __global__ void __launch_bounds__(kTileThreads)
     k_ring_write(RecordedPred pred, const std::uint32_t* __restrict__ n_arr,
                  const std::uint32_t* __restrict__ tile_cnt, std::uint32_t tiles_per_frame, std::uint32_t cnt_per_tile,
-                 std::uint16_t* __restrict__ ring, std::uint32_t cap)
+                 std::uint16_t* __restrict__ ring, std::uint32_t cap, std::uint32_t f0)
 {
     __shared__ std::uint32_t sh[kItems * (kTileThreads / 32) + 1];
     __shared__ std::uint32_t sh2[33];
-    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t f = blockIdx.y + f0;
     const std::uint32_t n = n_arr[f];
     const std::uint32_t base = blockIdx.x * kTile;
     if (base >= n)
@@ -119,10 +119,10 @@ void launch_ring(Ctx* c, std::uint32_t nf)
     // writes later in the chain
     const RingWrapPred pred{d.pts_in, d.cap};
     k_compact_count<<<grid, kTileThreads, 0, c->stream>>>(RecordingPred<RingWrapPred>{pred, d.lab, d.cap}, d.n_in, 0u,
-                                                          d.tile_cnt, d.tiles);
+                                                          d.tile_cnt, d.tiles, d.f0);
     mark(c, "ring_count");
     k_ring_write<<<grid, kTileThreads, 0, c->stream>>>(RecordedPred{d.lab, d.cap}, d.n_in, d.tile_cnt, d.tiles, 1u, d.ring,
-                                                      d.cap);
+                                                      d.cap, d.f0);
     mark(c, "ring_write");
 }
 
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(256)
     k_dror_near(Dev d, DrorParams prm)
 {
     __shared__ float4 sh[256 + 2 * kNearHalo];
-    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t f = blockIdx.y + d.f0;
     const std::uint32_t n = d.n_in[f];
     const std::uint32_t base = blockIdx.x * 256u;
     if (base >= n)
@@ -329,7 +329,7 @@ __device__ __forceinline__ DrorBox dror_box(const float4& p, float r_sqr, int le
 // bitmap (16 KB), and the grid is then built from the points of marked cells alone.
 __global__ void __launch_bounds__(256) k_dror_mark(Dev d, DrorParams prm)
 {
-    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t f = blockIdx.y + d.f0;
     const std::uint32_t nu = d.n_unres[f];
     std::uint32_t* mask = d.grid_mask + static_cast<std::size_t>(f) * (kDrorCells / 32);
     if (nu >= d.n_in[f] / 4u)
@@ -377,7 +377,7 @@ __device__ __forceinline__ bool dror_marked(const std::uint32_t* mask, int cell)
 
 __global__ void __launch_bounds__(256) k_dror_grid_count(Dev d)
 {
-    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t f = blockIdx.y + d.f0;
     const std::uint32_t n = d.n_in[f];
     if (blockIdx.x * 256u >= n || d.n_unres[f] == 0)
     {
@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(256) k_dror_grid_count(Dev d)
 
 __global__ void __launch_bounds__(256) k_dror_grid_scatter(Dev d)
 {
-    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t f = blockIdx.y + d.f0;
     const std::uint32_t n = d.n_in[f];
     if (blockIdx.x * 256u >= n || d.n_unres[f] == 0)
     {
@@ -478,7 +478,7 @@ constexpr int kDrorDense = LPL_DROR_DENSE; // queries among 32 consecutive grid 
 #endif
 __global__ void __launch_bounds__(kDrorQueryWarps * 32, LPL_DROR_MINB) k_dror_query(Dev d, DrorParams prm)
 {
-    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t f = blockIdx.y + d.f0;
     if (d.n_unres[f] == 0u)
     {
         return;
@@ -626,10 +626,10 @@ __global__ void __launch_bounds__(kDrorQueryWarps * 32, LPL_DROR_MINB) k_dror_qu
 __global__ void k_excl_scan(const std::uint32_t* __restrict__ in, std::uint32_t in_stride,
                             std::uint32_t* __restrict__ out, std::uint32_t out_stride,
                             std::uint32_t len, const std::uint32_t* __restrict__ len_arr,
-                            std::uint32_t* __restrict__ total_out)
+                            std::uint32_t* __restrict__ total_out, std::uint32_t f0)
 {
     __shared__ std::uint32_t sh[33];
-    const std::uint32_t f = blockIdx.x;
+    const std::uint32_t f = blockIdx.x + f0;
     if (len_arr != nullptr)
     {
         len = min(len, len_arr[f]);
@@ -701,7 +701,7 @@ __global__ void __launch_bounds__(1024) k_dror_grid_scan(Dev d)
     __shared__ std::uint32_t sh[33];
     __shared__ std::uint16_t s_list[kDrorWords];
     __shared__ std::uint32_t s_off[kDrorWords];
-    const std::uint32_t f = blockIdx.x;
+    const std::uint32_t f = blockIdx.x + d.f0;
     const std::uint32_t* mask = d.grid_mask + static_cast<std::size_t>(f) * kDrorWords;
     const std::uint32_t* cnt = d.grid_cnt + static_cast<std::size_t>(f) * kDrorCells;
     std::uint32_t* start = d.grid_start + static_cast<std::size_t>(f) * (kDrorCells + 1);
@@ -798,7 +798,7 @@ void launch_dror(Ctx* c, std::uint32_t nf, bool with_ring)
     Dev& d = c->d;
     if (!c->counters_cleared)
     {
-        cudaMemsetAsync(d.n_unres, 0, sizeof(std::uint32_t) * nf, c->stream);
+        cudaMemsetAsync(at_frame(d.n_unres, 1, d.f0), 0, sizeof(std::uint32_t) * nf, c->stream);
     }
     const dim3 grid((d.cap + 255) / 256, nf);
     if (with_ring)
@@ -806,7 +806,7 @@ void launch_dror(Ctx* c, std::uint32_t nf, bool with_ring)
         k_dror_near<true><<<grid, 256, 0, c->stream>>>(d, c->dror);
         mark(c, "front");
         k_ring_write<<<dim3(d.tiles, nf), kTileThreads, 0, c->stream>>>(RecordedPred{d.lab, d.cap}, d.n_in, d.wrap_cnt, d.tiles,
-                                                                         static_cast<std::uint32_t>(kTile / 32), d.ring, d.cap);
+                                                                         static_cast<std::uint32_t>(kTile / 32), d.ring, d.cap, d.f0);
         mark(c, "ring_write");
     }
     else
@@ -814,7 +814,7 @@ void launch_dror(Ctx* c, std::uint32_t nf, bool with_ring)
         k_dror_near<false><<<grid, 256, 0, c->stream>>>(d, c->dror);
         mark(c, "dror_near");
     }
-    cudaMemsetAsync(d.grid_mask, 0, sizeof(std::uint32_t) * (kDrorCells / 32) * nf, c->stream);
+    cudaMemsetAsync(at_frame(d.grid_mask, kDrorCells / 32, d.f0), 0, sizeof(std::uint32_t) * (kDrorCells / 32) * nf, c->stream);
     k_dror_mark<<<dim3(per_frame_ctas(8, nf, 256), nf), 256, 0, c->stream>>>(d, c->dror);
     mark(c, "dror_mark");
     k_dror_grid_count<<<grid, 256, 0, c->stream>>>(d);
@@ -823,7 +823,7 @@ void launch_dror(Ctx* c, std::uint32_t nf, bool with_ring)
     k_dror_grid_scan<<<nf, 1024, 0, c->stream>>>(d);
 #else
     k_excl_scan<<<nf, 1024, 0, c->stream>>>(d.grid_cnt, kDrorCells, d.grid_start, kDrorCells + 1, kDrorCells,
-                                            nullptr, nullptr);
+                                            nullptr, nullptr, d.f0);
 #endif
     mark(c, "dror_grid_scan");
     k_dror_grid_scatter<<<grid, 256, 0, c->stream>>>(d);

@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(256) k_seg_bin(Dev d, SegParams sp)
     // which a stable compaction of the VALID points would preserve - so the compaction (and the
     // index indirection it needs) is skipped; n_v only counts the valid points.
     __shared__ std::uint32_t s_valid;
-    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t f = blockIdx.y + d.f0;
     const std::uint32_t n = d.n_in[f];
     if (blockIdx.x * 256u >= n)
     {
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(256) k_seg_bin(Dev d, SegParams sp)
 // k_seg_cell and the rank selection of the RANSAC draws, neither of which needs cloud order
 __global__ void __launch_bounds__(256) k_seg_scatter(Dev d, SegParams sp)
 {
-    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t f = blockIdx.y + d.f0;
     const std::uint32_t n = d.n_in[f];
     const std::uint32_t i = blockIdx.x * 256u + threadIdx.x;
     if (i >= n)
@@ -476,7 +476,7 @@ __device__ __forceinline__ void seg_cell_one(const Dev& d, const SegParams& sp, 
 __global__ void __launch_bounds__(kCellWarps * 32) k_seg_cell(Dev d, SegParams sp)
 {
     __shared__ float sh[kCellWarps][kCellSmem];
-    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t f = blockIdx.y + d.f0;
     const std::uint32_t warp = threadIdx.x >> 5;
     // consecutive cells are radial neighbours of one slice (dense near the sensor, empty far out):
     // interleaving them over the warps keeps the warps of a CTA equally loaded. Lane j fetches the
@@ -508,7 +508,7 @@ __global__ void __launch_bounds__(kCellWarps * 32) k_seg_cell(Dev d, SegParams s
 // `+ delta` is not re-associable bit-exactly, so it stays sequential (50 steps).
 __global__ void __launch_bounds__(128) k_seg_elev(Dev d, SegParams sp)
 {
-    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t f = blockIdx.y + d.f0;
     const std::uint32_t s = blockIdx.x * 128u + threadIdx.x;
     if (s >= static_cast<std::uint32_t>(sp.slices))
     {
@@ -537,7 +537,7 @@ __global__ void __launch_bounds__(128) k_seg_elev(Dev d, SegParams sp)
 // image, so it is evaluated there (k_seg_px) and no per-point label plane exists.
 __global__ void __launch_bounds__(256) k_seg_label(Dev d, SegParams sp)
 {
-    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t f = blockIdx.y + d.f0;
     const std::uint32_t n = d.n_in[f];
     if (blockIdx.x * 256u >= n)
     {
@@ -641,7 +641,7 @@ __global__ void __launch_bounds__(kDrawThreads) k_ransac_draw(Dev d, SegParams s
 {
     __shared__ std::uint32_t sh[33];
     __shared__ std::uint32_t raws[kRawStage];
-    const std::uint32_t f = blockIdx.x;
+    const std::uint32_t f = blockIdx.x + d.f0;
     const std::uint32_t J = static_cast<std::uint32_t>(sp.slices) * sp.nb; // candidate cells in rank order
     std::uint32_t* ccnt = d.ccnt + static_cast<std::size_t>(f) * sp.ncell;
     for (std::uint32_t t = threadIdx.x; t < kRawStage; t += kDrawThreads)
@@ -705,7 +705,7 @@ __global__ void __launch_bounds__(64) k_ransac_plane(Dev d, SegParams sp)
 {
     __shared__ std::uint32_t sel[2][kSelCap];
     __shared__ std::uint32_t pidx[2];
-    const std::uint32_t it = blockIdx.x, f = blockIdx.y;
+    const std::uint32_t it = blockIdx.x, f = blockIdx.y + d.f0;
     const std::uint32_t nc = d.n_cand[f];
     const bool runit = nc >= 2;
     const std::size_t o = static_cast<std::size_t>(f) * d.cap;
@@ -846,7 +846,7 @@ __global__ void __launch_bounds__(256) k_ransac_count(Dev d, SegParams sp)
 {
     __shared__ float4 pl[kRansacIters];
     __shared__ std::uint32_t cnt[kRansacIters];
-    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t f = blockIdx.y + d.f0;
     const std::uint32_t nc = d.n_cpts[f]; // = n_cand, the dense copy is unordered
     const std::uint32_t base = blockIdx.x * (256u * kRansacPer);
     if (nc < 2 || base >= nc)
@@ -927,7 +927,7 @@ __global__ void __launch_bounds__(256) k_ransac_count(Dev d, SegParams sp)
 // count, flipped so that c >= 0. One warp per frame, once - not once per CTA of k_seg_px.
 __global__ void __launch_bounds__(32) k_ransac_best(Dev d)
 {
-    const std::uint32_t f = blockIdx.x;
+    const std::uint32_t f = blockIdx.x + d.f0;
     const std::uint32_t lane = lane_id();
     unsigned long long key = 0; // (count << 8) | (255 - iteration): maximum = largest count, earliest iteration
     if (d.n_cand[f] >= 2)
@@ -964,7 +964,7 @@ __global__ void __launch_bounds__(32) k_ransac_best(Dev d)
 
 __global__ void __launch_bounds__(256) k_seg_px(Dev d, SegParams sp)
 {
-    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t f = blockIdx.y + d.f0;
     const std::uint32_t p = blockIdx.x * 256u + threadIdx.x;
     if (p >= static_cast<std::uint32_t>(sp.npx))
     {
@@ -1048,7 +1048,7 @@ __global__ void __launch_bounds__(256) k_seg_dilate_tma(Dev d, SegParams sp, con
     __shared__ __align__(128) std::uint8_t raw[kDilTh + 4][kDilBoxW];
     __shared__ std::uint8_t hmax[kDilTh + 4][kDilTw + 4];
     __shared__ __align__(8) unsigned long long mbar;
-    const std::uint32_t f = blockIdx.z;
+    const std::uint32_t f = blockIdx.z + d.f0;
     const int h0 = blockIdx.y * kDilTh, w0 = blockIdx.x * kDilTw;
     const std::uint32_t mbar_s = static_cast<std::uint32_t>(__cvta_generic_to_shared(&mbar));
     if (threadIdx.x == 0)
@@ -1102,7 +1102,7 @@ __global__ void __launch_bounds__(256) k_seg_dilate(Dev d, SegParams sp)
 {
     __shared__ std::uint8_t tile[kDilTh + 4][kDilTw + 4 + 4];
     __shared__ std::uint8_t hmax[kDilTh + 4][kDilTw + 4];
-    const std::uint32_t f = blockIdx.z;
+    const std::uint32_t f = blockIdx.z + d.f0;
     const int h0 = blockIdx.y * kDilTh, w0 = blockIdx.x * kDilTw;
     const std::uint8_t* code = d.code + static_cast<std::size_t>(f) * sp.npx;
     for (int t = threadIdx.x; t < (kDilTh + 4) * (kDilTw + 4); t += 256)
@@ -1228,7 +1228,7 @@ __global__ void __launch_bounds__(128) k_jcp_pre(Dev d, SegParams sp)
 {
     __shared__ float s_w[128][25]; // raw weights of the CTA's 128 queued pixels (+1 pad: no bank conflicts)
     __shared__ float s_inv[128];   // the divisor (sum) or 0 when the pixel cannot be decided
-    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t f = blockIdx.y + d.f0;
     const std::uint32_t nq = min(d.n_queue[f], d.qcap);
     const std::size_t po = static_cast<std::size_t>(f) * sp.npx;
     const std::uint32_t* queue = d.queue + static_cast<std::size_t>(f) * d.qcap;
@@ -1395,7 +1395,7 @@ __global__ void __launch_bounds__(kJcpRowsThreads, LPL_JCP_ROWS_MINB) k_jcp_rows
     extern __shared__ std::uint32_t plane[]; // npx / 16 words, then row_start[H + 1]
     __shared__ unsigned long long s_tot[2][kJcpRowsThreads / 32];
     __shared__ std::uint32_t s_carry[2];
-    const std::uint32_t f = blockIdx.x;
+    const std::uint32_t f = blockIdx.x + d.f0;
     const std::size_t po = static_cast<std::size_t>(f) * sp.npx;
     std::uint8_t* code = d.code + po;
     const std::uint32_t nwords = (sp.npx + 15) / 16;
@@ -1674,7 +1674,7 @@ __global__ void __launch_bounds__(kJcpRowsThreads, LPL_JCP_ROWS_MINB) k_jcp_rows
 // populateLabels (segmenter.cpp:640-669): only pixel winners receive a label; optional BGR image
 __global__ void __launch_bounds__(256) k_seg_labels_out(Dev d, SegParams sp, int want_image)
 {
-    const std::uint32_t f = blockIdx.y;
+    const std::uint32_t f = blockIdx.y + d.f0;
     const std::uint32_t p = blockIdx.x * 256u + threadIdx.x;
     if (p >= static_cast<std::uint32_t>(sp.npx))
     {
@@ -1725,22 +1725,22 @@ void launch_segment(Ctx* c, std::uint32_t nf, bool want_image)
     const SegParams& sp = c->seg;
     cudaStream_t s = c->stream;
     // per-batch resets
-    cudaMemsetAsync(d.cell_cnt, 0, sizeof(std::uint32_t) * sp.ncell * nf, s);
-    cudaMemsetAsync(d.ccnt, 0, sizeof(std::uint32_t) * sp.ncell * nf, s);
-    cudaMemsetAsync(d.key, 0xff, sizeof(unsigned long long) * sp.npx * nf, s);
-    cudaMemsetAsync(d.labels_out, 0, static_cast<std::size_t>(d.cap) * nf, s);
+    cudaMemsetAsync(at_frame(d.cell_cnt, sp.ncell, d.f0), 0, sizeof(std::uint32_t) * sp.ncell * nf, s);
+    cudaMemsetAsync(at_frame(d.ccnt, sp.ncell, d.f0), 0, sizeof(std::uint32_t) * sp.ncell * nf, s);
+    cudaMemsetAsync(at_frame(d.key, sp.npx, d.f0), 0xff, sizeof(unsigned long long) * sp.npx * nf, s);
+    cudaMemsetAsync(at_frame(d.labels_out, d.cap, d.f0), 0, static_cast<std::size_t>(d.cap) * nf, s);
     if (!c->counters_cleared)
     {
-        cudaMemsetAsync(d.n_cpts, 0, sizeof(std::uint32_t) * nf, s);
-        cudaMemsetAsync(d.n_v, 0, sizeof(std::uint32_t) * nf, s);
-        cudaMemsetAsync(d.n_border, 0, sizeof(std::uint32_t) * nf, s);
+        cudaMemsetAsync(at_frame(d.n_cpts, 1, d.f0), 0, sizeof(std::uint32_t) * nf, s);
+        cudaMemsetAsync(at_frame(d.n_v, 1, d.f0), 0, sizeof(std::uint32_t) * nf, s);
+        cudaMemsetAsync(at_frame(d.n_border, 1, d.f0), 0, sizeof(std::uint32_t) * nf, s);
     }
 
     const dim3 gpts((d.cap + 255) / 256, nf);
     k_seg_bin<<<gpts, 256, 0, s>>>(d, sp);
     mark(c, "seg_bin");
     k_excl_scan<<<nf, 1024, 0, s>>>(d.cell_cnt, sp.ncell, d.cell_start, sp.ncell + 1,
-                                    static_cast<std::uint32_t>(sp.ncell), nullptr, d.n_binned);
+                                    static_cast<std::uint32_t>(sp.ncell), nullptr, d.n_binned, d.f0);
     mark(c, "seg_cell_scan");
     k_seg_scatter<<<gpts, 256, 0, s>>>(d, sp);
     mark(c, "seg_scatter");

@@ -746,22 +746,27 @@ def test_full_sequence_chained_with_dror_vs_reference():
         c.cluster_config(**NODE_CLUSTER_CFG)
         xyz = np.ascontiguousarray(np.concatenate(frames)[:, :3])
         nf = c.upload_packed_xyz(xyz, [f.shape[0] for f in frames])   # the bench's e2e upload path
-        c.run(nf, lpl.STAGE_ALL)
         bufs = lpl.PackedBuffers(nf, nf * 131072 * 8, want=("labels_u8", "noise", "cluster_labels", "hull_offsets",
                                                              "hull_xy", "zminmax"))
-        counts = c.download_packed(nf, bufs)
-        bad = []
-        for f, g in enumerate(gold):
-            ok = (counts[0, f] == g["n"] and counts[3, f] == g["clusters"] and counts[4, f] == g["hull_vertices"]
-                  and sha(bufs.frame("noise", f), np.uint8) == g["noise_sha1"]
-                  and sha(bufs.frame("labels_u8", f), np.uint8) == g["labels_sha1"]
-                  and sha(bufs.frame("cluster_labels", f), np.int32) == g["cluster_sha1"]
-                  and sha(bufs.frame("hull_offsets", f), np.uint32) == g["hull_offsets_sha1"]
-                  and sha(bufs.frame("hull_xy", f), np.float32) == g["hull_xy_sha1"]
-                  and sha(bufs.frame("zminmax", f), np.float32) == g["zminmax_sha1"])
-            if not ok:
-                bad.append(f)
-        assert not bad, bad
+        # one stream, then the batch as 3 and as 2 concurrent sub-batches (lpl_pipeline_use_split); every variant runs
+        # plainly (first run), as a freshly captured graph and as a replayed graph
+        for parts in (1, 3, 2):
+            c.use_split(parts)
+            for rep in range(3):
+                c.run(nf, lpl.STAGE_ALL)
+                counts = c.download_packed(nf, bufs)
+                bad = []
+                for f, g in enumerate(gold):
+                    ok = (counts[0, f] == g["n"] and counts[3, f] == g["clusters"] and counts[4, f] == g["hull_vertices"]
+                          and sha(bufs.frame("noise", f), np.uint8) == g["noise_sha1"]
+                          and sha(bufs.frame("labels_u8", f), np.uint8) == g["labels_sha1"]
+                          and sha(bufs.frame("cluster_labels", f), np.int32) == g["cluster_sha1"]
+                          and sha(bufs.frame("hull_offsets", f), np.uint32) == g["hull_offsets_sha1"]
+                          and sha(bufs.frame("hull_xy", f), np.float32) == g["hull_xy_sha1"]
+                          and sha(bufs.frame("zminmax", f), np.float32) == g["zminmax_sha1"])
+                    if not ok:
+                        bad.append(f)
+                assert not bad, (parts, rep, bad)
         bufs.close()
     finally:
         c.close()

@@ -22,6 +22,8 @@ def main():
         stages = lpl.STAGE_ALL & ~lpl.STAGE_RING if opts["stages"] in ("ringless", "ring_field") else lpl.STAGE_ALL
         ctx = bench.make_ctx_factory(lpl, 0, max(f.shape[0] for f in frames), opts["image_height"])(nf)
         ctx.upload(frames, rings=rings)
+        if os.environ.get("LPL_PARTS"):
+            ctx.use_split(int(os.environ["LPL_PARTS"]))
         for _ in range(5):
             ctx.run(nf, stages)
         ctx.sync(nf)
