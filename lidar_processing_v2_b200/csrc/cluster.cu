@@ -23,6 +23,12 @@
 
 namespace lpl
 {
+// k_clu_sph and k_clu_edges stride a fixed number of CTAs over a frame's points / voxels (kCluCtas tiles of 256 cover a
+// typical HDL-64E frame's obstacle points in one trip): a grid sized to the frame CAPACITY launched 60 - 90 % of its CTAs
+// only to read the count and leave (edges 0.134 -> 0.106 ms). k_clu_insert and k_clu_labels keep the capacity grid:
+// with the loop, the frames that need a second trip became the tail of the launch (labels 0.226 -> 0.262 ms).
+constexpr std::uint32_t kCluCtas = 224;
+
 __global__ void __launch_bounds__(256) k_clu_sph(Dev d)
 {
     __shared__ std::uint32_t smax[3];
@@ -37,11 +43,10 @@ __global__ void __launch_bounds__(256) k_clu_sph(Dev d)
         smax[threadIdx.x] = 0;
     }
     __syncthreads();
-    const std::uint32_t i = blockIdx.x * 256u + threadIdx.x;
     std::uint32_t br = 0, ba = 0, be = 0;
-    if (i < n)
+    const std::size_t o = static_cast<std::size_t>(f) * d.cap;
+    for (std::uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u)
     {
-        const std::size_t o = static_cast<std::size_t>(f) * d.cap;
         const float4 p = d.pts_o[o + i];
         float az = atan2f_glibc(p.y, p.x);
         az = (az < 0.f) ? (az + 6.28318530717958647692f) : az;
@@ -51,9 +56,9 @@ __global__ void __launch_bounds__(256) k_clu_sph(Dev d)
         const float el = atanf_glibc(p.z / dxy) + 1.57079632679489661923f;
         d.sph[o + i] = make_float4(range, az, el, 0.f);
         // non-negative floats order like their bit patterns; "+ 0.0f" folds -0.0 into +0.0
-        br = __float_as_uint(range + 0.0f);
-        ba = __float_as_uint(az + 0.0f);
-        be = __float_as_uint(el + 0.0f);
+        br = max(br, __float_as_uint(range + 0.0f));
+        ba = max(ba, __float_as_uint(az + 0.0f));
+        be = max(be, __float_as_uint(el + 0.0f));
     }
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1)
@@ -227,13 +232,11 @@ constexpr int kFwd = 13; // forward half of the 26-neighbourhood
 __global__ void __launch_bounds__(256) k_clu_edges(Dev d, ClusterParams cp)
 {
     const std::uint32_t f = blockIdx.y + d.f0;
-    const std::uint32_t v = blockIdx.x * 256u + threadIdx.x;
-    if (v >= d.n_vox[f])
-    {
-        return;
-    }
+    const std::uint32_t nvox = d.n_vox[f];
     const std::size_t o = static_cast<std::size_t>(f) * d.cap;
     const std::size_t ho = static_cast<std::size_t>(f) * d.hcap;
+    for (std::uint32_t v = blockIdx.x * 256u + threadIdx.x; v < nvox; v += gridDim.x * 256u)
+    {
     const std::uint32_t slot = d.vlist[o + v];
     const VoxelDims vd = voxel_dims(d, cp, f);
     const std::int32_t* keys = d.hkey + ho;
@@ -303,6 +306,7 @@ __global__ void __launch_bounds__(256) k_clu_edges(Dev d, ClusterParams cp)
         row[q] = nb;
     }
     d.hparent[ho + v] = v; // forest of the global path, indexed by voxel id
+    }
 }
 
 // parent[] is updated with atomics while other threads walk it. The walk halves the path as it
@@ -616,11 +620,11 @@ void launch_cluster(Ctx* c, std::uint32_t nf)
         c->hash_clean = true;
     }
     const dim3 g((d.cap + 255) / 256, nf);
-    k_clu_sph<<<g, 256, 0, s>>>(d);
+    k_clu_sph<<<dim3(std::min<std::uint32_t>((d.cap + 255) / 256, per_frame_ctas(kCluCtas, nf, 4096)), nf), 256, 0, s>>>(d);
     mark(c, "clu_sph");
     k_clu_insert<<<g, 256, 0, s>>>(d, c->clu);
     mark(c, "clu_insert");
-    k_clu_edges<<<g, 256, 0, s>>>(d, c->clu);
+    k_clu_edges<<<dim3(std::min<std::uint32_t>((d.cap + 255) / 256, per_frame_ctas(72, nf, 4096)), nf), 256, 0, s>>>(d, c->clu);
     mark(c, "clu_edges");
     cudaFuncSetAttribute(k_clu_union_sm, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          static_cast<int>(kUfSmemVoxels * sizeof(std::uint32_t)));
