@@ -118,6 +118,7 @@ void carve(Dev& d, Carver& cv, int npx, int ncell_cap, std::uint32_t** mt_raw)
     cv.take(d.best_cnt, B);
     cv.take(d.key, B * npx);
     cv.take(d.pxpt, B * npx);
+    cv.take(d.pxidx, B * npx);
     cv.take(d.code, B * npx);
     cv.take(d.queue, B * q);
     cv.take(d.n_queue, B);

@@ -488,24 +488,6 @@ __global__ void __launch_bounds__(256) k_clu_flatten(Dev d)
     }
 }
 
-// The hash planes (key / minimum point / count) are self-cleaning: once the cluster ids are ranked,
-// the slots of the frame's occupied voxels (~17k of 262k) are reset, instead of three full-table
-// memsets (484 MB per 154-frame batch) ahead of every run.
-__global__ void __launch_bounds__(256) k_clu_clean(Dev d)
-{
-    const std::uint32_t f = blockIdx.y + d.f0;
-    const std::uint32_t nvox = d.n_vox[f];
-    const std::size_t o = static_cast<std::size_t>(f) * d.cap;
-    const std::size_t ho = static_cast<std::size_t>(f) * d.hcap;
-    for (std::uint32_t v = blockIdx.x * 256u + threadIdx.x; v < nvox; v += gridDim.x * 256u)
-    {
-        const std::uint32_t slot = d.vlist[o + v];
-        d.hkey[ho + slot] = -1;
-        d.hmin[ho + slot] = 0xffffffffu;
-        d.hcount[ho + slot] = 0u;
-    }
-}
-
 struct ClusterRepPred
 {
     Dev d;
@@ -552,11 +534,22 @@ __global__ void __launch_bounds__(256) k_clu_labels(Dev d)
         return;
     }
     const std::size_t o = static_cast<std::size_t>(f) * d.cap;
+    const std::size_t ho = static_cast<std::size_t>(f) * d.hcap;
+    // The hash planes (key / minimum point / count) are self-cleaning: once the cluster ids are ranked (k_clu_rank is
+    // their last reader), the slots of the frame's occupied voxels (~17k of 262k) are reset - instead of three
+    // full-table memsets (484 MB per 154-frame batch) ahead of every run. There are at most as many voxels as points,
+    // so the threads of this launch cover them; the labels below only read hroot / hlabel.
+    if (i < d.n_vox[f])
+    {
+        const std::uint32_t slot = d.vlist[o + i];
+        d.hkey[ho + slot] = -1;
+        d.hmin[ho + slot] = 0xffffffffu;
+        d.hcount[ho + slot] = 0u;
+    }
     std::int32_t l = -1;
     float x = 0.f, y = 0.f, z = 0.f;
     if (i < n)
     {
-        const std::size_t ho = static_cast<std::size_t>(f) * d.hcap;
         const float4 p = d.pts_o[o + i]; // in flight while the three dependent look-ups below resolve
         l = d.hlabel[ho + d.hroot[ho + d.vslot[o + i]]];
         d.clabel[o + i] = l;
@@ -613,7 +606,7 @@ void launch_cluster(Ctx* c, std::uint32_t nf)
     }
     if (!c->hash_clean)
     {
-        // first use of this context: all frames' tables; afterwards k_clu_clean keeps them clean
+        // first use of this context: all frames' tables; afterwards k_clu_labels resets the used slots
         cudaMemsetAsync(d.hkey, 0xff, sizeof(std::int32_t) * static_cast<std::size_t>(d.hcap) * d.B, s);
         cudaMemsetAsync(d.hmin, 0xff, sizeof(std::uint32_t) * static_cast<std::size_t>(d.hcap) * d.B, s);
         cudaMemsetAsync(d.hcount, 0, sizeof(std::uint32_t) * static_cast<std::size_t>(d.hcap) * d.B, s);
@@ -640,8 +633,6 @@ void launch_cluster(Ctx* c, std::uint32_t nf)
     // d.lab (RECM labels of the segmenter) is free by now: it holds the recorded verdicts
     launch_compact_recorded(c, "clu_rank", nf, d.tiles, d.n_o, d.tile_cnt, d.n_clusters, d.lab,
                             ClusterRepPred{d, c->clu.min_cluster_size}, ClusterRepEmit{d});
-    k_clu_clean<<<gbig, 256, 0, s>>>(d);
-    mark(c, "clu_clean");
     k_clu_labels<<<g, 256, 0, s>>>(d);
     mark(c, "clu_labels");
 }

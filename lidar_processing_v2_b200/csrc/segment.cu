@@ -974,13 +974,18 @@ __global__ void __launch_bounds__(256) k_seg_px(Dev d, SegParams sp)
     const unsigned long long key = d.key[po + p];
     float4 v = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
     std::uint8_t c = PX_EMPTY;
+    std::int32_t widx = -1;
     if (key != ~0ULL)
     {
         const std::size_t o = static_cast<std::size_t>(f) * d.cap;
         const std::uint32_t i = static_cast<std::uint32_t>(key & ((1ULL << sp.idx_bits) - 1ULL));
         const float4 q = d.pts_in[o + i];
-        const std::int32_t cell = d.cell[o + i];
+        // the winner's polar cell without a gather: the azimuth slice rides in the key, the radial bin follows from the
+        // coordinates exactly as in k_seg_bin
+        const std::int32_t slice = static_cast<std::int32_t>((key & ((1ULL << 33) - 1ULL)) >> sp.idx_bits);
+        const std::int32_t cell = slice * sp.rings + static_cast<std::int32_t>(sqrtf(q.x * q.x + q.y * q.y) / sp.radial_spacing);
         v = make_float4(q.x, q.y, q.z, __int_as_float(static_cast<int>(i)));
+        widx = static_cast<std::int32_t>(i);
         // obstacle classification against the cell's elevation (segmenter.cpp:271-283), then the RANSAC plane over the
         // near-field bins (:455-477)
         const float e = d.elev[static_cast<std::size_t>(f) * sp.ncell + cell];
@@ -996,6 +1001,7 @@ __global__ void __launch_bounds__(256) k_seg_px(Dev d, SegParams sp)
         }
     }
     d.pxpt[po + p] = v;
+    d.pxidx[po + p] = widx; // dense copy of the winner index for k_seg_labels_out (4 B instead of a 16-byte record per pixel)
     d.code[po + p] = c;
 }
 
@@ -1360,26 +1366,52 @@ constexpr int kJcpRowsThreads = LPL_JCP_ROWS_THREADS;
 #ifndef LPL_JCP_ROWS_MINB
 #define LPL_JCP_ROWS_MINB 2 // CTAs per SM: a 154-frame batch must not spill into a second wave on 148 SMs
 #endif
-constexpr unsigned long long kJcpIdentityMap = 0x876543210ULL;
-
-// (later o earlier)[x] = later[earlier[x]] on maps of the nine states, 4 bits per state
-__device__ __forceinline__ unsigned long long jcp_compose(unsigned long long later, unsigned long long earlier)
+// A map on the nine states X = 3 * (outcome of entry q-2) + (outcome of entry q-1) is nine bytes: byte x of (r0, r1, r2)
+// is the image of state x. Composition is a table look-up of nine indices, which is what PRMT does: the indices of the
+// earlier map, packed four bits each, are the selector of a byte permute over the later map's bytes 0..7; index 8 sets
+// the selector's "replicate the sign" bit, which yields 0x00 from the table (all entries < 0x80) and 0xff from a
+// register of 0x80 bytes - the mask that lets the ninth entry in. ~16 instructions per composition (the 4-bit-packed
+// form of round 1 shifted and masked its way through nine entries: ~60, a third of the kernel's instructions).
+struct JcpMap
 {
-    const std::uint32_t lo = static_cast<std::uint32_t>(later), hi = static_cast<std::uint32_t>(later >> 32);
-    unsigned long long r = 0;
-#pragma unroll
-    for (int x = 0; x < 9; ++x)
-    {
-        const std::uint32_t idx = static_cast<std::uint32_t>(earlier >> (4 * x)) & 15u;
-        const std::uint32_t v = idx < 8u ? ((lo >> (4u * idx)) & 15u) : (hi & 15u);
-        r |= static_cast<unsigned long long>(v) << (4 * x);
-    }
+    std::uint32_t r0, r1, r2;
+};
+
+__device__ __forceinline__ std::uint32_t prmt(std::uint32_t a, std::uint32_t b, std::uint32_t sel)
+{
+    std::uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
     return r;
 }
 
-__device__ __forceinline__ std::uint32_t jcp_apply(unsigned long long map, std::uint32_t x)
+__device__ __forceinline__ JcpMap jcp_identity()
 {
-    return static_cast<std::uint32_t>(map >> (4u * x)) & 15u;
+    return JcpMap{0x03020100u, 0x07060504u, 0x00000008u};
+}
+
+// selector form of a map: n0 = the images of the states 0..7, four bits each; n1 = the image of state 8
+__device__ __forceinline__ void jcp_pack(const JcpMap& m, std::uint32_t& n0, std::uint32_t& n1)
+{
+    const std::uint32_t t0 = m.r0 | (m.r0 >> 4), t1 = m.r1 | (m.r1 >> 4);
+    n0 = prmt(t0, t1, 0x6420u);
+    n1 = m.r2;
+}
+
+// (later o earlier)[x] = later[earlier[x]]; the earlier map comes in selector form (e0, e1)
+__device__ __forceinline__ JcpMap jcp_compose(const JcpMap& later, std::uint32_t e0, std::uint32_t e1)
+{
+    const std::uint32_t l8 = prmt(later.r2, 0u, 0x0000u); // later[8] in every byte
+    const std::uint32_t k80 = 0x80808080u;
+    JcpMap r;
+    r.r0 = prmt(later.r0, later.r1, e0) | (prmt(k80, k80, e0) & l8);
+    r.r1 = prmt(later.r0, later.r1, e0 >> 16) | (prmt(k80, k80, e0 >> 16) & l8);
+    r.r2 = (prmt(later.r0, later.r1, e1) | (prmt(k80, k80, e1) & l8)) & 0xffu;
+    return r;
+}
+
+__device__ __forceinline__ std::uint32_t jcp_apply(const JcpMap& m, std::uint32_t x)
+{
+    return (x == 8u ? m.r2 : prmt(m.r0, m.r1, x)) & 0xffu;
 }
 
 struct JcpEntry
@@ -1393,7 +1425,7 @@ struct JcpEntry
 __global__ void __launch_bounds__(kJcpRowsThreads, LPL_JCP_ROWS_MINB) k_jcp_rows(Dev d, SegParams sp)
 {
     extern __shared__ std::uint32_t plane[]; // npx / 16 words, then row_start[H + 1]
-    __shared__ unsigned long long s_tot[2][kJcpRowsThreads / 32];
+    __shared__ JcpMap s_tot[2][kJcpRowsThreads / 32];
     __shared__ std::uint32_t s_carry[2];
     const std::uint32_t f = blockIdx.x + d.f0;
     const std::size_t po = static_cast<std::size_t>(f) * sp.npx;
@@ -1596,12 +1628,12 @@ __global__ void __launch_bounds__(kJcpRowsThreads, LPL_JCP_ROWS_MINB) k_jcp_rows
         {
             p_before = cur.p_before;
         }
-        unsigned long long map = kJcpIdentityMap;
+        JcpMap map = jcp_identity();
         if (cur.valid)
         {
             // slot 10 (pixel w - 2) is the previous entry when that is not the pixel w - 1
             const bool prev_is_w2 = p_before + 2u == cur.p;
-            map = 0;
+            std::uint32_t img[9];
 #pragma unroll
             for (int x = 0; x < 9; ++x)
             {
@@ -1613,17 +1645,23 @@ __global__ void __launch_bounds__(kJcpRowsThreads, LPL_JCP_ROWS_MINB) k_jcp_rows
                     const std::uint32_t s10 = (entry & 0x400u) ? (prev_is_w2 ? b : a) : 0u;
                     out = ((entry >> (s10 * 3u + s11)) & 1u) ? 2u : 1u;
                 }
-                map |= static_cast<unsigned long long>(b * 3u + out) << (4 * x);
+                img[x] = b * 3u + out;
             }
+            map.r0 = img[0] | (img[1] << 8) | (img[2] << 16) | (img[3] << 24);
+            map.r1 = img[4] | (img[5] << 8) | (img[6] << 16) | (img[7] << 24);
+            map.r2 = img[8];
         }
         // ---- inclusive scan of the maps over the warp, totals chained across the warps
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1)
         {
-            const unsigned long long earlier = __shfl_up_sync(0xffffffffu, map, off);
+            std::uint32_t n0, n1;
+            jcp_pack(map, n0, n1);
+            const std::uint32_t e0 = __shfl_up_sync(0xffffffffu, n0, off);
+            const std::uint32_t e1 = __shfl_up_sync(0xffffffffu, n1, off);
             if (lane >= static_cast<std::uint32_t>(off))
             {
-                map = jcp_compose(map, earlier);
+                map = jcp_compose(map, e0, e1);
             }
         }
         if (lane == 31u)
@@ -1683,10 +1721,10 @@ __global__ void __launch_bounds__(256) k_seg_labels_out(Dev d, SegParams sp, int
     const std::size_t po = static_cast<std::size_t>(f) * sp.npx;
     const std::size_t o = static_cast<std::size_t>(f) * d.cap;
     const std::uint8_t cfull = d.code[po + p];
+    const int idx = d.pxidx[po + p]; // issued together with the code byte
     const std::uint8_t c = cfull & 0xf;
     if (c == PX_GROUND || c == PX_OBSTACLE)
     {
-        const int idx = __float_as_int(d.pxpt[po + p].w);
         if (idx >= 0)
         {
             d.labels_out[o + idx] = c;
