@@ -101,6 +101,10 @@ int lpl_create(lpl_ctx** out, int device, uint32_t max_points, uint32_t max_fram
                int32_t image_height, int32_t image_width);
 void lpl_destroy(lpl_ctx* ctx);
 const char* lpl_last_error(const lpl_ctx* ctx);
+/* Device memory the context holds (one slab: every plane of every frame of the batch), in bytes. About 0.59 KB per
+ * point of capacity plus ~0.1 MB per frame of range-image, polar-grid and DROR-grid planes; stage-local scratch
+ * planes of equal element size share storage. */
+size_t lpl_device_bytes(const lpl_ctx* ctx);
 const char* lpl_version(void);
 
 /* ---- configuration (defaults = the reference's struct defaults) ------------------------ */

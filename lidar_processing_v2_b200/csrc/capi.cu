@@ -96,21 +96,19 @@ void carve(Dev& d, Carver& cv, int npx, int ncell_cap, std::uint32_t** mt_raw)
     cv.take(d.grid_start, B * (kDrorCells + 1));
     cv.take(d.grid_mask, B * (kDrorCells / 32));
     cv.take(d.grid_pts, B * cap);
-    cv.take(d.unres, B * cap);
+    cv.take(d.unres, B * cap);       // = slot = vslot = hfin (see below)
     cv.take(d.cell, B * cap);
-    cv.take(d.px, B * cap);
-    cv.take(d.slot, B * cap);
+    cv.take(d.px, B * cap);          // = vlist
     cv.take(d.cell_cnt, B * ncell_cap);
     cv.take(d.cell_start, B * (ncell_cap + 1));
     cv.take(d.n_binned, B);
-    cv.take(d.zo, B * cap);
-    cv.take(d.zsort, B * cap);
+    cv.take(d.zo, B * cap);          // = hstack
+    cv.take(d.zsort, B * cap);       // = hseg_cnt
     cv.take(d.ccnt, B * ncell_cap);
     cv.take(d.cell_zmin, B * ncell_cap);
     cv.take(d.elev, B * ncell_cap);
     cv.take(d.lab, B * cap);
     cv.take(d.n_cand, B);
-    cv.take(d.cpts, B * cap);
     cv.take(d.pairs, B * kRansacIters * 2);
     cv.take(d.planes, B * kRansacIters);
     cv.take(d.inliers, B * kRansacIters);
@@ -130,7 +128,6 @@ void carve(Dev& d, Carver& cv, int npx, int ncell_cap, std::uint32_t** mt_raw)
     cv.take(d.bgr, B * npx * 3);
     cv.take(d.pts_o, B * cap);
     cv.take(d.idx_o, B * cap);
-    cv.take(d.sph, B * cap);
     cv.take(d.hkey, B * h);
     cv.take(d.hparent, B * h);
     cv.take(d.hmin, B * h);
@@ -138,16 +135,11 @@ void carve(Dev& d, Carver& cv, int npx, int ncell_cap, std::uint32_t** mt_raw)
     cv.take(d.hlabel, B * h);
     cv.take(d.hroot, B * h);
     cv.take(d.hvid, B * h);
-    cv.take(d.edges, B * cap * 13);
-    cv.take(d.vslot, B * cap);
-    cv.take(d.vlist, B * cap);
+    cv.take(d.edges, B * cap * kEdgePitch); // = octa
     cv.take(d.clabel, B * cap);
     cv.take(d.ccount, B * cap);
     cv.take(d.cstart, B * (cap + 1));
-    cv.take(d.hsA, B * cap);
     cv.take(d.hsB, B * cap);
-    cv.take(d.hstack, B * 2 * cap);
-    cv.take(d.hfin, B * cap);
     cv.take(d.hcnt, B * cap);
     cv.take(d.hull_off, B * (cap + 1));
     cv.take(d.hull_idx, B * cap);
@@ -157,8 +149,6 @@ void carve(Dev& d, Carver& cv, int npx, int ncell_cap, std::uint32_t** mt_raw)
     cv.take(d.zmax_u, B * cap);
     cv.take(d.zzero, B * cap);
     cv.take(d.ext, B * cap * kExtDirs);
-    cv.take(d.octa, B * cap * kExtDirs);
-    cv.take(d.hseg_cnt, B * cap);
     cv.take(d.n_h, B);
     cv.take(d.hull_next, B);
     cv.take(d.hwk_off, B * (cap + 1));
@@ -166,7 +156,6 @@ void carve(Dev& d, Carver& cv, int npx, int ncell_cap, std::uint32_t** mt_raw)
     cv.take(d.n_work, B);
     cv.take(d.n_multi, B);
     cv.take(d.boxes, B * cap);
-    cv.take(d.raw, B * cap * kRawRecord);
     cv.take(d.raw_desc, B * 32);
     const std::size_t tl = std::max<std::size_t>(d.tiles, d.ptiles);
     cv.take(d.tile_cnt, B * tl);
@@ -185,6 +174,28 @@ void carve(Dev& d, Carver& cv, int npx, int ncell_cap, std::uint32_t** mt_raw)
     d.ctr_begin = cv.base != nullptr ? reinterpret_cast<unsigned char*>(cv.base) + ctr_first : nullptr;
     d.ctr_bytes = cv.off - ctr_first;
     cv.take(*mt_raw, kMtRaws);
+    // Stage-local scratch shares storage. A frame's chain runs its stages in order (S1 DROR, S2 segmentation, S3
+    // clustering, S4 hulls), and every pair below has the same element size AND the same per-frame stride, so frame f
+    // of one plane is frame f of the other: safe for sub-batches of one run that are at different stages, and for the
+    // stage entry points, which use these planes as scratch only.
+    //   16 B / point: grid_pts (S1) = cpts (S2) = sph (S3) = hsA (S4)
+    //    4 B / point: unres (S1) = slot (S2) = vslot (S3) = hfin (S4);  px (S2) = vlist (S3);  zsort (S2) = hseg_cnt (S4)
+    //    8 B / point: zo (S2) = hstack (S4)
+    //   64 B / point: edges (S3, rows of 13 padded to 16) = octa (S4) = raw (the 32 B / point staging of the packed
+    //                 uploads and downloads and of raw PointCloud2 records: consumed before / filled after a run)
+    d.cpts = d.grid_pts;
+    d.sph = d.grid_pts;
+    d.hsA = reinterpret_cast<uint4*>(d.grid_pts);
+    d.slot = d.unres;
+    d.vslot = d.unres;
+    d.hfin = d.unres;
+    d.vlist = d.px;
+    d.hstack = reinterpret_cast<std::uint32_t*>(d.zo);
+    d.hseg_cnt = reinterpret_cast<std::uint32_t*>(d.zsort);
+    d.octa = reinterpret_cast<float2*>(d.edges);
+    d.raw = reinterpret_cast<unsigned char*>(d.edges);
+    static_assert(kRawRecord <= kEdgePitch * sizeof(std::uint32_t), "the raw-record staging fits the edge plane");
+    static_assert(kEdgePitch * sizeof(std::uint32_t) == kExtDirs * sizeof(float2) || kExtDirs != 8, "edges and octa share a plane");
 }
 
 void drop_graphs(lpl_ctx* ctx)
@@ -639,6 +650,8 @@ void lpl_destroy(lpl_ctx* ctx)
 }
 
 const char* lpl_last_error(const lpl_ctx* ctx) { return ctx != nullptr ? ctx->c.err : "null context"; }
+
+size_t lpl_device_bytes(const lpl_ctx* ctx) { return ctx != nullptr ? ctx->c.slab_bytes : 0; }
 
 int lpl_segmenter_config(lpl_ctx* ctx, const lpl_segmenter_cfg* cfg)
 {

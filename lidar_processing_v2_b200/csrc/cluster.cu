@@ -222,7 +222,7 @@ constexpr std::uint32_t kUfSmemVoxels = 24576; // occupied voxels per frame the 
 #define LPL_UF_THREADS 1024 // measured: 512 -> 0.25 ms, 256 -> 0.42 ms, 1024 -> 0.19 ms per 154-frame batch
 #endif
 constexpr int kUfThreads = LPL_UF_THREADS;
-constexpr int kFwd = 13; // forward half of the 26-neighbourhood
+constexpr int kFwd = 13; // forward half of the 26-neighbourhood (rows of kEdgePitch = 16 words: the plane doubles as hull.cu's octagon plane)
 
 // Occupied voxels are numbered by their position in the frame's voxel list ("voxel id").
 // k_clu_edges (one thread per voxel, whole GPU): the 26-neighbourhood is symmetric (also across
@@ -279,7 +279,12 @@ __global__ void __launch_bounds__(256) k_clu_edges(Dev d, ClusterParams cp)
     {
         found[q] = key2[q] >= 0 ? keys[slot2[q]] : -1;
     }
-    std::uint32_t* row = d.edges + (o + v) * kFwd;
+    std::uint32_t* row = d.edges + (o + v) * kEdgePitch;
+#pragma unroll
+    for (int q = kFwd; q < kEdgePitch; ++q)
+    {
+        row[q] = 0xffffffffu; // padding reads as "no neighbour"
+    }
 #pragma unroll
     for (int q = 0; q < kFwd; ++q)
     {
@@ -386,19 +391,19 @@ __global__ void __launch_bounds__(kUfThreads) k_clu_union_sm(Dev d)
         par[v] = v;
     }
     __syncthreads();
-    const std::uint32_t* edges = d.edges + o * kFwd;
+    const std::uint32_t* edges = d.edges + o * kEdgePitch;
     // the next edge word is in flight while the current one is united (a single frame has one CTA walking ~220k edge
     // words: without this every trip waits for its own load)
-    std::uint32_t u_next = threadIdx.x < nv * kFwd ? edges[threadIdx.x] : 0xffffffffu;
-    for (std::uint32_t e = threadIdx.x; e < nv * kFwd; e += kUfThreads)
+    std::uint32_t u_next = threadIdx.x < nv * kEdgePitch ? edges[threadIdx.x] : 0xffffffffu;
+    for (std::uint32_t e = threadIdx.x; e < nv * kEdgePitch; e += kUfThreads)
     {
         const std::uint32_t u = u_next;
-        u_next = e + kUfThreads < nv * kFwd ? edges[e + kUfThreads] : 0xffffffffu;
+        u_next = e + kUfThreads < nv * kEdgePitch ? edges[e + kUfThreads] : 0xffffffffu;
         if (u == 0xffffffffu)
         {
             continue;
         }
-        std::uint32_t a = e / kFwd, b = u;
+        std::uint32_t a = e / kEdgePitch, b = u;
         while (true)
         {
             a = uf_find_sm(par, a);
@@ -440,7 +445,7 @@ __global__ void __launch_bounds__(256) k_clu_union(Dev d)
     std::uint32_t* parent = d.hparent + static_cast<std::size_t>(f) * d.hcap;
     for (std::uint32_t v = blockIdx.x * 256u + threadIdx.x; v < nvox; v += gridDim.x * 256u)
     {
-    const std::uint32_t* row = d.edges + (o + v) * kFwd;
+    const std::uint32_t* row = d.edges + (o + v) * kEdgePitch;
     for (int q = 0; q < kFwd; ++q)
     {
         const std::uint32_t u = row[q];

@@ -116,6 +116,8 @@ inline std::size_t pack_payload_start(std::uint32_t nf)
 
 // All device buffers of a context. Pointers are to the start of frame 0; frame f lives at
 // ptr + f * stride (stride noted per field).
+constexpr int kEdgePitch = 16; // words per voxel row of Dev::edges (13 forward neighbours + padding): 64 bytes, as a row of Dev::octa
+
 struct Dev
 {
     std::uint32_t cap;    // points per frame (multiple of kTile)
@@ -190,7 +192,7 @@ struct Dev
     std::int32_t* hlabel;     // [B][hcap] final label per root
     std::uint32_t* hroot;     // [B][hcap] root slot per occupied voxel
     std::uint32_t* hvid;      // [B][hcap] position of the slot in the frame's voxel list
-    std::uint32_t* edges;     // [B][cap][13] voxel ids of the occupied forward neighbours (or ~0)
+    std::uint32_t* edges;     // [B][cap][16] voxel ids of the 13 occupied forward neighbours (or ~0), rows padded to kEdgePitch
     std::uint32_t* vslot;     // [B][cap]  voxel slot per point
     std::uint32_t* vlist;     // [B][cap]  slots of the occupied voxels (unordered)
     std::uint32_t* n_vox;     // [B]

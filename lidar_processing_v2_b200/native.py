@@ -38,7 +38,7 @@ EXPORTS = [
     "lpl_cluster_hulls", "lpl_bounding_boxes", "lpl_vehicle_match",
     "lpl_pipeline_upload", "lpl_pipeline_upload_device", "lpl_pipeline_upload_cloud2", "lpl_pipeline_upload_packed",
     "lpl_pipeline_upload_packed_xyz", "lpl_pcd_read",
-    "lpl_pipeline_run", "lpl_pipeline_use_graph", "lpl_pipeline_use_split", "lpl_pipeline_sync", "lpl_pipeline_status", "lpl_pipeline_download_packed",
+    "lpl_device_bytes", "lpl_pipeline_run", "lpl_pipeline_use_graph", "lpl_pipeline_use_split", "lpl_pipeline_sync", "lpl_pipeline_status", "lpl_pipeline_download_packed",
     "lpl_pipeline_split_clouds", "lpl_glibc_rand_stream",
     "lpl_knn_build", "lpl_knn_token", "lpl_knn_k_nearest", "lpl_knn_radius_search",
     "lpl_pipeline_want_image", "lpl_pipeline_counts", "lpl_pipeline_download",
@@ -265,6 +265,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     L.lpl_pipeline_run.argtypes = [vp, u32, u32]
     L.lpl_pipeline_use_graph.argtypes = [vp, C.c_int]
     L.lpl_pipeline_use_graph.restype = C.c_int
+    L.lpl_device_bytes.argtypes = [vp]
+    L.lpl_device_bytes.restype = sz
     L.lpl_pipeline_use_split.argtypes = [vp, u32]
     L.lpl_pipeline_use_split.restype = C.c_int
     L.lpl_pipeline_sync.argtypes = [vp, u32]
@@ -614,6 +616,10 @@ class Context:
 
     def use_graph(self, enable: bool):
         self._chk(self.lib.lpl_pipeline_use_graph(self.h, 1 if enable else 0))
+
+    def device_bytes(self) -> int:
+        """Device memory held by the context (lpl_device_bytes)."""
+        return int(self.lib.lpl_device_bytes(self.h))
 
     def use_split(self, parts: int):
         """Sub-batches of one run on concurrent streams (lpl_pipeline_use_split)."""

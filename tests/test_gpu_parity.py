@@ -28,6 +28,13 @@ def _assert_parity(rep):
     assert not bad and rep.get("seg_status", 0) == 0, rep
 
 
+def test_device_footprint(ctx):
+    # one slab per context; stage-local scratch planes share storage (capi.cu: carve): < 0.7 KB per point of capacity
+    # including the per-frame range-image / polar-grid / DROR-grid planes (0.75 KB in round 1)
+    per_point = ctx.device_bytes() / (8 * 131072)
+    assert 300 < per_point < 700, per_point
+
+
 def test_native_library_is_the_path(ctx):
     # the extension in-tree is what runs: kernels were launched by this context
     ctx.launch_count(reset=True)
