@@ -235,7 +235,7 @@ def algorithmic_bytes(name: str, s: dict) -> float:
         "seg_cell": 8 * NB + 8 * CELLS, "seg_elev": 12 * CELLS,
         "seg_label": (16 + 4) * N + 16 * C,
         "ransac_draw": 1024 * F + 8 * CELLS, "ransac_plane": 120 * 64 * F, "ransac_count": 16 * C,
-        "seg_px": 8 * PX + 20 * min(PX, NB) + 17 * PX,
+        "seg_px": 8 * PX + 16 * min(PX, NB) + 21 * PX,
         "seg_dilate": 2 * PX, "jcp_queue": 2 * PX + 4 * Q,
         # the 5 x 5 neighbourhoods of queued pixels overlap: ~4 distinct pixel records (16 B point + 1 B code) are
         # fetched per queued pixel (ncu dram__bytes: profiles/traffic.json), 104 B of weights + masks are written

@@ -172,7 +172,8 @@ __global__ void __launch_bounds__(256)
     for (int t = threadIdx.x; t < 256 + 2 * kNearHalo; t += 256)
     {
         const long long gi = static_cast<long long>(base) + t - kNearHalo;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        // beyond the ends of the cloud: NaN, within() of nothing - the neighbour loop needs no bounds tests
+        float4 v = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);
         if (gi >= 0 && gi < static_cast<long long>(n))
         {
             v = pts[gi];
@@ -205,14 +206,8 @@ __global__ void __launch_bounds__(256)
         {
             if (!done)
             {
-                if (i >= static_cast<std::uint32_t>(o))
-                {
-                    cnt += dror_within(p, sh[threadIdx.x + kNearHalo - o], r_sqr) ? 1u : 0u;
-                }
-                if (i + o < n)
-                {
-                    cnt += dror_within(p, sh[threadIdx.x + kNearHalo + o], r_sqr) ? 1u : 0u;
-                }
+                cnt += dror_within(p, sh[threadIdx.x + kNearHalo - o], r_sqr) ? 1u : 0u;
+                cnt += dror_within(p, sh[threadIdx.x + kNearHalo + o], r_sqr) ? 1u : 0u;
                 // on a continuous surface the two nearest scan neighbours on each side already settle the point
                 done = cnt >= prm.min_neighbours;
             }
