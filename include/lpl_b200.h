@@ -231,7 +231,7 @@ int lpl_pipeline_run(lpl_ctx* ctx, uint32_t num_frames, uint32_t stages);
  * latency; several contexts rotating on one GPU (stream.py: FramePipeline) interleave better kernel by kernel
  * and switch it off. */
 int lpl_pipeline_use_graph(lpl_ctx* ctx, int enable);
-/* Sub-batches: lpl_pipeline_run cuts a batch of >= 16 frames into `parts` (1..8) contiguous sub-batches whose chains
+/* Sub-batches: lpl_pipeline_run cuts a batch of >= 4 frames into `parts` (1..8) contiguous sub-batches whose chains
  * run on concurrent streams (parallel branches of the captured graph), so that the one-CTA-per-frame kernels of one
  * sub-batch (JCP row sweep, union-find, scans) overlap the per-point kernels of another. Frames are independent
  * (segmenter.cpp:73-85, clusterer.cpp:104-106), the results do not change. Default: environment LPL_SPLIT, else 2

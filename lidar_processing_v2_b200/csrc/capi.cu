@@ -994,7 +994,7 @@ static int enqueue_chain(lpl_ctx* ctx, Ctx& c, std::uint32_t nf, std::uint32_t s
 // SMs it leaves idle. Every kernel takes its frame as blockIdx + Dev::f0, so a sub-batch is the same launch with a
 // smaller grid and a frame offset; all per-frame state is disjoint. Not while the per-kernel profile is on (its
 // events time one stream).
-constexpr std::uint32_t kSplitMinFrames = 16;
+constexpr std::uint32_t kSplitMinFrames = 4;
 
 static int enqueue_stages(lpl_ctx* ctx, std::uint32_t nf, std::uint32_t stages)
 {
