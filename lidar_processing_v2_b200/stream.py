@@ -52,10 +52,12 @@ class FramePipeline:
     def __init__(self, device: int, max_points: int, batch: int, stages: int = _n.STAGE_ALL,
                  cluster_cfg: dict | None = None, want=("labels_u8", "cluster_labels", "hull_offsets", "hull_xy",
                                                          "zminmax"), n_ctx: int = 2,
-                 image_height: int = 64, packed_results: bool = True, result_bytes_per_point: int = 8):
+                 image_height: int = 64, packed_results: bool = True, result_bytes_per_point: int = 8,
+                 graph: bool | None = None, split: int | None = None):
         """`want`: result planes that come back (obstacle_index is derivable on the host: the ascending positions
         of label 2). packed_results: one D2H transfer per batch of exactly the occupied bytes
-        (lpl_pipeline_download_packed) instead of one strided copy per plane."""
+        (lpl_pipeline_download_packed) instead of one strided copy per plane. graph / split: override the per-context
+        CUDA-graph replay and sub-batch count (defaults: graph replay on, no sub-batches in a rotation)."""
         if n_ctx < 1:
             raise ValueError("n_ctx must be >= 1")
         self.stages = stages
@@ -64,10 +66,12 @@ class FramePipeline:
         self.ctx = [_n.Context(device, max_points=max_points, max_frames=batch, image_height=image_height)
                     for _ in range(n_ctx)]
         for c in self.ctx:
-            # several streams rotating on one GPU overlap best kernel by kernel: a whole-chain graph per batch
-            # measured ~5 % slower end to end than plain launches (and ~2 % faster for one stream working alone)
-            c.use_graph(n_ctx == 1)
-            if n_ctx > 1:
+            # whole-chain graph per batch: +2 % for one stream working alone; in a rotation of four it measured -5 %
+            # early in round 2 and +1 % with the final kernels (tools/e2e_sweep.py: 36.25k vs 35.89k frames/s) - on
+            c.use_graph(True if graph is None else bool(graph))
+            if split is not None:
+                c.use_split(int(split))
+            elif n_ctx > 1:
                 c.use_split(1)  # the rotation already overlaps whole batches (measured: 36.9k vs 36.7k frames/s with 2 sub-batches)
             if image_height != 64:
                 cfg = c.segmenter_default_cfg()
