@@ -235,11 +235,11 @@ def algorithmic_bytes(name: str, s: dict) -> float:
         "seg_cell": 8 * NB + 8 * CELLS, "seg_elev": 12 * CELLS,
         "seg_label": (16 + 4) * N + 16 * C,
         "ransac_draw": 1024 * F + 8 * CELLS, "ransac_plane": 120 * 64 * F, "ransac_count": 16 * C,
-        "seg_px": 8 * PX + 16 * min(PX, NB) + 21 * PX,
+        "seg_px": 8 * PX + 16 * min(PX, NB) + 5 * PX,
         "seg_dilate": 2 * PX, "jcp_queue": 2 * PX + 4 * Q,
-        # the 5 x 5 neighbourhoods of queued pixels overlap: ~4 distinct pixel records (16 B point + 1 B code) are
+        # the 5 x 5 neighbourhoods of queued pixels overlap: ~4 distinct pixels (4 B index + 16 B point + 1 B code) are
         # fetched per queued pixel (ncu dram__bytes: profiles/traffic.json), 104 B of weights + masks are written
-        "jcp_pre": min(PX, 4 * Q) * 17 + Q * (24 * 4 + 8),
+        "jcp_pre": min(PX, 4 * Q) * (4 + 16 + 1) + Q * (24 * 4 + 8),
         "jcp_rows": PX * 1 + Q * (8 + 4 + 96) + Q * 1,
         "seg_labels_out": PX * (1 + 4) + 1 * NB,
         "take_obstacles": 1 * N + 16 * M + 20 * M,

@@ -115,7 +115,6 @@ void carve(Dev& d, Carver& cv, int npx, int ncell_cap, std::uint32_t** mt_raw)
     cv.take(d.best_plane, B);
     cv.take(d.best_cnt, B);
     cv.take(d.key, B * npx);
-    cv.take(d.pxpt, B * npx);
     cv.take(d.pxidx, B * npx);
     cv.take(d.code, B * npx);
     cv.take(d.queue, B * q);

@@ -166,8 +166,7 @@ struct Dev
     float4* best_plane;       // [B]  (a, b, c, d); w component of [B + f] unused
     std::uint32_t* best_cnt;  // [B]
     unsigned long long* key;  // [B][npx]  (depth_sqr bits << 33) | (azimuth slice << idx_bits) | point index
-    float4* pxpt;             // [B][npx]  x, y, z, point index (int bits; -1 = none)
-    std::int32_t* pxidx;      // [B][npx]  the point index alone (-1 = none)
+    std::int32_t* pxidx;      // [B][npx]  the range image: index of the pixel's winner in the input cloud (-1 = none)
     std::uint8_t* code;       // [B][npx]  PX_* before / after JCP
     std::uint32_t* queue;     // [B][qcap] queued pixels in raster order
     std::uint32_t* n_queue;   // [B]

@@ -972,7 +972,6 @@ __global__ void __launch_bounds__(256) k_seg_px(Dev d, SegParams sp)
     }
     const std::size_t po = static_cast<std::size_t>(f) * sp.npx;
     const unsigned long long key = d.key[po + p];
-    float4 v = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
     std::uint8_t c = PX_EMPTY;
     std::int32_t widx = -1;
     if (key != ~0ULL)
@@ -984,7 +983,6 @@ __global__ void __launch_bounds__(256) k_seg_px(Dev d, SegParams sp)
         // coordinates exactly as in k_seg_bin
         const std::int32_t slice = static_cast<std::int32_t>((key & ((1ULL << 33) - 1ULL)) >> sp.idx_bits);
         const std::int32_t cell = slice * sp.rings + static_cast<std::int32_t>(sqrtf(q.x * q.x + q.y * q.y) / sp.radial_spacing);
-        v = make_float4(q.x, q.y, q.z, __int_as_float(static_cast<int>(i)));
         widx = static_cast<std::int32_t>(i);
         // obstacle classification against the cell's elevation (segmenter.cpp:271-283), then the RANSAC plane over the
         // near-field bins (:455-477)
@@ -1000,8 +998,7 @@ __global__ void __launch_bounds__(256) k_seg_px(Dev d, SegParams sp)
             }
         }
     }
-    d.pxpt[po + p] = v;
-    d.pxidx[po + p] = widx; // dense copy of the winner index for k_seg_labels_out (4 B instead of a 16-byte record per pixel)
+    d.pxidx[po + p] = widx; // the range image proper: the winner's index (k_jcp_pre gathers coordinates through it, k_seg_labels_out labels through it)
     d.code[po + p] = c;
 }
 
@@ -1191,17 +1188,20 @@ struct QueueEmit
 // pixel that precedes this one in raster order (slots 0..11 only).
 // mk bit 48: the pixel can be decided (|sum| > FLT_EPSILON); bits 49..63: 1 + row of stale_ref.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void jcp_slot(const Dev& d, const SegParams& sp, std::size_t po, const float4& core,
+__device__ __forceinline__ void jcp_slot(const Dev& d, const SegParams& sp, std::size_t po, std::size_t o, const float4& core,
                                          int hh, int ww, int i, float& wgt, std::uint32_t& msk)
 {
     const std::uint32_t np = static_cast<std::uint32_t>(hh * sp.W + ww);
-    const float4 q = d.pxpt[po + np];
+    // the range image holds point indices; the coordinates come from the cloud itself (a per-pixel copy of them cost
+    // 323 MB of writes per batch for the ~7 % of the pixels whose neighbourhoods are ever read)
+    const std::int32_t qi = d.pxidx[po + np];
     wgt = 0.f;
     msk = 0;
-    if (__float_as_int(q.w) < 0)
+    if (qi < 0)
     {
         return;
     }
+    const float4 q = d.pts_in[o + static_cast<std::uint32_t>(qi)];
     const float dx = core.x - q.x;
     const float dy = core.y - q.y;
     const float dz = core.z - q.z;
@@ -1245,7 +1245,8 @@ __global__ void __launch_bounds__(128) k_jcp_pre(Dev d, SegParams sp)
     const bool live = blk * 128u + threadIdx.x < nq;
     const std::uint32_t p = queue[k];
     const int h = static_cast<int>(p / sp.W), w = static_cast<int>(p % sp.W);
-    const float4 core = d.pxpt[po + p];
+    const std::size_t o = static_cast<std::size_t>(f) * d.cap;
+    const float4 core = d.pts_in[o + static_cast<std::uint32_t>(d.pxidx[po + p])]; // a queued pixel has a winner
     float* wn = d.wn + static_cast<std::size_t>(f) * 24 * d.qcap;
     unsigned long long mk = 0;
     std::uint32_t brow = 0; // 1 + stale_ref row once allocated
@@ -1258,7 +1259,7 @@ __global__ void __launch_bounds__(128) k_jcp_pre(Dev d, SegParams sp)
         std::uint32_t msk = 0;
         if (hh >= 0 && hh < sp.H && ww >= 0 && ww < sp.W)
         {
-            jcp_slot(d, sp, po, core, hh, ww, i, wgt, msk);
+            jcp_slot(d, sp, po, o, core, hh, ww, i, wgt, msk);
             if (wgt != 0.f)
             {
                 sum += wgt;
@@ -1274,7 +1275,7 @@ __global__ void __launch_bounds__(128) k_jcp_pre(Dev d, SegParams sp)
                 const int hh2 = h2 + c_off_h[i], ww2 = w2 + c_off_w[i];
                 if (hh2 >= 0 && hh2 < sp.H && ww2 >= 0 && ww2 < sp.W)
                 {
-                    jcp_slot(d, sp, po, d.pxpt[po + pp], hh2, ww2, i, wgt, msk);
+                    jcp_slot(d, sp, po, o, d.pts_in[o + static_cast<std::uint32_t>(d.pxidx[po + pp])], hh2, ww2, i, wgt, msk);
                     if (msk == 3)
                     {
                         if (brow == 0 && live)
