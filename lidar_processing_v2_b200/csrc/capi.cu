@@ -929,6 +929,41 @@ int lpl_pipeline_upload_cloud2(lpl_ctx* ctx, const lpl_cloud2_frame* frames, std
     return LPL_OK;
 }
 
+// streams and events of the sub-batches (created outside any stream capture: lpl_pipeline_run calls this first)
+static bool ensure_split_resources(lpl_ctx* ctx, std::uint32_t parts)
+{
+    while (ctx->aux.size() + 1 < parts)
+    {
+        lpl_ctx::Aux a{};
+        if (cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&a.done, cudaEventDisableTiming) != cudaSuccess)
+        {
+            cudaGetLastError();
+            if (a.stream != nullptr)
+            {
+                cudaStreamDestroy(a.stream);
+            }
+            return false;
+        }
+        try
+        {
+            ctx->aux.push_back(a);
+        }
+        catch (...)
+        {
+            cudaEventDestroy(a.done);
+            cudaStreamDestroy(a.stream);
+            return false;
+        }
+    }
+    if (ctx->fork_ev == nullptr && cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return false;
+    }
+    return true;
+}
+
 // one pass of the selected stages over the frames [c.d.f0, c.d.f0 + nf) on c.stream (c: the context itself or the
 // view of one sub-batch, see enqueue_stages)
 static int enqueue_chain(lpl_ctx* ctx, Ctx& c, std::uint32_t nf, std::uint32_t stages)
@@ -1020,34 +1055,8 @@ static int enqueue_stages(lpl_ctx* ctx, std::uint32_t nf, std::uint32_t stages)
     {
         parts = 1; // (the first run of a context clears whole hash planes: one stream)
     }
-    while (parts > 1 && ctx->aux.size() < parts - 1)
+    if (parts > 1 && !ensure_split_resources(ctx, parts))
     {
-        lpl_ctx::Aux a{};
-        if (cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaEventCreateWithFlags(&a.done, cudaEventDisableTiming) != cudaSuccess)
-        {
-            cudaGetLastError();
-            if (a.stream != nullptr)
-            {
-                cudaStreamDestroy(a.stream);
-            }
-            parts = 1;
-            break;
-        }
-        try
-        {
-            ctx->aux.push_back(a);
-        }
-        catch (...)
-        {
-            cudaEventDestroy(a.done);
-            cudaStreamDestroy(a.stream);
-            parts = 1;
-        }
-    }
-    if (parts > 1 && ctx->fork_ev == nullptr && cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming) != cudaSuccess)
-    {
-        cudaGetLastError();
         parts = 1;
     }
     if (parts <= 1)
@@ -1123,6 +1132,10 @@ int lpl_pipeline_run(lpl_ctx* ctx, std::uint32_t nf, std::uint32_t stages)
     }
     Ctx& c = ctx->c;
     LPL_TRY(cudaSetDevice(c.device));
+    if (ctx->split_parts > 1 && nf >= kSplitMinFrames)
+    {
+        ensure_split_resources(ctx, ctx->split_parts); // not inside a capture; enqueue_stages falls back to one stream without them
+    }
     const bool ring_stage = (stages & LPL_STAGE_RING) != 0;
     const unsigned long long key = (static_cast<unsigned long long>(nf) << 32) | (static_cast<unsigned long long>(stages & 0xffffu) << 8) |
                                    (ctx->want_image ? 1u : 0u) | (ctx->have_ring ? 2u : 0u) | (ring_stage ? 4u : 0u);

@@ -8,7 +8,9 @@
 //                   min_neighbours) — the reference's KD-tree early exit leaves a stale traversal
 //                   stack whose effect depends on nth_element's tree shape (hazard H1).
 //
-// Both stages are HBM-bound streaming kernels over float4 points (16 B/pt in, 2 B or 1 B out).
+// One scan-line pass over float4 points settles ~95 % of an organised sweep and the ring wrap flags (16 B/pt in,
+// 4 B out); the rest are searched exactly in a two-level grid built from the points near them, the queries taken in
+// grid order (k_dror_query).
 #include "common.cuh"
 
 namespace lpl

@@ -2,10 +2,12 @@
 //
 // Reference: lidar_processing_lib/src/segmenter.cpp
 //   constructPolarGrid :103-204   -> k_seg_bin, k_excl_scan, k_seg_scatter, k_seg_cell
-//   RECM               :206-283   -> k_seg_cell (robust per-cell minimum), k_seg_elev, k_seg_label
-//   RANSAC             :321-479   -> candidate flags (k_seg_label), k_ransac_draw, k_ransac_plane,
-//                                    k_ransac_count
-//   image scatter      :291-318   -> 64-bit atomicMin keys (issued by k_seg_scatter), k_seg_px (winner decode + its label)
+//   RECM               :206-283   -> k_seg_cell (robust per-cell minimum), k_seg_elev; the obstacle test itself is
+//                                    evaluated for the pixel winners only (k_seg_px)
+//   RANSAC             :321-479   -> candidates (k_seg_label), k_ransac_draw, k_ransac_plane, k_ransac_count,
+//                                    k_ransac_best; the plane is applied to the pixel winners (k_seg_px)
+//   image scatter      :291-318   -> 64-bit atomicMin keys (issued by k_seg_scatter), k_seg_px (winner decode + its label);
+//                                    the range image is a plane of point indices
 //   JCP                :481-638   -> k_seg_dilate_tma (5x5 stencil on range-image tiles staged by TMA),
 //                                    queue compaction, k_jcp_pre, k_jcp_rows
 //   populateLabels     :640-669   -> k_seg_labels_out

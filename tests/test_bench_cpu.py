@@ -48,7 +48,7 @@ def test_stage_and_kernel_byte_models():
     assert bench.stage_of("jcp_rows") == "S2 segment" and bench.stage_of("take_obstacles") == "S3 cluster"
     assert bench.stage_of("hull_thin") == "S4 hulls" and bench.stage_of("dror_query") == "S1 dror"
     # the JCP pre-pass is charged with the distinct pixels its neighbourhoods touch, not 25 gathers per pixel
-    assert bench.algorithmic_bytes("jcp_pre", s) == 4 * 90 * 17 + 90 * 104
+    assert bench.algorithmic_bytes("jcp_pre", s) == 4 * 90 * 21 + 90 * 104  # index + point + code per distinct pixel
 
 
 def test_ring_walls_scene_is_organised():
