@@ -18,6 +18,7 @@
 // The azimuth wrap is the reference's literal one (index -1 -> num_azimuth - 1, num_azimuth -> 0
 // with num_azimuth = ceil(max_az / res) + 1), see DESIGN.md hazard H3.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -375,12 +376,12 @@ __device__ __forceinline__ void uf_publish(const Dev& d, std::size_t o, std::siz
 // Shared-memory union-find: a frame's forest (typically 10-17k voxels) lives in one CTA's shared
 // memory, so the pointer chasing of find() costs shared-memory instead of L2 latency; the CTA
 // streams the frame's edge rows (coalesced) and hooks lock-free with shared-memory CAS.
-__global__ void __launch_bounds__(kUfThreads) k_clu_union_sm(Dev d)
+__global__ void __launch_bounds__(kUfThreads) k_clu_union_sm(Dev d, std::uint32_t sm_max)
 {
     extern __shared__ std::uint32_t par[];
     const std::uint32_t f = blockIdx.x + d.f0;
     const std::uint32_t nv = d.n_vox[f];
-    if (nv == 0 || nv > kUfSmemVoxels)
+    if (nv == 0 || nv > sm_max)
     {
         return;
     }
@@ -433,11 +434,11 @@ __global__ void __launch_bounds__(kUfThreads) k_clu_union_sm(Dev d)
 
 // Global-memory path for frames with more occupied voxels than the shared-memory forest holds
 // (e.g. the 2M-point clouds): one thread per voxel walks its edge row.
-__global__ void __launch_bounds__(256) k_clu_union(Dev d)
+__global__ void __launch_bounds__(256) k_clu_union(Dev d, std::uint32_t sm_max)
 {
     const std::uint32_t f = blockIdx.y + d.f0;
     const std::uint32_t nvox = d.n_vox[f];
-    if (nvox <= kUfSmemVoxels)
+    if (nvox <= sm_max)
     {
         return;
     }
@@ -477,11 +478,11 @@ __global__ void __launch_bounds__(256) k_clu_union(Dev d)
     }
 }
 
-__global__ void __launch_bounds__(256) k_clu_flatten(Dev d)
+__global__ void __launch_bounds__(256) k_clu_flatten(Dev d, std::uint32_t sm_max)
 {
     const std::uint32_t f = blockIdx.y + d.f0;
     const std::uint32_t nvox = d.n_vox[f];
-    if (nvox <= kUfSmemVoxels)
+    if (nvox <= sm_max)
     {
         return;
     }
@@ -626,14 +627,22 @@ void launch_cluster(Ctx* c, std::uint32_t nf)
     mark(c, "clu_edges");
     cudaFuncSetAttribute(k_clu_union_sm, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          static_cast<int>(kUfSmemVoxels * sizeof(std::uint32_t)));
-    k_clu_union_sm<<<nf, kUfThreads, kUfSmemVoxels * sizeof(std::uint32_t), s>>>(d);
+    // One CTA per frame is the right shape for a batch that fills the GPU with frames. A launch of a few frames leaves
+    // the other SMs idle for the whole (latency-bound) walk, so it takes the global-memory form, which spreads a frame's
+    // voxels over the whole GPU: a single frame 0.105 -> 0.06 ms (chain 0.81 -> 0.76 ms), five 2M-point clouds 2.63 -> 2.44 ms; at 16
+    // frames both forms take the same time.
+    static const std::uint32_t few = std::getenv("LPL_UF_GLOBAL_MAX_FRAMES") != nullptr
+                                         ? static_cast<std::uint32_t>(std::atoi(std::getenv("LPL_UF_GLOBAL_MAX_FRAMES")))
+                                         : 8u;
+    const std::uint32_t sm_max = nf <= few ? 0u : kUfSmemVoxels;
+    k_clu_union_sm<<<nf, kUfThreads, kUfSmemVoxels * sizeof(std::uint32_t), s>>>(d, sm_max);
     mark(c, "clu_union_sm");
     // frames with more occupied voxels than the shared-memory forest holds take the global path
     // about one resident wave of CTAs in total: the kernels stride over a frame's voxels
     const dim3 gbig(std::max(1u, std::min<std::uint32_t>((d.cap + 255) / 256, (148u * 8u + nf - 1u) / nf)), nf);
-    k_clu_union<<<gbig, 256, 0, s>>>(d);
+    k_clu_union<<<gbig, 256, 0, s>>>(d, sm_max);
     mark(c, "clu_union");
-    k_clu_flatten<<<gbig, 256, 0, s>>>(d);
+    k_clu_flatten<<<gbig, 256, 0, s>>>(d, sm_max);
     mark(c, "clu_flatten");
     // d.lab (RECM labels of the segmenter) is free by now: it holds the recorded verdicts
     launch_compact_recorded(c, "clu_rank", nf, d.tiles, d.n_o, d.tile_cnt, d.n_clusters, d.lab,

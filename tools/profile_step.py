@@ -21,13 +21,23 @@ def main():
     ap.add_argument("--frames", type=int, default=64)
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--stages", type=int, default=lpl.STAGE_ALL)
+    ap.add_argument("--workload", default=None, help="synth128 | cloud2m | synth64 (bench.py shapes); default: the KITTI pack")
     a = ap.parse_args()
-    fr = F.load_pack(limit=a.frames) if F.have_pack() else [F.synth_scan(4000 + i)[0] for i in range(a.frames)]
-    ctx = lpl.Context(0, max_points=max(f.shape[0] for f in fr), max_frames=len(fr))
-    ctx.cluster_config(range_m=0.4, az_deg=1.0, el_deg=3.0, min_size=3)
-    nf = ctx.upload(fr)
+    if a.workload:
+        import bench
+
+        fr, _, _, opts = bench.load_frames(None, a.workload)
+        stages = lpl.STAGE_ALL & ~lpl.STAGE_RING if opts["stages"] in ("ringless", "ring_field") else lpl.STAGE_ALL
+        ctx = bench.make_ctx_factory(lpl, 0, max(f.shape[0] for f in fr), opts["image_height"])(len(fr))
+        nf = ctx.upload(fr, rings=opts["rings"])
+    else:
+        fr = F.load_pack(limit=a.frames) if F.have_pack() else [F.synth_scan(4000 + i)[0] for i in range(a.frames)]
+        stages = a.stages
+        ctx = lpl.Context(0, max_points=max(f.shape[0] for f in fr), max_frames=len(fr))
+        ctx.cluster_config(range_m=0.4, az_deg=1.0, el_deg=3.0, min_size=3)
+        nf = ctx.upload(fr)
     for _ in range(a.steps):
-        ctx.run(nf, a.stages)
+        ctx.run(nf, stages)
     ctx.sync(nf)
     print("launches", ctx.launch_count())
 
