@@ -100,6 +100,37 @@ def test_pcd_reader(tmp_path):
         assert got.shape == (123398, 4) and np.array_equal(got, read_pcd_xyzi(ref_file))
 
 
+def test_pcd_reader_rejects_crafted_headers(tmp_path):
+    """Headers whose field sizes / counts would send the x, y, z offsets outside the record (negative or huge SIZE /
+    COUNT of fields that are not even read), overflow the record length or the 32-bit point count are refused with a
+    status code - no read outside the staging buffer, no exception across the C ABI."""
+    import lidar_processing_v2_b200 as lpl
+
+    def pcd(fields, size, typ, count, points="4", data="binary", payload=b"\0" * 4096):
+        path = tmp_path / f"bad{len(list(tmp_path.iterdir()))}.pcd"
+        head = (f"# .PCD v0.7\nVERSION 0.7\nFIELDS {fields}\nSIZE {size}\nTYPE {typ}\nCOUNT {count}\n"
+                f"WIDTH {points}\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS {points}\nDATA {data}\n")
+        path.write_bytes(head.encode() + payload)
+        return str(path)
+
+    bad = [
+        pcd("x a y b z", "4 1000 4 -1000 4", "F F F F F", "1 1 1 1 1"),      # offsets cancel out: y would sit at byte 1004 of a 12-byte record
+        pcd("x y z pad", "4 4 4 4", "F F F F", "1 1 1 -3"),                  # negative count
+        pcd("x y z pad", "4 4 4 1", "F F F U", "1 1 1 100000000"),           # record length overflow
+        pcd("x y z", "4 4 4", "F F F", "1 1 1", points="99999999999"),       # more points than 32 bits hold
+        pcd("x y z", "8 4 4", "F F F", "1 1 1"),                             # double x: not what the node consumes
+        pcd("x y", "4 4", "F F", "1 1"),                                     # no z
+        pcd("x y z", "4 4", "F F F", "1 1 1"),                               # SIZE list shorter than FIELDS
+    ]
+    for path in bad:
+        with pytest.raises(lpl.LplError):
+            lpl.pcd_read(path)
+    # an ascii file whose rows are shorter than the header promises is a parse error, not an out-of-range read
+    short = pcd("x y z intensity", "4 4 4 4", "F F F F", "1 1 1 1", data="ascii", payload=b"1 2 3\n4 5\n6\n\n")
+    with pytest.raises(lpl.LplError):
+        lpl.pcd_read(short)
+
+
 def test_glibc_rand_replica_matches_libc():
     """lpl_pipeline_split_clouds colours clusters with the C library's rand() % 256 as the node does
     (processor.cpp:629-631); the replica of glibc's generator is checked against libc itself."""
