@@ -219,19 +219,34 @@ __global__ void __launch_bounds__(256)
         // k_dror_query writes the final verdict over it)
         d.noise[static_cast<std::size_t>(f) * d.cap + i] = unresolved ? 2 : 0;
     }
-    // warp-aggregated append
-    const std::uint32_t m = __ballot_sync(0xffffffffu, unresolved);
-    if (m != 0)
+    // CTA-aggregated append: one atomic per CTA on the frame's counter (per warp, an unorganised 2 M-point cloud - all of
+    // whose points are unresolved - queued 62k atomics on one address per frame: that, not the distance tests, was the
+    // whole cost of this pass there)
     {
-        std::uint32_t pos = 0;
+        __shared__ std::uint32_t s_wcnt[8], s_base;
+        const std::uint32_t m = __ballot_sync(0xffffffffu, unresolved);
+        const std::uint32_t w = threadIdx.x >> 5;
         if (lane_id() == 0)
         {
-            pos = atomicAdd(&d.n_unres[f], __popc(m));
+            s_wcnt[w] = __popc(m);
         }
-        pos = __shfl_sync(0xffffffffu, pos, 0);
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            std::uint32_t tot = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+            {
+                const std::uint32_t c = s_wcnt[k];
+                s_wcnt[k] = tot;
+                tot += c;
+            }
+            s_base = tot != 0u ? atomicAdd(&d.n_unres[f], tot) : 0u;
+        }
+        __syncthreads();
         if (unresolved)
         {
-            d.unres[static_cast<std::size_t>(f) * d.cap + pos + __popc(m & ((1u << lane_id()) - 1u))] = i;
+            d.unres[static_cast<std::size_t>(f) * d.cap + s_base + s_wcnt[w] + __popc(m & ((1u << lane_id()) - 1u))] = i;
         }
     }
     if (kWithRing)
