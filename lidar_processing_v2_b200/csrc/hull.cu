@@ -275,17 +275,23 @@ __device__ __forceinline__ std::uint32_t merge_path_warp(GetA A, std::uint32_t l
     return lo;
 }
 
-// merge pass p: runs of (kTile << p) elements, pairwise, one output tile per CTA
+constexpr std::uint32_t kMergeCtas = 64;
+
+// merge pass p: runs of (kTile << p) elements, pairwise, one output tile per CTA and trip
 __global__ void __launch_bounds__(kTileThreads) k_hull_merge(Dev d, std::uint32_t pass)
 {
     __shared__ uint4 s[kTile];
     __shared__ std::uint32_t s_split[2];
     const std::uint32_t f = blockIdx.y + d.f0;
     const std::uint32_t n = d.n_h[f];
-    const std::uint32_t out0 = blockIdx.x * kTile;
+    // at most kMergeCtas CTAs per frame stride over the output tiles: a 2 M-point capacity means 977 tiles and ten
+    // passes, nearly all of them empty
+    for (std::uint32_t tile = blockIdx.x;; tile += gridDim.x)
+    {
+    const std::uint32_t out0 = tile * kTile;
     if (out0 >= n || sort_passes(n) <= pass)
     {
-        return; // this frame was fully sorted by an earlier pass
+        return; // past the end, or this frame was fully sorted by an earlier pass
     }
     const std::size_t o = static_cast<std::size_t>(f) * d.cap;
     const uint4* src = ((pass & 1u) ? d.hsB : d.hsA) + o;
@@ -304,7 +310,7 @@ __global__ void __launch_bounds__(kTileThreads) k_hull_merge(Dev d, std::uint32_
         {
             dst[out0 + t] = src[out0 + t];
         }
-        return;
+        continue;
     }
     if (threadIdx.x < 64u)
     {
@@ -361,6 +367,8 @@ __global__ void __launch_bounds__(kTileThreads) k_hull_merge(Dev d, std::uint32_
         {
             dst[out0 + dg + k] = out[k];
         }
+    }
+    __syncthreads(); // s / s_split are rewritten by the next trip
     }
 }
 
@@ -1014,7 +1022,7 @@ void launch_hull_sort(Ctx* c, std::uint32_t nf)
     for (std::uint32_t p = 0; p < passes; ++p)
     {
         // frames whose obstacle cloud is already one sorted run leave at once
-        k_hull_merge<<<dim3(d.tiles, nf), kTileThreads, 0, s>>>(d, p);
+        k_hull_merge<<<dim3(std::min<std::uint32_t>(d.tiles, kMergeCtas), nf), kTileThreads, 0, s>>>(d, p);
         mark(c, "hull_merge");
     }
 }
