@@ -234,9 +234,9 @@ int lpl_pipeline_use_graph(lpl_ctx* ctx, int enable);
 /* Sub-batches: lpl_pipeline_run cuts a batch of >= 4 frames into `parts` (1..8) contiguous sub-batches whose chains
  * run on concurrent streams (parallel branches of the captured graph), so that the one-CTA-per-frame kernels of one
  * sub-batch (JCP row sweep, union-find, scans) overlap the per-point kernels of another. Frames are independent
- * (segmenter.cpp:73-85, clusterer.cpp:104-106), the results do not change. Default: environment LPL_SPLIT, else 2
- * (measured on the 154-frame batch: 1 -> 4.48 ms, 2 -> 4.19, 3 -> 4.17, 4 -> 4.19; starting the sub-batches one stage
- * apart instead of together: 4.36 and worse). */
+ * (segmenter.cpp:73-85, clusterer.cpp:104-106), the results do not change. Default: environment LPL_SPLIT, else 3
+ * (measured on the 154-frame batch: 1 -> 4.48 ms, 2 -> 4.19, 3 -> 4.17, 4 -> 4.19 when introduced, 2 -> 4.07, 3 -> 4.04,
+ * 4 -> 4.08 with the final kernels; starting the sub-batches one stage apart instead of together: 4.36 and worse). */
 int lpl_pipeline_use_split(lpl_ctx* ctx, uint32_t parts);
 /* Wait for the stream; fails if any kernel raised a capacity flag. */
 int lpl_pipeline_sync(lpl_ctx* ctx, uint32_t num_frames);

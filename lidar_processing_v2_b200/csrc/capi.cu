@@ -60,7 +60,7 @@ struct lpl_ctx
     };
     std::vector<Aux> aux;
     cudaEvent_t fork_ev = nullptr;
-    std::uint32_t split_parts = 2;
+    std::uint32_t split_parts = 3;
     std::vector<std::uint32_t> h_status;
 };
 
@@ -571,7 +571,7 @@ int lpl_create(lpl_ctx** out, int device, std::uint32_t max_points, std::uint32_
     if (const char* sp = std::getenv("LPL_SPLIT"))
     {
         const int v = std::atoi(sp);
-        ctx->split_parts = v >= 1 && v <= 8 ? static_cast<std::uint32_t>(v) : 2u;
+        ctx->split_parts = v >= 1 && v <= 8 ? static_cast<std::uint32_t>(v) : 3u;
     }
     lpl_segmenter_default_cfg(&ctx->seg_cfg);
     ctx->seg_cfg.image_height = H;
