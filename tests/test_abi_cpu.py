@@ -21,6 +21,19 @@ def test_library_exports_every_declared_symbol():
     assert sorted(EXPORTS) == declared
 
 
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/lpl_b200.h compiles as C99 with pedantic warnings as errors (no C++ types,
+    no CUDA or torch types in any signature), so any FFI of the reference's host language can bind it."""
+    import subprocess
+
+    src = tmp_path / "abi.c"
+    src.write_text('#include "lpl_b200.h"\nint main(void) { return sizeof(lpl_segmenter_cfg) > 0 ? 0 : 1; }\n')
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    res = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", inc, "-fsyntax-only", str(src)],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+
+
 def test_defaults_mirror_reference_structs():
     lib = lpl.load_library()
     s = lpl.SegmenterCfg()
